@@ -1,0 +1,192 @@
+#!/usr/bin/env python
+"""Multi-GPU correctness + bandwidth check of the NVLink data plane (run under torchrun):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29511 tests/dist_comm_check.py [--out gpurun_out/comm_N.json]
+
+Checks (every rank asserts; rank 0 prints one JSON line):
+  * symmetric heap bring-up (VMM + fd passing), multicast availability
+  * P2P pull / multimem push / multimem reduce correctness and GB/s
+  * K2 fedavg_round vs a closed-form expectation for every server optimizer / upload mode /
+    server placement, with unequal weights and with a non-reporting node
+  * K3 small_allreduce correctness + latency vs ncclAllReduce
+  * ResNet-50-sized (102 MB fp32) aggregation: device time (max over ranks) vs the NCCL
+    reduce + torch optimizer + broadcast baseline, and achieved bus GB/s vs the link roofline
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def timed(fn, iters=20, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    dist.barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / iters
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="")
+    ap.add_argument("--big", type=int, default=25_610_152, help="elements of the large aggregation test")
+    args = ap.parse_args()
+    rank, world, lr_ = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(lr_)
+    dev = torch.device("cuda", lr_)
+    dist.init_process_group("nccl", device_id=dev)
+    from vantage6_b200.ops import native, stream_ptr
+    from vantage6_b200.parallel.fedavg import FedAvgEngine, ServerOptConfig, SmallAggregator
+    from vantage6_b200.parallel.symm import SymmetricHeap
+
+    C = native()
+    res = {"world": world}
+    # ------------------------------------------------------------ heap + raw copies
+    heap = SymmetricHeap(rank, world, dev)
+    res["multicast_supported"] = heap.multicast
+    nbytes = 256 << 20
+    buf = heap.alloc(nbytes, multicast=True)
+    res["multicast_bound"] = bool(buf.mc_ptr)
+    x = buf.view(torch.float32)
+    x.fill_(float(rank + 1))
+    torch.cuda.synchronize()
+    dist.barrier()
+    dst = torch.empty_like(x)
+    peer = (rank + 1) % world
+    C.p2p_pull(buf.peer_ptrs[peer], dst.data_ptr(), nbytes, stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.all(dst == float(peer + 1)), "p2p pull mismatch"
+    if world > 1:
+        ms = timed(lambda: C.p2p_pull(buf.peer_ptrs[peer], dst.data_ptr(), nbytes, stream_ptr()))
+        res["p2p_pull_GBps"] = nbytes / ms / 1e6
+    if buf.mc_ptr:
+        C.mc_reduce(buf.mc_ptr, dst.data_ptr(), nbytes, stream_ptr())
+        torch.cuda.synchronize()
+        assert torch.all(dst == float(world * (world + 1) // 2)), "multimem.ld_reduce mismatch"
+        ms = timed(lambda: C.mc_reduce(buf.mc_ptr, dst.data_ptr(), nbytes, stream_ptr()))
+        res["mc_reduce_GBps_out"] = nbytes / ms / 1e6
+        dist.barrier()
+        src = torch.full_like(x, 7.0)
+        if rank == 0:
+            C.mc_push(src.data_ptr(), buf.mc_ptr, nbytes, stream_ptr())
+        torch.cuda.synchronize()
+        dist.barrier()
+        assert torch.all(x == 7.0), "multimem.st mismatch"
+        if rank == 0:
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(10):
+                C.mc_push(src.data_ptr(), buf.mc_ptr, nbytes, stream_ptr())
+            e.record()
+            torch.cuda.synchronize()
+            res["mc_push_GBps"] = nbytes / (s.elapsed_time(e) / 10) / 1e6
+        dist.barrier()
+    del x, dst
+    heap.close()
+
+    # ------------------------------------------------------------ K2 correctness
+    n = 1_000_003
+    checks = 0
+    for server_mode in ("sharded", "central"):
+        for upload in ("weights_f32", "delta_f32", "delta_bf16"):
+            for opt in ("fedavg", "fedavgm", "fedadam"):
+                for mc in ("auto", False):
+                    e1 = FedAvgEngine(n, rank, world, dev, data_plane="native", server_mode=server_mode,
+                                      server_opt=ServerOptConfig(opt, 0.5), upload=upload, multicast=mc)
+                    e2 = FedAvgEngine(n, rank, world, dev, data_plane="collective", server_mode=server_mode,
+                                      server_opt=ServerOptConfig(opt, 0.5), upload=upload)
+                    g = torch.Generator(device=dev).manual_seed(17)
+                    w0 = torch.randn(e1.n, device=dev, generator=g)
+                    for e in (e1, e2):
+                        e.w.copy_(w0 if rank == 0 else torch.zeros_like(w0))
+                        e.initialize_global()
+                    torch.cuda.synchronize()
+                    torch.testing.assert_close(e1.w, w0)
+                    for rnd, weights in enumerate([[float(r + 1) for r in range(world)], 4.0,
+                                                   [0.0 if (r == world - 1 and world > 1) else 2.0 for r in range(world)]]):
+                        gl = torch.Generator(device=dev).manual_seed(1000 * rnd + rank)
+                        step = torch.randn(e1.n, device=dev, generator=gl) * 0.1
+                        for e in (e1, e2):
+                            if upload == "weights_f32":
+                                e.w.add_(step)
+                            else:
+                                e.upload.copy_(step.to(e.upload.dtype))
+                            e.aggregate(weights)
+                        torch.cuda.synchronize()
+                        tol = dict(rtol=3e-2, atol=3e-3) if upload == "delta_bf16" else dict(rtol=1e-4, atol=1e-5)
+                        torch.testing.assert_close(e1.w, e2.w, **tol)
+                        checks += 1
+                    assert e1.poll_status() == 0
+                    dist.barrier()
+                    e1.close()
+    res["k2_checks_passed"] = checks
+
+    # ------------------------------------------------------------ K3
+    agg = SmallAggregator(1024, rank, world, dev)
+    for it in range(3):
+        v = torch.full((1024,), float(rank + it), device=dev)
+        agg.slot().copy_(v)
+        out = agg.allreduce([float(r + 1) for r in range(world)])
+        torch.cuda.synchronize()
+        tot = sum(r + 1 for r in range(world))
+        exp = sum((r + 1) * (r + it) for r in range(world)) / tot
+        assert torch.allclose(out, torch.full_like(out, exp), rtol=1e-5), (out[:4], exp)
+    res["k3_us"] = 1e3 * timed(lambda: agg.allreduce(1.0), iters=200, warm=20)
+    small = torch.zeros(1024, device=dev)
+    res["nccl_allreduce_4KB_us"] = 1e3 * timed(lambda: dist.all_reduce(small), iters=200, warm=20)
+    agg.close()
+
+    # ------------------------------------------------------------ large aggregation timing
+    for server_mode in ("sharded", "central"):
+        for mc in ("auto", False):
+            eng = FedAvgEngine(args.big, rank, world, dev, data_plane="native", server_mode=server_mode, multicast=mc)
+            eng.w.normal_()
+            eng.initialize_global()
+            ms = timed(lambda: eng.aggregate(1.0), iters=10, warm=3)
+            key = f"k2_{server_mode}_{'mc' if eng.use_multicast else 'p2p'}"
+            res[key + "_ms"] = ms
+            res[key + "_busGBps"] = (2 * eng.n * 4 * (world - 1) / world) / ms / 1e6 if world > 1 else eng.n * 12 / ms / 1e6
+            assert eng.poll_status() == 0
+            eng.close()
+            if not heap.multicast:
+                break
+    base = FedAvgEngine(args.big, rank, world, dev, data_plane="collective", server_mode="central")
+    base.w.normal_()
+    base.initialize_global()
+    res["nccl_central_ms"] = timed(lambda: base.aggregate(1.0), iters=10, warm=3)
+    base2 = FedAvgEngine(args.big, rank, world, dev, data_plane="collective", server_mode="sharded")
+    base2.w.normal_()
+    base2.initialize_global()
+    res["nccl_allreduce_based_ms"] = timed(lambda: base2.aggregate(1.0), iters=10, warm=3)
+    flat = torch.randn(args.big, device=dev)
+    res["nccl_pure_allreduce_ms"] = timed(lambda: dist.all_reduce(flat), iters=10, warm=3)
+    res["payload_MB"] = args.big * 4 / 1e6
+    if rank == 0:
+        line = json.dumps(res)
+        print(line, flush=True)
+        if args.out:
+            os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+            with open(args.out, "w") as f:
+                f.write(line + "\n")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

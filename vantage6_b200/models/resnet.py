@@ -1,0 +1,107 @@
+"""ResNet-50 (BASELINE config 2: "ResNet-50 FedAvg, 8 GPU-nodes, 1 local epoch/round, synthetic
+ImageNet-shape").  Standard bottleneck architecture (v1.5: stride on the 3x3), 25.6 M
+parameters = 102 MB fp32 -- the payload of the broadcast / reduction rooflines in BASELINE.md.
+
+Convolutions and BatchNorm run on cuDNN (library code); what is hand-written for this model
+is everything the north star names for it: the fused flat SGD step (K7), the FedAvg
+reduce + server optimizer + broadcast kernel (K2) and the CUDA-graph captured local step.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes: int, planes: int, stride: int = 1, downsample: nn.Module | None = None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+
+    def forward(self, x):
+        idt = x
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.relu(self.bn2(self.conv2(out)))
+        out = self.bn3(self.conv3(out))
+        if self.downsample is not None:
+            idt = self.downsample(x)
+        return self.relu(out + idt)
+
+
+class ResNet(nn.Module):
+    def __init__(self, layers=(3, 4, 6, 3), num_classes: int = 1000, width: int = 64):
+        super().__init__()
+        self.inplanes = width
+        self.conv1 = nn.Conv2d(3, width, 7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(width)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
+        self.layer1 = self._make_layer(width, layers[0])
+        self.layer2 = self._make_layer(width * 2, layers[1], stride=2)
+        self.layer3 = self._make_layer(width * 4, layers[2], stride=2)
+        self.layer4 = self._make_layer(width * 8, layers[3], stride=2)
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+        self.fc = nn.Linear(width * 8 * 4, num_classes)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+        for m in self.modules():
+            if isinstance(m, Bottleneck):
+                nn.init.zeros_(m.bn3.weight)       # zero-init last BN of each residual branch
+
+    def _make_layer(self, planes: int, blocks: int, stride: int = 1) -> nn.Sequential:
+        downsample = None
+        if stride != 1 or self.inplanes != planes * 4:
+            downsample = nn.Sequential(nn.Conv2d(self.inplanes, planes * 4, 1, stride=stride, bias=False),
+                                       nn.BatchNorm2d(planes * 4))
+        layers = [Bottleneck(self.inplanes, planes, stride, downsample)]
+        self.inplanes = planes * 4
+        layers += [Bottleneck(self.inplanes, planes) for _ in range(1, blocks)]
+        return nn.Sequential(*layers)
+
+    def forward(self, x):
+        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        return self.fc(torch.flatten(self.avgpool(x), 1))
+
+
+def resnet50(num_classes: int = 1000) -> ResNet:
+    return ResNet((3, 4, 6, 3), num_classes)
+
+
+def resnet_tiny(num_classes: int = 10) -> ResNet:
+    """Same code path at toy size (smoke tests, CPU tests)."""
+    return ResNet((1, 1, 1, 1), num_classes, width=8)
+
+
+_MEAN = (0.485 * 255, 0.456 * 255, 0.406 * 255)
+_STD = (0.229 * 255, 0.224 * 255, 0.225 * 255)
+_NORM_CACHE: dict = {}
+
+
+def imagenet_forward_loss(model: nn.Module, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """uint8 NCHW images -> normalised channels_last -> logits -> cross-entropy.
+
+    The normalisation runs on the GPU inside the captured step so the host only ever ships the
+    raw uint8 batch (9.6 MB for 64x3x224x224) over PCIe.
+    """
+    if x.dtype == torch.uint8:
+        key = str(x.device)
+        if key not in _NORM_CACHE:      # created on the eager warm-up pass, never during graph capture
+            _NORM_CACHE[key] = (torch.tensor(_MEAN, device=x.device, dtype=torch.float32).view(1, 3, 1, 1),
+                                1.0 / torch.tensor(_STD, device=x.device, dtype=torch.float32).view(1, 3, 1, 1))
+        mean, inv_std = _NORM_CACHE[key]
+        x = (x.float() - mean) * inv_std
+    x = x.contiguous(memory_format=torch.channels_last)
+    return nn.functional.cross_entropy(model(x).float(), y)

@@ -1,0 +1,120 @@
+// C ABI shared by the CUDA translation units and the pybind11 module (module.cpp).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#ifndef V6_MAX_PEERS
+#define V6_MAX_PEERS 8
+#endif
+
+struct PeerTable { void* p[V6_MAX_PEERS]; };
+
+// pad word layout (uint32 words inside each rank's signal pad, one 128 B line per group)
+#define PAD_UPLOAD   0      // [0,8)   : rank p's weights for epoch e are final
+#define PAD_BCAST    32     // [32,40) : reducer q has pushed its slice for epoch e
+#define PAD_BARRIER  64     // [64,72) : generic barrier
+#define PAD_SMALL    96     // [96,104): small_allreduce arrivals
+#define PAD_ABORT    128    // host/any rank sets != 0 to abort all waits
+#define PAD_STATUS   129    // kernel writes 1 here (own pad) when a wait timed out
+
+struct FedAvgParams {
+    PeerTable upload;        // contribution buffer of every rank (peer VAs in my address space)
+    PeerTable param_out;     // fp32 parameter buffer of every rank (push target)
+    PeerTable shadow_out;    // optional bf16 shadow parameter buffer of every rank (or null)
+    PeerTable pads;          // signal pad of every rank
+    const void* upload_mc;   // multicast VA over all upload buffers (null -> P2P loads)
+    void* param_mc;          // multicast VA over all param buffers (null -> P2P stores)
+    void* shadow_mc;         // multicast VA over all shadow buffers (null -> P2P stores)
+    float* w_global;         // fp32 master copy of my slice owner (full-size buffer, local)
+    float* opt_m;            // server momentum / Adam m (local, full-size)
+    float* opt_v;            // Adam v
+    float weight[V6_MAX_PEERS];   // n_i of each rank (0 => not participating)
+    long long lo, hi;        // my element slice [lo, hi) -- multiples of 8
+    int rank, world;
+    int n_reducers;          // ranks [0, n_reducers) own a slice (1 = central server on GPU 0)
+    uint32_t epoch;
+    int upload_is_delta;     // 1: upload holds n_i*(w_i - w_g); 0: upload holds w_i (unscaled)
+    int upload_prescaled;    // 1: contributions already multiplied by n_i (needed for multicast)
+    int server_opt;          // 0 FedAvg (w += lr*d), 1 FedAvgM, 2 FedAdam
+    float server_lr, beta1, beta2, eps, bias1, bias2;
+    float inv_total;         // 1 / sum_i n_i over participants
+    long long timeout_cycles;
+    unsigned int* cta_counter;   // local scratch, zeroed by host once; self-resetting
+};
+
+struct SmallParams {
+    PeerTable slots;      // payload slot of every rank (peer VAs), for this epoch's parity
+    PeerTable pads;
+    float weight[V6_MAX_PEERS];
+    float* out;           // local result, n floats
+    int n;                // floats, multiple of 4
+    int rank, world;
+    uint32_t epoch;
+    float inv_total;
+    long long timeout_cycles;
+};
+
+struct OptimParams {
+    float* w;              // fp32 master weights (flat)
+    const float* g;        // fp32 gradients (flat)
+    float* m;              // momentum / Adam m
+    float* v;              // Adam v (null for SGD)
+    float* w_ref;          // (optional) global model received this round
+    void* upload;          // (optional) contribution buffer (fp32 or bf16)
+    void* shadow;           // (optional) bf16 copy of w
+    const float* grad_scale_ptr;   // (optional) device scalar multiplied into g (loss-scale / clip)
+    long long n;           // elements, multiple of 4
+    float lr, momentum, dampening, weight_decay, beta1, beta2, eps, bias1, bias2;
+    float contrib_scale;   // n_i
+    int nesterov;
+    int save_ref;          // 1: w_ref <- w(before step)
+    int publish;           // 0 none, 1 delta fp32, 2 delta bf16, 3 weights fp32 (n_i * w_new)
+    int first_momentum_step;   // torch semantics: buf = g on the very first step
+};
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+int v6_fedavg_round(const FedAvgParams* hp, int upload_dtype, int grid, cudaStream_t stream);
+int v6_symm_barrier(const PeerTable* pads, int rank, int world, uint32_t epoch, long long timeout_cycles, cudaStream_t stream);
+int v6_small_allreduce(const SmallParams* hp, cudaStream_t stream);
+int v6_p2p_pull(const void* src_peer, void* dst_local, long long nbytes, cudaStream_t s);
+int v6_mc_push(const void* src_local, void* mc_dst, long long nbytes, cudaStream_t s);
+int v6_mc_reduce(const void* mc_src, void* dst_local, long long nbytes, cudaStream_t s);
+int v6_flat_sgd(const OptimParams* hp, cudaStream_t s);
+int v6_flat_adamw(const OptimParams* hp, cudaStream_t s);
+int v6_delta_publish(const float* w, const float* ref, void* upload, long long n, float scale, int bf16_out, cudaStream_t s);
+int v6_cast_bf16(const float* src, void* dst, long long n, cudaStream_t s);
+int v6_clip_coef(const float* g, long long n, float max_norm, float* sumsq_scratch, float* coef, cudaStream_t s);
+int v6_layernorm_fwd(const void* x, const void* residual, const float* gamma, const float* beta, void* y, void* res_out,
+                     float* mean, float* rstd, int rows, int cols, float eps, int bf16, cudaStream_t s);
+int v6_rmsnorm_fwd(const void* x, const void* residual, const float* gamma, void* y, void* res_out, float* rstd, int rows,
+                   int cols, float eps, int bf16, cudaStream_t s);
+int v6_layernorm_bwd(const void* dy, const void* x_in, const void* dres, const float* gamma, const float* mean,
+                     const float* rstd, void* dx, float* dgamma, float* dbeta, float* scratch, int scratch_parts, int rows,
+                     int cols, int accumulate, int bf16, cudaStream_t s);
+int v6_rmsnorm_bwd(const void* dy, const void* x_in, const void* dres, const float* gamma, const float* rstd, void* dx,
+                   float* dgamma, float* scratch, int scratch_parts, int rows, int cols, int accumulate, int bf16,
+                   cudaStream_t s);
+int v6_rope(void* q, void* k, const float* cos_t, const float* sin_t, const int* pos_ids, int B, int S, int Hq, int Hkv,
+            int D, int inverse, cudaStream_t st);
+int v6_glm_logistic_grad(const void* X, const float* y, const float* w, float* part, int max_parts, float* out, int rows,
+                         int F, int bf16, cudaStream_t s);
+int v6_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, int lda, int ldb, int ldc,
+                 int act, cudaStream_t stream);
+int v6_bcast_gemm_bf16(const void* A, void* B_local, const void* B_server_peer, void* C, const float* bias, int M, int N,
+                       int K, int lda, int ldb, int ldc, int act, uint32_t* ready_flags, uint32_t epoch, cudaStream_t stream);
+int v6_gemm_smem_bytes();
+// symm.cpp
+const char* v6_symm_last_error();
+int v6_driver_available();
+int v6_symm_init(int rank, int world, int device, const char* dir, int timeout_s);
+int v6_symm_multicast_supported(int gid);
+int v6_symm_alloc(int gid, size_t size, int want_multicast, uint64_t* peer_ptrs, uint64_t* mc_ptr, size_t* padded);
+int v6_symm_barrier_host(int gid);
+int v6_symm_free(int gid, int aid);
+int v6_symm_finalize(int gid);
+int v6_make_tmap_2d_bf16(void* out, uint64_t gptr, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                         uint32_t box_rows, uint32_t box_cols, int swizzle128);
+#ifdef __cplusplus
+}
+#endif

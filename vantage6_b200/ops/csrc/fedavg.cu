@@ -1,0 +1,302 @@
+// K2 / K3 of SURVEY.md section 2.6: the federated aggregation hot path.
+//
+//   fedavg_round  : ONE kernel per round per rank that (1) signals "my local weights are
+//                   final" to every reducer, (2) waits for the contributors, (3) pulls the
+//                   contributions over NVLink (P2P loads from peer-mapped symmetric memory, or
+//                   a single in-switch `multimem.ld_reduce`), forms the weighted FedAvg mean,
+//                   (4) applies the server optimizer (FedAvg / FedAvgM / FedAdam) in registers
+//                   on the fp32 master copy, (5) pushes the new global model straight into
+//                   every node's parameter buffer (P2P stores or one `multimem.st`), and
+//                   (6) signals / waits "broadcast complete".  No NCCL call, no separate
+//                   broadcast, reduce, scale, cast or optimizer kernels.
+//   small_allreduce: K3, latency-bound one-shot weighted all-reduce for <= 64 KB payloads
+//                   (GLM coefficients, the 1k-parameter vector): single CTA, flag barrier,
+//                   P2P loads of every peer slot, no grid sync.
+//
+// The reference transports these payloads as REST blobs through a SQL database
+// (reference: vantage6/cli/server.py:223-228); here they never leave HBM.
+#include "common.cuh"
+#include "api.h"
+
+
+
+
+template <typename T> struct Vec;            // 16 B vector of T
+template <> struct Vec<float> { static constexpr int N = 4; };
+template <> struct Vec<__nv_bfloat16> { static constexpr int N = 8; };
+
+V6_DEVINL void load_contrib(const float* base, long long e, float (&v)[4]) {
+    float4 t = ld_sys_f4(reinterpret_cast<const float4*>(base + e));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+V6_DEVINL void load_contrib(const __nv_bfloat16* base, long long e, float (&v)[8]) {
+    uint4 t = ld_sys_u4(reinterpret_cast<const uint4*>(base + e));
+    float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+V6_DEVINL void load_contrib_mc(const float* mc, long long e, float (&v)[4]) {
+    float4 t = multimem_ld_reduce_add_f4(reinterpret_cast<const float4*>(mc + e));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+V6_DEVINL void load_contrib_mc(const __nv_bfloat16* mc, long long e, float (&v)[8]) {
+    uint4 t = multimem_ld_reduce_add_bf16x8(reinterpret_cast<const uint4*>(mc + e));
+    float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+
+template <typename UpT>
+__global__ void __launch_bounds__(512, 1)
+fedavg_round_kernel(const FedAvgParams P) {
+    constexpr int VN = Vec<UpT>::N;
+    __shared__ int s_ok;
+    const bool reducer = P.rank < P.n_reducers && P.hi > P.lo;
+    uint32_t* my_pad = reinterpret_cast<uint32_t*>(P.pads.p[P.rank]);
+
+    // (1) tell every reducer that my contribution for this epoch is final. Stream order
+    // guarantees the producing kernels completed; the release makes it visible system-wide.
+    if (blockIdx.x == 0 && threadIdx.x < P.n_reducers) {
+        uint32_t* pad = reinterpret_cast<uint32_t*>(P.pads.p[threadIdx.x]);
+        fence_acq_rel_sys();
+        st_release_sys_u32(pad + PAD_UPLOAD + P.rank, P.epoch);
+    }
+
+    if (reducer) {
+        // (2) wait for every participating contributor
+        if (threadIdx.x == 0) s_ok = 1;
+        __syncthreads();
+        if (threadIdx.x < P.world && P.weight[threadIdx.x] > 0.f) {
+            if (!spin_wait_ge(my_pad + PAD_UPLOAD + threadIdx.x, P.epoch, P.timeout_cycles, my_pad + PAD_ABORT))
+                atomicExch(&s_ok, 0);
+        }
+        __syncthreads();
+        if (!s_ok) { if (threadIdx.x == 0) my_pad[PAD_STATUS] = 1; }
+        else {
+            // (3)-(5) reduce -> optimizer -> push
+            const long long nvec = (P.hi - P.lo) / VN;
+            for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+                 i += (long long)gridDim.x * blockDim.x) {
+                const long long e = P.lo + i * VN;
+                float acc[VN];
+#pragma unroll
+                for (int k = 0; k < VN; ++k) acc[k] = 0.f;
+                if (P.upload_mc) {
+                    load_contrib_mc(reinterpret_cast<const UpT*>(P.upload_mc), e, acc);
+                } else {
+                    float v[V6_MAX_PEERS][VN];
+#pragma unroll
+                    for (int p = 0; p < V6_MAX_PEERS; ++p)      // issue all peer loads first (MLP)
+                        if (p < P.world && P.weight[p] > 0.f)
+                            load_contrib(reinterpret_cast<const UpT*>(P.upload.p[p]), e, v[p]);
+#pragma unroll
+                    for (int p = 0; p < V6_MAX_PEERS; ++p)
+                        if (p < P.world && P.weight[p] > 0.f) {
+                            const float s = P.upload_prescaled ? 1.f : P.weight[p];
+#pragma unroll
+                            for (int k = 0; k < VN; ++k) acc[k] = fmaf(s, v[p][k], acc[k]);
+                        }
+                }
+                // VN elements of master state (fp32): 1 or 2 float4
+#pragma unroll
+                for (int h = 0; h < VN / 4; ++h) {
+                    const long long eh = e + 4 * h;
+                    float4 wg = *reinterpret_cast<const float4*>(P.w_global + eh);
+                    float w[4] = {wg.x, wg.y, wg.z, wg.w};
+                    float d[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float mean = acc[4 * h + k] * P.inv_total;
+                        d[k] = P.upload_is_delta ? mean : (mean - w[k]);   // pseudo-gradient (ascent dir)
+                    }
+                    if (P.server_opt == 1) {
+                        float4 m4 = *reinterpret_cast<const float4*>(P.opt_m + eh);
+                        float m[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { m[k] = fmaf(P.beta1, m[k], d[k]); w[k] = fmaf(P.server_lr, m[k], w[k]); }
+                        *reinterpret_cast<float4*>(P.opt_m + eh) = make_float4(m[0], m[1], m[2], m[3]);
+                    } else if (P.server_opt == 2) {
+                        float4 m4 = *reinterpret_cast<const float4*>(P.opt_m + eh);
+                        float4 v4 = *reinterpret_cast<const float4*>(P.opt_v + eh);
+                        float m[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            m[k] = fmaf(P.beta1, m[k], (1.f - P.beta1) * d[k]);
+                            vv[k] = fmaf(P.beta2, vv[k], (1.f - P.beta2) * d[k] * d[k]);
+                            const float mh = m[k] * P.bias1, vh = vv[k] * P.bias2;
+                            w[k] = fmaf(P.server_lr, mh / (sqrtf(vh) + P.eps), w[k]);
+                        }
+                        *reinterpret_cast<float4*>(P.opt_m + eh) = make_float4(m[0], m[1], m[2], m[3]);
+                        *reinterpret_cast<float4*>(P.opt_v + eh) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) w[k] = fmaf(P.server_lr, d[k], w[k]);
+                    }
+                    const float4 wn = make_float4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<float4*>(P.w_global + eh) = wn;
+                    // (5) broadcast fused into the epilogue
+                    if (P.param_mc) {
+                        multimem_st_f4(reinterpret_cast<float4*>(reinterpret_cast<float*>(P.param_mc) + eh), wn);
+                    } else {
+#pragma unroll
+                        for (int p = 0; p < V6_MAX_PEERS; ++p)
+                            if (p < P.world)
+                                st_f4(reinterpret_cast<float4*>(reinterpret_cast<float*>(P.param_out.p[p]) + eh), wn);
+                    }
+                    acc[4 * h + 0] = w[0]; acc[4 * h + 1] = w[1]; acc[4 * h + 2] = w[2]; acc[4 * h + 3] = w[3];
+                }
+                if (P.shadow_out.p[0] != nullptr || P.shadow_mc != nullptr) {
+                    // bf16 shadow copy of the new global for bf16 compute paths (VN elements)
+                    if constexpr (VN == 8) {
+                        uint4 s = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                             pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+                        if (P.shadow_mc) multimem_st_u4(reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.shadow_mc) + e), s);
+                        else {
+#pragma unroll
+                            for (int p = 0; p < V6_MAX_PEERS; ++p)
+                                if (p < P.world)
+                                    st_u4(reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.shadow_out.p[p]) + e), s);
+                        }
+                    } else {
+                        uint2 s = make_uint2(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]));
+#pragma unroll
+                        for (int p = 0; p < V6_MAX_PEERS; ++p)
+                            if (p < P.world)
+                                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.shadow_out.p[p]) + e) = s;
+                    }
+                }
+            }
+        }
+    }
+
+    // (6) completion: last CTA signals "my slice is pushed" and waits for all other reducers
+    __shared__ unsigned int s_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(P.cta_counter, 1u);
+        s_last = (t == gridDim.x - 1) ? 1u : 0u;
+        if (s_last) *P.cta_counter = 0u;        // self-reset for the next launch
+    }
+    __syncthreads();
+    if (s_last) {
+        if (P.rank < P.n_reducers && threadIdx.x < P.world) {
+            uint32_t* pad = reinterpret_cast<uint32_t*>(P.pads.p[threadIdx.x]);
+            fence_acq_rel_sys();
+            st_release_sys_u32(pad + PAD_BCAST + P.rank, P.epoch);
+        }
+        if (threadIdx.x < P.n_reducers) {
+            if (!spin_wait_ge(my_pad + PAD_BCAST + threadIdx.x, P.epoch, P.timeout_cycles, my_pad + PAD_ABORT))
+                my_pad[PAD_STATUS] = 1;
+        }
+    }
+}
+
+extern "C" int v6_fedavg_round(const FedAvgParams* hp, int upload_dtype /*0 f32, 1 bf16*/, int grid,
+                               cudaStream_t stream) {
+    FedAvgParams P = *hp;
+    if (grid <= 0) grid = 148;
+    if (upload_dtype == 0) fedavg_round_kernel<float><<<grid, 512, 0, stream>>>(P);
+    else fedavg_round_kernel<__nv_bfloat16><<<grid, 512, 0, stream>>>(P);
+    V6_CHECK_LAUNCH();
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------
+// Cross-GPU barrier kernel (bring-up, tests, and round boundaries of the NCCL-free path)
+// ----------------------------------------------------------------------------------------
+__global__ void symm_barrier_kernel(PeerTable pads, int rank, int world, uint32_t epoch,
+                                    long long timeout_cycles) {
+    uint32_t* my_pad = reinterpret_cast<uint32_t*>(pads.p[rank]);
+    if (threadIdx.x < world) {
+        uint32_t* pad = reinterpret_cast<uint32_t*>(pads.p[threadIdx.x]);
+        fence_acq_rel_sys();
+        st_release_sys_u32(pad + PAD_BARRIER + rank, epoch);
+        if (!spin_wait_ge(my_pad + PAD_BARRIER + threadIdx.x, epoch, timeout_cycles, my_pad + PAD_ABORT))
+            my_pad[PAD_STATUS] = 1;
+    }
+}
+extern "C" int v6_symm_barrier(const PeerTable* pads, int rank, int world, uint32_t epoch,
+                               long long timeout_cycles, cudaStream_t stream) {
+    symm_barrier_kernel<<<1, 32, 0, stream>>>(*pads, rank, world, epoch, timeout_cycles);
+    V6_CHECK_LAUNCH();
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------
+// K3: small-message one-shot weighted all-reduce (+ optional server optimizer step).
+//   every rank: slot[rank] holds its payload (n floats, n*4 <= 64 KB) in symmetric memory.
+//   out[e] = sum_p weight[p] * slot_p[e] * inv_total       (written locally on every rank)
+// Single CTA: signal -> wait -> P2P loads from all peers -> reduce -> local store.
+// Double-buffered by epoch parity on the host side, so no trailing barrier is needed.
+// ----------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(1024, 1) small_allreduce_kernel(const SmallParams P) {
+    __shared__ int s_ok;
+    uint32_t* my_pad = reinterpret_cast<uint32_t*>(P.pads.p[P.rank]);
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    if (threadIdx.x < P.world) {
+        uint32_t* pad = reinterpret_cast<uint32_t*>(P.pads.p[threadIdx.x]);
+        fence_acq_rel_sys();
+        st_release_sys_u32(pad + PAD_SMALL + P.rank, P.epoch);
+        if (P.weight[threadIdx.x] > 0.f &&
+            !spin_wait_ge(my_pad + PAD_SMALL + threadIdx.x, P.epoch, P.timeout_cycles, my_pad + PAD_ABORT))
+            atomicExch(&s_ok, 0);
+    }
+    __syncthreads();
+    if (!s_ok) { if (threadIdx.x == 0) my_pad[PAD_STATUS] = 1; return; }
+    for (int i = threadIdx.x; i < P.n / 4; i += blockDim.x) {
+        float4 v[V6_MAX_PEERS];
+#pragma unroll
+        for (int p = 0; p < V6_MAX_PEERS; ++p)
+            if (p < P.world && P.weight[p] > 0.f)
+                v[p] = ld_sys_f4(reinterpret_cast<const float4*>(P.slots.p[p]) + i);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < V6_MAX_PEERS; ++p)
+            if (p < P.world && P.weight[p] > 0.f) {
+                a.x = fmaf(P.weight[p], v[p].x, a.x); a.y = fmaf(P.weight[p], v[p].y, a.y);
+                a.z = fmaf(P.weight[p], v[p].z, a.z); a.w = fmaf(P.weight[p], v[p].w, a.w);
+            }
+        a.x *= P.inv_total; a.y *= P.inv_total; a.z *= P.inv_total; a.w *= P.inv_total;
+        reinterpret_cast<float4*>(P.out)[i] = a;
+    }
+}
+extern "C" int v6_small_allreduce(const SmallParams* hp, cudaStream_t stream) {
+    small_allreduce_kernel<<<1, 1024, 0, stream>>>(*hp);
+    V6_CHECK_LAUNCH();
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------
+// Plain NVLink copy kernels used for bandwidth bring-up ("bus GB/s vs 900"):
+//   pull: dst_local[i] = src_peer[i];   push_mc: multimem.st of a local buffer to all peers.
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512, 2) p2p_pull_kernel(const float4* __restrict__ src, float4* __restrict__ dst, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x * 4) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { long long j = i + (long long)u * gridDim.x * blockDim.x; if (j < n4) v[u] = ld_sys_f4(src + j); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { long long j = i + (long long)u * gridDim.x * blockDim.x; if (j < n4) dst[j] = v[u]; }
+    }
+}
+__global__ void __launch_bounds__(512, 2) mc_push_kernel(const float4* __restrict__ src, float4* mc_dst, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+        multimem_st_f4(mc_dst + i, src[i]);
+}
+__global__ void __launch_bounds__(512, 2) mc_reduce_kernel(const float4* mc_src, float4* __restrict__ dst, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = multimem_ld_reduce_add_f4(mc_src + i);
+}
+extern "C" int v6_p2p_pull(const void* src_peer, void* dst_local, long long nbytes, cudaStream_t s) {
+    p2p_pull_kernel<<<148 * 2, 512, 0, s>>>((const float4*)src_peer, (float4*)dst_local, nbytes / 16);
+    V6_CHECK_LAUNCH(); return 0;
+}
+extern "C" int v6_mc_push(const void* src_local, void* mc_dst, long long nbytes, cudaStream_t s) {
+    mc_push_kernel<<<148 * 2, 512, 0, s>>>((const float4*)src_local, (float4*)mc_dst, nbytes / 16);
+    V6_CHECK_LAUNCH(); return 0;
+}
+extern "C" int v6_mc_reduce(const void* mc_src, void* dst_local, long long nbytes, cudaStream_t s) {
+    mc_reduce_kernel<<<148 * 2, 512, 0, s>>>((const float4*)mc_src, (float4*)dst_local, nbytes / 16);
+    V6_CHECK_LAUNCH(); return 0;
+}

@@ -1,0 +1,279 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a, hand-written (no CUTLASS):
+//
+//     C[M,N] = act( A[M,K] . B[N,K]^T + bias[N] )        bf16 in, fp32 accumulate in TMEM
+//
+// i.e. y = x @ W^T exactly as nn.Linear stores W.  Two entry points share the kernel:
+//   * v6_gemm_bf16        : plain fused linear (bias + optional GELU epilogue)
+//   * v6_bcast_gemm_bf16  : K1 of SURVEY.md 2.6 -- "global-model broadcast fused with the first
+//     forward GEMM that consumes it": the B operand (weights) is fetched by TMA straight from
+//     the SERVER GPU's copy through a peer-mapped VA over NVLink; the m_blk==0 tile of every
+//     weight column-block pulls the tile, feeds tcgen05.mma from shared memory AND writes the
+//     tile back to the local weight buffer with a TMA store (so the weights are resident for
+//     the other row-blocks, the backward pass and later steps); other row-blocks wait on a
+//     per-(n_blk,k_blk) ready flag and read the local copy.  NVLink traffic = 1x weights and
+//     the transfer overlaps the MMA tile by tile; no NCCL broadcast, no separate copy kernel.
+//
+// Structure (persistent, warp-specialised, one CTA per SM, 256 threads):
+//   warp 0 : TMA producer (one elected lane)        smem ring: kStages x (A 128x64 | B 256x64)
+//   warp 1 : MMA issuer  (one elected lane)         UMMA 128x256x16, kind::f16, cta_group::1
+//   warp 2 : TMEM allocator (512 columns = 2 accumulator stages of 128x256 fp32)
+//   warp 3 : K1 write-back warp (TMA store of pulled weight tiles + ready flags)
+//   warps 4-7 : epilogue (tcgen05.ld 32x32b.x32 -> bias/act -> bf16 -> global)
+// Pipelines: full/empty mbarriers per smem stage; tmem_full/tmem_empty per accumulator stage,
+// so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+#include "common.cuh"
+#include "api.h"
+
+namespace gemm {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B atom
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;
+constexpr int kTmemCols = 512;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;      // 16 KB
+constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;      // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // 48 KB
+constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kThreads = 256;
+
+struct Params {
+    int M, N, K;
+    __nv_bfloat16* C;          // [M, ldc]
+    int ldc;
+    const float* bias;         // [N] or null
+    int act;                   // 0 none, 1 gelu(erf), 2 relu
+    // K1 fusion (all null/0 for the plain GEMM)
+    int fused_bcast;
+    uint32_t* ready_flags;     // [num_n_blk * num_k_blk] local, zero before round 1
+    uint32_t epoch;            // flags are compared against this monotonically increasing value
+};
+
+V6_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K]  box 128x64
+                 const __grid_constant__ CUtensorMap tmap_b,        // B  [N,K]  box 256x64 (local copy)
+                 const __grid_constant__ CUtensorMap tmap_b_src,    // B on the server GPU (peer VA); K1 only
+                 const Params P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tfull_bar = empty_bar + kStages;
+    uint64_t* tempty_bar = tfull_bar + kAccStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kAccStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m = (P.M + BLOCK_M - 1) / BLOCK_M;
+    const int num_n = (P.N + BLOCK_N - 1) / BLOCK_N;
+    const int num_k = (P.K + BLOCK_K - 1) / BLOCK_K;
+    const int num_tiles = num_m * num_n;
+    const int empty_count = P.fused_bcast ? 2 : 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        if (P.fused_bcast) tma_prefetch_desc(&tmap_b_src);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], empty_count); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile order: all m_blk==0 tiles first (they are the K1 pullers), then column-major sweeps
+    auto tile_coords = [&](int t, int& m_blk, int& n_blk) {
+        if (t < num_n) { m_blk = 0; n_blk = t; }
+        else { const int u = t - num_n; m_blk = 1 + u % (num_m - 1); n_blk = u / (num_m - 1); }
+    };
+
+    if (warp == 0) {
+        // ============================ TMA producer ============================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                int m_blk, n_blk;
+                tile_coords(t, m_blk, n_blk);
+                const bool puller = P.fused_bcast && m_blk == 0;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+                    if (puller) {
+                        tma_load_2d(sb, &tmap_b_src, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);   // over NVLink
+                    } else {
+                        if (P.fused_bcast) {
+                            // wait until the puller tile has landed this weight tile locally
+                            const uint32_t* f = P.ready_flags + n_blk * num_k + kb;
+                            uint32_t spins = 0;
+                            while ((int32_t)(ld_acquire_sys_u32(f) - P.epoch) < 0) {
+                                __nanosleep(64);
+                                if (++spins > (1u << 24)) asm volatile("trap;");
+                            }
+                            asm volatile("fence.proxy.async.global;" ::: "memory");
+                        }
+                        tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================ MMA issuer ==============================
+        constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
+            tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            for (int kb = 0; kb < num_k; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tcgen05_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t da = make_smem_desc_sw128(sa + k * UMMA_K * 2);
+                        const uint64_t db = make_smem_desc_sw128(sb + k * UMMA_K * 2);
+                        umma_bf16_ss(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);               // frees the smem stage when the MMAs retire
+                    if (kb == num_k - 1) umma_commit(&tfull_bar[acc]);
+                }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp == 3) {
+        // ============================ K1 write-back warp =======================
+        if (P.fused_bcast && lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                int m_blk, n_blk;
+                tile_coords(t, m_blk, n_blk);
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    if (m_blk == 0) {
+                        uint8_t* sb = smem + stage * STAGE_BYTES + A_BYTES;
+                        fence_proxy_async_smem();
+                        tma_store_2d(&tmap_b, sb, kb * BLOCK_K, n_blk * BLOCK_N);     // un-swizzles on the way out
+                        tma_store_commit();
+                        tma_store_wait_all();                                         // writes complete
+                        asm volatile("fence.proxy.async.global;" ::: "memory");
+                        __threadfence();
+                        st_release_sys_u32(P.ready_flags + n_blk * num_k + kb, P.epoch);
+                    }
+                    mbar_arrive(&empty_bar[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ============================ epilogue ================================
+        const int ew = warp - 4;                      // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            int m_blk, n_blk;
+            tile_coords(t, m_blk, n_blk);
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tcgen05_fence_after();
+            const int row = m_blk * BLOCK_M + ew * 32 + lane;
+            const uint32_t t_row = tmem_base + acc * BLOCK_N + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(t_row + c, v);
+                tmem_ld_wait();
+                const int col0 = n_blk * BLOCK_N + c;
+                if (row < P.M && col0 < P.N) {
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (P.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (col0 + j < P.N) f[j] += __ldg(P.bias + col0 + j);
+                    }
+                    if (P.act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                    } else if (P.act == 2) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                    }
+                    __nv_bfloat16* dst = P.C + (size_t)row * P.ldc + col0;
+                    if (col0 + 32 <= P.N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8)
+                            *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_bf16x2(f[j], f[j + 1]), pack_bf16x2(f[j + 2], f[j + 3]),
+                                                                            pack_bf16x2(f[j + 4], f[j + 5]), pack_bf16x2(f[j + 6], f[j + 7]));
+                    } else {
+                        for (int j = 0; j < 32 && col0 + j < P.N; ++j) dst[j] = __float2bfloat16(f[j]);
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) { tcgen05_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
+}
+
+}  // namespace gemm
+
+
+static int launch_gemm(const void* A, const void* B, const void* B_src, void* C, const float* bias, int M, int N, int K,
+                       int lda, int ldb, int ldc, int act, uint32_t* ready_flags, uint32_t epoch, int max_ctas,
+                       cudaStream_t stream) {
+    using namespace gemm;
+    if (K % 8 != 0 || lda % 8 != 0 || ldb % 8 != 0 || ldc % 8 != 0) return (int)cudaErrorInvalidValue;
+    alignas(64) CUtensorMap ta, tb, tbs;
+    if (v6_make_tmap_2d_bf16(&ta, (uint64_t)A, M, K, (uint64_t)lda * 2, BLOCK_M, BLOCK_K, 1)) return -2;
+    if (v6_make_tmap_2d_bf16(&tb, (uint64_t)B, N, K, (uint64_t)ldb * 2, BLOCK_N, BLOCK_K, 1)) return -2;
+    if (B_src) { if (v6_make_tmap_2d_bf16(&tbs, (uint64_t)B_src, N, K, (uint64_t)ldb * 2, BLOCK_N, BLOCK_K, 1)) return -2; }
+    else tbs = tb;
+    Params P;
+    P.M = M; P.N = N; P.K = K; P.C = (__nv_bfloat16*)C; P.ldc = ldc; P.bias = bias; P.act = act;
+    P.fused_bcast = B_src ? 1 : 0; P.ready_flags = ready_flags; P.epoch = epoch;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int num_tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
+    int sms = max_ctas > 0 ? max_ctas : 148;
+    const int grid = num_tiles < sms ? num_tiles : sms;
+    gemm_bf16_kernel<<<grid, kThreads, SMEM_BYTES, stream>>>(ta, tb, tbs, P);
+    V6_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int v6_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, int lda,
+                            int ldb, int ldc, int act, cudaStream_t stream) {
+    return launch_gemm(A, B, nullptr, C, bias, M, N, K, lda, ldb, ldc, act, nullptr, 0, 0, stream);
+}
+extern "C" int v6_bcast_gemm_bf16(const void* A, void* B_local, const void* B_server_peer, void* C, const float* bias,
+                                  int M, int N, int K, int lda, int ldb, int ldc, int act, uint32_t* ready_flags,
+                                  uint32_t epoch, cudaStream_t stream) {
+    return launch_gemm(A, B_local, B_server_peer, C, bias, M, N, K, lda, ldb, ldc, act, ready_flags, epoch, 0, stream);
+}
+extern "C" int v6_gemm_smem_bytes() { return gemm::SMEM_BYTES; }

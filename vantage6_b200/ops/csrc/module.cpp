@@ -1,0 +1,160 @@
+// pybind11 bindings (CPython C-API, no torch headers): every function takes raw device
+// pointers (tensor.data_ptr()) and a CUDA stream handle (torch.cuda.current_stream().cuda_stream).
+// Python-side wrappers with shape/dtype checks and autograd live in vantage6_b200/ops/*.py.
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "api.h"
+
+namespace py = pybind11;
+using u64 = uint64_t;
+
+static void check(int rc, const char* what) {
+    if (rc == 0) return;
+    std::string msg = std::string(what) + " failed: ";
+    if (rc > 0) msg += cudaGetErrorString((cudaError_t)rc);
+    else msg += v6_symm_last_error();
+    throw std::runtime_error(msg);
+}
+static inline cudaStream_t S(u64 s) { return reinterpret_cast<cudaStream_t>(s); }
+template <typename T> static inline T* P(u64 p) { return reinterpret_cast<T*>(p); }
+static PeerTable table(const std::vector<u64>& v) {
+    PeerTable t;
+    for (int i = 0; i < V6_MAX_PEERS; ++i) t.p[i] = i < (int)v.size() ? reinterpret_cast<void*>(v[i]) : nullptr;
+    return t;
+}
+
+PYBIND11_MODULE(_C, m) {
+    m.doc() = "vantage6_b200 native sm_100a kernels + NVLink symmetric heap";
+    m.attr("MAX_PEERS") = V6_MAX_PEERS;
+    m.attr("PAD_WORDS") = 256;
+    m.attr("PAD_ABORT") = PAD_ABORT;
+    m.attr("PAD_STATUS") = PAD_STATUS;
+
+    // ------------------------------------------------------------------ symmetric heap
+    m.def("driver_available", [] { return v6_driver_available() != 0; });
+    m.def("symm_init", [](int rank, int world, int device, const std::string& dir, int timeout_s) {
+        int gid;
+        { py::gil_scoped_release nogil; gid = v6_symm_init(rank, world, device, dir.c_str(), timeout_s); }
+        if (gid < 0) throw std::runtime_error(std::string("symm_init: ") + v6_symm_last_error());
+        return gid;
+    });
+    m.def("symm_multicast_supported", &v6_symm_multicast_supported);
+    m.def("symm_alloc", [](int gid, size_t size, bool want_mc) {
+        uint64_t ptrs[V6_MAX_PEERS] = {0};
+        uint64_t mc = 0;
+        size_t padded = 0;
+        int aid;
+        { py::gil_scoped_release nogil; aid = v6_symm_alloc(gid, size, want_mc ? 1 : 0, ptrs, &mc, &padded); }
+        if (aid < 0) throw std::runtime_error(std::string("symm_alloc: ") + v6_symm_last_error());
+        std::vector<u64> v(ptrs, ptrs + V6_MAX_PEERS);
+        return py::make_tuple(aid, v, mc, padded);
+    });
+    m.def("symm_barrier_host", [](int gid) { py::gil_scoped_release nogil; check(v6_symm_barrier_host(gid), "symm_barrier_host"); });
+    m.def("symm_free", [](int gid, int aid) { py::gil_scoped_release nogil; v6_symm_free(gid, aid); });
+    m.def("symm_finalize", [](int gid) { py::gil_scoped_release nogil; v6_symm_finalize(gid); });
+
+    // ------------------------------------------------------------------ K2 / K3 / barrier
+    m.def("fedavg_round",
+          [](const std::vector<u64>& upload, const std::vector<u64>& param_out, const std::vector<u64>& shadow_out,
+             const std::vector<u64>& pads, u64 upload_mc, u64 param_mc, u64 shadow_mc, u64 w_global, u64 opt_m, u64 opt_v,
+             const std::vector<float>& weight, long long lo, long long hi, int rank, int world, int n_reducers,
+             uint32_t epoch, bool upload_is_delta, bool upload_prescaled, int server_opt, float server_lr, float beta1,
+             float beta2, float eps, float bias1, float bias2, float inv_total, long long timeout_cycles, u64 cta_counter,
+             int upload_dtype, int grid, u64 stream) {
+              FedAvgParams p;
+              p.upload = table(upload); p.param_out = table(param_out); p.shadow_out = table(shadow_out); p.pads = table(pads);
+              p.upload_mc = P<void>(upload_mc); p.param_mc = P<void>(param_mc); p.shadow_mc = P<void>(shadow_mc);
+              p.w_global = P<float>(w_global); p.opt_m = P<float>(opt_m); p.opt_v = P<float>(opt_v);
+              for (int i = 0; i < V6_MAX_PEERS; ++i) p.weight[i] = i < (int)weight.size() ? weight[i] : 0.f;
+              p.lo = lo; p.hi = hi; p.rank = rank; p.world = world; p.n_reducers = n_reducers; p.epoch = epoch;
+              p.upload_is_delta = upload_is_delta; p.upload_prescaled = upload_prescaled; p.server_opt = server_opt;
+              p.server_lr = server_lr; p.beta1 = beta1; p.beta2 = beta2; p.eps = eps; p.bias1 = bias1; p.bias2 = bias2;
+              p.inv_total = inv_total; p.timeout_cycles = timeout_cycles; p.cta_counter = P<unsigned int>(cta_counter);
+              check(v6_fedavg_round(&p, upload_dtype, grid, S(stream)), "fedavg_round");
+          });
+    m.def("symm_barrier", [](const std::vector<u64>& pads, int rank, int world, uint32_t epoch, long long timeout_cycles, u64 stream) {
+        PeerTable t = table(pads);
+        check(v6_symm_barrier(&t, rank, world, epoch, timeout_cycles, S(stream)), "symm_barrier");
+    });
+    m.def("small_allreduce", [](const std::vector<u64>& slots, const std::vector<u64>& pads, const std::vector<float>& weight,
+                                u64 out, int n, int rank, int world, uint32_t epoch, float inv_total, long long timeout_cycles,
+                                u64 stream) {
+        SmallParams p;
+        p.slots = table(slots); p.pads = table(pads);
+        for (int i = 0; i < V6_MAX_PEERS; ++i) p.weight[i] = i < (int)weight.size() ? weight[i] : 0.f;
+        p.out = P<float>(out); p.n = n; p.rank = rank; p.world = world; p.epoch = epoch; p.inv_total = inv_total;
+        p.timeout_cycles = timeout_cycles;
+        check(v6_small_allreduce(&p, S(stream)), "small_allreduce");
+    });
+    m.def("p2p_pull", [](u64 src, u64 dst, long long nbytes, u64 s) { check(v6_p2p_pull(P<void>(src), P<void>(dst), nbytes, S(s)), "p2p_pull"); });
+    m.def("mc_push", [](u64 src, u64 mc, long long nbytes, u64 s) { check(v6_mc_push(P<void>(src), P<void>(mc), nbytes, S(s)), "mc_push"); });
+    m.def("mc_reduce", [](u64 mc, u64 dst, long long nbytes, u64 s) { check(v6_mc_reduce(P<void>(mc), P<void>(dst), nbytes, S(s)), "mc_reduce"); });
+
+    // ------------------------------------------------------------------ K7 optimizers
+    m.def("flat_optim",
+          [](int kind, u64 w, u64 g, u64 mm, u64 v, u64 w_ref, u64 upload, u64 shadow, u64 grad_scale_ptr, long long n,
+             float lr, float momentum, float dampening, float weight_decay, float beta1, float beta2, float eps, float bias1,
+             float bias2, float contrib_scale, bool nesterov, bool save_ref, int publish, bool first_momentum_step, u64 stream) {
+              OptimParams p;
+              p.w = P<float>(w); p.g = P<float>(g); p.m = P<float>(mm); p.v = P<float>(v); p.w_ref = P<float>(w_ref);
+              p.upload = P<void>(upload); p.shadow = P<void>(shadow); p.grad_scale_ptr = P<float>(grad_scale_ptr); p.n = n;
+              p.lr = lr; p.momentum = momentum; p.dampening = dampening; p.weight_decay = weight_decay; p.beta1 = beta1;
+              p.beta2 = beta2; p.eps = eps; p.bias1 = bias1; p.bias2 = bias2; p.contrib_scale = contrib_scale;
+              p.nesterov = nesterov; p.save_ref = save_ref; p.publish = publish; p.first_momentum_step = first_momentum_step;
+              check(kind == 0 ? v6_flat_sgd(&p, S(stream)) : v6_flat_adamw(&p, S(stream)), "flat_optim");
+          });
+    m.def("delta_publish", [](u64 w, u64 ref, u64 upload, long long n, float scale, bool bf16_out, u64 s) {
+        check(v6_delta_publish(P<float>(w), P<float>(ref), P<void>(upload), n, scale, bf16_out, S(s)), "delta_publish");
+    });
+    m.def("cast_bf16", [](u64 src, u64 dst, long long n, u64 s) { check(v6_cast_bf16(P<float>(src), P<void>(dst), n, S(s)), "cast_bf16"); });
+    m.def("clip_coef", [](u64 g, long long n, float max_norm, u64 scratch, u64 coef, u64 s) {
+        check(v6_clip_coef(P<float>(g), n, max_norm, P<float>(scratch), P<float>(coef), S(s)), "clip_coef");
+    });
+
+    // ------------------------------------------------------------------ K5 norms
+    m.def("layernorm_fwd", [](u64 x, u64 res, u64 gamma, u64 beta, u64 y, u64 res_out, u64 mean, u64 rstd, int rows, int cols,
+                              float eps, bool bf16, u64 s) {
+        check(v6_layernorm_fwd(P<void>(x), P<void>(res), P<float>(gamma), P<float>(beta), P<void>(y), P<void>(res_out),
+                               P<float>(mean), P<float>(rstd), rows, cols, eps, bf16, S(s)), "layernorm_fwd");
+    });
+    m.def("rmsnorm_fwd", [](u64 x, u64 res, u64 gamma, u64 y, u64 res_out, u64 rstd, int rows, int cols, float eps, bool bf16, u64 s) {
+        check(v6_rmsnorm_fwd(P<void>(x), P<void>(res), P<float>(gamma), P<void>(y), P<void>(res_out), P<float>(rstd), rows, cols,
+                             eps, bf16, S(s)), "rmsnorm_fwd");
+    });
+    m.def("layernorm_bwd", [](u64 dy, u64 x_in, u64 dres, u64 gamma, u64 mean, u64 rstd, u64 dx, u64 dgamma, u64 dbeta,
+                              u64 scratch, int parts, int rows, int cols, bool accumulate, bool bf16, u64 s) {
+        check(v6_layernorm_bwd(P<void>(dy), P<void>(x_in), P<void>(dres), P<float>(gamma), P<float>(mean), P<float>(rstd),
+                               P<void>(dx), P<float>(dgamma), P<float>(dbeta), P<float>(scratch), parts, rows, cols, accumulate,
+                               bf16, S(s)), "layernorm_bwd");
+    });
+    m.def("rmsnorm_bwd", [](u64 dy, u64 x_in, u64 dres, u64 gamma, u64 rstd, u64 dx, u64 dgamma, u64 scratch, int parts,
+                            int rows, int cols, bool accumulate, bool bf16, u64 s) {
+        check(v6_rmsnorm_bwd(P<void>(dy), P<void>(x_in), P<void>(dres), P<float>(gamma), P<float>(rstd), P<void>(dx),
+                             P<float>(dgamma), P<float>(scratch), parts, rows, cols, accumulate, bf16, S(s)), "rmsnorm_bwd");
+    });
+
+    // ------------------------------------------------------------------ K6 / K8
+    m.def("rope", [](u64 q, u64 k, u64 cos_t, u64 sin_t, u64 pos, int B, int Sq, int Hq, int Hkv, int D, bool inverse, u64 s) {
+        check(v6_rope(P<void>(q), P<void>(k), P<float>(cos_t), P<float>(sin_t), P<int>(pos), B, Sq, Hq, Hkv, D, inverse, S(s)), "rope");
+    });
+    m.def("glm_logistic_grad", [](u64 X, u64 y, u64 w, u64 part, int max_parts, u64 out, int rows, int F, bool bf16, u64 s) {
+        check(v6_glm_logistic_grad(P<void>(X), P<float>(y), P<float>(w), P<float>(part), max_parts, P<float>(out), rows, F, bf16, S(s)),
+              "glm_logistic_grad");
+    });
+
+    // ------------------------------------------------------------------ K1 / tcgen05 GEMM
+    m.def("gemm_bf16", [](u64 A, u64 B, u64 C, u64 bias, int M, int N, int K, int lda, int ldb, int ldc, int act, u64 s) {
+        check(v6_gemm_bf16(P<void>(A), P<void>(B), P<void>(C), P<float>(bias), M, N, K, lda, ldb, ldc, act, S(s)), "gemm_bf16");
+    });
+    m.def("bcast_gemm_bf16", [](u64 A, u64 B_local, u64 B_peer, u64 C, u64 bias, int M, int N, int K, int lda, int ldb, int ldc,
+                                int act, u64 flags, uint32_t epoch, u64 s) {
+        check(v6_bcast_gemm_bf16(P<void>(A), P<void>(B_local), P<void>(B_peer), P<void>(C), P<float>(bias), M, N, K, lda, ldb,
+                                 ldc, act, P<uint32_t>(flags), epoch, S(s)), "bcast_gemm_bf16");
+    });
+    m.def("gemm_smem_bytes", &v6_gemm_smem_bytes);
+}

@@ -1,0 +1,306 @@
+// K5 of SURVEY.md 2.6: LayerNorm (BERT, 768) and RMSNorm (Llama, 4096) forward + backward,
+// with the residual add fused into the forward and the bf16 cast fused into both directions.
+//
+// Memory-bound design: every activation element is read once and written once per pass.
+// A row is owned by a thread group (TPR threads, a power of two <= 256) which keeps the whole
+// row in registers (<= 4 x 16 B vectors per thread), so mean/var use the exact two-pass form
+// without re-reading HBM.  gamma/beta stay fp32 (they live in the flat fp32 master buffer).
+// Backward: persistent CTAs walk rows; dgamma/dbeta are accumulated in registers across rows,
+// written as per-CTA partials and folded by a second tiny kernel (no atomics).
+#include "common.cuh"
+#include "api.h"
+
+template <typename T> struct IO;
+template <> struct IO<__nv_bfloat16> {
+    static constexpr int VEC = 8;
+    V6_DEVINL static void load(const __nv_bfloat16* p, float (&v)[8]) {
+        uint4 t = *reinterpret_cast<const uint4*>(p);
+        float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+    }
+    V6_DEVINL static void store(__nv_bfloat16* p, const float (&v)[8]) {
+        *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                  pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+};
+template <> struct IO<float> {
+    static constexpr int VEC = 8;
+    V6_DEVINL static void load(const float* p, float (&v)[8]) {
+        float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    V6_DEVINL static void store(float* p, const float (&v)[8]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+};
+
+// sum across the TPR threads that own one row. TPR <= 32: shuffles only. TPR > 32: smem.
+template <int TPR>
+V6_DEVINL float group_sum(float v, float* smem, int row_in_cta, int t) {
+    if constexpr (TPR <= 32) {
+#pragma unroll
+        for (int o = TPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    } else {
+        constexpr int W = TPR / 32;
+        v = warp_sum(v);
+        __syncthreads();
+        if ((t & 31) == 0) smem[row_in_cta * W + (t >> 5)] = v;
+        __syncthreads();
+        float r = 0.f;
+#pragma unroll
+        for (int w = 0; w < W; ++w) r += smem[row_in_cta * W + w];
+        return r;
+    }
+}
+
+constexpr int NORM_THREADS = 256;
+constexpr int MAXV = 4;   // 16 B vectors per thread per row
+
+template <typename T, int TPR, bool RMS>
+__global__ void __launch_bounds__(NORM_THREADS) norm_fwd_kernel(
+    const T* __restrict__ x, const T* __restrict__ residual, const float* __restrict__ gamma,
+    const float* __restrict__ beta, T* __restrict__ y, T* __restrict__ res_out,
+    float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int cols, float eps) {
+    constexpr int RPC = NORM_THREADS / TPR;     // rows per CTA iteration
+    __shared__ float red[NORM_THREADS / 32];
+    const int t = threadIdx.x % TPR, rin = threadIdx.x / TPR;
+    const int nvec = cols / 8;                  // vectors per row
+    for (int row0 = blockIdx.x * RPC; row0 < rows; row0 += gridDim.x * RPC) {
+        const int row = row0 + rin;
+        const bool active = row < rows;
+        float v[MAXV][8];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+            const int vi = t + j * TPR;
+            if (active && vi < nvec) {
+                IO<T>::load(x + (size_t)row * cols + vi * 8, v[j]);
+                if (residual) {
+                    float r[8];
+                    IO<T>::load(residual + (size_t)row * cols + vi * 8, r);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[j][k] += r[k];
+                }
+                if (res_out) IO<T>::store(res_out + (size_t)row * cols + vi * 8, v[j]);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s += v[j][k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[j][k] = 0.f;
+            }
+        }
+        float mean = 0.f;
+        if constexpr (!RMS) mean = group_sum<TPR>(s, red, rin, t) / cols;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+            const int vi = t + j * TPR;
+            if (vi < nvec) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const float d = v[j][k] - mean; q += d * d; }
+            }
+        }
+        const float var = group_sum<TPR>(q, red, rin, t) / cols;
+        const float rstd = rsqrtf(var + eps);
+        if (active && t == 0) { if (mean_out) mean_out[row] = mean; rstd_out[row] = rstd; }
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+            const int vi = t + j * TPR;
+            if (active && vi < nvec) {
+                float g[8], o[8];
+                IO<float>::load(gamma + vi * 8, g);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = (v[j][k] - mean) * rstd * g[k];
+                if constexpr (!RMS) {
+                    float b[8];
+                    IO<float>::load(beta + vi * 8, b);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o[k] += b[k];
+                }
+                IO<T>::store(y + (size_t)row * cols + vi * 8, o);
+            }
+        }
+    }
+}
+
+// backward. x_in is the (post-residual) input of the norm. dres (optional) is the incoming
+// gradient of the residual stream, added into dx (fused residual-gradient add).
+template <typename T, int TPR, bool RMS>
+__global__ void __launch_bounds__(NORM_THREADS) norm_bwd_kernel(
+    const T* __restrict__ dy, const T* __restrict__ x_in, const T* __restrict__ dres,
+    const float* __restrict__ gamma, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+    T* __restrict__ dx, float* __restrict__ dgamma_part, float* __restrict__ dbeta_part,
+    int rows, int cols) {
+    constexpr int RPC = NORM_THREADS / TPR;
+    __shared__ float red[NORM_THREADS / 32];
+    const int t = threadIdx.x % TPR, rin = threadIdx.x / TPR;
+    const int nvec = cols / 8;
+    float dg[MAXV][8], db[MAXV][8];
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { dg[j][k] = 0.f; db[j][k] = 0.f; }
+
+    for (int row0 = blockIdx.x * RPC; row0 < rows; row0 += gridDim.x * RPC) {
+        const int row = row0 + rin;
+        const bool active = row < rows;
+        const float mean = (active && !RMS) ? mean_in[row] : 0.f;
+        const float rstd = active ? rstd_in[row] : 0.f;
+        float xh[MAXV][8], dyg[MAXV][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+            const int vi = t + j * TPR;
+            if (active && vi < nvec) {
+                float d[8], g[8];
+                IO<T>::load(dy + (size_t)row * cols + vi * 8, d);
+                IO<T>::load(x_in + (size_t)row * cols + vi * 8, xh[j]);
+                IO<float>::load(gamma + vi * 8, g);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    xh[j][k] = (xh[j][k] - mean) * rstd;
+                    dyg[j][k] = d[k] * g[k];
+                    s1 += dyg[j][k];
+                    s2 += dyg[j][k] * xh[j][k];
+                    dg[j][k] += d[k] * xh[j][k];
+                    db[j][k] += d[k];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { xh[j][k] = 0.f; dyg[j][k] = 0.f; }
+            }
+        }
+        float m1 = 0.f;
+        if constexpr (!RMS) m1 = group_sum<TPR>(s1, red, rin, t) / cols;
+        const float m2 = group_sum<TPR>(s2, red, rin, t) / cols;
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+            const int vi = t + j * TPR;
+            if (active && vi < nvec) {
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = rstd * (dyg[j][k] - m1 - xh[j][k] * m2);
+                if (dres) {
+                    float r[8];
+                    IO<T>::load(dres + (size_t)row * cols + vi * 8, r);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o[k] += r[k];
+                }
+                IO<T>::store(dx + (size_t)row * cols + vi * 8, o);
+            }
+        }
+    }
+    // fold the RPC row-groups of this CTA through shared memory, then write one partial per CTA
+    extern __shared__ float part[];    // [RPC][cols] for dgamma, then the same for dbeta
+    float* pg = part;
+    float* pb = part + (size_t)RPC * cols;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int vi = t + j * TPR;
+        if (vi < nvec) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                pg[(size_t)rin * cols + vi * 8 + k] = dg[j][k];
+                if (!RMS) pb[(size_t)rin * cols + vi * 8 + k] = db[j][k];
+            }
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < cols; c += NORM_THREADS) {
+        float a = 0.f, b = 0.f;
+        for (int r = 0; r < RPC; ++r) { a += pg[(size_t)r * cols + c]; if (!RMS) b += pb[(size_t)r * cols + c]; }
+        dgamma_part[(size_t)blockIdx.x * cols + c] = a;
+        if (!RMS) dbeta_part[(size_t)blockIdx.x * cols + c] = b;
+    }
+}
+
+__global__ void norm_param_grad_fold(const float* __restrict__ part, float* __restrict__ out, int nparts, int cols, int accumulate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float a = 0.f;
+    for (int p = 0; p < nparts; ++p) a += part[(size_t)p * cols + c];
+    out[c] = accumulate ? out[c] + a : a;
+}
+
+static inline int pick_tpr(int cols) {
+    const int nvec = cols / 8;
+    int tpr = 8;
+    while (tpr * MAXV < nvec && tpr < 256) tpr <<= 1;
+    return tpr;
+}
+
+#define DISPATCH_TPR(TPRV, ...) \
+    switch (TPRV) { \
+        case 8:   { constexpr int TPR = 8;   __VA_ARGS__; break; } \
+        case 16:  { constexpr int TPR = 16;  __VA_ARGS__; break; } \
+        case 32:  { constexpr int TPR = 32;  __VA_ARGS__; break; } \
+        case 64:  { constexpr int TPR = 64;  __VA_ARGS__; break; } \
+        case 128: { constexpr int TPR = 128; __VA_ARGS__; break; } \
+        default:  { constexpr int TPR = 256; __VA_ARGS__; break; } \
+    }
+
+template <typename T, bool RMS>
+static int launch_fwd(const void* x, const void* residual, const float* gamma, const float* beta, void* y,
+                      void* res_out, float* mean, float* rstd, int rows, int cols, float eps, cudaStream_t s) {
+    if (cols % 8 != 0 || cols > 8 * MAXV * 256) return (int)cudaErrorInvalidValue;
+    const int tpr = pick_tpr(cols);
+    const int rpc = NORM_THREADS / tpr;
+    int grid = (rows + rpc - 1) / rpc;
+    if (grid > 148 * 8) grid = 148 * 8;
+    DISPATCH_TPR(tpr, (norm_fwd_kernel<T, TPR, RMS><<<grid, NORM_THREADS, 0, s>>>(
+        (const T*)x, (const T*)residual, gamma, beta, (T*)y, (T*)res_out, mean, rstd, rows, cols, eps)));
+    V6_CHECK_LAUNCH();
+    return 0;
+}
+
+template <typename T, bool RMS>
+static int launch_bwd(const void* dy, const void* x_in, const void* dres, const float* gamma, const float* mean,
+                      const float* rstd, void* dx, float* dgamma, float* dbeta, float* scratch, int scratch_parts,
+                      int rows, int cols, int accumulate, cudaStream_t s) {
+    if (cols % 8 != 0 || cols > 8 * MAXV * 256) return (int)cudaErrorInvalidValue;
+    const int tpr = pick_tpr(cols);
+    const int rpc = NORM_THREADS / tpr;
+    int grid = (rows + rpc - 1) / rpc;
+    if (grid > scratch_parts) grid = scratch_parts;
+    const size_t smem = (size_t)rpc * cols * sizeof(float) * (RMS ? 1 : 2);
+    float* pg = scratch;
+    float* pb = scratch + (size_t)scratch_parts * cols;
+    DISPATCH_TPR(tpr, {
+        auto kern = norm_bwd_kernel<T, TPR, RMS>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, NORM_THREADS, smem, s>>>((const T*)dy, (const T*)x_in, (const T*)dres, gamma, mean, rstd,
+                                                (T*)dx, pg, pb, rows, cols);
+    });
+    V6_CHECK_LAUNCH();
+    const int fb = (cols + 255) / 256;
+    norm_param_grad_fold<<<fb, 256, 0, s>>>(pg, dgamma, grid, cols, accumulate);
+    if (!RMS) norm_param_grad_fold<<<fb, 256, 0, s>>>(pb, dbeta, grid, cols, accumulate);
+    V6_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int v6_layernorm_fwd(const void* x, const void* residual, const float* gamma, const float* beta, void* y,
+                                void* res_out, float* mean, float* rstd, int rows, int cols, float eps, int bf16,
+                                cudaStream_t s) {
+    return bf16 ? launch_fwd<__nv_bfloat16, false>(x, residual, gamma, beta, y, res_out, mean, rstd, rows, cols, eps, s)
+                : launch_fwd<float, false>(x, residual, gamma, beta, y, res_out, mean, rstd, rows, cols, eps, s);
+}
+extern "C" int v6_rmsnorm_fwd(const void* x, const void* residual, const float* gamma, void* y, void* res_out,
+                              float* rstd, int rows, int cols, float eps, int bf16, cudaStream_t s) {
+    return bf16 ? launch_fwd<__nv_bfloat16, true>(x, residual, gamma, nullptr, y, res_out, nullptr, rstd, rows, cols, eps, s)
+                : launch_fwd<float, true>(x, residual, gamma, nullptr, y, res_out, nullptr, rstd, rows, cols, eps, s);
+}
+extern "C" int v6_layernorm_bwd(const void* dy, const void* x_in, const void* dres, const float* gamma, const float* mean,
+                                const float* rstd, void* dx, float* dgamma, float* dbeta, float* scratch,
+                                int scratch_parts, int rows, int cols, int accumulate, int bf16, cudaStream_t s) {
+    return bf16 ? launch_bwd<__nv_bfloat16, false>(dy, x_in, dres, gamma, mean, rstd, dx, dgamma, dbeta, scratch, scratch_parts, rows, cols, accumulate, s)
+                : launch_bwd<float, false>(dy, x_in, dres, gamma, mean, rstd, dx, dgamma, dbeta, scratch, scratch_parts, rows, cols, accumulate, s);
+}
+extern "C" int v6_rmsnorm_bwd(const void* dy, const void* x_in, const void* dres, const float* gamma, const float* rstd,
+                              void* dx, float* dgamma, float* scratch, int scratch_parts, int rows, int cols,
+                              int accumulate, int bf16, cudaStream_t s) {
+    return bf16 ? launch_bwd<__nv_bfloat16, true>(dy, x_in, dres, gamma, nullptr, rstd, dx, dgamma, nullptr, scratch, scratch_parts, rows, cols, accumulate, s)
+                : launch_bwd<float, true>(dy, x_in, dres, gamma, nullptr, rstd, dx, dgamma, nullptr, scratch, scratch_parts, rows, cols, accumulate, s);
+}

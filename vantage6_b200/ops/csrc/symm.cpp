@@ -1,0 +1,414 @@
+// Symmetric heap over NVLink 5 / NVSwitch, owned by this framework:
+//
+//   * every rank (one process per GPU) creates its physical allocation with the CUDA VMM API
+//     (cuMemCreate, POSIX-fd shareable), passes the fd to every peer over a Unix-domain
+//     socket (SCM_RIGHTS), and maps every peer's allocation into its own address space
+//     -> `peer_ptr[world]` per buffer: plain ld/st on those VAs travel over NVLink.
+//   * optionally one NVLS multicast object is created over the same physical memory
+//     (cuMulticastCreate/AddDevice/BindMem) -> `mc_ptr`: `multimem.st` replicates in the
+//     switch, `multimem.ld_reduce` sums in the switch.
+//   * no NCCL / NVSHMEM call anywhere on this path.
+//
+// This replaces the reference's data plane (task payloads as REST blobs through a SQL DB and
+// an optional node-to-node VPN: reference vantage6/cli/configuration_wizard.py:78-84,
+// vantage6/cli/context.py:133-138).
+//
+// The driver API is resolved at run time with cudaGetDriverEntryPoint so that the module
+// imports on machines without libcuda (build / CPU test boxes).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/socket.h>
+#include <sys/stat.h>
+#include <sys/un.h>
+#include <time.h>
+#include <unistd.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#define V6_MAX_PEERS 8
+
+namespace {
+
+struct Driver {
+    bool ok = false;
+    std::string err;
+#define DRV(name) decltype(&name) p_##name = nullptr;
+    DRV(cuMemCreate) DRV(cuMemRelease) DRV(cuMemAddressReserve) DRV(cuMemAddressFree) DRV(cuMemMap)
+    DRV(cuMemUnmap) DRV(cuMemSetAccess) DRV(cuMemExportToShareableHandle) DRV(cuMemImportFromShareableHandle)
+    DRV(cuMemGetAllocationGranularity) DRV(cuMulticastCreate) DRV(cuMulticastAddDevice) DRV(cuMulticastBindMem)
+    DRV(cuMulticastGetGranularity) DRV(cuMulticastUnbind) DRV(cuDeviceGetAttribute) DRV(cuGetErrorString)
+    DRV(cuTensorMapEncodeTiled) DRV(cuDeviceGet)
+#undef DRV
+};
+
+Driver& drv() {
+    static Driver d;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        auto get = [&](const char* name, void** fn) -> bool {
+            cudaDriverEntryPointQueryResult q;
+            cudaError_t e = cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q);
+            if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || *fn == nullptr) {
+                d.err = std::string("cannot resolve driver symbol ") + name + ": " + cudaGetErrorString(e);
+                cudaGetLastError();
+                return false;
+            }
+            return true;
+        };
+        bool ok = true;
+#define GET(name) ok = ok && get(#name, reinterpret_cast<void**>(&d.p_##name));
+        GET(cuMemCreate) GET(cuMemRelease) GET(cuMemAddressReserve) GET(cuMemAddressFree) GET(cuMemMap)
+        GET(cuMemUnmap) GET(cuMemSetAccess) GET(cuMemExportToShareableHandle) GET(cuMemImportFromShareableHandle)
+        GET(cuMemGetAllocationGranularity) GET(cuMulticastCreate) GET(cuMulticastAddDevice) GET(cuMulticastBindMem)
+        GET(cuMulticastGetGranularity) GET(cuMulticastUnbind) GET(cuDeviceGetAttribute) GET(cuGetErrorString)
+        GET(cuTensorMapEncodeTiled) GET(cuDeviceGet)
+#undef GET
+        d.ok = ok;
+    });
+    return d;
+}
+
+thread_local std::string g_last_error;
+
+bool cu_ok(CUresult r, const char* what) {
+    if (r == CUDA_SUCCESS) return true;
+    const char* s = nullptr;
+    if (drv().p_cuGetErrorString) drv().p_cuGetErrorString(r, &s);
+    g_last_error = std::string(what) + " failed: " + (s ? s : "unknown") + " (" + std::to_string((int)r) + ")";
+    return false;
+}
+
+// ---------------------------------------------------------------- unix-socket mesh ------
+int send_fd(int sock, int fd, uint64_t tag) {
+    struct msghdr msg;
+    memset(&msg, 0, sizeof(msg));
+    char cbuf[CMSG_SPACE(sizeof(int))];
+    memset(cbuf, 0, sizeof(cbuf));
+    struct iovec io;
+    io.iov_base = &tag;
+    io.iov_len = sizeof(tag);
+    msg.msg_iov = &io;
+    msg.msg_iovlen = 1;
+    if (fd >= 0) {
+        msg.msg_control = cbuf;
+        msg.msg_controllen = sizeof(cbuf);
+        struct cmsghdr* c = CMSG_FIRSTHDR(&msg);
+        c->cmsg_level = SOL_SOCKET;
+        c->cmsg_type = SCM_RIGHTS;
+        c->cmsg_len = CMSG_LEN(sizeof(int));
+        memcpy(CMSG_DATA(c), &fd, sizeof(int));
+    }
+    ssize_t n;
+    do { n = sendmsg(sock, &msg, 0); } while (n < 0 && errno == EINTR);
+    return n == (ssize_t)sizeof(tag) ? 0 : -1;
+}
+int recv_fd(int sock, int* fd, uint64_t* tag) {
+    struct msghdr msg;
+    memset(&msg, 0, sizeof(msg));
+    char cbuf[CMSG_SPACE(sizeof(int))];
+    memset(cbuf, 0, sizeof(cbuf));
+    struct iovec io;
+    io.iov_base = tag;
+    io.iov_len = sizeof(*tag);
+    msg.msg_iov = &io;
+    msg.msg_iovlen = 1;
+    msg.msg_control = cbuf;
+    msg.msg_controllen = sizeof(cbuf);
+    ssize_t n;
+    do { n = recvmsg(sock, &msg, MSG_WAITALL); } while (n < 0 && errno == EINTR);
+    if (n != (ssize_t)sizeof(*tag)) return -1;
+    *fd = -1;
+    for (struct cmsghdr* c = CMSG_FIRSTHDR(&msg); c; c = CMSG_NXTHDR(&msg, c))
+        if (c->cmsg_level == SOL_SOCKET && c->cmsg_type == SCM_RIGHTS) memcpy(fd, CMSG_DATA(c), sizeof(int));
+    return 0;
+}
+
+struct Alloc {
+    size_t size = 0;
+    CUmemGenericAllocationHandle local = 0;
+    CUmemGenericAllocationHandle peer_h[V6_MAX_PEERS] = {0};
+    CUdeviceptr va[V6_MAX_PEERS] = {0};
+    CUmemGenericAllocationHandle mc = 0;
+    CUdeviceptr mc_va = 0;
+    bool has_mc = false;
+};
+
+struct Group {
+    int rank = 0, world = 1, device = 0;
+    int conn[V6_MAX_PEERS];
+    int listener = -1;
+    std::string sock_path;
+    bool mc_supported = false;
+    std::vector<Alloc*> allocs;
+};
+
+std::vector<Group*> g_groups;
+std::mutex g_mu;
+
+void sleep_ms(int ms) {
+    struct timespec ts = {ms / 1000, (ms % 1000) * 1000000L};
+    nanosleep(&ts, nullptr);
+}
+
+bool mesh_barrier(Group* g) {
+    for (int p = 0; p < g->world; ++p)
+        if (p != g->rank && send_fd(g->conn[p], -1, 0xB0B0) != 0) return false;
+    for (int p = 0; p < g->world; ++p)
+        if (p != g->rank) {
+            int fd; uint64_t tag;
+            if (recv_fd(g->conn[p], &fd, &tag) != 0 || tag != 0xB0B0) return false;
+        }
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* v6_symm_last_error() { return g_last_error.c_str(); }
+
+// 1 if the CUDA driver entry points resolved (i.e. a GPU driver is present).
+int v6_driver_available() { return drv().ok ? 1 : 0; }
+
+// Create the rendezvous mesh. `dir` must be a directory shared by all ranks (same box).
+// Returns a group id >= 0, or -1 (see v6_symm_last_error).
+int v6_symm_init(int rank, int world, int device, const char* dir, int timeout_s) {
+    if (world < 1 || world > V6_MAX_PEERS || rank < 0 || rank >= world) { g_last_error = "bad rank/world"; return -1; }
+    if (!drv().ok) { g_last_error = "CUDA driver not available: " + drv().err; return -1; }
+    if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess) { g_last_error = "cudaSetDevice failed"; return -1; }
+    Group* g = new Group();
+    g->rank = rank; g->world = world; g->device = device;
+    for (int i = 0; i < V6_MAX_PEERS; ++i) g->conn[i] = -1;
+
+    CUdevice cudev;
+    if (!cu_ok(drv().p_cuDeviceGet(&cudev, device), "cuDeviceGet")) return -1;
+    int mc = 0;
+    drv().p_cuDeviceGetAttribute(&mc, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, cudev);
+    g->mc_supported = mc != 0;
+
+    if (world > 1) {
+        g->sock_path = std::string(dir) + "/v6symm_" + std::to_string(rank) + ".sock";
+        unlink(g->sock_path.c_str());
+        g->listener = socket(AF_UNIX, SOCK_STREAM, 0);
+        struct sockaddr_un addr;
+        memset(&addr, 0, sizeof(addr));
+        addr.sun_family = AF_UNIX;
+        strncpy(addr.sun_path, g->sock_path.c_str(), sizeof(addr.sun_path) - 1);
+        if (bind(g->listener, (struct sockaddr*)&addr, sizeof(addr)) != 0 || listen(g->listener, world) != 0) {
+            g_last_error = std::string("bind/listen ") + g->sock_path + ": " + strerror(errno);
+            return -1;
+        }
+        // connect to lower ranks, accept from higher ranks
+        for (int p = 0; p < rank; ++p) {
+            std::string peer = std::string(dir) + "/v6symm_" + std::to_string(p) + ".sock";
+            int s = -1;
+            for (int tries = 0; tries < timeout_s * 20; ++tries) {
+                s = socket(AF_UNIX, SOCK_STREAM, 0);
+                struct sockaddr_un pa;
+                memset(&pa, 0, sizeof(pa));
+                pa.sun_family = AF_UNIX;
+                strncpy(pa.sun_path, peer.c_str(), sizeof(pa.sun_path) - 1);
+                if (connect(s, (struct sockaddr*)&pa, sizeof(pa)) == 0) break;
+                close(s); s = -1;
+                sleep_ms(50);
+            }
+            if (s < 0) { g_last_error = "connect to " + peer + " timed out"; return -1; }
+            if (send_fd(s, -1, (uint64_t)rank) != 0) { g_last_error = "hello send failed"; return -1; }
+            g->conn[p] = s;
+        }
+        struct timeval tv = {timeout_s, 0};
+        setsockopt(g->listener, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+        for (int k = 0; k < world - 1 - rank; ++k) {
+            int s = accept(g->listener, nullptr, nullptr);
+            if (s < 0) { g_last_error = std::string("accept: ") + strerror(errno); return -1; }
+            int fd; uint64_t who;
+            if (recv_fd(s, &fd, &who) != 0 || who >= (uint64_t)world) { g_last_error = "hello recv failed"; return -1; }
+            g->conn[who] = s;
+        }
+        for (int p = 0; p < world; ++p)
+            if (p != rank) setsockopt(g->conn[p], SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_groups.push_back(g);
+    return (int)g_groups.size() - 1;
+}
+
+int v6_symm_multicast_supported(int gid) { return g_groups[gid]->mc_supported ? 1 : 0; }
+
+// Allocate `size` bytes on every rank (collective). Fills peer_ptrs[world] (peer_ptrs[rank] is
+// the local VA) and *mc_ptr (0 when multicast is unavailable / not requested).
+// Returns alloc id >= 0 or -1.
+int v6_symm_alloc(int gid, size_t size, int want_multicast, uint64_t* peer_ptrs, uint64_t* mc_ptr, size_t* padded) {
+    Group* g = g_groups[gid];
+    Driver& d = drv();
+    cudaSetDevice(g->device);
+    CUmemAllocationProp prop;
+    memset(&prop, 0, sizeof(prop));
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = g->device;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    size_t gran = 0;
+    if (!cu_ok(d.p_cuMemGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED), "cuMemGetAllocationGranularity")) return -1;
+    bool use_mc = want_multicast && g->mc_supported && g->world > 1;
+    CUmulticastObjectProp mprop;
+    memset(&mprop, 0, sizeof(mprop));
+    if (use_mc) {
+        mprop.numDevices = g->world;
+        mprop.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+        mprop.size = size;
+        size_t mgran = 0;
+        if (d.p_cuMulticastGetGranularity(&mgran, &mprop, CU_MULTICAST_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS && mgran > gran) gran = mgran;
+    }
+    size = (size + gran - 1) / gran * gran;
+    mprop.size = size;
+    *padded = size;
+
+    Alloc* a = new Alloc();
+    a->size = size;
+    if (!cu_ok(d.p_cuMemCreate(&a->local, size, &prop, 0), "cuMemCreate")) return -1;
+
+    CUmemAccessDesc acc;
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = g->device;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+
+    // local mapping
+    if (!cu_ok(d.p_cuMemAddressReserve(&a->va[g->rank], size, gran, 0, 0), "cuMemAddressReserve")) return -1;
+    if (!cu_ok(d.p_cuMemMap(a->va[g->rank], size, 0, a->local, 0), "cuMemMap(local)")) return -1;
+    if (!cu_ok(d.p_cuMemSetAccess(a->va[g->rank], size, &acc, 1), "cuMemSetAccess(local)")) return -1;
+    a->peer_h[g->rank] = a->local;
+
+    if (g->world > 1) {
+        int myfd = -1;
+        if (!cu_ok(d.p_cuMemExportToShareableHandle(&myfd, a->local, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0), "cuMemExportToShareableHandle")) return -1;
+        const uint64_t tag = 0xA110C000ull + g->allocs.size();
+        for (int p = 0; p < g->world; ++p)
+            if (p != g->rank && send_fd(g->conn[p], myfd, tag) != 0) { g_last_error = "send_fd failed"; return -1; }
+        for (int p = 0; p < g->world; ++p) {
+            if (p == g->rank) continue;
+            int fd = -1; uint64_t t = 0;
+            if (recv_fd(g->conn[p], &fd, &t) != 0 || fd < 0 || t != tag) { g_last_error = "recv_fd failed (peer " + std::to_string(p) + ")"; return -1; }
+            if (!cu_ok(d.p_cuMemImportFromShareableHandle(&a->peer_h[p], (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR), "cuMemImportFromShareableHandle")) return -1;
+            close(fd);
+            if (!cu_ok(d.p_cuMemAddressReserve(&a->va[p], size, gran, 0, 0), "cuMemAddressReserve(peer)")) return -1;
+            if (!cu_ok(d.p_cuMemMap(a->va[p], size, 0, a->peer_h[p], 0), "cuMemMap(peer)")) return -1;
+            if (!cu_ok(d.p_cuMemSetAccess(a->va[p], size, &acc, 1), "cuMemSetAccess(peer)")) return -1;
+        }
+        close(myfd);
+        if (!mesh_barrier(g)) { g_last_error = "mesh barrier failed"; return -1; }
+    }
+
+    *mc_ptr = 0;
+    if (use_mc) {
+        // rank 0 creates the multicast object and ships its fd; everyone adds its device, then
+        // (after a barrier: all devices must be added before any bind) binds its memory.
+        bool ok = true;
+        int mcfd = -1;
+        if (g->rank == 0) {
+            ok = cu_ok(d.p_cuMulticastCreate(&a->mc, &mprop), "cuMulticastCreate") &&
+                 cu_ok(d.p_cuMemExportToShareableHandle(&mcfd, a->mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0), "export(mc)");
+            for (int p = 1; p < g->world; ++p) send_fd(g->conn[p], ok ? mcfd : -1, ok ? 0x3C3Cull : 0xDEADull);
+            if (mcfd >= 0) close(mcfd);
+        } else {
+            uint64_t t = 0;
+            if (recv_fd(g->conn[0], &mcfd, &t) != 0 || t != 0x3C3Cull || mcfd < 0) ok = false;
+            else {
+                ok = cu_ok(d.p_cuMemImportFromShareableHandle(&a->mc, (void*)(uintptr_t)mcfd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR), "import(mc)");
+                close(mcfd);
+            }
+        }
+        CUdevice cudev;
+        d.p_cuDeviceGet(&cudev, g->device);
+        if (ok) ok = cu_ok(d.p_cuMulticastAddDevice(a->mc, cudev), "cuMulticastAddDevice");
+        if (!mesh_barrier(g)) ok = false;
+        if (ok) ok = cu_ok(d.p_cuMulticastBindMem(a->mc, 0, a->local, 0, size, 0), "cuMulticastBindMem");
+        if (ok) ok = cu_ok(d.p_cuMemAddressReserve(&a->mc_va, size, gran, 0, 0), "reserve(mc)") &&
+                     cu_ok(d.p_cuMemMap(a->mc_va, size, 0, a->mc, 0), "cuMemMap(mc)") &&
+                     cu_ok(d.p_cuMemSetAccess(a->mc_va, size, &acc, 1), "cuMemSetAccess(mc)");
+        // agree on the outcome: everybody must have succeeded
+        uint64_t mine = ok ? 1 : 0;
+        bool all = ok;
+        for (int p = 0; p < g->world; ++p) if (p != g->rank) send_fd(g->conn[p], -1, 0x0C00ull | mine);
+        for (int p = 0; p < g->world; ++p) if (p != g->rank) {
+            int fd; uint64_t t;
+            if (recv_fd(g->conn[p], &fd, &t) != 0 || (t & ~1ull) != 0x0C00ull || !(t & 1)) all = false;
+        }
+        if (all) { a->has_mc = true; *mc_ptr = (uint64_t)a->mc_va; }
+    }
+    cudaMemset((void*)a->va[g->rank], 0, size);
+    cudaDeviceSynchronize();
+    if (g->world > 1 && !mesh_barrier(g)) { g_last_error = "final mesh barrier failed"; return -1; }
+    for (int p = 0; p < g->world; ++p) peer_ptrs[p] = (uint64_t)a->va[p];
+    g->allocs.push_back(a);
+    return (int)g->allocs.size() - 1;
+}
+
+int v6_symm_barrier_host(int gid) { return mesh_barrier(g_groups[gid]) ? 0 : -1; }
+
+int v6_symm_free(int gid, int aid) {
+    Group* g = g_groups[gid];
+    Alloc* a = g->allocs[aid];
+    if (!a) return 0;
+    Driver& d = drv();
+    cudaSetDevice(g->device);
+    cudaDeviceSynchronize();
+    if (g->world > 1) mesh_barrier(g);
+    if (a->has_mc) {
+        d.p_cuMemUnmap(a->mc_va, a->size);
+        d.p_cuMemAddressFree(a->mc_va, a->size);
+        CUdevice cudev;
+        d.p_cuDeviceGet(&cudev, g->device);
+        d.p_cuMulticastUnbind(a->mc, cudev, 0, a->size);
+    }
+    if (a->mc) d.p_cuMemRelease(a->mc);
+    for (int p = 0; p < g->world; ++p) {
+        if (!a->va[p]) continue;
+        d.p_cuMemUnmap(a->va[p], a->size);
+        d.p_cuMemAddressFree(a->va[p], a->size);
+        if (p != g->rank && a->peer_h[p]) d.p_cuMemRelease(a->peer_h[p]);
+    }
+    d.p_cuMemRelease(a->local);
+    delete a;
+    g->allocs[aid] = nullptr;
+    return 0;
+}
+
+int v6_symm_finalize(int gid) {
+    Group* g = g_groups[gid];
+    if (!g) return 0;
+    for (size_t i = 0; i < g->allocs.size(); ++i) v6_symm_free(gid, (int)i);
+    for (int p = 0; p < V6_MAX_PEERS; ++p) if (g->conn[p] >= 0) close(g->conn[p]);
+    if (g->listener >= 0) close(g->listener);
+    if (!g->sock_path.empty()) unlink(g->sock_path.c_str());
+    delete g;
+    g_groups[gid] = nullptr;
+    return 0;
+}
+
+// ---------------------------------------------------------------- TMA descriptors --------
+// Encode a 2-D bf16 row-major tensor map [rows, cols] with box [box_rows, box_cols] and
+// 128-byte swizzle into `out` (128 bytes, 64 B aligned). Works for peer-mapped VAs too.
+int v6_make_tmap_2d_bf16(void* out, uint64_t gptr, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                         uint32_t box_rows, uint32_t box_cols, int swizzle128) {
+    if (!drv().ok) { g_last_error = "CUDA driver not available: " + drv().err; return -1; }
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = drv().p_cuTensorMapEncodeTiled(
+        reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)gptr, dims, strides, box, estr,
+        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return cu_ok(r, "cuTensorMapEncodeTiled") ? 0 : -1;
+}
+
+}  // extern "C"

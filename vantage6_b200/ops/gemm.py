@@ -1,0 +1,122 @@
+"""tcgen05/TMEM/TMA GEMM (csrc/gemm.cu) and K1, the broadcast-fused first forward GEMM.
+
+``linear(x, W, bias, act)``        : y = act(x @ W^T + bias), bf16 in / fp32 accumulate in TMEM.
+``bcast_linear(x, W_local, W_server_peer, ...)`` : same math, but the weight tiles are pulled by
+TMA from the *server GPU's* copy over NVLink (peer-mapped VA) while the MMAs of already-landed
+tiles run; the pulled tiles are written back to ``W_local`` so that after the call the node owns
+the new global weights of that layer.  This replaces "ncclBroadcast then cuBLAS GEMM".
+
+Backward passes use cuBLAS (torch.matmul) -- plain library GEMMs -- with the activation
+derivative recomputed from the saved pre-activation-free formulation (GELU saved input).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import native, stream_ptr
+
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+
+
+def _check(x: torch.Tensor, W: torch.Tensor):
+    assert x.dtype == torch.bfloat16 and W.dtype == torch.bfloat16, "tcgen05 GEMM is bf16 x bf16 -> fp32 acc"
+    assert x.stride(-1) == 1 and W.stride(-1) == 1
+    K = x.shape[-1]
+    assert W.shape[1] == K and K % 8 == 0, "K must be a multiple of 8 (16-byte TMA rows)"
+
+
+def gemm_bf16(x2: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x2:[M,K], W:[N,K] -> [M,N] bf16 (raw op, no autograd)."""
+    _check(x2, W)
+    M, K = x2.shape
+    N = W.shape[0]
+    assert N % 8 == 0
+    if out is None:
+        out = torch.empty(M, N, device=x2.device, dtype=torch.bfloat16)
+    native().gemm_bf16(x2.data_ptr(), W.data_ptr(), out.data_ptr(), 0 if bias is None else bias.data_ptr(),
+                       M, N, K, x2.stride(0), W.stride(0), out.stride(0), act, stream_ptr())
+    return out
+
+
+def bcast_gemm_bf16(x2: torch.Tensor, W_local: torch.Tensor, W_server_ptr: int, ready_flags: torch.Tensor,
+                    epoch: int, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K1. ``W_server_ptr`` is the peer-mapped device address of the server's [N,K] bf16 weights."""
+    _check(x2, W_local)
+    M, K = x2.shape
+    N = W_local.shape[0]
+    n_flags = ((N + 255) // 256) * ((K + 63) // 64)
+    assert ready_flags.dtype == torch.int32 and ready_flags.numel() >= n_flags
+    if out is None:
+        out = torch.empty(M, N, device=x2.device, dtype=torch.bfloat16)
+    native().bcast_gemm_bf16(x2.data_ptr(), W_local.data_ptr(), W_server_ptr, out.data_ptr(),
+                             0 if bias is None else bias.data_ptr(), M, N, K, x2.stride(0), W_local.stride(0),
+                             out.stride(0), act, ready_flags.data_ptr(), epoch, stream_ptr())
+    return out
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, bias, act):
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        if act == ACT_NONE:
+            y = gemm_bf16(x2, W, bias, ACT_NONE)
+            ctx.save_for_backward(x2, W, None)
+        else:
+            pre = gemm_bf16(x2, W, bias, ACT_NONE)          # keep pre-activation for the backward
+            y = torch.nn.functional.gelu(pre) if act == ACT_GELU else torch.relu(pre)
+            ctx.save_for_backward(x2, W, pre)
+        ctx.act = act
+        ctx.has_bias = bias is not None
+        ctx.xshape = x.shape
+        return y.view(*x.shape[:-1], W.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, W, pre = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if ctx.act == ACT_GELU:
+            p = pre.float()
+            cdf = 0.5 * (1.0 + torch.erf(p * 0.7071067811865476))
+            pdf = torch.exp(-0.5 * p * p) * 0.3989422804014327
+            dy2 = (dy2.float() * (cdf + p * pdf)).to(dy.dtype)
+        elif ctx.act == ACT_RELU:
+            dy2 = dy2 * (pre > 0)
+        dx = (dy2 @ W).view(ctx.xshape)
+        dW = dy2.t() @ x2
+        db = dy2.float().sum(0) if ctx.has_bias else None
+        return dx, dW, db, None
+
+
+class _LinearFusedActFn(torch.autograd.Function):
+    """Inference / no-grad fast path: activation fused in the tcgen05 epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, act):
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        return gemm_bf16(x2, W, bias, act).view(*x.shape[:-1], W.shape[0])
+
+
+def linear(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE) -> torch.Tensor:
+    """y = act(x @ W^T + bias) on the hand-written tcgen05 kernel (CUDA) or torch (CPU)."""
+    if x.is_cuda:
+        if not torch.is_grad_enabled() or not (x.requires_grad or W.requires_grad):
+            return _LinearFusedActFn.apply(x, W, bias, act)
+        return _LinearFn.apply(x, W, bias, act)
+    return reference_linear(x, W, bias, act)
+
+
+def reference_linear(x, W, bias=None, act=ACT_NONE):
+    y = x.float() @ W.float().t()
+    if bias is not None:
+        y = y + bias.float()
+    if act == ACT_GELU:
+        y = torch.nn.functional.gelu(y)
+    elif act == ACT_RELU:
+        y = torch.relu(y)
+    return y.to(x.dtype)

@@ -1,0 +1,45 @@
+"""K8: fused logistic-regression step -- gradient, intercept gradient and loss in one pass over X.
+
+Returns the *payload vector* ``[g_w (F), g_b, loss_sum, n_rows]`` (padded to a multiple of 4)
+that is handed unchanged to the K3 small-message all-reduce: the federated GLM update is
+``w <- w - lr * sum_i g_i / sum_i n_i``.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import native, stream_ptr
+
+_MAX_PARTS = 148 * 4
+
+
+def payload_len(F: int) -> int:
+    return (F + 3 + 3) // 4 * 4
+
+
+def logistic_grad(X: torch.Tensor, y: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None,
+                  scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """X:[rows,F] (bf16/fp32), y:[rows] fp32 in {0,1}, w:[F+1] fp32 (last = intercept)."""
+    rows, F = X.shape
+    if out is None:
+        out = torch.zeros(payload_len(F), device=X.device, dtype=torch.float32)
+    if X.is_cuda:
+        if scratch is None:
+            scratch = torch.empty(_MAX_PARTS * (F + 2), device=X.device, dtype=torch.float32)
+        native().glm_logistic_grad(X.data_ptr(), y.data_ptr(), w.data_ptr(), scratch.data_ptr(), _MAX_PARTS,
+                                   out.data_ptr(), rows, F, X.dtype == torch.bfloat16, stream_ptr())
+    else:
+        out[: F + 3] = reference_logistic_grad(X, y, w)
+    return out
+
+
+def reference_logistic_grad(X, y, w):
+    Xf = X.float()
+    F = Xf.shape[1]
+    z = Xf @ w[:F].float() + w[F].float()
+    r = torch.sigmoid(z) - y.float()
+    g = Xf.t() @ r
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(z, y.float(), reduction="sum")
+    return torch.cat([g, r.sum()[None], loss[None], torch.tensor([float(Xf.shape[0])], device=X.device)])

@@ -1,0 +1,356 @@
+"""FedAvg aggregation engine -- the server's per-round loop on the GPUs.
+
+Data planes
+-----------
+``native``      ONE fused kernel per round per rank (csrc/fedavg.cu, K2): flag handshake ->
+                weighted reduction over NVLink (P2P loads or in-switch ``multimem.ld_reduce``)
+                -> server optimizer (FedAvg / FedAvgM / FedAdam) on the fp32 master ->
+                broadcast of the new global model fused in the epilogue (P2P stores or
+                ``multimem.st``).  No NCCL call.
+``collective``  the baseline / CPU path: ``torch.distributed.reduce`` of pre-scaled
+                contributions + torch optimizer math + ``torch.distributed.broadcast``
+                (NCCL on GPUs, gloo on CPU).  "A path that only calls NCCL for the named ops is
+                the baseline, not the product" (BASELINE.md).
+
+Server placement
+----------------
+``central``  the whole aggregation runs on rank 0 / GPU 0 (the vantage6 central server);
+``sharded``  every rank owns 1/world of the global model and of the server-optimizer state
+             (the same kernel with a different slice) -- NVLink traffic is balanced over all
+             18x8 links instead of funnelled through GPU 0.
+
+Semantics kept from vantage6: node-local data never leaves the node,
+only model parameters / deltas cross; weights ``n_i`` are the node sample counts; partial
+participation renormalises over the reporters (weight 0 == not reporting).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from .symm import PAD_WORDS, SymmetricHeap
+
+SERVER_OPTS = {"fedavg": 0, "fedavgm": 1, "fedadam": 2}
+UPLOAD_MODES = ("weights_f32", "delta_f32", "delta_bf16")
+
+
+@dataclass
+class ServerOptConfig:
+    name: str = "fedavg"
+    lr: float = 1.0
+    beta1: float = 0.9
+    beta2: float = 0.99
+    eps: float = 1e-3
+
+
+class FedAvgEngine:
+    """Owns the symmetric buffers of one rank and runs aggregation rounds.
+
+    Attributes
+    ----------
+    w : torch.Tensor
+        fp32 parameter buffer of this node (length ``n``) living in symmetric memory.  The local
+        model's parameters are views into it; after :meth:`aggregate` it holds the new global model.
+    upload : torch.Tensor
+        contribution buffer (aliases ``w`` in ``weights_f32`` mode).
+    """
+
+    def __init__(self, n_params: int, rank: int = 0, world: int = 1, device="cpu", *, data_plane: str = "auto",
+                 server_mode: str = "sharded", server_opt: ServerOptConfig | None = None, upload: str = "weights_f32",
+                 shadow_bf16: bool = False, multicast: bool | str = "auto", timeout_ms: float = 20000.0,
+                 process_group=None):
+        assert upload in UPLOAD_MODES and server_mode in ("central", "sharded")
+        self.rank, self.world = rank, world
+        self.device = torch.device(device)
+        self.server_mode = server_mode
+        self.opt = server_opt or ServerOptConfig()
+        self.upload_mode = upload
+        self.pg = process_group
+        if data_plane == "auto":
+            data_plane = "native" if self.device.type == "cuda" else "collective"
+        self.data_plane = data_plane
+        self.n = (n_params + 7) // 8 * 8
+        self.n_real = n_params
+        self.epoch = 0
+        self.server_step = 0
+        self.last_status = 0
+
+        if data_plane == "native":
+            assert self.device.type == "cuda"
+            from ..ops import native
+
+            self._C = native()
+            self.heap = SymmetricHeap(rank, world, self.device)
+            want_mc = (multicast is True) or (multicast == "auto")
+            self._w_buf = self.heap.alloc(self.n * 4, multicast=want_mc)
+            self.w = self._w_buf.view(torch.float32, self.n)
+            if upload == "weights_f32":
+                self._up_buf = self._w_buf
+                self.upload = self.w
+            else:
+                esz = 4 if upload == "delta_f32" else 2
+                self._up_buf = self.heap.alloc(self.n * esz, multicast=want_mc)
+                self.upload = self._up_buf.view(torch.float32 if esz == 4 else torch.bfloat16, self.n)
+            self._shadow_buf = self.heap.alloc(self.n * 2, multicast=want_mc) if shadow_bf16 else None
+            self.shadow = self._shadow_buf.view(torch.bfloat16, self.n) if shadow_bf16 else None
+            self._pad_buf = self.heap.alloc(PAD_WORDS * 4, multicast=False)
+            self.pad = self._pad_buf.view(torch.int32, PAD_WORDS)
+            self.use_multicast = bool(self._w_buf.mc_ptr) and bool(self._up_buf.mc_ptr) and want_mc
+            self._cta_counter = torch.zeros(4, dtype=torch.int32, device=self.device)
+            clock_khz = torch.cuda.get_device_properties(self.device).clock_rate if hasattr(
+                torch.cuda.get_device_properties(self.device), "clock_rate") else 1_965_000
+            self.timeout_cycles = int(timeout_ms * clock_khz)
+        else:
+            self.heap = None
+            self.w = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+            if upload == "weights_f32":
+                self.upload = self.w
+            else:
+                self.upload = torch.zeros(self.n, dtype=torch.float32 if upload == "delta_f32" else torch.bfloat16,
+                                          device=self.device)
+            self.shadow = torch.zeros(self.n, dtype=torch.bfloat16, device=self.device) if shadow_bf16 else None
+            self.use_multicast = False
+        # server state (fp32 master + optimizer moments). Full-size for simplicity; only the
+        # owned slice is touched.
+        self.n_reducers = 1 if server_mode == "central" else world
+        chunk = (self.n + self.n_reducers - 1) // self.n_reducers
+        chunk = (chunk + 7) // 8 * 8
+        self.lo = min(self.n, rank * chunk) if rank < self.n_reducers else 0
+        self.hi = min(self.n, self.lo + chunk) if rank < self.n_reducers else 0
+        is_reducer = rank < self.n_reducers
+        self.w_global = torch.zeros(self.n if is_reducer else 8, dtype=torch.float32, device=self.device)
+        need_m = self.opt.name in ("fedavgm", "fedadam") and is_reducer
+        need_v = self.opt.name == "fedadam" and is_reducer
+        self.opt_m = torch.zeros(self.n if need_m else 8, dtype=torch.float32, device=self.device)
+        self.opt_v = torch.zeros(self.n if need_v else 8, dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def is_reducer(self) -> bool:
+        return self.rank < self.n_reducers
+
+    def nvlink_bytes_per_round(self) -> int:
+        """Bytes this rank must pull + push over NVLink in one native round (roofline numerator)."""
+        esz = 2 if self.upload_mode == "delta_bf16" else 4
+        mine = self.hi - self.lo
+        if self.world == 1:
+            return 0
+        pull = mine * esz * (1 if self.use_multicast else self.world - 1)
+        push = mine * 4 * (1 if self.use_multicast else self.world - 1)
+        return pull + push
+
+    def _weights_vector(self, weight: float | Sequence[float]) -> List[float]:
+        """All ranks must pass the same vector; a scalar means 'everyone reports with this n_i'."""
+        if isinstance(weight, (int, float)):
+            return [float(weight)] * self.world
+        w = [float(x) for x in weight]
+        assert len(w) == self.world
+        return w
+
+    # ------------------------------------------------------------------ rounds
+    @torch.no_grad()
+    def initialize_global(self) -> None:
+        """Round 0: the model in rank 0's ``w`` becomes the global model on every node."""
+        weights = [1.0] + [0.0] * (self.world - 1)
+        saved = (self.opt, self.upload_mode, self.upload)
+        self.opt = ServerOptConfig("fedavg", 1.0)
+        self.upload_mode, self.upload = "weights_f32", self.w
+        try:
+            self._aggregate(weights, count_step=False, force_p2p=True)
+        finally:
+            self.opt, self.upload_mode, self.upload = saved
+        if self.shadow is not None:
+            self.shadow.copy_(self.w.to(torch.bfloat16))
+
+    @torch.no_grad()
+    def aggregate(self, weight: float | Sequence[float] = 1.0) -> None:
+        """One federated aggregation: after it returns (stream order) ``w`` is the new global."""
+        self._aggregate(self._weights_vector(weight), count_step=True)
+
+    def _aggregate(self, weights: List[float], count_step: bool, force_p2p: bool = False) -> None:
+        total = sum(weights)
+        assert total > 0, "at least one node must report"
+        self.epoch += 1
+        if count_step:
+            self.server_step += 1
+        t = max(self.server_step, 1)
+        bias1 = 1.0 / (1.0 - self.opt.beta1 ** t)
+        bias2 = 1.0 / (1.0 - self.opt.beta2 ** t)
+        if self.data_plane == "native":
+            all_report = all(w > 0 for w in weights)
+            equal = all_report and len(set(weights)) == 1
+            mode_idx = UPLOAD_MODES.index(self.upload_mode)
+            is_delta = mode_idx != 0
+            # the in-switch reduction sums un-weighted, so it is used when all n_i are equal (the
+            # mean is then sum/world); unequal n_i take the P2P path where the reducer applies n_i.
+            use_mc_ld = self.use_multicast and equal and not force_p2p
+            prescaled = False
+            eff_weights = weights
+            inv_total = 1.0 / total
+            if use_mc_ld:
+                inv_total = 1.0 / self.world
+            from ..ops import stream_ptr
+
+            up, wb = self._up_buf, self._w_buf
+            null8 = [0] * 8
+            self._C.fedavg_round(
+                up.peer(), wb.peer(), self._shadow_buf.peer() if self._shadow_buf else null8, self._pad_buf.peer(),
+                up.mc() if use_mc_ld else 0, wb.mc() if (self.use_multicast and not force_p2p) else 0,
+                self._shadow_buf.mc() if (self._shadow_buf and self.use_multicast and not force_p2p) else 0,
+                self.w_global.data_ptr(), self.opt_m.data_ptr(), self.opt_v.data_ptr(), eff_weights,
+                self.lo, self.hi, self.rank, self.world, self.n_reducers, self.epoch, is_delta, prescaled,
+                SERVER_OPTS[self.opt.name], self.opt.lr, self.opt.beta1, self.opt.beta2, self.opt.eps, bias1, bias2,
+                inv_total, self.timeout_cycles, self._cta_counter.data_ptr(),
+                1 if self.upload_mode == "delta_bf16" else 0,
+                148 if (self.is_reducer and self.hi > self.lo) else 1, stream_ptr())
+        else:
+            self._aggregate_collective(weights, total, bias1, bias2)
+
+    # -- baseline / CPU data plane -------------------------------------------------------------
+    def _aggregate_collective(self, weights, total, bias1, bias2) -> None:
+        import torch.distributed as dist
+
+        is_delta = self.upload_mode != "weights_f32"
+        my_w = weights[self.rank]
+        if my_w == 0:
+            contrib = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        elif is_delta:
+            contrib = self.upload.float() * my_w
+        else:
+            contrib = self.w * my_w
+        if self.world > 1:
+            if self.server_mode == "central":
+                dist.reduce(contrib, dst=0, group=self.pg)
+            else:
+                dist.all_reduce(contrib, group=self.pg)
+        if self.is_reducer:
+            lo, hi = (0, self.n) if self.server_mode == "central" else (self.lo, self.hi)
+            mean = contrib[lo:hi] / total
+            wg = self.w_global[lo:hi]
+            d = mean if is_delta else mean - wg
+            o = self.opt
+            if o.name == "fedavgm":
+                m = self.opt_m[lo:hi]
+                m.mul_(o.beta1).add_(d)
+                wg.add_(m, alpha=o.lr)
+            elif o.name == "fedadam":
+                m, v = self.opt_m[lo:hi], self.opt_v[lo:hi]
+                m.mul_(o.beta1).add_(d, alpha=1 - o.beta1)
+                v.mul_(o.beta2).addcmul_(d, d, value=1 - o.beta2)
+                wg.add_((m * bias1) / ((v * bias2).sqrt() + o.eps), alpha=o.lr)
+            else:
+                wg.add_(d, alpha=o.lr)
+        if self.server_mode == "central":
+            if self.rank == 0:
+                self.w.copy_(self.w_global)
+            if self.world > 1:
+                dist.broadcast(self.w, src=0, group=self.pg)
+        else:
+            if self.world > 1:
+                out = torch.zeros_like(self.w)
+                out[self.lo:self.hi] = self.w_global[self.lo:self.hi]
+                dist.all_reduce(out, group=self.pg)
+                self.w.copy_(out)
+            else:
+                self.w.copy_(self.w_global)
+        if self.shadow is not None:
+            self.shadow.copy_(self.w.to(torch.bfloat16))
+
+    # ------------------------------------------------------------------ fault handling
+    def poll_status(self) -> int:
+        """Non-zero when a kernel wait timed out (a peer died / was stopped mid-round)."""
+        if self.data_plane != "native":
+            return 0
+        from ..ops import native
+
+        self.last_status = int(self.pad[native().PAD_STATUS].item())
+        return self.last_status
+
+    def abort(self) -> None:
+        """Raise the abort flag on this rank's pad: every kernel waiting on it returns promptly."""
+        if self.data_plane == "native":
+            from ..ops import native
+
+            self.pad[native().PAD_ABORT] = 1
+
+    # ------------------------------------------------------------------ checkpoint
+    def state_dict(self) -> dict:
+        return {"w_global": self.w_global, "opt_m": self.opt_m, "opt_v": self.opt_v, "server_step": self.server_step,
+                "lo": self.lo, "hi": self.hi, "n": self.n}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.w_global.copy_(sd["w_global"])
+        self.opt_m.copy_(sd["opt_m"])
+        self.opt_v.copy_(sd["opt_v"])
+        self.server_step = int(sd["server_step"])
+
+    def close(self) -> None:
+        if self.heap is not None:
+            self.w = self.upload = self.shadow = self.pad = None  # type: ignore[assignment]
+            self.heap.close()
+            self.heap = None
+
+
+# ----------------------------------------------------------------------------------------------
+# K3: small-message aggregation (GLM coefficients, the 1k-parameter vector)
+# ----------------------------------------------------------------------------------------------
+class SmallAggregator:
+    """One-shot weighted all-reduce for payloads <= 64 KB (latency-bound path, csrc K3)."""
+
+    MAX_FLOATS = 16384
+
+    def __init__(self, n_floats: int, rank: int = 0, world: int = 1, device="cpu", process_group=None,
+                 timeout_ms: float = 20000.0):
+        assert n_floats <= self.MAX_FLOATS
+        self.n = (n_floats + 3) // 4 * 4
+        self.rank, self.world, self.device = rank, world, torch.device(device)
+        self.pg = process_group
+        self.epoch = 0
+        self.native = self.device.type == "cuda"
+        if self.native:
+            from ..ops import native
+
+            self._C = native()
+            self.heap = SymmetricHeap(rank, world, self.device)
+            self._slots = self.heap.alloc(2 * self.n * 4, multicast=False)      # double-buffered by epoch parity
+            self._pad_buf = self.heap.alloc(PAD_WORDS * 4, multicast=False)
+            self.slots = self._slots.view(torch.float32, 2 * self.n).view(2, self.n)
+            self.timeout_cycles = int(timeout_ms * 1_965_000)
+        else:
+            self.heap = None
+            self.slots = torch.zeros(2, self.n, dtype=torch.float32)
+        self.out = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+
+    def slot(self) -> torch.Tensor:
+        """The buffer the caller fills with its payload for the NEXT all-reduce."""
+        return self.slots[(self.epoch + 1) & 1]
+
+    @torch.no_grad()
+    def allreduce(self, weights: float | Sequence[float] = 1.0, normalize: bool = True) -> torch.Tensor:
+        w = [float(weights)] * self.world if isinstance(weights, (int, float)) else [float(x) for x in weights]
+        total = sum(w) if normalize else 1.0
+        self.epoch += 1
+        par = self.epoch & 1
+        if self.native:
+            from ..ops import stream_ptr
+
+            off = par * self.n * 4
+            self._C.small_allreduce(self._slots.peer(off), self._pad_buf.peer(), w, self.out.data_ptr(), self.n,
+                                    self.rank, self.world, self.epoch, 1.0 / total, self.timeout_cycles, stream_ptr())
+        else:
+            import torch.distributed as dist
+
+            contrib = self.slots[par] * w[self.rank]
+            if self.world > 1:
+                dist.all_reduce(contrib, group=self.pg)
+            self.out.copy_(contrib / total)
+        return self.out
+
+    def close(self):
+        if self.heap is not None:
+            self.slots = None  # type: ignore[assignment]
+            self.heap.close()
+            self.heap = None

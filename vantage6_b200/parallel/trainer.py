@@ -1,0 +1,217 @@
+"""FederatedTrainer -- the public training API of one federated node (one GPU, one process).
+
+    trainer = FederatedTrainer(model, forward_loss, rank=r, world=W, device=dev, ...)
+    trainer.initialize_global()                    # rank 0's init becomes everyone's model
+    loss = trainer.run_round(host_or_device_batches, n_samples)   # E local steps + aggregation
+
+A round = ``len(batches)`` local steps (forward, backward, fused flat optimizer -- captured in
+ONE CUDA graph and replayed per step, because a ResNet-50 step is ~500 small launches) followed
+by ONE fused aggregation kernel (parallel/fedavg.py).  Input batches may live in pinned host
+memory: they are copied host->device on a side stream, double-buffered, overlapping compute.
+
+In vantage6 terms this object is what the ``fedavg`` algorithm's node-side partial function
+drives (algorithm/builtin/fedavg.py); task dispatch and result bookkeeping stay in the
+server/node control plane.
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+
+from ..models.flat import FlatModel, flat_size
+from ..ops import optim as fused_optim
+from .fedavg import FedAvgEngine, ServerOptConfig
+
+
+class FederatedTrainer:
+    def __init__(self, model: nn.Module, forward_loss: Callable[[nn.Module, torch.Tensor, torch.Tensor], torch.Tensor],
+                 *, rank: int = 0, world: int = 1, device="cpu", optimizer: str = "sgd", lr: float = 0.1,
+                 momentum: float = 0.9, weight_decay: float = 0.0, betas: Tuple[float, float] = (0.9, 0.999),
+                 eps: float = 1e-8, server_mode: str = "sharded", server_opt: Optional[ServerOptConfig] = None,
+                 upload: str = "weights_f32", data_plane: str = "auto", multicast="auto",
+                 use_cuda_graph: Optional[bool] = None, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
+                 max_grad_norm: Optional[float] = None, process_group=None, include_buffers: bool = True,
+                 shadow_bf16: bool = False, fused_local_optimizer: bool = True):
+        self.rank, self.world = rank, world
+        self.device = torch.device(device)
+        self.model = model.to(self.device)
+        self.forward_loss = forward_loss
+        self.amp_dtype = amp_dtype if self.device.type == "cuda" else None
+        self.max_grad_norm = max_grad_norm
+        n = flat_size(self.model, include_buffers)
+        self.engine = FedAvgEngine(n, rank, world, self.device, data_plane=data_plane, server_mode=server_mode,
+                                   server_opt=server_opt, upload=upload, multicast=multicast,
+                                   process_group=process_group, shadow_bf16=shadow_bf16)
+        self.fm = FlatModel(self.model, storage=self.engine.w, shadow=self.engine.shadow,
+                            include_buffers=include_buffers)
+        self.upload_mode = upload
+        self.w_ref = torch.zeros_like(self.fm.params) if upload != "weights_f32" else None
+        self.fused_local_optimizer = fused_local_optimizer
+        if fused_local_optimizer:
+            if optimizer == "sgd":
+                self.opt = fused_optim.FlatSGD(self.fm.params, lr=lr, momentum=momentum, weight_decay=weight_decay)
+            elif optimizer == "adamw":
+                self.opt = fused_optim.FlatAdamW(self.fm.params, lr=lr, beta1=betas[0], beta2=betas[1], eps=eps,
+                                                 weight_decay=weight_decay)
+            else:
+                raise ValueError(optimizer)
+            self.torch_opt = None
+        else:       # baseline: stock torch.optim over the per-tensor views
+            params = [p for p in self.model.parameters() if p.requires_grad]
+            self.torch_opt = (torch.optim.SGD(params, lr=lr, momentum=momentum, weight_decay=weight_decay)
+                              if optimizer == "sgd" else
+                              torch.optim.AdamW(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+            self.opt = None
+        self.use_graph = (self.device.type == "cuda") if use_cuda_graph is None else use_cuda_graph
+        self._graphs: dict = {}
+        self._static_x: Optional[torch.Tensor] = None
+        self._static_y: Optional[torch.Tensor] = None
+        self.loss_sum = torch.zeros((), dtype=torch.float32, device=self.device)
+        self._clip_scratch = torch.zeros(2, dtype=torch.float32, device=self.device) if max_grad_norm else None
+        self.copy_stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        self._staging: List[Tuple[torch.Tensor, torch.Tensor]] = []
+        self.kernel_launches_last_round = 0
+        self.rounds = 0
+
+    # ------------------------------------------------------------------ local step
+    def _step_body(self, x: torch.Tensor, y: torch.Tensor, variant: str) -> None:
+        self.fm.zero_grad()
+        ctx = torch.autocast("cuda", dtype=self.amp_dtype) if self.amp_dtype is not None else contextlib.nullcontext()
+        with ctx:
+            loss = self.forward_loss(self.model, x, y)
+        loss.backward()
+        self.loss_sum += loss.detach().float()
+        if self.torch_opt is not None:
+            if self.max_grad_norm:
+                torch.nn.utils.clip_grad_norm_([p for p in self.model.parameters() if p.requires_grad], self.max_grad_norm)
+            self.torch_opt.step()
+            return
+        gs = None
+        if self.max_grad_norm:
+            gs = fused_optim.clip_grad_coef(self.fm.grad, self.max_grad_norm, self._clip_scratch)
+        kw = {}
+        if self.upload_mode != "weights_f32":
+            publish = fused_optim.PUBLISH_DELTA_F32 if self.upload_mode == "delta_f32" else fused_optim.PUBLISH_DELTA_BF16
+            first, last = variant in ("first", "only"), variant in ("last", "only")
+            kw = dict(w_ref=self.w_ref, save_ref=first, upload=self.engine.upload[: self.fm.n_trainable] if last else None,
+                      publish=publish if last else fused_optim.PUBLISH_NONE, contrib_scale=1.0)
+        shadow = self.engine.shadow[: self.fm.n_trainable] if self.engine.shadow is not None else None
+        if isinstance(self.opt, fused_optim.FlatSGD):
+            self.opt.step(self.fm.grad, grad_scale=gs, shadow=shadow, first_momentum_step=False if self.use_graph else None, **kw)
+        else:
+            self.opt.step(self.fm.grad, grad_scale=gs, shadow=shadow, **kw)
+
+    def _variant(self, i: int, n: int) -> str:
+        if self.upload_mode == "weights_f32":
+            return "mid"
+        if n == 1:
+            return "only"
+        return "first" if i == 0 else ("last" if i == n - 1 else "mid")
+
+    def _capture(self, variant: str, x: torch.Tensor, y: torch.Tensor) -> torch.cuda.CUDAGraph:
+        if self._static_x is None:
+            self._static_x, self._static_y = x.clone(), y.clone()
+        # snapshot mutable state, warm up on a side stream, restore
+        snap = (self.engine.w.clone(), self.opt.state_dict() if self.opt else None, self.loss_sum.clone())
+        snap_opt = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in snap[1].items()} if snap[1] else None
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._step_body(self._static_x, self._static_y, variant)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        pool = next(iter(self._graphs.values())).pool() if self._graphs else None
+        with torch.cuda.graph(g, pool=pool):
+            self._step_body(self._static_x, self._static_y, variant)
+        self.engine.w.copy_(snap[0])
+        if snap_opt is not None:
+            self.opt.load_state_dict(snap_opt)
+        self.loss_sum.copy_(snap[2])
+        return g
+
+    def local_step(self, x: torch.Tensor, y: torch.Tensor, i: int = 0, n: int = 1) -> None:
+        """One local optimisation step on device-resident (x, y)."""
+        variant = self._variant(i, n)
+        if self.use_graph and not isinstance(self.opt, fused_optim.FlatAdamW) and self.torch_opt is None:
+            if variant not in self._graphs:
+                self._graphs[variant] = self._capture(variant, x, y)
+            self._static_x.copy_(x, non_blocking=True)
+            self._static_y.copy_(y, non_blocking=True)
+            self._graphs[variant].replay()
+            if self.opt is not None:
+                self.opt.steps += 1
+        else:
+            self._step_body(x, y, variant)
+
+    # ------------------------------------------------------------------ rounds
+    def initialize_global(self) -> None:
+        self.engine.initialize_global()
+
+    def _stage(self, k: int, x: torch.Tensor, y: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        while len(self._staging) <= k:
+            self._staging.append((torch.empty_like(x, device=self.device), torch.empty_like(y, device=self.device)))
+        return self._staging[k]
+
+    def run_round(self, batches: Sequence[Tuple[torch.Tensor, torch.Tensor]], n_samples: Optional[float] = None,
+                  weights: Optional[Sequence[float]] = None) -> torch.Tensor:
+        """E = len(batches) local steps, then the fused FedAvg aggregation.
+
+        ``batches`` may be pinned-host tensors (copied H2D on a side stream, double-buffered) or
+        device tensors.  Returns the mean local loss of the round as a device scalar; calling
+        ``.item()`` on it is the round's only device->host read.
+        """
+        n = len(batches)
+        if n_samples is None:
+            n_samples = float(sum(b[0].shape[0] for b in batches))
+        self.loss_sum.zero_()
+        cur = torch.cuda.current_stream(self.device) if self.device.type == "cuda" else None
+        on_host = n > 0 and batches[0][0].device.type == "cpu" and self.device.type == "cuda"
+        events: List[Optional[torch.cuda.Event]] = [None, None]
+        done: List[Optional[torch.cuda.Event]] = [None, None]
+
+        def prefetch(i: int):
+            k = i & 1
+            xs, ys = self._stage(k, *batches[i])
+            with torch.cuda.stream(self.copy_stream):
+                if done[k] is not None:
+                    self.copy_stream.wait_event(done[k])      # staging slot no longer read by compute
+                xs.copy_(batches[i][0], non_blocking=True)
+                ys.copy_(batches[i][1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+            events[k] = ev
+
+        if on_host:
+            prefetch(0)
+        for i in range(n):
+            if on_host:
+                if i + 1 < n:
+                    prefetch(i + 1)
+                k = i & 1
+                cur.wait_event(events[k])
+                x, y = self._staging[k]
+            else:
+                x, y = batches[i]
+            self.local_step(x, y, i, n)
+            if on_host:
+                d = torch.cuda.Event()
+                d.record(cur)
+                done[i & 1] = d
+        agg_w = weights if weights is not None else float(n_samples)
+        self.engine.aggregate(agg_w)
+        self.rounds += 1
+        return self.loss_sum / max(n, 1)
+
+    def launches_per_round(self, n_steps: int) -> int:
+        """Number of OUR kernels launched in one round (bench.py ``gpu_launches``): per local step the
+        fused flat optimizer (+2 for grad clipping); per round the fused aggregation kernel."""
+        per_step = (1 if self.opt is not None else 0) + (2 if (self.max_grad_norm and self.opt is not None) else 0)
+        return n_steps * per_step + (1 if self.engine.data_plane == "native" else 0)
+
+    def close(self) -> None:
+        self._graphs.clear()
+        self.engine.close()
