@@ -63,7 +63,7 @@ def main():
     nbytes = 256 << 20
     buf = heap.alloc(nbytes, multicast=True)
     res["multicast_bound"] = bool(buf.mc_ptr)
-    x = buf.view(torch.float32)
+    x = buf.view(torch.float32, nbytes // 4)
     x.fill_(float(rank + 1))
     torch.cuda.synchronize()
     dist.barrier()
@@ -129,7 +129,7 @@ def main():
                                 e.upload.copy_(step.to(e.upload.dtype))
                             e.aggregate(weights)
                         torch.cuda.synchronize()
-                        tol = dict(rtol=3e-2, atol=3e-3) if upload == "delta_bf16" else dict(rtol=1e-4, atol=1e-5)
+                        tol = dict(rtol=3e-2, atol=3e-3) if upload == "delta_bf16" else dict(rtol=2e-4, atol=1e-4)
                         torch.testing.assert_close(e1.w, e2.w, **tol)
                         checks += 1
                     assert e1.poll_status() == 0

@@ -92,7 +92,7 @@ def test_layernorm_fwd_bwd(dev, rows, cols, dtype, with_res):
     g2, b2 = gamma.detach().clone().requires_grad_(), beta.detach().clone().requires_grad_()
     hf = xf + rf if with_res else xf
     if dtype == torch.bfloat16 and with_res:
-        hf = hf.to(dtype).float() + (hf - hf.detach())       # kernel rounds the residual stream to bf16
+        hf = hf + (hf.to(dtype).float() - hf).detach()          # kernel rounds the residual stream to bf16
     yr = torch.nn.functional.layer_norm(hf, (cols,), g2, b2, 1e-5)
     (yr * dy.float()).sum().add((hf * dh.float()).sum() if with_res else 0).backward()
     tol = dict(rtol=3e-2, atol=3e-2) if dtype == torch.bfloat16 else dict(rtol=1e-4, atol=1e-4)
@@ -224,7 +224,7 @@ def test_fedavg_engine_world1_matches_collective(dev, opt, upload):
                 e.upload.copy_(step.to(e.upload.dtype))
             e.aggregate(5.0)
         torch.cuda.synchronize()
-        tol = dict(rtol=2e-2, atol=2e-3) if upload == "delta_bf16" else dict(rtol=1e-5, atol=1e-5)
+        tol = dict(rtol=2e-2, atol=2e-3) if upload == "delta_bf16" else dict(rtol=1e-4, atol=1e-4)
         torch.testing.assert_close(e1.w, e2.w, **tol)
     assert e1.poll_status() == 0
     e1.close()

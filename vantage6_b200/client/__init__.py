@@ -1,0 +1,379 @@
+"""Client library (the ``vantage6-client`` package the reference CLI depends on: reference
+vantage6/cli/node.py:43,781-784 ``Client(host, port, api_path).authenticate(user, pw)``,
+``.whoami.organization_name/.organization_id``, ``.request(path, method=, json=)``).
+
+* ``ClientBase``     -- REST + JWT plumbing, token refresh, optional RSA encryption.
+* ``UserClient``     -- researcher-facing API: ``client.task.create(...)``,
+  ``client.wait_for_results(task_id)``, ``client.result.from_task(...)``, plus
+  organization / collaboration / node / user / role / rule / util sub-clients.
+  ``Client`` is an alias (vantage6 3.x name).
+* ``ContainerClient``-- what a running algorithm's *master* uses (through the node's proxy) to
+  create sub-tasks and collect their results.
+"""
+from __future__ import annotations
+
+import json as _json
+import logging
+import time
+from types import SimpleNamespace
+from typing import Any, Dict, List, Optional, Union
+
+import requests
+
+from ..common import STRING_ENCODING, bytes_to_base64s  # noqa: F401
+from ..common.encryption import CryptorBase, DummyCryptor, RSACryptor
+from ..common.serialization import deserialize, serialize
+
+module_name = __name__.split(".")[-1]
+
+
+class ServerError(Exception):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"[{status}] {msg}")
+        self.status, self.msg = status, msg
+
+
+class ClientBase:
+    def __init__(self, host: str, port: Optional[int] = 5000, path: str = "/api"):
+        self.log = logging.getLogger(module_name)
+        self.__host, self.__port, self.__api_path = host.rstrip("/"), port, path
+        self._access_token: Optional[str] = None
+        self.__refresh_token: Optional[str] = None
+        self.__refresh_url: Optional[str] = None
+        self.cryptor: Optional[CryptorBase] = None
+        self.whoami: Optional[SimpleNamespace] = None
+        self._session = requests.Session()
+        self._session.trust_env = False          # never route loopback traffic through a proxy
+
+    # -- addresses ---------------------------------------------------------------------------
+    @property
+    def host(self):
+        return self.__host
+
+    @property
+    def port(self):
+        return self.__port
+
+    @property
+    def path(self):
+        return self.__api_path
+
+    @property
+    def base_path(self) -> str:
+        if self.__port:
+            return f"{self.host}:{self.port}{self.__api_path}"
+        return f"{self.host}{self.__api_path}"
+
+    def generate_path_to(self, endpoint: str) -> str:
+        if endpoint.startswith("/"):
+            return self.base_path + endpoint
+        return self.base_path + "/" + endpoint
+
+    @property
+    def headers(self) -> Dict[str, str]:
+        return {"Authorization": "Bearer " + self._access_token} if self._access_token else {}
+
+    @property
+    def token(self):
+        return self._access_token
+
+    # -- requests ----------------------------------------------------------------------------
+    def request(self, endpoint: str, json: dict = None, method: str = "get", params: dict = None,
+                first_try: bool = True, timeout: float = 70.0):
+        url = self.generate_path_to(endpoint)
+        rest = {"get": self._session.get, "post": self._session.post, "put": self._session.put,
+                "patch": self._session.patch, "delete": self._session.delete}.get(method.lower(), self._session.get)
+        response = rest(url, json=json, headers=self.headers, params=params, timeout=timeout)
+        if response.status_code > 210:
+            try:
+                msg = response.json().get("msg", response.text)
+            except Exception:  # noqa: BLE001
+                msg = response.text
+            if response.status_code == 401 and first_try and self.__refresh_token and "expired" in str(msg).lower():
+                self.refresh_token()
+                return self.request(endpoint, json, method, params, first_try=False)
+            raise ServerError(response.status_code, str(msg))
+        return response.json()
+
+    # -- authentication ----------------------------------------------------------------------
+    def authenticate(self, credentials: dict, path: str = "token/user") -> None:
+        data = self.request(path, json=credentials, method="post")
+        self._access_token = data.get("access_token")
+        self.__refresh_token = data.get("refresh_token")
+        self.__refresh_url = data.get("refresh_url")
+        self._auth_reply = data
+
+    def refresh_token(self) -> None:
+        assert self.__refresh_token, "Refresh token not found, did you authenticate?"
+        url = f"{self.host}:{self.port}{self.__refresh_url}" if self.port else f"{self.host}{self.__refresh_url}"
+        r = self._session.post(url, headers={"Authorization": "Bearer " + self.__refresh_token}, timeout=30)
+        if r.status_code != 200:
+            raise ServerError(r.status_code, "Authentication Error!")
+        self._access_token = r.json()["access_token"]
+
+    # -- encryption --------------------------------------------------------------------------
+    def setup_encryption(self, private_key_file: Optional[str]) -> None:
+        """``None`` disables encryption (un-encrypted collaboration)."""
+        if private_key_file is None:
+            self.cryptor = DummyCryptor()
+        else:
+            self.cryptor = RSACryptor(private_key_file)
+
+    def _encrypt_input(self, blob: bytes, organization_id: int) -> str:
+        assert self.cryptor is not None, "Encryption has not yet been setup! (call setup_encryption)"
+        if isinstance(self.cryptor, RSACryptor):
+            org = self.request(f"organization/{organization_id}")
+            pub = org.get("public_key")
+            if not pub:
+                raise ValueError(f"organization {organization_id} has no public key; cannot encrypt its input")
+            return self.cryptor.encrypt_bytes_to_str(blob, pub)
+        return self.cryptor.encrypt_bytes_to_str(blob, "")
+
+    def _decrypt_result(self, value: Optional[str]) -> Any:
+        if value is None or value == "":
+            return None
+        assert self.cryptor is not None, "Encryption has not yet been setup! (call setup_encryption)"
+        try:
+            return deserialize(self.cryptor.decrypt_str_to_bytes(value))
+        except Exception:  # noqa: BLE001 -- not one of ours (e.g. plain JSON from a fixture)
+            return value
+
+
+class UserClient(ClientBase):
+    """Researcher client."""
+
+    def __init__(self, host: str = "http://localhost", port: Optional[int] = 5000, path: str = "/api",
+                 verbose: bool = False):
+        super().__init__(host, port, path)
+        self.util = self.Util(self)
+        self.collaboration = self.Collaboration(self)
+        self.organization = self.Organization(self)
+        self.user = self.User(self)
+        self.result = self.Result(self)
+        self.task = self.Task(self)
+        self.role = self.Role(self)
+        self.node = self.Node(self)
+        self.rule = self.Rule(self)
+
+    def authenticate(self, username: str, password: str) -> None:  # type: ignore[override]
+        super().authenticate({"username": username, "password": password}, path="token/user")
+        user = self.request(self._auth_reply["user_url"][len(self.path):])
+        org = self.request(f"organization/{user['organization']['id']}")
+        self.whoami = SimpleNamespace(type_="user", id_=user["id"], name=user["username"],
+                                      organization_id=org["id"], organization_name=org["name"])
+        self.log.info("Successfully authenticated as %s (organization %s)", user["username"], org["name"])
+
+    def wait_for_results(self, task_id: int, sleep: float = 0.05, timeout: float = 600.0) -> List[Any]:
+        """Block until the task is complete, then return the decrypted results."""
+        t0 = time.time()
+        last = 0
+        while True:
+            task = self.request(f"task/{task_id}")
+            if task.get("complete"):
+                break
+            if time.time() - t0 > timeout:
+                raise TimeoutError(f"task {task_id} did not complete in {timeout}s")
+            try:    # push-style wake-up; falls back to polling on any error
+                ev = self.request("event", params={"since": last, "timeout": 5, "task_id": task_id}, timeout=15)
+                last = ev.get("last_id", last)
+            except Exception:  # noqa: BLE001
+                time.sleep(sleep)
+        return self.result.from_task(task_id)
+
+    # ---------------------------------------------------------------- sub clients
+    class SubClient:
+        def __init__(self, parent: "UserClient"):
+            self.parent = parent
+
+    class Util(SubClient):
+        def get_server_version(self) -> dict:
+            return self.parent.request("version")
+
+        def get_server_health(self) -> dict:
+            return self.parent.request("health")
+
+    class Collaboration(SubClient):
+        def list(self) -> List[dict]:
+            return self.parent.request("collaboration")
+
+        def get(self, id_: int) -> dict:
+            return self.parent.request(f"collaboration/{id_}")
+
+        def create(self, name: str, organizations: List[int], encrypted: bool = False) -> dict:
+            return self.parent.request("collaboration", method="post",
+                                       json={"name": name, "organization_ids": organizations, "encrypted": encrypted})
+
+        def update(self, id_: int, **fields) -> dict:
+            return self.parent.request(f"collaboration/{id_}", method="patch", json=fields)
+
+        def delete(self, id_: int) -> dict:
+            return self.parent.request(f"collaboration/{id_}", method="delete")
+
+    class Organization(SubClient):
+        def list(self) -> List[dict]:
+            return self.parent.request("organization")
+
+        def get(self, id_: Optional[int] = None) -> dict:
+            id_ = id_ if id_ is not None else self.parent.whoami.organization_id
+            return self.parent.request(f"organization/{id_}")
+
+        def create(self, name: str, **fields) -> dict:
+            return self.parent.request("organization", method="post", json={"name": name, **fields})
+
+        def update(self, id_: Optional[int] = None, **fields) -> dict:
+            id_ = id_ if id_ is not None else self.parent.whoami.organization_id
+            return self.parent.request(f"organization/{id_}", method="patch", json=fields)
+
+    class User(SubClient):
+        def list(self) -> List[dict]:
+            return self.parent.request("user")
+
+        def get(self, id_: Optional[int] = None) -> dict:
+            id_ = id_ if id_ is not None else self.parent.whoami.id_
+            return self.parent.request(f"user/{id_}")
+
+        def create(self, username: str, password: str, organization: Optional[int] = None, roles: List[int] = (),
+                   rules: List[int] = (), **fields) -> dict:
+            body = {"username": username, "password": password, "organization_id": organization, "roles": list(roles),
+                    "rules": list(rules), **fields}
+            return self.parent.request("user", method="post", json=body)
+
+        def update(self, id_: Optional[int] = None, **fields) -> dict:
+            id_ = id_ if id_ is not None else self.parent.whoami.id_
+            return self.parent.request(f"user/{id_}", method="patch", json=fields)
+
+        def delete(self, id_: int) -> dict:
+            return self.parent.request(f"user/{id_}", method="delete")
+
+    class Role(SubClient):
+        def list(self) -> List[dict]:
+            return self.parent.request("role")
+
+    class Rule(SubClient):
+        def list(self) -> List[dict]:
+            return self.parent.request("rule")
+
+    class Node(SubClient):
+        def list(self) -> List[dict]:
+            return self.parent.request("node")
+
+        def get(self, id_: int) -> dict:
+            return self.parent.request(f"node/{id_}")
+
+        def create(self, collaboration: int, organization: Optional[int] = None, name: Optional[str] = None) -> dict:
+            """Returns the node *including its api_key* (shown only once)."""
+            return self.parent.request("node", method="post",
+                                       json={"collaboration_id": collaboration, "organization_id": organization, "name": name})
+
+        def update(self, id_: int, **fields) -> dict:
+            return self.parent.request(f"node/{id_}", method="patch", json=fields)
+
+        def delete(self, id_: int) -> dict:
+            return self.parent.request(f"node/{id_}", method="delete")
+
+    class Task(SubClient):
+        def list(self, **filters) -> List[dict]:
+            return self.parent.request("task", params=filters or None)
+
+        def get(self, id_: int, include_results: bool = False) -> dict:
+            return self.parent.request(f"task/{id_}", params={"include": "results"} if include_results else None)
+
+        def create(self, collaboration: int, organizations: List[int], name: str, image: str, description: str = "",
+                   input: dict = None, data_format: str = "json", database: str = "default") -> dict:  # noqa: A002
+            """Create a task for ``organizations``; the serialized input is encrypted per
+            receiving organization when the collaboration is encrypted."""
+            assert self.parent.cryptor, "Encryption has not yet been setup!"
+            blob = serialize(input or {}, data_format)
+            orgs = [{"id": oid, "input": self.parent._encrypt_input(blob, oid)} for oid in organizations]
+            return self.parent.request("task", method="post", json={
+                "name": name, "image": image, "collaboration_id": collaboration, "description": description,
+                "organizations": orgs, "database": database})
+
+        def delete(self, id_: int) -> dict:
+            return self.parent.request(f"task/{id_}", method="delete")
+
+    class Result(SubClient):
+        def get(self, id_: int) -> dict:
+            r = self.parent.request(f"result/{id_}")
+            r["result"] = self.parent._decrypt_result(r.get("result"))
+            return r
+
+        def list(self, **filters) -> List[dict]:
+            return self.parent.request("result", params=filters or None)
+
+        def from_task(self, task_id: int) -> List[dict]:
+            rows = self.parent.request(f"task/{task_id}/result")
+            for r in rows:
+                r["result"] = self.parent._decrypt_result(r.get("result"))
+            return rows
+
+
+Client = UserClient
+
+
+class ContainerClient(ClientBase):
+    """Client used by an algorithm's *master* function.  It talks to the node's proxy server
+    (host/port from the environment the node prepared), which adds encryption and forwards to
+    the central server with the container token."""
+
+    def __init__(self, token: str, host: str, port: Optional[int], path: str = ""):
+        super().__init__(host, port, path)
+        self._access_token = token
+        import jwt
+
+        claims = _json.loads(jwt.decode(token, options={"verify_signature": False})["sub"])
+        self.image = claims.get("image")
+        self.host_node_id = claims.get("node_id")
+        self.collaboration_id = claims.get("collaboration_id")
+        self.organization_id = claims.get("organization_id")
+        self.task_id = claims.get("task_id")
+        self.cryptor = DummyCryptor()     # the proxy handles the real encryption
+        self.log.info("Container client for task %s in collaboration %s", self.task_id, self.collaboration_id)
+
+    def authenticate(self, *a, **k):  # type: ignore[override]
+        self.log.warning("Containers do not need to authenticate!")
+
+    def refresh_token(self):  # type: ignore[override]
+        self.log.warning("Containers cannot refresh their token!")
+
+    def get_results(self, task_id: int) -> List[Any]:
+        """Decoded outputs of all (finished) results of ``task_id``."""
+        rows = self.request(f"task/{task_id}/result")
+        out = []
+        for r in rows:
+            if r.get("result"):
+                out.append(deserialize(self.cryptor.str_to_bytes(r["result"])))
+        return out
+
+    def get_task(self, task_id: int) -> dict:
+        return self.request(f"task/{task_id}")
+
+    def create_new_task(self, input_: dict, organization_ids: List[int] = (), name: str = "subtask",
+                        description: Optional[str] = None, data_format: str = "json") -> dict:
+        self.log.debug("Creating new subtask for organizations %s", list(organization_ids))
+        blob = self.cryptor.bytes_to_str(serialize(input_, data_format))
+        orgs = [{"id": oid, "input": blob} for oid in organization_ids]
+        return self.request("task", method="post", json={
+            "name": name, "image": self.image, "collaboration_id": self.collaboration_id,
+            "description": description or f"task from container on node_id={self.host_node_id}", "organizations": orgs})
+
+    def wait_for_results(self, task_id: int, sleep: float = 0.05, timeout: float = 3600.0) -> List[Any]:
+        t0 = time.time()
+        while not self.get_task(task_id).get("complete"):
+            if time.time() - t0 > timeout:
+                raise TimeoutError(f"subtask {task_id} did not complete in {timeout}s")
+            time.sleep(sleep)
+        return self.get_results(task_id)
+
+    def get_organizations_in_my_collaboration(self) -> List[dict]:
+        return self.request(f"collaboration/{self.collaboration_id}/organization")
+
+    def get_algorithm_addresses(self, task_id: int) -> List[dict]:
+        """vantage6's VPN address book; on one NVSwitch box node-to-node traffic is symmetric
+        memory, so the 'address' of a peer algorithm is its rank in the rendezvous."""
+        nodes = self.request(f"collaboration/{self.collaboration_id}/node")
+        return [{"rank": i, "node_id": n["id"], "organization_id": n["organization"]["id"], "gpu": n.get("gpu")}
+                for i, n in enumerate(sorted(nodes, key=lambda n: n["id"]))]
+
+
+__all__ = ["ClientBase", "UserClient", "Client", "ContainerClient", "ServerError", "RSACryptor", "DummyCryptor"]

@@ -1,0 +1,69 @@
+"""Payload (de)serialisation for task inputs and results on the control plane.
+
+vantage6 3.x ships inputs/results as JSON (default) or pickle (legacy) blobs; algorithm outputs
+here are frequently numeric arrays, so the JSON flavour understands numpy arrays and torch
+tensors (encoded as ``{"__ndarray__": b64, "dtype", "shape"}``).  Large tensors should not use
+this path at all -- they stay in NVLink symmetric memory (parallel/symm.py).
+"""
+from __future__ import annotations
+
+import base64
+import json
+import pickle
+from typing import Any
+
+import numpy as np
+
+
+def _default(o: Any):
+    try:
+        import torch
+
+        if isinstance(o, torch.Tensor):
+            t = o.detach().cpu()
+            if t.dtype == torch.bfloat16:
+                t = t.float()
+            o = t.numpy()
+    except ImportError:  # pragma: no cover
+        pass
+    if isinstance(o, np.ndarray):
+        a = np.ascontiguousarray(o)
+        return {"__ndarray__": base64.b64encode(a.tobytes()).decode("ascii"), "dtype": str(a.dtype), "shape": list(a.shape)}
+    if isinstance(o, (np.integer,)):
+        return int(o)
+    if isinstance(o, (np.floating,)):
+        return float(o)
+    if isinstance(o, (np.bool_,)):
+        return bool(o)
+    if isinstance(o, bytes):
+        return {"__bytes__": base64.b64encode(o).decode("ascii")}
+    if isinstance(o, (set, tuple)):
+        return list(o)
+    raise TypeError(f"Object of type {type(o).__name__} is not JSON serializable")
+
+
+def _hook(d: dict):
+    if "__ndarray__" in d:
+        a = np.frombuffer(base64.b64decode(d["__ndarray__"]), dtype=np.dtype(d["dtype"])).reshape(d["shape"])
+        return a.copy()
+    if "__bytes__" in d:
+        return base64.b64decode(d["__bytes__"])
+    return d
+
+
+def serialize(obj: Any, data_format: str = "json") -> bytes:
+    if data_format == "json":
+        return json.dumps(obj, default=_default).encode("utf-8")
+    if data_format == "pickle":
+        return pickle.dumps(obj)
+    raise ValueError(f"unknown data format {data_format!r}")
+
+
+def deserialize(blob: bytes | str, data_format: str | None = None) -> Any:
+    if isinstance(blob, str):
+        blob = blob.encode("utf-8")
+    if data_format is None:
+        data_format = "json" if blob[:1] in (b"{", b"[", b'"') or blob[:1].isdigit() or blob[:4] in (b"null", b"true", b"fals") else "pickle"
+    if data_format == "json":
+        return json.loads(blob.decode("utf-8"), object_hook=_hook)
+    return pickle.loads(blob)

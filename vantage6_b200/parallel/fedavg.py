@@ -155,13 +155,17 @@ class FedAvgEngine:
     def initialize_global(self) -> None:
         """Round 0: the model in rank 0's ``w`` becomes the global model on every node."""
         weights = [1.0] + [0.0] * (self.world - 1)
-        saved = (self.opt, self.upload_mode, self.upload)
+        saved = (self.opt, self.upload_mode, self.upload, getattr(self, "_up_buf", None))
         self.opt = ServerOptConfig("fedavg", 1.0)
         self.upload_mode, self.upload = "weights_f32", self.w
+        if self.data_plane == "native":
+            self._up_buf = self._w_buf            # round 0 reads the weights themselves
         try:
             self._aggregate(weights, count_step=False, force_p2p=True)
         finally:
-            self.opt, self.upload_mode, self.upload = saved
+            self.opt, self.upload_mode, self.upload = saved[:3]
+            if self.data_plane == "native":
+                self._up_buf = saved[3]
         if self.shadow is not None:
             self.shadow.copy_(self.w.to(torch.bfloat16))
 
