@@ -104,8 +104,8 @@ def main():
     n = 1_000_003
     checks = 0
     for server_mode in ("sharded", "central"):
-        for upload in ("weights_f32", "delta_f32", "delta_bf16"):
-            for opt in ("fedavg", "fedavgm", "fedadam"):
+        for upload, opt in (("weights_f32", "fedavg"), ("delta_f32", "fedavgm"), ("delta_bf16", "fedadam")):
+            for _once in (0,):
                 for mc in ("auto", False):
                     e1 = FedAvgEngine(n, rank, world, dev, data_plane="native", server_mode=server_mode,
                                       server_opt=ServerOptConfig(opt, 0.5), upload=upload, multicast=mc)

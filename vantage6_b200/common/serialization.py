@@ -10,22 +10,19 @@ from __future__ import annotations
 import base64
 import json
 import pickle
+import sys
 from typing import Any
 
 import numpy as np
 
 
 def _default(o: Any):
-    try:
-        import torch
-
-        if isinstance(o, torch.Tensor):
-            t = o.detach().cpu()
-            if t.dtype == torch.bfloat16:
-                t = t.float()
-            o = t.numpy()
-    except ImportError:  # pragma: no cover
-        pass
+    torch = sys.modules.get("torch")        # never import torch here: it costs seconds per algorithm run
+    if torch is not None and isinstance(o, torch.Tensor):
+        t = o.detach().cpu()
+        if t.dtype == torch.bfloat16:
+            t = t.float()
+        o = t.numpy()
     if isinstance(o, np.ndarray):
         a = np.ascontiguousarray(o)
         return {"__ndarray__": base64.b64encode(a.tobytes()).decode("ascii"), "dtype": str(a.dtype), "shape": list(a.shape)}

@@ -1,0 +1,202 @@
+"""Transformer building blocks wired to the hand-written sm_100a ops.
+
+Parameter policy (mixed precision without autocast):
+* trainable parameters are fp32 and live in the flat master buffer (models/flat.py);
+* GEMM weights are *consumed* in bf16: either from the bf16 shadow buffer that the fused
+  optimizer (K7) and the aggregation kernel (K2) keep up to date -- no cast kernel in the step --
+  or from an on-the-fly cast when no shadow is attached (CPU / tests);
+* activations are bf16; norms read fp32 gamma/beta directly from the master buffer.
+
+``ShadowLinear`` runs its forward on the tcgen05 GEMM (ops/gemm.py); backward GEMMs (dX, dW) are
+plain library GEMMs (cuBLAS) and dW is emitted in fp32 straight into the flat gradient buffer.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+from torch import nn
+
+from ..ops import gemm as G
+from ..ops import norm as N
+
+
+def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """bf16 x bf16 -> fp32 (cuBLAS, fp32 output when the build supports it)."""
+    try:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    except TypeError:
+        return torch.mm(a, b).float()
+    except RuntimeError:
+        return torch.mm(a, b).float()
+
+
+class _ShadowLinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, w_bf16, act):
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        wb = w_bf16 if w_bf16 is not None else weight.detach().to(torch.bfloat16)
+        if x2.is_cuda:
+            pre = G.gemm_bf16(x2, wb, bias, G.ACT_NONE)
+        else:
+            pre = G.reference_linear(x2, wb, bias, G.ACT_NONE)
+        y = pre
+        if act == G.ACT_GELU:
+            y = torch.nn.functional.gelu(pre)
+        elif act == G.ACT_RELU:
+            y = torch.relu(pre)
+        ctx.save_for_backward(x2, wb, pre if act != G.ACT_NONE else None)
+        ctx.act, ctx.has_bias, ctx.xshape = act, bias is not None, x.shape
+        ctx.need_w = weight.requires_grad
+        return y.view(*x.shape[:-1], wb.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wb, pre = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if ctx.act == G.ACT_GELU:
+            p = pre.float()
+            dy2 = (dy2.float() * (0.5 * (1.0 + torch.erf(p * 0.7071067811865476))
+                                  + p * torch.exp(-0.5 * p * p) * 0.3989422804014327)).to(dy.dtype)
+        elif ctx.act == G.ACT_RELU:
+            dy2 = dy2 * (pre > 0)
+        dy2 = dy2.contiguous()
+        dx = torch.mm(dy2, wb).view(ctx.xshape) if ctx.needs_input_grad[0] else None
+        dw = _mm_f32(dy2.t(), x2) if ctx.need_w else None
+        db = dy2.float().sum(0) if ctx.has_bias else None
+        return dx, dw, db, None, None
+
+
+class ShadowLinear(nn.Module):
+    """nn.Linear with fp32 master weight, bf16 compute copy and optional fused activation."""
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, act: int = G.ACT_NONE,
+                 init_std: float = 0.02):
+        super().__init__()
+        self.in_features, self.out_features, self.act = in_features, out_features, act
+        self.weight = nn.Parameter(torch.empty(out_features, in_features).normal_(0.0, init_std))
+        self.bias = nn.Parameter(torch.zeros(out_features)) if bias else None
+        self.w_bf16: Optional[torch.Tensor] = None      # view into the shadow buffer (set by attach_shadow)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dtype != torch.bfloat16:
+            x = x.to(torch.bfloat16)
+        return _ShadowLinearFn.apply(x, self.weight, self.bias, self.w_bf16, self.act)
+
+
+class FrozenLinear(nn.Module):
+    """Frozen bf16 base weight (Llama LoRA): forward on the tcgen05 GEMM, dX on cuBLAS; the
+    weight is a buffer-less plain tensor so it is neither federated nor optimised."""
+
+    def __init__(self, in_features: int, out_features: int, device=None, init_std: float = 0.02):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        w = torch.empty(out_features, in_features, dtype=torch.bfloat16, device=device)
+        w.normal_(0.0, init_std)
+        self.weight_bf16 = w                      # deliberately not a Parameter / buffer
+
+    def _apply(self, fn, recurse=True):
+        super()._apply(fn, recurse)
+        self.weight_bf16 = fn(self.weight_bf16)
+        return self
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return _FrozenLinearFn.apply(x, self.weight_bf16)
+
+
+class _FrozenLinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w):
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        y = G.gemm_bf16(x2, w) if x2.is_cuda else G.reference_linear(x2, w)
+        ctx.save_for_backward(w)
+        ctx.xshape = x.shape
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        (w,) = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        return torch.mm(dy2, w).view(ctx.xshape), None
+
+
+class LoRALinear(nn.Module):
+    """y = x W^T + (alpha/r) (x A^T) B^T with W frozen; A,B are the federated parameters."""
+
+    def __init__(self, in_features: int, out_features: int, r: int = 16, alpha: float = 32.0, device=None):
+        super().__init__()
+        self.base = FrozenLinear(in_features, out_features, device=device)
+        self.lora_A = nn.Parameter(torch.empty(r, in_features).normal_(0.0, 1.0 / math.sqrt(in_features)))
+        self.lora_B = nn.Parameter(torch.zeros(out_features, r))
+        self.scaling = alpha / r
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        y = self.base(x)
+        a = torch.nn.functional.linear(x, self.lora_A.to(x.dtype))
+        return y + self.scaling * torch.nn.functional.linear(a, self.lora_B.to(x.dtype))
+
+
+class FusedLayerNorm(nn.Module):
+    def __init__(self, dim: int, eps: float = 1e-12):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+        self.bias = nn.Parameter(torch.zeros(dim))
+        self.eps = eps
+
+    def forward(self, x, residual=None):
+        """Returns LN(x + residual) (and the summed stream when ``residual`` is given)."""
+        y, h = N.layer_norm(x, self.weight, self.bias, self.eps, residual)
+        return (y, h) if residual is not None else y
+
+
+class FusedRMSNorm(nn.Module):
+    def __init__(self, dim: int, eps: float = 1e-5):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+        self.eps = eps
+
+    def forward(self, x, residual=None):
+        y, h = N.rms_norm(x, self.weight, self.eps, residual)
+        return (y, h) if residual is not None else y
+
+
+def attach_shadow(module: nn.Module, flat_model) -> int:
+    """Point every ``ShadowLinear.w_bf16`` at its slice of the flat bf16 shadow buffer."""
+    if flat_model.shadow is None:
+        return 0
+    views = flat_model.shadow_views()
+    n = 0
+    for name, m in module.named_modules():
+        if isinstance(m, ShadowLinear):
+            key = f"{name}.weight" if name else "weight"
+            if key in views:
+                m.w_bf16 = views[key]
+                n += 1
+    return n
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool, mask=None) -> torch.Tensor:
+    """q:[B,S,Hq,D] k,v:[B,S,Hkv,D] -> [B,S,Hq,D].
+
+    K4 (hand-written tcgen05 flash attention) is used when available (ops/attention.py);
+    otherwise the library SDPA kernel (same role as cuBLAS for plain GEMMs)."""
+    try:
+        from ..ops import attention as A
+
+        if q.is_cuda and A.available() and mask is None:
+            return A.flash_attention(q, k, v, causal)
+    except ImportError:
+        pass
+    Hq, Hkv = q.shape[2], k.shape[2]
+    qt, kt, vt = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
+    if Hkv != Hq:
+        rep = Hq // Hkv
+        kt = kt.repeat_interleave(rep, dim=1)
+        vt = vt.repeat_interleave(rep, dim=1)
+    o = torch.nn.functional.scaled_dot_product_attention(qt, kt, vt, attn_mask=mask, is_causal=causal and mask is None)
+    return o.transpose(1, 2)

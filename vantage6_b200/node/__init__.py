@@ -1,0 +1,312 @@
+"""Node runtime (``vnode-local start``: what the reference launches inside the node container,
+reference vantage6/cli/node.py:380-382; behaviour per SURVEY.md Appendix C).
+
+One node = one process pinned to one GPU.  It
+
+1. authenticates at the central server with its ``api_key`` (-> node JWT),
+2. sets up encryption (RSA private key vs the organization's public key at the server),
+3. starts the local proxy server for algorithm -> server traffic,
+4. syncs the results that were assigned while it was offline, then listens on the event
+   channel for new tasks of its collaboration,
+5. runs every assigned result's algorithm in an isolated child process with vantage6's
+   input/output/token file + environment contract (algorithm/wrapper.py) inside a per-run
+   temporary volume (``...-{run_id}-tmpvol``: reference vantage6/cli/context.py:140-141),
+6. PATCHes started_at / finished_at / result / log back,
+7. heartbeats (``last_seen``) and marks itself offline on shutdown.
+"""
+from __future__ import annotations
+
+import json
+import logging
+import os
+import queue
+import signal
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+from typing import Dict, Optional
+
+from .. import __version__
+from ..algorithm import resolve_image
+from ..client import ClientBase, ServerError
+from ..common import base64s_to_bytes, bytes_to_base64s
+from ..common.encryption import DummyCryptor, RSACryptor
+from ..runtime import runtime_dir
+from .proxy import ProxyServer
+
+log = logging.getLogger("node")
+
+
+def _now() -> str:
+    import datetime as dt
+
+    return dt.datetime.now(dt.timezone.utc).isoformat()
+
+
+class NodeClient(ClientBase):
+    """Server client with node (api_key) authentication."""
+
+    def authenticate(self, api_key: str, gpu: Optional[int] = None) -> None:  # type: ignore[override]
+        super().authenticate({"api_key": api_key, "gpu": gpu}, path="token/node")
+        node = self.request(self._auth_reply["node_url"][len(self.path):])
+        self.node_id = node["id"]
+        self.name = node["name"]
+        self.collaboration_id = node["collaboration"]["id"]
+        self.organization_id = node["organization"]["id"]
+        org = self.request(f"organization/{self.organization_id}")
+        self.organization_name = org["name"]
+
+
+class Node:
+    def __init__(self, ctx, heartbeat_s: float = 15.0):
+        self.ctx = ctx
+        self.config = ctx.config
+        self.heartbeat_s = heartbeat_s
+        self.client = NodeClient(self.config["server_url"], self.config.get("port"), self.config.get("api_path", "/api"))
+        self.proxy = ProxyServer(self)
+        self.queue: "queue.Queue[dict]" = queue.Queue()
+        self.running: Dict[int, subprocess.Popen] = {}
+        self._seen: set = set()
+        self._stop = threading.Event()
+        self._threads = []
+        self.cryptor = DummyCryptor()
+        self.gpu = self._gpu_index()
+        self._org_keys: Dict[int, Optional[str]] = {}
+
+    # ------------------------------------------------------------------ setup
+    def _gpu_index(self) -> Optional[int]:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis not in (None, ""):
+            try:
+                return int(vis.split(",")[0])
+            except ValueError:
+                return None
+        g = self.config.get("gpu") if hasattr(self.config, "get") else None
+        return int(g) if g is not None else None
+
+    def authenticate(self, retries: int = 60) -> None:
+        for attempt in range(retries):
+            try:
+                self.client.authenticate(self.config["api_key"], self.gpu)
+                log.info("Node '%s' authenticated (id=%s, organization=%s, collaboration=%s)", self.client.name,
+                         self.client.node_id, self.client.organization_name, self.client.collaboration_id)
+                return
+            except ServerError as e:
+                if e.status == 401:
+                    raise
+                log.warning("server not ready (%s); retrying", e)
+            except Exception as e:  # noqa: BLE001 -- connection refused while the server starts
+                log.warning("cannot reach server (%s); retry %d/%d", type(e).__name__, attempt + 1, retries)
+            time.sleep(1.0)
+        raise RuntimeError("could not authenticate with the server")
+
+    def setup_encryption(self) -> None:
+        collab = self.client.request(f"collaboration/{self.client.collaboration_id}")
+        enc_cfg = self.config.get("encryption", {}) or {}
+        if collab.get("encrypted") != bool(enc_cfg.get("enabled")):
+            msg = (f"Expectations on encryption don't match! server: {collab.get('encrypted')}, "
+                   f"node config: {bool(enc_cfg.get('enabled'))}")
+            log.critical(msg)
+            raise RuntimeError(msg)
+        if not collab.get("encrypted"):
+            log.warning("Disabling encryption!")
+            self.cryptor = DummyCryptor()
+            return
+        key_file = os.environ.get("PRIVATE_KEY") or enc_cfg.get("private_key") or "private_key.pem"
+        key_file = self.ctx.get_data_file(key_file)
+        if not Path(key_file).exists():
+            raise FileNotFoundError(f"private key {key_file} not found; run `vnode create-private-key`")
+        self.cryptor = RSACryptor(key_file)
+        org = self.client.request(f"organization/{self.client.organization_id}")
+        if not org.get("public_key") or not self.cryptor.verify_public_key(org["public_key"]):
+            log.warning("Local public key differs from the server's: uploading ours")
+            self.client.request(f"organization/{self.client.organization_id}", method="patch",
+                                json={"public_key": self.cryptor.public_key_str})
+
+    # ------------------------------------------------------------------ crypto helpers (used by the proxy)
+    def _org_public_key(self, org_id: int) -> Optional[str]:
+        if org_id not in self._org_keys:
+            self._org_keys[org_id] = self.client.request(f"organization/{org_id}").get("public_key")
+        return self._org_keys[org_id]
+
+    def encrypt_for_organization(self, plain: bytes, org_id: int) -> str:
+        if isinstance(self.cryptor, RSACryptor):
+            pub = self._org_public_key(org_id)
+            if not pub:
+                raise ValueError(f"organization {org_id} has no public key")
+            return self.cryptor.encrypt_bytes_to_str(plain, pub)
+        return self.cryptor.encrypt_bytes_to_str(plain, "")
+
+    def decrypt_to_plain_b64(self, value: Optional[str]) -> Optional[str]:
+        if not value:
+            return value
+        return bytes_to_base64s(self.cryptor.decrypt_str_to_bytes(value))
+
+    # ------------------------------------------------------------------ task intake
+    def sync_open_results(self) -> None:
+        rows = self.client.request("result", params={"state": "open", "node_id": self.client.node_id, "include": "task"})
+        for r in rows:
+            self._enqueue(r)
+        log.info("received %d open task(s) from the server", len(rows))
+
+    def _enqueue(self, result: dict) -> None:
+        if result["id"] in self._seen:
+            return
+        self._seen.add(result["id"])
+        self.queue.put(result)
+
+    def _listen(self) -> None:
+        since = None
+        while not self._stop.is_set():
+            try:
+                params = {"timeout": 20}
+                if since is not None:
+                    params["since"] = since
+                reply = self.client.request("event", params=params, timeout=40)
+                for ev in reply.get("events", []):
+                    if ev["name"] == "new_task" and ev["data"].get("organization_id") == self.client.organization_id:
+                        r = self.client.request(f"result/{ev['data']['result_id']}", params={"include": "task"})
+                        if r.get("finished_at") is None:
+                            self._enqueue(r)
+                    elif ev["name"] == "kill_containers":
+                        self.kill_task(ev["data"].get("task_id"))
+                if since is None:
+                    self.sync_open_results()        # close the race between the first sync and the subscription
+                since = reply.get("last_id", since)
+            except Exception as e:  # noqa: BLE001
+                if self._stop.is_set():
+                    return
+                log.warning("event channel error (%s); reconnecting", e)
+                time.sleep(1.0)
+                try:
+                    self.sync_open_results()
+                except Exception:  # noqa: BLE001
+                    pass
+
+    def _heartbeat(self) -> None:
+        while not self._stop.wait(self.heartbeat_s):
+            try:
+                self.client.request(f"node/{self.client.node_id}", method="patch", json={"status": "online", "gpu": self.gpu})
+            except Exception as e:  # noqa: BLE001
+                log.debug("heartbeat failed: %s", e)
+
+    # ------------------------------------------------------------------ execution
+    def _worker(self) -> None:
+        while not self._stop.is_set():
+            try:
+                result = self.queue.get(timeout=0.5)
+            except queue.Empty:
+                continue
+            threading.Thread(target=self._run_result, args=(result,), daemon=True).start()
+
+    def _run_result(self, result: dict) -> None:
+        rid = result["id"]
+        task = result["task"]
+        log.info("starting task %s (result %s, image %s)", task["id"], rid, task.get("image"))
+        self.client.request(f"result/{rid}", method="patch", json={"started_at": _now(), "status": "active"})
+        logtxt, out_b64, status = "", None, "failed"
+        try:
+            module = resolve_image(task["image"], self.config.get("algorithms"), bool(self.config.get("allow_module_images")))
+            plain = self.cryptor.decrypt_str_to_bytes(result["input"]) if result.get("input") else b"{}"
+            token = self.client.request("token/container", method="post",
+                                        json={"task_id": task["id"], "image": task["image"]})["container_token"]
+            run_dir = runtime_dir() / "volumes" / self.ctx.docker_temporary_volume_name(task["run_id"])
+            work = run_dir / f"result-{rid}"
+            work.mkdir(parents=True, exist_ok=True)
+            (work / "input").write_bytes(plain)
+            (work / "token").write_text(token)
+            (work / "output").write_bytes(b"")
+            env = dict(os.environ)
+            label = (task.get("database") or "default")
+            uri = self.ctx.databases.get(label) if hasattr(self.ctx, "databases") else None
+            env.update({
+                "INPUT_FILE": str(work / "input"), "OUTPUT_FILE": str(work / "output"), "TOKEN_FILE": str(work / "token"),
+                "TEMPORARY_FOLDER": str(run_dir), "HOST": "http://127.0.0.1", "PORT": str(self.proxy.port), "API_PATH": "",
+                "DATABASE_LABEL": label, "V6_ORGANIZATION_ID": str(self.client.organization_id),
+                "V6_NODE_ID": str(self.client.node_id), "V6_COLLABORATION_ID": str(self.client.collaboration_id),
+            })
+            if uri is not None:
+                env["DATABASE_URI"] = str(uri)
+                env[f"{label.upper()}_DATABASE_URI"] = str(uri)
+            if self.gpu is not None:
+                env["V6_GPU"] = str(self.gpu)
+            pkg_root = str(Path(__file__).resolve().parent.parent.parent)
+            env["PYTHONPATH"] = pkg_root + os.pathsep + env.get("PYTHONPATH", "")
+            proc = subprocess.Popen([sys.executable, "-m", "vantage6_b200.algorithm.wrapper", module],
+                                    stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, start_new_session=True)
+            self.running[rid] = proc
+            out, _ = proc.communicate(timeout=float(self.config.get("task_timeout_s", 3600)))
+            logtxt = out.decode("utf-8", errors="replace")
+            if proc.returncode == 0:
+                data = (work / "output").read_bytes()
+                dest_org = task.get("initiator") or self.client.request(f"task/{task['id']}").get("initiator")
+                out_b64 = self.encrypt_for_organization(data, int(dest_org)) if dest_org else self.cryptor.bytes_to_str(data)
+                status = "completed"
+            else:
+                logtxt += f"\n[node] algorithm exited with code {proc.returncode}"
+        except subprocess.TimeoutExpired:
+            logtxt += "\n[node] algorithm timed out and was killed"
+            self._kill_proc(self.running.get(rid))
+        except Exception as e:  # noqa: BLE001
+            log.exception("task %s failed", task.get("id"))
+            logtxt += f"\n[node] failed to run algorithm: {e!r}"
+        finally:
+            self.running.pop(rid, None)
+        try:
+            self.client.request(f"result/{rid}", method="patch",
+                                json={"finished_at": _now(), "result": out_b64, "log": logtxt[-20000:], "status": status})
+        except Exception as e:  # noqa: BLE001
+            log.error("could not report result %s: %s", rid, e)
+        log.info("task %s result %s: %s", task.get("id"), rid, status)
+
+    @staticmethod
+    def _kill_proc(proc: Optional[subprocess.Popen]) -> None:
+        if proc is None:
+            return
+        try:
+            os.killpg(os.getpgid(proc.pid), signal.SIGKILL)
+        except Exception:  # noqa: BLE001
+            try:
+                proc.kill()
+            except Exception:  # noqa: BLE001
+                pass
+
+    def kill_task(self, task_id) -> None:
+        for rid, proc in list(self.running.items()):
+            self._kill_proc(proc)
+
+    # ------------------------------------------------------------------ lifecycle
+    def start(self, block: bool = True) -> None:
+        log.info("vantage6-b200 node runtime %s (gpu=%s)", __version__, self.gpu)
+        self.authenticate()
+        self.setup_encryption()
+        self.proxy.start()
+        self.sync_open_results()
+        for target in (self._listen, self._worker, self._heartbeat):
+            t = threading.Thread(target=target, daemon=True)
+            t.start()
+            self._threads.append(t)
+        print(f"node '{self.client.name}' online (id={self.client.node_id}, gpu={self.gpu})", flush=True)
+        if block:
+            try:
+                while not self._stop.wait(0.5):
+                    pass
+            except KeyboardInterrupt:
+                pass
+            self.stop()
+
+    def stop(self) -> None:
+        if self._stop.is_set() and not self._threads:
+            return
+        self._stop.set()
+        for proc in list(self.running.values()):
+            self._kill_proc(proc)
+        try:
+            self.client.request(f"node/{self.client.node_id}", method="patch", json={"status": "offline"})
+        except Exception:  # noqa: BLE001
+            pass
+        self.proxy.stop()
+        self._threads = []
+        log.info("node stopped")

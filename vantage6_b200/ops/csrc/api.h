@@ -30,7 +30,7 @@ struct FedAvgParams {
     float weight[V6_MAX_PEERS];   // n_i of each rank (0 => not participating)
     long long lo, hi;        // my element slice [lo, hi) -- multiples of 8
     int rank, world;
-    int n_reducers;          // ranks [0, n_reducers) own a slice (1 = central server on GPU 0)
+    int n_reducers; uint32_t live_mask;   // bit p: rank p is alive (waited for + pushed to); n_reducers:          // ranks [0, n_reducers) own a slice (1 = central server on GPU 0)
     uint32_t epoch;
     int upload_is_delta;     // 1: upload holds n_i*(w_i - w_g); 0: upload holds w_i (unscaled)
     int upload_prescaled;    // 1: contributions already multiplied by n_i (needed for multicast)

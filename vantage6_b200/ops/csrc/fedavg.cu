@@ -64,7 +64,7 @@ fedavg_round_kernel(const FedAvgParams P) {
         // (2) wait for every participating contributor
         if (threadIdx.x == 0) s_ok = 1;
         __syncthreads();
-        if (threadIdx.x < P.world && P.weight[threadIdx.x] > 0.f) {
+        if (threadIdx.x < P.world && ((P.live_mask >> threadIdx.x) & 1u)) {
             if (!spin_wait_ge(my_pad + PAD_UPLOAD + threadIdx.x, P.epoch, P.timeout_cycles, my_pad + PAD_ABORT))
                 atomicExch(&s_ok, 0);
         }
@@ -138,7 +138,7 @@ fedavg_round_kernel(const FedAvgParams P) {
                     } else {
 #pragma unroll
                         for (int p = 0; p < V6_MAX_PEERS; ++p)
-                            if (p < P.world)
+                            if (p < P.world && ((P.live_mask >> p) & 1u))
                                 st_f4(reinterpret_cast<float4*>(reinterpret_cast<float*>(P.param_out.p[p]) + eh), wn);
                     }
                     acc[4 * h + 0] = w[0]; acc[4 * h + 1] = w[1]; acc[4 * h + 2] = w[2]; acc[4 * h + 3] = w[3];
@@ -152,14 +152,14 @@ fedavg_round_kernel(const FedAvgParams P) {
                         else {
 #pragma unroll
                             for (int p = 0; p < V6_MAX_PEERS; ++p)
-                                if (p < P.world)
+                                if (p < P.world && ((P.live_mask >> p) & 1u))
                                     st_u4(reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.shadow_out.p[p]) + e), s);
                         }
                     } else {
                         uint2 s = make_uint2(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]));
 #pragma unroll
                         for (int p = 0; p < V6_MAX_PEERS; ++p)
-                            if (p < P.world)
+                            if (p < P.world && ((P.live_mask >> p) & 1u))
                                 *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.shadow_out.p[p]) + e) = s;
                     }
                 }

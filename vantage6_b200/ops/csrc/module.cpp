@@ -63,7 +63,7 @@ PYBIND11_MODULE(_C, m) {
           [](const std::vector<u64>& upload, const std::vector<u64>& param_out, const std::vector<u64>& shadow_out,
              const std::vector<u64>& pads, u64 upload_mc, u64 param_mc, u64 shadow_mc, u64 w_global, u64 opt_m, u64 opt_v,
              const std::vector<float>& weight, long long lo, long long hi, int rank, int world, int n_reducers,
-             uint32_t epoch, bool upload_is_delta, bool upload_prescaled, int server_opt, float server_lr, float beta1,
+             uint32_t live_mask, uint32_t epoch, bool upload_is_delta, bool upload_prescaled, int server_opt, float server_lr, float beta1,
              float beta2, float eps, float bias1, float bias2, float inv_total, long long timeout_cycles, u64 cta_counter,
              int upload_dtype, int grid, u64 stream) {
               FedAvgParams p;
@@ -71,7 +71,7 @@ PYBIND11_MODULE(_C, m) {
               p.upload_mc = P<void>(upload_mc); p.param_mc = P<void>(param_mc); p.shadow_mc = P<void>(shadow_mc);
               p.w_global = P<float>(w_global); p.opt_m = P<float>(opt_m); p.opt_v = P<float>(opt_v);
               for (int i = 0; i < V6_MAX_PEERS; ++i) p.weight[i] = i < (int)weight.size() ? weight[i] : 0.f;
-              p.lo = lo; p.hi = hi; p.rank = rank; p.world = world; p.n_reducers = n_reducers; p.epoch = epoch;
+              p.lo = lo; p.hi = hi; p.rank = rank; p.world = world; p.n_reducers = n_reducers; p.live_mask = live_mask; p.epoch = epoch;
               p.upload_is_delta = upload_is_delta; p.upload_prescaled = upload_prescaled; p.server_opt = server_opt;
               p.server_lr = server_lr; p.beta1 = beta1; p.beta2 = beta2; p.eps = eps; p.bias1 = bias1; p.bias2 = bias2;
               p.inv_total = inv_total; p.timeout_cycles = timeout_cycles; p.cta_counter = P<unsigned int>(cta_counter);

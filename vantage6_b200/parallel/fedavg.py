@@ -77,6 +77,11 @@ class FedAvgEngine:
         self.epoch = 0
         self.server_step = 0
         self.last_status = 0
+        # bit p set: rank p is alive. Reducers wait for every live rank to ARRIVE at the round
+        # (a weight-0 node is alive but not reporting: it is still waited for -- its buffer must not
+        # be overwritten while it is in use -- and still receives the new global model). A dead
+        # node (mark_dead) is neither waited for nor written to.
+        self.live_mask = (1 << world) - 1
 
         if data_plane == "native":
             assert self.device.type == "cuda"
@@ -174,7 +179,14 @@ class FedAvgEngine:
         """One federated aggregation: after it returns (stream order) ``w`` is the new global."""
         self._aggregate(self._weights_vector(weight), count_step=True)
 
+    def mark_dead(self, rank: int) -> None:
+        """Exclude a failed node from all future rounds (every surviving rank must call this with
+        the same argument, e.g. after ``poll_status()`` reported a timeout): the FedAvg weights
+        renormalise over the reporters, as with any partial participation."""
+        self.live_mask &= ~(1 << rank)
+
     def _aggregate(self, weights: List[float], count_step: bool, force_p2p: bool = False) -> None:
+        weights = [w if (self.live_mask >> r) & 1 else 0.0 for r, w in enumerate(weights)]
         total = sum(weights)
         assert total > 0, "at least one node must report"
         self.epoch += 1
@@ -205,7 +217,7 @@ class FedAvgEngine:
                 up.mc() if use_mc_ld else 0, wb.mc() if (self.use_multicast and not force_p2p) else 0,
                 self._shadow_buf.mc() if (self._shadow_buf and self.use_multicast and not force_p2p) else 0,
                 self.w_global.data_ptr(), self.opt_m.data_ptr(), self.opt_v.data_ptr(), eff_weights,
-                self.lo, self.hi, self.rank, self.world, self.n_reducers, self.epoch, is_delta, prescaled,
+                self.lo, self.hi, self.rank, self.world, self.n_reducers, self.live_mask, self.epoch, is_delta, prescaled,
                 SERVER_OPTS[self.opt.name], self.opt.lr, self.opt.beta1, self.opt.beta2, self.opt.eps, bias1, bias2,
                 inv_total, self.timeout_cycles, self._cta_counter.data_ptr(),
                 1 if self.upload_mode == "delta_bf16" else 0,

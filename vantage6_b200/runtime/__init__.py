@@ -358,7 +358,11 @@ class LocalRuntime:
         self.root = Path(root) if root else runtime_dir()
         self._containers = ContainerCollection(self)
         self._volumes = VolumeCollection(self)
-        self.images = ImageCollection()
+        self._images = ImageCollection()
+
+    @property
+    def images(self) -> ImageCollection:
+        return self._images
 
     # class-level properties so tests can patch ``LocalRuntime.containers`` / ``.volumes`` the
     # way the reference tests patch ``docker.DockerClient.containers``

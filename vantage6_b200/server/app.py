@@ -834,6 +834,8 @@ class ServerApp:
 
         class Handler(BaseHTTPRequestHandler):
             protocol_version = "HTTP/1.1"
+            wbufsize = 64 * 1024                 # one send per response (no Nagle / delayed-ACK stall)
+            disable_nagle_algorithm = True
             server_version = "vantage6-b200"
 
             def log_message(self, fmt, *args):
