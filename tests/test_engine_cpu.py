@@ -1,0 +1,224 @@
+"""Host-side logic of the FedAvg engine / trainer on CPU: closed-form checks of the aggregation
+math for every server optimizer / upload mode / server placement, partial participation, dead
+nodes, checkpoint round-trip, multi-process gloo (world_size 2) and the reference
+implementations that serve as numerics oracles for the CUDA kernels."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from vantage6_b200.models import zoo
+from vantage6_b200.models.flat import FlatModel, flat_size
+from vantage6_b200.models.resnet import imagenet_forward_loss, resnet_tiny
+from vantage6_b200.ops import glm as K8
+from vantage6_b200.ops import norm as N
+from vantage6_b200.ops import optim as O
+from vantage6_b200.ops import rope as R
+from vantage6_b200.parallel.fedavg import FedAvgEngine, ServerOptConfig, SmallAggregator
+from vantage6_b200.parallel.trainer import FederatedTrainer
+from vantage6_b200.utils.checkpoint import load_checkpoint, save_checkpoint
+
+
+def test_flat_model_aliases_parameters_and_buffers():
+    m = resnet_tiny(10)
+    n = flat_size(m)
+    fm = FlatModel(m)
+    assert fm.n_total == n and fm.check_aliasing()
+    before = m.fc.weight.clone()
+    fm.flat.mul_(2.0)
+    assert torch.equal(m.fc.weight, before * 2)                       # views, not copies
+    assert m.bn1.running_var.data_ptr() >= fm.flat.data_ptr()         # BN stats are federated too
+    x = torch.randn(2, 3, 32, 32)
+    m(x).sum().backward()
+    assert fm.grad.abs().sum() > 0 and m.fc.weight.grad.data_ptr() >= fm.grad.data_ptr()
+
+
+@pytest.mark.parametrize("opt", ["fedavg", "fedavgm", "fedadam"])
+def test_world1_server_optimizers_closed_form(opt):
+    n = 64
+    e = FedAvgEngine(n, data_plane="collective", server_opt=ServerOptConfig(opt, 0.5, 0.9, 0.99, 1e-3))
+    w0 = torch.randn(e.n)
+    e.w.copy_(w0)
+    e.initialize_global()
+    step = torch.randn(e.n)
+    e.w.add_(step)
+    e.aggregate(10.0)
+    d = step
+    if opt == "fedavg":
+        exp = w0 + 0.5 * d
+    elif opt == "fedavgm":
+        exp = w0 + 0.5 * d                                            # m = d on the first step
+    else:
+        m, v = 0.1 * d, 0.01 * d * d
+        exp = w0 + 0.5 * (m / 0.1) / ((v / 0.01).sqrt() + 1e-3)
+    torch.testing.assert_close(e.w, exp, rtol=1e-5, atol=1e-6)
+
+
+def test_trainer_cpu_all_upload_modes_agree():
+    outs = []
+    for upload in ("weights_f32", "delta_f32"):
+        torch.manual_seed(0)
+        tr = FederatedTrainer(resnet_tiny(10), imagenet_forward_loss, device="cpu", lr=0.01, upload=upload)
+        tr.initialize_global()
+        x = torch.randint(0, 256, (2, 4, 3, 32, 32), dtype=torch.uint8)
+        y = torch.randint(0, 10, (2, 4))
+        for _ in range(2):
+            tr.run_round([(x[0], y[0]), (x[1], y[1])])
+        outs.append(tr.engine.w.clone())
+    torch.testing.assert_close(outs[0][: outs[1].numel()], outs[1], rtol=1e-5, atol=1e-6)
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    torch.manual_seed(0)
+    tr = FederatedTrainer(resnet_tiny(10), imagenet_forward_loss, device="cpu", lr=0.01,
+                          server_opt=ServerOptConfig("fedadam", 0.1))
+    tr.initialize_global()
+    x = torch.randint(0, 256, (1, 4, 3, 32, 32), dtype=torch.uint8)
+    y = torch.randint(0, 10, (1, 4))
+    tr.run_round([(x[0], y[0])])
+    path = save_checkpoint(tmp_path / "ckpt", tr, round_idx=1)
+    ref_next = None
+    w_after_1 = tr.engine.w.clone()
+    tr.run_round([(x[0], y[0])])
+    ref_next = tr.engine.w.clone()
+    torch.manual_seed(1)
+    tr2 = FederatedTrainer(resnet_tiny(10), imagenet_forward_loss, device="cpu", lr=0.01,
+                           server_opt=ServerOptConfig("fedadam", 0.1))
+    meta = load_checkpoint(path, tr2)
+    assert meta["round"] == 1
+    torch.testing.assert_close(tr2.engine.w, w_after_1)
+    tr2.run_round([(x[0], y[0])])
+    torch.testing.assert_close(tr2.engine.w, ref_next, rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ multi-process (gloo)
+def _worker(rank, world, port, q, server_mode, upload, opt):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 1003
+        e = FedAvgEngine(n, rank, world, "cpu", server_mode=server_mode, upload=upload, server_opt=ServerOptConfig(opt, 1.0))
+        g = torch.Generator().manual_seed(7)
+        w0 = torch.randn(e.n, generator=g)
+        e.w.copy_(w0 if rank == 0 else torch.zeros(e.n))
+        e.initialize_global()
+        assert torch.allclose(e.w, w0)
+        steps = [torch.randn(e.n, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
+        weights = [1.0, 3.0]
+        if upload == "weights_f32":
+            e.w.add_(steps[rank])
+        else:
+            e.upload.copy_(steps[rank])
+        e.aggregate(weights)
+        exp = w0 + sum(w * s for w, s in zip(weights, steps)) / sum(weights)
+        ok1 = torch.allclose(e.w, exp, rtol=1e-5, atol=1e-6)
+        # partial participation: node 1 does not report -> renormalise over the reporters
+        w1 = e.w.clone()
+        if upload == "weights_f32":
+            e.w.add_(steps[rank])
+        else:
+            e.upload.copy_(steps[rank])
+        e.aggregate([2.0, 0.0])
+        ok2 = torch.allclose(e.w, w1 + steps[0], rtol=1e-5, atol=1e-6)
+        # K3 path
+        agg = SmallAggregator(10, rank, world, "cpu")
+        agg.slot()[:10] = float(rank + 1)
+        out = agg.allreduce([1.0, 3.0])
+        ok3 = torch.allclose(out[:10], torch.full((10,), (1 * 1 + 3 * 2) / 4.0))
+        q.put((rank, bool(ok1), bool(ok2), bool(ok3)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("server_mode,upload,opt", [("sharded", "weights_f32", "fedavg"), ("central", "delta_f32", "fedavg"),
+                                                   ("sharded", "delta_f32", "fedavg")])
+def test_two_process_gloo_aggregation(server_mode, upload, opt):
+    from vantage6_b200.dev import free_port
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, server_mode, upload, opt)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(30)
+    assert res == [(0, True, True, True), (1, True, True, True)], res
+
+
+def test_dead_node_is_excluded():
+    e = FedAvgEngine(16, data_plane="collective")
+    e.world = 3                                   # host-side logic only
+    e.live_mask = 0b111
+    e.mark_dead(1)
+    assert e.live_mask == 0b101
+    w = [1.0, 2.0, 3.0]
+    assert [x if (e.live_mask >> r) & 1 else 0.0 for r, x in enumerate(w)] == [1.0, 0.0, 3.0]
+
+
+# ------------------------------------------------------------------ reference oracles
+def test_reference_sgd_matches_torch_optim():
+    torch.manual_seed(0)
+    p = torch.nn.Parameter(torch.randn(100))
+    w, buf = p.detach().clone(), torch.zeros(100)
+    topt = torch.optim.SGD([p], lr=0.1, momentum=0.9, weight_decay=1e-3, nesterov=True)
+    for i in range(3):
+        g = torch.randn(100)
+        p.grad = g.clone()
+        topt.step()
+        O.reference_sgd_step(w, g, buf, 0.1, 0.9, 0.0, 1e-3, True, i == 0)
+    torch.testing.assert_close(w, p.detach(), rtol=1e-6, atol=1e-6)
+
+
+def test_flat_optimizers_cpu_publish_modes():
+    w = torch.randn(32)
+    w0 = w.clone()
+    ref, up = torch.zeros(32), torch.zeros(32, dtype=torch.bfloat16)
+    sh = torch.zeros(32, dtype=torch.bfloat16)
+    opt = O.FlatAdamW(w, lr=1e-2)
+    opt.step(torch.randn(32), w_ref=ref, save_ref=True, upload=up, publish=O.PUBLISH_DELTA_BF16, contrib_scale=2.0, shadow=sh)
+    torch.testing.assert_close(ref, w0)
+    torch.testing.assert_close(up.float(), (2.0 * (w - w0)).to(torch.bfloat16).float())
+    torch.testing.assert_close(sh.float(), w.to(torch.bfloat16).float())
+    c = O.clip_grad_coef(torch.full((100,), 3.0), 1.0)
+    assert abs(c.item() - 1.0 / 30.0) < 1e-4
+
+
+def test_reference_norms_rope_glm_linear():
+    x = torch.randn(5, 64)
+    g, b = torch.rand(64) + 0.5, torch.randn(64)
+    y, _ = N.layer_norm(x, g, b, 1e-5)
+    torch.testing.assert_close(y, torch.nn.functional.layer_norm(x, (64,), g, b, 1e-5))
+    r = torch.randn(5, 64)
+    y2, h = N.rms_norm(x, g, 1e-5, residual=r)
+    hh = x + r
+    torch.testing.assert_close(h, hh)
+    torch.testing.assert_close(y2, hh * torch.rsqrt(hh.pow(2).mean(-1, keepdim=True) + 1e-5) * g)
+    cos, sin = R.rope_tables(8, 16)
+    q, k = torch.randn(1, 8, 2, 16), torch.randn(1, 8, 1, 16)
+    q2, k2 = R.apply_rope(q, k, cos, sin)
+    torch.testing.assert_close(q2.norm(dim=-1), q.norm(dim=-1))        # rotations preserve norms
+    torch.testing.assert_close(q2[:, 0], q[:, 0])                       # position 0: identity
+    X, yv, w = torch.randn(50, 256), (torch.rand(50) < 0.5).float(), torch.randn(257) * 0.1
+    out = K8.logistic_grad(X, yv, w)
+    wp = w.clone().requires_grad_()
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(X @ wp[:256] + wp[256], yv, reduction="sum")
+    loss.backward()
+    torch.testing.assert_close(out[:257], wp.grad, rtol=1e-4, atol=1e-4)
+    assert abs(out[257].item() - loss.item()) < 1e-3 and out[258].item() == 50
+
+
+@pytest.mark.parametrize("name", ["bert_tiny", "llama_tiny_lora", "resnet_tiny"])
+def test_zoo_models_train_on_cpu(name):
+    torch.manual_seed(0)
+    tr, spec = zoo.build_trainer(name, rank=0, world=1, device="cpu")
+    tr.initialize_global()
+    batches = spec.make_batches(spec.local_steps, spec.batch, seed=3)
+    losses = [tr.run_round(batches).item() for _ in range(3)]
+    assert all(l == l for l in losses) and losses[-1] < losses[0], losses
+    if name == "llama_tiny_lora":           # only the adapters are federated
+        names = [s.name for s in tr.fm.segments]
+        assert names and all("lora_" in n for n in names)

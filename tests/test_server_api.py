@@ -1,0 +1,190 @@
+"""Central server REST API, permissions, events, client library and encryption, in-process
+(server on an ephemeral port, real HTTP)."""
+import threading
+import time
+
+import pytest
+
+from vantage6_b200.client import ContainerClient, ServerError, UserClient
+from vantage6_b200.common.encryption import DummyCryptor, RSACryptor
+from vantage6_b200.common.serialization import deserialize, serialize
+from vantage6_b200.node import NodeClient
+from vantage6_b200.server import fixtures
+from vantage6_b200.server.app import ServerApp
+
+ENTITIES = {
+    "organizations": [
+        {"name": "A", "domain": "a.test", "users": [{"username": "alice", "password": "pw-a", "roles": ["Root"]}]},
+        {"name": "B", "domain": "b.test", "users": [{"username": "bob", "password": "pw-b", "roles": ["Researcher"]}]},
+        {"name": "C", "domain": "c.test", "users": [{"username": "carol", "password": "pw-c", "roles": ["Viewer"]}]},
+    ],
+    "collaborations": [{"name": "AB", "participants": [{"name": "A", "api-key": "key-a"}, {"name": "B", "api-key": "key-b"}]}],
+}
+
+
+@pytest.fixture
+def server():
+    app = ServerApp({"uri": "sqlite://", "api_path": "/api", "jwt_secret_key": "s" * 40, "allow_drop_all": True})
+    # drop the bootstrap root user/organization so that the fixture ids are A=1, B=2, C=3
+    for sql in ("DELETE FROM user_role", "DELETE FROM user", "DELETE FROM organization",
+                "DELETE FROM sqlite_sequence WHERE name IN ('organization', 'user')"):
+        app.db.execute(sql)
+    fixtures.load(app.db, ENTITIES)
+    port = app.start("127.0.0.1", 0)
+    yield app, port
+    app.stop()
+
+
+def user(port, name, pw):
+    c = UserClient("http://127.0.0.1", port, "/api")
+    c.authenticate(name, pw)
+    c.setup_encryption(None)
+    return c
+
+
+def test_version_health_and_auth_errors(server):
+    app, port = server
+    c = UserClient("http://127.0.0.1", port, "/api")
+    assert c.util.get_server_version()["version"] == "3.1.0"
+    assert c.util.get_server_health()["database"] is True
+    with pytest.raises(ServerError) as e:
+        c.authenticate("alice", "wrong")
+    assert e.value.status == 401
+    with pytest.raises(ServerError) as e:
+        c.request("organization")
+    assert e.value.status == 401
+    c.authenticate("alice", "pw-a")
+    assert c.whoami.organization_name == "A"
+    c.refresh_token()
+    assert len(c.organization.list()) >= 3
+
+
+def test_permissions_scopes(server):
+    app, port = server
+    alice, bob, carol = user(port, "alice", "pw-a"), user(port, "bob", "pw-b"), user(port, "carol", "pw-c")
+    assert {o["name"] for o in alice.organization.list()} >= {"A", "B", "C"}
+    assert {o["name"] for o in bob.organization.list()} == {"A", "B"}        # collaboration scope
+    assert {o["name"] for o in carol.organization.list()} == {"C"}           # organization scope
+    with pytest.raises(ServerError) as e:
+        bob.organization.create("D")
+    assert e.value.status == 401
+    new = alice.organization.create("D", domain="d.test")
+    assert new["name"] == "D"
+    with pytest.raises(ServerError):
+        carol.task.create(collaboration=1, organizations=[1], name="x", image="img", input={})
+    with pytest.raises(ServerError):
+        bob.user.create("eve", "pw", organization=1)
+    u = alice.user.create("eve", "pw", organization=new["id"], roles=[r["id"] for r in alice.role.list() if r["name"] == "Viewer"])
+    assert u["username"] == "eve"
+    assert len(alice.rule.list()) == 9 * 4 * 4
+    collab = alice.collaboration.create("AD", [1, new["id"]])
+    node = alice.node.create(collab["id"], new["id"])
+    assert "api_key" in node
+    with pytest.raises(ServerError):
+        alice.node.create(collab["id"], new["id"])          # one node per org x collaboration
+    alice.node.delete(node["id"])
+    alice.collaboration.delete(collab["id"])
+
+
+def test_task_lifecycle_with_node_and_container_identities(server):
+    app, port = server
+    bob = user(port, "bob", "pw-b")
+    task = bob.task.create(collaboration=1, organizations=[1, 2], name="t", image="v6b200/average",
+                           input={"method": "m", "master": True})
+    assert not task["complete"] and len(task["results"]) == 2 and task["run_id"] == 1
+
+    node = NodeClient("http://127.0.0.1", port, "/api")
+    with pytest.raises(ServerError):
+        node.authenticate("wrong-key")
+    node.authenticate("key-a", gpu=3)
+    assert node.organization_name == "A"
+    open_ = node.request("result", params={"state": "open", "node_id": node.node_id, "include": "task"})
+    assert len(open_) == 1 and open_[0]["task"]["image"] == "v6b200/average"
+    rid = open_[0]["id"]
+    inp = deserialize(DummyCryptor().decrypt_str_to_bytes(open_[0]["input"]))
+    assert inp == {"method": "m", "master": True}
+
+    # container token: wrong image is refused, correct one can create a sub-task with the same image only
+    with pytest.raises(ServerError):
+        node.request("token/container", method="post", json={"task_id": task["id"], "image": "other"})
+    tok = node.request("token/container", method="post", json={"task_id": task["id"], "image": "v6b200/average"})["container_token"]
+    cc = ContainerClient(tok, "http://127.0.0.1", port, "/api")
+    sub = cc.create_new_task({"method": "p"}, [1, 2])
+    assert sub["parent"]["id"] == task["id"] and sub["run_id"] == task["run_id"]
+    assert [o["name"] for o in cc.get_organizations_in_my_collaboration()] == ["A", "B"]
+    assert [a["rank"] for a in cc.get_algorithm_addresses(sub["id"])] == [0, 1]
+
+    # node reports; a finished result cannot be patched again; other orgs' results are off limits
+    node.request(f"result/{rid}", method="patch", json={"started_at": "now"})
+    out = DummyCryptor().bytes_to_str(serialize({"answer": 42}))
+    node.request(f"result/{rid}", method="patch", json={"finished_at": "now", "result": out, "log": "ok"})
+    with pytest.raises(ServerError):
+        node.request(f"result/{rid}", method="patch", json={"log": "again"})
+    other = [r for r in bob.result.list(task_id=task["id"]) if r["id"] != rid][0]
+    with pytest.raises(ServerError):
+        node.request(f"result/{other['id']}", method="patch", json={"log": "x"})
+    res = bob.result.from_task(task["id"])
+    assert res[0]["result"] == {"answer": 42} and res[1]["result"] is None
+    assert not bob.task.get(task["id"])["complete"]
+    assert node.request(f"node/{node.node_id}")["status"] == "online" and node.request(f"node/{node.node_id}")["gpu"] == 3
+
+    # deleting a task removes its sub-tasks and results
+    alice = user(port, "alice", "pw-a")
+    alice.task.delete(task["id"])
+    assert alice.task.list() == []
+    assert app.db.query("SELECT * FROM result") == []
+
+
+def test_event_long_poll_pushes_new_tasks(server):
+    app, port = server
+    node = NodeClient("http://127.0.0.1", port, "/api")
+    node.authenticate("key-b")
+    start = node.request("event", params={"timeout": 0})["last_id"]
+    got = {}
+
+    def listen():
+        got["reply"] = node.request("event", params={"since": start, "timeout": 10}, timeout=20)
+
+    th = threading.Thread(target=listen)
+    th.start()
+    time.sleep(0.2)
+    bob = user(port, "bob", "pw-b")
+    t0 = time.time()
+    bob.task.create(collaboration=1, organizations=[2], name="t", image="img", input={})
+    th.join(5)
+    assert not th.is_alive() and time.time() - t0 < 2.0          # pushed, not polled
+    evs = [e for e in got["reply"]["events"] if e["name"] == "new_task"]
+    assert evs and evs[0]["data"]["organization_id"] == 2
+
+
+def test_patch_organization_public_key_and_rsa_roundtrip(server, tmp_path):
+    """``vnode create-private-key`` flow + end-to-end encrypted task input (reference node.py:591-614)."""
+    app, port = server
+    key_b = tmp_path / "b.pem"
+    RSACryptor.create_new_rsa_key(key_b, bits=2048)
+    cb = RSACryptor(key_b)
+    alice = user(port, "alice", "pw-a")
+    alice.organization.update(2, public_key=cb.public_key_str)
+    assert cb.verify_public_key(alice.organization.get(2)["public_key"])
+    key_a = tmp_path / "a.pem"
+    RSACryptor.create_new_rsa_key(key_a, bits=2048)
+    alice.setup_encryption(str(key_a))
+    alice.organization.update(1, public_key=alice.cryptor.public_key_str)
+    task = alice.task.create(collaboration=1, organizations=[2], name="enc", image="img", input={"secret": [1, 2, 3]})
+    stored = app.db.one("SELECT input FROM result WHERE task_id=?", (task["id"],))["input"]
+    assert "secret" not in stored and stored.count("$") == 2            # ciphertext on the server
+    assert deserialize(cb.decrypt_str_to_bytes(stored)) == {"secret": [1, 2, 3]}
+    # result encrypted for A comes back decrypted through the client
+    enc = cb.encrypt_bytes_to_str(serialize({"ok": True}), alice.cryptor.public_key_str)
+    rid = app.db.one("SELECT id FROM result WHERE task_id=?", (task["id"],))["id"]
+    app.db.update("result", rid, result=enc, finished_at="now")
+    assert alice.wait_for_results(task["id"])[0]["result"] == {"ok": True}
+
+
+def test_fixtures_drop_all_respects_flag():
+    app = ServerApp({"uri": "sqlite://", "api_path": "/api", "allow_drop_all": False})
+    with pytest.raises(PermissionError):
+        fixtures.load(app.db, ENTITIES, drop_all=True)
+    counts = fixtures.load(app.db, ENTITIES)
+    assert counts["organizations"] == 3 and counts["nodes"] == 2
+    assert fixtures.load(app.db, ENTITIES)["organizations"] == 0         # idempotent

@@ -59,11 +59,12 @@ def RPC_gradient(data, w=None) -> Dict[str, Any]:
 
 # ------------------------------------------------------------------ data-plane flavour
 def master_fused(client, data, iterations: int = 20, lr: float = 1.0, rows_per_node: int = 125_000,
-                 features: int = 256, organization_ids=None) -> Dict[str, Any]:
+                 features: int = 256, organization_ids=None, synthetic: bool = False) -> Dict[str, Any]:
     ids = sorted(organization_ids or [o["id"] for o in client.get_organizations_in_my_collaboration()])
     rv = {"addr": "127.0.0.1", "port": _free_port(), "world": len(ids), "ranks": {str(o): r for r, o in enumerate(ids)}}
     task = client.create_new_task(input_={"method": "fit", "kwargs": dict(iterations=iterations, lr=lr, rendezvous=rv,
-                                                                         rows_per_node=rows_per_node, features=features)},
+                                                                         rows_per_node=rows_per_node, features=features,
+                                                                         synthetic=synthetic)},
                                   organization_ids=ids, name="glm-fit")
     while not client.get_task(task["id"]).get("complete"):
         time.sleep(0.05)
@@ -74,7 +75,7 @@ def master_fused(client, data, iterations: int = 20, lr: float = 1.0, rows_per_n
 
 
 def RPC_fit(data, iterations: int = 20, lr: float = 1.0, rendezvous: Optional[dict] = None,
-            rows_per_node: int = 125_000, features: int = 256) -> Dict[str, Any]:
+            rows_per_node: int = 125_000, features: int = 256, synthetic: bool = False) -> Dict[str, Any]:
     import torch
     import torch.distributed as dist
 
@@ -92,7 +93,7 @@ def RPC_fit(data, iterations: int = 20, lr: float = 1.0, rendezvous: Optional[di
         os.environ["MASTER_PORT"] = str(rv["port"])
         created = True
     w_true = None
-    if isinstance(data, str) or data is None:      # synthetic://... -> generate this node's shard on its GPU
+    if synthetic or isinstance(data, str) or data is None:      # synthetic://... -> generate this node's shard on its GPU
         X, y, w_true = synthetic_glm_shard(rows_per_node, features, seed=100 + org_id, device=device,
                                            dtype=torch.bfloat16 if use_cuda else torch.float32)
     else:

@@ -57,8 +57,8 @@ class BertForMaskedLM(nn.Module):
         self.cfg = c
         self.word = nn.Embedding(c.vocab_size, c.hidden)
         self.pos = nn.Embedding(c.max_pos, c.hidden)
-        self.type = nn.Embedding(c.type_vocab, c.hidden)
-        for e in (self.word, self.pos, self.type):
+        self.tok_type = nn.Embedding(c.type_vocab, c.hidden)
+        for e in (self.word, self.pos, self.tok_type):
             nn.init.normal_(e.weight, 0.0, 0.02)
         self.emb_ln = FusedLayerNorm(c.hidden, c.eps)
         self.layers = nn.ModuleList(BertLayer(c) for _ in range(c.layers))
@@ -69,7 +69,7 @@ class BertForMaskedLM(nn.Module):
     def forward(self, input_ids: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         B, S = input_ids.shape
         pos = torch.arange(S, device=input_ids.device)
-        h = self.word(input_ids) + self.pos(pos)[None] + self.type.weight[0][None, None]
+        h = self.word(input_ids) + self.pos(pos)[None] + self.tok_type.weight[0][None, None]
         x = self.emb_ln(h.to(torch.bfloat16))
         for layer in self.layers:
             x = layer(x)

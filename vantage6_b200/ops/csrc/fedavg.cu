@@ -44,7 +44,7 @@ V6_DEVINL void load_contrib_mc(const __nv_bfloat16* mc, long long e, float (&v)[
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 }
 
-template <typename UpT>
+template <typename UpT, int U, int WMAX>
 __global__ void __launch_bounds__(512, 1)
 fedavg_round_kernel(const FedAvgParams P) {
     constexpr int VN = Vec<UpT>::N;
@@ -72,29 +72,48 @@ fedavg_round_kernel(const FedAvgParams P) {
         if (!s_ok) { if (threadIdx.x == 0) my_pad[PAD_STATUS] = 1; }
         else {
             // (3)-(5) reduce -> optimizer -> push
+            // U vectors per thread per iteration, all peer loads issued before any is consumed:
+            // U x (world-1) remote 16 B loads in flight per thread cover the ~2-3 us NVLink
+            // round trip (bytes in flight per SM = 512 thr x U x (world-1) x 16 B).
             const long long nvec = (P.hi - P.lo) / VN;
-            for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-                 i += (long long)gridDim.x * blockDim.x) {
-                const long long e = P.lo + i * VN;
-                float acc[VN];
-#pragma unroll
-                for (int k = 0; k < VN; ++k) acc[k] = 0.f;
+            const long long stride = (long long)gridDim.x * blockDim.x;
+            for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * U) {
+                float accs[U][VN];
                 if (P.upload_mc) {
-                    load_contrib_mc(reinterpret_cast<const UpT*>(P.upload_mc), e, acc);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const long long iu = i0 + u * stride;
+                        if (iu < nvec) load_contrib_mc(reinterpret_cast<const UpT*>(P.upload_mc), P.lo + iu * VN, accs[u]);
+                    }
                 } else {
-                    float v[V6_MAX_PEERS][VN];
+                    float v[U][WMAX][VN];
 #pragma unroll
-                    for (int p = 0; p < V6_MAX_PEERS; ++p)      // issue all peer loads first (MLP)
-                        if (p < P.world && P.weight[p] > 0.f)
-                            load_contrib(reinterpret_cast<const UpT*>(P.upload.p[p]), e, v[p]);
+                    for (int u = 0; u < U; ++u) {
+                        const long long iu = i0 + u * stride;
 #pragma unroll
-                    for (int p = 0; p < V6_MAX_PEERS; ++p)
-                        if (p < P.world && P.weight[p] > 0.f) {
-                            const float s = P.upload_prescaled ? 1.f : P.weight[p];
+                        for (int p = 0; p < WMAX; ++p)
+                            if (iu < nvec && p < P.world && P.weight[p] > 0.f)
+                                load_contrib(reinterpret_cast<const UpT*>(P.upload.p[p]), P.lo + iu * VN, v[u][p]);
+                    }
 #pragma unroll
-                            for (int k = 0; k < VN; ++k) acc[k] = fmaf(s, v[p][k], acc[k]);
-                        }
+                    for (int u = 0; u < U; ++u) {
+#pragma unroll
+                        for (int k = 0; k < VN; ++k) accs[u][k] = 0.f;
+#pragma unroll
+                        for (int p = 0; p < WMAX; ++p)
+                            if (p < P.world && P.weight[p] > 0.f) {
+                                const float s = P.upload_prescaled ? 1.f : P.weight[p];
+#pragma unroll
+                                for (int k = 0; k < VN; ++k) accs[u][k] = fmaf(s, v[u][p][k], accs[u][k]);
+                            }
+                    }
                 }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                const long long iu = i0 + u * stride;
+                if (iu >= nvec) continue;
+                const long long e = P.lo + iu * VN;
+                float (&acc)[VN] = accs[u];
                 // VN elements of master state (fp32): 1 or 2 float4
 #pragma unroll
                 for (int h = 0; h < VN / 4; ++h) {
@@ -163,6 +182,7 @@ fedavg_round_kernel(const FedAvgParams P) {
                                 *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.shadow_out.p[p]) + e) = s;
                     }
                 }
+                }   // u
             }
         }
     }
@@ -194,8 +214,16 @@ extern "C" int v6_fedavg_round(const FedAvgParams* hp, int upload_dtype /*0 f32,
                                cudaStream_t stream) {
     FedAvgParams P = *hp;
     if (grid <= 0) grid = 148;
-    if (upload_dtype == 0) fedavg_round_kernel<float><<<grid, 512, 0, stream>>>(P);
-    else fedavg_round_kernel<__nv_bfloat16><<<grid, 512, 0, stream>>>(P);
+    // few peers -> deeper unroll (keep ~8 remote loads in flight per thread)
+#define V6_LAUNCH(T) \
+    do { \
+        if (P.world <= 2) fedavg_round_kernel<T, 4, 2><<<grid, 512, 0, stream>>>(P); \
+        else if (P.world <= 4) fedavg_round_kernel<T, 2, 4><<<grid, 512, 0, stream>>>(P); \
+        else fedavg_round_kernel<T, 1, 8><<<grid, 512, 0, stream>>>(P); \
+    } while (0)
+    if (upload_dtype == 0) V6_LAUNCH(float);
+    else V6_LAUNCH(__nv_bfloat16);
+#undef V6_LAUNCH
     V6_CHECK_LAUNCH();
     return 0;
 }

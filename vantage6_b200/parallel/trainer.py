@@ -48,7 +48,10 @@ class FederatedTrainer:
         self.fm = FlatModel(self.model, storage=self.engine.w, shadow=self.engine.shadow,
                             include_buffers=include_buffers)
         self.upload_mode = upload
-        self.w_ref = torch.zeros_like(self.fm.params) if upload != "weights_f32" else None
+        # delta modes: received global model (trainable prefix saved by the fused optimizer on the
+        # first local step; the float-buffer tail, e.g. BatchNorm statistics, saved per round below)
+        self.w_ref = torch.zeros(self.fm.n_total, dtype=torch.float32, device=self.device) \
+            if upload != "weights_f32" else None
         self.fused_local_optimizer = fused_local_optimizer
         if fused_local_optimizer:
             if optimizer == "sgd":
@@ -96,7 +99,7 @@ class FederatedTrainer:
         if self.upload_mode != "weights_f32":
             publish = fused_optim.PUBLISH_DELTA_F32 if self.upload_mode == "delta_f32" else fused_optim.PUBLISH_DELTA_BF16
             first, last = variant in ("first", "only"), variant in ("last", "only")
-            kw = dict(w_ref=self.w_ref, save_ref=first, upload=self.engine.upload[: self.fm.n_trainable] if last else None,
+            kw = dict(w_ref=self.w_ref[: self.fm.n_trainable], save_ref=first, upload=self.engine.upload[: self.fm.n_trainable] if last else None,
                       publish=publish if last else fused_optim.PUBLISH_NONE, contrib_scale=1.0)
         shadow = self.engine.shadow[: self.fm.n_trainable] if self.engine.shadow is not None else None
         if isinstance(self.opt, fused_optim.FlatSGD):
@@ -168,7 +171,11 @@ class FederatedTrainer:
         if n_samples is None:
             n_samples = float(sum(b[0].shape[0] for b in batches))
         self.loss_sum.zero_()
-        cur = torch.cuda.current_stream(self.device) if self.device.type == "cuda" else None
+        nt, na = self.fm.n_trainable, self.fm.n_total
+        has_tail = self.upload_mode != "weights_f32" and na > nt
+        if has_tail:        # buffers (BN running stats) are federated too: remember their incoming value
+            self.w_ref[nt:na].copy_(self.fm.flat[nt:na])
+        cur =torch.cuda.current_stream(self.device) if self.device.type == "cuda" else None
         on_host = n > 0 and batches[0][0].device.type == "cpu" and self.device.type == "cuda"
         events: List[Optional[torch.cuda.Event]] = [None, None]
         done: List[Optional[torch.cuda.Event]] = [None, None]
@@ -201,6 +208,8 @@ class FederatedTrainer:
                 d = torch.cuda.Event()
                 d.record(cur)
                 done[i & 1] = d
+        if has_tail:        # publish the buffer deltas next to the parameter deltas of the last step
+            fused_optim.delta_publish(self.fm.flat[nt:na], self.w_ref[nt:na], self.engine.upload[nt:na], 1.0)
         agg_w = weights if weights is not None else float(n_samples)
         self.engine.aggregate(agg_w)
         self.rounds += 1
