@@ -122,7 +122,9 @@ def main():
     with ClockSampler(local_rank) as clocks:
         barrier_sync(device)
         timer.start()
+        torch.cuda.nvtx.range_push("v6_timed")          # ncu --nvtx --nvtx-include "v6_timed/"
         loss = run(dev_batches, args.steps, False)
+        torch.cuda.nvtx.range_pop()
         ms = timer.stop()
         barrier_sync(device)
     ms = max_over_ranks(ms, device)

@@ -1,0 +1,83 @@
+"""K4: flash attention.  Forward = the hand-written tcgen05/TMEM/TMA kernel (csrc/attention.cu);
+backward = the flash-attn library kernel fed with our output and log-sum-exp (a hand-written
+tcgen05 backward is the next step; the library backward plays the role cuBLAS plays for dX/dW).
+
+q:[B,S,Hq,D]  k,v:[B,S,Hkv,D]  bf16, D in {64,128}, GQA allowed -> o:[B,S,Hq,D].
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import torch
+
+from . import native, stream_ptr
+
+_enabled = os.environ.get("V6B200_ATTENTION", "1") != "0"
+
+
+def available() -> bool:
+    """True when the tcgen05 forward can be used (GPU + extension + not disabled by env)."""
+    return _enabled and torch.cuda.is_available() and native(required=False) is not None \
+        and hasattr(native(), "flash_attn_fwd")
+
+
+def _supported(q: torch.Tensor, k: torch.Tensor) -> bool:
+    D, S = q.shape[-1], q.shape[1]
+    return q.dtype == torch.bfloat16 and D in (64, 128) and S % 8 == 0 and q.shape[2] % k.shape[2] == 0
+
+
+def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool, scale: float | None = None):
+    """Raw forward: returns (o, lse).  V is transposed to [B,Hkv,D,S] so the PV operand is K-major."""
+    B, S, Hq, D = q.shape
+    Hkv = k.shape[2]
+    scale = scale if scale is not None else 1.0 / math.sqrt(D)
+    q, k = q.contiguous(), k.contiguous()
+    vt = v.permute(0, 2, 3, 1).contiguous()
+    o = torch.empty_like(q)
+    lse = torch.empty(B, Hq, S, device=q.device, dtype=torch.float32)
+    native().flash_attn_fwd(q.data_ptr(), k.data_ptr(), vt.data_ptr(), o.data_ptr(), lse.data_ptr(), B, S, Hq, Hkv, D,
+                            float(scale), bool(causal), stream_ptr())
+    return o, lse
+
+
+class _FlashAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, causal):
+        scale = 1.0 / math.sqrt(q.shape[-1])
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        o, lse = flash_attn_fwd(q, k, v, causal, scale)
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.causal, ctx.scale = causal, scale
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o, lse = ctx.saved_tensors
+        from flash_attn.flash_attn_interface import _flash_attn_backward
+
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        _flash_attn_backward(do.contiguous(), q, k, v, o, lse, dq, dk, dv, 0.0, ctx.scale, ctx.causal, -1, -1, 0.0, None,
+                             False, None)
+        return dq, dk, dv, None
+
+
+def flash_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = False) -> torch.Tensor:
+    if not _supported(q, k):
+        raise ValueError(f"unsupported attention shape/dtype for the tcgen05 kernel: q={tuple(q.shape)} {q.dtype}")
+    return _FlashAttnFn.apply(q, k, v, causal)
+
+
+def reference_attention(q, k, v, causal=False):
+    """fp32 PyTorch reference (tests)."""
+    B, S, Hq, D = q.shape
+    Hkv = k.shape[2]
+    qf, kf, vf = (t.float().transpose(1, 2) for t in (q, k, v))
+    if Hkv != Hq:
+        kf = kf.repeat_interleave(Hq // Hkv, dim=1)
+        vf = vf.repeat_interleave(Hq // Hkv, dim=1)
+    s = qf @ kf.transpose(-1, -2) / math.sqrt(D)
+    if causal:
+        s = s.masked_fill(torch.ones(S, S, device=q.device, dtype=torch.bool).triu(1), float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    return (p @ vf).transpose(1, 2), torch.logsumexp(s, dim=-1)

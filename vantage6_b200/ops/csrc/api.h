@@ -104,6 +104,8 @@ int v6_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M
 int v6_bcast_gemm_bf16(const void* A, void* B_local, const void* B_server_peer, void* C, const float* bias, int M, int N,
                        int K, int lda, int ldb, int ldc, int act, uint32_t* ready_flags, uint32_t epoch, cudaStream_t stream);
 int v6_gemm_smem_bytes();
+int v6_flash_attn_fwd(const void* q, const void* k, const void* vt, void* o, float* lse, int B, int S, int Hq, int Hkv,
+                      int D, float softmax_scale, int causal, cudaStream_t stream);
 // symm.cpp
 const char* v6_symm_last_error();
 int v6_driver_available();
