@@ -152,6 +152,55 @@ def main():
     res["nccl_allreduce_4KB_us"] = 1e3 * timed(lambda: dist.all_reduce(small), iters=200, warm=20)
     agg.close()
 
+    # ------------------------------------------------------------ K1: broadcast fused with the first GEMM
+    if rank == 0 and args.out:      # K1 is the newest kernel: keep what we have if it takes the context down
+        os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+        with open(args.out + ".partial", "w") as f:
+            f.write(json.dumps(res) + "\n")
+    try:
+        from vantage6_b200.ops import gemm as G
+
+        M, Nw, K = 4096, 2304, 768            # BERT-base layer-0 QKV projection, batch 32 x seq 128
+        heap = SymmetricHeap(rank, world, dev)
+        wbuf = heap.alloc(Nw * K * 2, multicast=False)
+        w_srv = wbuf.view(torch.bfloat16, Nw * K).view(Nw, K)
+        gsrc = torch.Generator(device=dev).manual_seed(5)
+        w0 = (torch.randn(Nw, K, device=dev, generator=gsrc) * 0.05).to(torch.bfloat16)
+        if rank == 0:
+            w_srv.copy_(w0)
+        torch.cuda.synchronize()
+        dist.barrier()
+        x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+        w_local = torch.zeros(Nw, K, device=dev, dtype=torch.bfloat16)
+        flags = torch.zeros(((Nw + 255) // 256) * ((K + 63) // 64), device=dev, dtype=torch.int32)
+        y = G.bcast_gemm_bf16(x, w_local, wbuf.peer_ptrs[0], flags, 1)
+        torch.cuda.synchronize()
+        ref = x.float() @ w0.float().t()
+        err = ((y.float() - ref).abs().max() / ref.abs().max()).item()
+        assert err < 1e-2, f"K1 output mismatch {err}"
+        assert torch.equal(w_local, w0), "K1 did not materialise the weights locally"
+        ep = [1]
+
+        def k1():
+            ep[0] += 1
+            G.bcast_gemm_bf16(x, w_local, wbuf.peer_ptrs[0], flags, ep[0], out=y)
+        res["k1_bcast_gemm_ms"] = timed(k1, iters=20, warm=5)
+        wb = w0.clone() if rank == 0 else torch.empty_like(w0)
+
+        def base():
+            dist.broadcast(wb, src=0)
+            torch.matmul(x, wb.t(), out=y)
+        res["nccl_bcast_then_cublas_ms"] = timed(base, iters=20, warm=5)
+        res["plain_tcgen05_gemm_ms"] = timed(lambda: G.gemm_bf16(x, w_local, out=y), iters=20, warm=5)
+        res["k1_shape"] = [M, Nw, K]
+        dist.barrier()
+        del w_srv
+        heap.close()
+    except AssertionError:
+        raise
+    except Exception as e:  # noqa: BLE001 -- record, do not hide (e.g. TMA on a peer VA unsupported)
+        res["k1_error"] = repr(e)
+
     # ------------------------------------------------------------ large aggregation timing
     for server_mode in ("sharded", "central"):
         for mc in ("auto", False):

@@ -188,3 +188,16 @@ def test_fixtures_drop_all_respects_flag():
     counts = fixtures.load(app.db, ENTITIES)
     assert counts["organizations"] == 3 and counts["nodes"] == 2
     assert fixtures.load(app.db, ENTITIES)["organizations"] == 0         # idempotent
+
+
+def test_silent_nodes_are_marked_offline(server):
+    app, port = server
+    node = NodeClient("http://127.0.0.1", port, "/api")
+    node.authenticate("key-a")
+    assert app.db.get("node", node.node_id)["status"] == "online"
+    assert app.reap_silent_nodes(timeout_s=3600) == 0
+    time.sleep(0.05)
+    assert app.reap_silent_nodes(timeout_s=0.01) == 1
+    assert app.db.get("node", node.node_id)["status"] == "offline"
+    node.request(f"node/{node.node_id}", method="patch", json={"status": "online"})        # next heartbeat revives it
+    assert app.db.get("node", node.node_id)["status"] == "online"

@@ -188,7 +188,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool, m
     try:
         from ..ops import attention as A
 
-        if q.is_cuda and A.available() and mask is None:
+        if q.is_cuda and A.available() and mask is None and A._supported(q, k):
             return A.flash_attention(q, k, v, causal)
     except ImportError:
         pass

@@ -18,14 +18,16 @@ def rope_tables(seq_len: int, head_dim: int, theta: float = 500000.0, device="cp
 class _RopeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, cos, sin, pos_ids):
-        assert q.is_contiguous() and k.is_contiguous() and q.dtype == torch.bfloat16
+        assert q.dtype == torch.bfloat16
+        # rotate copies: q/k are usually views of a projection output, and autograd does not allow a
+        # multi-output Function to modify views in place
+        q, k = q.contiguous().clone(), k.contiguous().clone()
         B, S, Hq, D = q.shape
         Hkv = k.shape[2]
         native().rope(q.data_ptr(), k.data_ptr(), cos.data_ptr(), sin.data_ptr(),
                       0 if pos_ids is None else pos_ids.data_ptr(), B, S, Hq, Hkv, D, False, stream_ptr())
         ctx.save_for_backward(cos, sin, pos_ids if pos_ids is not None else torch.empty(0))
         ctx.has_pos = pos_ids is not None
-        ctx.mark_dirty(q, k)
         return q, k
 
     @staticmethod

@@ -874,8 +874,31 @@ class ServerApp:
 
         return Handler
 
+    def reap_silent_nodes(self, timeout_s: Optional[float] = None) -> int:
+        """Failure detection: a node whose last heartbeat is older than
+        ``node_timeout_s`` is marked offline and the collaboration is told.  Returns #nodes reaped."""
+        timeout_s = float(self.config.get("node_timeout_s", 60)) if timeout_s is None else timeout_s
+        cutoff = (_dt.datetime.now(_dt.timezone.utc) - _dt.timedelta(seconds=timeout_s)).isoformat()
+        n = 0
+        for node in self.db.query("SELECT * FROM node WHERE status='online' AND (last_seen IS NULL OR last_seen < ?)", (cutoff,)):
+            self.db.update("node", node["id"], status="offline")
+            self.events.emit("node-status-changed", {"id": node["id"], "name": node["name"], "online": False},
+                             [f"collaboration_{node['collaboration_id']}"])
+            log.warning("node %s (%s) missed its heartbeats: marked offline", node["id"], node["name"])
+            n += 1
+        return n
+
+    def _reaper_loop(self) -> None:
+        while self._httpd is not None:
+            time.sleep(5.0)
+            try:
+                self.reap_silent_nodes()
+            except Exception:  # noqa: BLE001
+                log.debug("reaper error", exc_info=True)
+
     def start(self, ip: str = "127.0.0.1", port: int = 5000, block: bool = False) -> int:
         """Serve; returns the bound port (``port=0`` picks a free one)."""
+        threading.Thread(target=lambda: (time.sleep(1.0), self._reaper_loop()), daemon=True).start()
         ThreadingHTTPServer.daemon_threads = True
         ThreadingHTTPServer.request_queue_size = 128
         self._httpd = ThreadingHTTPServer((ip, port), self.make_handler())
