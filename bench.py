@@ -87,8 +87,10 @@ def main():
     torch.backends.cudnn.benchmark = True
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.allow_tf32 = True
-    model = (resnet50() if args.model == "resnet50" else resnet_tiny(1000)).to(memory_format=torch.channels_last)
     b200 = args.impl == "b200"
+    # product arm: hand-written fused BN(+add)(+ReLU) kernels; baseline arm: stock BatchNorm2d / ReLU / add
+    model = (resnet50(fused_bn=b200) if args.model == "resnet50" else resnet_tiny(1000, fused_bn=b200))
+    model = model.to(memory_format=torch.channels_last)
     trainer = FederatedTrainer(
         model, imagenet_forward_loss, rank=rank, world=world, device=device, optimizer="sgd", lr=0.05, momentum=0.9,
         weight_decay=1e-4, server_mode=args.server_mode, server_opt=ServerOptConfig(args.server_opt, 1.0),
@@ -121,9 +123,11 @@ def main():
     timer = DeviceTimer(device)
     with ClockSampler(local_rank) as clocks:
         barrier_sync(device)
+        launches0 = trainer.native_launches
         timer.start()
         torch.cuda.nvtx.range_push("v6_timed")          # ncu --nvtx --nvtx-include "v6_timed/"
         loss = run(dev_batches, args.steps, False)
+        launches = trainer.native_launches - launches0
         torch.cuda.nvtx.range_pop()
         ms = timer.stop()
         barrier_sync(device)
@@ -161,7 +165,7 @@ def main():
                        "data_plane": trainer.engine.data_plane, "multicast": bool(trainer.engine.use_multicast),
                        "cuda_graph": bool(trainer.use_graph)},
             "clocks": clocks.summary(), "e2e": e2e,
-            "gpu_launches": trainer.launches_per_round(n_steps) * args.steps,
+            "gpu_launches": int(launches),
             "final_loss": loss_val, "comm_status": status,
             "nvlink_bytes_per_round_per_gpu": nv_bytes,
         }

@@ -12,37 +12,57 @@ import torch
 from torch import nn
 
 
+class _StockBNAct(nn.BatchNorm2d):
+    """Stock path with the same call signature as FusedBatchNormAct (baseline arm / comparisons)."""
+
+    def __init__(self, num_features: int, relu: bool = True):
+        super().__init__(num_features)
+        self.relu = relu
+
+    def forward(self, x, residual=None, relu=None):
+        relu = self.relu if relu is None else relu
+        y = super().forward(x)
+        if residual is not None:
+            y = y + residual
+        return torch.relu(y) if relu else y
+
+
+def _bn(planes: int, relu: bool, fused: bool) -> nn.Module:
+    if fused:
+        from ..ops.bn import FusedBatchNormAct
+
+        return FusedBatchNormAct(planes, relu=relu)
+    return _StockBNAct(planes, relu=relu)
+
+
 class Bottleneck(nn.Module):
     expansion = 4
 
-    def __init__(self, inplanes: int, planes: int, stride: int = 1, downsample: nn.Module | None = None):
+    def __init__(self, inplanes: int, planes: int, stride: int = 1, downsample: nn.Module | None = None,
+                 fused_bn: bool = True):
         super().__init__()
         self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
-        self.bn1 = nn.BatchNorm2d(planes)
+        self.bn1 = _bn(planes, True, fused_bn)
         self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
-        self.bn2 = nn.BatchNorm2d(planes)
+        self.bn2 = _bn(planes, True, fused_bn)
         self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
-        self.bn3 = nn.BatchNorm2d(planes * 4)
-        self.relu = nn.ReLU(inplace=True)
+        self.bn3 = _bn(planes * 4, True, fused_bn)
         self.downsample = downsample
 
     def forward(self, x):
-        idt = x
-        out = self.relu(self.bn1(self.conv1(x)))
-        out = self.relu(self.bn2(self.conv2(out)))
-        out = self.bn3(self.conv3(out))
-        if self.downsample is not None:
-            idt = self.downsample(x)
-        return self.relu(out + idt)
+        out = self.bn1(self.conv1(x))                      # BN + ReLU in one pass
+        out = self.bn2(self.conv2(out))
+        idt = x if self.downsample is None else self.downsample(x)
+        return self.bn3(self.conv3(out), residual=idt)     # BN + residual add + ReLU in one pass
 
 
 class ResNet(nn.Module):
-    def __init__(self, layers=(3, 4, 6, 3), num_classes: int = 1000, width: int = 64):
+    def __init__(self, layers=(3, 4, 6, 3), num_classes: int = 1000, width: int = 64, fused_bn: bool = True):
         super().__init__()
         self.inplanes = width
+        self.fused_bn = fused_bn
         self.conv1 = nn.Conv2d(3, width, 7, stride=2, padding=3, bias=False)
-        self.bn1 = nn.BatchNorm2d(width)
-        self.relu = nn.ReLU(inplace=True)
+        self.bn1 = _bn(width, True, fused_bn)
         self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
         self.layer1 = self._make_layer(width, layers[0])
         self.layer2 = self._make_layer(width * 2, layers[1], stride=2)
@@ -64,25 +84,25 @@ class ResNet(nn.Module):
         downsample = None
         if stride != 1 or self.inplanes != planes * 4:
             downsample = nn.Sequential(nn.Conv2d(self.inplanes, planes * 4, 1, stride=stride, bias=False),
-                                       nn.BatchNorm2d(planes * 4))
-        layers = [Bottleneck(self.inplanes, planes, stride, downsample)]
+                                       _bn(planes * 4, False, self.fused_bn))
+        layers = [Bottleneck(self.inplanes, planes, stride, downsample, self.fused_bn)]
         self.inplanes = planes * 4
-        layers += [Bottleneck(self.inplanes, planes) for _ in range(1, blocks)]
+        layers += [Bottleneck(self.inplanes, planes, fused_bn=self.fused_bn) for _ in range(1, blocks)]
         return nn.Sequential(*layers)
 
     def forward(self, x):
-        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.maxpool(self.bn1(self.conv1(x)))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.fc(torch.flatten(self.avgpool(x), 1))
 
 
-def resnet50(num_classes: int = 1000) -> ResNet:
-    return ResNet((3, 4, 6, 3), num_classes)
+def resnet50(num_classes: int = 1000, fused_bn: bool = True) -> ResNet:
+    return ResNet((3, 4, 6, 3), num_classes, fused_bn=fused_bn)
 
 
-def resnet_tiny(num_classes: int = 10) -> ResNet:
+def resnet_tiny(num_classes: int = 10, fused_bn: bool = True) -> ResNet:
     """Same code path at toy size (smoke tests, CPU tests)."""
-    return ResNet((1, 1, 1, 1), num_classes, width=8)
+    return ResNet((1, 1, 1, 1), num_classes, width=8, fused_bn=fused_bn)
 
 
 _MEAN = (0.485 * 255, 0.456 * 255, 0.406 * 255)

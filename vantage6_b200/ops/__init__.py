@@ -63,6 +63,16 @@ def cuda_ready() -> bool:
     return True
 
 
+# Number of launches of OUR kernels issued from Python (bench.py `gpu_launches`): wrappers call
+# count(n) next to each native call; kernels replayed inside a CUDA graph are accounted for by the
+# trainer (launches recorded at capture time x number of replays).
+LAUNCHES = [0]
+
+
+def count(n: int = 1) -> None:
+    LAUNCHES[0] += n
+
+
 def stream_ptr() -> int:
     import torch
 

@@ -1,0 +1,106 @@
+"""Fused BatchNorm2d (+ residual add) (+ ReLU) for channels-last bf16 activations (csrc/bn.cu).
+
+``FusedBatchNormAct`` is a drop-in ``nn.BatchNorm2d`` subclass (same parameters / buffers / state
+dict) whose forward takes the optional residual and fuses the activation:
+
+    y = relu( BN(x) + residual )
+
+On CUDA with channels-last bf16 inputs the hand-written kernels run (training: batch statistics,
+running-stat update, saved mean/rstd for the backward; eval: running statistics); anywhere else the
+stock PyTorch ops are used (CPU tests, fp32 inputs).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import count, native, stream_ptr
+
+_scratch: dict = {}
+
+
+def _get_scratch(device, C: int):
+    key = (str(device), C)
+    s = _scratch.get(key)
+    if s is None:
+        parts = 148 * 4
+        s = (torch.empty(parts * 2 * C, device=device, dtype=torch.float32),      # per-CTA partials
+             torch.empty(3 * C, device=device, dtype=torch.float32))              # bwd coefficients
+        _scratch[key] = s
+    return s
+
+
+def _fast_path(x: torch.Tensor) -> bool:
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4):
+        return False
+    C = x.shape[1]
+    cg = C // 8
+    return C % 8 == 0 and 1 <= cg <= 256 and (cg & (cg - 1)) == 0 and x.is_contiguous(memory_format=torch.channels_last)
+
+
+class _BNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, eps, momentum, relu):
+        N, C, H, W = x.shape
+        R = N * H * W
+        y = torch.empty_like(x)                              # preserves channels_last strides
+        mean = torch.empty(C, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(C, device=x.device, dtype=torch.float32)
+        scale_bias = torch.empty(2 * C, device=x.device, dtype=torch.float32)
+        part, _ = _get_scratch(x.device, C)
+        count(3)                                             # stats + finalize + apply
+        native().bn_fwd(x.data_ptr(), 0 if residual is None else residual.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                        0 if running_mean is None else running_mean.data_ptr(),
+                        0 if running_var is None else running_var.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                        scale_bias.data_ptr(), part.data_ptr(), R, C, eps, momentum, relu, stream_ptr())
+        ctx.save_for_backward(x, y if relu else None, gamma, mean, rstd)
+        ctx.relu, ctx.has_res, ctx.R, ctx.C = relu, residual is not None, R, C
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, gamma, mean, rstd = ctx.saved_tensors
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if ctx.has_res else None
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(gamma)
+        part, coef = _get_scratch(x.device, ctx.C)
+        count(3)                                             # reduce + finalize + apply
+        native().bn_bwd(dy.data_ptr(), 0 if y is None else y.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
+                        rstd.data_ptr(), dx.data_ptr(), 0 if dres is None else dres.data_ptr(), dgamma.data_ptr(),
+                        dbeta.data_ptr(), coef.data_ptr(), part.data_ptr(), ctx.R, ctx.C, ctx.relu, False, stream_ptr())
+        return dx, dres, dgamma, dbeta, None, None, None, None, None
+
+
+class FusedBatchNormAct(nn.BatchNorm2d):
+    """BatchNorm2d with fused residual add and ReLU (``relu`` is the module default, overridable per call)."""
+
+    def __init__(self, num_features: int, relu: bool = True, **kw):
+        super().__init__(num_features, **kw)
+        self.relu = relu
+
+    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None, relu: Optional[bool] = None) -> torch.Tensor:
+        relu = self.relu if relu is None else relu
+        if _fast_path(x) and (residual is None or (_fast_path(residual) and residual.shape == x.shape)):
+            mom = 0.1 if self.momentum is None else self.momentum
+            if self.training:
+                if self.num_batches_tracked is not None:
+                    self.num_batches_tracked.add_(1)
+                return _BNFn.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var, self.eps, mom,
+                                   relu)
+            # eval: per-channel affine from the running statistics, one fused pass
+            scale = self.weight.float() * torch.rsqrt(self.running_var + self.eps)
+            bias = self.bias.float() - self.running_mean * scale
+            y = torch.empty_like(x)
+            N, C, H, W = x.shape
+            native().bn_apply(x.data_ptr(), 0 if residual is None else residual.data_ptr(), scale.data_ptr(), bias.data_ptr(),
+                              y.data_ptr(), N * H * W, C, relu, stream_ptr())
+            return y
+        y = super().forward(x)
+        if residual is not None:
+            y = y + residual
+        return torch.relu(y) if relu else y

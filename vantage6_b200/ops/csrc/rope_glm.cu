@@ -61,80 +61,118 @@ extern "C" int v6_rope(void* q, void* k, const float* cos_t, const float* sin_t,
 // ----------------------------------------------------------------------------------------
 // K8: logistic-regression gradient in ONE pass over X (memory-bound, X read exactly once):
 //   z = X w + b ; p = sigmoid(z) ; r = p - y ; g_w = X^T r ; g_b = sum r ; loss = sum BCE
-// X:[rows, F] bf16 or fp32 row-major, F == 256 (BASELINE config 5) or any multiple of 256.
-// One warp per row: each lane owns 8 consecutive features per 256-chunk; the dot product is
-// a shuffle reduction; the X^T r outer-product accumulates in registers across rows; CTAs fold
-// through shared memory and emit one partial per CTA; `fold` sums the partials into
+// X:[rows, F] bf16 / fp32 row-major, F % 64 == 0, F <= 512; w = [coefficients (F), intercept].
+//
+// Mapping (v2; v1 used one warp per row and reached only 16% of HBM bandwidth -- one 16 B load in
+// flight per lane and a 5-step shuffle per row): a row is owned by 8 lanes, so a warp handles 4
+// rows at a time, 2x unrolled = 8 rows in flight per warp; lane l of the group reads vectors
+// l, l+8, l+16, ... of its row (8 lanes x 16 B = one 128 B line per access).  The dot product is a
+// 3-step shuffle inside the 8-lane group; X^T r accumulates in registers (F/8 per lane); warps and
+// lane groups fold through shared memory into one partial per CTA; `fold` sums the partials into
 // out = [g_w (F), g_b, loss, n_rows] -- exactly the payload handed to the K3 small all-reduce.
 // ----------------------------------------------------------------------------------------
 constexpr int GLM_THREADS = 256;
-constexpr int GLM_MAXCH = 4;          // up to F = 1024
 
-template <typename T>
-__global__ void __launch_bounds__(GLM_THREADS) glm_logistic_kernel(const T* __restrict__ X, const float* __restrict__ y,
-                                                                    const float* __restrict__ w,
-                                                                    float* __restrict__ part, int rows, int F) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int nwarp = GLM_THREADS / 32;
-    const int nch = F / 256;
-    float wr[GLM_MAXCH][8], g[GLM_MAXCH][8];
-#pragma unroll
-    for (int c = 0; c < GLM_MAXCH; ++c)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { g[c][k] = 0.f; wr[c][k] = (c < nch) ? w[c * 256 + lane * 8 + k] : 0.f; }
-    float gb = 0.f, loss = 0.f;
-    const float bias = w[F];          // w = [coefficients (F), intercept]
-    for (long long row = (long long)blockIdx.x * nwarp + wid; row < rows; row += (long long)gridDim.x * nwarp) {
-        float x[GLM_MAXCH][8];
-        float dot = 0.f;
-#pragma unroll
-        for (int c = 0; c < GLM_MAXCH; ++c) {
-            if (c < nch) {
-                const T* p = X + (size_t)row * F + c * 256 + lane * 8;
-                if constexpr (sizeof(T) == 2) {
-                    uint4 t;
-                    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                                 : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p));
-                    float2 a = unpack_bf16x2(t.x), b2 = unpack_bf16x2(t.y), c2 = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
-                    x[c][0] = a.x; x[c][1] = a.y; x[c][2] = b2.x; x[c][3] = b2.y;
-                    x[c][4] = c2.x; x[c][5] = c2.y; x[c][6] = d.x; x[c][7] = d.y;
-                } else {
-                    float4 a = ldg_stream_f4(reinterpret_cast<const float4*>(p));
-                    float4 b2 = ldg_stream_f4(reinterpret_cast<const float4*>(p) + 1);
-                    x[c][0] = a.x; x[c][1] = a.y; x[c][2] = a.z; x[c][3] = a.w;
-                    x[c][4] = b2.x; x[c][5] = b2.y; x[c][6] = b2.z; x[c][7] = b2.w;
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) dot = fmaf(x[c][k], wr[c][k], dot);
-            }
-        }
-        dot = warp_sum(dot) + bias;
-        const float yy = y[row];
-        const float p = 1.f / (1.f + __expf(-dot));
-        const float r = p - yy;
-        // numerically stable BCE: max(z,0) - z*y + log(1+exp(-|z|))
-        if (lane == 0) { loss += fmaxf(dot, 0.f) - dot * yy + log1pf(__expf(-fabsf(dot))); gb += r; }
-#pragma unroll
-        for (int c = 0; c < GLM_MAXCH; ++c)
-            if (c < nch) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) g[c][k] = fmaf(r, x[c][k], g[c][k]);
-            }
+template <typename T> struct GlmLoad;
+template <> struct GlmLoad<__nv_bfloat16> {
+    V6_DEVINL static void load(const __nv_bfloat16* p, float (&v)[8]) {
+        uint4 t;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p));
+        float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
     }
-    // fold the warps of this CTA
-    extern __shared__ float sm[];   // [nwarp][F + 2]
-    float* mine = sm + (size_t)wid * (F + 2);
+};
+template <> struct GlmLoad<float> {
+    V6_DEVINL static void load(const float* p, float (&v)[8]) {
+        float4 a = ldg_stream_f4(reinterpret_cast<const float4*>(p));
+        float4 b = ldg_stream_f4(reinterpret_cast<const float4*>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+};
+
+template <typename T, int NV /* 8-feature vectors per lane = F/64 */>
+__global__ void __launch_bounds__(GLM_THREADS, 2) glm_logistic_kernel(const T* __restrict__ X, const float* __restrict__ y,
+                                                                       const float* __restrict__ w,
+                                                                       float* __restrict__ part, int rows) {
+    constexpr int F = NV * 64;
+    constexpr int U = 2;                                       // row unroll per lane group
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int gl = lane & 7, grp = lane >> 3;                  // lane in group, group in warp
+    const int groups_per_cta = (GLM_THREADS / 32) * 4;
+    const int my_group = wid * 4 + grp;
+    float wr[NV][8], g[NV][8];
 #pragma unroll
-    for (int c = 0; c < GLM_MAXCH; ++c)
-        if (c < nch) {
+    for (int c = 0; c < NV; ++c)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) mine[c * 256 + lane * 8 + k] = g[c][k];
+        for (int k = 0; k < 8; ++k) { g[c][k] = 0.f; wr[c][k] = w[(c * 8 + gl) * 8 + k]; }
+    const float bias = w[F];
+    float gb = 0.f, loss = 0.f;
+    const long long stride = (long long)gridDim.x * groups_per_cta;
+    for (long long row0 = (long long)blockIdx.x * groups_per_cta + my_group; row0 < rows; row0 += stride * U) {
+        float x[U][NV][8];
+        float dot[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long row = row0 + u * stride;
+            dot[u] = 0.f;
+            if (row < rows) {
+#pragma unroll
+                for (int c = 0; c < NV; ++c) GlmLoad<T>::load(X + (size_t)row * F + (c * 8 + gl) * 8, x[u][c]);
+            }
         }
-    if (lane == 0) { mine[F] = gb; mine[F + 1] = loss; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long row = row0 + u * stride;
+            const bool ok = row < rows;                        // uniform inside the 8-lane group
+            if (ok) {
+#pragma unroll
+                for (int c = 0; c < NV; ++c)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) dot[u] = fmaf(x[u][c][k], wr[c][k], dot[u]);
+            }
+            float d = dot[u];
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            d += __shfl_xor_sync(0xffffffffu, d, 2);
+            d += __shfl_xor_sync(0xffffffffu, d, 4);
+            if (ok) {
+                const float z = d + bias;
+                const float yy = y[row];
+                const float r = 1.f / (1.f + __expf(-z)) - yy;
+                if (gl == 0) { loss += fmaxf(z, 0.f) - z * yy + log1pf(__expf(-fabsf(z))); gb += r; }
+#pragma unroll
+                for (int c = 0; c < NV; ++c)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) g[c][k] = fmaf(r, x[u][c][k], g[c][k]);
+            }
+        }
+    }
+    // fold the 4 lane groups of each warp (same gl -> same features), then the warps through smem
+#pragma unroll
+    for (int c = 0; c < NV; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float v = g[c][k];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            g[c][k] = v;
+        }
+    gb += __shfl_xor_sync(0xffffffffu, gb, 8);  gb += __shfl_xor_sync(0xffffffffu, gb, 16);
+    loss += __shfl_xor_sync(0xffffffffu, loss, 8);  loss += __shfl_xor_sync(0xffffffffu, loss, 16);
+    __shared__ float sm[(GLM_THREADS / 32) * (F + 2)];
+    float* mine = sm + wid * (F + 2);
+    if (grp == 0) {
+#pragma unroll
+        for (int c = 0; c < NV; ++c)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mine[(c * 8 + gl) * 8 + k] = g[c][k];
+        if (gl == 0) { mine[F] = gb; mine[F + 1] = loss; }
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < F + 2; i += GLM_THREADS) {
         float a = 0.f;
-        for (int w2 = 0; w2 < nwarp; ++w2) a += sm[(size_t)w2 * (F + 2) + i];
+#pragma unroll
+        for (int w2 = 0; w2 < GLM_THREADS / 32; ++w2) a += sm[w2 * (F + 2) + i];
         part[(size_t)blockIdx.x * (F + 2) + i] = a;
     }
 }
@@ -147,15 +185,29 @@ __global__ void glm_fold_kernel(const float* __restrict__ part, float* __restric
     }
     if (i == F + 2) out[F + 2] = rows;
 }
+
+template <typename T>
+static int launch_glm(const void* X, const float* y, const float* w, float* part, int grid, int rows, int F, cudaStream_t s) {
+    switch (F / 64) {
+        case 1: glm_logistic_kernel<T, 1><<<grid, GLM_THREADS, 0, s>>>((const T*)X, y, w, part, rows); break;
+        case 2: glm_logistic_kernel<T, 2><<<grid, GLM_THREADS, 0, s>>>((const T*)X, y, w, part, rows); break;
+        case 4: glm_logistic_kernel<T, 4><<<grid, GLM_THREADS, 0, s>>>((const T*)X, y, w, part, rows); break;
+        case 8: glm_logistic_kernel<T, 8><<<grid, GLM_THREADS, 0, s>>>((const T*)X, y, w, part, rows); break;
+        default: return (int)cudaErrorInvalidValue;
+    }
+    return 0;
+}
+
 extern "C" int v6_glm_logistic_grad(const void* X, const float* y, const float* w, float* part,
                                     int max_parts, float* out, int rows, int F, int bf16, cudaStream_t s) {
-    if (F % 256 != 0 || F > 256 * GLM_MAXCH) return (int)cudaErrorInvalidValue;
-    int grid = (rows + 7) / 8;
-    if (grid > 148 * 4) grid = 148 * 4;
+    if (F % 64 != 0 || F > 512) return (int)cudaErrorInvalidValue;
+    const int groups = (GLM_THREADS / 32) * 4;
+    int grid = (rows + groups * 2 - 1) / (groups * 2);
+    if (grid > 148 * 2) grid = 148 * 2;                          // 2 resident CTAs per SM, persistent over rows
     if (grid > max_parts) grid = max_parts;
-    const size_t smem = (size_t)(GLM_THREADS / 32) * (F + 2) * sizeof(float);
-    if (bf16) glm_logistic_kernel<__nv_bfloat16><<<grid, GLM_THREADS, smem, s>>>((const __nv_bfloat16*)X, y, w, part, rows, F);
-    else glm_logistic_kernel<float><<<grid, GLM_THREADS, smem, s>>>((const float*)X, y, w, part, rows, F);
+    if (grid < 1) grid = 1;
+    int rc = bf16 ? launch_glm<__nv_bfloat16>(X, y, w, part, grid, rows, F, s) : launch_glm<float>(X, y, w, part, grid, rows, F, s);
+    if (rc) return rc;
     V6_CHECK_LAUNCH();
     glm_fold_kernel<<<(F + 3 + 255) / 256, 256, 0, s>>>(part, out, grid, F, (float)rows);
     V6_CHECK_LAUNCH();

@@ -16,7 +16,7 @@ from typing import Optional
 
 import torch
 
-from . import native, stream_ptr
+from . import count, native, stream_ptr
 
 PUBLISH_NONE, PUBLISH_DELTA_F32, PUBLISH_DELTA_BF16, PUBLISH_WEIGHTS_F32 = 0, 1, 2, 3
 
@@ -50,6 +50,7 @@ class FlatSGD:
         first = (self.steps == 0) if first_momentum_step is None else first_momentum_step
         if self.params.is_cuda:
             assert n % 4 == 0, "flat buffers are padded to a multiple of 4 elements"
+            count(1)
             native().flat_optim(0, self.params.data_ptr(), grads.data_ptr(), self.buf.data_ptr(), 0, _ptr(w_ref),
                                 _ptr(upload), _ptr(shadow), _ptr(grad_scale), n, self.lr, self.momentum,
                                 self.dampening, self.weight_decay, 0.0, 0.0, 0.0, 1.0, 1.0, contrib_scale,
@@ -97,6 +98,7 @@ class FlatAdamW:
         n = self.params.numel()
         if self.params.is_cuda:
             assert n % 4 == 0
+            count(1)
             native().flat_optim(1, self.params.data_ptr(), grads.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                 _ptr(w_ref), _ptr(upload), _ptr(shadow), _ptr(grad_scale), n, self.lr, 0.0, 0.0,
                                 self.weight_decay, self.beta1, self.beta2, self.eps, bias1, bias2, contrib_scale,
@@ -164,6 +166,7 @@ def clip_grad_coef(grads: torch.Tensor, max_norm: float, scratch: Optional[torch
     """Global-norm clipping coefficient as a device scalar (consumed via ``grad_scale=``)."""
     if grads.is_cuda:
         scratch = scratch if scratch is not None else torch.empty(2, device=grads.device, dtype=torch.float32)
+        count(2)
         native().clip_coef(grads.data_ptr(), grads.numel(), float(max_norm), scratch[0:1].data_ptr(),
                            scratch[1:2].data_ptr(), stream_ptr())
         return scratch[1:2]

@@ -76,7 +76,8 @@ class FederatedTrainer:
         self._clip_scratch = torch.zeros(2, dtype=torch.float32, device=self.device) if max_grad_norm else None
         self.copy_stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
         self._staging: List[Tuple[torch.Tensor, torch.Tensor]] = []
-        self.kernel_launches_last_round = 0
+        self.native_launches = 0            # launches of OUR kernels so far (graph replays included)
+        self._graph_launches: dict = {}
         self.rounds = 0
 
     # ------------------------------------------------------------------ local step
@@ -128,8 +129,12 @@ class FederatedTrainer:
         torch.cuda.current_stream(self.device).wait_stream(s)
         g = torch.cuda.CUDAGraph()
         pool = next(iter(self._graphs.values())).pool() if self._graphs else None
+        from ..ops import LAUNCHES
+
+        before = LAUNCHES[0]
         with torch.cuda.graph(g, pool=pool):
             self._step_body(self._static_x, self._static_y, variant)
+        self._graph_launches[variant] = LAUNCHES[0] - before      # our kernels inside one replay
         self.engine.w.copy_(snap[0])
         if snap_opt is not None:
             self.opt.load_state_dict(snap_opt)
@@ -145,10 +150,15 @@ class FederatedTrainer:
             self._static_x.copy_(x, non_blocking=True)
             self._static_y.copy_(y, non_blocking=True)
             self._graphs[variant].replay()
+            self.native_launches += self._graph_launches.get(variant, 0)
             if self.opt is not None:
                 self.opt.steps += 1
         else:
+            from ..ops import LAUNCHES
+
+            before = LAUNCHES[0]
             self._step_body(x, y, variant)
+            self.native_launches += LAUNCHES[0] - before
 
     # ------------------------------------------------------------------ rounds
     def initialize_global(self) -> None:
@@ -212,6 +222,8 @@ class FederatedTrainer:
             fused_optim.delta_publish(self.fm.flat[nt:na], self.w_ref[nt:na], self.engine.upload[nt:na], 1.0)
         agg_w = weights if weights is not None else float(n_samples)
         self.engine.aggregate(agg_w)
+        if self.engine.data_plane == "native":
+            self.native_launches += 1 + (1 if has_tail else 0)
         self.rounds += 1
         return self.loss_sum / max(n, 1)
 
