@@ -31,13 +31,16 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 256;
 constexpr int BLOCK_K = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B atom
 constexpr int UMMA_K = 16;
-constexpr int kStages = 4;
+constexpr int kStages = 4;            // plain GEMM: 4-stage ring; K1: 3 stages + a 2-slot pull staging area
+constexpr int kStagesK1 = 3;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = 512;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;      // 16 KB
 constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;      // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // 48 KB
-constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int PULL_OFF = kStagesK1 * STAGE_BYTES;   // K1 pull staging: 2 x 32 KB after the 3-stage ring
+constexpr int BAR_OFF = PULL_OFF + 2 * B_BYTES;     // 208 KB (>= 4 x 48 KB of the plain ring)
+constexpr int SMEM_BYTES = BAR_OFF + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kThreads = 256;
 
 struct Params {
@@ -48,6 +51,7 @@ struct Params {
     int act;                   // 0 none, 1 gelu(erf), 2 relu
     // K1 fusion (all null/0 for the plain GEMM)
     int fused_bcast;
+    int stages;                // smem ring depth (kStages or kStagesK1)
     uint32_t* ready_flags;     // [num_n_blk * num_k_blk] local, zero before round 1
     uint32_t epoch;            // flags are compared against this monotonically increasing value
 };
@@ -61,18 +65,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
                  const Params P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tfull_bar = empty_bar + kStages;
     uint64_t* tempty_bar = tfull_bar + kAccStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kAccStages);
+    uint64_t* pull_bar = tempty_bar + kAccStages;       // [2] K1 pull staging
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pull_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_m = (P.M + BLOCK_M - 1) / BLOCK_M;
     const int num_n = (P.N + BLOCK_N - 1) / BLOCK_N;
     const int num_k = (P.K + BLOCK_K - 1) / BLOCK_K;
     const int num_tiles = num_m * num_n;
-    const int empty_count = P.fused_bcast ? 2 : 1;
+    const int empty_count = 1;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -82,6 +87,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], empty_count); }
         for (int s = 0; s < kAccStages; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        mbar_init(&pull_bar[0], 1); mbar_init(&pull_bar[1], 1);
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
@@ -90,11 +96,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // tile order: all m_blk==0 tiles first (they are the K1 pullers), then column-major sweeps
-    auto tile_coords = [&](int t, int& m_blk, int& n_blk) {
-        if (t < num_n) { m_blk = 0; n_blk = t; }
-        else { const int u = t - num_n; m_blk = 1 + u % (num_m - 1); n_blk = u / (num_m - 1); }
-    };
+    // tile order: m fastest, so CTAs running concurrently share the same weight column block (L2 reuse)
+    auto tile_coords = [&](int t, int& m_blk, int& n_blk) { m_blk = t % num_m; n_blk = t / num_m; };
 
     if (warp == 0) {
         // ============================ TMA producer ============================
@@ -103,29 +106,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 int m_blk, n_blk;
                 tile_coords(t, m_blk, n_blk);
-                const bool puller = P.fused_bcast && m_blk == 0;
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
                     mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                     tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-                    if (puller) {
-                        tma_load_2d(sb, &tmap_b_src, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);   // over NVLink
-                    } else {
-                        if (P.fused_bcast) {
-                            // wait until the puller tile has landed this weight tile locally
-                            const uint32_t* f = P.ready_flags + n_blk * num_k + kb;
-                            uint32_t spins = 0;
-                            while ((int32_t)(ld_acquire_sys_u32(f) - P.epoch) < 0) {
-                                __nanosleep(64);
-                                if (++spins > (1u << 24)) asm volatile("trap;");
-                            }
-                            asm volatile("fence.proxy.async.global;" ::: "memory");
+                    if (P.fused_bcast) {
+                        // K1: wait until some CTA's pull warp has landed this weight tile in the local copy
+                        const uint32_t* f = P.ready_flags + n_blk * num_k + kb;
+                        const long long t0 = clock64();
+                        while ((int32_t)(ld_acquire_sys_u32(f) - P.epoch) < 0) {
+                            __nanosleep(32);
+                            if (clock64() - t0 > 4000000000LL) asm volatile("trap;");
                         }
-                        tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+                        asm volatile("fence.proxy.async.global;" ::: "memory");
                     }
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -154,33 +152,50 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
                     if (kb == num_k - 1) umma_commit(&tfull_bar[acc]);
                 }
                 __syncwarp();
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                if (++stage == P.stages) { stage = 0; phase ^= 1; }
             }
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp == 3) {
-        // ============================ K1 write-back warp =======================
+        // ============================ K1 pull warp ============================
+        // Every CTA pulls its share of the weight tiles from the server GPU (TMA load through the
+        // peer-mapped VA, over NVLink) into a 2-slot staging area, TMA-stores them into the local
+        // weight buffer and publishes a per-tile ready flag.  Pull order is k-major so that the
+        // first k-blocks of every column land first; all CTAs pull in parallel (NVLink saturated)
+        // and never wait on anything but their own staging slots, so the GEMM tiles can start as
+        // soon as their first weight tiles are local: transfer and MMA overlap tile by tile.
         if (P.fused_bcast && lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                int m_blk, n_blk;
-                tile_coords(t, m_blk, n_blk);
-                for (int kb = 0; kb < num_k; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    if (m_blk == 0) {
-                        uint8_t* sb = smem + stage * STAGE_BYTES + A_BYTES;
-                        fence_proxy_async_smem();
-                        tma_store_2d(&tmap_b, sb, kb * BLOCK_K, n_blk * BLOCK_N);     // un-swizzles on the way out
-                        tma_store_commit();
-                        tma_store_wait_all();                                         // writes complete
-                        asm volatile("fence.proxy.async.global;" ::: "memory");
-                        __threadfence();
-                        st_release_sys_u32(P.ready_flags + n_blk * num_k + kb, P.epoch);
-                    }
-                    mbar_arrive(&empty_bar[stage]);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+            const int n_pull = num_k * num_n;
+            uint8_t* stg = smem + PULL_OFF;
+            int slot = 0; uint32_t ph[2] = {0, 0};
+            int issued = 0;
+            int first = blockIdx.x;
+            // software pipeline: load(i+1) is in flight while tile i is stored
+            auto issue_load = [&](int idx, int s) {
+                const int kb = idx / num_n, nb = idx % num_n;
+                mbar_expect_tx(&pull_bar[s], B_BYTES);
+                tma_load_2d(stg + s * B_BYTES, &tmap_b_src, &pull_bar[s], kb * BLOCK_K, nb * BLOCK_N);
+            };
+            if (first < n_pull) { issue_load(first, 0); issued = 1; }
+            for (int idx = first; idx < n_pull; idx += gridDim.x) {
+                const int nxt = idx + gridDim.x;
+                if (nxt < n_pull) {
+                    tma_store_wait_read();                    // staging slot (slot^1) no longer read by a store
+                    issue_load(nxt, slot ^ 1);
+                    ++issued;
                 }
+                mbar_wait(&pull_bar[slot], ph[slot]);
+                ph[slot] ^= 1;
+                const int kb = idx / num_n, nb = idx % num_n;
+                tma_store_2d(&tmap_b, stg + slot * B_BYTES, kb * BLOCK_K, nb * BLOCK_N);   // un-swizzles on the way out
+                tma_store_commit();
+                tma_store_wait_all();                         // bytes are in the local copy
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+                __threadfence();
+                st_release_sys_u32(P.ready_flags + nb * num_k + kb, P.epoch);
+                slot ^= 1;
             }
+            (void)issued;
         }
     } else if (warp >= 4) {
         // ============================ epilogue ================================
@@ -253,6 +268,7 @@ static int launch_gemm(const void* A, const void* B, const void* B_src, void* C,
     Params P;
     P.M = M; P.N = N; P.K = K; P.C = (__nv_bfloat16*)C; P.ldc = ldc; P.bias = bias; P.act = act;
     P.fused_bcast = B_src ? 1 : 0; P.ready_flags = ready_flags; P.epoch = epoch;
+    P.stages = B_src ? kStagesK1 : kStages;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
