@@ -75,11 +75,17 @@ def main():
             a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
             w = torch.randn(Nn, K, device=dev, dtype=torch.bfloat16)
             c = torch.empty(M, Nn, device=dev, dtype=torch.bfloat16)
-            ms = timeit(lambda: G.gemm_bf16(a, w, out=c), flush=False)
+            ms = timeit(lambda: G.gemm_bf16(a, w, out=c, variant="1cta"), flush=False)
             ms_ref = timeit(lambda: torch.matmul(a, w.t(), out=c), flush=False)
             fl = 2.0 * M * Nn * K
             rows.append({"M": M, "N": Nn, "K": K, "ms": ms, "tflops": fl / ms / 1e9, "frac_of_peak": fl / ms / 1e9 / tflops,
                          "cublas_ms": ms_ref, "cublas_tflops": fl / ms_ref / 1e9, "vs_cublas": ms_ref / ms})
+            if os.environ.get("V6B200_BENCH_2CTA", "1") == "1":
+                try:
+                    ms2 = timeit(lambda: G.gemm_bf16(a, w, out=c, variant="2cta"), flush=False)
+                    rows[-1].update({"ms_2cta": ms2, "tflops_2cta": fl / ms2 / 1e9, "frac_of_peak_2cta": fl / ms2 / 1e9 / tflops})
+                except Exception as e:  # noqa: BLE001
+                    rows[-1]["error_2cta"] = repr(e)
             print(rows[-1], flush=True)
         out["gemm_tcgen05"] = rows
 

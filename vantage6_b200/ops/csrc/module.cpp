@@ -169,6 +169,9 @@ PYBIND11_MODULE(_C, m) {
     m.def("gemm_bf16", [](u64 A, u64 B, u64 C, u64 bias, int M, int N, int K, int lda, int ldb, int ldc, int act, u64 s) {
         check(v6_gemm_bf16(P<void>(A), P<void>(B), P<void>(C), P<float>(bias), M, N, K, lda, ldb, ldc, act, S(s)), "gemm_bf16");
     });
+    m.def("gemm2_bf16", [](u64 A, u64 B, u64 C, u64 bias, int M, int N, int K, int lda, int ldb, int ldc, int act, u64 s) {
+        check(v6_gemm2_bf16(P<void>(A), P<void>(B), P<void>(C), P<float>(bias), M, N, K, lda, ldb, ldc, act, S(s)), "gemm2_bf16");
+    });
     m.def("bcast_gemm_bf16", [](u64 A, u64 B_local, u64 B_peer, u64 C, u64 bias, int M, int N, int K, int lda, int ldb, int ldc,
                                 int act, u64 flags, uint32_t epoch, u64 s) {
         check(v6_bcast_gemm_bf16(P<void>(A), P<void>(B_local), P<void>(B_peer), P<void>(C), P<float>(bias), M, N, K, lda, ldb,

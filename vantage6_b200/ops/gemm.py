@@ -15,7 +15,7 @@ from typing import Optional
 
 import torch
 
-from . import native, stream_ptr
+from . import count, native, stream_ptr
 
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 
@@ -28,7 +28,7 @@ def _check(x: torch.Tensor, W: torch.Tensor):
 
 
 def gemm_bf16(x2: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, variant: Optional[str] = None) -> torch.Tensor:
     """x2:[M,K], W:[N,K] -> [M,N] bf16 (raw op, no autograd)."""
     _check(x2, W)
     M, K = x2.shape
@@ -36,9 +36,24 @@ def gemm_bf16(x2: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = 
     assert N % 8 == 0
     if out is None:
         out = torch.empty(M, N, device=x2.device, dtype=torch.bfloat16)
-    native().gemm_bf16(x2.data_ptr(), W.data_ptr(), out.data_ptr(), 0 if bias is None else bias.data_ptr(),
-                       M, N, K, x2.stride(0), W.stride(0), out.stride(0), act, stream_ptr())
+    count(1)
+    C = native()
+    # 2-CTA (cta_group::2, 256x256 tiles) when there is enough work to fill 74 SM pairs; the 1-CTA
+    # 128x256 kernel otherwise (finer tiles -> better SM fill for small problems).
+    two_cta = _two_cta_default() if variant is None else variant == "2cta"
+    if two_cta and M >= 256 and N >= 256 and hasattr(C, "gemm2_bf16"):
+        C.gemm2_bf16(x2.data_ptr(), W.data_ptr(), out.data_ptr(), 0 if bias is None else bias.data_ptr(),
+                     M, N, K, x2.stride(0), W.stride(0), out.stride(0), act, stream_ptr())
+    else:
+        C.gemm_bf16(x2.data_ptr(), W.data_ptr(), out.data_ptr(), 0 if bias is None else bias.data_ptr(),
+                    M, N, K, x2.stride(0), W.stride(0), out.stride(0), act, stream_ptr())
     return out
+
+
+def _two_cta_default() -> bool:
+    import os
+
+    return os.environ.get("V6B200_GEMM_2CTA", "0") == "1"
 
 
 def bcast_gemm_bf16(x2: torch.Tensor, W_local: torch.Tensor, W_server_ptr: int, ready_flags: torch.Tensor,
