@@ -11,7 +11,7 @@ import os
 
 import torch
 
-from . import native, stream_ptr
+from . import count, native, stream_ptr
 
 _enabled = os.environ.get("V6B200_ATTENTION", "1") != "0"
 
@@ -41,6 +41,32 @@ def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
     return o, lse
 
 
+def _bwd_native() -> bool:
+    """Hand-written tcgen05 backward (csrc/attention_bwd.cu) vs the flash-attn library backward."""
+    return os.environ.get("V6B200_ATTN_BWD", "lib") == "native" and hasattr(native(), "flash_attn_bwd")
+
+
+def flash_attn_bwd(do: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, lse: torch.Tensor,
+                   causal: bool, scale: float | None = None):
+    """dQ, dK, dV on the tcgen05 kernels.  Pre-pass (plain torch ops): delta = rowsum(dO o O), lse in
+    log2 units, and the [B,H,D,S] transposes that make every MMA B operand K-major."""
+    B, S, Hq, D = q.shape
+    Hkv = k.shape[2]
+    scale = scale if scale is not None else 1.0 / math.sqrt(D)
+    do = do.contiguous()
+    delta = (do.float() * o.float()).sum(-1).permute(0, 2, 1).contiguous()            # [B,Hq,S]
+    lse2 = (lse * 1.4426950408889634).contiguous()
+    kt = k.permute(0, 2, 3, 1).contiguous()
+    qt = q.permute(0, 2, 3, 1).contiguous()
+    dot = do.permute(0, 2, 3, 1).contiguous()
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    count(2)
+    native().flash_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), do.data_ptr(), kt.data_ptr(), qt.data_ptr(),
+                            dot.data_ptr(), lse2.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                            B, S, Hq, Hkv, D, float(scale), bool(causal), stream_ptr())
+    return dq, dk, dv
+
+
 class _FlashAttnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, causal):
@@ -54,6 +80,9 @@ class _FlashAttnFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, do):
         q, k, v, o, lse = ctx.saved_tensors
+        if _bwd_native():
+            dq, dk, dv = flash_attn_bwd(do, q, k, v, o, lse, ctx.causal, ctx.scale)
+            return dq, dk, dv, None
         from flash_attn.flash_attn_interface import _flash_attn_backward
 
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)

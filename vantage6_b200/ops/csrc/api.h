@@ -103,6 +103,9 @@ int v6_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M
                  int act, cudaStream_t stream);
 int v6_bcast_gemm_bf16(const void* A, void* B_local, const void* B_server_peer, void* C, const float* bias, int M, int N,
                        int K, int lda, int ldb, int ldc, int act, uint32_t* ready_flags, uint32_t epoch, cudaStream_t stream);
+int v6_flash_attn_bwd(const void* q, const void* k, const void* v, const void* dout, const void* kt, const void* qt,
+                      const void* dot, const float* lse2, const float* delta, void* dq, void* dk, void* dv, int B, int S,
+                      int Hq, int Hkv, int D, float softmax_scale, int causal, cudaStream_t stream);
 int v6_bn_fwd(const void* x, const void* res, const float* gamma, const float* beta, float* running_mean, float* running_var,
               void* y, float* mean, float* rstd, float* scale_bias, float* scratch, long long R, int C, float eps,
               float momentum, int relu, cudaStream_t s);

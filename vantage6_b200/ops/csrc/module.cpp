@@ -179,6 +179,12 @@ PYBIND11_MODULE(_C, m) {
     });
     m.def("gemm_smem_bytes", &v6_gemm_smem_bytes);
 
+    m.def("flash_attn_bwd", [](u64 q, u64 k, u64 v, u64 dout, u64 kt, u64 qt, u64 dot, u64 lse2, u64 delta, u64 dq, u64 dk,
+                               u64 dv, int B, int Sq, int Hq, int Hkv, int D, float scale, bool causal, u64 s) {
+        check(v6_flash_attn_bwd(P<void>(q), P<void>(k), P<void>(v), P<void>(dout), P<void>(kt), P<void>(qt), P<void>(dot),
+                                P<float>(lse2), P<float>(delta), P<void>(dq), P<void>(dk), P<void>(dv), B, Sq, Hq, Hkv, D,
+                                scale, causal, S(s)), "flash_attn_bwd");
+    });
     // ------------------------------------------------------------------ K4 attention
     m.def("flash_attn_fwd", [](u64 q, u64 k, u64 vt, u64 o, u64 lse, int B, int Sq, int Hq, int Hkv, int D, float scale,
                                bool causal, u64 s) {
