@@ -20,7 +20,7 @@
 namespace bn {
 
 constexpr int THREADS = 256;
-constexpr int MAX_PARTS = 148 * 4;
+constexpr int MAX_PARTS = 148 * 2;
 
 V6_DEVINL void load8(const __nv_bfloat16* p, float (&v)[8]) {
     uint4 t = *reinterpret_cast<const uint4*>(p);
@@ -64,26 +64,57 @@ __global__ void __launch_bounds__(THREADS) bn_stats_kernel(const __nv_bfloat16* 
     load8(x + cg * 8, shift);                                   // row 0 as the per-channel shift
 #pragma unroll
     for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
-    for (long long r = (long long)blockIdx.x * RL + rl; r < R; r += (long long)gridDim.x * RL) {
-        float v[8];
-        load8(x + r * C + cg * 8, v);
+    const long long G = (long long)gridDim.x * RL;
+    for (long long r = (long long)blockIdx.x * RL + rl; r < R; r += 4 * G) {      // 4 independent 16 B loads in flight
+        float v[4][8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { const float d = v[k] - shift[k]; s1[k] += d; s2[k] = fmaf(d, d, s2[k]); }
+        for (int u = 0; u < 4; ++u)
+            if (r + u * G < R) load8(x + (r + u * G) * C + cg * 8, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (r + u * G < R) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const float d = v[u][k] - shift[k]; s1[k] += d; s2[k] = fmaf(d, d, s2[k]); }
+            }
     }
     fold_and_write(s1, s2, smem, part, C, cg, rl, RL);
 }
 
-// one thread per channel: mean / rstd, running stats, and the affine (scale, bias) of the apply pass
-__global__ void bn_fwd_finalize_kernel(const float* __restrict__ part, int nparts, const __nv_bfloat16* __restrict__ x,
+// Finalize kernels: block = 32 channels x 8 partial-slices (256 threads).  Each thread sums every 8th
+// partial with 4 independent loads in flight, the 8 slices are folded through shared memory, and the
+// slice-0 thread of each channel does the per-channel math.  (v1 used one thread per channel looping
+// over ~600 partials: latency-bound, 79 us per launch, 54% of the step in profiles/launches_*fusedbn*.)
+constexpr int FIN_THREADS = 256;
+V6_DEVINL int fold_parts(const float* __restrict__ part, int nparts, int C, float& a_out, float& b_out) {
+    __shared__ float sa[8][33], sb[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    float a = 0.f, b = 0.f;
+    if (c < C) {
+#pragma unroll 4
+        for (int p = ty; p < nparts; p += 8) {
+            a += part[(size_t)p * 2 * C + c];
+            b += part[(size_t)p * 2 * C + C + c];
+        }
+    }
+    sa[ty][tx] = a; sb[ty][tx] = b;
+    __syncthreads();
+    if (ty != 0 || c >= C) return -1;
+#pragma unroll
+    for (int s = 1; s < 8; ++s) { a += sa[s][tx]; b += sb[s][tx]; }
+    a_out = a; b_out = b;
+    return c;
+}
+
+__global__ void __launch_bounds__(FIN_THREADS) bn_fwd_finalize_kernel(const float* __restrict__ part, int nparts, const __nv_bfloat16* __restrict__ x,
                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                        float* __restrict__ running_mean, float* __restrict__ running_var,
                                        float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                        float* __restrict__ scale_out, float* __restrict__ bias_out,
                                        long long R, int C, float eps, float momentum) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    float a = 0.f, b = 0.f;
-    for (int p = 0; p < nparts; ++p) { a += part[(size_t)p * 2 * C + c]; b += part[(size_t)p * 2 * C + C + c]; }
+    float a, b;
+    const int c = fold_parts(part, nparts, C, a, b);
+    if (c < 0) return;
     const float shift = __bfloat162float(x[c]);
     const float invR = 1.f / (float)R;
     const float dm = a * invR;
@@ -111,23 +142,30 @@ __global__ void __launch_bounds__(THREADS) bn_apply_kernel(const __nv_bfloat16* 
     float sc[8], bi[8];
     loadf8(scale + cg * 8, sc);
     loadf8(bias + cg * 8, bi);
-    for (long long r = (long long)blockIdx.x * RL + rl; r < R; r += (long long)gridDim.x * RL) {
-        float v[8];
-        load8(x + r * C + cg * 8, v);
-        if (RES) {
-            float q[8];
-            load8(res + r * C + cg * 8, q);
+    const long long G = (long long)gridDim.x * RL;
+    for (long long r0 = (long long)blockIdx.x * RL + rl; r0 < R; r0 += 2 * G) {   // 2 rows x (x [+ res]) loads in flight
+        float v[2][8], q[2][8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], bi[k]) + q[k];
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], bi[k]);
+        for (int u = 0; u < 2; ++u) {
+            const long long r = r0 + u * G;
+            if (r < R) {
+                load8(x + r * C + cg * 8, v[u]);
+                if (RES) load8(res + r * C + cg * 8, q[u]);
+            }
         }
-        if (RELU) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+        for (int u = 0; u < 2; ++u) {
+            const long long r = r0 + u * G;
+            if (r < R) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float t = fmaf(v[u][k], sc[k], bi[k]);
+                    if (RES) t += q[u][k];
+                    v[u][k] = RELU ? fmaxf(t, 0.f) : t;
+                }
+                store8(y + r * C + cg * 8, v[u]);
+            }
         }
-        store8(y + r * C + cg * 8, v);
     }
 }
 
@@ -145,32 +183,43 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(const __nv_bfloa
     loadf8(rstd + cg * 8, rs);
 #pragma unroll
     for (int k = 0; k < 8; ++k) { sg[k] = 0.f; sgx[k] = 0.f; }
-    for (long long r = (long long)blockIdx.x * RL + rl; r < R; r += (long long)gridDim.x * RL) {
-        float g[8], xv[8];
-        load8(dy + r * C + cg * 8, g);
-        load8(x + r * C + cg * 8, xv);
-        if (RELU) {
-            float yv[8];
-            load8(y + r * C + cg * 8, yv);
+    const long long G = (long long)gridDim.x * RL;
+    for (long long r0 = (long long)blockIdx.x * RL + rl; r0 < R; r0 += 2 * G) {   // 2 rows x 3 tensors in flight
+        float g[2][8], xv[2][8], yv[2][8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) g[k] = yv[k] > 0.f ? g[k] : 0.f;
+        for (int u = 0; u < 2; ++u) {
+            const long long r = r0 + u * G;
+            if (r < R) {
+                load8(dy + r * C + cg * 8, g[u]);
+                load8(x + r * C + cg * 8, xv[u]);
+                if (RELU) load8(y + r * C + cg * 8, yv[u]);
+            }
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { sg[k] += g[k]; sgx[k] = fmaf(g[k], (xv[k] - mu[k]) * rs[k], sgx[k]); }
+        for (int u = 0; u < 2; ++u) {
+            if (r0 + u * G < R) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float gg = (RELU && !(yv[u][k] > 0.f)) ? 0.f : g[u][k];
+                    sg[k] += gg;
+                    sgx[k] = fmaf(gg, (xv[u][k] - mu[k]) * rs[k], sgx[k]);
+                }
+            }
+        }
     }
     fold_and_write(sg, sgx, smem, part, C, cg, rl, RL);
 }
 
 // per channel: dgamma, dbeta (accumulated into the flat fp32 grad buffer) and the coefficients of
 // dx = c0 * g + c1 * x + c2  with  c0 = gamma*rstd, c1 = -gamma*rstd^2*mean(g*xhat), c2 = -c0*mean(g) - c1*mean
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(FIN_THREADS) bn_bwd_finalize_kernel(
+                                       const float* __restrict__ part, int nparts, const float* __restrict__ gamma,
                                        const float* __restrict__ mean, const float* __restrict__ rstd,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef,
                                        long long R, int C, int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    float sg = 0.f, sgx = 0.f;
-    for (int p = 0; p < nparts; ++p) { sg += part[(size_t)p * 2 * C + c]; sgx += part[(size_t)p * 2 * C + C + c]; }
+    float sg, sgx;
+    const int c = fold_parts(part, nparts, C, sg, sgx);
+    if (c < 0) return;
     dgamma[c] = accumulate ? dgamma[c] + sgx : sgx;
     dbeta[c] = accumulate ? dbeta[c] + sg : sg;
     const float invR = 1.f / (float)R;
@@ -192,20 +241,32 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const __nv_bfloat
     loadf8(coef + cg * 8, c0);
     loadf8(coef + C + cg * 8, c1);
     loadf8(coef + 2 * C + cg * 8, c2);
-    for (long long r = (long long)blockIdx.x * RL + rl; r < R; r += (long long)gridDim.x * RL) {
-        float g[8], xv[8], o[8];
-        load8(dy + r * C + cg * 8, g);
-        load8(x + r * C + cg * 8, xv);
-        if (RELU) {
-            float yv[8];
-            load8(y + r * C + cg * 8, yv);
+    const long long G = (long long)gridDim.x * RL;
+    for (long long r0 = (long long)blockIdx.x * RL + rl; r0 < R; r0 += 2 * G) {
+        float g[2][8], xv[2][8], yv[2][8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) g[k] = yv[k] > 0.f ? g[k] : 0.f;
+        for (int u = 0; u < 2; ++u) {
+            const long long r = r0 + u * G;
+            if (r < R) {
+                load8(dy + r * C + cg * 8, g[u]);
+                load8(x + r * C + cg * 8, xv[u]);
+                if (RELU) load8(y + r * C + cg * 8, yv[u]);
+            }
         }
-        if (RES) store8(dres + r * C + cg * 8, g);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = fmaf(c0[k], g[k], fmaf(c1[k], xv[k], c2[k]));
-        store8(dx + r * C + cg * 8, o);
+        for (int u = 0; u < 2; ++u) {
+            const long long r = r0 + u * G;
+            if (r < R) {
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (RELU && !(yv[u][k] > 0.f)) g[u][k] = 0.f;
+                    o[k] = fmaf(c0[k], g[u][k], fmaf(c1[k], xv[u][k], c2[k]));
+                }
+                if (RES) store8(dres + r * C + cg * 8, g[u]);
+                store8(dx + r * C + cg * 8, o);
+            }
+        }
     }
 }
 
@@ -239,7 +300,7 @@ extern "C" int v6_bn_fwd(const void* x, const void* res, const float* gamma, con
     const size_t smem = (size_t)RL * C * 2 * sizeof(float);
     if (smem > 48 * 1024) cudaFuncSetAttribute(bn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     bn_stats_kernel<<<grid, THREADS, smem, s>>>((const __nv_bfloat16*)x, scratch, R, C);
-    bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(scratch, grid, (const __nv_bfloat16*)x, gamma, beta, running_mean,
+    bn_fwd_finalize_kernel<<<(C + 31) / 32, FIN_THREADS, 0, s>>>(scratch, grid, (const __nv_bfloat16*)x, gamma, beta, running_mean,
                                                            running_var, mean, rstd, scale_bias, scale_bias + C, R, C, eps, momentum);
     const int ag = apply_grid(R, C);
     const __nv_bfloat16* xx = (const __nv_bfloat16*)x;
@@ -295,7 +356,7 @@ extern "C" int v6_bn_bwd(const void* dy, const void* y, const void* x, const flo
         if (smem > 48 * 1024) cudaFuncSetAttribute(bn_bwd_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         bn_bwd_reduce_kernel<false><<<grid, THREADS, smem, s>>>(dyy, yy, xx, mean, rstd, scratch, R, C);
     }
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(scratch, grid, gamma, mean, rstd, dgamma, dbeta, coef, R, C, accumulate);
+    bn_bwd_finalize_kernel<<<(C + 31) / 32, FIN_THREADS, 0, s>>>(scratch, grid, gamma, mean, rstd, dgamma, dbeta, coef, R, C, accumulate);
     const int ag = apply_grid(R, C);
     __nv_bfloat16* dxx = (__nv_bfloat16*)dx;
     __nv_bfloat16* drr = (__nv_bfloat16*)dres;

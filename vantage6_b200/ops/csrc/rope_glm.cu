@@ -73,21 +73,35 @@ extern "C" int v6_rope(void* q, void* k, const float* cos_t, const float* sin_t,
 // ----------------------------------------------------------------------------------------
 constexpr int GLM_THREADS = 256;
 
+// Rows are kept in registers in their RAW storage format (bf16: one uint4 per 8 features) and unpacked
+// twice (dot product, then outer product): the unpack is 2 ALU ops per pair, the registers saved
+// (32 instead of 64 for two rows in flight) keep the kernel at 2 CTAs/SM without spills.
 template <typename T> struct GlmLoad;
 template <> struct GlmLoad<__nv_bfloat16> {
-    V6_DEVINL static void load(const __nv_bfloat16* p, float (&v)[8]) {
+    using Raw = uint4;
+    static constexpr int U = 2;                                // rows in flight per lane group
+    V6_DEVINL static Raw load_raw(const __nv_bfloat16* p) {
         uint4 t;
         asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                      : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p));
+        return t;
+    }
+    V6_DEVINL static void unpack(const Raw& t, float (&v)[8]) {
         float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
         v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
     }
 };
 template <> struct GlmLoad<float> {
-    V6_DEVINL static void load(const float* p, float (&v)[8]) {
-        float4 a = ldg_stream_f4(reinterpret_cast<const float4*>(p));
-        float4 b = ldg_stream_f4(reinterpret_cast<const float4*>(p) + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    struct Raw { float4 a, b; };
+    static constexpr int U = 1;
+    V6_DEVINL static Raw load_raw(const float* p) {
+        Raw r;
+        r.a = ldg_stream_f4(reinterpret_cast<const float4*>(p));
+        r.b = ldg_stream_f4(reinterpret_cast<const float4*>(p) + 1);
+        return r;
+    }
+    V6_DEVINL static void unpack(const Raw& r, float (&v)[8]) {
+        v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
     }
 };
 
@@ -96,7 +110,7 @@ __global__ void __launch_bounds__(GLM_THREADS, 2) glm_logistic_kernel(const T* _
                                                                        const float* __restrict__ w,
                                                                        float* __restrict__ part, int rows) {
     constexpr int F = NV * 64;
-    constexpr int U = 2;                                       // row unroll per lane group
+    constexpr int U = GlmLoad<T>::U;                           // row unroll per lane group
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gl = lane & 7, grp = lane >> 3;                  // lane in group, group in warp
     const int groups_per_cta = (GLM_THREADS / 32) * 4;
@@ -110,7 +124,7 @@ __global__ void __launch_bounds__(GLM_THREADS, 2) glm_logistic_kernel(const T* _
     float gb = 0.f, loss = 0.f;
     const long long stride = (long long)gridDim.x * groups_per_cta;
     for (long long row0 = (long long)blockIdx.x * groups_per_cta + my_group; row0 < rows; row0 += stride * U) {
-        float x[U][NV][8];
+        typename GlmLoad<T>::Raw xr[U][NV];
         float dot[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -118,7 +132,7 @@ __global__ void __launch_bounds__(GLM_THREADS, 2) glm_logistic_kernel(const T* _
             dot[u] = 0.f;
             if (row < rows) {
 #pragma unroll
-                for (int c = 0; c < NV; ++c) GlmLoad<T>::load(X + (size_t)row * F + (c * 8 + gl) * 8, x[u][c]);
+                for (int c = 0; c < NV; ++c) xr[u][c] = GlmLoad<T>::load_raw(X + (size_t)row * F + (c * 8 + gl) * 8);
             }
         }
 #pragma unroll
@@ -127,9 +141,12 @@ __global__ void __launch_bounds__(GLM_THREADS, 2) glm_logistic_kernel(const T* _
             const bool ok = row < rows;                        // uniform inside the 8-lane group
             if (ok) {
 #pragma unroll
-                for (int c = 0; c < NV; ++c)
+                for (int c = 0; c < NV; ++c) {
+                    float xv[8];
+                    GlmLoad<T>::unpack(xr[u][c], xv);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) dot[u] = fmaf(x[u][c][k], wr[c][k], dot[u]);
+                    for (int k = 0; k < 8; ++k) dot[u] = fmaf(xv[k], wr[c][k], dot[u]);
+                }
             }
             float d = dot[u];
             d += __shfl_xor_sync(0xffffffffu, d, 1);
@@ -141,9 +158,12 @@ __global__ void __launch_bounds__(GLM_THREADS, 2) glm_logistic_kernel(const T* _
                 const float r = 1.f / (1.f + __expf(-z)) - yy;
                 if (gl == 0) { loss += fmaxf(z, 0.f) - z * yy + log1pf(__expf(-fabsf(z))); gb += r; }
 #pragma unroll
-                for (int c = 0; c < NV; ++c)
+                for (int c = 0; c < NV; ++c) {
+                    float xv[8];
+                    GlmLoad<T>::unpack(xr[u][c], xv);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) g[c][k] = fmaf(r, x[u][c][k], g[c][k]);
+                    for (int k = 0; k < 8; ++k) g[c][k] = fmaf(r, xv[k], g[c][k]);
+                }
             }
         }
     }
