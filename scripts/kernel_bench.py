@@ -169,6 +169,45 @@ def main():
         out["rope"] = {"ms": ms, "GBps": byts / ms / 1e6, "frac_of_hbm": byts / ms / 1e6 / hbm, "torch_ms": ms_t}
         print(out["rope"], flush=True)
 
+    if "attn" in only:
+        from vantage6_b200.ops import attention as A
+
+        rows = []
+        for (B, S, Hq, Hkv, D, causal) in [(32, 128, 12, 12, 64, False), (8, 512, 12, 12, 64, False), (4, 2048, 32, 8, 128, True),
+                                           (2, 4096, 32, 8, 128, True), (8, 1024, 32, 8, 128, False)]:
+            q = torch.randn(B, S, Hq, D, device=dev, dtype=torch.bfloat16)
+            k = torch.randn(B, S, Hkv, D, device=dev, dtype=torch.bfloat16)
+            v = torch.randn(B, S, Hkv, D, device=dev, dtype=torch.bfloat16)
+            fl = 4.0 * B * Hq * S * S * D * (0.5 if causal else 1.0)
+            ms = timeit(lambda: A.flash_attn_fwd(q, k, v, causal), flush=False)
+            row = {"B": B, "S": S, "Hq": Hq, "Hkv": Hkv, "D": D, "causal": causal, "fwd_ms": ms, "fwd_tflops": fl / ms / 1e9}
+            try:
+                from flash_attn import flash_attn_func
+
+                ms_fa = timeit(lambda: flash_attn_func(q, k, v, causal=causal), flush=False)
+                row.update(flash_attn2_ms=ms_fa, flash_attn2_tflops=fl / ms_fa / 1e9, vs_flash_attn2=ms_fa / ms)
+            except Exception as e:  # noqa: BLE001
+                row["flash_attn2_error"] = repr(e)[:100]
+            qt, kt, vt = q.transpose(1, 2), k.transpose(1, 2).repeat_interleave(Hq // Hkv, 1), v.transpose(1, 2).repeat_interleave(Hq // Hkv, 1)
+            ms_sd = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qt, kt, vt, is_causal=causal), flush=False)
+            row.update(sdpa_ms=ms_sd, sdpa_tflops=fl / ms_sd / 1e9)
+            try:
+                o, lse = A.flash_attn_fwd(q, k, v, causal)
+                do = torch.randn_like(o)
+                msb = timeit(lambda: A.flash_attn_bwd(do, q, k, v, o, lse, causal), flush=False)
+                row.update(bwd_native_ms=msb, bwd_native_tflops=2.5 * fl / msb / 1e9)
+                from flash_attn.flash_attn_interface import _flash_attn_backward
+
+                dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+                sc = 1.0 / (D ** 0.5)
+                msl = timeit(lambda: _flash_attn_backward(do, q, k, v, o, lse, dq, dk, dv, 0.0, sc, causal, -1, -1, 0.0, None, False, None), flush=False)
+                row.update(bwd_flash_attn2_ms=msl, bwd_flash_attn2_tflops=2.5 * fl / msl / 1e9)
+            except Exception as e:  # noqa: BLE001
+                row["bwd_native_error"] = repr(e)[:100]
+            rows.append(row)
+            print(row, flush=True)
+        out["attention"] = rows
+
     if "k2" in only:
         from vantage6_b200.parallel.fedavg import FedAvgEngine, ServerOptConfig
 

@@ -64,6 +64,7 @@ struct OptimParams {
     const float* grad_scale_ptr;   // (optional) device scalar multiplied into g (loss-scale / clip)
     long long n;           // elements, multiple of 4
     float lr, momentum, dampening, weight_decay, beta1, beta2, eps, bias1, bias2;
+    const float* bias_ptr;         // (optional) device [2]: Adam bias corrections computed on device (CUDA-graph safe)
     float contrib_scale;   // n_i
     int nesterov;
     int save_ref;          // 1: w_ref <- w(before step)
@@ -84,6 +85,7 @@ int v6_flat_sgd(const OptimParams* hp, cudaStream_t s);
 int v6_flat_adamw(const OptimParams* hp, cudaStream_t s);
 int v6_delta_publish(const float* w, const float* ref, void* upload, long long n, float scale, int bf16_out, cudaStream_t s);
 int v6_cast_bf16(const float* src, void* dst, long long n, cudaStream_t s);
+int v6_adam_bias_update(int* step_counter, float beta1, float beta2, float* bias_out, cudaStream_t s);
 int v6_clip_coef(const float* g, long long n, float max_norm, float* sumsq_scratch, float* coef, cudaStream_t s);
 int v6_layernorm_fwd(const void* x, const void* residual, const float* gamma, const float* beta, void* y, void* res_out,
                      float* mean, float* rstd, int rows, int cols, float eps, int bf16, cudaStream_t s);

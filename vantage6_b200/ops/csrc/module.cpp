@@ -99,15 +99,20 @@ PYBIND11_MODULE(_C, m) {
     m.def("flat_optim",
           [](int kind, u64 w, u64 g, u64 mm, u64 v, u64 w_ref, u64 upload, u64 shadow, u64 grad_scale_ptr, long long n,
              float lr, float momentum, float dampening, float weight_decay, float beta1, float beta2, float eps, float bias1,
-             float bias2, float contrib_scale, bool nesterov, bool save_ref, int publish, bool first_momentum_step, u64 stream) {
+             float bias2, float contrib_scale, bool nesterov, bool save_ref, int publish, bool first_momentum_step, u64 stream,
+             u64 bias_ptr) {
               OptimParams p;
               p.w = P<float>(w); p.g = P<float>(g); p.m = P<float>(mm); p.v = P<float>(v); p.w_ref = P<float>(w_ref);
               p.upload = P<void>(upload); p.shadow = P<void>(shadow); p.grad_scale_ptr = P<float>(grad_scale_ptr); p.n = n;
               p.lr = lr; p.momentum = momentum; p.dampening = dampening; p.weight_decay = weight_decay; p.beta1 = beta1;
               p.beta2 = beta2; p.eps = eps; p.bias1 = bias1; p.bias2 = bias2; p.contrib_scale = contrib_scale;
+              p.bias_ptr = P<float>(bias_ptr);
               p.nesterov = nesterov; p.save_ref = save_ref; p.publish = publish; p.first_momentum_step = first_momentum_step;
               check(kind == 0 ? v6_flat_sgd(&p, S(stream)) : v6_flat_adamw(&p, S(stream)), "flat_optim");
           });
+    m.def("adam_bias_update", [](u64 step, float beta1, float beta2, u64 out, u64 s) {
+        check(v6_adam_bias_update(P<int>(step), beta1, beta2, P<float>(out), S(s)), "adam_bias_update");
+    });
     m.def("delta_publish", [](u64 w, u64 ref, u64 upload, long long n, float scale, bool bf16_out, u64 s) {
         check(v6_delta_publish(P<float>(w), P<float>(ref), P<void>(upload), n, scale, bf16_out, S(s)), "delta_publish");
     });

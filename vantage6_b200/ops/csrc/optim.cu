@@ -15,6 +15,8 @@
 template <int KIND /*0 sgd, 1 adamw*/>
 __global__ void __launch_bounds__(512, 2) flat_optim_kernel(const OptimParams P) {
     const float gs = P.grad_scale_ptr ? *P.grad_scale_ptr : 1.f;
+    const float bias1 = P.bias_ptr ? P.bias_ptr[0] : P.bias1;
+    const float bias2 = P.bias_ptr ? P.bias_ptr[1] : P.bias2;
     const long long n4 = P.n >> 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
          i += (long long)gridDim.x * blockDim.x) {
@@ -42,8 +44,8 @@ __global__ void __launch_bounds__(512, 2) flat_optim_kernel(const OptimParams P)
                 w[k] *= (1.f - P.lr * P.weight_decay);                 // decoupled decay
                 m[k] = fmaf(P.beta1, m[k], (1.f - P.beta1) * g[k]);
                 v[k] = fmaf(P.beta2, v[k], (1.f - P.beta2) * g[k] * g[k]);
-                const float mh = m[k] * P.bias1;                       // bias1 = 1/(1-b1^t)
-                const float vh = v[k] * P.bias2;
+                const float mh = m[k] * bias1;                       // bias1 = 1/(1-b1^t)
+                const float vh = v[k] * bias2;
                 w[k] = fmaf(-P.lr, mh / (sqrtf(vh) + P.eps), w[k]);
             }
             reinterpret_cast<float4*>(P.v)[i] = make_float4(v[0], v[1], v[2], v[3]);
@@ -138,6 +140,17 @@ __global__ void clip_coef_kernel(const float* sumsq, float max_norm, float* coef
     const float nrm = sqrtf(*sumsq);
     *coef = fminf(1.f, max_norm / (nrm + 1e-6f));
 }
+// step counter lives on the device so that a captured CUDA graph advances Adam's bias correction
+__global__ void adam_bias_kernel(int* step, float beta1, float beta2, float* out) {
+    const int t = ++(*step);
+    out[0] = 1.f / (1.f - powf(beta1, (float)t));
+    out[1] = 1.f / (1.f - powf(beta2, (float)t));
+}
+extern "C" int v6_adam_bias_update(int* step_counter, float beta1, float beta2, float* bias_out, cudaStream_t s) {
+    adam_bias_kernel<<<1, 1, 0, s>>>(step_counter, beta1, beta2, bias_out);
+    V6_CHECK_LAUNCH(); return 0;
+}
+
 extern "C" int v6_clip_coef(const float* g, long long n, float max_norm, float* sumsq_scratch, float* coef, cudaStream_t s) {
     cudaMemsetAsync(sumsq_scratch, 0, sizeof(float), s);
     sumsq_kernel<<<optim_grid(n), 512, 0, s>>>(g, n / 4, sumsq_scratch);

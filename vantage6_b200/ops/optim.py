@@ -54,7 +54,7 @@ class FlatSGD:
             native().flat_optim(0, self.params.data_ptr(), grads.data_ptr(), self.buf.data_ptr(), 0, _ptr(w_ref),
                                 _ptr(upload), _ptr(shadow), _ptr(grad_scale), n, self.lr, self.momentum,
                                 self.dampening, self.weight_decay, 0.0, 0.0, 0.0, 1.0, 1.0, contrib_scale,
-                                self.nesterov, save_ref, publish, first, stream_ptr())
+                                self.nesterov, save_ref, publish, first, stream_ptr(), 0)
         else:
             reference_sgd_step(self.params, grads, self.buf, self.lr, self.momentum, self.dampening,
                                self.weight_decay, self.nesterov, first, w_ref=w_ref, save_ref=save_ref, upload=upload,
@@ -81,6 +81,8 @@ class FlatAdamW:
     steps: int = 0
     m: torch.Tensor = field(default=None)  # type: ignore[assignment]
     v: torch.Tensor = field(default=None)  # type: ignore[assignment]
+    _dev_step: Optional[torch.Tensor] = None
+    _dev_bias: Optional[torch.Tensor] = None
 
     def __post_init__(self):
         assert self.params.dtype == torch.float32 and self.params.is_contiguous()
@@ -91,7 +93,8 @@ class FlatAdamW:
 
     def step(self, grads: torch.Tensor, *, w_ref: Optional[torch.Tensor] = None, save_ref: bool = False,
              upload: Optional[torch.Tensor] = None, publish: int = PUBLISH_NONE, contrib_scale: float = 1.0,
-             shadow: Optional[torch.Tensor] = None, grad_scale: Optional[torch.Tensor] = None) -> None:
+             shadow: Optional[torch.Tensor] = None, grad_scale: Optional[torch.Tensor] = None,
+             device_step: bool = False) -> None:
         self.steps += 1
         bias1 = 1.0 / (1.0 - self.beta1 ** self.steps)
         bias2 = 1.0 / (1.0 - self.beta2 ** self.steps)
@@ -99,10 +102,19 @@ class FlatAdamW:
         if self.params.is_cuda:
             assert n % 4 == 0
             count(1)
+            bias_ptr = 0
+            if device_step:
+                # CUDA-graph safe: the step counter and the bias corrections live on the device
+                if self._dev_step is None:
+                    self._dev_step = torch.full((1,), self.steps - 1, dtype=torch.int32, device=self.params.device)
+                    self._dev_bias = torch.zeros(2, dtype=torch.float32, device=self.params.device)
+                count(1)
+                native().adam_bias_update(self._dev_step.data_ptr(), self.beta1, self.beta2, self._dev_bias.data_ptr(), stream_ptr())
+                bias_ptr = self._dev_bias.data_ptr()
             native().flat_optim(1, self.params.data_ptr(), grads.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                 _ptr(w_ref), _ptr(upload), _ptr(shadow), _ptr(grad_scale), n, self.lr, 0.0, 0.0,
                                 self.weight_decay, self.beta1, self.beta2, self.eps, bias1, bias2, contrib_scale,
-                                False, save_ref, publish, False, stream_ptr())
+                                False, save_ref, publish, False, stream_ptr(), bias_ptr)
         else:
             reference_adamw_step(self.params, grads, self.m, self.v, self.lr, self.beta1, self.beta2, self.eps,
                                  self.weight_decay, self.steps, w_ref=w_ref, save_ref=save_ref, upload=upload,
@@ -115,6 +127,8 @@ class FlatAdamW:
         self.m.copy_(sd["m"])
         self.v.copy_(sd["v"])
         self.steps = int(sd["steps"])
+        if self._dev_step is not None:
+            self._dev_step.fill_(self.steps)
 
 
 # ----------------------------------------------------------------------------------------------

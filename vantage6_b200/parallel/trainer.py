@@ -106,7 +106,9 @@ class FederatedTrainer:
         if isinstance(self.opt, fused_optim.FlatSGD):
             self.opt.step(self.fm.grad, grad_scale=gs, shadow=shadow, first_momentum_step=False if self.use_graph else None, **kw)
         else:
-            self.opt.step(self.fm.grad, grad_scale=gs, shadow=shadow, **kw)
+            # device_step: Adam's step counter / bias corrections live on the GPU so the captured
+            # graph advances them on every replay
+            self.opt.step(self.fm.grad, grad_scale=gs, shadow=shadow, device_step=bool(self.use_graph), **kw)
 
     def _variant(self, i: int, n: int) -> str:
         if self.upload_mode == "weights_f32":
@@ -144,7 +146,7 @@ class FederatedTrainer:
     def local_step(self, x: torch.Tensor, y: torch.Tensor, i: int = 0, n: int = 1) -> None:
         """One local optimisation step on device-resident (x, y)."""
         variant = self._variant(i, n)
-        if self.use_graph and not isinstance(self.opt, fused_optim.FlatAdamW) and self.torch_opt is None:
+        if self.use_graph and self.torch_opt is None:
             if variant not in self._graphs:
                 self._graphs[variant] = self._capture(variant, x, y)
             self._static_x.copy_(x, non_blocking=True)
