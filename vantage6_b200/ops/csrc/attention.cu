@@ -10,12 +10,13 @@
 //   warp 1   MMA issuer (one lane):  S_j = Q K_j^T  (SS, 128x128xD)  into TMEM S[j%2]
 //                                    O  += P_j V_j  (TS: A = P_j from TMEM, 128xDx128) into TMEM O
 //            S_{j+1} is issued before softmax_j finishes, so the tensor pipe overlaps the softmax.
-//   warp 2   TMEM allocator (512 columns: S0 | S1 | O)
+//   warp 2   TMEM allocator (512 columns: S0 | S1 | O | P0 | P1)
 //   warps 4-7  softmax: thread == query row (tcgen05.ld 32x32b gives each thread its own row ->
 //            row max / row sum need no shuffles); online softmax with LAZY rescaling: the running
 //            max is only raised when the tile max exceeds it by > 8 (log2 units); only then is O
-//            (in TMEM) rescaled, after waiting for the previous PV MMA.  P_j is written back as
-//            packed bf16 over S_j's own columns (tcgen05.st) and consumed by the PV MMA from TMEM.
+//            (in TMEM) rescaled, after waiting for the previous PV MMA.  P_j is written as packed
+//            bf16 into its own TMEM columns (tcgen05.st) and consumed by the PV MMA from TMEM; one
+//            sweep over S produces both P and the tile max (optimistic single-pass softmax).
 #include <cuda.h>
 #include "common.cuh"
 #include "api.h"
@@ -26,7 +27,7 @@ constexpr int BM = 128;          // query rows per CTA
 constexpr int BN = 128;          // keys per KV tile
 constexpr int kThreads = 256;
 constexpr int kTmemCols = 512;
-constexpr int S_COL0 = 0, S_COL1 = 128, O_COL = 256;
+constexpr int S_COL0 = 0, S_COL1 = 128, O_COL = 256, P_COL0 = 384, P_COL1 = 448;   // P: 64 packed-bf16 columns each
 
 struct Params {
     __nv_bfloat16* O;     // [B,S,Hq,D]
@@ -142,7 +143,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq*D] 
             mbar_wait(&v_full[st], (j >> 1) & 1);
             tcgen05_fence_after();
             if (lane == 0) {
-                const uint32_t p_tmem = tmem_base + (st ? S_COL1 : S_COL0);
+                const uint32_t p_tmem = tmem_base + (st ? P_COL1 : P_COL0);
                 const uint32_t vb = smem_u32(sV + st * V_BYTES);
 #pragma unroll
                 for (int kk = 0; kk < BN / 16; ++kk)
@@ -168,28 +169,57 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq*D] 
             tcgen05_fence_after();
             const int key0 = j * BN;
             const bool need_mask = (key0 + BN > P.S) || (CAUSAL && key0 + BN - 1 > m0);
-            // ---- pass 1: row max
-            float mx = -INFINITY;
+            const uint32_t p_tmem = tmem_base + lane_addr + (st ? P_COL1 : P_COL0);
+            // One sweep over S computes P = exp2(S*c - m) AND the tile max.  m is the running
+            // ("lazy") max: it is only raised when the tile max exceeds it by more than 8 (log2 units);
+            // then -- rarely, after the first tiles -- O is rescaled and the sweep is repeated with the
+            // new m (P lives in its own TMEM columns, so S is still intact for the second sweep).
+            // The very first tile has no estimate yet: it gets a max-only sweep first.
+            auto sweep = [&](bool want_p, float m_ref, float& mx_out, float& l_out) {
+                float mx = -INFINITY, lsum = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(s_tmem + c, v);
-                tmem_ld_wait();
-                if (need_mask) {
+                for (int c2 = 0; c2 < BN; c2 += 64) {
+                    uint32_t pk[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int key = key0 + c + i;
-                        const bool ok = key < P.S && (!CAUSAL || key <= row);
-                        mx = fmaxf(mx, ok ? __uint_as_float(v[i]) : -INFINITY);
+                    for (int half = 0; half < 2; ++half) {
+                        const int c = c2 + half * 32;
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(s_tmem + c, v);
+                        tmem_ld_wait();
+                        float p[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float sv = __uint_as_float(v[i]);
+                            bool ok = true;
+                            if (need_mask) {
+                                const int key = key0 + c + i;
+                                ok = key < P.S && (!CAUSAL || key <= row);
+                            }
+                            mx = fmaxf(mx, ok ? sv : -INFINITY);
+                            if (want_p) {
+                                const float e = ok ? exp2f(fmaf(sv, P.scale_log2, -m_ref)) : 0.f;
+                                p[i] = e;
+                                lsum += e;
+                            }
+                        }
+                        if (want_p) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) pk[half * 16 + i] = pack_bf16x2(p[2 * i], p[2 * i + 1]);
+                        }
                     }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    if (want_p) tmem_st_32x32b_x32(p_tmem + (c2 >> 1), pk);
                 }
+                mx_out = mx; l_out = lsum;
+            };
+            float mx, l_tile;
+            if (j == 0) {
+                sweep(false, 0.f, mx, l_tile);
+                const float m0v = mx * P.scale_log2;
+                m_used = (m0v == -INFINITY) ? 0.f : m0v;
             }
+            sweep(true, m_used, mx, l_tile);
             const float m_new = mx * P.scale_log2;
-            bool raise = m_new > m_used + 8.f;               // lazy rescaling threshold (log2 units)
-            if (j == 0) { m_used = (m_new == -INFINITY) ? 0.f : m_new; raise = false; }
+            const bool raise = j > 0 && m_new > m_used + 8.f;
             if (__any_sync(0xffffffffu, raise)) {
                 // O must be rescaled: wait until PV_{j-1} has retired, then scale this thread's row
                 mbar_wait(pv_done, (j - 1) & 1);
@@ -205,34 +235,9 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq*D] 
                     for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
                     tmem_st_32x32b_x32(tmem_base + lane_addr + O_COL + c, v);
                 }
-                tmem_st_wait();
+                sweep(true, m_used, mx, l_tile);              // redo P with the raised max
             }
-            // ---- pass 2: P = exp2(S*scale - m), row sum, pack to bf16 over S's own columns
-#pragma unroll 1
-            for (int c2 = 0; c2 < BN; c2 += 64) {
-                uint32_t pk[32];
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int c = c2 + half * 32;
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(s_tmem + c, v);
-                    tmem_ld_wait();
-                    float p[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float e = exp2f(fmaf(__uint_as_float(v[i]), P.scale_log2, -m_used));
-                        if (need_mask) {
-                            const int key = key0 + c + i;
-                            if (!(key < P.S && (!CAUSAL || key <= row))) e = 0.f;
-                        }
-                        p[i] = e;
-                        l += e;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) pk[half * 16 + i] = pack_bf16x2(p[2 * i], p[2 * i + 1]);
-                }
-                tmem_st_32x32b_x32(s_tmem + (c2 >> 1), pk);
-            }
+            l += l_tile;
             tmem_st_wait();
             tcgen05_fence_before();
             __syncwarp();
