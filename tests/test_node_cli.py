@@ -155,7 +155,7 @@ def test_start(ping, containers, context, pull, volumes):
     kwargs = containers.run.call_args.kwargs
     assert kwargs["command"].startswith("vnode-local start -c /mnt/config/some-name.yaml -n some-name -e application")
     assert kwargs["labels"][f"{APPNAME}-type"] == "node"
-    assert kwargs["environment"]["CUDA_VISIBLE_DEVICES"] == "3"
+    assert kwargs["environment"]["V6_GPU"] == "3"
     assert kwargs["environment"]["DATA_VOLUME_NAME"] == "data-vol-name"
     assert "DEFAULT_DATABASE_URI" in kwargs["environment"]
 

@@ -69,7 +69,7 @@ def RPC_train(data, model: str = "resnet_tiny", rounds: int = 2, local_steps: Op
     rv = rendezvous or {"addr": "127.0.0.1", "port": _free_port(), "world": 1, "ranks": {str(org_id): 0}}
     rank, world = int(rv["ranks"][str(org_id)]), int(rv["world"])
     use_cuda = torch.cuda.is_available()
-    device = torch.device("cuda", 0) if use_cuda else torch.device("cpu")   # the node pinned its GPU via CUDA_VISIBLE_DEVICES
+    device = torch.device("cuda", int(os.environ.get("V6_GPU", "0"))) if use_cuda else torch.device("cpu")
     if use_cuda:
         torch.cuda.set_device(device)
     created_pg = False

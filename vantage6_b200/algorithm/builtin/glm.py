@@ -85,7 +85,7 @@ def RPC_fit(data, iterations: int = 20, lr: float = 1.0, rendezvous: Optional[di
     rv = rendezvous or {"addr": "127.0.0.1", "port": _free_port(), "world": 1, "ranks": {str(org_id): 0}}
     rank, world = int(rv["ranks"][str(org_id)]), int(rv["world"])
     use_cuda = torch.cuda.is_available()
-    device = torch.device("cuda", 0) if use_cuda else torch.device("cpu")
+    device = torch.device("cuda", int(os.environ.get("V6_GPU", "0"))) if use_cuda else torch.device("cpu")
     created = False
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl" if use_cuda else "gloo", init_method=f"tcp://{rv['addr']}:{rv['port']}",

@@ -11,7 +11,7 @@ the local proxy host ``proxyserver`` at vantage6/cli/globals.py:27):
 
     INPUT_FILE  OUTPUT_FILE  TOKEN_FILE  TEMPORARY_FOLDER  DATABASE_URI
     HOST  PORT  API_PATH            (address of the node's proxy server)
-    V6_GPU / CUDA_VISIBLE_DEVICES   (B200 extension: the GPU this node is pinned to)
+    V6_GPU                          (B200 extension: index of the GPU this node is pinned to)
 
 Data loading understands ``.csv`` / ``.parquet`` (pandas), ``.pt`` (torch), ``.npy`` / ``.npz``
 (numpy) and ``synthetic://...`` URIs (algorithms generate data on their own GPU).

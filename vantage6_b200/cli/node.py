@@ -3,7 +3,7 @@
 Behavioural spec: reference vantage6/cli/node.py (commands ``list new files start stop attach
 create-private-key clean remove version`` with the same options, defaults, console messages and
 exit codes).  What differs is *what gets launched*: a federated node is
-one process pinned to one B200 (``--gpu K`` -> ``CUDA_VISIBLE_DEVICES=K``) managed by the
+one process pinned to one B200 (``--gpu K`` -> ``V6_GPU=K``) managed by the
 process runtime (vantage6_b200/runtime) instead of a Docker container.
 """
 from __future__ import annotations
@@ -267,7 +267,7 @@ def cli_node_start(name, config, environment, system_folders, image, keep, mount
     if gpu is None and ctx.config.get("gpu") is not None:
         gpu = int(ctx.config.get("gpu"))
     if gpu is not None:
-        env["CUDA_VISIBLE_DEVICES"] = str(gpu)
+        env["V6_GPU"] = str(gpu)              # all GPUs stay visible: peers are mapped over NVLink (symmetric heap)
         info(f"Pinning node to GPU {gpu}")
 
     system_folders_option = "--system" if system_folders else "--user"

@@ -77,10 +77,10 @@ class Node:
 
     # ------------------------------------------------------------------ setup
     def _gpu_index(self) -> Optional[int]:
-        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-        if vis not in (None, ""):
+        pinned = os.environ.get("V6_GPU")
+        if pinned not in (None, ""):
             try:
-                return int(vis.split(",")[0])
+                return int(pinned)
             except ValueError:
                 return None
         g = self.config.get("gpu") if hasattr(self.config, "get") else None

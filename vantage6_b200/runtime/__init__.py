@@ -16,7 +16,8 @@ TO ONE GPU, so this module exposes the same object model over plain processes:
   are resolved to host paths inside the command line and exported as ``V6_MOUNTS``;
 * ``attach`` tails the process's log file; ``exec_run`` runs a command in the same environment.
 
-GPU pinning: ``environment={"CUDA_VISIBLE_DEVICES": "k"}`` (set by ``vnode start --gpu k``).
+GPU pinning: ``environment={"V6_GPU": "k"}`` (set by ``vnode start --gpu k``); every GPU stays visible so that
+peer memory can be mapped (parallel/symm.py).
 """
 from __future__ import annotations
 
