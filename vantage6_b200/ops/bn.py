@@ -22,14 +22,16 @@ _scratch: dict = {}
 
 
 def _get_scratch(device, C: int):
-    key = (str(device), C)
-    s = _scratch.get(key)
-    if s is None:
-        parts = 148 * 4
-        s = (torch.empty(parts * 2 * C, device=device, dtype=torch.float32),      # per-CTA partials
-             torch.empty(3 * C, device=device, dtype=torch.float32))              # bwd coefficients
-        _scratch[key] = s
-    return s
+    """(reduction scratch shared by every BN launch of the device -- partials + self-resetting arrival
+    counters, zeroed once --, per-C backward coefficient buffer).  Launches are stream-ordered."""
+    key = str(device)
+    red = _scratch.get(key)
+    if red is None:
+        red = _scratch[key] = torch.zeros(int(native().BN_SCRATCH_FLOATS), device=device, dtype=torch.float32)
+    coef = _scratch.get((key, C))
+    if coef is None:
+        coef = _scratch[(key, C)] = torch.empty(3 * C, device=device, dtype=torch.float32)
+    return red, coef
 
 
 def _fast_path(x: torch.Tensor) -> bool:
@@ -42,7 +44,7 @@ def _fast_path(x: torch.Tensor) -> bool:
 
 class _BNFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, eps, momentum, relu):
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, num_batches_tracked, eps, momentum, relu):
         N, C, H, W = x.shape
         R = N * H * W
         y = torch.empty_like(x)                              # preserves channels_last strides
@@ -50,10 +52,12 @@ class _BNFn(torch.autograd.Function):
         rstd = torch.empty(C, device=x.device, dtype=torch.float32)
         scale_bias = torch.empty(2 * C, device=x.device, dtype=torch.float32)
         part, _ = _get_scratch(x.device, C)
-        count(3)                                             # stats + finalize + apply
+        count(2)                                             # stats(+finalize) + apply
         native().bn_fwd(x.data_ptr(), 0 if residual is None else residual.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                         0 if running_mean is None else running_mean.data_ptr(),
-                        0 if running_var is None else running_var.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                        0 if running_var is None else running_var.data_ptr(),
+                        0 if num_batches_tracked is None else num_batches_tracked.data_ptr(), y.data_ptr(), mean.data_ptr(),
+                        rstd.data_ptr(),
                         scale_bias.data_ptr(), part.data_ptr(), R, C, eps, momentum, relu, stream_ptr())
         ctx.save_for_backward(x, y if relu else None, gamma, mean, rstd)
         ctx.relu, ctx.has_res, ctx.R, ctx.C = relu, residual is not None, R, C
@@ -69,11 +73,11 @@ class _BNFn(torch.autograd.Function):
         dgamma = torch.empty_like(gamma)
         dbeta = torch.empty_like(gamma)
         part, coef = _get_scratch(x.device, ctx.C)
-        count(3)                                             # reduce + finalize + apply
+        count(2)                                             # reduce(+finalize) + apply
         native().bn_bwd(dy.data_ptr(), 0 if y is None else y.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
                         rstd.data_ptr(), dx.data_ptr(), 0 if dres is None else dres.data_ptr(), dgamma.data_ptr(),
                         dbeta.data_ptr(), coef.data_ptr(), part.data_ptr(), ctx.R, ctx.C, ctx.relu, False, stream_ptr())
-        return dx, dres, dgamma, dbeta, None, None, None, None, None
+        return dx, dres, dgamma, dbeta, None, None, None, None, None, None
 
 
 class FusedBatchNormAct(nn.BatchNorm2d):
@@ -88,10 +92,8 @@ class FusedBatchNormAct(nn.BatchNorm2d):
         if _fast_path(x) and (residual is None or (_fast_path(residual) and residual.shape == x.shape)):
             mom = 0.1 if self.momentum is None else self.momentum
             if self.training:
-                if self.num_batches_tracked is not None:
-                    self.num_batches_tracked.add_(1)
-                return _BNFn.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var, self.eps, mom,
-                                   relu)
+                return _BNFn.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var,
+                                   self.num_batches_tracked, self.eps, mom, relu)      # the kernel also bumps the counter
             # eval: per-channel affine from the running statistics, one fused pass
             scale = self.weight.float() * torch.rsqrt(self.running_var + self.eps)
             bias = self.bias.float() - self.running_mean * scale

@@ -108,9 +108,10 @@ int v6_bcast_gemm_bf16(const void* A, void* B_local, const void* B_server_peer, 
 int v6_flash_attn_bwd(const void* q, const void* k, const void* v, const void* dout, const void* kt, const void* qt,
                       const void* dot, const float* lse2, const float* delta, void* dq, void* dk, void* dv, int B, int S,
                       int Hq, int Hkv, int D, float softmax_scale, int causal, cudaStream_t stream);
+long long v6_bn_scratch_floats();
 int v6_bn_fwd(const void* x, const void* res, const float* gamma, const float* beta, float* running_mean, float* running_var,
-              void* y, float* mean, float* rstd, float* scale_bias, float* scratch, long long R, int C, float eps,
-              float momentum, int relu, cudaStream_t s);
+              long long* num_batches_tracked, void* y, float* mean, float* rstd, float* scale_bias, float* scratch, long long R,
+              int C, float eps, float momentum, int relu, cudaStream_t s);
 int v6_bn_apply(const void* x, const void* res, const float* scale, const float* bias, void* y, long long R, int C, int relu,
                 cudaStream_t s);
 int v6_bn_bwd(const void* dy, const void* y, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,

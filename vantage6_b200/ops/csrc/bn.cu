@@ -6,21 +6,20 @@
 // ~15%.  These kernels make that part memory-bound at HBM speed and remove the separate ReLU /
 // residual-add passes:
 //
-//   forward :  stats (1 read of x)  ->  finalize (per channel)  ->  y = relu(x*scale + bias + res)
-//   backward:  reduce (dy, y, x)    ->  finalize (dgamma, dbeta) ->  dx (and dres) in one pass
+//   forward :  stats + per-channel finalize (1 read of x, one launch)  ->  y = relu(x*scale + bias + res)
+//   backward:  reduce + finalize (dy, y, x -> dgamma, dbeta, coefficients)  ->  dx (and dres) in one pass
 //
 // x viewed as [R = N*H*W, C], C % 8 == 0 and C/8 a power of two <= 256 (64..2048 in ResNet-50).
-// Thread mapping: threadIdx % (C/8) owns 8 consecutive channels (one 16 B vector), threadIdx / (C/8)
-// is a row lane; CTAs stride over rows.  Per-channel sums are accumulated in registers across rows
-// (shifted by x[0,c] to avoid cancellation in E[x^2]-E[x]^2), folded across row lanes in shared
-// memory, written as per-CTA partials and summed by the finalize kernel (no atomics, deterministic).
+// Element-wise passes: threadIdx % (C/8) owns 8 consecutive channels (one 16 B vector), threadIdx / (C/8)
+// is a row lane; CTAs stride over rows.  Reductions: see "in-kernel tree reduction" below; per-channel
+// sums are accumulated in registers across rows (shifted by x[0,c] to avoid cancellation in
+// E[x^2]-E[x]^2) -- no floating-point atomics, deterministic.
 #include "common.cuh"
 #include "api.h"
 
 namespace bn {
 
 constexpr int THREADS = 256;
-constexpr int MAX_PARTS = 148 * 2;
 
 V6_DEVINL void load8(const __nv_bfloat16* p, float (&v)[8]) {
     uint4 t = *reinterpret_cast<const uint4*>(p);
@@ -31,105 +30,166 @@ V6_DEVINL void store8(__nv_bfloat16* p, const float (&v)[8]) {
     *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
                                               pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
 }
+V6_DEVINL uint4 ldg_nc_v4(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+V6_DEVINL void unpack8(const uint4& t, float (&v)[8]) {
+    float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+V6_DEVINL void acc_stats(const uint4& raw, const float (&shift)[8], float (&s1)[8], float (&s2)[8]) {
+    float v[8];
+    unpack8(raw, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float d = v[k] - shift[k]; s1[k] += d; s2[k] = fmaf(d, d, s2[k]); }
+}
 V6_DEVINL void loadf8(const float* p, float (&v)[8]) {
     float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-// fold the per-thread accumulators a[8], b[8] over the row lanes of the CTA and write one partial
-// row [2C] = [sum_a (C) | sum_b (C)] for this CTA.
-V6_DEVINL void fold_and_write(float (&a)[8], float (&b)[8], float* smem, float* part, int C, int cg, int rl, int RL) {
-    const int CG = C >> 3;
-    float* sa = smem;                       // [RL][C]
-    float* sb = smem + (size_t)RL * C;      // [RL][C]
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { sa[(size_t)rl * C + cg * 8 + k] = a[k]; sb[(size_t)rl * C + cg * 8 + k] = b[k]; }
+// ------------------------------------------------------------------ in-kernel tree reduction
+// v3: the separate finalize kernels are gone.  A reduce CTA covers a 64-channel slice (blockIdx.y) and
+// a strided set of rows (blockIdx.x); its [2*SW] partial goes to global memory, then a two-level
+// "last CTA to arrive folds" tree (groups of G1 row-CTAs, then the groups of the slice) produces the
+// per-channel totals inside the same launch and the last CTA of each slice does the per-channel math.
+// Every fold sums its inputs in a fixed order, so the result does not depend on which CTA happens to
+// arrive last (deterministic, no floating-point atomics); the counters reset themselves.
+// (v2 profile, profiles/launches_resnet50_fusedbn_r1.txt: finalize 12.5 us per launch, latency-bound,
+// 15% of the forward; stats at 2 TB/s because only 2 CTAs/SM were resident.)
+constexpr int G1 = 16;
+constexpr int MAX_CTAS = 148 * 8;                    // upper bound on reduce CTAs per launch
+constexpr int L2_SLOTS = 256;                        // >= MAX_CTAS / G1 + slices
+constexpr size_t SCR_L2 = (size_t)MAX_CTAS * 128;    // float offsets into the scratch buffer
+constexpr size_t SCR_CNT1 = SCR_L2 + (size_t)L2_SLOTS * 128;
+constexpr size_t SCR_CNT2 = SCR_CNT1 + L2_SLOTS;
+constexpr size_t SCR_FLOATS = SCR_CNT2 + 64;
+
+struct Red {
+    float* l1;      // [slice][row-CTA][2*SW]
+    float* l2;      // [slice][group][2*SW]
+    int* cnt1;      // [slice][group]   (zero between launches)
+    int* cnt2;      // [slice]
+};
+static inline Red make_red(float* scratch) {
+    return Red{scratch, scratch + SCR_L2, reinterpret_cast<int*>(scratch + SCR_CNT1), reinterpret_cast<int*>(scratch + SCR_CNT2)};
+}
+
+// true in exactly one CTA: the last of `expected` to arrive at `counter` (which it resets to 0)
+V6_DEVINL bool arrive_last(int* counter, int expected, int* s_flag) {
+    __threadfence();
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += THREADS) {
-        float x = 0.f, y = 0.f;
-        for (int r = 0; r < RL; ++r) { x += sa[(size_t)r * C + c]; y += sb[(size_t)r * C + c]; }
-        part[(size_t)blockIdx.x * 2 * C + c] = x;
-        part[(size_t)blockIdx.x * 2 * C + C + c] = y;
+    if (threadIdx.x == 0) {
+        const int last = atomicAdd(counter, 1) == expected - 1;
+        if (last) atomicExch(counter, 0);
+        *s_flag = last;
     }
-    (void)CG;
+    __syncthreads();
+    const bool last = *s_flag != 0;
+    if (last) __threadfence();
+    return last;
+}
+
+// dst[col] = sum_p src[p][col], p < n; cols in {16..128}; THREADS/cols lanes each take every lanes-th row
+V6_DEVINL void fold_rows(const float* __restrict__ src, int n, int cols, float* red, float* dst) {
+    const int lanes = THREADS / cols;
+    const int col = threadIdx.x % cols, ln = threadIdx.x / cols;
+    float s = 0.f;
+#pragma unroll 4
+    for (int p = ln; p < n; p += lanes) s += __ldcg(src + (size_t)p * cols + col);
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < cols) {
+        float t = 0.f;
+        for (int l = 0; l < lanes; ++l) t += red[l * cols + threadIdx.x];
+        dst[threadIdx.x] = t;
+    }
+}
+
+// Reduce the per-thread accumulators a[8], b[8] (thread = 8 channels of one row lane) over the whole
+// slice.  Returns true in the one CTA per slice that ends up with the totals in tot[0..SW) (sum a) and
+// tot[SW..2SW) (sum b).
+V6_DEVINL bool slice_reduce(float (&a)[8], float (&b)[8], const Red& rd, int SW, float* tot) {
+    __shared__ float red[8 * 128];
+    __shared__ int s_flag;
+    const int CGS = SW >> 3, cols = 2 * SW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int off = CGS; off < 32; off <<= 1) {           // lanes with the same channel group hold different rows
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            a[k] += __shfl_xor_sync(0xffffffffu, a[k], off);
+            b[k] += __shfl_xor_sync(0xffffffffu, b[k], off);
+        }
+    }
+    if (lane < CGS) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { red[warp * 128 + lane * 8 + k] = a[k]; red[warp * 128 + SW + lane * 8 + k] = b[k]; }
+    }
+    __syncthreads();
+    const int slice = blockIdx.y, rc = blockIdx.x, nrc = gridDim.x;
+    const int ngrp = (nrc + G1 - 1) / G1;
+    if (threadIdx.x < cols) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) s += red[w * 128 + threadIdx.x];
+        __stcg(rd.l1 + ((size_t)slice * nrc + rc) * cols + threadIdx.x, s);
+    }
+    const int grp = rc / G1;
+    const int gsz = min(G1, nrc - grp * G1);
+    if (!arrive_last(rd.cnt1 + slice * ngrp + grp, gsz, &s_flag)) return false;
+    fold_rows(rd.l1 + ((size_t)slice * nrc + (size_t)grp * G1) * cols, gsz, cols, red, rd.l2 + ((size_t)slice * ngrp + grp) * cols);
+    if (!arrive_last(rd.cnt2 + slice, ngrp, &s_flag)) return false;
+    fold_rows(rd.l2 + (size_t)slice * ngrp * cols, ngrp, cols, red, tot);
+    __syncthreads();
+    return true;
 }
 
 // ---------------------------------------------------------------------------------- forward
-__global__ void __launch_bounds__(THREADS) bn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part,
-                                                           long long R, int C) {
-    extern __shared__ float smem[];
-    const int CG = C >> 3, RL = THREADS / CG;
-    const int cg = threadIdx.x % CG, rl = threadIdx.x / CG;
-    float shift[8], s1[8], s2[8];
-    load8(x + cg * 8, shift);                                   // row 0 as the per-channel shift
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
-    const long long G = (long long)gridDim.x * RL;
-    for (long long r = (long long)blockIdx.x * RL + rl; r < R; r += 4 * G) {      // 4 independent 16 B loads in flight
-        float v[4][8];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (r + u * G < R) load8(x + (r + u * G) * C + cg * 8, v[u]);
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (r + u * G < R) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) { const float d = v[u][k] - shift[k]; s1[k] += d; s2[k] = fmaf(d, d, s2[k]); }
-            }
-    }
-    fold_and_write(s1, s2, smem, part, C, cg, rl, RL);
-}
-
-// Finalize kernels: block = 32 channels x 8 partial-slices (256 threads).  Each thread sums every 8th
-// partial with 4 independent loads in flight, the 8 slices are folded through shared memory, and the
-// slice-0 thread of each channel does the per-channel math.  (v1 used one thread per channel looping
-// over ~600 partials: latency-bound, 79 us per launch, 54% of the step in profiles/launches_*fusedbn*.)
-constexpr int FIN_THREADS = 256;
-V6_DEVINL int fold_parts(const float* __restrict__ part, int nparts, int C, float& a_out, float& b_out) {
-    __shared__ float sa[8][33], sb[8][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + tx;
-    float a = 0.f, b = 0.f;
-    if (c < C) {
-#pragma unroll 4
-        for (int p = ty; p < nparts; p += 8) {
-            a += part[(size_t)p * 2 * C + c];
-            b += part[(size_t)p * 2 * C + C + c];
-        }
-    }
-    sa[ty][tx] = a; sb[ty][tx] = b;
-    __syncthreads();
-    if (ty != 0 || c >= C) return -1;
-#pragma unroll
-    for (int s = 1; s < 8; ++s) { a += sa[s][tx]; b += sb[s][tx]; }
-    a_out = a; b_out = b;
-    return c;
-}
-
-__global__ void __launch_bounds__(FIN_THREADS) bn_fwd_finalize_kernel(const float* __restrict__ part, int nparts, const __nv_bfloat16* __restrict__ x,
+// stats + finalize: per-channel mean / rstd / (scale, bias) of y = x*scale + bias, running-stat update.
+constexpr int STATS_UNROLL = 4;
+__global__ void __launch_bounds__(THREADS, 4) bn_stats_kernel(const __nv_bfloat16* __restrict__ x, Red rd,
                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                        float* __restrict__ running_mean, float* __restrict__ running_var,
+                                       long long* __restrict__ num_batches_tracked,
                                        float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                        float* __restrict__ scale_out, float* __restrict__ bias_out,
                                        long long R, int C, float eps, float momentum) {
-    float a, b;
-    const int c = fold_parts(part, nparts, C, a, b);
-    if (c < 0) return;
-    const float shift = __bfloat162float(x[c]);
-    const float invR = 1.f / (float)R;
-    const float dm = a * invR;
-    const float mean = shift + dm;
-    const float var = fmaxf(b * invR - dm * dm, 0.f);
-    const float rstd = rsqrtf(var + eps);
-    mean_out[c] = mean;
-    rstd_out[c] = rstd;
-    const float sc = gamma[c] * rstd;
-    scale_out[c] = sc;
-    bias_out[c] = beta[c] - mean * sc;
-    if (running_mean) {
-        const float unbiased = R > 1 ? var * (float)R / (float)(R - 1) : var;
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
-        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    __shared__ float tot[128];
+    const int SW = C < 64 ? C : 64, CGS = SW >> 3, RL = THREADS / CGS;
+    const int cg = threadIdx.x % CGS, rl = threadIdx.x / CGS;
+    const __nv_bfloat16* xc = x + blockIdx.y * SW + cg * 8;
+    float shift[8], s1[8], s2[8];
+    load8(xc, shift);                                           // row 0 as the per-channel shift
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
+    const long long G = (long long)gridDim.x * RL;
+    long long r = (long long)blockIdx.x * RL + rl;
+    for (; r + (STATS_UNROLL - 1) * G < R; r += STATS_UNROLL * G) {            // UNROLL independent 16 B loads in flight
+        uint4 raw[STATS_UNROLL];
+#pragma unroll
+        for (int u = 0; u < STATS_UNROLL; ++u) raw[u] = ldg_nc_v4(xc + (r + u * G) * C);
+#pragma unroll
+        for (int u = 0; u < STATS_UNROLL; ++u) acc_stats(raw[u], shift, s1, s2);
+    }
+    for (; r < R; r += G) acc_stats(ldg_nc_v4(xc + r * C), shift, s1, s2);
+    if (!slice_reduce(s1, s2, rd, SW, tot)) return;
+    if (threadIdx.x < SW) {
+        const int c = blockIdx.y * SW + threadIdx.x;
+        const float sh = __bfloat162float(x[c]);
+        const float invR = 1.f / (float)R;
+        const float dm = tot[threadIdx.x] * invR;
+        const float mean = sh + dm;
+        const float var = fmaxf(tot[SW + threadIdx.x] * invR - dm * dm, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        mean_out[c] = mean;
+        rstd_out[c] = rstd;
+        const float sc = gamma[c] * rstd;
+        scale_out[c] = sc;
+        bias_out[c] = beta[c] - mean * sc;
+        if (running_mean) {
+            const float unbiased = R > 1 ? var * (float)R / (float)(R - 1) : var;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+        }
+        if (num_batches_tracked && c == 0) *num_batches_tracked += 1;
     }
 }
 
@@ -171,63 +231,71 @@ __global__ void __launch_bounds__(THREADS) bn_apply_kernel(const __nv_bfloat16* 
 
 // ---------------------------------------------------------------------------------- backward
 template <bool RELU>
-__global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
-                                                                const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
-                                                                const float* __restrict__ rstd, float* __restrict__ part,
-                                                                long long R, int C) {
-    extern __shared__ float smem[];
-    const int CG = C >> 3, RL = THREADS / CG;
-    const int cg = threadIdx.x % CG, rl = threadIdx.x / CG;
+V6_DEVINL void acc_bwd(const uint4& graw, const uint4& xraw, const uint4& yraw, const float (&mu)[8], const float (&rs)[8],
+                       float (&sg)[8], float (&sgx)[8]) {
+    float g[8], xv[8], yv[8];
+    unpack8(graw, g);
+    unpack8(xraw, xv);
+    if (RELU) unpack8(yraw, yv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float gg = (RELU && !(yv[k] > 0.f)) ? 0.f : g[k];
+        sg[k] += gg;
+        sgx[k] = fmaf(gg, (xv[k] - mu[k]) * rs[k], sgx[k]);
+    }
+}
+
+// reduce + finalize: per channel dgamma, dbeta (optionally accumulated into the flat fp32 grad buffer) and
+// the coefficients of dx = c0 * g + c1 * x + c2 with
+//   c0 = gamma*rstd, c1 = -gamma*rstd^2*mean(g*xhat), c2 = -c0*mean(g) - c1*mean
+template <bool RELU>
+__global__ void __launch_bounds__(THREADS, 3) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                                       const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                       const float* __restrict__ mean, const float* __restrict__ rstd, Red rd,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef,
+                                       long long R, int C, int accumulate) {
+    __shared__ float tot[128];
+    const int SW = C < 64 ? C : 64, CGS = SW >> 3, RL = THREADS / CGS;
+    const int cg = threadIdx.x % CGS, rl = threadIdx.x / CGS;
+    const size_t c0 = (size_t)blockIdx.y * SW + cg * 8;
     float mu[8], rs[8], sg[8], sgx[8];
-    loadf8(mean + cg * 8, mu);
-    loadf8(rstd + cg * 8, rs);
+    loadf8(mean + c0, mu);
+    loadf8(rstd + c0, rs);
 #pragma unroll
     for (int k = 0; k < 8; ++k) { sg[k] = 0.f; sgx[k] = 0.f; }
     const long long G = (long long)gridDim.x * RL;
-    for (long long r0 = (long long)blockIdx.x * RL + rl; r0 < R; r0 += 2 * G) {   // 2 rows x 3 tensors in flight
-        float g[2][8], xv[2][8], yv[2][8];
+    long long r = (long long)blockIdx.x * RL + rl;
+    for (; r + G < R; r += 2 * G) {                                            // 2 rows x 3 tensors in flight
+        uint4 g[2], xv[2], yv[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            const long long r = r0 + u * G;
-            if (r < R) {
-                load8(dy + r * C + cg * 8, g[u]);
-                load8(x + r * C + cg * 8, xv[u]);
-                if (RELU) load8(y + r * C + cg * 8, yv[u]);
-            }
+            const long long o = (r + u * G) * C + c0;
+            g[u] = ldg_nc_v4(dy + o);
+            xv[u] = ldg_nc_v4(x + o);
+            if (RELU) yv[u] = ldg_nc_v4(y + o);
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (r0 + u * G < R) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float gg = (RELU && !(yv[u][k] > 0.f)) ? 0.f : g[u][k];
-                    sg[k] += gg;
-                    sgx[k] = fmaf(gg, (xv[u][k] - mu[k]) * rs[k], sgx[k]);
-                }
-            }
-        }
+        for (int u = 0; u < 2; ++u) acc_bwd<RELU>(g[u], xv[u], yv[u], mu, rs, sg, sgx);
     }
-    fold_and_write(sg, sgx, smem, part, C, cg, rl, RL);
-}
-
-// per channel: dgamma, dbeta (accumulated into the flat fp32 grad buffer) and the coefficients of
-// dx = c0 * g + c1 * x + c2  with  c0 = gamma*rstd, c1 = -gamma*rstd^2*mean(g*xhat), c2 = -c0*mean(g) - c1*mean
-__global__ void __launch_bounds__(FIN_THREADS) bn_bwd_finalize_kernel(
-                                       const float* __restrict__ part, int nparts, const float* __restrict__ gamma,
-                                       const float* __restrict__ mean, const float* __restrict__ rstd,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef,
-                                       long long R, int C, int accumulate) {
-    float sg, sgx;
-    const int c = fold_parts(part, nparts, C, sg, sgx);
-    if (c < 0) return;
-    dgamma[c] = accumulate ? dgamma[c] + sgx : sgx;
-    dbeta[c] = accumulate ? dbeta[c] + sg : sg;
-    const float invR = 1.f / (float)R;
-    const float c0 = gamma[c] * rstd[c];
-    const float c1 = -c0 * rstd[c] * sgx * invR;
-    coef[c] = c0;
-    coef[C + c] = c1;
-    coef[2 * C + c] = -c0 * sg * invR - c1 * mean[c];
+    for (; r < R; r += G) {
+        const long long o = r * C + c0;
+        uint4 yv = make_uint4(0, 0, 0, 0);
+        if (RELU) yv = ldg_nc_v4(y + o);
+        acc_bwd<RELU>(ldg_nc_v4(dy + o), ldg_nc_v4(x + o), yv, mu, rs, sg, sgx);
+    }
+    if (!slice_reduce(sg, sgx, rd, SW, tot)) return;
+    if (threadIdx.x < SW) {
+        const int c = blockIdx.y * SW + threadIdx.x;
+        const float tg = tot[threadIdx.x], tgx = tot[SW + threadIdx.x];
+        dgamma[c] = accumulate ? dgamma[c] + tgx : tgx;
+        dbeta[c] = accumulate ? dbeta[c] + tg : tg;
+        const float invR = 1.f / (float)R;
+        const float k0 = gamma[c] * rstd[c];
+        const float k1 = -k0 * rstd[c] * tgx * invR;
+        coef[c] = k0;
+        coef[C + c] = k1;
+        coef[2 * C + c] = -k0 * tg * invR - k1 * mean[c];
+    }
 }
 
 template <bool RELU, bool RES>
@@ -272,12 +340,28 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const __nv_bfloat
 
 static inline bool shape_ok(int C) {
     const int cg = C >> 3;
-    return C % 8 == 0 && cg >= 1 && cg <= THREADS && (cg & (cg - 1)) == 0;
+    return C % 8 == 0 && cg >= 1 && cg <= THREADS && (cg & (cg - 1)) == 0;     // 8, 16, ..., 2048
 }
-static inline int grid_for(long long R, int C) {
-    const int RL = THREADS / (C >> 3);
-    long long g = (R + RL - 1) / RL;
-    return (int)(g < 1 ? 1 : (g > MAX_PARTS ? MAX_PARTS : g));
+// one full wave of resident CTAs for a reduce kernel (occupancy queried once per kernel)
+template <typename K>
+static int wave_ctas(K kernel, int& cache) {
+    if (cache == 0) {
+        int dev = 0, sms = 148, occ = 1;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, THREADS, 0) != cudaSuccess || occ < 1) occ = 1;
+        cache = occ * sms > MAX_CTAS ? MAX_CTAS : occ * sms;
+    }
+    return cache;
+}
+
+// reduce grids: x = row-CTAs, y = 64-channel slices
+static inline dim3 reduce_grid(long long R, int C, int target) {
+    const int SW = C < 64 ? C : 64, slices = C / SW, RL = THREADS / (SW >> 3);
+    long long nrc = (R + RL - 1) / RL;
+    const long long cap = target / slices > 0 ? target / slices : 1;
+    if (nrc > cap) nrc = cap;
+    return dim3((unsigned)(nrc < 1 ? 1 : nrc), (unsigned)slices, 1);
 }
 
 // element-wise passes keep no partials: use every resident CTA slot (8 CTAs/SM x 148 SMs)
@@ -289,19 +373,20 @@ static inline int apply_grid(long long R, int C) {
 
 }  // namespace bn
 
-// scratch: >= MAX_PARTS*2*C floats (partials) ; stats: mean[C] rstd[C] scale[C] bias[C]
+// scratch: v6_bn_scratch_floats() floats, zero-initialised once (partials + self-resetting counters), shared by
+// every launch on one stream.  stats: mean[C] rstd[C] scale_bias[2C].
+extern "C" long long v6_bn_scratch_floats() { return (long long)bn::SCR_FLOATS; }
+
 extern "C" int v6_bn_fwd(const void* x, const void* res, const float* gamma, const float* beta, float* running_mean,
-                         float* running_var, void* y, float* mean, float* rstd, float* scale_bias, float* scratch,
-                         long long R, int C, float eps, float momentum, int relu, cudaStream_t s) {
+                         float* running_var, long long* num_batches_tracked, void* y, float* mean, float* rstd,
+                         float* scale_bias, float* scratch, long long R, int C, float eps, float momentum, int relu,
+                         cudaStream_t s) {
     using namespace bn;
     if (!shape_ok(C)) return (int)cudaErrorInvalidValue;
-    const int grid = grid_for(R, C);
-    const int RL = THREADS / (C >> 3);
-    const size_t smem = (size_t)RL * C * 2 * sizeof(float);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(bn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    bn_stats_kernel<<<grid, THREADS, smem, s>>>((const __nv_bfloat16*)x, scratch, R, C);
-    bn_fwd_finalize_kernel<<<(C + 31) / 32, FIN_THREADS, 0, s>>>(scratch, grid, (const __nv_bfloat16*)x, gamma, beta, running_mean,
-                                                           running_var, mean, rstd, scale_bias, scale_bias + C, R, C, eps, momentum);
+    static int wave = 0;
+    bn_stats_kernel<<<reduce_grid(R, C, wave_ctas(bn_stats_kernel, wave)), THREADS, 0, s>>>((const __nv_bfloat16*)x, make_red(scratch), gamma, beta,
+                                                                  running_mean, running_var, num_batches_tracked, mean, rstd,
+                                                                  scale_bias, scale_bias + C, R, C, eps, momentum);
     const int ag = apply_grid(R, C);
     const __nv_bfloat16* xx = (const __nv_bfloat16*)x;
     const __nv_bfloat16* rr = (const __nv_bfloat16*)res;
@@ -343,20 +428,13 @@ extern "C" int v6_bn_bwd(const void* dy, const void* y, const void* x, const flo
                          int relu, int accumulate, cudaStream_t s) {
     using namespace bn;
     if (!shape_ok(C)) return (int)cudaErrorInvalidValue;
-    const int grid = grid_for(R, C);
-    const int RL = THREADS / (C >> 3);
-    const size_t smem = (size_t)RL * C * 2 * sizeof(float);
     const __nv_bfloat16* dyy = (const __nv_bfloat16*)dy;
     const __nv_bfloat16* yy = (const __nv_bfloat16*)y;
     const __nv_bfloat16* xx = (const __nv_bfloat16*)x;
-    if (relu) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(bn_bwd_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        bn_bwd_reduce_kernel<true><<<grid, THREADS, smem, s>>>(dyy, yy, xx, mean, rstd, scratch, R, C);
-    } else {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(bn_bwd_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        bn_bwd_reduce_kernel<false><<<grid, THREADS, smem, s>>>(dyy, yy, xx, mean, rstd, scratch, R, C);
-    }
-    bn_bwd_finalize_kernel<<<(C + 31) / 32, FIN_THREADS, 0, s>>>(scratch, grid, gamma, mean, rstd, dgamma, dbeta, coef, R, C, accumulate);
+    static int wave_relu = 0, wave_lin = 0;
+    const dim3 rg = reduce_grid(R, C, relu ? wave_ctas(bn_bwd_reduce_kernel<true>, wave_relu) : wave_ctas(bn_bwd_reduce_kernel<false>, wave_lin));
+    if (relu) bn_bwd_reduce_kernel<true><<<rg, THREADS, 0, s>>>(dyy, yy, xx, gamma, mean, rstd, make_red(scratch), dgamma, dbeta, coef, R, C, accumulate);
+    else bn_bwd_reduce_kernel<false><<<rg, THREADS, 0, s>>>(dyy, yy, xx, gamma, mean, rstd, make_red(scratch), dgamma, dbeta, coef, R, C, accumulate);
     const int ag = apply_grid(R, C);
     __nv_bfloat16* dxx = (__nv_bfloat16*)dx;
     __nv_bfloat16* drr = (__nv_bfloat16*)dres;

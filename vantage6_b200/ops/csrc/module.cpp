@@ -144,10 +144,11 @@ PYBIND11_MODULE(_C, m) {
     });
 
     // ------------------------------------------------------------------ fused BatchNorm (+add)(+ReLU), NHWC bf16
-    m.def("bn_fwd", [](u64 x, u64 res, u64 gamma, u64 beta, u64 rmean, u64 rvar, u64 y, u64 mean, u64 rstd, u64 scale_bias,
-                       u64 scratch, long long R, int C, float eps, float momentum, bool relu, u64 s) {
-        check(v6_bn_fwd(P<void>(x), P<void>(res), P<float>(gamma), P<float>(beta), P<float>(rmean), P<float>(rvar), P<void>(y),
-                        P<float>(mean), P<float>(rstd), P<float>(scale_bias), P<float>(scratch), R, C, eps, momentum, relu, S(s)),
+    m.def("bn_fwd", [](u64 x, u64 res, u64 gamma, u64 beta, u64 rmean, u64 rvar, u64 nbt, u64 y, u64 mean, u64 rstd,
+                       u64 scale_bias, u64 scratch, long long R, int C, float eps, float momentum, bool relu, u64 s) {
+        check(v6_bn_fwd(P<void>(x), P<void>(res), P<float>(gamma), P<float>(beta), P<float>(rmean), P<float>(rvar),
+                        P<long long>(nbt), P<void>(y), P<float>(mean), P<float>(rstd), P<float>(scale_bias), P<float>(scratch), R,
+                        C, eps, momentum, relu, S(s)),
               "bn_fwd");
     });
     m.def("bn_apply", [](u64 x, u64 res, u64 scale, u64 bias, u64 y, long long R, int C, bool relu, u64 s) {
@@ -159,7 +160,7 @@ PYBIND11_MODULE(_C, m) {
                         P<void>(dres), P<float>(dgamma), P<float>(dbeta), P<float>(coef), P<float>(scratch), R, C, relu,
                         accumulate, S(s)), "bn_bwd");
     });
-    m.attr("BN_MAX_PARTS") = 148 * 4;
+    m.attr("BN_SCRATCH_FLOATS") = v6_bn_scratch_floats();
 
     // ------------------------------------------------------------------ K6 / K8
     m.def("rope", [](u64 q, u64 k, u64 cos_t, u64 sin_t, u64 pos, int B, int Sq, int Hq, int Hkv, int D, bool inverse, u64 s) {
