@@ -1,0 +1,123 @@
+"""ResNet-50 local-step pieces on the GPU: max-pool / image-normalise kernels, the multi-tensor gradient sink,
+ShadowConv2d (bf16 shadow filters + gradient sink) against the autocast path, in-kernel BN reduction trees."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from vantage6_b200.ops import native
+
+    native()
+    torch.cuda.set_device(0)
+    return torch.device("cuda", 0)
+
+
+@pytest.mark.parametrize("N,C,H,W", [(4, 64, 112, 112), (2, 8, 9, 7), (3, 16, 32, 32), (1, 64, 5, 5)])
+def test_maxpool_matches_torch(dev, N, C, H, W):
+    from vantage6_b200.ops.pool import MaxPool3x3s2
+
+    torch.manual_seed(0)
+    x = torch.randn(N, C, H, W, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_()
+    y = MaxPool3x3s2()(x)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr = x.detach().float().requires_grad_()
+    yr = torch.nn.functional.max_pool2d(xr, 3, 2, 1)
+    yr.backward(dy.float())
+    assert y.shape == yr.shape and y.is_contiguous(memory_format=torch.channels_last)
+    torch.testing.assert_close(y.float(), yr, rtol=0, atol=0)
+    # ties (equal bf16 values inside a window) may pick a different arg-max than the fp32 reference only when
+    # values are exactly equal; the routed gradient mass is identical either way
+    torch.testing.assert_close(x.grad.float().sum(), xr.grad.sum(), rtol=1e-2, atol=1e-1)
+    mism = (x.grad.float() - xr.grad).abs() > 2e-2
+    assert mism.float().mean().item() < 2e-3
+
+
+def test_image_normalize_matches_torch(dev):
+    from vantage6_b200.models.resnet import _MEAN, _STD
+    from vantage6_b200.ops.pool import image_normalize
+
+    g = torch.Generator().manual_seed(1)
+    img = torch.randint(0, 256, (5, 3, 64, 48), dtype=torch.uint8, generator=g).to(dev)
+    out = image_normalize(img, _MEAN, _STD)
+    m = torch.tensor(_MEAN, device=dev).view(1, 3, 1, 1)
+    s = torch.tensor(_STD, device=dev).view(1, 3, 1, 1)
+    ref = ((img.float() - m) / s).to(torch.bfloat16)
+    assert out.shape == img.shape and out.is_contiguous(memory_format=torch.channels_last)
+    torch.testing.assert_close(out.float(), ref.float(), rtol=1e-2, atol=1e-2)
+
+
+def test_multi_accumulate(dev):
+    from vantage6_b200.ops.optim import multi_accumulate
+
+    torch.manual_seed(2)
+    sizes = [8, 4096, 9408, 64 * 64 * 9, 2048 * 512, 24] + [128] * 120       # > 96 tensors: two launches
+    offs, o = [], 0
+    for n in sizes:
+        offs.append(o)
+        o += (n + 7) // 8 * 8
+    dst = torch.randn(o, device=dev)
+    ref = dst.clone()
+    items = []
+    for n, off in zip(sizes, offs):
+        g = torch.randn(n, device=dev).to(torch.bfloat16)
+        items.append((g, off))
+        ref[off: off + n] += g.float()
+    multi_accumulate(dst, items)
+    torch.testing.assert_close(dst, ref, rtol=0, atol=0)
+
+
+def test_bn_large_shapes_repeatable(dev):
+    """Two-level reduction trees (many row-CTAs per slice); counters must reset: run twice, bitwise equal."""
+    from vantage6_b200.ops.bn import FusedBatchNormAct
+
+    for (N, C, H, W) in [(64, 64, 56, 56), (32, 256, 56, 56), (64, 2048, 7, 7), (64, 512, 28, 28)]:
+        torch.manual_seed(3)
+        x = (torch.randn(N, C, H, W, device=dev) * 1.5 - 0.3).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        bn = FusedBatchNormAct(C).to(dev)
+        outs = []
+        for _ in range(3):
+            xi = x.clone().requires_grad_()
+            y = bn(xi)
+            y.backward(torch.ones_like(y))
+            outs.append((y.detach().clone(), xi.grad.clone(), bn.weight.grad.clone()))
+            bn.weight.grad = None
+            bn.bias.grad = None
+        for a, b in zip(outs[0], outs[2]):
+            assert torch.equal(a, b)
+        xf = x.float()
+        mean = xf.mean((0, 2, 3))
+        var = xf.var((0, 2, 3), unbiased=False)
+        ref = torch.relu((xf - mean.view(1, -1, 1, 1)) * torch.rsqrt(var + bn.eps).view(1, -1, 1, 1))
+        torch.testing.assert_close(outs[0][0].float(), ref, rtol=2e-2, atol=2e-2)
+        assert int(bn.num_batches_tracked) == 3
+
+
+def test_resnet_shadow_conv_trainer_matches_autocast(dev):
+    """Same seeds, fused arm (ShadowConv2d + gradient sink + fused BN/pool + K7 + CUDA graph) vs the stock arm."""
+    from vantage6_b200.models import zoo
+
+    def run(fused):
+        torch.manual_seed(11)
+        tr, spec = zoo.build_trainer("resnet_tiny", rank=0, world=1, device=dev, data_plane="auto" if fused else "collective",
+                                     fused_local_optimizer=fused, use_cuda_graph=fused)
+        batches = spec.make_batches(2, 8, 1234, pin=True)
+        tr.initialize_global()
+        losses = [float(tr.run_round(batches, 16.0).item()) for _ in range(4)]
+        shadow_ok = True
+        if fused:
+            nt = tr.fm.n_trainable
+            shadow_ok = torch.equal(tr.engine.shadow[:nt], tr.engine.w[:nt].to(torch.bfloat16))
+            from vantage6_b200.models.conv import ShadowConv2d
+
+            assert all(m.w_bf16 is not None for m in tr.model.modules() if isinstance(m, ShadowConv2d))
+        tr.close()
+        return losses, shadow_ok
+
+    a, ok = run(True)
+    b, _ = run(False)
+    assert ok
+    assert abs(a[0] - b[0]) < 0.08 and abs(a[-1] - b[-1]) < 0.35, (a, b)

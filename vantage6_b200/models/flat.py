@@ -26,6 +26,7 @@ class Segment:
     numel: int
     shape: Tuple[int, ...]
     trainable: bool
+    channels_last: bool = False      # 4-D tensor stored [O,H,W,I] (cuDNN's NHWC filter layout), exposed as a permuted view
 
 
 class FlatModel:
@@ -41,7 +42,7 @@ class FlatModel:
         params = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
         frozen = [(n, p) for n, p in module.named_parameters() if not p.requires_grad]
         for n, p in params:
-            self.segments.append(Segment(n, off, p.numel(), tuple(p.shape), True))
+            self.segments.append(Segment(n, off, p.numel(), tuple(p.shape), True, _is_channels_last(p)))
             off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.n_trainable = off
         bufs = []
@@ -59,17 +60,18 @@ class FlatModel:
         self.flat = storage
         self.grad = torch.zeros(self.n_trainable, dtype=torch.float32, device=storage.device)
         self.shadow = shadow
+        self.grad_sink: List[Tuple[torch.Tensor, int]] = []     # (bf16 weight gradient, flat offset) queued by ShadowConv2d
         # move values into the flat storage and alias the module tensors to views
         named = dict(params)
         named_b = dict(bufs)
         with torch.no_grad():
             for seg in self.segments:
-                view = self.flat[seg.offset: seg.offset + seg.numel].view(seg.shape)
+                view = self.view_of(self.flat, seg)
                 if seg.trainable:
                     p = named[seg.name]
                     view.copy_(p.detach().to(device=self.flat.device, dtype=torch.float32))
                     p.data = view
-                    p.grad = self.grad[seg.offset: seg.offset + seg.numel].view(seg.shape)
+                    p.grad = self.view_of(self.grad, seg)
                 else:
                     b = named_b[seg.name]
                     view.copy_(b.detach().to(device=self.flat.device, dtype=torch.float32))
@@ -81,21 +83,52 @@ class FlatModel:
         """Trainable prefix of the flat buffer (what the optimizer updates)."""
         return self.flat[: self.n_trainable]
 
+    @staticmethod
+    def view_of(buf: torch.Tensor, seg: Segment) -> torch.Tensor:
+        """The segment of ``buf`` (any flat buffer with this layout) shaped like the parameter.  Channels-last
+        conv filters keep their memory format: no layout-conversion kernel in the step."""
+        flat = buf[seg.offset: seg.offset + seg.numel]
+        if seg.channels_last:
+            o, i, h, w = seg.shape
+            return flat.view(o, h, w, i).permute(0, 3, 1, 2)
+        return flat.view(seg.shape)
+
     def zero_grad(self) -> None:
         self.grad.zero_()
 
+    def flush_grad_sink(self) -> int:
+        """Add the queued bf16 weight gradients into the flat fp32 gradient buffer with ONE multi-tensor
+        kernel (ops/optim.py::multi_accumulate) instead of one cast + one add per layer."""
+        n = len(self.grad_sink)
+        if n:
+            from ..ops import optim as O
+
+            O.multi_accumulate(self.grad, [(g, off) for g, off in self.grad_sink])
+            self.grad_sink.clear()
+        return n
+
     def views(self) -> Dict[str, torch.Tensor]:
-        return {s.name: self.flat[s.offset: s.offset + s.numel].view(s.shape) for s in self.segments}
+        return {s.name: self.view_of(self.flat, s) for s in self.segments}
 
     def shadow_views(self) -> Dict[str, torch.Tensor]:
         assert self.shadow is not None
-        return {s.name: self.shadow[s.offset: s.offset + s.numel].view(s.shape) for s in self.segments}
+        return {s.name: self.view_of(self.shadow, s) for s in self.segments}
+
+    def segment(self, name: str) -> Segment:
+        for s in self.segments:
+            if s.name == name:
+                return s
+        raise KeyError(name)
 
     def check_aliasing(self) -> bool:
         """True if every module parameter still aliases the flat storage (debug / tests)."""
         base = self.flat.data_ptr()
         end = base + self.flat.numel() * 4
         return all(base <= p.data_ptr() < end for _, p in self.module.named_parameters() if p.requires_grad)
+
+
+def _is_channels_last(t: torch.Tensor) -> bool:
+    return (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous())
 
 
 def flat_size(module: nn.Module, include_buffers: bool = True) -> int:

@@ -2,14 +2,17 @@
 ImageNet-shape").  Standard bottleneck architecture (v1.5: stride on the 3x3), 25.6 M
 parameters = 102 MB fp32 -- the payload of the broadcast / reduction rooflines in BASELINE.md.
 
-Convolutions and BatchNorm run on cuDNN (library code); what is hand-written for this model
-is everything the north star names for it: the fused flat SGD step (K7), the FedAvg
-reduce + server optimizer + broadcast kernel (K2) and the CUDA-graph captured local step.
+Convolutions run on cuDNN (library code, models/conv.py); what is hand-written for this model is
+everything around them: fused BatchNorm(+add)(+ReLU) (ops/bn.py), the bf16-shadow / gradient-sink
+plumbing that removes the per-layer cast / layout / accumulate launches, the fused flat SGD step (K7),
+the FedAvg reduce + server optimizer + broadcast kernel (K2) and the CUDA-graph captured local step.
 """
 from __future__ import annotations
 
 import torch
 from torch import nn
+
+from .conv import ShadowConv2d
 
 
 class _StockBNAct(nn.BatchNorm2d):
@@ -35,17 +38,25 @@ def _bn(planes: int, relu: bool, fused: bool) -> nn.Module:
     return _StockBNAct(planes, relu=relu)
 
 
+def _maxpool(fused: bool) -> nn.Module:
+    if fused:
+        from ..ops.pool import MaxPool3x3s2
+
+        return MaxPool3x3s2()
+    return nn.MaxPool2d(3, stride=2, padding=1)
+
+
 class Bottleneck(nn.Module):
     expansion = 4
 
     def __init__(self, inplanes: int, planes: int, stride: int = 1, downsample: nn.Module | None = None,
                  fused_bn: bool = True):
         super().__init__()
-        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.conv1 = ShadowConv2d(inplanes, planes, 1, bias=False)
         self.bn1 = _bn(planes, True, fused_bn)
-        self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
+        self.conv2 = ShadowConv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
         self.bn2 = _bn(planes, True, fused_bn)
-        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.conv3 = ShadowConv2d(planes, planes * 4, 1, bias=False)
         self.bn3 = _bn(planes * 4, True, fused_bn)
         self.downsample = downsample
 
@@ -61,9 +72,9 @@ class ResNet(nn.Module):
         super().__init__()
         self.inplanes = width
         self.fused_bn = fused_bn
-        self.conv1 = nn.Conv2d(3, width, 7, stride=2, padding=3, bias=False)
+        self.conv1 = ShadowConv2d(3, width, 7, stride=2, padding=3, bias=False)
         self.bn1 = _bn(width, True, fused_bn)
-        self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
+        self.maxpool = _maxpool(fused_bn)
         self.layer1 = self._make_layer(width, layers[0])
         self.layer2 = self._make_layer(width * 2, layers[1], stride=2)
         self.layer3 = self._make_layer(width * 4, layers[2], stride=2)
@@ -83,7 +94,7 @@ class ResNet(nn.Module):
     def _make_layer(self, planes: int, blocks: int, stride: int = 1) -> nn.Sequential:
         downsample = None
         if stride != 1 or self.inplanes != planes * 4:
-            downsample = nn.Sequential(nn.Conv2d(self.inplanes, planes * 4, 1, stride=stride, bias=False),
+            downsample = nn.Sequential(ShadowConv2d(self.inplanes, planes * 4, 1, stride=stride, bias=False),
                                        _bn(planes * 4, False, self.fused_bn))
         layers = [Bottleneck(self.inplanes, planes, stride, downsample, self.fused_bn)]
         self.inplanes = planes * 4
@@ -116,7 +127,12 @@ def imagenet_forward_loss(model: nn.Module, x: torch.Tensor, y: torch.Tensor) ->
     The normalisation runs on the GPU inside the captured step so the host only ever ships the
     raw uint8 batch (9.6 MB for 64x3x224x224) over PCIe.
     """
-    if x.dtype == torch.uint8:
+    if x.dtype == torch.uint8 and x.is_cuda and getattr(model, "fused_bn", False) and x.is_contiguous() \
+            and (x.shape[2] * x.shape[3]) % 4 == 0:
+        from ..ops.pool import image_normalize
+
+        x = image_normalize(x, _MEAN, _STD)              # one kernel: cast + normalise + NCHW->NHWC, bf16 out
+    elif x.dtype == torch.uint8:
         key = str(x.device)
         if key not in _NORM_CACHE:      # created on the eager warm-up pass, never during graph capture
             _NORM_CACHE[key] = (torch.tensor(_MEAN, device=x.device, dtype=torch.float32).view(1, 3, 1, 1),

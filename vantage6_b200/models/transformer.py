@@ -166,17 +166,24 @@ class FusedRMSNorm(nn.Module):
 
 
 def attach_shadow(module: nn.Module, flat_model) -> int:
-    """Point every ``ShadowLinear.w_bf16`` at its slice of the flat bf16 shadow buffer."""
+    """Point every ``ShadowLinear.w_bf16`` / ``ShadowConv2d.w_bf16`` at its slice of the flat bf16 shadow
+    buffer (convolutions also get the flat model's gradient sink)."""
     if flat_model.shadow is None:
         return 0
+    from .conv import ShadowConv2d
+
     views = flat_model.shadow_views()
     n = 0
     for name, m in module.named_modules():
+        key = f"{name}.weight" if name else "weight"
+        if key not in views:
+            continue
         if isinstance(m, ShadowLinear):
-            key = f"{name}.weight" if name else "weight"
-            if key in views:
-                m.w_bf16 = views[key]
-                n += 1
+            m.w_bf16 = views[key]
+            n += 1
+        elif isinstance(m, ShadowConv2d) and (flat_model.segment(key).channels_last or tuple(m.kernel_size) == (1, 1)):
+            m.attach(views[key], flat_model.grad_sink, flat_model.segment(key).offset)
+            n += 1
     return n
 
 

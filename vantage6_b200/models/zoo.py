@@ -73,10 +73,10 @@ def _specs() -> Dict[str, ModelSpec]:
     cl = torch.channels_last
     return {
         "resnet50": ModelSpec("resnet50", lambda d: resnet.resnet50().to(memory_format=cl), resnet.imagenet_forward_loss,
-                              _image_batches(224, 1000), "sgd", 0.05, "weights_f32", False, True, 8, 64,
+                              _image_batches(224, 1000), "sgd", 0.05, "weights_f32", True, True, 8, 64,
                               dict(momentum=0.9, weight_decay=1e-4)),
         "resnet_tiny": ModelSpec("resnet_tiny", lambda d: resnet.resnet_tiny(10).to(memory_format=cl),
-                                 resnet.imagenet_forward_loss, _image_batches(32, 10), "sgd", 0.05, "weights_f32", False,
+                                 resnet.imagenet_forward_loss, _image_batches(32, 10), "sgd", 0.05, "weights_f32", True,
                                  True, 2, 8, dict(momentum=0.9)),
         "bert_base": ModelSpec("bert_base", lambda d: bert.bert_base(), bert.bert_forward_loss, _mlm_batches(30522, 128),
                                "adamw", 1e-4, "delta_bf16", True, False, 4, 32, dict(weight_decay=0.01, max_grad_norm=1.0)),

@@ -53,6 +53,15 @@ struct SmallParams {
     long long timeout_cycles;
 };
 
+#define V6_MULTI_MAX 96
+// multi-tensor gradient sink (optim.cu::multi_accum_kernel); passed by value as a kernel parameter (< 4 KB)
+struct MultiAccumParams {
+    const void* src[V6_MULTI_MAX];      // bf16 tensors, 16-byte aligned, dense
+    long long dst_off[V6_MULTI_MAX];    // element offset into the fp32 destination (multiple of 8)
+    long long numel[V6_MULTI_MAX];
+    int count;
+};
+
 struct OptimParams {
     float* w;              // fp32 master weights (flat)
     const float* g;        // fp32 gradients (flat)
@@ -108,7 +117,12 @@ int v6_bcast_gemm_bf16(const void* A, void* B_local, const void* B_server_peer, 
 int v6_flash_attn_bwd(const void* q, const void* k, const void* v, const void* dout, const void* kt, const void* qt,
                       const void* dot, const float* lse2, const float* delta, void* dq, void* dk, void* dv, int B, int S,
                       int Hq, int Hkv, int D, float softmax_scale, int causal, cudaStream_t stream);
+int v6_maxpool3x3s2_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, cudaStream_t s);
+int v6_maxpool3x3s2_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, cudaStream_t s);
+int v6_image_normalize(const void* img, void* out, long long N, long long HW, float m0, float m1, float m2, float s0, float s1,
+                       float s2, cudaStream_t s);
 long long v6_bn_scratch_floats();
+int v6_multi_accum_bf16(const MultiAccumParams* p, float* dst, cudaStream_t s);
 int v6_bn_fwd(const void* x, const void* res, const float* gamma, const float* beta, float* running_mean, float* running_var,
               long long* num_batches_tracked, void* y, float* mean, float* rstd, float* scale_bias, float* scratch, long long R,
               int C, float eps, float momentum, int relu, cudaStream_t s);

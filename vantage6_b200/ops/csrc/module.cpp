@@ -4,6 +4,7 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -144,6 +145,29 @@ PYBIND11_MODULE(_C, m) {
     });
 
     // ------------------------------------------------------------------ fused BatchNorm (+add)(+ReLU), NHWC bf16
+    m.def("multi_accum_bf16", [](std::vector<u64> src, std::vector<long long> off, std::vector<long long> numel, u64 dst, u64 s) {
+        if (src.size() != off.size() || src.size() != numel.size()) throw std::runtime_error("multi_accum_bf16: list sizes differ");
+        for (size_t base = 0; base < src.size(); base += V6_MULTI_MAX) {
+            MultiAccumParams p;
+            p.count = (int)std::min<size_t>(V6_MULTI_MAX, src.size() - base);
+            for (int i = 0; i < p.count; ++i) {
+                p.src[i] = P<void>(src[base + i]);
+                p.dst_off[i] = off[base + i];
+                p.numel[i] = numel[base + i];
+            }
+            check(v6_multi_accum_bf16(&p, P<float>(dst), S(s)), "multi_accum_bf16");
+        }
+    });
+    m.def("maxpool3x3s2_fwd", [](u64 x, u64 y, u64 idx, int N, int H, int W, int C, u64 s) {
+        check(v6_maxpool3x3s2_fwd(P<void>(x), P<void>(y), P<void>(idx), N, H, W, C, S(s)), "maxpool3x3s2_fwd");
+    });
+    m.def("maxpool3x3s2_bwd", [](u64 dy, u64 idx, u64 dx, int N, int H, int W, int C, u64 s) {
+        check(v6_maxpool3x3s2_bwd(P<void>(dy), P<void>(idx), P<void>(dx), N, H, W, C, S(s)), "maxpool3x3s2_bwd");
+    });
+    m.def("image_normalize", [](u64 img, u64 out, long long N, long long HW, float m0, float m1, float m2, float s0, float s1,
+                                float s2, u64 s) {
+        check(v6_image_normalize(P<void>(img), P<void>(out), N, HW, m0, m1, m2, s0, s1, s2, S(s)), "image_normalize");
+    });
     m.def("bn_fwd", [](u64 x, u64 res, u64 gamma, u64 beta, u64 rmean, u64 rvar, u64 nbt, u64 y, u64 mean, u64 rstd,
                        u64 scale_bias, u64 scratch, long long R, int C, float eps, float momentum, bool relu, u64 s) {
         check(v6_bn_fwd(P<void>(x), P<void>(res), P<float>(gamma), P<float>(beta), P<float>(rmean), P<float>(rvar),

@@ -124,6 +124,32 @@ extern "C" int v6_cast_bf16(const float* src, void* dst, long long n, cudaStream
     V6_CHECK_LAUNCH(); return 0;
 }
 
+// Multi-tensor gradient sink: dst[off_k + i] += float(src_k[i]) for up to MULTI_MAX bf16 tensors in ONE launch
+// (the per-layer bf16 weight gradients the conv backward produces -> the flat fp32 gradient buffer;
+// replaces one cast + one add launch per layer).  blockIdx.y = tensor, blockIdx.x strides over it.
+__global__ void __launch_bounds__(256) multi_accum_kernel(const MultiAccumParams p, float* __restrict__ dst) {
+    const int k = blockIdx.y;
+    const __nv_bfloat16* __restrict__ src = reinterpret_cast<const __nv_bfloat16*>(p.src[k]);
+    float* __restrict__ d = dst + p.dst_off[k];
+    const long long n = p.numel[k], n8 = n >> 3;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4*>(src) + i);
+        float4 a = reinterpret_cast<float4*>(d)[2 * i], b = reinterpret_cast<float4*>(d)[2 * i + 1];
+        const float2 t0 = unpack_bf16x2(t.x), t1 = unpack_bf16x2(t.y), t2 = unpack_bf16x2(t.z), t3 = unpack_bf16x2(t.w);
+        a.x += t0.x; a.y += t0.y; a.z += t1.x; a.w += t1.y;
+        b.x += t2.x; b.y += t2.y; b.z += t3.x; b.w += t3.y;
+        reinterpret_cast<float4*>(d)[2 * i] = a;
+        reinterpret_cast<float4*>(d)[2 * i + 1] = b;
+    }
+    if (blockIdx.x == 0)
+        for (long long i = (n8 << 3) + threadIdx.x; i < n; i += blockDim.x) d[i] += __bfloat162float(src[i]);
+}
+extern "C" int v6_multi_accum_bf16(const MultiAccumParams* p, float* dst, cudaStream_t s) {
+    if (p->count < 1 || p->count > V6_MULTI_MAX) return (int)cudaErrorInvalidValue;
+    multi_accum_kernel<<<dim3(32, p->count), 256, 0, s>>>(*p, dst);
+    V6_CHECK_LAUNCH(); return 0;
+}
+
 // out[0] += sum(x^2)  (out must be zeroed by the caller); used for global-norm clipping:
 // the clip coefficient is then computed on device and consumed via OptimParams::grad_scale_ptr.
 __global__ void __launch_bounds__(512, 2) sumsq_kernel(const float* __restrict__ x, long long n4, float* out) {

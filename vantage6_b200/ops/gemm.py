@@ -40,7 +40,7 @@ def gemm_bf16(x2: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = 
     C = native()
     # 2-CTA (cta_group::2, 256x256 tiles) when there is enough work to fill 74 SM pairs; the 1-CTA
     # 128x256 kernel otherwise (finer tiles -> better SM fill for small problems).
-    two_cta = _two_cta_default() if variant is None else variant == "2cta"
+    two_cta = _two_cta_default(M, N, K) if variant is None else variant == "2cta"
     if two_cta and M >= 256 and N >= 256 and hasattr(C, "gemm2_bf16"):
         C.gemm2_bf16(x2.data_ptr(), W.data_ptr(), out.data_ptr(), 0 if bias is None else bias.data_ptr(),
                      M, N, K, x2.stride(0), W.stride(0), out.stride(0), act, stream_ptr())
@@ -50,10 +50,17 @@ def gemm_bf16(x2: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = 
     return out
 
 
-def _two_cta_default() -> bool:
+def _two_cta_default(M: int, N: int, K: int) -> bool:
+    """Measured on B200 (profiles/kernel_bench_r1b.json): the 2-CTA kernel wins when the K loop is long
+    enough to amortise the cluster prologue and there are >= ~1 wave of 256x256 tiles (8192^3: 1363 vs 1247
+    TFLOP/s, 16384x4096x4096: 1262 vs 1006); the 1-CTA kernel wins or ties on short-K / few-tile problems.
+    ``V6B200_GEMM_2CTA=0|1`` forces one kernel."""
     import os
 
-    return os.environ.get("V6B200_GEMM_2CTA", "0") == "1"
+    forced = os.environ.get("V6B200_GEMM_2CTA")
+    if forced in ("0", "1"):
+        return forced == "1"
+    return K >= 2048 and M % 256 == 0 and (M // 256) * ((N + 255) // 256) >= 64
 
 
 def bcast_gemm_bf16(x2: torch.Tensor, W_local: torch.Tensor, W_server_ptr: int, ready_flags: torch.Tensor,

@@ -188,6 +188,27 @@ def clip_grad_coef(grads: torch.Tensor, max_norm: float, scratch: Optional[torch
     return torch.clamp(max_norm / (nrm + 1e-6), max=1.0).reshape(1)
 
 
+def multi_accumulate(dst: torch.Tensor, items) -> None:
+    """dst[off : off + g.numel()] += g for every (g, off) in ``items`` (g: dense bf16, memory order = the
+    destination's).  CUDA: one launch per 96 tensors (csrc/optim.cu::multi_accum_kernel)."""
+    if not items:
+        return
+    if dst.is_cuda:
+        count(-(-len(items) // 96))
+        native().multi_accum_bf16([g.data_ptr() for g, _ in items], [int(o) for _, o in items],
+                                  [g.numel() for g, _ in items], dst.data_ptr(), stream_ptr())
+    else:
+        for g, off in items:
+            dst[off: off + g.numel()] += _dense_1d(g).float()
+
+
+def _dense_1d(g: torch.Tensor) -> torch.Tensor:
+    """The tensor's elements in memory order (channels-last 4-D tensors are permuted back first)."""
+    if g.dim() == 4 and not g.is_contiguous():
+        return g.permute(0, 2, 3, 1).reshape(-1)
+    return g.reshape(-1)
+
+
 def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
     if src.is_cuda:
         native().cast_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), stream_ptr())

@@ -47,6 +47,9 @@ class FederatedTrainer:
                                    process_group=process_group, shadow_bf16=shadow_bf16)
         self.fm = FlatModel(self.model, storage=self.engine.w, shadow=self.engine.shadow,
                             include_buffers=include_buffers)
+        from ..models.transformer import attach_shadow
+
+        attach_shadow(self.model, self.fm)      # ShadowLinear / ShadowConv2d read the bf16 copy (no-op without a shadow)
         self.upload_mode = upload
         # delta modes: received global model (trainable prefix saved by the fused optimizer on the
         # first local step; the float-buffer tail, e.g. BatchNorm statistics, saved per round below)
@@ -87,6 +90,7 @@ class FederatedTrainer:
         with ctx:
             loss = self.forward_loss(self.model, x, y)
         loss.backward()
+        self.fm.flush_grad_sink()          # bf16 conv weight gradients -> flat fp32 grads, one multi-tensor kernel
         self.loss_sum += loss.detach().float()
         if self.torch_opt is not None:
             if self.max_grad_norm:
@@ -138,6 +142,8 @@ class FederatedTrainer:
             self._step_body(self._static_x, self._static_y, variant)
         self._graph_launches[variant] = LAUNCHES[0] - before      # our kernels inside one replay
         self.engine.w.copy_(snap[0])
+        if self.engine.shadow is not None:          # the warm-up / capture steps advanced the bf16 copy as well
+            self.engine.shadow.copy_(self.engine.w.to(torch.bfloat16))
         if snap_opt is not None:
             self.opt.load_state_dict(snap_opt)
         self.loss_sum.copy_(snap[2])
