@@ -127,7 +127,9 @@ def imagenet_forward_loss(model: nn.Module, x: torch.Tensor, y: torch.Tensor) ->
     The normalisation runs on the GPU inside the captured step so the host only ever ships the
     raw uint8 batch (9.6 MB for 64x3x224x224) over PCIe.
     """
-    if x.dtype == torch.uint8 and x.is_cuda and getattr(model, "fused_bn", False) and x.is_contiguous() \
+    stem = getattr(model, "conv1", None)
+    bf16_stem = torch.is_autocast_enabled() or getattr(stem, "w_bf16", None) is not None
+    if x.dtype == torch.uint8 and x.is_cuda and getattr(model, "fused_bn", False) and bf16_stem and x.is_contiguous() \
             and (x.shape[2] * x.shape[3]) % 4 == 0:
         from ..ops.pool import image_normalize
 

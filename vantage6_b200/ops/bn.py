@@ -52,31 +52,39 @@ class _BNFn(torch.autograd.Function):
         rstd = torch.empty(C, device=x.device, dtype=torch.float32)
         scale_bias = torch.empty(2 * C, device=x.device, dtype=torch.float32)
         part, _ = _get_scratch(x.device, C)
+        mask = torch.empty((R, C // 8), device=x.device, dtype=torch.uint8) if relu else None    # 1 bit / element
         count(2)                                             # stats(+finalize) + apply
         native().bn_fwd(x.data_ptr(), 0 if residual is None else residual.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                         0 if running_mean is None else running_mean.data_ptr(),
                         0 if running_var is None else running_var.data_ptr(),
-                        0 if num_batches_tracked is None else num_batches_tracked.data_ptr(), y.data_ptr(), mean.data_ptr(),
-                        rstd.data_ptr(),
+                        0 if num_batches_tracked is None else num_batches_tracked.data_ptr(), y.data_ptr(),
+                        0 if mask is None else mask.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                         scale_bias.data_ptr(), part.data_ptr(), R, C, eps, momentum, relu, stream_ptr())
-        ctx.save_for_backward(x, y if relu else None, gamma, mean, rstd)
+        ctx.save_for_backward(x, mask, gamma, mean, rstd)        # the ReLU mask, not y: 16x fewer bytes re-read
         ctx.relu, ctx.has_res, ctx.R, ctx.C = relu, residual is not None, R, C
+        ctx.params = (gamma, beta)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, gamma, mean, rstd = ctx.saved_tensors
+        x, mask, gamma, mean, rstd = ctx.saved_tensors
         if not dy.is_contiguous(memory_format=torch.channels_last):
             dy = dy.contiguous(memory_format=torch.channels_last)
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if ctx.has_res else None
-        dgamma = torch.empty_like(gamma)
-        dbeta = torch.empty_like(gamma)
+        # Flat-buffer models pre-allocate .grad as views of one fp32 gradient buffer (models/flat.py): the
+        # kernel then accumulates dgamma / dbeta straight into it (no AccumulateGrad add launches).
+        pg, pb = ctx.params
+        direct = all(p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous() for p in (pg, pb))
+        dgamma = pg.grad if direct else torch.empty_like(gamma)
+        dbeta = pb.grad if direct else torch.empty_like(gamma)
         part, coef = _get_scratch(x.device, ctx.C)
         count(2)                                             # reduce(+finalize) + apply
-        native().bn_bwd(dy.data_ptr(), 0 if y is None else y.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
+        native().bn_bwd(dy.data_ptr(), 0 if mask is None else mask.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
                         rstd.data_ptr(), dx.data_ptr(), 0 if dres is None else dres.data_ptr(), dgamma.data_ptr(),
-                        dbeta.data_ptr(), coef.data_ptr(), part.data_ptr(), ctx.R, ctx.C, ctx.relu, False, stream_ptr())
+                        dbeta.data_ptr(), coef.data_ptr(), part.data_ptr(), ctx.R, ctx.C, ctx.relu, direct, stream_ptr())
+        if direct:
+            return dx, dres, None, None, None, None, None, None, None, None
         return dx, dres, dgamma, dbeta, None, None, None, None, None, None
 
 

@@ -124,11 +124,11 @@ int v6_image_normalize(const void* img, void* out, long long N, long long HW, fl
 long long v6_bn_scratch_floats();
 int v6_multi_accum_bf16(const MultiAccumParams* p, float* dst, cudaStream_t s);
 int v6_bn_fwd(const void* x, const void* res, const float* gamma, const float* beta, float* running_mean, float* running_var,
-              long long* num_batches_tracked, void* y, float* mean, float* rstd, float* scale_bias, float* scratch, long long R,
-              int C, float eps, float momentum, int relu, cudaStream_t s);
+              long long* num_batches_tracked, void* y, void* relu_mask, float* mean, float* rstd, float* scale_bias,
+              float* scratch, long long R, int C, float eps, float momentum, int relu, cudaStream_t s);
 int v6_bn_apply(const void* x, const void* res, const float* scale, const float* bias, void* y, long long R, int C, int relu,
                 cudaStream_t s);
-int v6_bn_bwd(const void* dy, const void* y, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
+int v6_bn_bwd(const void* dy, const void* relu_mask, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
               void* dres, float* dgamma, float* dbeta, float* coef, float* scratch, long long R, int C, int relu,
               int accumulate, cudaStream_t s);
 int v6_gemm2_bf16(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, int lda, int ldb, int ldc,

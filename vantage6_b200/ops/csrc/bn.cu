@@ -56,6 +56,7 @@ V6_DEVINL void loadf8(const float* p, float (&v)[8]) {
 // (v2 profile, profiles/launches_resnet50_fusedbn_r1.txt: finalize 12.5 us per launch, latency-bound,
 // 15% of the forward; stats at 2 TB/s because only 2 CTAs/SM were resident.)
 constexpr int G1 = 16;
+constexpr int ONE_LEVEL_MAX = 128;
 constexpr int MAX_CTAS = 148 * 8;                    // upper bound on reduce CTAs per launch
 constexpr int L2_SLOTS = 256;                        // >= MAX_CTAS / G1 + slices
 constexpr size_t SCR_L2 = (size_t)MAX_CTAS * 128;    // float offsets into the scratch buffer
@@ -73,29 +74,39 @@ static inline Red make_red(float* scratch) {
     return Red{scratch, scratch + SCR_L2, reinterpret_cast<int*>(scratch + SCR_CNT1), reinterpret_cast<int*>(scratch + SCR_CNT2)};
 }
 
-// true in exactly one CTA: the last of `expected` to arrive at `counter` (which it resets to 0)
+// true in exactly one CTA: the last of `expected` to arrive at `counter` (which it resets to 0).
+// CUTLASS-semaphore pattern: the CTA barrier orders every thread's partial writes before thread 0's
+// acq_rel arrival (release is cumulative), and the acquire side orders the last CTA's reads after it.
 V6_DEVINL bool arrive_last(int* counter, int expected, int* s_flag) {
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const int last = atomicAdd(counter, 1) == expected - 1;
-        if (last) atomicExch(counter, 0);
+        int old;
+        asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+        const int last = old == expected - 1;
+        if (last) *counter = 0;                 // every expected arrival has happened: plain reset for the next launch
         *s_flag = last;
     }
     __syncthreads();
-    const bool last = *s_flag != 0;
-    if (last) __threadfence();
-    return last;
+    return *s_flag != 0;
 }
 
-// dst[col] = sum_p src[p][col], p < n; cols in {16..128}; THREADS/cols lanes each take every lanes-th row
+// dst[col] = sum_p src[p][col], p < n; cols in {16..128}.  float4 columns: cols/4 threads per row, THREADS/(cols/4)
+// row lanes, up to 8 independent 16 B loads in flight per thread; fixed summation order.
 V6_DEVINL void fold_rows(const float* __restrict__ src, int n, int cols, float* red, float* dst) {
-    const int lanes = THREADS / cols;
-    const int col = threadIdx.x % cols, ln = threadIdx.x / cols;
-    float s = 0.f;
-#pragma unroll 4
-    for (int p = ln; p < n; p += lanes) s += __ldcg(src + (size_t)p * cols + col);
-    red[threadIdx.x] = s;
+    const int c4 = cols >> 2, lanes = THREADS / c4;
+    const int col4 = threadIdx.x % c4, ln = threadIdx.x / c4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p0 = ln; p0 < n; p0 += 8 * lanes) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int p = p0 + u * lanes;
+            v[u] = p < n ? __ldcg(reinterpret_cast<const float4*>(src + (size_t)p * cols) + col4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+    }
+    reinterpret_cast<float4*>(red)[threadIdx.x] = s;          // red: [lanes][cols]
     __syncthreads();
     if (threadIdx.x < cols) {
         float t = 0.f;
@@ -108,7 +119,7 @@ V6_DEVINL void fold_rows(const float* __restrict__ src, int n, int cols, float* 
 // slice.  Returns true in the one CTA per slice that ends up with the totals in tot[0..SW) (sum a) and
 // tot[SW..2SW) (sum b).
 V6_DEVINL bool slice_reduce(float (&a)[8], float (&b)[8], const Red& rd, int SW, float* tot) {
-    __shared__ float red[8 * 128];
+    __shared__ __align__(16) float red[8 * 128];
     __shared__ int s_flag;
     const int CGS = SW >> 3, cols = 2 * SW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -125,19 +136,24 @@ V6_DEVINL bool slice_reduce(float (&a)[8], float (&b)[8], const Red& rd, int SW,
     }
     __syncthreads();
     const int slice = blockIdx.y, rc = blockIdx.x, nrc = gridDim.x;
-    const int ngrp = (nrc + G1 - 1) / G1;
+    const int g1 = nrc <= ONE_LEVEL_MAX ? nrc : G1;          // few row-CTAs: one fold does it all
+    const int ngrp = (nrc + g1 - 1) / g1;
     if (threadIdx.x < cols) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < THREADS / 32; ++w) s += red[w * 128 + threadIdx.x];
         __stcg(rd.l1 + ((size_t)slice * nrc + rc) * cols + threadIdx.x, s);
     }
-    const int grp = rc / G1;
-    const int gsz = min(G1, nrc - grp * G1);
+    const int grp = rc / g1;
+    const int gsz = min(g1, nrc - grp * g1);
     if (!arrive_last(rd.cnt1 + slice * ngrp + grp, gsz, &s_flag)) return false;
-    fold_rows(rd.l1 + ((size_t)slice * nrc + (size_t)grp * G1) * cols, gsz, cols, red, rd.l2 + ((size_t)slice * ngrp + grp) * cols);
-    if (!arrive_last(rd.cnt2 + slice, ngrp, &s_flag)) return false;
-    fold_rows(rd.l2 + (size_t)slice * ngrp * cols, ngrp, cols, red, tot);
+    if (ngrp == 1) {
+        fold_rows(rd.l1 + (size_t)slice * nrc * cols, gsz, cols, red, tot);
+    } else {
+        fold_rows(rd.l1 + ((size_t)slice * nrc + (size_t)grp * g1) * cols, gsz, cols, red, rd.l2 + ((size_t)slice * ngrp + grp) * cols);
+        if (!arrive_last(rd.cnt2 + slice, ngrp, &s_flag)) return false;
+        fold_rows(rd.l2 + (size_t)slice * ngrp * cols, ngrp, cols, red, tot);
+    }
     __syncthreads();
     return true;
 }
@@ -196,7 +212,8 @@ __global__ void __launch_bounds__(THREADS, 4) bn_stats_kernel(const __nv_bfloat1
 template <bool RELU, bool RES>
 __global__ void __launch_bounds__(THREADS) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                                                            const float* __restrict__ scale, const float* __restrict__ bias,
-                                                           __nv_bfloat16* __restrict__ y, long long R, int C) {
+                                                           __nv_bfloat16* __restrict__ y, unsigned char* __restrict__ mask,
+                                                           long long R, int C) {
     const int CG = C >> 3, RL = THREADS / CG;
     const int cg = threadIdx.x % CG, rl = threadIdx.x / CG;
     float sc[8], bi[8];
@@ -217,13 +234,16 @@ __global__ void __launch_bounds__(THREADS) bn_apply_kernel(const __nv_bfloat16* 
         for (int u = 0; u < 2; ++u) {
             const long long r = r0 + u * G;
             if (r < R) {
+                unsigned bits = 0;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     float t = fmaf(v[u][k], sc[k], bi[k]);
                     if (RES) t += q[u][k];
+                    if (RELU) bits |= (t > 0.f ? 1u : 0u) << k;
                     v[u][k] = RELU ? fmaxf(t, 0.f) : t;
                 }
                 store8(y + r * C + cg * 8, v[u]);
+                if (RELU && mask) mask[r * CG + cg] = (unsigned char)bits;      // 1 bit / element for the backward
             }
         }
     }
@@ -231,15 +251,14 @@ __global__ void __launch_bounds__(THREADS) bn_apply_kernel(const __nv_bfloat16* 
 
 // ---------------------------------------------------------------------------------- backward
 template <bool RELU>
-V6_DEVINL void acc_bwd(const uint4& graw, const uint4& xraw, const uint4& yraw, const float (&mu)[8], const float (&rs)[8],
+V6_DEVINL void acc_bwd(const uint4& graw, const uint4& xraw, unsigned bits, const float (&mu)[8], const float (&rs)[8],
                        float (&sg)[8], float (&sgx)[8]) {
-    float g[8], xv[8], yv[8];
+    float g[8], xv[8];
     unpack8(graw, g);
     unpack8(xraw, xv);
-    if (RELU) unpack8(yraw, yv);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float gg = (RELU && !(yv[k] > 0.f)) ? 0.f : g[k];
+        const float gg = (RELU && !((bits >> k) & 1u)) ? 0.f : g[k];
         sg[k] += gg;
         sgx[k] = fmaf(gg, (xv[k] - mu[k]) * rs[k], sgx[k]);
     }
@@ -249,7 +268,7 @@ V6_DEVINL void acc_bwd(const uint4& graw, const uint4& xraw, const uint4& yraw, 
 // the coefficients of dx = c0 * g + c1 * x + c2 with
 //   c0 = gamma*rstd, c1 = -gamma*rstd^2*mean(g*xhat), c2 = -c0*mean(g) - c1*mean
 template <bool RELU>
-__global__ void __launch_bounds__(THREADS, 3) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+__global__ void __launch_bounds__(THREADS, 3) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const unsigned char* __restrict__ mask,
                                        const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                        const float* __restrict__ mean, const float* __restrict__ rstd, Red rd,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef,
@@ -258,6 +277,7 @@ __global__ void __launch_bounds__(THREADS, 3) bn_bwd_reduce_kernel(const __nv_bf
     const int SW = C < 64 ? C : 64, CGS = SW >> 3, RL = THREADS / CGS;
     const int cg = threadIdx.x % CGS, rl = threadIdx.x / CGS;
     const size_t c0 = (size_t)blockIdx.y * SW + cg * 8;
+    const long long CGT = C >> 3, cgt = (long long)blockIdx.y * CGS + cg;       // mask: [R][C/8] bytes
     float mu[8], rs[8], sg[8], sgx[8];
     loadf8(mean + c0, mu);
     loadf8(rstd + c0, rs);
@@ -266,22 +286,23 @@ __global__ void __launch_bounds__(THREADS, 3) bn_bwd_reduce_kernel(const __nv_bf
     const long long G = (long long)gridDim.x * RL;
     long long r = (long long)blockIdx.x * RL + rl;
     for (; r + G < R; r += 2 * G) {                                            // 2 rows x 3 tensors in flight
-        uint4 g[2], xv[2], yv[2];
+        uint4 g[2], xv[2];
+        unsigned mb[2] = {0xffu, 0xffu};
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const long long o = (r + u * G) * C + c0;
             g[u] = ldg_nc_v4(dy + o);
             xv[u] = ldg_nc_v4(x + o);
-            if (RELU) yv[u] = ldg_nc_v4(y + o);
+            if (RELU) mb[u] = __ldg(mask + (r + u * G) * CGT + cgt);
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) acc_bwd<RELU>(g[u], xv[u], yv[u], mu, rs, sg, sgx);
+        for (int u = 0; u < 2; ++u) acc_bwd<RELU>(g[u], xv[u], mb[u], mu, rs, sg, sgx);
     }
     for (; r < R; r += G) {
         const long long o = r * C + c0;
-        uint4 yv = make_uint4(0, 0, 0, 0);
-        if (RELU) yv = ldg_nc_v4(y + o);
-        acc_bwd<RELU>(ldg_nc_v4(dy + o), ldg_nc_v4(x + o), yv, mu, rs, sg, sgx);
+        unsigned mb = 0xffu;
+        if (RELU) mb = __ldg(mask + r * CGT + cgt);
+        acc_bwd<RELU>(ldg_nc_v4(dy + o), ldg_nc_v4(x + o), mb, mu, rs, sg, sgx);
     }
     if (!slice_reduce(sg, sgx, rd, SW, tot)) return;
     if (threadIdx.x < SW) {
@@ -299,7 +320,7 @@ __global__ void __launch_bounds__(THREADS, 3) bn_bwd_reduce_kernel(const __nv_bf
 }
 
 template <bool RELU, bool RES>
-__global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+__global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const unsigned char* __restrict__ mask,
                                                                const __nv_bfloat16* __restrict__ x, const float* __restrict__ coef,
                                                                __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres,
                                                                long long R, int C) {
@@ -311,14 +332,15 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const __nv_bfloat
     loadf8(coef + 2 * C + cg * 8, c2);
     const long long G = (long long)gridDim.x * RL;
     for (long long r0 = (long long)blockIdx.x * RL + rl; r0 < R; r0 += 2 * G) {
-        float g[2][8], xv[2][8], yv[2][8];
+        float g[2][8], xv[2][8];
+        unsigned mb[2] = {0xffu, 0xffu};
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const long long r = r0 + u * G;
             if (r < R) {
                 load8(dy + r * C + cg * 8, g[u]);
                 load8(x + r * C + cg * 8, xv[u]);
-                if (RELU) load8(y + r * C + cg * 8, yv[u]);
+                if (RELU) mb[u] = __ldg(mask + r * CG + cg);
             }
         }
 #pragma unroll
@@ -328,7 +350,7 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const __nv_bfloat
                 float o[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    if (RELU && !(yv[u][k] > 0.f)) g[u][k] = 0.f;
+                    if (RELU && !((mb[u] >> k) & 1u)) g[u][k] = 0.f;
                     o[k] = fmaf(c0[k], g[u][k], fmaf(c1[k], xv[u][k], c2[k]));
                 }
                 if (RES) store8(dres + r * C + cg * 8, g[u]);
@@ -358,7 +380,7 @@ static int wave_ctas(K kernel, int& cache) {
 // reduce grids: x = row-CTAs, y = 64-channel slices
 static inline dim3 reduce_grid(long long R, int C, int target) {
     const int SW = C < 64 ? C : 64, slices = C / SW, RL = THREADS / (SW >> 3);
-    long long nrc = (R + RL - 1) / RL;
+    long long nrc = (R + 4LL * RL - 1) / (4LL * RL);          // >= 4 rows per thread: the unrolled fast path, fewer partials
     const long long cap = target / slices > 0 ? target / slices : 1;
     if (nrc > cap) nrc = cap;
     return dim3((unsigned)(nrc < 1 ? 1 : nrc), (unsigned)slices, 1);
@@ -378,7 +400,7 @@ static inline int apply_grid(long long R, int C) {
 extern "C" long long v6_bn_scratch_floats() { return (long long)bn::SCR_FLOATS; }
 
 extern "C" int v6_bn_fwd(const void* x, const void* res, const float* gamma, const float* beta, float* running_mean,
-                         float* running_var, long long* num_batches_tracked, void* y, float* mean, float* rstd,
+                         float* running_var, long long* num_batches_tracked, void* y, void* relu_mask, float* mean, float* rstd,
                          float* scale_bias, float* scratch, long long R, int C, float eps, float momentum, int relu,
                          cudaStream_t s) {
     using namespace bn;
@@ -392,11 +414,12 @@ extern "C" int v6_bn_fwd(const void* x, const void* res, const float* gamma, con
     const __nv_bfloat16* rr = (const __nv_bfloat16*)res;
     __nv_bfloat16* yy = (__nv_bfloat16*)y;
     if (relu) {
-        if (res) bn_apply_kernel<true, true><<<ag, THREADS, 0, s>>>(xx, rr, scale_bias, scale_bias + C, yy, R, C);
-        else bn_apply_kernel<true, false><<<ag, THREADS, 0, s>>>(xx, rr, scale_bias, scale_bias + C, yy, R, C);
+        unsigned char* mk = (unsigned char*)relu_mask;
+        if (res) bn_apply_kernel<true, true><<<ag, THREADS, 0, s>>>(xx, rr, scale_bias, scale_bias + C, yy, mk, R, C);
+        else bn_apply_kernel<true, false><<<ag, THREADS, 0, s>>>(xx, rr, scale_bias, scale_bias + C, yy, mk, R, C);
     } else {
-        if (res) bn_apply_kernel<false, true><<<ag, THREADS, 0, s>>>(xx, rr, scale_bias, scale_bias + C, yy, R, C);
-        else bn_apply_kernel<false, false><<<ag, THREADS, 0, s>>>(xx, rr, scale_bias, scale_bias + C, yy, R, C);
+        if (res) bn_apply_kernel<false, true><<<ag, THREADS, 0, s>>>(xx, rr, scale_bias, scale_bias + C, yy, nullptr, R, C);
+        else bn_apply_kernel<false, false><<<ag, THREADS, 0, s>>>(xx, rr, scale_bias, scale_bias + C, yy, nullptr, R, C);
     }
     V6_CHECK_LAUNCH();
     return 0;
@@ -412,25 +435,26 @@ extern "C" int v6_bn_apply(const void* x, const void* res, const float* scale, c
     const __nv_bfloat16* rr = (const __nv_bfloat16*)res;
     __nv_bfloat16* yy = (__nv_bfloat16*)y;
     if (relu) {
-        if (res) bn_apply_kernel<true, true><<<ag, THREADS, 0, s>>>(xx, rr, scale, bias, yy, R, C);
-        else bn_apply_kernel<true, false><<<ag, THREADS, 0, s>>>(xx, rr, scale, bias, yy, R, C);
+        if (res) bn_apply_kernel<true, true><<<ag, THREADS, 0, s>>>(xx, rr, scale, bias, yy, nullptr, R, C);
+        else bn_apply_kernel<true, false><<<ag, THREADS, 0, s>>>(xx, rr, scale, bias, yy, nullptr, R, C);
     } else {
-        if (res) bn_apply_kernel<false, true><<<ag, THREADS, 0, s>>>(xx, rr, scale, bias, yy, R, C);
-        else bn_apply_kernel<false, false><<<ag, THREADS, 0, s>>>(xx, rr, scale, bias, yy, R, C);
+        if (res) bn_apply_kernel<false, true><<<ag, THREADS, 0, s>>>(xx, rr, scale, bias, yy, nullptr, R, C);
+        else bn_apply_kernel<false, false><<<ag, THREADS, 0, s>>>(xx, rr, scale, bias, yy, nullptr, R, C);
     }
     V6_CHECK_LAUNCH();
     return 0;
 }
 
 // coef scratch: 3*C floats. dres may be null (no residual branch).
-extern "C" int v6_bn_bwd(const void* dy, const void* y, const void* x, const float* gamma, const float* mean, const float* rstd,
+extern "C" int v6_bn_bwd(const void* dy, const void* relu_mask, const void* x, const float* gamma, const float* mean, const float* rstd,
                          void* dx, void* dres, float* dgamma, float* dbeta, float* coef, float* scratch, long long R, int C,
                          int relu, int accumulate, cudaStream_t s) {
     using namespace bn;
     if (!shape_ok(C)) return (int)cudaErrorInvalidValue;
     const __nv_bfloat16* dyy = (const __nv_bfloat16*)dy;
-    const __nv_bfloat16* yy = (const __nv_bfloat16*)y;
+    const unsigned char* yy = (const unsigned char*)relu_mask;     // 1 bit / element, written by the forward apply pass
     const __nv_bfloat16* xx = (const __nv_bfloat16*)x;
+    if (relu && !relu_mask) return (int)cudaErrorInvalidValue;
     static int wave_relu = 0, wave_lin = 0;
     const dim3 rg = reduce_grid(R, C, relu ? wave_ctas(bn_bwd_reduce_kernel<true>, wave_relu) : wave_ctas(bn_bwd_reduce_kernel<false>, wave_lin));
     if (relu) bn_bwd_reduce_kernel<true><<<rg, THREADS, 0, s>>>(dyy, yy, xx, gamma, mean, rstd, make_red(scratch), dgamma, dbeta, coef, R, C, accumulate);

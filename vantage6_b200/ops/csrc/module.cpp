@@ -168,10 +168,10 @@ PYBIND11_MODULE(_C, m) {
                                 float s2, u64 s) {
         check(v6_image_normalize(P<void>(img), P<void>(out), N, HW, m0, m1, m2, s0, s1, s2, S(s)), "image_normalize");
     });
-    m.def("bn_fwd", [](u64 x, u64 res, u64 gamma, u64 beta, u64 rmean, u64 rvar, u64 nbt, u64 y, u64 mean, u64 rstd,
+    m.def("bn_fwd", [](u64 x, u64 res, u64 gamma, u64 beta, u64 rmean, u64 rvar, u64 nbt, u64 y, u64 mask, u64 mean, u64 rstd,
                        u64 scale_bias, u64 scratch, long long R, int C, float eps, float momentum, bool relu, u64 s) {
         check(v6_bn_fwd(P<void>(x), P<void>(res), P<float>(gamma), P<float>(beta), P<float>(rmean), P<float>(rvar),
-                        P<long long>(nbt), P<void>(y), P<float>(mean), P<float>(rstd), P<float>(scale_bias), P<float>(scratch), R,
+                        P<long long>(nbt), P<void>(y), P<void>(mask), P<float>(mean), P<float>(rstd), P<float>(scale_bias), P<float>(scratch), R,
                         C, eps, momentum, relu, S(s)),
               "bn_fwd");
     });
