@@ -121,3 +121,35 @@ def test_resnet_shadow_conv_trainer_matches_autocast(dev):
     b, _ = run(False)
     assert ok
     assert abs(a[0] - b[0]) < 0.08 and abs(a[-1] - b[-1]) < 0.35, (a, b)
+
+
+@pytest.mark.parametrize("N,H,W,O", [(2, 64, 64, 8), (3, 224, 224, 64), (1, 32, 48, 16)])
+def test_stem_space_to_depth_matches_direct_conv(dev, N, H, W, O):
+    """4x4/s1 conv on the space-to-depth image == 7x7/s2/p3 conv on the normalised image (values and filter grads)."""
+    from vantage6_b200.models.resnet import _MEAN, _STD
+    from vantage6_b200.ops import pool
+
+    g = torch.Generator().manual_seed(4)
+    img = torch.randint(0, 256, (N, 3, H, W), dtype=torch.uint8, generator=g).to(dev)
+    conv = torch.nn.Conv2d(3, O, 7, stride=2, padding=3, bias=False).to(dev).to(memory_format=torch.channels_last)
+    assert pool.stem_s2d_supported(img, conv)
+    y = pool.stem_s2d(img, conv, _MEAN, _STD)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    got_dw = conv.weight.grad.clone()
+    conv.weight.grad = None
+    m = torch.tensor(_MEAN, device=dev).view(1, 3, 1, 1)
+    s = torch.tensor(_STD, device=dev).view(1, 3, 1, 1)
+    xn = ((img.float() - m) / s).to(torch.bfloat16).float()
+    wr = conv.weight.detach().to(torch.bfloat16).float().requires_grad_()
+    yr = torch.nn.functional.conv2d(xn, wr, None, 2, 3)
+    yr.backward(dy.float())
+    assert y.shape == yr.shape and y.is_contiguous(memory_format=torch.channels_last)
+    torch.testing.assert_close(y.float(), yr, rtol=2e-2, atol=2e-2)
+    scale = wr.grad.abs().max().item()
+    assert (got_dw - wr.grad).abs().max().item() < 2e-2 * scale
+    # accumulate-into-existing-grad path
+    conv.weight.grad = torch.ones_like(conv.weight, memory_format=torch.channels_last)
+    y2 = pool.stem_s2d(img, conv, _MEAN, _STD)
+    y2.backward(dy)
+    assert ((conv.weight.grad - 1.0) - wr.grad).abs().max().item() < 2e-2 * scale

@@ -101,10 +101,36 @@ class ResNet(nn.Module):
         layers += [Bottleneck(self.inplanes, planes, fused_bn=self.fused_bn) for _ in range(1, blocks)]
         return nn.Sequential(*layers)
 
+    def _stem(self, x: torch.Tensor) -> torch.Tensor:
+        """conv1 + bn1(+ReLU).  uint8 NCHW images are normalised on the GPU (the host only ships raw bytes);
+        on the fused path the stem runs as a space-to-depth 4x4 convolution (ops/pool.py::stem_s2d)."""
+        if x.dtype != torch.uint8:
+            return self.bn1(self.conv1(x.contiguous(memory_format=torch.channels_last)))
+        bf16_stem = torch.is_autocast_enabled() or getattr(self.conv1, "w_bf16", None) is not None
+        if self.fused_bn and x.is_cuda and bf16_stem and torch.is_grad_enabled():
+            from ..ops import pool
+
+            if pool.stem_s2d_supported(x, self.conv1):
+                return self.bn1(pool.stem_s2d(x, self.conv1, _MEAN, _STD))
+            if x.is_contiguous() and (x.shape[2] * x.shape[3]) % 4 == 0:
+                return self.bn1(self.conv1(pool.image_normalize(x, _MEAN, _STD)))
+        key = str(x.device)
+        if key not in _NORM_CACHE:      # created on the eager warm-up pass, never during graph capture
+            _NORM_CACHE[key] = (torch.tensor(_MEAN, device=x.device, dtype=torch.float32).view(1, 3, 1, 1),
+                                1.0 / torch.tensor(_STD, device=x.device, dtype=torch.float32).view(1, 3, 1, 1))
+        mean, inv_std = _NORM_CACHE[key]
+        x = ((x.float() - mean) * inv_std).contiguous(memory_format=torch.channels_last)
+        return self.bn1(self.conv1(x))
+
     def forward(self, x):
-        x = self.maxpool(self.bn1(self.conv1(x)))
+        x = self.maxpool(self._stem(x))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.fc(torch.flatten(self.avgpool(x), 1))
+
+
+_MEAN = (0.485 * 255, 0.456 * 255, 0.406 * 255)
+_STD = (0.229 * 255, 0.224 * 255, 0.225 * 255)
+_NORM_CACHE: dict = {}
 
 
 def resnet50(num_classes: int = 1000, fused_bn: bool = True) -> ResNet:
@@ -116,30 +142,10 @@ def resnet_tiny(num_classes: int = 10, fused_bn: bool = True) -> ResNet:
     return ResNet((1, 1, 1, 1), num_classes, width=8, fused_bn=fused_bn)
 
 
-_MEAN = (0.485 * 255, 0.456 * 255, 0.406 * 255)
-_STD = (0.229 * 255, 0.224 * 255, 0.225 * 255)
-_NORM_CACHE: dict = {}
-
-
 def imagenet_forward_loss(model: nn.Module, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-    """uint8 NCHW images -> normalised channels_last -> logits -> cross-entropy.
+    """uint8 NCHW images (or already-normalised float images) -> logits -> cross-entropy.
 
-    The normalisation runs on the GPU inside the captured step so the host only ever ships the
+    The normalisation runs on the GPU inside the captured step (ResNet._stem), so the host only ever ships the
     raw uint8 batch (9.6 MB for 64x3x224x224) over PCIe.
     """
-    stem = getattr(model, "conv1", None)
-    bf16_stem = torch.is_autocast_enabled() or getattr(stem, "w_bf16", None) is not None
-    if x.dtype == torch.uint8 and x.is_cuda and getattr(model, "fused_bn", False) and bf16_stem and x.is_contiguous() \
-            and (x.shape[2] * x.shape[3]) % 4 == 0:
-        from ..ops.pool import image_normalize
-
-        x = image_normalize(x, _MEAN, _STD)              # one kernel: cast + normalise + NCHW->NHWC, bf16 out
-    elif x.dtype == torch.uint8:
-        key = str(x.device)
-        if key not in _NORM_CACHE:      # created on the eager warm-up pass, never during graph capture
-            _NORM_CACHE[key] = (torch.tensor(_MEAN, device=x.device, dtype=torch.float32).view(1, 3, 1, 1),
-                                1.0 / torch.tensor(_STD, device=x.device, dtype=torch.float32).view(1, 3, 1, 1))
-        mean, inv_std = _NORM_CACHE[key]
-        x = (x.float() - mean) * inv_std
-    x = x.contiguous(memory_format=torch.channels_last)
     return nn.functional.cross_entropy(model(x).float(), y)

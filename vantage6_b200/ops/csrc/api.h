@@ -121,6 +121,10 @@ int v6_maxpool3x3s2_fwd(const void* x, void* y, void* idx, int N, int H, int W, 
 int v6_maxpool3x3s2_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, cudaStream_t s);
 int v6_image_normalize(const void* img, void* out, long long N, long long HW, float m0, float m1, float m2, float s0, float s1,
                        float s2, cudaStream_t s);
+int v6_image_normalize_s2d(const void* img, void* out, int N, int H, int W, float m0, float m1, float m2, float s0, float s1,
+                           float s2, cudaStream_t s);
+int v6_stem_weight_s2d(const void* w, int w_is_bf16, void* ws, int O, cudaStream_t s);
+int v6_stem_wgrad_d2s(const void* dws, float* dw, int O, int accumulate, cudaStream_t s);
 long long v6_bn_scratch_floats();
 int v6_multi_accum_bf16(const MultiAccumParams* p, float* dst, cudaStream_t s);
 int v6_bn_fwd(const void* x, const void* res, const float* gamma, const float* beta, float* running_mean, float* running_var,

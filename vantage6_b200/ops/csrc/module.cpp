@@ -168,6 +168,16 @@ PYBIND11_MODULE(_C, m) {
                                 float s2, u64 s) {
         check(v6_image_normalize(P<void>(img), P<void>(out), N, HW, m0, m1, m2, s0, s1, s2, S(s)), "image_normalize");
     });
+    m.def("image_normalize_s2d", [](u64 img, u64 out, int N, int H, int W, float m0, float m1, float m2, float s0, float s1, float s2,
+                                    u64 s) {
+        check(v6_image_normalize_s2d(P<void>(img), P<void>(out), N, H, W, m0, m1, m2, s0, s1, s2, S(s)), "image_normalize_s2d");
+    });
+    m.def("stem_weight_s2d", [](u64 w, bool w_is_bf16, u64 ws, int O, u64 s) {
+        check(v6_stem_weight_s2d(P<void>(w), w_is_bf16, P<void>(ws), O, S(s)), "stem_weight_s2d");
+    });
+    m.def("stem_wgrad_d2s", [](u64 dws, u64 dw, int O, bool accumulate, u64 s) {
+        check(v6_stem_wgrad_d2s(P<void>(dws), P<float>(dw), O, accumulate, S(s)), "stem_wgrad_d2s");
+    });
     m.def("bn_fwd", [](u64 x, u64 res, u64 gamma, u64 beta, u64 rmean, u64 rvar, u64 nbt, u64 y, u64 mask, u64 mean, u64 rstd,
                        u64 scale_bias, u64 scratch, long long R, int C, float eps, float momentum, bool relu, u64 s) {
         check(v6_bn_fwd(P<void>(x), P<void>(res), P<float>(gamma), P<float>(beta), P<float>(rmean), P<float>(rvar),

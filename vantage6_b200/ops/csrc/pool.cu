@@ -127,6 +127,75 @@ __global__ void __launch_bounds__(THREADS) image_normalize_kernel(const unsigned
     }
 }
 
+// ---------------------------------------------------------------------------------- space-to-depth stem
+// The 7x7 / stride-2 / pad-3 stem convolution on 3 input channels runs on cuDNN's legacy kernels (390 us
+// forward for a 64x224x224 batch, profiles/launches_resnet50_v3_r1.txt) because C=3 defeats the NHWC
+// tensor-core path.  It is algebraically a 4x4 / stride-1 convolution on the 2x2 space-to-depth image
+// (12 real channels, padded to 16 -> the sm_100 implicit-GEMM kernels apply):
+//   y[i,j] = sum_{p,q<4} sum_{r,s<2,c<3} xs[i+p-2, j+q-2, (r,s,c)] * ws[p,q,(r,s,c)]
+//   xs[u,v,(r,s,c)] = x[2u+r, 2v+s, c],   ws[p,q,(r,s,c)] = w[2p+r-1, 2q+s-1, c] (0 outside the 7x7 filter)
+// The asymmetric padding (2 before, 1 after) is materialised by the image kernel: xs is [N, H/2+3, W/2+3, 16].
+
+// one thread = one output pixel of xs: 12 uint8 reads -> 16 bf16 (32 B) write
+__global__ void __launch_bounds__(THREADS) image_normalize_s2d_kernel(const unsigned char* __restrict__ img, __nv_bfloat16* __restrict__ out,
+                                                                      int N, int H, int W, float m0, float m1, float m2, float s0,
+                                                                      float s1, float s2) {
+    const int Hs = H / 2 + 3, Ws = W / 2 + 3;
+    const long long total = (long long)N * Hs * Ws;
+    const float mean[3] = {m0, m1, m2}, inv[3] = {s0, s1, s2};
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(t % Ws);
+        const int u = (int)((t / Ws) % Hs);
+        const int n = (int)(t / ((long long)Ws * Hs));
+        const int uu = u - 2, vv = v - 2;
+        float o[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) o[k] = 0.f;
+        if (uu >= 0 && uu < H / 2 && vv >= 0 && vv < W / 2) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const unsigned char* pl = img + ((long long)n * 3 + c) * H * W + (long long)(2 * uu) * W + 2 * vv;
+                const uchar2 top = *reinterpret_cast<const uchar2*>(pl);
+                const uchar2 bot = *reinterpret_cast<const uchar2*>(pl + W);
+                o[0 * 3 + c] = ((float)top.x - mean[c]) * inv[c];       // (r=0, s=0)
+                o[1 * 3 + c] = ((float)top.y - mean[c]) * inv[c];       // (r=0, s=1)
+                o[2 * 3 + c] = ((float)bot.x - mean[c]) * inv[c];       // (r=1, s=0)
+                o[3 * 3 + c] = ((float)bot.y - mean[c]) * inv[c];       // (r=1, s=1)
+            }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + t * 16);
+        dst[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+        dst[1] = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), 0u, 0u);
+    }
+}
+
+// ws[o][p][q][16] (bf16) from w[o][kh][kw][c] (the flat buffers' [O,H,W,I] layout; fp32 master or bf16 shadow)
+template <typename T>
+__global__ void stem_weight_s2d_kernel(const T* __restrict__ w, __nv_bfloat16* __restrict__ ws, int O) {
+    const int total = O * 256;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int ch = t & 15, q = (t >> 4) & 3, p = (t >> 6) & 3, o = t >> 8;
+        float val = 0.f;
+        if (ch < 12) {
+            const int c = ch % 3, rs = ch / 3, r = rs >> 1, s2 = rs & 1;
+            const int kh = 2 * p + r - 1, kw = 2 * q + s2 - 1;
+            if (kh >= 0 && kh < 7 && kw >= 0 && kw < 7) val = (float)w[((o * 7 + kh) * 7 + kw) * 3 + c];
+        }
+        ws[t] = __float2bfloat16(val);
+    }
+}
+
+// dw[o][kh][kw][c] (fp32) (+)= dws[o][p][q][ch]
+__global__ void stem_wgrad_d2s_kernel(const __nv_bfloat16* __restrict__ dws, float* __restrict__ dw, int O, int accumulate) {
+    const int total = O * 147;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int c = t % 3, kw = (t / 3) % 7, kh = (t / 21) % 7, o = t / 147;
+        const int p = (kh + 1) >> 1, r = (kh + 1) & 1, q = (kw + 1) >> 1, s2 = (kw + 1) & 1;
+        const float g = __bfloat162float(dws[((o * 4 + p) * 4 + q) * 16 + (r * 2 + s2) * 3 + c]);
+        dw[t] = accumulate ? dw[t] + g : g;
+    }
+}
+
 static inline int grid_for(long long work) {
     long long g = (work + THREADS - 1) / THREADS;
     return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
@@ -162,6 +231,32 @@ extern "C" int v6_image_normalize(const void* img, void* out, long long N, long 
     const long long quads = N * HW / 4;
     image_normalize_kernel<<<grid_for(quads), THREADS, 0, s>>>((const unsigned char*)img, (__nv_bfloat16*)out, quads, HW, m0, m1, m2,
                                                                s0, s1, s2);
+    V6_CHECK_LAUNCH();
+    return 0;
+}
+
+// img: uint8 [N,3,H,W] (H, W even) -> out: bf16 [N, H/2+3, W/2+3, 16]
+extern "C" int v6_image_normalize_s2d(const void* img, void* out, int N, int H, int W, float m0, float m1, float m2, float s0,
+                                      float s1, float s2, cudaStream_t s) {
+    using namespace pool;
+    if ((H & 1) || (W & 1) || N < 1) return (int)cudaErrorInvalidValue;
+    image_normalize_s2d_kernel<<<grid_for((long long)N * (H / 2 + 3) * (W / 2 + 3)), THREADS, 0, s>>>(
+        (const unsigned char*)img, (__nv_bfloat16*)out, N, H, W, m0, m1, m2, s0, s1, s2);
+    V6_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int v6_stem_weight_s2d(const void* w, int w_is_bf16, void* ws, int O, cudaStream_t s) {
+    using namespace pool;
+    if (w_is_bf16) stem_weight_s2d_kernel<<<grid_for((long long)O * 256), THREADS, 0, s>>>((const __nv_bfloat16*)w, (__nv_bfloat16*)ws, O);
+    else stem_weight_s2d_kernel<<<grid_for((long long)O * 256), THREADS, 0, s>>>((const float*)w, (__nv_bfloat16*)ws, O);
+    V6_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int v6_stem_wgrad_d2s(const void* dws, float* dw, int O, int accumulate, cudaStream_t s) {
+    using namespace pool;
+    stem_wgrad_d2s_kernel<<<grid_for((long long)O * 147), THREADS, 0, s>>>((const __nv_bfloat16*)dws, dw, O, accumulate);
     V6_CHECK_LAUNCH();
     return 0;
 }

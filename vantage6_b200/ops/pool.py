@@ -67,3 +67,56 @@ def image_normalize(img: torch.Tensor, mean: Sequence[float], std: Sequence[floa
     m = torch.tensor(list(mean), device=img.device, dtype=torch.float32).view(1, 3, 1, 1)
     s = torch.tensor(list(std), device=img.device, dtype=torch.float32).view(1, 3, 1, 1)
     return ((img.float() - m) / s).contiguous(memory_format=torch.channels_last)
+
+
+class _StemS2DFn(torch.autograd.Function):
+    """7x7/s2/p3 stem convolution on 3 channels as a 4x4/s1 convolution on the 16-channel space-to-depth image
+    (csrc/pool.cu).  ``weight`` is the fp32 master filter ([O,3,7,7], channels-last memory), ``w_src`` the tensor the
+    filter values are read from (the bf16 shadow view when attached)."""
+
+    @staticmethod
+    def forward(ctx, xs, weight, w_src):
+        O = weight.shape[0]
+        ws = torch.empty((O, 16, 4, 4), device=xs.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+        src = weight.detach() if w_src is None else w_src
+        count(1)
+        native().stem_weight_s2d(src.data_ptr(), src.dtype == torch.bfloat16, ws.data_ptr(), O, stream_ptr())
+        y = torch.ops.aten.convolution(xs, ws, None, (1, 1), (0, 0), (1, 1), False, (0, 0), 1)
+        ctx.save_for_backward(xs, ws)
+        ctx.weight = weight
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, ws = ctx.saved_tensors
+        w = ctx.weight
+        _, dws, _ = torch.ops.aten.convolution_backward(dy, xs, ws, None, (1, 1), (0, 0), (1, 1), False, (0, 0), 1,
+                                                        (False, True, False))
+        if not dws.is_contiguous(memory_format=torch.channels_last):
+            dws = dws.contiguous(memory_format=torch.channels_last)
+        count(1)
+        g = w.grad
+        if g is not None and g.dtype == torch.float32 and g.is_contiguous(memory_format=torch.channels_last):
+            native().stem_wgrad_d2s(dws.data_ptr(), g.data_ptr(), w.shape[0], True, stream_ptr())     # straight into the flat grads
+            return None, None, None
+        dw = torch.empty(w.shape, device=w.device, dtype=torch.float32, memory_format=torch.channels_last)
+        native().stem_wgrad_d2s(dws.data_ptr(), dw.data_ptr(), w.shape[0], False, stream_ptr())
+        return None, dw, None
+
+
+def stem_s2d_supported(img: torch.Tensor, conv: nn.Conv2d) -> bool:
+    return (img.is_cuda and img.dtype == torch.uint8 and img.dim() == 4 and img.shape[1] == 3 and img.is_contiguous()
+            and img.shape[2] % 2 == 0 and img.shape[3] % 2 == 0 and tuple(conv.kernel_size) == (7, 7)
+            and tuple(conv.stride) == (2, 2) and tuple(conv.padding) == (3, 3) and conv.in_channels == 3
+            and conv.bias is None and conv.weight.dtype == torch.float32
+            and conv.weight.is_contiguous(memory_format=torch.channels_last))
+
+
+def stem_s2d(img: torch.Tensor, conv: nn.Conv2d, mean: Sequence[float], std: Sequence[float]) -> torch.Tensor:
+    """uint8 NCHW images -> stem convolution output (bf16, channels-last), see :class:`_StemS2DFn`."""
+    N, _, H, W = img.shape
+    xs = torch.empty((N, 16, H // 2 + 3, W // 2 + 3), device=img.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+    count(1)
+    native().image_normalize_s2d(img.data_ptr(), xs.data_ptr(), N, H, W, float(mean[0]), float(mean[1]), float(mean[2]),
+                                 1.0 / float(std[0]), 1.0 / float(std[1]), 1.0 / float(std[2]), stream_ptr())
+    return _StemS2DFn.apply(xs, conv.weight, getattr(conv, "w_bf16", None))
