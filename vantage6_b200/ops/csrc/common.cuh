@@ -215,6 +215,7 @@ V6_DEVINL void tma_store_2d(const void* tmap, const void* smem_src, int c0, int 
 V6_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 V6_DEVINL void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 V6_DEVINL void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+V6_DEVINL void tma_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }   // <= 1 store still reading
 V6_DEVINL void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(tmap) : "memory");
 }

@@ -18,7 +18,7 @@
 //   warp 1 : MMA issuer  (one elected lane)         UMMA 128x256x16, kind::f16, cta_group::1
 //   warp 2 : TMEM allocator (512 columns = 2 accumulator stages of 128x256 fp32)
 //   warp 3 : K1 write-back warp (TMA store of pulled weight tiles + ready flags)
-//   warps 4-7 : epilogue (tcgen05.ld 32x32b.x32 -> bias/act -> bf16 -> global)
+//   warps 4-7 : epilogue (tcgen05.ld 32x32b.x32 -> bias/act -> bf16 -> swizzled smem box -> TMA store)
 // Pipelines: full/empty mbarriers per smem stage; tmem_full/tmem_empty per accumulator stage,
 // so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
@@ -39,8 +39,11 @@ constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;      // 16 KB
 constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;      // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // 48 KB
 constexpr int PULL_OFF = kStagesK1 * STAGE_BYTES;   // K1 pull staging: 2 x 32 KB after the 3-stage ring
-constexpr int BAR_OFF = PULL_OFF + 2 * B_BYTES;     // 208 KB (>= 4 x 48 KB of the plain ring)
+constexpr int STG_OFF = PULL_OFF + 2 * B_BYTES;     // 208 KB (>= 4 x 48 KB of the plain ring): epilogue staging,
+constexpr int STG_WARP_BYTES = 32 * 128;            //   one 32-row x 64-col bf16 SWIZZLE_128B box (4 KB) per epilogue warp
+constexpr int BAR_OFF = STG_OFF + 4 * STG_WARP_BYTES;
 constexpr int SMEM_BYTES = BAR_OFF + 1024 /*align slack*/ + 256 /*barriers*/;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 constexpr int kThreads = 256;
 
 struct Params {
@@ -62,6 +65,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K]  box 128x64
                  const __grid_constant__ CUtensorMap tmap_b,        // B  [N,K]  box 256x64 (local copy)
                  const __grid_constant__ CUtensorMap tmap_b_src,    // B on the server GPU (peer VA); K1 only
+                 const __grid_constant__ CUtensorMap tmap_c,        // C  [M,N]  box 32x64 (epilogue TMA stores)
                  const Params P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -206,38 +210,50 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
             tile_coords(t, m_blk, n_blk);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tcgen05_fence_after();
-            const int row = m_blk * BLOCK_M + ew * 32 + lane;
+            // v2 epilogue: 64-column chunks go TMEM -> registers (bias / activation / bf16) -> a swizzled 4 KB
+            // staging box in shared memory -> ONE coalesced TMA store per chunk (v1 wrote 16 B per lane at a
+            // row stride: partial-sector writes, 77 us for a 200704x256x64 problem cuBLAS does in 26 us --
+            // profiles/conv1x1_bench_r1.json).  TMA clips rows >= M and columns >= N.
+            const int row0 = m_blk * BLOCK_M + ew * 32;
             const uint32_t t_row = tmem_base + acc * BLOCK_N + ((uint32_t)(ew * 32) << 16);
+            uint8_t* stg = smem + STG_OFF + ew * STG_WARP_BYTES;
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N; c += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(t_row + c, v);
+            for (int c = 0; c < BLOCK_N; c += 64) {
+                uint32_t v[2][32];
+                tmem_ld_32x32b_x32(t_row + c, v[0]);
+                tmem_ld_32x32b_x32(t_row + c + 32, v[1]);
                 tmem_ld_wait();
                 const int col0 = n_blk * BLOCK_N + c;
-                if (row < P.M && col0 < P.N) {
-                    float f[32];
+                if (row0 < P.M && col0 < P.N) {                       // warp-uniform
+                    uint32_t packed[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                    if (P.bias) {
+                    for (int h = 0; h < 2; ++h) {
+                        float f[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) if (col0 + j < P.N) f[j] += __ldg(P.bias + col0 + j);
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[h][j]);
+                        if (P.bias) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (col0 + h * 32 + j < P.N) f[j] += __ldg(P.bias + col0 + h * 32 + j);
+                        }
+                        if (P.act == 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                        } else if (P.act == 2) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) packed[h * 16 + j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
                     }
-                    if (P.act == 1) {
+                    if (lane == 0) tma_store_wait_read();             // previous chunk's store has read the staging box
+                    __syncwarp();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-                    } else if (P.act == 2) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-                    }
-                    __nv_bfloat16* dst = P.C + (size_t)row * P.ldc + col0;
-                    if (col0 + 32 <= P.N) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8)
-                            *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_bf16x2(f[j], f[j + 1]), pack_bf16x2(f[j + 2], f[j + 3]),
-                                                                            pack_bf16x2(f[j + 4], f[j + 5]), pack_bf16x2(f[j + 6], f[j + 7]));
-                    } else {
-                        for (int j = 0; j < 32 && col0 + j < P.N; ++j) dst[j] = __float2bfloat16(f[j]);
-                    }
+                    for (int j = 0; j < 8; ++j)                        // 16 B chunk j of row `lane`, SWIZZLE_128B position
+                        *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                            make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) { tma_store_2d(&tmap_c, stg, col0, row0); tma_store_commit(); }
                 }
             }
             tcgen05_fence_before();
@@ -245,6 +261,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
+        if (lane == 0) tma_store_wait_all();                          // staging must outlive the last store
     }
 
     tcgen05_fence_before();
@@ -265,6 +282,8 @@ static int launch_gemm(const void* A, const void* B, const void* B_src, void* C,
     if (v6_make_tmap_2d_bf16(&tb, (uint64_t)B, N, K, (uint64_t)ldb * 2, BLOCK_N, BLOCK_K, 1)) return -2;
     if (B_src) { if (v6_make_tmap_2d_bf16(&tbs, (uint64_t)B_src, N, K, (uint64_t)ldb * 2, BLOCK_N, BLOCK_K, 1)) return -2; }
     else tbs = tb;
+    alignas(64) CUtensorMap tc;
+    if (v6_make_tmap_2d_bf16(&tc, (uint64_t)C, M, N, (uint64_t)ldc * 2, 32, 64, 1)) return -2;
     Params P;
     P.M = M; P.N = N; P.K = K; P.C = (__nv_bfloat16*)C; P.ldc = ldc; P.bias = bias; P.act = act;
     P.fused_bcast = B_src ? 1 : 0; P.ready_flags = ready_flags; P.epoch = epoch;
@@ -278,7 +297,7 @@ static int launch_gemm(const void* A, const void* B, const void* B_src, void* C,
     const int num_tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
     int sms = max_ctas > 0 ? max_ctas : 148;
     const int grid = num_tiles < sms ? num_tiles : sms;
-    gemm_bf16_kernel<<<grid, kThreads, SMEM_BYTES, stream>>>(ta, tb, tbs, P);
+    gemm_bf16_kernel<<<grid, kThreads, SMEM_BYTES, stream>>>(ta, tb, tbs, tc, P);
     V6_CHECK_LAUNCH();
     return 0;
 }

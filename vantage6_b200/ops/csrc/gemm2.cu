@@ -27,8 +27,11 @@ constexpr int kTmemCols = 512;
 constexpr int A_BYTES = HALF_M * BLOCK_K * 2;        // 16 KB
 constexpr int B_BYTES = HALF_N * BLOCK_K * 2;        // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // 32 KB per CTA
-constexpr int BAR_OFF = kStages * STAGE_BYTES;       // 192 KB
+constexpr int STG_OFF = kStages * STAGE_BYTES;       // 192 KB: epilogue staging, 2 x (32 rows x 64 cols bf16, SWIZZLE_128B) per warp
+constexpr int STG_BOX_BYTES = 32 * 128;
+constexpr int BAR_OFF = STG_OFF + 4 * 2 * STG_BOX_BYTES;     // 224 KB
 constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 constexpr int kThreads = 256;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;       // clears the CTA-rank bit of a shared::cluster address
 
@@ -85,6 +88,7 @@ V6_DEVINL void umma_commit_2sm(uint64_t* bar) {       // arrive on the same-offs
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,     // A [M,K] box 128 x 64
                   const __grid_constant__ CUtensorMap tmap_b,     // B [N,K] box 128 x 64
+                  const __grid_constant__ CUtensorMap tmap_c,     // C [M,N] box 32 x 64 (epilogue TMA stores)
                   const Params P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -170,43 +174,55 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,     // A [M,K] box
         // ============================ epilogue (both CTAs, own 128 rows) ============================
         const int ew = warp - 4;
         int acc = 0; uint32_t acc_phase = 0;
+        int stg_slot = 0;
         for (int t = pair; t < num_tiles; t += num_pairs) {
             int m_blk, n_blk;
             tile_coords(t, m_blk, n_blk);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tcgen05_fence_after();
-            const int row = m_blk * TILE_M + (int)rank * HALF_M + ew * 32 + lane;
+            // 64-column chunks: TMEM -> registers (bias / activation / bf16) -> swizzled 4 KB staging box (two per
+            // warp, ping-pong) -> one coalesced TMA store per chunk; TMA clips rows >= M and columns >= N.
+            const int row0 = m_blk * TILE_M + (int)rank * HALF_M + ew * 32;
             const uint32_t t_row = tmem_base + acc * TILE_N + ((uint32_t)(ew * 32) << 16);
 #pragma unroll 1
-            for (int c = 0; c < TILE_N; c += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(t_row + c, v);
+            for (int c = 0; c < TILE_N; c += 64) {
+                uint32_t v[2][32];
+                tmem_ld_32x32b_x32(t_row + c, v[0]);
+                tmem_ld_32x32b_x32(t_row + c + 32, v[1]);
                 tmem_ld_wait();
                 const int col0 = n_blk * TILE_N + c;
-                if (row < P.M && col0 < P.N) {
-                    float f[32];
+                if (row0 < P.M && col0 < P.N) {                       // warp-uniform
+                    uint32_t packed[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                    if (P.bias) {
+                    for (int h = 0; h < 2; ++h) {
+                        float f[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) if (col0 + j < P.N) f[j] += __ldg(P.bias + col0 + j);
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[h][j]);
+                        if (P.bias) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (col0 + h * 32 + j < P.N) f[j] += __ldg(P.bias + col0 + h * 32 + j);
+                        }
+                        if (P.act == 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                        } else if (P.act == 2) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) packed[h * 16 + j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
                     }
-                    if (P.act == 1) {
+                    uint8_t* stg = smem + STG_OFF + (ew * 2 + stg_slot) * STG_BOX_BYTES;
+                    if (lane == 0) tma_store_wait_read_1();           // the store issued two chunks ago has read this box
+                    __syncwarp();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-                    } else if (P.act == 2) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-                    }
-                    __nv_bfloat16* dst = P.C + (size_t)row * P.ldc + col0;
-                    if (col0 + 32 <= P.N) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8)
-                            *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_bf16x2(f[j], f[j + 1]), pack_bf16x2(f[j + 2], f[j + 3]),
-                                                                            pack_bf16x2(f[j + 4], f[j + 5]), pack_bf16x2(f[j + 6], f[j + 7]));
-                    } else {
-                        for (int j = 0; j < 32 && col0 + j < P.N; ++j) dst[j] = __float2bfloat16(f[j]);
-                    }
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                            make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) { tma_store_2d(&tmap_c, stg, col0, row0); tma_store_commit(); }
+                    stg_slot ^= 1;
                 }
             }
             tcgen05_fence_before();
@@ -214,6 +230,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,     // A [M,K] box
             if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&tempty_bar[acc]), 0));     // leader's barrier
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
+        if (lane == 0) tma_store_wait_all();                          // staging must outlive the last store
     }
 
     tcgen05_fence_before();
@@ -231,6 +248,8 @@ extern "C" int v6_gemm2_bf16(const void* A, const void* B, void* C, const float*
     alignas(64) CUtensorMap ta, tb;
     if (v6_make_tmap_2d_bf16(&ta, (uint64_t)A, M, K, (uint64_t)lda * 2, HALF_M, BLOCK_K, 1)) return -2;
     if (v6_make_tmap_2d_bf16(&tb, (uint64_t)B, N, K, (uint64_t)ldb * 2, HALF_N, BLOCK_K, 1)) return -2;
+    alignas(64) CUtensorMap tc;
+    if (v6_make_tmap_2d_bf16(&tc, (uint64_t)C, M, N, (uint64_t)ldc * 2, 32, 64, 1)) return -2;
     Params P;
     P.M = M; P.N = N; P.K = K; P.C = (__nv_bfloat16*)C; P.ldc = ldc; P.bias = bias; P.act = act;
     static bool attr_set = false;
@@ -241,7 +260,7 @@ extern "C" int v6_gemm2_bf16(const void* A, const void* B, void* C, const float*
     }
     const int num_tiles = ((M + TILE_M - 1) / TILE_M) * ((N + TILE_N - 1) / TILE_N);
     int pairs = num_tiles < 74 ? num_tiles : 74;
-    gemm2_bf16_kernel<<<pairs * 2, kThreads, SMEM_BYTES, stream>>>(ta, tb, P);
+    gemm2_bf16_kernel<<<pairs * 2, kThreads, SMEM_BYTES, stream>>>(ta, tb, tc, P);
     V6_CHECK_LAUNCH();
     return 0;
 }
