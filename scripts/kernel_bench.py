@@ -179,8 +179,13 @@ def main():
             k = torch.randn(B, S, Hkv, D, device=dev, dtype=torch.bfloat16)
             v = torch.randn(B, S, Hkv, D, device=dev, dtype=torch.bfloat16)
             fl = 4.0 * B * Hq * S * S * D * (0.5 if causal else 1.0)
-            ms = timeit(lambda: A.flash_attn_fwd(q, k, v, causal), flush=False)
+            ms = timeit(lambda: A.flash_attn_fwd(q, k, v, causal, variant="1cta"), flush=False)
             row = {"B": B, "S": S, "Hq": Hq, "Hkv": Hkv, "D": D, "causal": causal, "fwd_ms": ms, "fwd_tflops": fl / ms / 1e9}
+            try:
+                ms2 = timeit(lambda: A.flash_attn_fwd(q, k, v, causal, variant="2cta"), flush=False)
+                row.update(fwd2_ms=ms2, fwd2_tflops=fl / ms2 / 1e9)
+            except Exception as e:  # noqa: BLE001
+                row["fwd2_error"] = repr(e)[:100]
             try:
                 from flash_attn import flash_attn_func
 

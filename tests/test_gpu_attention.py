@@ -23,14 +23,15 @@ def dev():
     (1, 200, 2, 2, 64, True),         # S not a multiple of 128
     (1, 2048, 32, 8, 128, True),
 ])
-def test_flash_attention_forward(dev, B, S, Hq, Hkv, D, causal):
+@pytest.mark.parametrize("variant", ["1cta", "2cta"])
+def test_flash_attention_forward(dev, B, S, Hq, Hkv, D, causal, variant):
     from vantage6_b200.ops import attention as A
 
     torch.manual_seed(0)
     q = torch.randn(B, S, Hq, D, device=dev, dtype=torch.bfloat16)
     k = torch.randn(B, S, Hkv, D, device=dev, dtype=torch.bfloat16)
     v = torch.randn(B, S, Hkv, D, device=dev, dtype=torch.bfloat16)
-    o, lse = A.flash_attn_fwd(q, k, v, causal)
+    o, lse = A.flash_attn_fwd(q, k, v, causal, variant=variant)
     torch.cuda.synchronize()
     ro, rlse = A.reference_attention(q, k, v, causal)
     err = (o.float() - ro).abs().max().item()
@@ -38,7 +39,8 @@ def test_flash_attention_forward(dev, B, S, Hq, Hkv, D, causal):
     torch.testing.assert_close(lse, rlse, rtol=1e-3, atol=2e-3)
 
 
-def test_flash_attention_large_logits_trigger_rescale(dev):
+@pytest.mark.parametrize("variant", ["1cta", "2cta"])
+def test_flash_attention_large_logits_trigger_rescale(dev, variant):
     """Scores grow along the key axis so the running max is raised repeatedly (lazy-rescale path)."""
     from vantage6_b200.ops import attention as A
 
@@ -49,7 +51,7 @@ def test_flash_attention_large_logits_trigger_rescale(dev):
     ramp = torch.linspace(0.5, 6.0, S, device=dev)[None, :, None, None]
     k = (k * ramp).to(torch.bfloat16)
     v = torch.randn(B, S, H, D, device=dev, dtype=torch.bfloat16)
-    o, lse = A.flash_attn_fwd(q, k, v, False)
+    o, lse = A.flash_attn_fwd(q, k, v, False, variant=variant)
     ro, rlse = A.reference_attention(q, k, v, False)
     assert (o.float() - ro).abs().max().item() < 5e-2
     torch.testing.assert_close(lse, rlse, rtol=1e-3, atol=5e-3)

@@ -1,6 +1,8 @@
-"""K4: flash attention.  Forward = the hand-written tcgen05/TMEM/TMA kernel (csrc/attention.cu);
-backward = the flash-attn library kernel fed with our output and log-sum-exp (a hand-written
-tcgen05 backward is the next step; the library backward plays the role cuBLAS plays for dX/dW).
+"""K4: flash attention.  Forward = hand-written tcgen05/TMEM/TMA kernels: ``csrc/attention.cu`` (one 128-query
+tile per SM, intra-CTA pipeline) and ``csrc/attention2.cu`` (two co-resident CTAs per SM, P aliased over S in
+TMEM); ``V6B200_ATTN_FWD=1cta|2cta`` or the ``variant`` argument selects one.  Backward = the flash-attn library
+kernel fed with our output and log-sum-exp by default (it plays the role cuBLAS plays for dX/dW), or the
+hand-written transpose-free tcgen05 backward (``csrc/attention_bwd.cu``, ``V6B200_ATTN_BWD=native``).
 
 q:[B,S,Hq,D]  k,v:[B,S,Hkv,D]  bf16, D in {64,128}, GQA allowed -> o:[B,S,Hq,D].
 """
@@ -27,7 +29,16 @@ def _supported(q: torch.Tensor, k: torch.Tensor) -> bool:
     return q.dtype == torch.bfloat16 and D in (64, 128) and S % 8 == 0 and q.shape[2] % k.shape[2] == 0
 
 
-def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool, scale: float | None = None):
+def _fwd_variant(variant: str | None) -> str:
+    v = variant or os.environ.get("V6B200_ATTN_FWD", _DEFAULT_FWD)
+    return v if v in ("1cta", "2cta") and (v == "1cta" or hasattr(native(), "flash_attn_fwd2")) else "1cta"
+
+
+_DEFAULT_FWD = "1cta"
+
+
+def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool, scale: float | None = None,
+                   variant: str | None = None):
     """Raw forward: returns (o, lse).  V is transposed to [B,Hkv,D,S] so the PV operand is K-major."""
     B, S, Hq, D = q.shape
     Hkv = k.shape[2]
@@ -36,8 +47,9 @@ def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
     vt = v.permute(0, 2, 3, 1).contiguous()
     o = torch.empty_like(q)
     lse = torch.empty(B, Hq, S, device=q.device, dtype=torch.float32)
-    native().flash_attn_fwd(q.data_ptr(), k.data_ptr(), vt.data_ptr(), o.data_ptr(), lse.data_ptr(), B, S, Hq, Hkv, D,
-                            float(scale), bool(causal), stream_ptr())
+    fn = native().flash_attn_fwd2 if _fwd_variant(variant) == "2cta" else native().flash_attn_fwd
+    fn(q.data_ptr(), k.data_ptr(), vt.data_ptr(), o.data_ptr(), lse.data_ptr(), B, S, Hq, Hkv, D, float(scale), bool(causal),
+       stream_ptr())
     return o, lse
 
 
