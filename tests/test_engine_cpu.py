@@ -222,3 +222,72 @@ def test_zoo_models_train_on_cpu(name):
     if name == "llama_tiny_lora":           # only the adapters are federated
         names = [s.name for s in tr.fm.segments]
         assert names and all("lora_" in n for n in names)
+
+
+def test_flat_model_keeps_channels_last_filters_and_gradient_sink():
+    """Conv filters live [O,H,W,I] inside the flat buffers (no per-step layout conversion); the gradient sink adds
+    bf16 filter gradients into the flat fp32 gradient buffer in memory order."""
+    import torch
+    from torch import nn
+
+    from vantage6_b200.models.flat import FlatModel
+    from vantage6_b200.ops.optim import multi_accumulate
+
+    torch.manual_seed(0)
+    m = nn.Sequential(nn.Conv2d(3, 8, 3, bias=False), nn.Conv2d(8, 4, 1, bias=False)).to(memory_format=torch.channels_last)
+    ref = [p.detach().clone() for p in m.parameters()]
+    fm = FlatModel(m)
+    seg3, seg1 = fm.segment("0.weight"), fm.segment("1.weight")
+    assert seg3.channels_last and not seg1.channels_last           # 1x1 filters: both layouts coincide
+    for p, r in zip(m.parameters(), ref):
+        assert torch.equal(p, r)
+    w = m[0].weight
+    assert w.is_contiguous(memory_format=torch.channels_last) and not w.is_contiguous()
+    flat = fm.flat[seg3.offset: seg3.offset + seg3.numel]
+    assert torch.equal(flat.view(8, 3, 3, 3), ref[0].permute(0, 2, 3, 1))     # stored O,H,W,I
+    assert m[0].weight.grad.is_contiguous(memory_format=torch.channels_last)
+    # gradient sink (CPU fallback of the multi-tensor kernel)
+    g3 = torch.randn(8, 3, 3, 3).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    g1 = torch.randn(4, 8, 1, 1).to(torch.bfloat16)
+    fm.grad_sink.extend([(g3, seg3.offset), (g1, seg1.offset)])
+    assert fm.flush_grad_sink() == 2 and not fm.grad_sink
+    torch.testing.assert_close(m[0].weight.grad, g3.float())
+    torch.testing.assert_close(m[1].weight.grad, g1.float())
+    fm.grad_sink.append((g3, seg3.offset))
+    fm.flush_grad_sink()
+    torch.testing.assert_close(m[0].weight.grad, 2 * g3.float())
+    dst = torch.zeros(64)
+    multi_accumulate(dst, [(torch.ones(5, dtype=torch.bfloat16), 8)])
+    assert dst[8:13].sum() == 5 and dst.sum() == 5
+
+
+def test_shadow_conv_falls_back_to_plain_conv_without_shadow():
+    import torch
+
+    from vantage6_b200.models.conv import ShadowConv2d
+
+    torch.manual_seed(1)
+    c = ShadowConv2d(4, 6, 3, padding=1, bias=False)
+    x = torch.randn(2, 4, 5, 5, requires_grad=True)
+    y = c(x)
+    ref = torch.nn.functional.conv2d(x, c.weight, None, 1, 1)
+    torch.testing.assert_close(y, ref)
+    y.sum().backward()
+    assert c.weight.grad is not None and x.grad is not None
+
+
+def test_resnet_stem_paths_agree_on_cpu():
+    """uint8 input (normalised inside the model) == pre-normalised float input."""
+    import torch
+
+    from vantage6_b200.models.resnet import _MEAN, _STD, resnet_tiny
+
+    torch.manual_seed(2)
+    m = resnet_tiny(10).eval()
+    img = torch.randint(0, 256, (2, 3, 32, 32), dtype=torch.uint8)
+    mean = torch.tensor(_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(_STD).view(1, 3, 1, 1)
+    with torch.no_grad():
+        a = m(img)
+        b = m((img.float() - mean) / std)
+    torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-4)
