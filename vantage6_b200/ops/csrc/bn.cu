@@ -21,6 +21,13 @@ namespace bn {
 
 constexpr int THREADS = 256;
 
+// Programmatic dependent launch (PDL): the element-wise pass of a BN layer is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs are scheduled while the reduction kernel's tree
+// tail is still running and block in griddepcontrol.wait until that grid has completed and flushed its writes.
+// Without the attribute both instructions are no-ops.
+V6_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+V6_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 V6_DEVINL void load8(const __nv_bfloat16* p, float (&v)[8]) {
     uint4 t = *reinterpret_cast<const uint4*>(p);
     float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
@@ -186,6 +193,7 @@ __global__ void __launch_bounds__(THREADS, 4) bn_stats_kernel(const __nv_bfloat1
         for (int u = 0; u < STATS_UNROLL; ++u) acc_stats(raw[u], shift, s1, s2);
     }
     for (; r < R; r += G) acc_stats(ldg_nc_v4(xc + r * C), shift, s1, s2);
+    pdl_launch_dependents();                                   // let the apply kernel's CTAs get scheduled
     if (!slice_reduce(s1, s2, rd, SW, tot)) return;
     if (threadIdx.x < SW) {
         const int c = blockIdx.y * SW + threadIdx.x;
@@ -216,6 +224,7 @@ __global__ void __launch_bounds__(THREADS) bn_apply_kernel(const __nv_bfloat16* 
                                                            long long R, int C) {
     const int CG = C >> 3, RL = THREADS / CG;
     const int cg = threadIdx.x % CG, rl = threadIdx.x / CG;
+    pdl_wait();                                                 // scale / bias come from the stats kernel
     float sc[8], bi[8];
     loadf8(scale + cg * 8, sc);
     loadf8(bias + cg * 8, bi);
@@ -304,6 +313,7 @@ __global__ void __launch_bounds__(THREADS, 3) bn_bwd_reduce_kernel(const __nv_bf
         if (RELU) mb = __ldg(mask + r * CGT + cgt);
         acc_bwd<RELU>(ldg_nc_v4(dy + o), ldg_nc_v4(x + o), mb, mu, rs, sg, sgx);
     }
+    pdl_launch_dependents();
     if (!slice_reduce(sg, sgx, rd, SW, tot)) return;
     if (threadIdx.x < SW) {
         const int c = blockIdx.y * SW + threadIdx.x;
@@ -326,6 +336,7 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const __nv_bfloat
                                                                long long R, int C) {
     const int CG = C >> 3, RL = THREADS / CG;
     const int cg = threadIdx.x % CG, rl = threadIdx.x / CG;
+    pdl_wait();                                                 // coefficients come from the reduce kernel
     float c0[8], c1[8], c2[8];
     loadf8(coef + cg * 8, c0);
     loadf8(coef + C + cg * 8, c1);
@@ -393,6 +404,22 @@ static inline int apply_grid(long long R, int C) {
     return (int)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
 }
 
+// launch `kernel` as a programmatic dependent of the previous kernel in the stream (V6B200_PDL=0: plain launch)
+template <typename... KArgs, typename... Args>
+static void launch_dependent(void (*kernel)(KArgs...), int grid, cudaStream_t s, Args... args) {
+    static const bool pdl = [] { const char* e = getenv("V6B200_PDL"); return !(e && e[0] == '0'); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(THREADS);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace bn
 
 // scratch: v6_bn_scratch_floats() floats, zero-initialised once (partials + self-resetting counters), shared by
@@ -415,11 +442,11 @@ extern "C" int v6_bn_fwd(const void* x, const void* res, const float* gamma, con
     __nv_bfloat16* yy = (__nv_bfloat16*)y;
     if (relu) {
         unsigned char* mk = (unsigned char*)relu_mask;
-        if (res) bn_apply_kernel<true, true><<<ag, THREADS, 0, s>>>(xx, rr, scale_bias, scale_bias + C, yy, mk, R, C);
-        else bn_apply_kernel<true, false><<<ag, THREADS, 0, s>>>(xx, rr, scale_bias, scale_bias + C, yy, mk, R, C);
+        if (res) launch_dependent(bn_apply_kernel<true, true>, ag, s, xx, rr, scale_bias, scale_bias + C, yy, mk, R, C);
+        else launch_dependent(bn_apply_kernel<true, false>, ag, s, xx, rr, scale_bias, scale_bias + C, yy, mk, R, C);
     } else {
-        if (res) bn_apply_kernel<false, true><<<ag, THREADS, 0, s>>>(xx, rr, scale_bias, scale_bias + C, yy, nullptr, R, C);
-        else bn_apply_kernel<false, false><<<ag, THREADS, 0, s>>>(xx, rr, scale_bias, scale_bias + C, yy, nullptr, R, C);
+        if (res) launch_dependent(bn_apply_kernel<false, true>, ag, s, xx, rr, scale_bias, scale_bias + C, yy, nullptr, R, C);
+        else launch_dependent(bn_apply_kernel<false, false>, ag, s, xx, rr, scale_bias, scale_bias + C, yy, nullptr, R, C);
     }
     V6_CHECK_LAUNCH();
     return 0;
@@ -463,11 +490,11 @@ extern "C" int v6_bn_bwd(const void* dy, const void* relu_mask, const void* x, c
     __nv_bfloat16* dxx = (__nv_bfloat16*)dx;
     __nv_bfloat16* drr = (__nv_bfloat16*)dres;
     if (relu) {
-        if (dres) bn_bwd_apply_kernel<true, true><<<ag, THREADS, 0, s>>>(dyy, yy, xx, coef, dxx, drr, R, C);
-        else bn_bwd_apply_kernel<true, false><<<ag, THREADS, 0, s>>>(dyy, yy, xx, coef, dxx, drr, R, C);
+        if (dres) launch_dependent(bn_bwd_apply_kernel<true, true>, ag, s, dyy, yy, xx, coef, dxx, drr, R, C);
+        else launch_dependent(bn_bwd_apply_kernel<true, false>, ag, s, dyy, yy, xx, coef, dxx, drr, R, C);
     } else {
-        if (dres) bn_bwd_apply_kernel<false, true><<<ag, THREADS, 0, s>>>(dyy, yy, xx, coef, dxx, drr, R, C);
-        else bn_bwd_apply_kernel<false, false><<<ag, THREADS, 0, s>>>(dyy, yy, xx, coef, dxx, drr, R, C);
+        if (dres) launch_dependent(bn_bwd_apply_kernel<false, true>, ag, s, dyy, yy, xx, coef, dxx, drr, R, C);
+        else launch_dependent(bn_bwd_apply_kernel<false, false>, ag, s, dyy, yy, xx, coef, dxx, drr, R, C);
     }
     V6_CHECK_LAUNCH();
     return 0;
