@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "nccl"])
     ap.add_argument("--rounds", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--no-graph", action="store_true", help="eager local steps (for ncu launch lists)")
     ap.add_argument("--local-steps", type=int, default=None)
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--seq", type=int, default=None)
@@ -86,7 +87,7 @@ def main():
         over = {}
         tr, spec = zoo.build_trainer(args.model, rank=rank, world=world, device=dev, server_mode=args.server_mode,
                                      data_plane="native" if b200 else "collective", fused_local_optimizer=b200,
-                                     use_cuda_graph=None if b200 else False, **over)
+                                     use_cuda_graph=(False if args.no_graph else None) if b200 else False, **over)
         n_steps = args.local_steps or spec.local_steps
         bsz = args.batch or spec.batch
         batches = [(x.to(dev), y.to(dev)) for x, y in spec.make_batches(n_steps, bsz, seed=500 + rank)]
@@ -99,6 +100,12 @@ def main():
         for _ in range(args.rounds):
             loss = tr.run_round(batches)
         ms = max_over_ranks(t.stop(), dev)
+        if os.environ.get("V6_PROFILE_RANGE"):      # ncu --profile-from-start off: one more round, every thread's launches
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            tr.run_round(batches)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
         # aggregation-only time (the communication-bound part)
         barrier_sync(dev)
         t.start()

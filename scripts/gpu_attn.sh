@@ -16,3 +16,11 @@ rm -f gpurun_out/models_1b.jsonl
 for m in bert_base llama3_8b_lora; do
   echo "== model $m b200"; timeout 600 python scripts/bench_models.py --model $m --impl b200 --rounds 5 --warmup 3 --out gpurun_out/models_1b.jsonl 2> gpurun_out/model_${m}_b200.err | cut -c1-400; tail -2 gpurun_out/model_${m}_b200.err | cut -c1-300
 done
+echo "== pytest bn/resnet (PDL launches)"; timeout 900 python -m pytest tests/test_gpu_bn.py tests/test_gpu_resnet_ops.py -m gpu -q --timeout 300 > gpurun_out/pytest_bn.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/pytest_bn.log | cut -c1-300
+for pdl in 1 0; do
+  echo "== bench b200 PDL=$pdl"; V6B200_PDL=$pdl timeout 600 python bench.py --steps 6 --warmup 3 --impl b200 > gpurun_out/bench_b200_pdl$pdl.json 2> gpurun_out/bench_b200_pdl$pdl.err; echo "rc=$?"; tail -2 gpurun_out/bench_b200_pdl$pdl.err | cut -c1-300; cut -c1-330 gpurun_out/bench_b200_pdl$pdl.json
+done
+echo "== launch list bert_base (one eager round)"
+V6_PROFILE_RANGE=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 6000 --csv \
+  --log-file gpurun_out/launches_bert.csv python scripts/bench_models.py --model bert_base --impl b200 --rounds 1 --warmup 2 --no-graph > gpurun_out/ncu_launch_bert.log 2>&1; echo "rc=$?"
+python scripts/launch_summary.py gpurun_out/launches_bert.csv gpurun_out/launches_bert_summary.txt | head -32
