@@ -24,3 +24,4 @@ echo "== launch list bert_base (one eager round)"
 V6_PROFILE_RANGE=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 6000 --csv \
   --log-file gpurun_out/launches_bert.csv python scripts/bench_models.py --model bert_base --impl b200 --rounds 1 --warmup 2 --no-graph > gpurun_out/ncu_launch_bert.log 2>&1; echo "rc=$?"
 python scripts/launch_summary.py gpurun_out/launches_bert.csv gpurun_out/launches_bert_summary.txt | head -32
+echo "== glm test + bench"; timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "glm" 2>&1 | tail -2; timeout 300 python scripts/kernel_bench.py --only glm 2>&1 | grep "rows" | cut -c1-300
