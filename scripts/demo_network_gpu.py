@@ -45,7 +45,8 @@ def main():
             if out is None:
                 print(res[0]["log"])
                 raise SystemExit(1)
-            out = {k: v for k, v in out.items() if k not in ("coef", "weights")}
+            out = {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in out.items() if k not in ("coef", "weights", "w")}
+            out = {k: v for k, v in out.items() if not (isinstance(v, list) and len(v) > 64)}
             out.update({"image": image, "nodes": args.nodes, "task_wall_s": round(time.time() - t0, 2)})
             lines.append(out)
             print(json.dumps(out), flush=True)
