@@ -34,7 +34,7 @@ def _fwd_variant(variant: str | None) -> str:
     return v if v in ("1cta", "2cta") and (v == "1cta" or hasattr(native(), "flash_attn_fwd2")) else "1cta"
 
 
-_DEFAULT_FWD = "1cta"
+_DEFAULT_FWD = "2cta"      # measured: 1.1-1.7x the 1-CTA design and 1.17-1.74x flash-attn 2 (profiles/kernel_bench_attn_r1c.json)
 
 
 def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool, scale: float | None = None,
