@@ -1,0 +1,89 @@
+"""Fused bias / activation backward (csrc/act.cu), LayerNorm parameter-gradient fold + in-place accumulation, and the
+ShadowLinear gradient-sink path against plain PyTorch references."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from vantage6_b200.ops import native
+
+    native()
+    torch.cuda.set_device(0)
+    return torch.device("cuda", 0)
+
+
+@pytest.mark.parametrize("R,C", [(4096, 3072), (4096, 768), (1000, 2304), (37, 64), (20000, 128)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+@pytest.mark.parametrize("direct", [False, True])
+def test_bias_act_backward(dev, R, C, act, direct):
+    from vantage6_b200.ops import gemm as G
+
+    torch.manual_seed(0)
+    dy = torch.randn(R, C, device=dev).to(torch.bfloat16)
+    pre = (torch.randn(R, C, device=dev) * 1.5).to(torch.bfloat16)
+    bias = torch.nn.Parameter(torch.zeros(C, device=dev))
+    if direct:
+        bias.grad = torch.full((C,), 0.5, device=dev)
+    for rep in range(2):                                   # second call: arrival counters must have reset
+        dpre, db = G.bias_act_backward(dy, pre if act else None, act, bias)
+    p = pre.float()
+    if act == 1:
+        g = dy.float() * (0.5 * (1 + torch.erf(p * 0.7071067811865476)) + p * torch.exp(-0.5 * p * p) * 0.3989422804014327)
+    elif act == 2:
+        g = dy.float() * (p > 0)
+    else:
+        g = dy.float()
+    torch.testing.assert_close(dpre.float(), g.to(torch.bfloat16).float(), rtol=2e-2, atol=2e-2)
+    ref_db = g.sum(0)
+    tol = 2e-2 * max(1.0, ref_db.abs().max().item())
+    if direct:
+        assert db is None
+        assert (bias.grad - (0.5 + 2 * ref_db)).abs().max().item() < 2 * tol
+    else:
+        assert (db - ref_db).abs().max().item() < tol
+
+
+def test_layernorm_accumulates_param_grads_in_place(dev):
+    from vantage6_b200.ops import norm as N
+
+    torch.manual_seed(1)
+    rows, cols = 4096, 768
+    x = torch.randn(rows, cols, device=dev).to(torch.bfloat16).requires_grad_()
+    g = torch.nn.Parameter(torch.rand(cols, device=dev) + 0.5)
+    b = torch.nn.Parameter(torch.randn(cols, device=dev) * 0.1)
+    dy = torch.randn(rows, cols, device=dev).to(torch.bfloat16)
+    y, _ = N.layer_norm(x, g, b, 1e-5)
+    y.backward(dy)
+    ref_g, ref_b = g.grad.clone(), b.grad.clone()                 # first backward: grads returned to autograd
+    xf = x.detach().float().requires_grad_()
+    gr = g.detach().clone().requires_grad_()
+    br = b.detach().clone().requires_grad_()
+    torch.nn.functional.layer_norm(xf, (cols,), gr, br, 1e-5).backward(dy.float())
+    assert (ref_g - gr.grad).abs().max().item() < 3e-2 * gr.grad.abs().max().item()
+    assert (ref_b - br.grad).abs().max().item() < 3e-2 * br.grad.abs().max().item()
+    y2, _ = N.layer_norm(x, g, b, 1e-5)                           # .grad exists now: accumulated in place by the kernel
+    y2.backward(dy)
+    torch.testing.assert_close(g.grad, 2 * ref_g, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(b.grad, 2 * ref_b, rtol=1e-4, atol=1e-3)
+
+
+def test_bert_tiny_fused_arm_matches_stock_arm(dev):
+    """ShadowLinear with gradient sink + fused bias/GELU backward + in-place LN grads vs the stock-optimizer arm."""
+    from vantage6_b200.models import zoo
+
+    def run(fused):
+        torch.manual_seed(21)
+        tr, spec = zoo.build_trainer("bert_tiny", rank=0, world=1, device=dev, data_plane="auto" if fused else "collective",
+                                     fused_local_optimizer=fused, use_cuda_graph=fused)
+        batches = [(x.to(dev), y.to(dev)) for x, y in spec.make_batches(2, 4, 77)]
+        tr.initialize_global()
+        losses = [float(tr.run_round(batches).item()) for _ in range(5)]
+        tr.close()
+        return losses
+
+    a, b = run(True), run(False)
+    assert abs(a[0] - b[0]) < 0.05, (a, b)
+    assert a[-1] < a[0] and abs(a[-1] - b[-1]) < 0.3, (a, b)

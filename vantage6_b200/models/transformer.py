@@ -8,7 +8,9 @@ Parameter policy (mixed precision without autocast):
 * activations are bf16; norms read fp32 gamma/beta directly from the master buffer.
 
 ``ShadowLinear`` runs its forward on the tcgen05 GEMM (ops/gemm.py); backward GEMMs (dX, dW) are
-plain library GEMMs (cuBLAS) and dW is emitted in fp32 straight into the flat gradient buffer.
+plain library GEMMs (cuBLAS); the activation derivative + bias gradient is one hand-written kernel
+(csrc/act.cu) and the bf16 dW of every layer is added into the flat fp32 gradient buffer by the
+multi-tensor gradient sink (one launch per step).
 """
 from __future__ import annotations
 
@@ -34,7 +36,7 @@ def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 class _ShadowLinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, w_bf16, act):
+    def forward(ctx, x, weight, bias, w_bf16, act, sink, offset):
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
@@ -49,25 +51,28 @@ class _ShadowLinearFn(torch.autograd.Function):
         elif act == G.ACT_RELU:
             y = torch.relu(pre)
         ctx.save_for_backward(x2, wb, pre if act != G.ACT_NONE else None)
-        ctx.act, ctx.has_bias, ctx.xshape = act, bias is not None, x.shape
+        ctx.act, ctx.xshape = act, x.shape
         ctx.need_w = weight.requires_grad
+        ctx.bias = bias                           # the Parameter itself: its .grad may be a flat-buffer view
+        ctx.sink, ctx.offset = sink, offset
         return y.view(*x.shape[:-1], wb.shape[0])
 
     @staticmethod
     def backward(ctx, dy):
         x2, wb, pre = ctx.saved_tensors
         dy2 = dy.reshape(-1, dy.shape[-1])
-        if ctx.act == G.ACT_GELU:
-            p = pre.float()
-            dy2 = (dy2.float() * (0.5 * (1.0 + torch.erf(p * 0.7071067811865476))
-                                  + p * torch.exp(-0.5 * p * p) * 0.3989422804014327)).to(dy.dtype)
-        elif ctx.act == G.ACT_RELU:
-            dy2 = dy2 * (pre > 0)
-        dy2 = dy2.contiguous()
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        # one kernel: activation derivative, bf16 dpre, bias gradient (accumulated in place when possible)
+        dy2, db = G.bias_act_backward(dy2, pre, ctx.act, ctx.bias)
         dx = torch.mm(dy2, wb).view(ctx.xshape) if ctx.needs_input_grad[0] else None
-        dw = _mm_f32(dy2.t(), x2) if ctx.need_w else None
-        db = dy2.float().sum(0) if ctx.has_bias else None
-        return dx, dw, db, None, None
+        dw = None
+        if ctx.need_w:
+            if ctx.sink is not None and dy2.is_cuda:
+                ctx.sink.append((torch.mm(dy2.t(), x2), ctx.offset))      # bf16 dW -> flat fp32 grads, one kernel per step
+            else:
+                dw = _mm_f32(dy2.t(), x2)
+        return dx, dw, db, None, None, None, None
 
 
 class ShadowLinear(nn.Module):
@@ -80,11 +85,13 @@ class ShadowLinear(nn.Module):
         self.weight = nn.Parameter(torch.empty(out_features, in_features).normal_(0.0, init_std))
         self.bias = nn.Parameter(torch.zeros(out_features)) if bias else None
         self.w_bf16: Optional[torch.Tensor] = None      # view into the shadow buffer (set by attach_shadow)
+        self._sink = None                               # the flat model's gradient sink (set by attach_shadow)
+        self._offset = 0
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if x.dtype != torch.bfloat16:
             x = x.to(torch.bfloat16)
-        return _ShadowLinearFn.apply(x, self.weight, self.bias, self.w_bf16, self.act)
+        return _ShadowLinearFn.apply(x, self.weight, self.bias, self.w_bf16, self.act, self._sink, self._offset)
 
 
 class FrozenLinear(nn.Module):
@@ -180,6 +187,7 @@ def attach_shadow(module: nn.Module, flat_model) -> int:
             continue
         if isinstance(m, ShadowLinear):
             m.w_bf16 = views[key]
+            m._sink, m._offset = flat_model.grad_sink, flat_model.segment(key).offset
             n += 1
         elif isinstance(m, ShadowConv2d) and (flat_model.segment(key).channels_last or tuple(m.kernel_size) == (1, 1)):
             m.attach(views[key], flat_model.grad_sink, flat_model.segment(key).offset)

@@ -77,3 +77,19 @@ def stream_ptr() -> int:
     import torch
 
     return torch.cuda.current_stream().cuda_stream
+
+
+_tree_scratch: dict = {}
+
+
+def tree_scratch(device):
+    """Scratch of the deterministic in-kernel tree reductions (csrc/tree_reduce.cuh): per-CTA partials plus
+    self-resetting arrival counters, zeroed once, shared by every BatchNorm / bias-backward launch of the device
+    (launches are stream-ordered)."""
+    import torch
+
+    key = str(device)
+    buf = _tree_scratch.get(key)
+    if buf is None:
+        buf = _tree_scratch[key] = torch.zeros(int(native().BN_SCRATCH_FLOATS), device=device, dtype=torch.float32)
+    return buf

@@ -16,7 +16,7 @@ from typing import Optional
 import torch
 from torch import nn
 
-from . import count, native, stream_ptr
+from . import count, native, stream_ptr, tree_scratch
 
 _scratch: dict = {}
 
@@ -25,9 +25,7 @@ def _get_scratch(device, C: int):
     """(reduction scratch shared by every BN launch of the device -- partials + self-resetting arrival
     counters, zeroed once --, per-C backward coefficient buffer).  Launches are stream-ordered."""
     key = str(device)
-    red = _scratch.get(key)
-    if red is None:
-        red = _scratch[key] = torch.zeros(int(native().BN_SCRATCH_FLOATS), device=device, dtype=torch.float32)
+    red = tree_scratch(device)
     coef = _scratch.get((key, C))
     if coef is None:
         coef = _scratch[(key, C)] = torch.empty(3 * C, device=device, dtype=torch.float32)

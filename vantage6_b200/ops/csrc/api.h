@@ -125,6 +125,8 @@ int v6_image_normalize_s2d(const void* img, void* out, int N, int H, int W, floa
                            float s2, cudaStream_t s);
 int v6_stem_weight_s2d(const void* w, int w_is_bf16, void* ws, int O, cudaStream_t s);
 int v6_stem_wgrad_d2s(const void* dws, float* dw, int O, int accumulate, cudaStream_t s);
+int v6_bias_act_bwd(const void* dy, const void* pre, void* dpre, float* db, float* scratch, long long R, int C, int act_kind,
+                    int accumulate, cudaStream_t s);
 long long v6_bn_scratch_floats();
 int v6_multi_accum_bf16(const MultiAccumParams* p, float* dst, cudaStream_t s);
 int v6_bn_fwd(const void* x, const void* res, const float* gamma, const float* beta, float* running_mean, float* running_var,

@@ -178,6 +178,10 @@ PYBIND11_MODULE(_C, m) {
     m.def("stem_wgrad_d2s", [](u64 dws, u64 dw, int O, bool accumulate, u64 s) {
         check(v6_stem_wgrad_d2s(P<void>(dws), P<float>(dw), O, accumulate, S(s)), "stem_wgrad_d2s");
     });
+    m.def("bias_act_bwd", [](u64 dy, u64 pre, u64 dpre, u64 db, u64 scratch, long long R, int C, int act, bool accumulate, u64 s) {
+        check(v6_bias_act_bwd(P<void>(dy), P<void>(pre), P<void>(dpre), P<float>(db), P<float>(scratch), R, C, act, accumulate, S(s)),
+              "bias_act_bwd");
+    });
     m.def("bn_fwd", [](u64 x, u64 res, u64 gamma, u64 beta, u64 rmean, u64 rvar, u64 nbt, u64 y, u64 mask, u64 mean, u64 rstd,
                        u64 scale_bias, u64 scratch, long long R, int C, float eps, float momentum, bool relu, u64 s) {
         check(v6_bn_fwd(P<void>(x), P<void>(res), P<float>(gamma), P<float>(beta), P<float>(rmean), P<float>(rvar),

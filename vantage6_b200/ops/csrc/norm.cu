@@ -216,12 +216,30 @@ __global__ void __launch_bounds__(NORM_THREADS) norm_bwd_kernel(
     }
 }
 
-__global__ void norm_param_grad_fold(const float* __restrict__ part, float* __restrict__ out, int nparts, int cols, int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+// out_k[c] (+)= sum_p part_k[p][c] for k = blockIdx.y (dgamma, dbeta).  Block = 32 columns x 8 partial-slices: each
+// thread sums every 8th partial with 4 loads in flight, the 8 slices fold through shared memory (v1: one thread per
+// column looping over up to 1184 partials, 21 us per launch and two launches per LayerNorm --
+// profiles/launches_bert_base_r1c.txt).
+__global__ void __launch_bounds__(256) norm_param_grad_fold(const float* __restrict__ part0, const float* __restrict__ part1,
+                                                            float* __restrict__ out0, float* __restrict__ out1, int nparts, int cols,
+                                                            int accumulate) {
+    __shared__ float sm[8][33];
+    const float* __restrict__ part = blockIdx.y ? part1 : part0;
+    float* __restrict__ out = blockIdx.y ? out1 : out0;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     float a = 0.f;
-    for (int p = 0; p < nparts; ++p) a += part[(size_t)p * cols + c];
-    out[c] = accumulate ? out[c] + a : a;
+    if (c < cols) {
+#pragma unroll 4
+        for (int p = ty; p < nparts; p += 8) a += part[(size_t)p * cols + c];
+    }
+    sm[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && c < cols) {
+#pragma unroll
+        for (int s2 = 1; s2 < 8; ++s2) a += sm[s2][tx];
+        out[c] = accumulate ? out[c] + a : a;
+    }
 }
 
 static inline int pick_tpr(int cols) {
@@ -274,9 +292,7 @@ static int launch_bwd(const void* dy, const void* x_in, const void* dres, const 
                                                 (T*)dx, pg, pb, rows, cols);
     });
     V6_CHECK_LAUNCH();
-    const int fb = (cols + 255) / 256;
-    norm_param_grad_fold<<<fb, 256, 0, s>>>(pg, dgamma, grid, cols, accumulate);
-    if (!RMS) norm_param_grad_fold<<<fb, 256, 0, s>>>(pb, dbeta, grid, cols, accumulate);
+    norm_param_grad_fold<<<dim3((cols + 31) / 32, RMS ? 1 : 2), 256, 0, s>>>(pg, pb, dgamma, dbeta, grid, cols, accumulate);
     V6_CHECK_LAUNCH();
     return 0;
 }

@@ -63,6 +63,35 @@ def _two_cta_default(M: int, N: int, K: int) -> bool:
     return K >= 2048 and M % 256 == 0 and (M // 256) * ((N + 255) // 256) >= 64
 
 
+def bias_act_backward(dy2: torch.Tensor, pre: Optional[torch.Tensor], act: int, bias: Optional[torch.Tensor]):
+    """Backward of ``y = act(x W^T + b)`` w.r.t. the pre-activation and the bias, ONE kernel (csrc/act.cu):
+    returns ``(dpre, db)``; ``dpre`` is ``dy2`` itself when there is no activation; ``db`` is None when it was
+    accumulated straight into ``bias.grad`` (flat-buffer models pre-allocate it) or when there is no bias."""
+    R, C = dy2.shape
+    need_db = bias is not None
+    if dy2.is_cuda and dy2.dtype == torch.bfloat16 and C % 64 == 0 and C <= 4096 and (act != ACT_NONE or need_db):
+        from . import tree_scratch
+
+        direct = need_db and bias.grad is not None and bias.grad.dtype == torch.float32 and bias.grad.is_contiguous()
+        db = None
+        if need_db:
+            db = bias.grad if direct else torch.empty(C, device=dy2.device, dtype=torch.float32)
+        dpre = torch.empty_like(dy2) if act != ACT_NONE else None
+        count(1)
+        native().bias_act_bwd(dy2.data_ptr(), 0 if pre is None or act == ACT_NONE else pre.data_ptr(),
+                              0 if dpre is None else dpre.data_ptr(), 0 if db is None else db.data_ptr(),
+                              tree_scratch(dy2.device).data_ptr(), R, C, int(act), bool(direct), stream_ptr())
+        return (dpre if dpre is not None else dy2), (None if (direct or not need_db) else db)
+    g = dy2
+    if act == ACT_GELU:
+        p = pre.float()
+        g = (dy2.float() * (0.5 * (1.0 + torch.erf(p * 0.7071067811865476))
+                            + p * torch.exp(-0.5 * p * p) * 0.3989422804014327)).to(dy2.dtype)
+    elif act == ACT_RELU:
+        g = dy2 * (pre > 0)
+    return g.contiguous(), (g.float().sum(0) if need_db else None)
+
+
 def bcast_gemm_bf16(x2: torch.Tensor, W_local: torch.Tensor, W_server_ptr: int, ready_flags: torch.Tensor,
                     epoch: int, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
                     out: Optional[torch.Tensor] = None) -> torch.Tensor:

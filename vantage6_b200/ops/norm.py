@@ -56,6 +56,7 @@ class _LayerNormFn(torch.autograd.Function):
         ctx.has_res = residual is not None
         ctx.shape = shape
         ctx.has_beta = beta is not None
+        ctx.params = (gamma, beta)                # the Parameters themselves: .grad may be a flat-buffer view
         if residual is not None:
             return y.view(shape), res_out.view(shape)
         return y.view(shape), None
@@ -68,19 +69,25 @@ class _LayerNormFn(torch.autograd.Function):
         dy2 = dy.reshape(-1, cols).contiguous()
         dres2 = dres.reshape(-1, cols).contiguous() if (ctx.has_res and dres is not None) else None
         dx = torch.empty_like(x_in)
-        dgamma = torch.empty_like(gamma)
-        dbeta = torch.empty_like(gamma) if not ctx.rms else None
+        # flat-buffer models pre-allocate .grad as views of one fp32 buffer: accumulate dgamma / dbeta in place
+        pg, pb = ctx.params
+        direct = all(p is None or (p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous())
+                     for p in ((pg,) if ctx.rms else (pg, pb))) and pg is not None and (ctx.rms or pb is not None)
+        dgamma = pg.grad if direct else torch.empty_like(gamma)
+        dbeta = None if ctx.rms else (pb.grad if direct else torch.empty_like(gamma))
         scratch = _get_scratch(x_in.device, cols)
         bf16 = x_in.dtype == torch.bfloat16
         C = native()
         if ctx.rms:
             C.rmsnorm_bwd(dy2.data_ptr(), x_in.data_ptr(), _ptr(dres2), gamma.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
-                          dgamma.data_ptr(), scratch.data_ptr(), _SCRATCH_PARTS, rows, cols, False, bf16, stream_ptr())
+                          dgamma.data_ptr(), scratch.data_ptr(), _SCRATCH_PARTS, rows, cols, direct, bf16, stream_ptr())
         else:
             C.layernorm_bwd(dy2.data_ptr(), x_in.data_ptr(), _ptr(dres2), gamma.data_ptr(), mean.data_ptr(),
                             rstd.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), scratch.data_ptr(),
-                            _SCRATCH_PARTS, rows, cols, False, bf16, stream_ptr())
+                            _SCRATCH_PARTS, rows, cols, direct, bf16, stream_ptr())
         dxv = dx.view(ctx.shape)
+        if direct:
+            return dxv, None, None, (dxv if ctx.has_res else None), None, None
         return dxv, dgamma, (dbeta if ctx.has_beta else None), (dxv if ctx.has_res else None), None, None
 
 
