@@ -86,6 +86,8 @@ def RPC_fit(data, iterations: int = 20, lr: float = 1.0, rendezvous: Optional[di
     rank, world = int(rv["ranks"][str(org_id)]), int(rv["world"])
     use_cuda = torch.cuda.is_available()
     device = torch.device("cuda", int(os.environ.get("V6_GPU", "0"))) if use_cuda else torch.device("cpu")
+    if use_cuda:
+        torch.cuda.set_device(device)        # all GPUs are visible (peers get mapped): make the pinned one current
     created = False
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl" if use_cuda else "gloo", init_method=f"tcp://{rv['addr']}:{rv['port']}",

@@ -85,6 +85,10 @@ class SymmetricHeap:
             os.makedirs(rendezvous_dir, exist_ok=True)
             self.dir = rendezvous_dir
             dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            if torch.cuda.current_device() != dev_index:
+                # our kernels launch on the CURRENT device's stream: a process that owns this heap must run on its GPU
+                # (nodes are pinned with V6_GPU while every GPU stays visible so that peers can be mapped)
+                torch.cuda.set_device(dev_index)
             self.gid = self._C.symm_init(rank, world, dev_index, rendezvous_dir, timeout_s)
             self.multicast = bool(self._C.symm_multicast_supported(self.gid)) and world > 1
         else:
