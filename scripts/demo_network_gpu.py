@@ -37,7 +37,7 @@ def main():
             task = c.task.create(collaboration=net.collaboration_id, organizations=[net.org_ids[0]], name=image, image=image,
                                  input=inp)
             try:
-                res = c.wait_for_results(task["id"], timeout=900)
+                res = c.wait_for_results(task["id"], timeout=240)
             except TimeoutError:
                 print(net.tail_logs(60))
                 raise
@@ -50,12 +50,11 @@ def main():
             out.update({"image": image, "nodes": args.nodes, "task_wall_s": round(time.time() - t0, 2)})
             lines.append(out)
             print(json.dumps(out), flush=True)
+            if args.out:                                    # incremental: a later task may time out
+                with open(args.out, "a") as f:
+                    f.write(json.dumps(out) + "\n")
     finally:
         net.stop()
-    if args.out:
-        with open(args.out, "w") as f:
-            for o in lines:
-                f.write(json.dumps(o) + "\n")
 
 
 if __name__ == "__main__":

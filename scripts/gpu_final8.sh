@@ -21,4 +21,4 @@ for m in bert_base glm; do for impl in b200 nccl; do
   tail -1 gpurun_out/model_${m}_${impl}_$N.err | cut -c1-200
 done; done
 echo "== full stack: vserver + $N x vnode --gpu k, FedAvg(resnet50) + GLM through the control plane"
-timeout 900 python scripts/demo_network_gpu.py --nodes $N --model resnet50 --rounds 4 --glm --out gpurun_out/demo_network_$N.jsonl 2>&1 | tail -6 | cut -c1-900
+rm -f gpurun_out/demo_network_$N.jsonl; timeout 420 python scripts/demo_network_gpu.py --nodes $N --model resnet50 --rounds 4 --glm --out gpurun_out/demo_network_$N.jsonl 2>&1 | tail -6 | cut -c1-900
