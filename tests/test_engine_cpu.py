@@ -291,3 +291,26 @@ def test_resnet_stem_paths_agree_on_cpu():
         a = m(img)
         b = m((img.float() - mean) / std)
     torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-4)
+
+
+def test_stock_optimizer_arm_matches_fused_arm_in_delta_mode():
+    """The baseline arm (torch.optim, no fused publish) must federate the same model as the fused arm: the round
+    reference is saved before the first local step and the delta published after the last one."""
+    import torch
+
+    from vantage6_b200.models import zoo
+
+    def run(fused):
+        torch.manual_seed(21)
+        tr, spec = zoo.build_trainer("bert_tiny", rank=0, world=1, device="cpu", data_plane="auto" if fused else "collective",
+                                     fused_local_optimizer=fused)
+        batches = spec.make_batches(2, 4, 77)
+        tr.initialize_global()
+        losses = [float(tr.run_round(batches)) for _ in range(4)]
+        tr.close()
+        return losses
+
+    a, b = run(True), run(False)
+    assert a[-1] < a[0] - 0.3                     # the (fixed, synthetic) shard is being fitted
+    for x, y in zip(a, b):
+        assert abs(x - y) < 5e-3, (a, b)

@@ -93,9 +93,17 @@ class FederatedTrainer:
         self.fm.flush_grad_sink()          # bf16 conv weight gradients -> flat fp32 grads, one multi-tensor kernel
         self.loss_sum += loss.detach().float()
         if self.torch_opt is not None:
+            # baseline arm: stock optimizer; delta upload modes save the round's reference / publish the delta with
+            # separate passes (the fused optimizer does both inside its one sweep)
+            nt = self.fm.n_trainable
+            delta_mode = self.upload_mode != "weights_f32"
+            if delta_mode and variant in ("first", "only"):
+                self.w_ref[:nt].copy_(self.fm.params)
             if self.max_grad_norm:
                 torch.nn.utils.clip_grad_norm_([p for p in self.model.parameters() if p.requires_grad], self.max_grad_norm)
             self.torch_opt.step()
+            if delta_mode and variant in ("last", "only"):
+                fused_optim.delta_publish(self.fm.params, self.w_ref[:nt], self.engine.upload[:nt], 1.0)
             return
         gs = None
         if self.max_grad_norm:
