@@ -100,3 +100,22 @@ def test_glm_fused_converges_on_gpu(dev):
     assert glm.last_loss.item() < 0.8 * l0
     assert (glm.w - w_true).abs().max().item() < 0.6
     glm.close()
+
+
+@pytest.mark.parametrize("variant", ["1cta", "2cta"])
+def test_packed_qkv_attention_forward_backward(dev, variant, monkeypatch):
+    """q / k consumed in place from a packed [B,S,3,H,D] projection output; dq/dk/dv written into one dqkv buffer."""
+    from vantage6_b200.ops import attention as A
+
+    monkeypatch.setenv("V6B200_ATTN_FWD", variant)
+    torch.manual_seed(5)
+    B, S, H, D = 2, 256, 12, 64
+    qkv = torch.randn(B, S, 3, H, D, device=dev, dtype=torch.bfloat16).requires_grad_()
+    o = A.packed_qkv_attention(qkv, False)
+    do = torch.randn_like(o)
+    o.backward(do)
+    ref = qkv.detach().float().requires_grad_()
+    ro, _ = A.reference_attention(ref[:, :, 0], ref[:, :, 1], ref[:, :, 2], False)
+    ro.backward(do.float())
+    assert (o.float() - ro).abs().max().item() < 3e-2
+    assert (qkv.grad.float() - ref.grad).abs().max().item() < 6e-2

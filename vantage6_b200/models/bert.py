@@ -16,7 +16,7 @@ import torch
 from torch import nn
 
 from ..ops import gemm as G
-from .transformer import FusedLayerNorm, ShadowLinear, attention
+from .transformer import packed_attention, FusedLayerNorm, ShadowLinear, attention
 
 
 @dataclass
@@ -45,7 +45,7 @@ class BertLayer(nn.Module):
     def forward(self, x, mask=None):
         B, S, H = x.shape
         qkv = self.qkv(x).view(B, S, 3, self.heads, self.hd)
-        a = attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], causal=False, mask=mask).reshape(B, S, H)
+        a = packed_attention(qkv, mask=mask).reshape(B, S, H)
         x, _ = self.ln1(self.out(a), residual=x)           # LN(x + attn) with the add fused in the kernel
         x, _ = self.ln2(self.ffn2(self.ffn1(x)), residual=x)
         return x

@@ -195,6 +195,20 @@ def attach_shadow(module: nn.Module, flat_model) -> int:
     return n
 
 
+def packed_attention(qkv: torch.Tensor, causal: bool = False, mask=None) -> torch.Tensor:
+    """Self-attention on a packed projection output qkv:[B,S,3,H,D] -> [B,S,H,D] (no q/k/v slice copies on the
+    tcgen05 path; falls back to :func:`attention` elsewhere)."""
+    try:
+        from ..ops import attention as A
+
+        q = qkv[:, :, 0]
+        if qkv.is_cuda and A.available() and mask is None and A._supported(q, q):
+            return A.packed_qkv_attention(qkv, causal)
+    except ImportError:
+        pass
+    return attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], causal, mask)
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool, mask=None) -> torch.Tensor:
     """q:[B,S,Hq,D] k,v:[B,S,Hkv,D] -> [B,S,Hq,D].
 

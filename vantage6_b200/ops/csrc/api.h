@@ -141,9 +141,9 @@ int v6_gemm2_bf16(const void* A, const void* B, void* C, const float* bias, int 
                   int act, cudaStream_t stream);
 int v6_gemm_smem_bytes();
 int v6_flash_attn_fwd2(const void* q, const void* k, const void* vt, void* o, float* lse, int B, int S, int Hq, int Hkv,
-                       int D, float softmax_scale, int causal, cudaStream_t stream);
+                       int D, long long ldq, long long ldk, float softmax_scale, int causal, cudaStream_t stream);
 int v6_flash_attn_fwd(const void* q, const void* k, const void* vt, void* o, float* lse, int B, int S, int Hq, int Hkv,
-                      int D, float softmax_scale, int causal, cudaStream_t stream);
+                      int D, long long ldq, long long ldk, float softmax_scale, int causal, cudaStream_t stream);
 // symm.cpp
 const char* v6_symm_last_error();
 int v6_driver_available();

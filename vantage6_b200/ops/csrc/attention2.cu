@@ -282,11 +282,16 @@ static int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
 
 // q:[B,S,Hq,D] k:[B,S,Hkv,D] vt:[B,Hkv,D,S] (all bf16, contiguous) -> o:[B,S,Hq,D], lse:[B,Hq,S]
 extern "C" int v6_flash_attn_fwd2(const void* q, const void* k, const void* vt, void* o, float* lse, int B, int S, int Hq,
-                                  int Hkv, int D, float softmax_scale, int causal, cudaStream_t stream) {
+                                  int Hkv, int D, long long ldq, long long ldk, float softmax_scale, int causal, cudaStream_t stream) {
     if ((D != 64 && D != 128) || Hq % Hkv != 0 || S % 8 != 0) return (int)cudaErrorInvalidValue;
+    // ldq / ldk: token-row strides in elements (0 = dense).  A packed QKV projection output [B,S,3,H,D] is consumed in
+    // place: q = base, k = base + H*D, ldq = ldk = 3*H*D -- no .contiguous() copies.
+    if (ldq <= 0) ldq = (long long)Hq * D;
+    if (ldk <= 0) ldk = (long long)Hkv * D;
+    if (ldq % 8 != 0 || ldk % 8 != 0 || ldq < (long long)Hq * D || ldk < (long long)Hkv * D) return (int)cudaErrorInvalidValue;
     alignas(64) CUtensorMap tq, tk, tv;
-    if (v6_make_tmap_2d_bf16(&tq, (uint64_t)q, (uint64_t)B * S, (uint64_t)Hq * D, (uint64_t)Hq * D * 2, 128, 64, 1)) return -2;
-    if (v6_make_tmap_2d_bf16(&tk, (uint64_t)k, (uint64_t)B * S, (uint64_t)Hkv * D, (uint64_t)Hkv * D * 2, 128, 64, 1)) return -2;
+    if (v6_make_tmap_2d_bf16(&tq, (uint64_t)q, (uint64_t)B * S, (uint64_t)Hq * D, (uint64_t)ldq * 2, 128, 64, 1)) return -2;
+    if (v6_make_tmap_2d_bf16(&tk, (uint64_t)k, (uint64_t)B * S, (uint64_t)Hkv * D, (uint64_t)ldk * 2, 128, 64, 1)) return -2;
     if (v6_make_tmap_2d_bf16(&tv, (uint64_t)vt, (uint64_t)B * Hkv * D, (uint64_t)S, (uint64_t)S * 2, (uint32_t)D, 64, 1)) return -2;
     attn2::Params P;
     P.O = (__nv_bfloat16*)o; P.lse = lse; P.B = B; P.S = S; P.Hq = Hq; P.Hkv = Hkv;

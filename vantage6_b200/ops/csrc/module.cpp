@@ -230,14 +230,14 @@ PYBIND11_MODULE(_C, m) {
                                 scale, causal, S(s)), "flash_attn_bwd");
     });
     // ------------------------------------------------------------------ K4 attention
-    m.def("flash_attn_fwd2", [](u64 q, u64 k, u64 vt, u64 o, u64 lse, int B, int Sq, int Hq, int Hkv, int D, float scale,
+    m.def("flash_attn_fwd2", [](u64 q, u64 k, u64 vt, u64 o, u64 lse, int B, int Sq, int Hq, int Hkv, int D, long long ldq, long long ldk, float scale,
                                bool causal, u64 s) {
-        check(v6_flash_attn_fwd2(P<void>(q), P<void>(k), P<void>(vt), P<void>(o), P<float>(lse), B, Sq, Hq, Hkv, D, scale,
+        check(v6_flash_attn_fwd2(P<void>(q), P<void>(k), P<void>(vt), P<void>(o), P<float>(lse), B, Sq, Hq, Hkv, D, ldq, ldk, scale,
                                  causal, S(s)), "flash_attn_fwd2");
     });
-    m.def("flash_attn_fwd", [](u64 q, u64 k, u64 vt, u64 o, u64 lse, int B, int Sq, int Hq, int Hkv, int D, float scale,
+    m.def("flash_attn_fwd", [](u64 q, u64 k, u64 vt, u64 o, u64 lse, int B, int Sq, int Hq, int Hkv, int D, long long ldq, long long ldk, float scale,
                                bool causal, u64 s) {
-        check(v6_flash_attn_fwd(P<void>(q), P<void>(k), P<void>(vt), P<void>(o), P<float>(lse), B, Sq, Hq, Hkv, D, scale,
+        check(v6_flash_attn_fwd(P<void>(q), P<void>(k), P<void>(vt), P<void>(o), P<float>(lse), B, Sq, Hq, Hkv, D, ldq, ldk, scale,
                                 causal, S(s)), "flash_attn_fwd");
     });
 }
