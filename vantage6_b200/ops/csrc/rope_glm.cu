@@ -63,13 +63,18 @@ extern "C" int v6_rope(void* q, void* k, const float* cos_t, const float* sin_t,
 //   z = X w + b ; p = sigmoid(z) ; r = p - y ; g_w = X^T r ; g_b = sum r ; loss = sum BCE
 // X:[rows, F] bf16 / fp32 row-major, F % 64 == 0, F <= 512; w = [coefficients (F), intercept].
 //
-// Mapping (v2-v4; v1 used one warp per row and reached only 16% of HBM bandwidth -- one 16 B load in
+// Mapping (v3; v1 used one warp per row and reached only 16% of HBM bandwidth -- one 16 B load in
 // flight per lane and a 5-step shuffle per row): a row is owned by 8 lanes, so a warp handles 4
 // rows at a time, 2x unrolled = 8 rows in flight per warp; lane l of the group reads vectors
 // l, l+8, l+16, ... of its row (8 lanes x 16 B = one 128 B line per access).  The dot product is a
 // 3-step shuffle inside the 8-lane group; X^T r accumulates in registers (F/8 per lane); warps and
 // lane groups fold through shared memory into one partial per CTA; `fold` sums the partials into
 // out = [g_w (F), g_b, loss, n_rows] -- exactly the payload handed to the K3 small all-reduce.
+// (A v4 with a software-pipelined row stream and the coefficients in shared memory measured 5% SLOWER
+// -- 163 vs 155 us, profiles/kernel_bench_r1b.json vs the r1d run -- and was reverted: the kernel is bound by
+// issue slots + latency at 2 CTAs/SM, not by bytes in flight.  The tcgen05 formulation (z = X w and g = X^T r as
+// two UMMA GEMVs with r split into hi/lo bf16 columns, X tiles fed by TMA, MN-major A for the second product)
+// is the round-2 item.)
 // ----------------------------------------------------------------------------------------
 constexpr int GLM_THREADS = 256;
 
@@ -106,60 +111,49 @@ template <> struct GlmLoad<float> {
 };
 
 template <typename T, int NV /* 8-feature vectors per lane = F/64 */>
-__global__ void __launch_bounds__(GLM_THREADS, NV >= 8 ? 1 : 2) glm_logistic_kernel(const T* __restrict__ X, const float* __restrict__ y,
+__global__ void __launch_bounds__(GLM_THREADS, 2) glm_logistic_kernel(const T* __restrict__ X, const float* __restrict__ y,
                                                                        const float* __restrict__ w,
                                                                        float* __restrict__ part, int rows) {
     constexpr int F = NV * 64;
-    constexpr int U = NV >= 8 ? 1 : GlmLoad<T>::U;             // rows per lane group per batch (x2 batches in flight)
+    constexpr int U = GlmLoad<T>::U;                           // row unroll per lane group
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gl = lane & 7, grp = lane >> 3;                  // lane in group, group in warp
     const int groups_per_cta = (GLM_THREADS / 32) * 4;
     const int my_group = wid * 4 + grp;
-    // v4: the coefficient vector lives in shared memory (frees 32 registers) and the row stream is software
-    // pipelined: the loads of batch i+1 are in flight while batch i is consumed, so the bytes in flight per SM
-    // never drop to zero between batches (v3 issued, waited, consumed: 0.50 of HBM -- profiles/kernel_bench_r1b.json).
-    __shared__ __align__(16) float sw[F + 4];
-    for (int i = threadIdx.x; i < F + 1; i += GLM_THREADS) sw[i] = w[i];
-    __syncthreads();
-    float g[NV][8];
+    float wr[NV][8], g[NV][8];
 #pragma unroll
     for (int c = 0; c < NV; ++c)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) g[c][k] = 0.f;
-    const float bias = sw[F];
+        for (int k = 0; k < 8; ++k) { g[c][k] = 0.f; wr[c][k] = w[(c * 8 + gl) * 8 + k]; }
+    const float bias = w[F];
     float gb = 0.f, loss = 0.f;
     const long long stride = (long long)gridDim.x * groups_per_cta;
-    typename GlmLoad<T>::Raw cur[U][NV], nxt[U][NV];
-    auto load_batch = [&](typename GlmLoad<T>::Raw (&dst)[U][NV], long long row0) {
+    for (long long row0 = (long long)blockIdx.x * groups_per_cta + my_group; row0 < rows; row0 += stride * U) {
+        typename GlmLoad<T>::Raw xr[U][NV];
+        float dot[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const long long row = row0 + u * stride;
+            dot[u] = 0.f;
             if (row < rows) {
 #pragma unroll
-                for (int c = 0; c < NV; ++c) dst[u][c] = GlmLoad<T>::load_raw(X + (size_t)row * F + (c * 8 + gl) * 8);
+                for (int c = 0; c < NV; ++c) xr[u][c] = GlmLoad<T>::load_raw(X + (size_t)row * F + (c * 8 + gl) * 8);
             }
         }
-    };
-    long long row0 = (long long)blockIdx.x * groups_per_cta + my_group;
-    load_batch(cur, row0);
-    for (; row0 < rows; row0 += stride * U) {
-        load_batch(nxt, row0 + stride * U);                    // prefetch (predicated off past the end)
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const long long row = row0 + u * stride;
             const bool ok = row < rows;                        // uniform inside the 8-lane group
-            float d = 0.f;
             if (ok) {
 #pragma unroll
                 for (int c = 0; c < NV; ++c) {
                     float xv[8];
-                    GlmLoad<T>::unpack(cur[u][c], xv);
-                    const float4 w0 = *reinterpret_cast<const float4*>(sw + (c * 8 + gl) * 8);
-                    const float4 w1 = *reinterpret_cast<const float4*>(sw + (c * 8 + gl) * 8 + 4);
-                    d = fmaf(xv[0], w0.x, d); d = fmaf(xv[1], w0.y, d); d = fmaf(xv[2], w0.z, d); d = fmaf(xv[3], w0.w, d);
-                    d = fmaf(xv[4], w1.x, d); d = fmaf(xv[5], w1.y, d); d = fmaf(xv[6], w1.z, d); d = fmaf(xv[7], w1.w, d);
+                    GlmLoad<T>::unpack(xr[u][c], xv);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) dot[u] = fmaf(xv[k], wr[c][k], dot[u]);
                 }
             }
+            float d = dot[u];
             d += __shfl_xor_sync(0xffffffffu, d, 1);
             d += __shfl_xor_sync(0xffffffffu, d, 2);
             d += __shfl_xor_sync(0xffffffffu, d, 4);
@@ -171,16 +165,12 @@ __global__ void __launch_bounds__(GLM_THREADS, NV >= 8 ? 1 : 2) glm_logistic_ker
 #pragma unroll
                 for (int c = 0; c < NV; ++c) {
                     float xv[8];
-                    GlmLoad<T>::unpack(cur[u][c], xv);
+                    GlmLoad<T>::unpack(xr[u][c], xv);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) g[c][k] = fmaf(r, xv[k], g[c][k]);
                 }
             }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int c = 0; c < NV; ++c) cur[u][c] = nxt[u][c];
     }
     // fold the 4 lane groups of each warp (same gl -> same features), then the warps through smem
 #pragma unroll
