@@ -26,7 +26,7 @@ from cryptography.hazmat.primitives.asymmetric import padding, rsa
 from cryptography.hazmat.primitives.ciphers import Cipher, algorithms, modes
 from cryptography.hazmat.primitives.serialization import load_pem_private_key, load_pem_public_key
 
-from . import STRING_ENCODING, base64s_to_bytes, bytes_to_base64s, logger_name
+from . import base64s_to_bytes, bytes_to_base64s, logger_name
 
 SEPARATOR = "$"
 

@@ -19,7 +19,7 @@ import socket
 import time
 import uuid
 from pathlib import Path
-from typing import Dict, List, Optional
+from typing import List, Optional
 
 import yaml
 from click.testing import CliRunner

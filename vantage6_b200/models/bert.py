@@ -16,7 +16,7 @@ import torch
 from torch import nn
 
 from ..ops import gemm as G
-from .transformer import packed_attention, FusedLayerNorm, ShadowLinear, attention
+from .transformer import FusedLayerNorm, ShadowLinear, packed_attention
 
 
 @dataclass

@@ -25,9 +25,8 @@ participation renormalises over the reporters (weight 0 == not reporting).
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass
-from typing import List, Optional, Sequence
+from typing import List, Sequence
 
 import torch
 

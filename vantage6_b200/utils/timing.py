@@ -7,10 +7,8 @@ import os
 import statistics
 import subprocess
 import tempfile
-import threading
-import time
 from contextlib import contextmanager
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import torch
 
