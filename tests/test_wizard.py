@@ -1,98 +1,105 @@
-"""Configuration wizard tests (cases mirror reference tests/test_wizard.py; the stale
-``"rabbitmq"`` key assertion there is corrected to ``"rabbitmq_uri"``)."""
+"""The configuration wizard: questionnaires (node, server), the driver that writes / extends the YAML file, and
+the configuration selector.  Scenario coverage follows the reference's wizard tests (tests/test_wizard.py) -- with
+its stale ``"rabbitmq"`` key assertion corrected to ``"rabbitmq_uri"`` -- plus the
+multi-environment merge and the empty-selector error, which the reference leaves untested."""
+from contextlib import contextmanager
 from pathlib import Path
 from unittest.mock import MagicMock, patch
 
+import pytest
 import yaml
 
-from vantage6_b200.cli.configuration_wizard import (configuration_wizard, node_configuration_questionaire,
-                                                    select_configuration_questionaire,
-                                                    server_configuration_questionaire)
+from vantage6_b200.cli import configuration_wizard as wizard
 
-module_path = "vantage6_b200.cli.configuration_wizard"
+WIZARD = "vantage6_b200.cli.configuration_wizard"
+NODE_KEYS = {"api_key", "server_url", "port", "api_path", "task_dir", "databases", "logging", "encryption", "vpn_subnet"}
+SERVER_KEYS = {"description", "ip", "port", "api_path", "uri", "allow_drop_all", "jwt_secret_key", "logging",
+               "vpn_server", "rabbitmq_uri"}
 
 
-def prompts(*args, **kwargs):
-    result = {}
-    for arg in args[0]:
-        name = arg["name"]
-        if name == "default":               # default db path
-            result[name] = "/some/path/db.sqlite"
+def accept_defaults(questions, **_):
+    """Answer every prompt with its default; the default database gets a path (it has no default)."""
+    return {item["name"]: ("/some/path/db.sqlite" if item["name"] == "default" else item.get("default"))
+            for item in questions}
+
+
+@contextmanager
+def scripted_prompts(confirm_answers, prompt=accept_defaults):
+    with patch(f"{WIZARD}.q") as q:
+        q.prompt.side_effect = prompt
+        q.confirm.return_value.ask.side_effect = list(confirm_answers)
+        yield q
+
+
+@pytest.mark.parametrize("kind,confirms,expected_keys", [
+    ("node", (True, False, True), NODE_KEYS),          # one extra database, then stop; VPN yes
+    ("server", (True, True, True), SERVER_KEYS),       # jwt secret, vpn server, message queue: all yes
+])
+def test_questionnaires_cover_every_section(kind, confirms, expected_keys):
+    with scripted_prompts(confirms):
+        if kind == "node":
+            config = wizard.node_configuration_questionaire({"data": "/"}, "iknl")
         else:
-            result[name] = arg.get("default")
-    return result
+            config = wizard.server_configuration_questionaire("", "vantage6")
+    assert expected_keys <= set(config)
+    if kind == "node":
+        assert set(config["databases"]) == {"default", "database_1"}
+        assert (config["logging"]["file"], config["logging"]["backup_count"]) == ("iknl.log", 5)
+    else:
+        assert (config["uri"], config["ip"], config["port"]) == ("sqlite:///default.sqlite", "0.0.0.0", "5000")
 
 
-def test_node_wizard():
-    with patch(f"{module_path}.q") as q:
-        q.prompt.side_effect = prompts
-        q.confirm.return_value.ask.side_effect = [True, False, True]
-        config = node_configuration_questionaire({"data": "/"}, "iknl")
-    for key in ["api_key", "server_url", "port", "api_path", "task_dir", "databases", "logging", "encryption",
-                "vpn_subnet"]:
-        assert key in config
-    assert set(config["databases"]) == {"default", "database_1"}
-    assert config["logging"]["file"] == "iknl.log" and config["logging"]["backup_count"] == 5
+def test_driver_returns_the_path_it_wrote():
+    targets = ("node_configuration_questionaire", "server_configuration_questionaire", "ServerConfigurationManager",
+               "NodeConfigurationManager", "NodeContext")
+    patches = [patch(f"{WIZARD}.{t}") for t in targets]
+    mocks = dict(zip(targets, (p.start() for p in patches)))
+    try:
+        mocks["NodeContext"].instance_folders.return_value = {"config": "/some/path/"}
+        for kind, system_folders in (("node", False), ("server", True)):
+            assert wizard.configuration_wizard(kind, "vtg6", "application", system_folders) == Path("/some/path/vtg6.yaml")
+    finally:
+        for p in patches:
+            p.stop()
 
 
-def test_server_wizard():
-    with patch(f"{module_path}.q") as q:
-        q.prompt.side_effect = prompts
-        q.confirm.return_value.ask.side_effect = [True, True, True]
-        config = server_configuration_questionaire("", "vantage6")
-    for key in ["description", "ip", "port", "api_path", "uri", "allow_drop_all", "jwt_secret_key", "logging",
-                "vpn_server", "rabbitmq_uri"]:
-        assert key in config
-    assert config["uri"] == "sqlite:///default.sqlite" and config["ip"] == "0.0.0.0" and config["port"] == "5000"
+def test_second_environment_extends_the_same_file(v6home):
+    """Running the wizard again for another environment adds to the file instead of replacing it
+    (reference configuration_wizard.py:234-242)."""
+    fixed = {"api_key": "k", "server_url": "http://localhost", "port": "5000", "api_path": "/api", "task_dir": "/tmp"}
 
+    def answer(questions, **_):
+        return {item["name"]: fixed.get(item["name"], item.get("default", "x")) for item in questions}
 
-@patch(f"{module_path}.node_configuration_questionaire")
-@patch(f"{module_path}.server_configuration_questionaire")
-@patch(f"{module_path}.ServerConfigurationManager")
-@patch(f"{module_path}.NodeConfigurationManager")
-@patch(f"{module_path}.NodeContext")
-def test_configuration_wizard_interface(context, node_m, server_m, server_q, node_q):
-    context.instance_folders.return_value = {"config": "/some/path/"}
-    assert configuration_wizard("node", "vtg6", "application", False) == Path("/some/path/vtg6.yaml")
-    assert configuration_wizard("server", "vtg6", "application", True) == Path("/some/path/vtg6.yaml")
-
-
-def test_wizard_writes_and_merges_environments(v6home):
-    """A second run for another environment extends the same file (reference wizard :234-242)."""
-    answers = {"api_key": "k", "server_url": "http://localhost", "port": "5000", "api_path": "/api", "task_dir": "/tmp"}
-    with patch(f"{module_path}.q") as q:
-        q.prompt.side_effect = lambda qs, **_: {d["name"]: answers.get(d["name"], d.get("default", "x")) for d in qs}
+    with patch(f"{WIZARD}.q") as q:
+        q.prompt.side_effect = answer
         q.confirm.return_value.ask.return_value = False
         q.select.return_value.ask.side_effect = ["INFO", "false", "DEBUG", "false"]
-        f1 = configuration_wizard("node", "n1", "application", False)
-        f2 = configuration_wizard("node", "n1", "dev", False)
-    assert f1 == f2
-    doc = yaml.safe_load(Path(f1).read_text())
-    assert doc["application"]["port"] == 5000                       # coerced by the schema
-    assert doc["environments"]["dev"]["logging"]["level"] == "DEBUG"
-    assert doc["environments"]["prod"] == {}
+        written = [wizard.configuration_wizard("node", "n1", env, False) for env in ("application", "dev")]
+    assert written[0] == written[1]
+    document = yaml.safe_load(Path(written[0]).read_text())
+    assert document["application"]["port"] == 5000                       # coerced by the schema
+    assert document["environments"]["dev"]["logging"]["level"] == "DEBUG"
+    assert document["environments"]["prod"] == {}
 
 
-@patch(f"{module_path}.NodeContext")
-@patch(f"{module_path}.ServerContext")
-def test_select_configuration(server_c, node_c):
-    config = MagicMock()
-    config.name = "vtg6"
-    config.available_environments = ["application"]
-    server_c.available_configurations.return_value = [[config], []]
-    node_c.available_configurations.return_value = [[config], []]
-    with patch(f"{module_path}.q") as q:
+def _one_configuration(name="vtg6", environments=("application",)):
+    cfg = MagicMock(available_environments=list(environments))
+    cfg.name = name
+    return [[cfg], []]
+
+
+def test_selector_returns_the_picked_pair():
+    with patch(f"{WIZARD}.NodeContext") as node_c, patch(f"{WIZARD}.ServerContext") as server_c, \
+            patch(f"{WIZARD}.q") as q:
+        node_c.available_configurations.return_value = _one_configuration()
+        server_c.available_configurations.return_value = _one_configuration()
         q.select.return_value.ask.return_value = ["vtg6", "application"]
-        name, env = select_configuration_questionaire("node", True)
-    assert (name, env) == ("vtg6", "application")
+        assert tuple(wizard.select_configuration_questionaire("node", True)) == ("vtg6", "application")
 
 
-@patch(f"{module_path}.NodeContext")
-def test_select_configuration_empty_raises(node_c):
-    node_c.available_configurations.return_value = [[], []]
-    try:
-        select_configuration_questionaire("node", False)
-    except Exception as e:  # noqa: BLE001
-        assert str(e) == "No configurations could be found!"
-    else:
-        raise AssertionError("expected an exception")
+def test_selector_without_configurations_raises():
+    with patch(f"{WIZARD}.NodeContext") as node_c:
+        node_c.available_configurations.return_value = [[], []]
+        with pytest.raises(Exception, match="No configurations could be found!"):
+            wizard.select_configuration_questionaire("node", False)

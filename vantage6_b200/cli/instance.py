@@ -16,6 +16,7 @@ reference vantage6/cli/node.py:71-119,428-502,734-763 and vantage6/cli/server.py
 """
 from __future__ import annotations
 
+import re
 import time
 from dataclasses import dataclass, field
 from threading import Thread
@@ -94,6 +95,29 @@ def environment_option(default: str):
 
 def config_option():
     return click.option("-c", "--config", default=None, help="absolute path to configuration-file; overrides NAME")
+
+
+# ----------------------------------------------------------------------------------------- guards
+_NAME_CHARSET = "a-zA-Z0-9_.-"
+_VALID_NAME = re.compile(f"[{_NAME_CHARSET}]+")
+
+
+def check_config_name_allowed(name: str) -> None:
+    """Configuration names end up in process, volume and file names: exit(1) unless ``name`` sticks to
+    ``a-zA-Z0-9_.-`` (reference vantage6/cli/utils.py:6-11)."""
+    if not name or _VALID_NAME.fullmatch(name) is None:
+        error(f"Name '{name}' is not allowed. Please use only the following characters: {_NAME_CHARSET}")
+        exit(1)
+
+
+def check_if_docker_deamon_is_running(docker_client) -> None:
+    """Exit(1) unless the local runtime answers a ping.  (The name is the reference's -- utils.py:14-19 --
+    where the thing being pinged is the Docker daemon.)"""
+    try:
+        docker_client.ping()
+    except Exception:  # noqa: BLE001
+        error("Docker socket can not be found. Make sure Docker is running.")
+        exit(1)
 
 
 # ------------------------------------------------------------------------------------ log tailing

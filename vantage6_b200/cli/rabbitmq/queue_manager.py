@@ -1,13 +1,18 @@
-"""Message-queue sidecar manager (behavioural spec: reference
-vantage6/cli/rabbitmq/queue_manager.py:25-238).
+"""The message-queue sidecar of a server.
 
-Purpose (reference vantage6/cli/server.py:267-268): without a message queue "the server
-application cannot scale horizontally" -- several server processes must share events.  The
-reference starts a RabbitMQ container; here the sidecar is an in-box ZeroMQ forwarder process
-(server/mq_broker.py) managed by the process runtime with the same lifecycle: definitions +
-config written into the server data dir, persistent dir ``<data>/rabbitmq``, label
-``vantage6-type=rabbitmq``, name ``vantage6-{name}-rabbitmq``, restart policy "always", start-up
-poll every 10 s up to ``RABBIT_TIMEOUT`` (300 s) then ``exit(1)``.
+Why it exists (reference vantage6/cli/server.py:267-268): without a message queue "the server application
+cannot scale horizontally" -- several server processes must see each other's events.  The reference runs a
+RabbitMQ container next to the server; here the sidecar is the in-box ZeroMQ forwarder
+(``v6-mq-broker``, server/mq_broker.py) run by the process runtime, with the lifecycle the reference gives
+its container (vantage6/cli/rabbitmq/queue_manager.py:25-238):
+
+* ``amqp://user:password@host:port/vhost`` from the ``rabbitmq_uri`` configuration key says who / where;
+* ``definitions.json`` (one administrator with a salted-SHA256 password hash, one vhost, full permissions) and
+  ``rabbitmq.config`` are written into the server's data directory and handed to the sidecar read-only, next to
+  a persistent ``<data>/rabbitmq`` directory;
+* the sidecar is called ``vantage6-{name}-rabbitmq``, labelled ``vantage6-type=rabbitmq``, restarted always, and
+  gets ``RABBIT_TIMEOUT`` seconds (polled every ``INTERVAL``) to answer a status probe before the CLI gives up
+  with exit code 1.
 """
 from __future__ import annotations
 
@@ -18,6 +23,7 @@ import json
 import os
 import shutil
 import time
+from dataclasses import dataclass
 from pathlib import Path
 from typing import Dict
 
@@ -31,51 +37,71 @@ from .definitions import RABBITMQ_DEFINITIONS
 DEFAULT_RABBIT_IMAGE = "harbor2.vantage6.ai/infrastructure/rabbitmq"
 RABBIT_CONFIG = "rabbitmq.config"
 RABBIT_DIR = "rabbitmq"
+_SALT_BYTES = 4                                 # RabbitMQ salts its password hashes with 32 bits
+_INSIDE = {"definitions": "/etc/rabbitmq/definitions.json", "config": f"/etc/rabbitmq/{RABBIT_CONFIG}",
+           "data": "/var/lib/rabbitmq"}
+
+
+@dataclass(frozen=True)
+class QueueAddress:
+    user: str
+    password: str
+    host: str
+    port: str
+    vhost: str
+
+    @classmethod
+    def parse(cls, uri: str) -> "QueueAddress":
+        """``amqp://$user:$pass@$host:$port/$vhost``; the password may itself contain ``:``."""
+        credentials, _, location = uri.partition("@")
+        user, _, password = credentials.rsplit("/", 1)[-1].partition(":")
+        host, _, rest = location.partition(":")
+        port, _, vhost = rest.partition("/")
+        return cls(user, password, host, port, vhost)
 
 
 def split_rabbitmq_uri(rabbit_uri: str) -> Dict[str, str]:
-    """``amqp://$user:$pass@$host:$port/$vhost`` -> its parts."""
-    user_details, location_details = rabbit_uri.split("@", 1)
-    user, password = user_details.split("/")[-1].split(":", 1)
-    host, remainder = location_details.split(":", 1)
-    port, vhost = remainder.split("/", 1)
-    return {"user": user, "password": password, "host": host, "port": port, "vhost": vhost}
+    """The parts of a queue URI as a plain dict (``user password host port vhost``)."""
+    return dict(QueueAddress.parse(rabbit_uri).__dict__)
 
 
 class RabbitMQManager:
-    """Manages the message-queue sidecar process."""
+    """Writes the sidecar's files, starts it on the server's network and waits until it answers."""
 
-    INTERVAL = 10
+    INTERVAL = 10           # seconds between status probes while waiting for the sidecar
 
     def __init__(self, ctx, network_mgr: NetworkManager, image: str = None) -> None:
         self.ctx = ctx
-        self.queue_uri = self.ctx.config.get("rabbitmq_uri")
-        parts = split_rabbitmq_uri(self.queue_uri)
-        self.rabbit_user, self.rabbit_pass = parts["user"], parts["password"]
-        self.vhost, self.port, self.host = parts["vhost"], parts["port"], parts["host"]
-        self.definitions_file = Path(self.ctx.data_dir / "definitions.json")
         self.network_mgr = network_mgr
+        self.queue_uri = ctx.config.get("rabbitmq_uri")
+        address = QueueAddress.parse(self.queue_uri)
+        self.rabbit_user, self.rabbit_pass = address.user, address.password
+        self.host, self.port, self.vhost = address.host, address.port, address.vhost
+        self.image = image or DEFAULT_RABBIT_IMAGE
         self.docker = docker.from_env()
-        self.image = image if image else DEFAULT_RABBIT_IMAGE
         self.rabbit_container_name = f"{APPNAME}-{ctx.name}-rabbitmq"
+        self.definitions_file = Path(ctx.data_dir / "definitions.json")
 
+    # -------------------------------------------------------------------------------- lifecycle
     def start(self) -> None:
         volumes = self._get_volumes()
-        ports = {f"{self.port}/tcp": self.port, "15672/tcp": 8080}
-        # a sidecar left over from a previous run is replaced
-        remove_container_if_exists(docker_client=self.docker, name=self.rabbit_container_name)
+        remove_container_if_exists(docker_client=self.docker, name=self.rabbit_container_name)     # stale sidecar
+        command = (f"v6-mq-broker serve --port {self.port} --definitions {_INSIDE['definitions']} "
+                   f"--data {_INSIDE['data']}")
         self.rabbit_container = self.docker.containers.run(
-            name=self.rabbit_container_name, image=self.image,
-            command=f"v6-mq-broker serve --port {self.port} --definitions /etc/rabbitmq/definitions.json "
-                    f"--data /var/lib/rabbitmq",
-            volumes=volumes, ports=ports, detach=True, restart_policy={"Name": "always"},
-            hostname=f"{APPNAME}-{self.ctx.name}-rabbitmq", labels={f"{APPNAME}-type": "rabbitmq"},
-            network=self.network_mgr.network_name, auto_remove=False)
+            image=self.image, name=self.rabbit_container_name, hostname=self.rabbit_container_name, command=command,
+            volumes=volumes, ports={f"{self.port}/tcp": self.port, "15672/tcp": 8080}, detach=True, auto_remove=False,
+            restart_policy={"Name": "always"}, labels={f"{APPNAME}-type": "rabbitmq"},
+            network=self.network_mgr.network_name)
         self._wait_for_startup()
 
+    def is_running(self) -> bool:
+        probe = self.rabbit_container.exec_run(cmd=f"rabbitmqctl status --formatter json --port {self.port}")
+        return probe.exit_code == 0
+
     def _wait_for_startup(self) -> None:
-        attempts = int((RABBIT_TIMEOUT + self.INTERVAL) / self.INTERVAL)
-        for _ in range(attempts):
+        deadline_probes = int((RABBIT_TIMEOUT + self.INTERVAL) / self.INTERVAL)
+        for _ in range(deadline_probes):
             if self.is_running():
                 info("RabbitMQ was started successfully!")
                 return
@@ -84,40 +110,41 @@ class RabbitMQManager:
         error("Could not start RabbitMQ! Exiting...")
         exit(1)
 
-    def is_running(self) -> bool:
-        response = self.rabbit_container.exec_run(cmd=f"rabbitmqctl status --formatter json --port {self.port}")
-        return response.exit_code == 0
-
+    # ---------------------------------------------------------------------------- files on disk
     def _get_volumes(self) -> Dict:
-        Path(self.ctx.data_dir).mkdir(parents=True, exist_ok=True)
-        with open(self.definitions_file, "w") as f:
-            json.dump(self._get_rabbitmq_definitions(), f, indent=2)
-        shutil.copyfile(Path(__file__).parent.resolve() / RABBIT_CONFIG, self.ctx.data_dir / RABBIT_CONFIG)
-        rabbit_data_dir = self.ctx.data_dir / RABBIT_DIR
-        rabbit_data_dir.mkdir(parents=True, exist_ok=True)
-        return {
-            self.definitions_file: {"bind": "/etc/rabbitmq/definitions.json", "mode": "ro"},
-            self.ctx.data_dir / RABBIT_CONFIG: {"bind": "/etc/rabbitmq/rabbitmq.config", "mode": "ro"},
-            rabbit_data_dir: {"bind": "/var/lib/rabbitmq", "mode": "rw"},
-        }
+        """Write definitions + config into the data directory; returns the bind specification."""
+        data_dir = Path(self.ctx.data_dir)
+        data_dir.mkdir(parents=True, exist_ok=True)
+        self.definitions_file.write_text(json.dumps(self._get_rabbitmq_definitions(), indent=2))
+        config_copy = data_dir / RABBIT_CONFIG
+        shutil.copyfile(Path(__file__).resolve().with_name(RABBIT_CONFIG), config_copy)
+        state_dir = data_dir / RABBIT_DIR
+        state_dir.mkdir(parents=True, exist_ok=True)
+        return {self.definitions_file: {"bind": _INSIDE["definitions"], "mode": "ro"},
+                config_copy: {"bind": _INSIDE["config"], "mode": "ro"},
+                state_dir: {"bind": _INSIDE["data"], "mode": "rw"}}
 
     def _get_rabbitmq_definitions(self) -> Dict:
-        d = copy.deepcopy(RABBITMQ_DEFINITIONS)
-        d["users"][0]["name"] = self.rabbit_user
-        d["permissions"][0]["user"] = self.rabbit_user
-        d["users"][0]["password_hash"] = self._get_hashed_pw(self.rabbit_pass)
-        d["vhosts"][0]["name"] = self.vhost
-        d["permissions"][0]["vhost"] = self.vhost
-        return d
+        """The definitions template with this queue's user, password hash and vhost filled in."""
+        doc = copy.deepcopy(RABBITMQ_DEFINITIONS)
+        (admin,), (vhost,), (grant,) = doc["users"], doc["vhosts"], doc["permissions"]
+        admin.update(name=self.rabbit_user, password_hash=self._get_hashed_pw(self.rabbit_pass))
+        vhost.update(name=self.vhost)
+        grant.update(user=self.rabbit_user, vhost=self.vhost)
+        return doc
 
+    # -------------------------------------------------------------------------- password hashing
     @staticmethod
-    def _get_hashed_pw(pw: str) -> str:
-        """RabbitMQ's salted SHA-256: b64(salt || sha256(salt || utf8(pw))) with a 32-bit salt."""
-        salt = os.urandom(4)
-        digest = hashlib.sha256(salt + pw.encode("utf-8")).digest()
-        return base64.b64encode(salt + digest).decode("utf-8")
+    def _digest(salt: bytes, pw: str) -> bytes:
+        return hashlib.sha256(salt + pw.encode("utf-8")).digest()
 
-    @staticmethod
-    def check_pw(pw: str, hashed: str) -> bool:
+    @classmethod
+    def _get_hashed_pw(cls, pw: str) -> str:
+        """RabbitMQ's ``rabbit_password_hashing_sha256``: base64(salt || sha256(salt || utf8(pw)))."""
+        salt = os.urandom(_SALT_BYTES)
+        return base64.b64encode(salt + cls._digest(salt, pw)).decode("utf-8")
+
+    @classmethod
+    def check_pw(cls, pw: str, hashed: str) -> bool:
         raw = base64.b64decode(hashed)
-        return hashlib.sha256(raw[:4] + pw.encode("utf-8")).digest() == raw[4:]
+        return cls._digest(raw[:_SALT_BYTES], pw) == raw[_SALT_BYTES:]
