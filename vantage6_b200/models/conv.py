@@ -29,7 +29,7 @@ class _ShadowConvFn(torch.autograd.Function):
         y = torch.ops.aten.convolution(x, w_bf16, None, stride, padding, (1, 1), False, (0, 0), 1)
         ctx.save_for_backward(x, w_bf16)
         ctx.conf = (stride, padding)
-        ctx.sink, ctx.offset, ctx.weight = sink, offset, weight
+        ctx.sink, ctx.offset = sink, offset
         return y
 
     @staticmethod
