@@ -314,3 +314,42 @@ def test_stock_optimizer_arm_matches_fused_arm_in_delta_mode():
     assert a[-1] < a[0] - 0.3                     # the (fixed, synthetic) shard is being fitted
     for x, y in zip(a, b):
         assert abs(x - y) < 5e-3, (a, b)
+
+
+def test_lora_linear_single_node_matches_composed_expression():
+    """_LoRALinearFn (base GEMM + x A^T + fused addmm, hand-written backward) == x W^T + s (x A^T) B^T."""
+    import torch
+
+    from vantage6_b200.models.transformer import LoRALinear
+
+    torch.manual_seed(0)
+    m = LoRALinear(32, 48, r=4, alpha=8.0)
+    with torch.no_grad():
+        m.lora_B.normal_(0, 0.1)
+    x = torch.randn(5, 7, 32, requires_grad=True)
+    y = m(x)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    W = m.base.weight_bf16.float()
+    A = m.lora_A.detach().clone().requires_grad_()
+    B = m.lora_B.detach().clone().requires_grad_()
+    xr = x.detach().clone().requires_grad_()
+    (xr @ W.t() + m.scaling * (xr @ A.t()) @ B.t()).backward(dy)
+    torch.testing.assert_close(x.grad, xr.grad, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(m.lora_A.grad, A.grad, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(m.lora_B.grad, B.grad, rtol=1e-5, atol=1e-5)
+
+
+def test_swiglu_cpu_fallback_and_frozen_norm_weights():
+    import torch
+
+    from vantage6_b200.ops.act import swiglu
+    from vantage6_b200.ops.norm import rms_norm
+
+    g, u = torch.randn(4, 16), torch.randn(4, 16)
+    torch.testing.assert_close(swiglu(g, u), torch.nn.functional.silu(g) * u)
+    w = torch.nn.Parameter(torch.ones(16), requires_grad=False)
+    x = torch.randn(4, 16, requires_grad=True)
+    y, _ = rms_norm(x, w, 1e-5)
+    y.sum().backward()
+    assert x.grad is not None and w.grad is None

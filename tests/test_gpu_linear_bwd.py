@@ -87,3 +87,41 @@ def test_bert_tiny_fused_arm_matches_stock_arm(dev):
     a, b = run(True), run(False)
     assert abs(a[0] - b[0]) < 0.05, (a, b)
     assert a[-1] < a[0] and abs(a[-1] - b[-1]) < 0.3, (a, b)
+
+
+@pytest.mark.parametrize("shape", [(1024, 14336), (37, 64), (8, 8)])
+def test_swiglu_kernels(dev, shape):
+    from vantage6_b200.ops.act import swiglu
+
+    torch.manual_seed(3)
+    g = (torch.randn(*shape, device=dev) * 2).to(torch.bfloat16).requires_grad_()
+    u = torch.randn(*shape, device=dev).to(torch.bfloat16).requires_grad_()
+    h = swiglu(g, u)
+    dh = torch.randn_like(h)
+    h.backward(dh)
+    gf, uf = g.detach().float().requires_grad_(), u.detach().float().requires_grad_()
+    hr = torch.nn.functional.silu(gf) * uf
+    hr.backward(dh.float())
+    torch.testing.assert_close(h.float(), hr, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(g.grad.float(), gf.grad, rtol=3e-2, atol=3e-2)
+    torch.testing.assert_close(u.grad.float(), uf.grad, rtol=3e-2, atol=3e-2)
+
+
+def test_llama_tiny_fused_arm_matches_stock_arm(dev):
+    """LoRA adapters through _LoRALinearFn (bf16 shadows + gradient sink), fused SwiGLU, frozen RMSNorm weights."""
+    from vantage6_b200.models import zoo
+
+    def run(fused):
+        torch.manual_seed(31)
+        tr, spec = zoo.build_trainer("llama_tiny_lora", rank=0, world=1, device=dev,
+                                     data_plane="auto" if fused else "collective", fused_local_optimizer=fused,
+                                     use_cuda_graph=fused)
+        batches = [(x.to(dev), y.to(dev)) for x, y in spec.make_batches(2, 2, 78)]
+        tr.initialize_global()
+        losses = [float(tr.run_round(batches).item()) for _ in range(5)]
+        tr.close()
+        return losses
+
+    a, b = run(True), run(False)
+    assert abs(a[0] - b[0]) < 0.05, (a, b)
+    assert a[-1] < a[0] and abs(a[-1] - b[-1]) < 0.3, (a, b)

@@ -17,6 +17,7 @@ import torch
 from torch import nn
 
 from ..ops import rope as R
+from ..ops.act import swiglu
 from .transformer import FrozenLinear, FusedRMSNorm, LoRALinear, attention
 
 
@@ -65,7 +66,7 @@ class LlamaLayer(nn.Module):
         a = attention(q, k, v, causal=True).reshape(B, S, -1)
         h = self.o(a)
         x, stream = self.norm2(h, residual=stream)
-        h = self.down(torch.nn.functional.silu(self.gate(x)) * self.up(x))
+        h = self.down(swiglu(self.gate(x), self.up(x)))        # one fused kernel each way (ops/act.py)
         return h, stream
 
 

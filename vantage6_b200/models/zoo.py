@@ -83,10 +83,10 @@ def _specs() -> Dict[str, ModelSpec]:
         "bert_tiny": ModelSpec("bert_tiny", lambda d: bert.bert_tiny(), bert.bert_forward_loss, _mlm_batches(512, 32),
                                "adamw", 1e-3, "delta_bf16", True, False, 2, 4, dict(weight_decay=0.01)),
         "llama3_8b_lora": ModelSpec("llama3_8b_lora", lambda d: llama.llama3_8b_lora(d), llama.llama_forward_loss,
-                                    _lm_batches(128256, 1024), "adamw", 2e-4, "delta_bf16", False, False, 2, 1,
+                                    _lm_batches(128256, 1024), "adamw", 2e-4, "delta_bf16", True, False, 2, 1,
                                     dict(weight_decay=0.0, max_grad_norm=1.0, include_buffers=False)),
         "llama_tiny_lora": ModelSpec("llama_tiny_lora", lambda d: llama.llama_tiny_lora(d), llama.llama_forward_loss,
-                                     _lm_batches(512, 32), "adamw", 1e-3, "delta_bf16", False, False, 2, 2,
+                                     _lm_batches(512, 32), "adamw", 1e-3, "delta_bf16", True, False, 2, 2,
                                      dict(weight_decay=0.0, include_buffers=False)),
     }
 

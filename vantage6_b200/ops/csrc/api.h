@@ -127,6 +127,8 @@ int v6_stem_weight_s2d(const void* w, int w_is_bf16, void* ws, int O, cudaStream
 int v6_stem_wgrad_d2s(const void* dws, float* dw, int O, int accumulate, cudaStream_t s);
 int v6_bias_act_bwd(const void* dy, const void* pre, void* dpre, float* db, float* scratch, long long R, int C, int act_kind,
                     int accumulate, cudaStream_t s);
+int v6_swiglu_fwd(const void* g, const void* u, void* h, long long n, cudaStream_t s);
+int v6_swiglu_bwd(const void* dh, const void* g, const void* u, void* dg, void* du, long long n, cudaStream_t s);
 long long v6_bn_scratch_floats();
 int v6_multi_accum_bf16(const MultiAccumParams* p, float* dst, cudaStream_t s);
 int v6_bn_fwd(const void* x, const void* res, const float* gamma, const float* beta, float* running_mean, float* running_var,

@@ -182,6 +182,12 @@ PYBIND11_MODULE(_C, m) {
         check(v6_bias_act_bwd(P<void>(dy), P<void>(pre), P<void>(dpre), P<float>(db), P<float>(scratch), R, C, act, accumulate, S(s)),
               "bias_act_bwd");
     });
+    m.def("swiglu_fwd", [](u64 g, u64 u, u64 h, long long n, u64 s) {
+        check(v6_swiglu_fwd(P<void>(g), P<void>(u), P<void>(h), n, S(s)), "swiglu_fwd");
+    });
+    m.def("swiglu_bwd", [](u64 dh, u64 g, u64 u, u64 dg, u64 du, long long n, u64 s) {
+        check(v6_swiglu_bwd(P<void>(dh), P<void>(g), P<void>(u), P<void>(dg), P<void>(du), n, S(s)), "swiglu_bwd");
+    });
     m.def("bn_fwd", [](u64 x, u64 res, u64 gamma, u64 beta, u64 rmean, u64 rvar, u64 nbt, u64 y, u64 mask, u64 mean, u64 rstd,
                        u64 scale_bias, u64 scratch, long long R, int C, float eps, float momentum, bool relu, u64 s) {
         check(v6_bn_fwd(P<void>(x), P<void>(res), P<float>(gamma), P<float>(beta), P<float>(rmean), P<float>(rvar),

@@ -292,7 +292,8 @@ static int launch_bwd(const void* dy, const void* x_in, const void* dres, const 
                                                 (T*)dx, pg, pb, rows, cols);
     });
     V6_CHECK_LAUNCH();
-    norm_param_grad_fold<<<dim3((cols + 31) / 32, RMS ? 1 : 2), 256, 0, s>>>(pg, pb, dgamma, dbeta, grid, cols, accumulate);
+    if (dgamma)      // frozen norm weights (LoRA fine-tuning): nothing to fold
+        norm_param_grad_fold<<<dim3((cols + 31) / 32, RMS ? 1 : 2), 256, 0, s>>>(pg, pb, dgamma, dbeta, grid, cols, accumulate);
     V6_CHECK_LAUNCH();
     return 0;
 }

@@ -73,20 +73,21 @@ class _LayerNormFn(torch.autograd.Function):
         pg, pb = ctx.params
         direct = all(p is None or (p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous())
                      for p in ((pg,) if ctx.rms else (pg, pb))) and pg is not None and (ctx.rms or pb is not None)
-        dgamma = pg.grad if direct else torch.empty_like(gamma)
-        dbeta = None if ctx.rms else (pb.grad if direct else torch.empty_like(gamma))
+        frozen = pg is not None and not pg.requires_grad and (ctx.rms or pb is None or not pb.requires_grad)
+        dgamma = None if frozen else (pg.grad if direct else torch.empty_like(gamma))
+        dbeta = None if (ctx.rms or frozen) else (pb.grad if direct else torch.empty_like(gamma))
         scratch = _get_scratch(x_in.device, cols)
         bf16 = x_in.dtype == torch.bfloat16
         C = native()
         if ctx.rms:
             C.rmsnorm_bwd(dy2.data_ptr(), x_in.data_ptr(), _ptr(dres2), gamma.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
-                          dgamma.data_ptr(), scratch.data_ptr(), _SCRATCH_PARTS, rows, cols, direct, bf16, stream_ptr())
+                          _ptr(dgamma), scratch.data_ptr(), _SCRATCH_PARTS, rows, cols, direct, bf16, stream_ptr())
         else:
             C.layernorm_bwd(dy2.data_ptr(), x_in.data_ptr(), _ptr(dres2), gamma.data_ptr(), mean.data_ptr(),
-                            rstd.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), scratch.data_ptr(),
+                            rstd.data_ptr(), dx.data_ptr(), _ptr(dgamma), _ptr(dbeta), scratch.data_ptr(),
                             _SCRATCH_PARTS, rows, cols, direct, bf16, stream_ptr())
         dxv = dx.view(ctx.shape)
-        if direct:
+        if direct or frozen:
             return dxv, None, None, (dxv if ctx.has_res else None), None, None
         return dxv, dgamma, (dbeta if ctx.has_beta else None), (dxv if ctx.has_res else None), None, None
 
