@@ -201,3 +201,20 @@ def test_silent_nodes_are_marked_offline(server):
     assert app.db.get("node", node.node_id)["status"] == "offline"
     node.request(f"node/{node.node_id}", method="patch", json={"status": "online"})        # next heartbeat revives it
     assert app.db.get("node", node.node_id)["status"] == "online"
+
+
+def test_database_refuses_non_identifier_columns(tmp_path):
+    """Table / column names are the only things interpolated into SQL: they must be known / plain identifiers."""
+    import pytest
+
+    from vantage6_b200.server.db import Database
+
+    db = Database(f"sqlite:///{tmp_path}/t.sqlite")
+    oid = db.insert("organization", name="o")
+    with pytest.raises(ValueError):
+        db.update("organization", oid, **{"name=?, domain": "x"})
+    with pytest.raises(ValueError):
+        db.insert("organization; DROP TABLE user", name="x")
+    db.update("organization", oid, name="renamed")
+    assert db.get("organization", oid)["name"] == "renamed"
+    db.close()

@@ -124,17 +124,23 @@ class Database:
         rows = self.query(sql, args)
         return rows[0] if rows else None
 
+    @staticmethod
+    def _columns(table: str, fields: Dict[str, Any]) -> List[str]:
+        """Table and column names are interpolated into SQL (values never are): only known tables and plain
+        identifiers get through."""
+        if table not in TABLES or not all(isinstance(k, str) and k.isidentifier() for k in fields):
+            raise ValueError(f"refusing SQL identifiers {table!r} / {sorted(fields)!r}")
+        return list(fields)
+
     def insert(self, table: str, **fields) -> int:
-        assert table in TABLES
-        keys = list(fields)
+        keys = self._columns(table, fields)
         sql = f"INSERT INTO {table} ({','.join(keys)}) VALUES ({','.join('?' * len(keys))})"
         with self._lock:
             cur = self._conn.execute(sql, [fields[k] for k in keys])
             return int(cur.lastrowid)
 
     def update(self, table: str, id_: int, **fields) -> None:
-        assert table in TABLES
-        if not fields:
+        if not self._columns(table, fields):
             return
         sets = ",".join(f"{k}=?" for k in fields)
         self.execute(f"UPDATE {table} SET {sets} WHERE id=?", list(fields.values()) + [id_])
