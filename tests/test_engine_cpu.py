@@ -353,3 +353,40 @@ def test_swiglu_cpu_fallback_and_frozen_norm_weights():
     y, _ = rms_norm(x, w, 1e-5)
     y.sum().backward()
     assert x.grad is not None and w.grad is None
+
+
+def test_bias_act_backward_reference_path_and_token_stride_detection():
+    import torch
+
+    from vantage6_b200.ops import attention as A
+    from vantage6_b200.ops import gemm as G
+
+    torch.manual_seed(4)
+    dy, pre = torch.randn(6, 64), torch.randn(6, 64)
+    bias = torch.nn.Parameter(torch.zeros(64))
+    for act in (G.ACT_NONE, G.ACT_GELU, G.ACT_RELU):
+        p = pre.clone().requires_grad_()
+        y = {G.ACT_NONE: lambda t: t, G.ACT_GELU: torch.nn.functional.gelu, G.ACT_RELU: torch.relu}[act](p)
+        y.backward(dy)
+        dpre, db = G.bias_act_backward(dy, pre, act, bias)
+        torch.testing.assert_close(dpre, p.grad, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(db, p.grad.sum(0), rtol=1e-4, atol=1e-5)
+    # packed QKV slices are token-strided views that the attention kernels can read in place
+    qkv = torch.zeros(2, 16, 3, 4, 8, dtype=torch.bfloat16)
+    q, ld = A._token_strided(qkv[:, :, 0])
+    assert ld == 3 * 4 * 8 and q.data_ptr() == qkv.data_ptr()
+    k, ld = A._token_strided(qkv[:, :, 1].transpose(1, 2).transpose(1, 2))
+    assert ld == 3 * 4 * 8
+    odd, ld = A._token_strided(torch.zeros(2, 16, 4, 9, dtype=torch.bfloat16)[..., :8])     # head dim not dense
+    assert ld == 4 * 8 and odd.is_contiguous()
+
+
+def test_packed_attention_falls_back_off_gpu():
+    import torch
+
+    from vantage6_b200.models.transformer import attention, packed_attention
+
+    torch.manual_seed(5)
+    qkv = torch.randn(2, 8, 3, 2, 16)
+    ref = attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], causal=False)
+    torch.testing.assert_close(packed_attention(qkv, causal=False), ref)
