@@ -1,0 +1,29 @@
+"""Opt-in tests of kernels that are in the tree but have not been validated on hardware yet (they are not used
+unless their environment switch is set).  Run with ``V6B200_EXPERIMENTAL=1 python -m pytest tests -m gpu -k experimental``."""
+import os
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("V6B200_EXPERIMENTAL") != "1", reason="set V6B200_EXPERIMENTAL=1")]
+
+
+@pytest.mark.parametrize("rows", [128, 1000, 125_000])
+def test_experimental_glm_tensor_core_kernel(rows, monkeypatch):
+    from vantage6_b200.ops import glm as K8
+    from vantage6_b200.ops import native
+
+    native()
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    X = torch.randn(rows, 256, device=dev).to(torch.bfloat16)
+    y = (torch.rand(rows, device=dev) < 0.4).float()
+    w = torch.randn(257, device=dev) * 0.1
+    ref = K8.reference_logistic_grad(X, y, w)
+    monkeypatch.setenv("V6B200_GLM", "tc")
+    out = K8.logistic_grad(X, y, w)
+    torch.cuda.synchronize()
+    scale = ref[:256].abs().max().item()
+    assert (out[:256] - ref[:256]).abs().max().item() < 2e-2 * scale
+    torch.testing.assert_close(out[256:259], ref[256:259], rtol=2e-3, atol=2e-2)

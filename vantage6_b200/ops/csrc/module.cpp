@@ -210,6 +210,11 @@ PYBIND11_MODULE(_C, m) {
     m.def("rope", [](u64 q, u64 k, u64 cos_t, u64 sin_t, u64 pos, int B, int Sq, int Hq, int Hkv, int D, bool inverse, u64 s) {
         check(v6_rope(P<void>(q), P<void>(k), P<float>(cos_t), P<float>(sin_t), P<int>(pos), B, Sq, Hq, Hkv, D, inverse, S(s)), "rope");
     });
+    m.def("glm_logistic_grad_tc", [](u64 X, u64 y, u64 w, u64 part, int max_parts, u64 out, int rows, int F, u64 s) {
+        const int grid = v6_glm_logistic_grad_tc(P<void>(X), P<float>(y), P<float>(w), P<float>(part), max_parts, rows, F, S(s));
+        if (grid < 1) throw std::runtime_error("glm_logistic_grad_tc failed (" + std::to_string(grid) + ")");
+        check(v6_glm_fold(P<float>(part), P<float>(out), grid, F, rows, S(s)), "glm_fold");
+    });
     m.def("glm_logistic_grad", [](u64 X, u64 y, u64 w, u64 part, int max_parts, u64 out, int rows, int F, bool bf16, u64 s) {
         check(v6_glm_logistic_grad(P<void>(X), P<float>(y), P<float>(w), P<float>(part), max_parts, P<float>(out), rows, F, bf16, S(s)),
               "glm_logistic_grad");

@@ -223,6 +223,13 @@ static int launch_glm(const void* X, const float* y, const float* w, float* part
     return 0;
 }
 
+// out = [sum of the partials (F + 2), n_rows]; used by the experimental tensor-core path (glm_tc.cu)
+extern "C" int v6_glm_fold(const float* part, float* out, int nparts, int F, int rows, cudaStream_t s) {
+    glm_fold_kernel<<<(F + 3 + 255) / 256, 256, 0, s>>>(part, out, nparts, F, (float)rows);
+    V6_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int v6_glm_logistic_grad(const void* X, const float* y, const float* w, float* part,
                                     int max_parts, float* out, int rows, int F, int bf16, cudaStream_t s) {
     if (F % 64 != 0 || F > 512) return (int)cudaErrorInvalidValue;

@@ -6,6 +6,7 @@ that is handed unchanged to the K3 small-message all-reduce: the federated GLM u
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -28,11 +29,22 @@ def logistic_grad(X: torch.Tensor, y: torch.Tensor, w: torch.Tensor, out: Option
     if X.is_cuda:
         if scratch is None:
             scratch = torch.empty(_MAX_PARTS * (F + 2), device=X.device, dtype=torch.float32)
-        native().glm_logistic_grad(X.data_ptr(), y.data_ptr(), w.data_ptr(), scratch.data_ptr(), _MAX_PARTS,
-                                   out.data_ptr(), rows, F, X.dtype == torch.bfloat16, stream_ptr())
+        if _tensor_core_path(X):     # experimental UMMA formulation (csrc/glm_tc.cu), opt-in
+            native().glm_logistic_grad_tc(X.data_ptr(), y.data_ptr(), w.data_ptr(), scratch.data_ptr(), _MAX_PARTS,
+                                          out.data_ptr(), rows, F, stream_ptr())
+        else:
+            native().glm_logistic_grad(X.data_ptr(), y.data_ptr(), w.data_ptr(), scratch.data_ptr(), _MAX_PARTS,
+                                       out.data_ptr(), rows, F, X.dtype == torch.bfloat16, stream_ptr())
     else:
         out[: F + 3] = reference_logistic_grad(X, y, w)
     return out
+
+
+def _tensor_core_path(X: torch.Tensor) -> bool:
+    """``V6B200_GLM=tc`` selects the tcgen05 kernel (F == 256, bf16, 16-byte aligned rows); not validated on
+    hardware yet, hence off by default."""
+    return (os.environ.get("V6B200_GLM") == "tc" and X.dtype == torch.bfloat16 and X.shape[1] == 256 and X.is_contiguous()
+            and hasattr(native(), "glm_logistic_grad_tc"))
 
 
 def reference_logistic_grad(X, y, w):
