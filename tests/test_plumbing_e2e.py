@@ -123,3 +123,21 @@ def test_node_restart_picks_up_missed_task(network):
     assert r.exit_code == 0, r.output
     res = c.wait_for_results(task["id"], timeout=120)
     assert res[0]["result"]["count"] == 70
+
+
+def test_kill_request_targets_only_the_named_task():
+    """A ``kill_containers`` event for task T ends T's algorithm processes and leaves the others running."""
+    from types import SimpleNamespace
+    from unittest.mock import MagicMock
+
+    from vantage6_b200.node import Node
+
+    ctx = SimpleNamespace(config={"server_url": "http://127.0.0.1", "port": 1, "api_path": "/api", "api_key": "k"})
+    node = Node(ctx)
+    procs = {rid: MagicMock(pid=10_000_000 + rid) for rid in (1, 2, 3)}       # pids that do not exist
+    node.running.update(procs)
+    node._task_of.update({1: 7, 2: 8, 3: 7})
+    node.kill_task(7)
+    assert procs[1].kill.called and procs[3].kill.called and not procs[2].kill.called
+    node.kill_task()
+    assert procs[2].kill.called

@@ -67,7 +67,8 @@ class Node:
         self.client = NodeClient(self.config["server_url"], self.config.get("port"), self.config.get("api_path", "/api"))
         self.proxy = ProxyServer(self)
         self.queue: "queue.Queue[dict]" = queue.Queue()
-        self.running: Dict[int, subprocess.Popen] = {}
+        self.running: Dict[int, subprocess.Popen] = {}           # result id -> algorithm process
+        self._task_of: Dict[int, int] = {}                          # result id -> task id (for kill requests)
         self._seen: set = set()
         self._stop = threading.Event()
         self._threads = []
@@ -237,6 +238,7 @@ class Node:
             proc = subprocess.Popen([sys.executable, "-m", "vantage6_b200.algorithm.wrapper", module],
                                     stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, start_new_session=True)
             self.running[rid] = proc
+            self._task_of[rid] = task["id"]
             out, _ = proc.communicate(timeout=float(self.config.get("task_timeout_s", 3600)))
             logtxt = out.decode("utf-8", errors="replace")
             if proc.returncode == 0:
@@ -254,6 +256,7 @@ class Node:
             logtxt += f"\n[node] failed to run algorithm: {e!r}"
         finally:
             self.running.pop(rid, None)
+            self._task_of.pop(rid, None)
         try:
             self.client.request(f"result/{rid}", method="patch",
                                 json={"finished_at": _now(), "result": out_b64, "log": logtxt[-20000:], "status": status})
@@ -273,9 +276,11 @@ class Node:
             except Exception:  # noqa: BLE001
                 pass
 
-    def kill_task(self, task_id) -> None:
+    def kill_task(self, task_id=None) -> None:
+        """Kill the algorithm processes of ``task_id`` (all of them when no task is named)."""
         for rid, proc in list(self.running.items()):
-            self._kill_proc(proc)
+            if task_id is None or self._task_of.get(rid) == task_id:
+                self._kill_proc(proc)
 
     # ------------------------------------------------------------------ lifecycle
     def start(self, block: bool = True) -> None:
