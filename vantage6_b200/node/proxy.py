@@ -22,6 +22,10 @@ from ..common import base64s_to_bytes
 log = logging.getLogger("proxy")
 
 
+class _DaemonHTTPServer(ThreadingHTTPServer):
+    daemon_threads = True          # request threads must not keep a stopping node alive
+
+
 class ProxyServer:
     def __init__(self, node):
         self.node = node
@@ -65,8 +69,7 @@ class ProxyServer:
             def do_DELETE(self):
                 self._serve("DELETE")
 
-        ThreadingHTTPServer.daemon_threads = True
-        self._httpd = ThreadingHTTPServer(("127.0.0.1", 0), Handler)
+        self._httpd = _DaemonHTTPServer(("127.0.0.1", 0), Handler)
         self.port = self._httpd.server_address[1]
         threading.Thread(target=self._httpd.serve_forever, kwargs={"poll_interval": 0.2}, daemon=True).start()
         log.info("proxy server listening on 127.0.0.1:%s", self.port)

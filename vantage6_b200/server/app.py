@@ -37,6 +37,11 @@ from .db import Database, check_password, hash_password, now
 
 log = logging.getLogger("server")
 
+
+class _ApiHTTPServer(ThreadingHTTPServer):
+    daemon_threads = True          # request threads must not keep a stopping server alive
+    request_queue_size = 128       # 8 nodes x (heartbeat + long-poll + proxy traffic) connect in bursts
+
 SCOPES = ["own", "organization", "collaboration", "global"]
 OPERATIONS = ["view", "create", "edit", "delete"]
 RESOURCES = ["user", "organization", "collaboration", "role", "node", "task", "result", "port", "event"]
@@ -899,9 +904,7 @@ class ServerApp:
     def start(self, ip: str = "127.0.0.1", port: int = 5000, block: bool = False) -> int:
         """Serve; returns the bound port (``port=0`` picks a free one)."""
         threading.Thread(target=lambda: (time.sleep(1.0), self._reaper_loop()), daemon=True).start()
-        ThreadingHTTPServer.daemon_threads = True
-        ThreadingHTTPServer.request_queue_size = 128
-        self._httpd = ThreadingHTTPServer((ip, port), self.make_handler())
+        self._httpd = _ApiHTTPServer((ip, port), self.make_handler())
         bound = self._httpd.server_address[1]
         log.info("vantage6-b200 server %s listening on http://%s:%s%s", __version__, ip, bound, self.api_path)
         if block:
