@@ -17,7 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 KEY = re.compile(r"UTC\w*MMA\w*|LDTM|STTM|UTMALDG|UTMASTG|UBLKCP|UTCBAR|UTCATOMSWS|LDGMC|MULTIMEM|SYNCS|HMMA|REDG|ATOMG|LDG|STG|MEMBAR|CCTL|ERRBAR")
-FULL = ("gemm_bf16_kernel", "gemm2_bf16_kernel", "fedavg_round_kernel", "small_allreduce_kernel", "flash_fwd_kernel")
+FULL = ("gemm_bf16_kernel", "gemm2_bf16_kernel", "fedavg_round_kernel", "small_allreduce_kernel", "flash_fwd_kernel", "flash_fwd2_kernel",
+        "flash_bwd_dq_kernel", "flash_bwd_dkv_kernel", "bn_stats_kernel", "bias_act_bwd_kernel", "glm_tc_kernel")
 
 
 def main():
