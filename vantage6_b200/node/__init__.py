@@ -35,6 +35,7 @@ from ..common import base64s_to_bytes, bytes_to_base64s
 from ..common.encryption import DummyCryptor, RSACryptor
 from ..runtime import runtime_dir
 from .proxy import ProxyServer
+from .zygote import Zygote, ZygoteProcess
 
 log = logging.getLogger("node")
 
@@ -69,6 +70,7 @@ class Node:
         self.queue: "queue.Queue[dict]" = queue.Queue()
         self.running: Dict[int, subprocess.Popen] = {}           # result id -> algorithm process
         self._task_of: Dict[int, int] = {}                          # result id -> task id (for kill requests)
+        self.zygote: Optional[Zygote] = None                        # warm-start helper for algorithm runs
         self._seen: set = set()
         self._stop = threading.Event()
         self._threads = []
@@ -235,12 +237,16 @@ class Node:
                 env["V6_GPU"] = str(self.gpu)
             pkg_root = str(Path(__file__).resolve().parent.parent.parent)
             env["PYTHONPATH"] = pkg_root + os.pathsep + env.get("PYTHONPATH", "")
-            proc = subprocess.Popen([sys.executable, "-m", "vantage6_b200.algorithm.wrapper", module],
-                                    stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, start_new_session=True)
+            proc = self._launch_algorithm(module, env, work / "log")
             self.running[rid] = proc
             self._task_of[rid] = task["id"]
-            out, _ = proc.communicate(timeout=float(self.config.get("task_timeout_s", 3600)))
-            logtxt = out.decode("utf-8", errors="replace")
+            budget = float(self.config.get("task_timeout_s", 3600))
+            if isinstance(proc, ZygoteProcess):
+                proc.wait(timeout=budget)
+                logtxt = proc.read_log()
+            else:
+                out, _ = proc.communicate(timeout=budget)
+                logtxt = out.decode("utf-8", errors="replace")
             if proc.returncode == 0:
                 data = (work / "output").read_bytes()
                 dest_org = task.get("initiator") or self.client.request(f"task/{task['id']}").get("initiator")
@@ -263,6 +269,31 @@ class Node:
         except Exception as e:  # noqa: BLE001
             log.error("could not report result %s: %s", rid, e)
         log.info("task %s result %s: %s", task.get("id"), rid, status)
+
+    def _start_zygote(self) -> None:
+        """GPU-pinned nodes run long, heavyweight algorithm processes (torch + CUDA): they keep one fresh interpreter
+        per task; the warm start is for the latency-bound CPU control-plane tasks (``V6B200_ZYGOTE=1`` forces it on,
+        ``=0`` off)."""
+        if os.environ.get("V6B200_ZYGOTE", "1" if self.gpu is None else "0") == "0":
+            return
+        zygote = Zygote(runtime_dir())
+        try:
+            if zygote.start() and not self._stop.is_set():
+                self.zygote = zygote
+            else:
+                zygote.stop()
+        except Exception as e:  # noqa: BLE001
+            log.warning("no warm-start helper (%s): one interpreter per task", e)
+
+    def _launch_algorithm(self, module: str, env: Dict[str, str], log_path: Path):
+        """Fork from the warm zygote when it is there (milliseconds), else start a fresh interpreter."""
+        if self.zygote is not None and self.zygote.alive():
+            try:
+                return self.zygote.spawn(module, env, log_path)
+            except Exception as e:  # noqa: BLE001
+                log.warning("zygote spawn failed (%s); starting a fresh interpreter", e)
+        return subprocess.Popen([sys.executable, "-m", "vantage6_b200.algorithm.wrapper", module],
+                                stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, start_new_session=True)
 
     @staticmethod
     def _kill_proc(proc: Optional[subprocess.Popen]) -> None:
@@ -288,6 +319,7 @@ class Node:
         self.authenticate()
         self.setup_encryption()
         self.proxy.start()
+        threading.Thread(target=self._start_zygote, daemon=True).start()     # tasks arriving before it is up run cold
         self.sync_open_results()
         for target in (self._listen, self._worker, self._heartbeat):
             t = threading.Thread(target=target, daemon=True)
@@ -313,5 +345,8 @@ class Node:
         except Exception:  # noqa: BLE001
             pass
         self.proxy.stop()
+        if self.zygote is not None:
+            self.zygote.stop()
+            self.zygote = None
         self._threads = []
         log.info("node stopped")
