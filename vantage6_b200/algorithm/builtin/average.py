@@ -1,7 +1,6 @@
 """Federated column average -- vantage6's canonical example algorithm:
 ``master`` creates an ``average_partial`` sub-task for every organization, waits, and combines
 ``sum_i / count_i`` into the global mean."""
-import time
 
 
 def master(client, data, column_name: str, organization_ids=None):
@@ -10,8 +9,7 @@ def master(client, data, column_name: str, organization_ids=None):
     task = client.create_new_task(
         input_={"method": "average_partial", "kwargs": {"column_name": column_name}}, organization_ids=ids)
     task_id = task.get("id")
-    while not client.get_task(task_id).get("complete"):
-        time.sleep(0.05)
+    client.wait_for_task(task_id)
     results = client.get_results(task_id=task_id)
     global_sum = sum(float(r["sum"]) for r in results)
     global_count = sum(int(r["count"]) for r in results)

@@ -38,8 +38,7 @@ def master(client, data, model: str = "resnet_tiny", rounds: int = 2, local_step
                                                   server_opt=server_opt, server_lr=server_lr, server_mode=server_mode,
                                                   rendezvous=rendezvous, seed=seed, return_weights=return_weights)},
         organization_ids=ids, name=f"fedavg-{model}")
-    while not client.get_task(task["id"]).get("complete"):
-        time.sleep(0.05)
+    client.wait_for_task(task["id"])
     results = client.get_results(task_id=task["id"])
     results = sorted((r for r in results if r), key=lambda r: r["rank"])
     losses = [sum(r["losses"][i] * r["n_samples"] for r in results) / sum(r["n_samples"] for r in results)

@@ -35,8 +35,7 @@ def master(client, data, iterations: int = 10, lr: float = 1.0, organization_ids
     for _ in range(iterations):
         task = client.create_new_task(input_={"method": "gradient", "kwargs": {"w": None if w is None else w.tolist()}},
                                       organization_ids=ids)
-        while not client.get_task(task["id"]).get("complete"):
-            time.sleep(0.02)
+        client.wait_for_task(task["id"])
         res = client.get_results(task_id=task["id"])
         g = sum(np.asarray(r["grad"], dtype=np.float64) for r in res)
         n = sum(r["n"] for r in res)
@@ -66,8 +65,7 @@ def master_fused(client, data, iterations: int = 20, lr: float = 1.0, rows_per_n
                                                                          rows_per_node=rows_per_node, features=features,
                                                                          synthetic=synthetic)},
                                   organization_ids=ids, name="glm-fit")
-    while not client.get_task(task["id"]).get("complete"):
-        time.sleep(0.05)
+    client.wait_for_task(task["id"])
     res = sorted(client.get_results(task_id=task["id"]), key=lambda r: r["rank"])
     return {"coefficients": res[0]["coefficients"], "intercept": res[0]["intercept"], "losses": res[0]["losses"],
             "us_per_iteration_max": max(r["us_per_iteration"] for r in res), "world": len(ids),

@@ -5,7 +5,6 @@ Every node owns ``n_i`` local observations of a d-dimensional vector (rows of it
 the partial returns ``(sum over rows, n_i)`` and the master forms ``sum_i sum_i / sum_i n_i``
 -- i.e. exactly the FedAvg combination rule ``sum_i (n_i / n) * mean_i`` on the control plane.
 """
-import time
 
 import numpy as np
 
@@ -24,8 +23,7 @@ def _as_matrix(data):
 def master(client, data, organization_ids=None):
     ids = organization_ids or [o.get("id") for o in client.get_organizations_in_my_collaboration()]
     task = client.create_new_task(input_={"method": "partial_sum"}, organization_ids=ids)
-    while not client.get_task(task.get("id")).get("complete"):
-        time.sleep(0.02)
+    client.wait_for_task(task.get("id"))
     results = client.get_results(task_id=task.get("id"))
     total = sum(int(r["count"]) for r in results)
     acc = sum(np.asarray(r["sum"], dtype=np.float64) for r in results)

@@ -17,7 +17,6 @@ reference vantage6/cli/node.py:71-119,428-502,734-763 and vantage6/cli/server.py
 from __future__ import annotations
 
 import re
-import time
 from dataclasses import dataclass, field
 from threading import Thread
 from typing import Callable, Dict, List, Optional, Tuple

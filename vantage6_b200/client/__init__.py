@@ -357,12 +357,31 @@ class ContainerClient(ClientBase):
             "name": name, "image": self.image, "collaboration_id": self.collaboration_id,
             "description": description or f"task from container on node_id={self.host_node_id}", "organizations": orgs})
 
-    def wait_for_results(self, task_id: int, sleep: float = 0.05, timeout: float = 3600.0) -> List[Any]:
+    def wait_for_task(self, task_id: int, sleep: float = 0.05, timeout: float = 3600.0) -> dict:
+        """Block until ``task_id`` is complete; woken by the server's ``status_update`` events (long poll through the
+        node's proxy) instead of sleeping between polls, with plain polling as the fallback."""
         t0 = time.time()
-        while not self.get_task(task_id).get("complete"):
+        try:        # event cursor taken BEFORE the first completeness check: no wake-up can be missed
+            cursor = self.request("event", params={"timeout": 0}, timeout=15).get("last_id")
+        except Exception:  # noqa: BLE001
+            cursor = None
+        while True:
+            task = self.get_task(task_id)
+            if task.get("complete"):
+                return task
             if time.time() - t0 > timeout:
                 raise TimeoutError(f"subtask {task_id} did not complete in {timeout}s")
-            time.sleep(sleep)
+            if cursor is None:
+                time.sleep(sleep)
+                continue
+            try:
+                reply = self.request("event", params={"since": cursor, "timeout": 5, "task_id": task_id}, timeout=15)
+                cursor = reply.get("last_id", cursor)
+            except Exception:  # noqa: BLE001
+                cursor = None
+
+    def wait_for_results(self, task_id: int, sleep: float = 0.05, timeout: float = 3600.0) -> List[Any]:
+        self.wait_for_task(task_id, sleep=sleep, timeout=timeout)
         return self.get_results(task_id)
 
     def get_organizations_in_my_collaboration(self) -> List[dict]:

@@ -36,6 +36,9 @@ class ClientMockProtocol:
     def get_task(self, task_id: int) -> dict:
         return {"id": task_id, "complete": True}
 
+    def wait_for_task(self, task_id: int, **_) -> dict:
+        return self.get_task(task_id)
+
     def get_results(self, task_id: int) -> List[Any]:
         return self.tasks[task_id]["results"]
 
