@@ -164,20 +164,26 @@ class UserClient(ClientBase):
         self.log.info("Successfully authenticated as %s (organization %s)", user["username"], org["name"])
 
     def wait_for_results(self, task_id: int, sleep: float = 0.05, timeout: float = 600.0) -> List[Any]:
-        """Block until the task is complete, then return the decrypted results."""
+        """Block until the task is complete, then return the decrypted results.  Woken by the server's
+        ``status_update`` events (long poll); plain polling every ``sleep`` seconds is the fallback."""
         t0 = time.time()
-        last = 0
+        try:        # event cursor taken BEFORE the first completeness check: no wake-up can be missed
+            cursor = self.request("event", params={"timeout": 0}, timeout=15).get("last_id")
+        except Exception:  # noqa: BLE001
+            cursor = None
         while True:
-            task = self.request(f"task/{task_id}")
-            if task.get("complete"):
+            if self.request(f"task/{task_id}").get("complete"):
                 break
             if time.time() - t0 > timeout:
                 raise TimeoutError(f"task {task_id} did not complete in {timeout}s")
-            try:    # push-style wake-up; falls back to polling on any error
-                ev = self.request("event", params={"since": last, "timeout": 5, "task_id": task_id}, timeout=15)
-                last = ev.get("last_id", last)
-            except Exception:  # noqa: BLE001
+            if cursor is None:
                 time.sleep(sleep)
+                continue
+            try:
+                reply = self.request("event", params={"since": cursor, "timeout": 5, "task_id": task_id}, timeout=15)
+                cursor = reply.get("last_id", cursor)
+            except Exception:  # noqa: BLE001
+                cursor = None
         return self.result.from_task(task_id)
 
     # ---------------------------------------------------------------- sub clients
