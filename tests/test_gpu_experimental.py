@@ -27,3 +27,31 @@ def test_experimental_glm_tensor_core_kernel(rows, monkeypatch):
     scale = ref[:256].abs().max().item()
     assert (out[:256] - ref[:256]).abs().max().item() < 2e-2 * scale
     torch.testing.assert_close(out[256:259], ref[256:259], rtol=2e-3, atol=2e-2)
+
+
+def test_experimental_glm_tensor_core_timing(monkeypatch, capsys):
+    """Not an assertion on speed -- prints both kernels' time on the benchmark shape (1M x 256 bf16)."""
+    from vantage6_b200.ops import glm as K8
+
+    dev = torch.device("cuda", 0)
+    X = torch.randn(1_000_000, 256, device=dev).to(torch.bfloat16)
+    y = (torch.rand(1_000_000, device=dev) < 0.5).float()
+    w = torch.zeros(257, device=dev)
+
+    def timed():
+        for _ in range(3):
+            K8.logistic_grad(X, y, w)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(10):
+            K8.logistic_grad(X, y, w)
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / 10
+
+    base = timed()
+    monkeypatch.setenv("V6B200_GLM", "tc")
+    tc = timed()
+    with capsys.disabled():
+        print(f"\n[glm] cuda-core {base * 1e3:.1f} us, tensor-core {tc * 1e3:.1f} us "
+              f"({512e6 / tc / 1e6:.0f} GB/s of X)")
