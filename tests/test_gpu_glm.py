@@ -1,16 +1,17 @@
-"""Opt-in tests of kernels that are in the tree but have not been validated on hardware yet (they are not used
-unless their environment switch is set).  Run with ``V6B200_EXPERIMENTAL=1 python -m pytest tests -m gpu -k experimental``."""
+"""K8 GLM: the tensor-core kernel (csrc/glm_tc.cu, MN-major UMMA operand for X^T r) and the CUDA-core kernel against
+the PyTorch reference; an opt-in timing print (``V6B200_EXPERIMENTAL=1``)."""
 import os
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("V6B200_EXPERIMENTAL") != "1", reason="set V6B200_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
+opt_in = pytest.mark.skipif(os.environ.get("V6B200_EXPERIMENTAL") != "1", reason="set V6B200_EXPERIMENTAL=1")
 
 
 @pytest.mark.parametrize("rows", [128, 1000, 125_000])
-def test_experimental_glm_tensor_core_kernel(rows, monkeypatch):
+@pytest.mark.parametrize("kernel", ["tc", "cuda"])
+def test_glm_kernels_match_reference(rows, kernel, monkeypatch):
     from vantage6_b200.ops import glm as K8
     from vantage6_b200.ops import native
 
@@ -21,7 +22,7 @@ def test_experimental_glm_tensor_core_kernel(rows, monkeypatch):
     y = (torch.rand(rows, device=dev) < 0.4).float()
     w = torch.randn(257, device=dev) * 0.1
     ref = K8.reference_logistic_grad(X, y, w)
-    monkeypatch.setenv("V6B200_GLM", "tc")
+    monkeypatch.setenv("V6B200_GLM", kernel)
     out = K8.logistic_grad(X, y, w)
     torch.cuda.synchronize()
     scale = ref[:256].abs().max().item()
@@ -29,7 +30,8 @@ def test_experimental_glm_tensor_core_kernel(rows, monkeypatch):
     torch.testing.assert_close(out[256:259], ref[256:259], rtol=2e-3, atol=2e-2)
 
 
-def test_experimental_glm_tensor_core_timing(monkeypatch, capsys):
+@opt_in
+def test_glm_kernel_timing(monkeypatch, capsys):
     """Not an assertion on speed -- prints both kernels' time on the benchmark shape (1M x 256 bf16)."""
     from vantage6_b200.ops import glm as K8
 
@@ -49,6 +51,7 @@ def test_experimental_glm_tensor_core_timing(monkeypatch, capsys):
         torch.cuda.synchronize()
         return s.elapsed_time(e) / 10
 
+    monkeypatch.setenv("V6B200_GLM", "cuda")
     base = timed()
     monkeypatch.setenv("V6B200_GLM", "tc")
     tc = timed()

@@ -1,4 +1,7 @@
-// K8 on the tensor cores -- EXPERIMENTAL, opt-in (V6B200_GLM=tc), not yet validated on hardware.
+// K8 on the tensor cores (default for bf16, F == 256; V6B200_GLM=cuda selects the CUDA-core kernel).
+// Measured on B200, 1M x 256 bf16: 99.6 us (5.1 TB/s, 0.78 of the measured HBM copy bandwidth) vs 124.2 us for the
+// CUDA-core kernel in the same process; federated GLM iteration (K8 + K3 + update) 115 us vs 141 us
+// (profiles/README.md).
 //
 // The CUDA-core kernel (rope_glm.cu::glm_logistic_kernel) reads X once but is bound by issue slots: ~160
 // instructions per lane and row for the two products z = X w and g = X^T r (0.50 of HBM bandwidth,
