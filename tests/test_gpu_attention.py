@@ -119,3 +119,20 @@ def test_packed_qkv_attention_forward_backward(dev, variant, monkeypatch):
     ro.backward(do.float())
     assert (o.float() - ro).abs().max().item() < 3e-2
     assert (qkv.grad.float() - ref.grad).abs().max().item() < 6e-2
+
+
+@pytest.mark.skipif(__import__("os").environ.get("V6B200_EXPERIMENTAL") != "1", reason="set V6B200_EXPERIMENTAL=1")
+@pytest.mark.parametrize("B,S,Hq,Hkv,D,causal", [(2, 256, 12, 12, 64, False), (1, 1024, 8, 2, 128, True), (1, 200, 2, 2, 64, True)])
+def test_experimental_attention_v_in_place(dev, B, S, Hq, Hkv, D, causal, monkeypatch):
+    """Opt-in (not validated on hardware yet): V consumed in its natural layout as an MN-major UMMA operand."""
+    from vantage6_b200.ops import attention as A
+
+    monkeypatch.setenv("V6B200_ATTN_V", "mn")
+    torch.manual_seed(7)
+    q = torch.randn(B, S, Hq, D, device=dev, dtype=torch.bfloat16)
+    k = torch.randn(B, S, Hkv, D, device=dev, dtype=torch.bfloat16)
+    v = torch.randn(B, S, Hkv, D, device=dev, dtype=torch.bfloat16)
+    o, lse = A.flash_attn_fwd(q, k, v, causal, variant="2cta")
+    ro, rlse = A.reference_attention(q, k, v, causal)
+    assert (o.float() - ro).abs().max().item() < 3e-2
+    torch.testing.assert_close(lse, rlse, rtol=1e-3, atol=2e-3)

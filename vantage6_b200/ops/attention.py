@@ -46,10 +46,16 @@ def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
     scale = scale if scale is not None else 1.0 / math.sqrt(D)
     q, ldq = _token_strided(q)
     k, ldk = _token_strided(k)
-    vt = v.permute(0, 2, 3, 1).contiguous()
     o = torch.empty((B, S, Hq, D), device=q.device, dtype=q.dtype)
     lse = torch.empty(B, Hq, S, device=q.device, dtype=torch.float32)
     count(1)
+    if os.environ.get("V6B200_ATTN_V") == "mn" and _fwd_variant(variant) == "2cta" and hasattr(native(), "flash_attn_fwd2_vmn"):
+        # opt-in, unvalidated: V consumed in place as an MN-major UMMA operand (no Vt copy)
+        v, ldv = _token_strided(v)
+        native().flash_attn_fwd2_vmn(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(), B, S, Hq, Hkv, D,
+                                     ldq, ldk, ldv, float(scale), bool(causal), stream_ptr())
+        return o, lse
+    vt = v.permute(0, 2, 3, 1).contiguous()
     fn = native().flash_attn_fwd2 if _fwd_variant(variant) == "2cta" else native().flash_attn_fwd
     fn(q.data_ptr(), k.data_ptr(), vt.data_ptr(), o.data_ptr(), lse.data_ptr(), B, S, Hq, Hkv, D, ldq, ldk, float(scale),
        bool(causal), stream_ptr())

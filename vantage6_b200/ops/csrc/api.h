@@ -145,6 +145,9 @@ int v6_bn_bwd(const void* dy, const void* relu_mask, const void* x, const float*
 int v6_gemm2_bf16(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, int lda, int ldb, int ldc,
                   int act, cudaStream_t stream);
 int v6_gemm_smem_bytes();
+int v6_flash_attn_fwd2_vmn(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S, int Hq, int Hkv,
+                           int D, long long ldq, long long ldk, long long ldv, float softmax_scale, int causal,
+                           cudaStream_t stream);
 int v6_flash_attn_fwd2(const void* q, const void* k, const void* vt, void* o, float* lse, int B, int S, int Hq, int Hkv,
                        int D, long long ldq, long long ldk, float softmax_scale, int causal, cudaStream_t stream);
 int v6_flash_attn_fwd(const void* q, const void* k, const void* vt, void* o, float* lse, int B, int S, int Hq, int Hkv,

@@ -35,7 +35,22 @@ struct Params {
     float scale_log2;     // softmax_scale * log2(e)
 };
 
-template <int D, bool CAUSAL>
+// MN-major SWIZZLE_128B operand descriptor (see glm_tc.cu / docs/ROUND2_PLAN.md appendix): 64 MN-elements contiguous,
+// 8 K-rows 128 B apart, sbo = bytes between 8-row K groups, lbo = bytes between 64-element MN chunks
+V6_DEVINL uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// VMN (opt-in, V6B200_ATTN_V=mn, not yet validated on hardware): V is read in its natural [B,S,Hkv,D] layout -- tiles
+// of [128 keys x 64 d] loaded like K tiles and consumed by the PV MMA as an MN-major B operand -- instead of from a
+// pre-transposed Vt copy; `tmap_vt` is then a map over V ([B*S, Hkv*D], box 128 x 64).
+template <int D, bool CAUSAL, bool VMN>
 __global__ void __launch_bounds__(kThreads, 2)
 flash_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq*D]   box 128 x 64
                   const __grid_constant__ CUtensorMap tmap_k,     // [B*S, Hkv*D]  box 128 x 64
@@ -103,15 +118,21 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq*D]
                     tma_load_2d(sK + hh * (BN * 128), &tmap_k, k_full, hk * D + hh * 64, b * P.S + j * BN);
                 mbar_wait(v_empty, ph ^ 1);                       // O += P_{j-1} V_{j-1} has retired
                 mbar_expect_tx(v_full, V_BYTES);
+                if (VMN) {
 #pragma unroll
-                for (int kh = 0; kh < 2; ++kh)
-                    tma_load_2d(sV + kh * (D * 128), &tmap_vt, v_full, j * BN + kh * 64, (b * P.Hkv + hk) * D);
+                    for (int hh = 0; hh < NH; ++hh)
+                        tma_load_2d(sV + hh * (BN * 128), &tmap_vt, v_full, hk * D + hh * 64, b * P.S + j * BN);
+                } else {
+#pragma unroll
+                    for (int kh = 0; kh < 2; ++kh)
+                        tma_load_2d(sV + kh * (D * 128), &tmap_vt, v_full, j * BN + kh * 64, (b * P.Hkv + hk) * D);
+                }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
         constexpr uint32_t idesc_s = make_idesc_bf16(BM, BN);
-        constexpr uint32_t idesc_o = make_idesc_bf16(BM, D);
+        constexpr uint32_t idesc_o = make_idesc_bf16(BM, D) | (VMN ? (1u << 16) : 0u);      // bit 16: B MN-major
         mbar_wait(q_full, 0);
         for (int j = 0; j < nkv; ++j) {
             const uint32_t ph = j & 1;
@@ -138,10 +159,11 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq*D]
             if (lane == 0) {
                 const uint32_t vb = smem_u32(sV);
 #pragma unroll
-                for (int kk = 0; kk < BN / 16; ++kk)
+                for (int kk = 0; kk < BN / 16; ++kk)                  // 16 keys per step
                     umma_bf16_ts(tmem_base + O_COL, tmem_base + S_COL + kk * 8,
-                                 make_smem_desc_sw128(vb + (kk >> 2) * (D * 128) + (kk & 3) * 32), idesc_o,
-                                 (j > 0 || kk > 0) ? 1u : 0u);
+                                 VMN ? make_smem_desc_sw128_mn(vb + kk * 2048, BN * 128, 1024)
+                                     : make_smem_desc_sw128(vb + (kk >> 2) * (D * 128) + (kk & 3) * 32),
+                                 idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
                 umma_commit(pv_done);
                 umma_commit(v_empty);
             }
@@ -267,10 +289,10 @@ constexpr int smem_bytes() { return BM * D * 2 + BN * D * 2 + D * BN * 2 + 1024 
 
 }  // namespace attn2
 
-template <int D, bool CAUSAL>
+template <int D, bool CAUSAL, bool VMN = false>
 static int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const attn2::Params& P,
                         cudaStream_t stream) {
-    auto kern = attn2::flash_fwd2_kernel<D, CAUSAL>;
+    auto kern = attn2::flash_fwd2_kernel<D, CAUSAL, VMN>;
     constexpr int smem = attn2::smem_bytes<D>();
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
@@ -298,4 +320,25 @@ extern "C" int v6_flash_attn_fwd2(const void* q, const void* k, const void* vt, 
     P.scale_log2 = softmax_scale * 1.4426950408889634f;
     if (D == 64) return causal ? launch_attn2<64, true>(tq, tk, tv, P, stream) : launch_attn2<64, false>(tq, tk, tv, P, stream);
     return causal ? launch_attn2<128, true>(tq, tk, tv, P, stream) : launch_attn2<128, false>(tq, tk, tv, P, stream);
+}
+
+// Opt-in variant: v:[B,S,Hkv,D] in its natural layout (token stride ldv elements, 0 = dense); no Vt copy.
+extern "C" int v6_flash_attn_fwd2_vmn(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S, int Hq,
+                                      int Hkv, int D, long long ldq, long long ldk, long long ldv, float softmax_scale, int causal,
+                                      cudaStream_t stream) {
+    if ((D != 64 && D != 128) || Hq % Hkv != 0 || S % 8 != 0) return (int)cudaErrorInvalidValue;
+    if (ldq <= 0) ldq = (long long)Hq * D;
+    if (ldk <= 0) ldk = (long long)Hkv * D;
+    if (ldv <= 0) ldv = (long long)Hkv * D;
+    if (ldq % 8 || ldk % 8 || ldv % 8 || ldq < (long long)Hq * D || ldk < (long long)Hkv * D || ldv < (long long)Hkv * D)
+        return (int)cudaErrorInvalidValue;
+    alignas(64) CUtensorMap tq, tk, tv;
+    if (v6_make_tmap_2d_bf16(&tq, (uint64_t)q, (uint64_t)B * S, (uint64_t)Hq * D, (uint64_t)ldq * 2, 128, 64, 1)) return -2;
+    if (v6_make_tmap_2d_bf16(&tk, (uint64_t)k, (uint64_t)B * S, (uint64_t)Hkv * D, (uint64_t)ldk * 2, 128, 64, 1)) return -2;
+    if (v6_make_tmap_2d_bf16(&tv, (uint64_t)v, (uint64_t)B * S, (uint64_t)Hkv * D, (uint64_t)ldv * 2, 128, 64, 1)) return -2;
+    attn2::Params P;
+    P.O = (__nv_bfloat16*)o; P.lse = lse; P.B = B; P.S = S; P.Hq = Hq; P.Hkv = Hkv;
+    P.scale_log2 = softmax_scale * 1.4426950408889634f;
+    if (D == 64) return causal ? launch_attn2<64, true, true>(tq, tk, tv, P, stream) : launch_attn2<64, false, true>(tq, tk, tv, P, stream);
+    return causal ? launch_attn2<128, true, true>(tq, tk, tv, P, stream) : launch_attn2<128, false, true>(tq, tk, tv, P, stream);
 }

@@ -241,6 +241,11 @@ PYBIND11_MODULE(_C, m) {
                                 scale, causal, S(s)), "flash_attn_bwd");
     });
     // ------------------------------------------------------------------ K4 attention
+    m.def("flash_attn_fwd2_vmn", [](u64 q, u64 k, u64 v, u64 o, u64 lse, int B, int Sq, int Hq, int Hkv, int D, long long ldq,
+                                   long long ldk, long long ldv, float scale, bool causal, u64 s) {
+        check(v6_flash_attn_fwd2_vmn(P<void>(q), P<void>(k), P<void>(v), P<void>(o), P<float>(lse), B, Sq, Hq, Hkv, D, ldq, ldk, ldv,
+                                     scale, causal, S(s)), "flash_attn_fwd2_vmn");
+    });
     m.def("flash_attn_fwd2", [](u64 q, u64 k, u64 vt, u64 o, u64 lse, int B, int Sq, int Hq, int Hkv, int D, long long ldq, long long ldk, float scale,
                                bool causal, u64 s) {
         check(v6_flash_attn_fwd2(P<void>(q), P<void>(k), P<void>(vt), P<void>(o), P<float>(lse), B, Sq, Hq, Hkv, D, ldq, ldk, scale,
