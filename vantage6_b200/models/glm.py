@@ -40,9 +40,35 @@ class FederatedGLM:
         self._scratch = torch.empty(148 * 4 * (self.F + 2), dtype=torch.float32, device=self.device) if X.is_cuda else None
         self.last_loss: Optional[torch.Tensor] = None
 
+    def _fused_ok(self) -> bool:
+        """Opt-in (``V6B200_GLM_FUSED=1``, not validated on hardware yet): gradient kernel + ONE kernel that folds its
+        partials, all-reduces the payload over NVLink and applies the update (csrc/fedavg.cu::glm_aggregate_update_kernel)."""
+        import os
+
+        return (os.environ.get("V6B200_GLM_FUSED") == "1" and self.X.is_cuda and getattr(self.agg, "native", False)
+                and K8._tensor_core_path(self.X))
+
+    @torch.no_grad()
+    def _step_fused(self) -> torch.Tensor:
+        from ..ops import native, stream_ptr
+
+        C, agg = native(), self.agg
+        if self.last_loss is None or self.last_loss.dim() != 0 or not self.last_loss.is_cuda:
+            self.last_loss = torch.zeros((), dtype=torch.float32, device=self.device)
+        nparts = C.glm_logistic_partials_tc(self.X.data_ptr(), self.y.data_ptr(), self.w.data_ptr(), self._scratch.data_ptr(),
+                                            148 * 4, self.rows, self.F, stream_ptr())
+        agg.epoch += 1
+        off = (agg.epoch & 1) * agg.n * 4
+        C.glm_aggregate_update(agg._slots.peer(off), agg._pad_buf.peer(), [1.0] * agg.world, agg.out.data_ptr(), agg.n, agg.rank,
+                               agg.world, agg.epoch, agg.timeout_cycles, self._scratch.data_ptr(), nparts, self.F,
+                               float(self.rows), float(self.lr), self.w.data_ptr(), self.last_loss.data_ptr(), stream_ptr())
+        return self.last_loss
+
     @torch.no_grad()
     def step(self) -> torch.Tensor:
         """One federated gradient step; returns the global mean loss (device scalar)."""
+        if self._fused_ok():
+            return self._step_fused()
         K8.logistic_grad(self.X, self.y, self.w, out=self.agg.slot(), scratch=self._scratch)
         tot = self.agg.allreduce(1.0, normalize=False)        # sums over nodes: [g_w, g_b, loss, n]
         n = tot[self.F + 2]

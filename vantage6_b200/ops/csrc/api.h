@@ -108,6 +108,8 @@ int v6_rmsnorm_bwd(const void* dy, const void* x_in, const void* dres, const flo
                    cudaStream_t s);
 int v6_rope(void* q, void* k, const float* cos_t, const float* sin_t, const int* pos_ids, int B, int S, int Hq, int Hkv,
             int D, int inverse, cudaStream_t st);
+int v6_glm_aggregate_update(const SmallParams* hp, const float* part, int nparts, int F, float rows, float lr, float* w,
+                            float* loss_out, cudaStream_t stream);
 int v6_glm_fold(const float* part, float* out, int nparts, int F, int rows, cudaStream_t s);
 int v6_glm_logistic_grad_tc(const void* X, const float* y, const float* w, float* part, int max_parts, int rows, int F,
                             cudaStream_t s);

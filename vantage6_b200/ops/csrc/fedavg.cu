@@ -289,6 +289,68 @@ __global__ void __launch_bounds__(1024, 1) small_allreduce_kernel(const SmallPar
         reinterpret_cast<float4*>(P.out)[i] = a;
     }
 }
+// ----------------------------------------------------------------------------------------
+// K8 + K3 fused tail of a federated GLM iteration (opt-in, V6B200_GLM_FUSED=1, not validated on hardware yet):
+//   fold the per-CTA partials of the gradient kernel into this rank's payload slot  (was: fold kernel)
+//   -> signal / wait / P2P loads of every node's payload, sum                        (was: K3)
+//   -> w -= lr * g / n,  loss = l / n                                               (was: three PyTorch kernels)
+// in ONE single-CTA launch.  payload = [g_w (F), g_b, loss, n_rows | pad]; P.n = padded payload length (<= 1024).
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1) glm_aggregate_update_kernel(const SmallParams P, const float* __restrict__ part,
+                                                                       int nparts, int F, float rows, float lr,
+                                                                       float* __restrict__ w, float* __restrict__ loss_out) {
+    __shared__ int s_ok;
+    __shared__ float tot[1024];
+    uint32_t* my_pad = reinterpret_cast<uint32_t*>(P.pads.p[P.rank]);
+    float* my_slot = reinterpret_cast<float*>(P.slots.p[P.rank]);
+    if (threadIdx.x == 0) s_ok = 1;
+    // 1. fold the gradient kernel's partials into this rank's slot (fixed order: deterministic)
+    for (int i = threadIdx.x; i < P.n; i += blockDim.x) {
+        float a = 0.f;
+        if (i < F + 2) {
+            for (int p = 0; p < nparts; ++p) a += part[(size_t)p * (F + 2) + i];
+        } else if (i == F + 2) {
+            a = rows;
+        }
+        my_slot[i] = a;
+    }
+    __syncthreads();
+    // 2. publish / wait / reduce (as small_allreduce_kernel)
+    if (threadIdx.x < P.world) {
+        uint32_t* pad = reinterpret_cast<uint32_t*>(P.pads.p[threadIdx.x]);
+        fence_acq_rel_sys();
+        st_release_sys_u32(pad + PAD_SMALL + P.rank, P.epoch);
+        if (P.weight[threadIdx.x] > 0.f &&
+            !spin_wait_ge(my_pad + PAD_SMALL + threadIdx.x, P.epoch, P.timeout_cycles, my_pad + PAD_ABORT))
+            atomicExch(&s_ok, 0);
+    }
+    __syncthreads();
+    if (!s_ok) { if (threadIdx.x == 0) my_pad[PAD_STATUS] = 1; return; }
+    for (int i = threadIdx.x; i < P.n / 4; i += blockDim.x) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < V6_MAX_PEERS; ++p)
+            if (p < P.world && P.weight[p] > 0.f) {
+                const float4 v = ld_sys_f4(reinterpret_cast<const float4*>(P.slots.p[p]) + i);
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            }
+        reinterpret_cast<float4*>(P.out)[i] = a;                    // the summed payload stays readable by the host side
+        tot[4 * i] = a.x; tot[4 * i + 1] = a.y; tot[4 * i + 2] = a.z; tot[4 * i + 3] = a.w;
+    }
+    __syncthreads();
+    // 3. the gradient step on this rank's copy of the coefficients
+    const float inv_n = 1.f / tot[F + 2];
+    for (int j = threadIdx.x; j <= F; j += blockDim.x) w[j] -= lr * tot[j] * inv_n;
+    if (threadIdx.x == 0) *loss_out = tot[F + 1] * inv_n;
+}
+extern "C" int v6_glm_aggregate_update(const SmallParams* hp, const float* part, int nparts, int F, float rows, float lr, float* w,
+                                       float* loss_out, cudaStream_t stream) {
+    if (hp->n > 1024 || hp->n % 4 != 0 || F + 3 > hp->n || nparts < 1) return (int)cudaErrorInvalidValue;
+    glm_aggregate_update_kernel<<<1, 1024, 0, stream>>>(*hp, part, nparts, F, rows, lr, w, loss_out);
+    V6_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int v6_small_allreduce(const SmallParams* hp, cudaStream_t stream) {
     small_allreduce_kernel<<<1, 1024, 0, stream>>>(*hp);
     V6_CHECK_LAUNCH();

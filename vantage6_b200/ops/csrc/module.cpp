@@ -92,6 +92,17 @@ PYBIND11_MODULE(_C, m) {
         p.timeout_cycles = timeout_cycles;
         check(v6_small_allreduce(&p, S(stream)), "small_allreduce");
     });
+    m.def("glm_aggregate_update", [](const std::vector<u64>& slots, const std::vector<u64>& pads, const std::vector<float>& weight,
+                                     u64 out, int n, int rank, int world, uint32_t epoch, long long timeout_cycles, u64 part,
+                                     int nparts, int F, float rows, float lr, u64 w, u64 loss_out, u64 stream) {
+        SmallParams p;
+        p.slots = table(slots); p.pads = table(pads);
+        for (int i = 0; i < V6_MAX_PEERS; ++i) p.weight[i] = i < (int)weight.size() ? weight[i] : 0.f;
+        p.out = P<float>(out); p.n = n; p.rank = rank; p.world = world; p.epoch = epoch; p.inv_total = 1.f;
+        p.timeout_cycles = timeout_cycles;
+        check(v6_glm_aggregate_update(&p, P<float>(part), nparts, F, rows, lr, P<float>(w), P<float>(loss_out), S(stream)),
+              "glm_aggregate_update");
+    });
     m.def("p2p_pull", [](u64 src, u64 dst, long long nbytes, u64 s) { check(v6_p2p_pull(P<void>(src), P<void>(dst), nbytes, S(s)), "p2p_pull"); });
     m.def("mc_push", [](u64 src, u64 mc, long long nbytes, u64 s) { check(v6_mc_push(P<void>(src), P<void>(mc), nbytes, S(s)), "mc_push"); });
     m.def("mc_reduce", [](u64 mc, u64 dst, long long nbytes, u64 s) { check(v6_mc_reduce(P<void>(mc), P<void>(dst), nbytes, S(s)), "mc_reduce"); });
@@ -209,6 +220,11 @@ PYBIND11_MODULE(_C, m) {
     // ------------------------------------------------------------------ K6 / K8
     m.def("rope", [](u64 q, u64 k, u64 cos_t, u64 sin_t, u64 pos, int B, int Sq, int Hq, int Hkv, int D, bool inverse, u64 s) {
         check(v6_rope(P<void>(q), P<void>(k), P<float>(cos_t), P<float>(sin_t), P<int>(pos), B, Sq, Hq, Hkv, D, inverse, S(s)), "rope");
+    });
+    m.def("glm_logistic_partials_tc", [](u64 X, u64 y, u64 w, u64 part, int max_parts, int rows, int F, u64 s) {
+        const int grid = v6_glm_logistic_grad_tc(P<void>(X), P<float>(y), P<float>(w), P<float>(part), max_parts, rows, F, S(s));
+        if (grid < 1) throw std::runtime_error("glm_logistic_partials_tc failed (" + std::to_string(grid) + ")");
+        return grid;
     });
     m.def("glm_logistic_grad_tc", [](u64 X, u64 y, u64 w, u64 part, int max_parts, u64 out, int rows, int F, u64 s) {
         const int grid = v6_glm_logistic_grad_tc(P<void>(X), P<float>(y), P<float>(w), P<float>(part), max_parts, rows, F, S(s));
