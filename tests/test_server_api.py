@@ -218,3 +218,61 @@ def test_database_refuses_non_identifier_columns(tmp_path):
     db.update("organization", oid, name="renamed")
     assert db.get("organization", oid)["name"] == "renamed"
     db.close()
+
+
+def test_no_privilege_escalation_through_user_roles(server):
+    """an Organization Admin must not be able to create or patch a user into a role (or rule) whose
+    permissions it does not hold itself."""
+    app, port = server
+    alice = user(port, "alice", "pw-a")
+    roles = {r["name"]: r["id"] for r in alice.role.list()}
+    admin = alice.user.create("dan", "pw-d", organization=2, roles=[roles["Organization Admin"]])
+    dan = user(port, "dan", "pw-d")
+    with pytest.raises(ServerError) as e:
+        dan.user.create("mallory", "pw", organization=2, roles=[roles["Root"]])
+    assert e.value.status == 401
+    with pytest.raises(ServerError) as e:
+        dan.request(f"user/{admin['id']}", method="patch", json={"roles": [roles["Root"]]})
+    assert e.value.status == 401
+    glob = [r["id"] for r in alice.rule.list() if r["scope"] == "global" and r["name"] == "collaboration" and r["operation"] == "delete"]
+    with pytest.raises(ServerError) as e:
+        dan.request("user", method="post", json={"username": "m2", "password": "pw", "organization_id": 2, "rules": glob})
+    assert e.value.status == 401
+    # what it does hold, it may hand out
+    ok = dan.user.create("erin", "pw-e", organization=2, roles=[roles["Viewer"]])
+    assert ok["username"] == "erin"
+    # and dan is still no root: deleting another organization's collaboration stays forbidden
+    with pytest.raises(ServerError):
+        dan.request("collaboration/1", method="delete")
+
+
+def test_item_endpoints_respect_collaboration_reach(server):
+    """GET /task/<id>, /task/<id>/result, /result/<id>, /collaboration/<id>/*, /node/<id> and the
+    task event room are only visible inside the collaboration's reach -- not to any authenticated identity."""
+    app, port = server
+    alice, carol = user(port, "alice", "pw-a"), user(port, "carol", "pw-c")          # carol: Viewer of organization C
+    t = alice.task.create(collaboration=1, organizations=[1, 2], name="secret", image="img", input={"method": "m"})
+    rid = alice.request("result", params={"task_id": t["id"]})[0]["id"]
+    for path in (f"task/{t['id']}", f"task/{t['id']}/result", f"result/{rid}", "collaboration/1/task", "collaboration/1/node",
+                 "collaboration/1/organization", "node/1"):
+        with pytest.raises(ServerError) as e:
+            carol.request(path)
+        assert e.value.status == 401, path
+        assert alice.request(path) is not None
+    with pytest.raises(ServerError) as e:
+        carol.request("event", params={"task_id": t["id"], "timeout": 0.1})
+    assert e.value.status == 401
+    # a node of another collaboration is locked out as well
+    new = alice.organization.create("D", domain="d.test")
+    cd = alice.collaboration.create("CD", [3, new["id"]])
+    n = alice.node.create(cd["id"], organization=3)
+    other = NodeClient("http://127.0.0.1", port, "/api")
+    other.authenticate(n["api_key"])
+    for path in (f"task/{t['id']}", f"result/{rid}", f"task/{t['id']}/result"):
+        with pytest.raises(ServerError) as e:
+            other.request(path)
+        assert e.value.status == 401, path
+    # the collaboration's own node still reads its work
+    mine = NodeClient("http://127.0.0.1", port, "/api")
+    mine.authenticate("key-a")
+    assert mine.request(f"task/{t['id']}")["name"] == "secret"

@@ -14,7 +14,11 @@ struct PeerTable { void* p[V6_MAX_PEERS]; };
 #define PAD_BARRIER  64     // [64,72) : generic barrier
 #define PAD_SMALL    96     // [96,104): small_allreduce arrivals
 #define PAD_ABORT    128    // host/any rank sets != 0 to abort all waits
-#define PAD_STATUS   129    // kernel writes 1 here (own pad) when a wait timed out
+#define PAD_STATUS   129    // kernel writes 1 here (own pad) when a wait timed out, 2 when a peer reducer reported a failed round
+#define PAD_MISSING  130    // own pad: bitmask of ranks whose contribution never arrived (own waits OR'd with the peers' reports)
+#define PAD_NI       136    // [136,144): n_i of rank p for this epoch (float bits), written by p into every reducer's pad
+#define PAD_RFAIL    144    // [144,152): reducer q's round `epoch` failed (value = epoch), written by q into every pad
+#define PAD_RMISS    152    // [152,160): the contributors reducer q missed (bitmask), written next to PAD_RFAIL
 
 struct FedAvgParams {
     PeerTable upload;        // contribution buffer of every rank (peer VAs in my address space)
@@ -27,10 +31,12 @@ struct FedAvgParams {
     float* w_global;         // fp32 master copy of my slice owner (full-size buffer, local)
     float* opt_m;            // server momentum / Adam m (local, full-size)
     float* opt_v;            // Adam v
-    float weight[V6_MAX_PEERS];   // n_i of each rank (0 => not participating)
+    float weight[V6_MAX_PEERS];   // n_i of each rank (0 => not participating); ignored when dynamic_weights
+    int dynamic_weights;     // 1: every rank only knows ITS n_i (my_weight); it travels to the reducers through PAD_NI
+    float my_weight;
     long long lo, hi;        // my element slice [lo, hi) -- multiples of 8
     int rank, world;
-    int n_reducers; uint32_t live_mask;   // bit p: rank p is alive (waited for + pushed to); n_reducers:          // ranks [0, n_reducers) own a slice (1 = central server on GPU 0)
+    int n_reducers; uint32_t reducer_mask; uint32_t live_mask;   // reducer_mask bit p: rank p owns a slice;   // bit p: rank p is alive (waited for + pushed to); n_reducers:          // ranks [0, n_reducers) own a slice (1 = central server on GPU 0)
     uint32_t epoch;
     int upload_is_delta;     // 1: upload holds n_i*(w_i - w_g); 0: upload holds w_i (unscaled)
     int upload_prescaled;    // 1: contributions already multiplied by n_i (needed for multicast)
@@ -165,6 +171,20 @@ int v6_symm_free(int gid, int aid);
 int v6_symm_finalize(int gid);
 int v6_make_tmap_2d_bf16(void* out, uint64_t gptr, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
                          uint32_t box_rows, uint32_t box_cols, int swizzle128);
+int v6_make_tmap_tiled_bf16(void* out, uint64_t gptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                            const uint32_t* box, int swizzle128);
+int v6_make_tmap_im2col_bf16(void* out, uint64_t gptr, uint64_t C, uint64_t W, uint64_t H, uint64_t N, int lower_w, int lower_h,
+                             int upper_w, int upper_h, uint32_t channels, uint32_t pixels, uint32_t stride_w, uint32_t stride_h);
+// igemm.cu: implicit-GEMM convolution / linear-backward family
+long long v6_igemm_scratch_floats();
+int v6_conv_fprop(const void* x, const void* w, void* y, const float* bias, int act, int N, int H, int W, int Cin, int Cout, int R,
+                  int S, int stride, int pad, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                  long long* num_batches_tracked, float* mean_out, float* rstd_out, float* scale_bias_out, float* scratch,
+                  float eps, float momentum, int force_im2col, cudaStream_t stream);
+int v6_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int R, int S, int pad,
+                  int force_im2col, cudaStream_t stream);
+int v6_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad,
+                  float scale, int splits, int force_im2col, cudaStream_t stream);
 #ifdef __cplusplus
 }
 #endif

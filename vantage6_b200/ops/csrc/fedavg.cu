@@ -49,28 +49,62 @@ __global__ void __launch_bounds__(512, 1)
 fedavg_round_kernel(const FedAvgParams P) {
     constexpr int VN = Vec<UpT>::N;
     __shared__ int s_ok;
-    const bool reducer = P.rank < P.n_reducers && P.hi > P.lo;
+    __shared__ unsigned int s_miss;
+    __shared__ float s_w[V6_MAX_PEERS];       // n_p of every contributor for this round (0 = not reporting / dead)
+    __shared__ float s_inv;                   // 1 / sum_p n_p (1 / world for the un-weighted in-switch sum)
+    __shared__ int s_use_mc;
+    const bool is_red = ((P.reducer_mask >> P.rank) & 1u) != 0u;     // this rank owns a slice of the global model
+    const bool reducer = is_red && P.hi > P.lo;
     uint32_t* my_pad = reinterpret_cast<uint32_t*>(P.pads.p[P.rank]);
 
-    // (1) tell every reducer that my contribution for this epoch is final. Stream order
-    // guarantees the producing kernels completed; the release makes it visible system-wide.
-    if (blockIdx.x == 0 && threadIdx.x < P.n_reducers) {
+    // (1) tell every reducer that my contribution for this epoch is final (and with which weight n_i: a rank only
+    // has to know its OWN sample count).  Stream order guarantees the producing kernels completed; the release
+    // makes contribution and weight visible system-wide.
+    if (blockIdx.x == 0 && threadIdx.x < P.world && ((P.reducer_mask >> threadIdx.x) & 1u)) {
         uint32_t* pad = reinterpret_cast<uint32_t*>(P.pads.p[threadIdx.x]);
+        if (P.dynamic_weights) pad[PAD_NI + P.rank] = __float_as_uint(P.my_weight);
         fence_acq_rel_sys();
         st_release_sys_u32(pad + PAD_UPLOAD + P.rank, P.epoch);
     }
 
     if (reducer) {
         // (2) wait for every participating contributor
-        if (threadIdx.x == 0) s_ok = 1;
+        if (threadIdx.x == 0) { s_ok = 1; s_miss = 0u; }
         __syncthreads();
         if (threadIdx.x < P.world && ((P.live_mask >> threadIdx.x) & 1u)) {
-            if (!spin_wait_ge(my_pad + PAD_UPLOAD + threadIdx.x, P.epoch, P.timeout_cycles, my_pad + PAD_ABORT))
+            if (!spin_wait_ge(my_pad + PAD_UPLOAD + threadIdx.x, P.epoch, P.timeout_cycles, my_pad + PAD_ABORT)) {
                 atomicExch(&s_ok, 0);
+                atomicOr(&s_miss, 1u << threadIdx.x);
+            }
         }
         __syncthreads();
-        if (!s_ok) { if (threadIdx.x == 0) my_pad[PAD_STATUS] = 1; }
-        else {
+        if (threadIdx.x == 0 && s_ok) {
+            float tot = 0.f, first = -1.f;
+            bool equal = true, all = true;
+            for (int p = 0; p < V6_MAX_PEERS; ++p) {
+                float w = 0.f;
+                if (p < P.world && ((P.live_mask >> p) & 1u))
+                    w = P.dynamic_weights ? __uint_as_float(ld_relaxed_sys_u32(my_pad + PAD_NI + p)) : P.weight[p];
+                if (!(w > 0.f)) w = 0.f;
+                s_w[p] = w;
+                if (p < P.world) {
+                    tot += w;
+                    if (w <= 0.f) all = false;
+                    if (first < 0.f) first = w; else if (w != first) equal = false;
+                }
+            }
+            // the in-switch reduction sums what every bound GPU holds: usable when every rank reports and either the
+            // contributions are already multiplied by n_i (delta modes) or all n_i are equal (mean = sum / world)
+            const bool mc = P.upload_mc != nullptr && all && (P.upload_prescaled || equal);
+            s_use_mc = mc ? 1 : 0;
+            s_inv = (mc && !P.upload_prescaled) ? 1.f / (float)P.world : (tot > 0.f ? 1.f / tot : 0.f);
+        }
+        __syncthreads();
+        if (!s_ok) {
+            // a contributor never arrived (dead / stopped node): nothing is reduced or pushed by this CTA; the status
+            // word and the set of missing ranks are reported to the host and, in step (6), to every peer
+            if (threadIdx.x == 0) { my_pad[PAD_STATUS] = 1; atomicOr(my_pad + PAD_MISSING, s_miss); }
+        } else {
             // (3)-(5) reduce -> optimizer -> push
             // U vectors per thread per iteration, all peer loads issued before any is consumed:
             // U x (world-1) remote 16 B loads in flight per thread cover the ~2-3 us NVLink
@@ -79,7 +113,7 @@ fedavg_round_kernel(const FedAvgParams P) {
             const long long stride = (long long)gridDim.x * blockDim.x;
             for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * U) {
                 float accs[U][VN];
-                if (P.upload_mc) {
+                if (s_use_mc) {
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         const long long iu = i0 + u * stride;
@@ -92,7 +126,7 @@ fedavg_round_kernel(const FedAvgParams P) {
                         const long long iu = i0 + u * stride;
 #pragma unroll
                         for (int p = 0; p < WMAX; ++p)
-                            if (iu < nvec && p < P.world && P.weight[p] > 0.f)
+                            if (iu < nvec && p < P.world && s_w[p] > 0.f)
                                 load_contrib(reinterpret_cast<const UpT*>(P.upload.p[p]), P.lo + iu * VN, v[u][p]);
                     }
 #pragma unroll
@@ -101,8 +135,8 @@ fedavg_round_kernel(const FedAvgParams P) {
                         for (int k = 0; k < VN; ++k) accs[u][k] = 0.f;
 #pragma unroll
                         for (int p = 0; p < WMAX; ++p)
-                            if (p < P.world && P.weight[p] > 0.f) {
-                                const float s = P.upload_prescaled ? 1.f : P.weight[p];
+                            if (p < P.world && s_w[p] > 0.f) {
+                                const float s = P.upload_prescaled ? 1.f : s_w[p];
 #pragma unroll
                                 for (int k = 0; k < VN; ++k) accs[u][k] = fmaf(s, v[u][p][k], accs[u][k]);
                             }
@@ -123,7 +157,7 @@ fedavg_round_kernel(const FedAvgParams P) {
                     float d[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const float mean = acc[4 * h + k] * P.inv_total;
+                        const float mean = acc[4 * h + k] * s_inv;
                         d[k] = P.upload_is_delta ? mean : (mean - w[k]);   // pseudo-gradient (ascent dir)
                     }
                     if (P.server_opt == 1) {
@@ -198,14 +232,27 @@ fedavg_round_kernel(const FedAvgParams P) {
     }
     __syncthreads();
     if (s_last) {
-        if (P.rank < P.n_reducers && threadIdx.x < P.world) {
+        if (is_red && threadIdx.x < P.world && ((P.live_mask >> threadIdx.x) & 1u)) {
             uint32_t* pad = reinterpret_cast<uint32_t*>(P.pads.p[threadIdx.x]);
+            // a failed round (some CTA of this reducer timed out in step 2) is announced to every live peer together
+            // with the contributors that were missed, BEFORE the completion flag: nobody leaves the round believing
+            // that a slice was pushed when it was not.
+            const uint32_t failed = reducer ? ld_relaxed_sys_u32(my_pad + PAD_STATUS) : 0u;
+            if (failed == 1u) {
+                pad[PAD_RMISS + P.rank] = ld_relaxed_sys_u32(my_pad + PAD_MISSING);
+                pad[PAD_RFAIL + P.rank] = P.epoch;
+            }
             fence_acq_rel_sys();
             st_release_sys_u32(pad + PAD_BCAST + P.rank, P.epoch);
         }
-        if (threadIdx.x < P.n_reducers) {
-            if (!spin_wait_ge(my_pad + PAD_BCAST + threadIdx.x, P.epoch, P.timeout_cycles, my_pad + PAD_ABORT))
+        if (threadIdx.x < P.world && ((P.reducer_mask >> threadIdx.x) & (P.live_mask >> threadIdx.x) & 1u)) {
+            if (!spin_wait_ge(my_pad + PAD_BCAST + threadIdx.x, P.epoch, P.timeout_cycles, my_pad + PAD_ABORT)) {
                 my_pad[PAD_STATUS] = 1;
+                atomicOr(my_pad + PAD_MISSING, 1u << threadIdx.x);
+            } else if (ld_relaxed_sys_u32(my_pad + PAD_RFAIL + threadIdx.x) == P.epoch) {
+                atomicCAS(my_pad + PAD_STATUS, 0u, 2u);
+                atomicOr(my_pad + PAD_MISSING, ld_relaxed_sys_u32(my_pad + PAD_RMISS + threadIdx.x));
+            }
         }
     }
 }

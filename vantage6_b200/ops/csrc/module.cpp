@@ -35,6 +35,7 @@ PYBIND11_MODULE(_C, m) {
     m.attr("PAD_WORDS") = 256;
     m.attr("PAD_ABORT") = PAD_ABORT;
     m.attr("PAD_STATUS") = PAD_STATUS;
+    m.attr("PAD_MISSING") = PAD_MISSING;
 
     // ------------------------------------------------------------------ symmetric heap
     m.def("driver_available", [] { return v6_driver_available() != 0; });
@@ -66,8 +67,10 @@ PYBIND11_MODULE(_C, m) {
              const std::vector<float>& weight, long long lo, long long hi, int rank, int world, int n_reducers,
              uint32_t live_mask, uint32_t epoch, bool upload_is_delta, bool upload_prescaled, int server_opt, float server_lr, float beta1,
              float beta2, float eps, float bias1, float bias2, float inv_total, long long timeout_cycles, u64 cta_counter,
-             int upload_dtype, int grid, u64 stream) {
+             int upload_dtype, int grid, u64 stream, bool dynamic_weights, float my_weight, uint32_t reducer_mask) {
               FedAvgParams p;
+              p.dynamic_weights = dynamic_weights ? 1 : 0; p.my_weight = my_weight;
+              p.reducer_mask = reducer_mask ? reducer_mask : ((n_reducers >= 32) ? 0xffffffffu : ((1u << n_reducers) - 1u));
               p.upload = table(upload); p.param_out = table(param_out); p.shadow_out = table(shadow_out); p.pads = table(pads);
               p.upload_mc = P<void>(upload_mc); p.param_mc = P<void>(param_mc); p.shadow_mc = P<void>(shadow_mc);
               p.w_global = P<float>(w_global); p.opt_m = P<float>(opt_m); p.opt_v = P<float>(opt_v);
@@ -236,6 +239,25 @@ PYBIND11_MODULE(_C, m) {
               "glm_logistic_grad");
     });
 
+    // ------------------------------------------------------------------ implicit-GEMM convolution family (igemm.cu)
+    m.attr("IGEMM_SCRATCH_FLOATS") = v6_igemm_scratch_floats();
+    m.def("conv_fprop", [](u64 x, u64 w, u64 y, u64 bias, int act, int N, int H, int W, int Cin, int Cout, int R, int Sw, int stride,
+                           int pad, u64 gamma, u64 beta, u64 rmean, u64 rvar, u64 nbt, u64 mean, u64 rstd, u64 scale_bias,
+                           u64 scratch, float eps, float momentum, bool force_im2col, u64 s) {
+        check(v6_conv_fprop(P<void>(x), P<void>(w), P<void>(y), P<float>(bias), act, N, H, W, Cin, Cout, R, Sw, stride, pad,
+                            P<float>(gamma), P<float>(beta), P<float>(rmean), P<float>(rvar), P<long long>(nbt), P<float>(mean),
+                            P<float>(rstd), P<float>(scale_bias), P<float>(scratch), eps, momentum, force_im2col, S(s)),
+              "conv_fprop");
+    });
+    m.def("conv_dgrad", [](u64 dy, u64 w, u64 dx, int N, int H, int W, int Cin, int Cout, int R, int Sw, int pad, bool force_im2col,
+                           u64 s) {
+        check(v6_conv_dgrad(P<void>(dy), P<void>(w), P<void>(dx), N, H, W, Cin, Cout, R, Sw, pad, force_im2col, S(s)), "conv_dgrad");
+    });
+    m.def("conv_wgrad", [](u64 dy, u64 x, u64 dw, int N, int H, int W, int Cin, int Cout, int R, int Sw, int stride, int pad,
+                           float scale, int splits, bool force_im2col, u64 s) {
+        check(v6_conv_wgrad(P<void>(dy), P<void>(x), P<float>(dw), N, H, W, Cin, Cout, R, Sw, stride, pad, scale, splits,
+                            force_im2col, S(s)), "conv_wgrad");
+    });
     // ------------------------------------------------------------------ K1 / tcgen05 GEMM
     m.def("gemm_bf16", [](u64 A, u64 B, u64 C, u64 bias, int M, int N, int K, int lda, int ldb, int ldc, int act, u64 s) {
         check(v6_gemm_bf16(P<void>(A), P<void>(B), P<void>(C), P<float>(bias), M, N, K, lda, ldb, ldc, act, S(s)), "gemm_bf16");

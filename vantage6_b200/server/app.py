@@ -195,6 +195,45 @@ class ServerApp:
             raise HTTPError(403, f"Not allowed for identity type {ident['type']!r}")
         return ident
 
+    def can_view_collaboration(self, ident: dict, collaboration_id: int, resource: str = "task") -> bool:
+        """May ``ident`` see items (tasks, results, nodes, members) of this collaboration?  Nodes and containers only
+        their own collaboration; users need a view rule on ``resource``: global scope sees everything, any narrower
+        scope only collaborations their organization takes part in (the same reach the list endpoints filter by)."""
+        if ident["type"] in ("node", "container"):
+            return ident.get("collaboration_id") == collaboration_id
+        sc = self.scope_of(ident, resource, "view")
+        if sc == "global":
+            return True
+        return sc is not None and collaboration_id in set(self.db.organization_collaborations(ident["organization_id"]))
+
+    def require_collaboration_view(self, ident: dict, collaboration_id: int, resource: str = "task") -> None:
+        if not self.can_view_collaboration(ident, collaboration_id, resource):
+            raise HTTPError(401, "You lack the permission to do that!")
+
+    def check_grant(self, ident: dict, role_ids, rule_ids, edit_scope: Optional[str]) -> None:
+        """A user may only hand out permissions it holds itself: every (resource, operation, scope) implied by the
+        requested roles / rules must be covered by one of the caller's own rules at an equal or wider scope, and a
+        caller without global user-edit scope may only assign default roles or roles of its own organization."""
+        implied = []
+        for rid in role_ids:
+            role = self.db.get("role", int(rid))
+            if role is None:
+                raise HTTPError(404, f"role id={rid} not found")
+            if edit_scope != "global" and role.get("organization_id") not in (None, ident["organization_id"]):
+                raise HTTPError(401, f"You cannot assign role id={rid} of another organization")
+            implied += self.db.query("SELECT rule.* FROM rule JOIN role_rule ON rule.id = role_rule.rule_id WHERE role_rule.role_id=?",
+                                     (int(rid),))
+        for rid in rule_ids:
+            rule = self.db.get("rule", int(rid))
+            if rule is None:
+                raise HTTPError(404, f"rule id={rid} not found")
+            implied.append(rule)
+        for r in implied:
+            mine = self.scope_of(ident, r["name"], r["operation"])
+            if mine is None or SCOPES.index(mine) < SCOPES.index(r["scope"]):
+                raise HTTPError(401, f"You cannot grant {r['name']}/{r['operation']} at scope {r['scope']!r}: "
+                                     "you do not hold that permission yourself")
+
     # ------------------------------------------------------------------ serialisation
     def link(self, resource: str, id_: int) -> dict:
         return {"id": id_, "link": f"{self.api_path}/{resource}/{id_}", "methods": ["GET", "PATCH", "DELETE"]}
@@ -482,17 +521,17 @@ class ServerApp:
 
         @app.route("GET", r"/collaboration/(\d+)/organization")
         def collab_orgs(ident, body, q, cid):
-            app.require(ident)
+            app.require_collaboration_view(app.require(ident), int(cid), "collaboration")
             return [app.org_json(db.get("organization", o)) for o in db.collaboration_organizations(int(cid))]
 
         @app.route("GET", r"/collaboration/(\d+)/node")
         def collab_nodes(ident, body, q, cid):
-            app.require(ident)
+            app.require_collaboration_view(app.require(ident), int(cid), "node")
             return [app.node_json(n) for n in db.query("SELECT * FROM node WHERE collaboration_id=?", (int(cid),))]
 
         @app.route("GET", r"/collaboration/(\d+)/task")
         def collab_tasks(ident, body, q, cid):
-            app.require(ident)
+            app.require_collaboration_view(app.require(ident), int(cid), "task")
             return [app.task_json(t) for t in db.query("SELECT * FROM task WHERE collaboration_id=? ORDER BY id", (int(cid),))]
 
         # ---- node
@@ -535,6 +574,8 @@ class ServerApp:
             n = db.get("node", int(nid))
             if n is None:
                 raise HTTPError(404, f"node id={nid} is not found")
+            if not (ident["type"] == "node" and ident["id"] == n["id"]):
+                app.require_collaboration_view(ident, n["collaboration_id"], "node")
             return app.node_json(n)
 
         @app.route("PATCH", r"/node/(\d+)")
@@ -592,6 +633,7 @@ class ServerApp:
             oid = int(body.get("organization_id") or ident["organization_id"])
             if sc != "global" and oid != ident["organization_id"]:
                 raise HTTPError(401, "You lack the permission to create users for another organization")
+            app.check_grant(ident, body.get("roles", []), body.get("rules", []), sc)
             uid = db.insert("user", username=body["username"], password=hash_password(body["password"]),
                             firstname=body.get("firstname"), lastname=body.get("lastname"), email=body.get("email"),
                             organization_id=oid)
@@ -624,11 +666,19 @@ class ServerApp:
             fields = {k: body[k] for k in ("firstname", "lastname", "email") if k in body}
             if body.get("password"):
                 fields["password"] = hash_password(body["password"])
+            if ("roles" in body or "rules" in body) and not sc:
+                raise HTTPError(401, "You lack the permission to change roles or rules")
+            if "roles" in body or "rules" in body:
+                app.check_grant(ident, body.get("roles", []), body.get("rules", []), sc)     # before anything is written
             db.update("user", u["id"], **fields)
-            if "roles" in body and sc:
+            if "roles" in body:
                 db.execute("DELETE FROM user_role WHERE user_id=?", (u["id"],))
                 for rid in body["roles"]:
                     db.execute("INSERT OR IGNORE INTO user_role VALUES (?,?)", (u["id"], int(rid)))
+            if "rules" in body:
+                db.execute("DELETE FROM user_rule WHERE user_id=?", (u["id"],))
+                for rid in body["rules"]:
+                    db.execute("INSERT OR IGNORE INTO user_rule VALUES (?,?)", (u["id"], int(rid)))
             return app.user_json(db.get("user", u["id"]))
 
         @app.route("DELETE", r"/user/(\d+)")
@@ -726,17 +776,20 @@ class ServerApp:
 
         @app.route("GET", r"/task/(\d+)")
         def task_get(ident, body, q, tid):
-            app.require(ident)
+            ident = app.require(ident)
             t = db.get("task", int(tid))
             if t is None:
                 raise HTTPError(404, f"task id={tid} is not found")
+            app.require_collaboration_view(ident, t["collaboration_id"], "task")
             return app.task_json(t, include_results=q.get("include") == "results")
 
         @app.route("GET", r"/task/(\d+)/result")
         def task_results(ident, body, q, tid):
-            app.require(ident)
-            if db.get("task", int(tid)) is None:
+            ident = app.require(ident)
+            t = db.get("task", int(tid))
+            if t is None:
                 raise HTTPError(404, f"task id={tid} is not found")
+            app.require_collaboration_view(ident, t["collaboration_id"], "result")
             return [app.result_json(r) for r in db.query("SELECT * FROM result WHERE task_id=? ORDER BY id", (int(tid),))]
 
         @app.route("DELETE", r"/task/(\d+)")
@@ -789,10 +842,12 @@ class ServerApp:
 
         @app.route("GET", r"/result/(\d+)")
         def result_get(ident, body, q, rid):
-            app.require(ident)
+            ident = app.require(ident)
             r = db.get("result", int(rid))
             if r is None:
                 raise HTTPError(404, f"result id={rid} not found")
+            t = db.get("task", r["task_id"])
+            app.require_collaboration_view(ident, t["collaboration_id"] if t else -1, "result")
             return app.result_json(r, with_task=q.get("include") == "task")
 
         @app.route("PATCH", r"/result/(\d+)")
@@ -829,7 +884,11 @@ class ServerApp:
                 if ident["type"] == "node":
                     rooms.append(f"node_{ident['id']}")
             if "task_id" in q:
-                rooms.append(f"task_{q['task_id']}")
+                t = db.get("task", int(q["task_id"]))
+                if t is None:
+                    raise HTTPError(404, f"task id={q['task_id']} is not found")
+                app.require_collaboration_view(ident, t["collaboration_id"], "task")
+                rooms.append(f"task_{t['id']}")
             evs = app.events.wait(since, rooms, timeout)
             return {"events": evs, "last_id": evs[-1]["id"] if evs else since}
 
