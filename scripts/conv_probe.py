@@ -189,6 +189,16 @@ def run_group(group: str, do_time: bool):
         wgrad_case(2, 64, 64, 16, 16, 3, 2, 1, splits=1)
         wgrad_case(B, 128, 128, 56, 56, 3, 2, 1)
         wgrad_case(B, 256, 512, 56, 56, 1, 2, 0)
+    elif group == "profile":
+        # the launches captured by `ncu --set full -k regex:igemm_kernel` (scripts/gpu_r2_prof_conv.sh), in this order
+        fprop_case(64, 64, 256, 56, 56, 1, 1, 0)
+        fprop_case(64, 64, 64, 56, 56, 3, 1, 1)
+        fprop_case(64, 64, 64, 56, 56, 3, 1, 1, stats=True)
+        fprop_case(64, 512, 512, 7, 7, 3, 1, 1)
+        dgrad_case(64, 64, 64, 56, 56, 3, 1)
+        wgrad_case(64, 64, 64, 56, 56, 3, 1, 1)
+        wgrad_case(64, 64, 256, 56, 56, 1, 1, 0)
+        wgrad_case(64, 512, 512, 7, 7, 3, 1, 1)
     elif group == "linear":
         # nn.Linear shapes through the same kernels: [tokens, K] x [N, K]^T (1x1 convolution over a 1-pixel-high image)
         fprop_case(1, 768, 2304, 1, 4096, 1, 1, 0)

@@ -88,7 +88,15 @@ def test_serialization_roundtrip_numpy_torch_bytes():
     np.testing.assert_array_equal(back["a"], obj["a"])
     np.testing.assert_array_equal(back["t"], np.ones(3, dtype=np.float32))
     assert back["b"] == b"\x00\x01" and back["n"] == 3 and back["f"] == 0.5 and sorted(back["s"]) == [1, 2]
-    assert deserialize(serialize({"k": [1, 2]}, "pickle")) == {"k": [1, 2]}
+    # pickle executes code on load: refused unless the operator opted in
+    from vantage6_b200.common.serialization import UnsafePayload
+
+    blob = serialize({"k": [1, 2]}, "pickle")
+    with pytest.raises(UnsafePayload):
+        deserialize(blob)
+    with pytest.raises(UnsafePayload):
+        deserialize(blob, "pickle")
+    assert deserialize(blob, allow_pickle=True) == {"k": [1, 2]}
 
 
 def test_image_registry():

@@ -149,6 +149,59 @@ def test_two_process_gloo_aggregation(server_mode, upload, opt):
     assert res == [(0, True, True, True), (1, True, True, True)], res
 
 
+def _unequal_worker(rank, world, port, q, server_mode, upload):
+    """Every rank passes only ITS OWN sample count (what a real node knows): the engine must still apply the
+    sample-weighted mean (a scalar used to be expanded to [n_r] * world on every rank)."""
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from torch import nn
+
+        from vantage6_b200.parallel.trainer import FederatedTrainer
+
+        torch.manual_seed(0)
+        model = nn.Linear(4, 1, bias=False)
+        tr = FederatedTrainer(model, lambda m, x, y: ((m(x) - y) ** 2).mean(), rank=rank, world=world, device="cpu",
+                              optimizer="sgd", lr=0.0, momentum=0.0, server_mode=server_mode, upload=upload, amp_dtype=None)
+        tr.initialize_global()
+        with torch.no_grad():                                   # local "training": node r moves every weight to a known value
+            target = 1.0 if rank == 0 else 3.0
+        x, y = torch.zeros(2, 4), torch.zeros(2, 1)
+        n_i = 100.0 if rank == 0 else 300.0
+        # lr = 0: the local step leaves the weights alone; set them by hand between the step and the aggregation
+        orig = tr.engine.aggregate
+
+        def agg(*a, **k):
+            with torch.no_grad():
+                if upload == "weights_f32":
+                    tr.fm.params.fill_(target)
+                else:
+                    tr.engine.upload[: tr.fm.n_trainable].copy_(((target - tr.w_ref[: tr.fm.n_trainable]) * n_i).to(tr.engine.upload.dtype))
+            return orig(*a, **k)
+        tr.engine.aggregate = agg
+        tr.run_round([(x, y)], n_samples=n_i)
+        q.put((rank, [round(float(v), 4) for v in tr.fm.params[:4]]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("server_mode,upload", [("sharded", "weights_f32"), ("central", "weights_f32"), ("sharded", "delta_f32")])
+def test_unequal_sample_counts_give_the_sample_weighted_mean(server_mode, upload):
+    from vantage6_b200.dev import free_port
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=_unequal_worker, args=(r, 2, port, q, server_mode, upload)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(30)
+    # w=1 with n=100 and w=3 with n=300 -> (100*1 + 300*3) / 400 = 2.5 everywhere (plain mean would be 2.0)
+    assert res == [(0, [2.5] * 4), (1, [2.5] * 4)], res
+
+
 def test_dead_node_is_excluded():
     e = FedAvgEngine(16, data_plane="collective")
     e.world = 3                                   # host-side logic only

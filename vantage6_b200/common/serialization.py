@@ -56,11 +56,33 @@ def serialize(obj: Any, data_format: str = "json") -> bytes:
     raise ValueError(f"unknown data format {data_format!r}")
 
 
-def deserialize(blob: bytes | str, data_format: str | None = None) -> Any:
+class UnsafePayload(ValueError):
+    """A pickle payload arrived where pickle was not explicitly enabled."""
+
+
+def pickle_allowed() -> bool:
+    """Pickle executes code on load.  Task inputs come from researchers and results from other organizations' nodes, so
+    it is OFF unless the operator of this process opted in (``V6B200_ALLOW_PICKLE=1``, set from the ``allow_pickle``
+    key of the node configuration / by the client's ``allow_pickle=True``)."""
+    import os
+
+    return os.environ.get("V6B200_ALLOW_PICKLE") == "1"
+
+
+def deserialize(blob: bytes | str, data_format: str | None = None, allow_pickle: bool | None = None) -> Any:
+    """JSON by default (the only format that is safe on untrusted bytes).  ``data_format="pickle"`` -- or an untagged blob
+    that is not JSON -- is only honoured when pickle was explicitly allowed; otherwise :class:`UnsafePayload`."""
     if isinstance(blob, str):
         blob = blob.encode("utf-8")
+    head = blob.lstrip()[:5]
+    looks_json = head[:1] in (b"{", b"[", b'"', b"-") or head[:1].isdigit() or head[:4] in (b"null", b"true") or head == b"false"
     if data_format is None:
-        data_format = "json" if blob[:1] in (b"{", b"[", b'"') or blob[:1].isdigit() or blob[:4] in (b"null", b"true", b"fals") else "pickle"
+        data_format = "json" if looks_json else "pickle"
     if data_format == "json":
         return json.loads(blob.decode("utf-8"), object_hook=_hook)
+    if data_format != "pickle":
+        raise ValueError(f"unknown data format {data_format!r}")
+    if not (pickle_allowed() if allow_pickle is None else allow_pickle):
+        raise UnsafePayload("refusing to unpickle a payload: pickle executes code on load and is disabled "
+                            "(set allow_pickle in the node configuration / V6B200_ALLOW_PICKLE=1 to opt in)")
     return pickle.loads(blob)

@@ -44,6 +44,57 @@ class _ShadowConvFn(torch.autograd.Function):
         return dx, None, None, None, None, None, None
 
 
+def _tc_mode() -> str:
+    """V6B200_CONV = tc (default: the hand-written tcgen05 implicit-GEMM kernels, csrc/igemm.cu) | cudnn (library arm)."""
+    import os
+
+    return os.environ.get("V6B200_CONV", "tc")
+
+
+class _TcConvFn(torch.autograd.Function):
+    """Convolution on the hand-written tcgen05 kernels (ops/conv.py): forward = implicit GEMM through TMA im2col maps
+    (+ the BatchNorm statistics of the output when ``bn`` is given), data gradient = the same kernel reading the filter
+    in place through an MN-major descriptor, filter gradient = split-K implicit GEMM accumulating in fp32 straight into
+    ``weight.grad`` (the flat gradient buffer) -- no bf16 gradient tensor, no gradient sink entry."""
+
+    @staticmethod
+    def forward(ctx, x, weight, w_bf16, stride, pad, bn):
+        from ..ops import conv as C
+
+        y = C.conv_fprop(x, w_bf16, stride, pad, bn=bn)
+        ctx.save_for_backward(x, w_bf16)
+        ctx.conf = (stride, pad)
+        ctx.weight = weight
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from ..ops import conv as C
+
+        x, w_bf16 = ctx.saved_tensors
+        stride, pad = ctx.conf
+        weight = ctx.weight
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        cout, cin, r, s = w_bf16.shape
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if stride == 1:
+                dx = C.conv_dgrad(dy, w_bf16, (x.shape[2], x.shape[3]), pad)
+            else:       # stride-2 data gradient (6 layers of ResNet-50): library kernel for now
+                dx = torch.ops.aten.convolution_backward(dy, x, w_bf16, None, (stride, stride), (pad, pad), (1, 1), False, (0, 0), 1,
+                                                         (True, False, False))[0]
+        g = weight.grad
+        direct = (g is not None and g.dtype == torch.float32 and g.shape == weight.shape
+                  and g.is_contiguous(memory_format=torch.channels_last))
+        if direct:
+            C.conv_wgrad(dy, x, g, (r, s), stride, pad)
+            return dx, None, None, None, None, None
+        dw = torch.zeros((cout, r, s, cin), device=x.device, dtype=torch.float32)
+        C.conv_wgrad(dy, x, dw, (r, s), stride, pad)
+        return dx, dw.permute(0, 3, 1, 2), None, None, None, None
+
+
 class ShadowConv2d(nn.Conv2d):
     """``nn.Conv2d`` (no bias, groups=1, dilation=1) whose forward uses the bf16 shadow filter when attached."""
 
@@ -57,6 +108,15 @@ class ShadowConv2d(nn.Conv2d):
     def attach(self, w_bf16: torch.Tensor, sink: list, offset: int) -> None:
         self.w_bf16, self._sink, self._offset = w_bf16, sink, int(offset)
 
+    def tc_supported(self, x: torch.Tensor) -> bool:
+        from ..ops import conv as C
+
+        return (_tc_mode() == "tc" and self.w_bf16 is not None and x.is_cuda and x.dim() == 4
+                and self.stride[0] == self.stride[1] and self.padding[0] == self.padding[1]
+                and C.supported(self.in_channels, self.out_channels, self.kernel_size[0], self.kernel_size[1], self.stride[0],
+                                self.padding[0])
+                and x.is_contiguous(memory_format=torch.channels_last))
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.w_bf16 is None or not x.is_cuda or not torch.is_grad_enabled() or not self.weight.requires_grad:
             if self.w_bf16 is not None and x.is_cuda:
@@ -65,5 +125,24 @@ class ShadowConv2d(nn.Conv2d):
             return super().forward(x)
         if x.dtype != torch.bfloat16:
             x = x.to(torch.bfloat16)
+        if self.tc_supported(x):
+            return _TcConvFn.apply(x, self.weight, self.w_bf16, self.stride[0], self.padding[0], None)
         return _ShadowConvFn.apply(x, self.weight, self.w_bf16, tuple(self.stride), tuple(self.padding), self._sink,
                                    self._offset)
+
+
+def conv_bn(conv: nn.Module, bn: nn.Module, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``bn(conv(x), residual)``.  On the tcgen05 path the BatchNorm batch statistics come out of the convolution's
+    epilogue (one launch less and one full read of the activation less per layer); everywhere else the two modules are
+    simply composed."""
+    from ..ops.bn import FusedBatchNormAct
+
+    if (isinstance(conv, ShadowConv2d) and isinstance(bn, FusedBatchNormAct) and bn.training and torch.is_grad_enabled()
+            and conv.w_bf16 is not None and conv.weight.requires_grad and x.is_cuda):
+        if x.dtype != torch.bfloat16:
+            x = x.to(torch.bfloat16)
+        if conv.tc_supported(x) and (residual is None or residual.is_contiguous(memory_format=torch.channels_last)):
+            stats = bn.stats_buffers(x.device)
+            y = _TcConvFn.apply(x, conv.weight, conv.w_bf16, conv.stride[0], conv.padding[0], stats)
+            return bn.apply_pre(y, stats, residual)
+    return bn(conv(x), residual=residual) if residual is not None else bn(conv(x))

@@ -12,7 +12,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from .conv import ShadowConv2d
+from .conv import ShadowConv2d, conv_bn
 
 
 class _StockBNAct(nn.BatchNorm2d):
@@ -61,10 +61,10 @@ class Bottleneck(nn.Module):
         self.downsample = downsample
 
     def forward(self, x):
-        out = self.bn1(self.conv1(x))                      # BN + ReLU in one pass
-        out = self.bn2(self.conv2(out))
-        idt = x if self.downsample is None else self.downsample(x)
-        return self.bn3(self.conv3(out), residual=idt)     # BN + residual add + ReLU in one pass
+        out = conv_bn(self.conv1, self.bn1, x)             # conv (+ BN statistics in its epilogue) -> BN apply + ReLU
+        out = conv_bn(self.conv2, self.bn2, out)
+        idt = x if self.downsample is None else conv_bn(self.downsample[0], self.downsample[1], x)
+        return conv_bn(self.conv3, self.bn3, out, residual=idt)     # BN + residual add + ReLU in one pass
 
 
 class ResNet(nn.Module):

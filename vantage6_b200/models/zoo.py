@@ -78,6 +78,11 @@ def _specs() -> Dict[str, ModelSpec]:
         "resnet_tiny": ModelSpec("resnet_tiny", lambda d: resnet.resnet_tiny(10).to(memory_format=cl),
                                  resnet.imagenet_forward_loss, _image_batches(32, 10), "sgd", 0.05, "weights_f32", True,
                                  True, 2, 8, dict(momentum=0.9)),
+        # ResNet at full channel width (64..2048) but one block per stage and 64x64 images: every convolution family of
+        # ResNet-50 runs on the tcgen05 kernels (smoke / GPU tests) at a fraction of the cost
+        "resnet_mini": ModelSpec("resnet_mini", lambda d: resnet.ResNet((1, 1, 1, 1), 10).to(memory_format=cl),
+                                 resnet.imagenet_forward_loss, _image_batches(64, 10), "sgd", 0.05, "weights_f32", True,
+                                 True, 2, 16, dict(momentum=0.9)),
         "bert_base": ModelSpec("bert_base", lambda d: bert.bert_base(), bert.bert_forward_loss, _mlm_batches(30522, 128),
                                "adamw", 1e-4, "delta_bf16", True, False, 4, 32, dict(weight_decay=0.01, max_grad_norm=1.0)),
         "bert_tiny": ModelSpec("bert_tiny", lambda d: bert.bert_tiny(), bert.bert_forward_loss, _mlm_batches(512, 32),
@@ -119,4 +124,5 @@ def build_trainer(name: str, *, rank: int, world: int, device, data_plane: str =
                           server_opt=server_opt, process_group=process_group, use_cuda_graph=use_cuda_graph,
                           fused_local_optimizer=fused_local_optimizer, **kw)
     attach_shadow(tr.model, tr.fm)
+    tr._fresh_model = lambda: spec.build(torch.device("cpu"))      # FederatedTrainer.reset(seed) of a resident trainer
     return tr, spec

@@ -77,6 +77,8 @@ class Node:
         self.cryptor = DummyCryptor()
         self.gpu = self._gpu_index()
         self._org_keys: Dict[int, Optional[str]] = {}
+        self.gpu_worker: Optional[subprocess.Popen] = None          # resident GPU worker (node/gpu_worker.py)
+        self.gpu_worker_sock: Optional[str] = None
 
     # ------------------------------------------------------------------ setup
     def _gpu_index(self) -> Optional[int]:
@@ -221,7 +223,7 @@ class Node:
             (work / "input").write_bytes(plain)
             (work / "token").write_text(token)
             (work / "output").write_bytes(b"")
-            env = dict(os.environ)
+            env = self._algorithm_env()
             label = (task.get("database") or "default")
             uri = self.ctx.databases.get(label) if hasattr(self.ctx, "databases") else None
             env.update({
@@ -235,6 +237,8 @@ class Node:
                 env[f"{label.upper()}_DATABASE_URI"] = str(uri)
             if self.gpu is not None:
                 env["V6_GPU"] = str(self.gpu)
+            if self.gpu_worker_sock and self.gpu_worker is not None and self.gpu_worker.poll() is None:
+                env["V6_GPU_WORKER"] = self.gpu_worker_sock
             pkg_root = str(Path(__file__).resolve().parent.parent.parent)
             env["PYTHONPATH"] = pkg_root + os.pathsep + env.get("PYTHONPATH", "")
             proc = self._launch_algorithm(module, env, work / "log")
@@ -270,11 +274,65 @@ class Node:
             log.error("could not report result %s: %s", rid, e)
         log.info("task %s result %s: %s", task.get("id"), rid, status)
 
+    # environment variables an algorithm process inherits from the node (everything else is dropped: the reference
+    # isolates algorithms in containers -- reference vantage6/cli/node.py:320 hands the node the docker socket for that --
+    # here they are same-uid child processes, so at least the node's own secrets and unrelated settings stay out)
+    ENV_PASSTHROUGH = ("PATH", "HOME", "LANG", "LC_ALL", "TMPDIR", "USER", "LD_LIBRARY_PATH", "PYTHONPATH", "VIRTUAL_ENV",
+                       "CUDA_HOME", "CUDA_VISIBLE_DEVICES", "NVIDIA_VISIBLE_DEVICES", "XDG_RUNTIME_DIR", "V6B200_RUNTIME_DIR")
+    ENV_PREFIXES = ("V6B200_", "NCCL_", "CUDA_", "TORCH_", "OMP_", "MKL_")
+    ENV_BLOCKED = ("PRIVATE_KEY", "V6B200_ALLOW_PICKLE")
+
+    def _algorithm_env(self) -> Dict[str, str]:
+        env = {k: v for k, v in os.environ.items()
+               if (k in self.ENV_PASSTHROUGH or k.startswith(self.ENV_PREFIXES)) and k not in self.ENV_BLOCKED}
+        env["V6B200_ALLOW_PICKLE"] = "1" if self.config.get("allow_pickle") else "0"
+        log_dir = getattr(self.ctx, "log_dir", None)
+        if log_dir:
+            env["V6_LOG_DIR"] = str(log_dir)
+        return env
+
+    def _start_gpu_worker(self) -> None:
+        """GPU-pinned nodes keep ONE resident process that owns the CUDA context, the NVLink symmetric heap and the
+        trainers (model, optimizer state, captured CUDA graphs) across tasks; algorithm processes stay short-lived and
+        talk to it over a Unix socket (node/gpu_worker.py).  ``V6B200_GPU_WORKER=0`` turns it off (one CUDA bring-up
+        per task, the round-1 behaviour)."""
+        if self.gpu is None or os.environ.get("V6B200_GPU_WORKER", "1") == "0":
+            return
+        sock = str(runtime_dir() / f"gpu-worker-{self.ctx.name}-{os.getpid()}.sock")
+        env = self._algorithm_env()
+        env["V6_GPU"] = str(self.gpu)
+        pkg_root = str(Path(__file__).resolve().parent.parent.parent)
+        env["PYTHONPATH"] = pkg_root + os.pathsep + env.get("PYTHONPATH", "")
+        log_dir = getattr(self.ctx, "log_dir", None)
+        out = open(Path(log_dir) / "gpu_worker.log", "ab") if log_dir else subprocess.DEVNULL
+        self.gpu_worker = subprocess.Popen([sys.executable, "-m", "vantage6_b200.node.gpu_worker", "--socket", sock, "--gpu", str(self.gpu)],
+                                           stdout=out, stderr=subprocess.STDOUT, env=env, start_new_session=True)
+        deadline = time.time() + 180
+        while time.time() < deadline and not self._stop.is_set():
+            if self.gpu_worker.poll() is not None:
+                log.error("GPU worker exited with code %s; tasks will bring up CUDA themselves", self.gpu_worker.returncode)
+                self.gpu_worker = None
+                return
+            if os.path.exists(sock):
+                try:
+                    from .gpu_worker import call
+
+                    call(sock, {"op": "ping"}, timeout=5)
+                    self.gpu_worker_sock = sock
+                    log.info("resident GPU worker up on GPU %s (pid %s)", self.gpu, self.gpu_worker.pid)
+                    return
+                except Exception:  # noqa: BLE001
+                    pass
+            time.sleep(0.2)
+        log.warning("GPU worker did not come up in time")
+
     def _start_zygote(self) -> None:
-        """GPU-pinned nodes run long, heavyweight algorithm processes (torch + CUDA): they keep one fresh interpreter
-        per task; the warm start is for the latency-bound CPU control-plane tasks (``V6B200_ZYGOTE=1`` forces it on,
+        """Warm-start helper for the (short-lived) algorithm processes.  On GPU-pinned nodes the heavy state lives in the
+        resident GPU worker, so their algorithm processes are as light as the CPU control-plane ones and fork from the
+        zygote too; without the worker a GPU task needs a fresh interpreter (``V6B200_ZYGOTE=1`` forces the zygote on,
         ``=0`` off)."""
-        if os.environ.get("V6B200_ZYGOTE", "1" if self.gpu is None else "0") == "0":
+        default = "1" if (self.gpu is None or os.environ.get("V6B200_GPU_WORKER", "1") != "0") else "0"
+        if os.environ.get("V6B200_ZYGOTE", default) == "0":
             return
         zygote = Zygote(runtime_dir())
         try:
@@ -320,6 +378,7 @@ class Node:
         self.setup_encryption()
         self.proxy.start()
         threading.Thread(target=self._start_zygote, daemon=True).start()     # tasks arriving before it is up run cold
+        threading.Thread(target=self._start_gpu_worker, daemon=True).start()
         self.sync_open_results()
         for target in (self._listen, self._worker, self._heartbeat):
             t = threading.Thread(target=target, daemon=True)
@@ -345,6 +404,15 @@ class Node:
         except Exception:  # noqa: BLE001
             pass
         self.proxy.stop()
+        if self.gpu_worker is not None:
+            try:
+                from .gpu_worker import call
+
+                call(self.gpu_worker_sock, {"op": "shutdown"}, timeout=5)
+                self.gpu_worker.wait(timeout=10)
+            except Exception:  # noqa: BLE001
+                self._kill_proc(self.gpu_worker)
+            self.gpu_worker = None
         if self.zygote is not None:
             self.zygote.stop()
             self.zygote = None

@@ -42,22 +42,31 @@ def _fast_path(x: torch.Tensor) -> bool:
 
 class _BNFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, num_batches_tracked, eps, momentum, relu):
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, num_batches_tracked, eps, momentum, relu, pre=None):
+        """``pre`` = (mean, rstd, scale_bias) already produced by the convolution that wrote ``x`` (the statistics
+        epilogue of csrc/igemm.cu, which also updated the running statistics): only the apply pass runs here."""
         N, C, H, W = x.shape
         R = N * H * W
         y = torch.empty_like(x)                              # preserves channels_last strides
-        mean = torch.empty(C, device=x.device, dtype=torch.float32)
-        rstd = torch.empty(C, device=x.device, dtype=torch.float32)
-        scale_bias = torch.empty(2 * C, device=x.device, dtype=torch.float32)
-        part, _ = _get_scratch(x.device, C)
         mask = torch.empty((R, C // 8), device=x.device, dtype=torch.uint8) if relu else None    # 1 bit / element
-        count(2)                                             # stats(+finalize) + apply
-        native().bn_fwd(x.data_ptr(), 0 if residual is None else residual.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                        0 if running_mean is None else running_mean.data_ptr(),
-                        0 if running_var is None else running_var.data_ptr(),
-                        0 if num_batches_tracked is None else num_batches_tracked.data_ptr(), y.data_ptr(),
-                        0 if mask is None else mask.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                        scale_bias.data_ptr(), part.data_ptr(), R, C, eps, momentum, relu, stream_ptr())
+        if pre is not None:
+            mean, rstd, scale_bias = pre
+            count(1)
+            native().bn_apply(x.data_ptr(), 0 if residual is None else residual.data_ptr(), scale_bias.data_ptr(),
+                              scale_bias.data_ptr() + 4 * C, y.data_ptr(), 0 if mask is None else mask.data_ptr(), R, C, relu,
+                              stream_ptr())
+        else:
+            mean = torch.empty(C, device=x.device, dtype=torch.float32)
+            rstd = torch.empty(C, device=x.device, dtype=torch.float32)
+            scale_bias = torch.empty(2 * C, device=x.device, dtype=torch.float32)
+            part, _ = _get_scratch(x.device, C)
+            count(2)                                             # stats(+finalize) + apply
+            native().bn_fwd(x.data_ptr(), 0 if residual is None else residual.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                            0 if running_mean is None else running_mean.data_ptr(),
+                            0 if running_var is None else running_var.data_ptr(),
+                            0 if num_batches_tracked is None else num_batches_tracked.data_ptr(), y.data_ptr(),
+                            0 if mask is None else mask.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                            scale_bias.data_ptr(), part.data_ptr(), R, C, eps, momentum, relu, stream_ptr())
         ctx.save_for_backward(x, mask, gamma, mean, rstd)        # the ReLU mask, not y: 16x fewer bytes re-read
         ctx.relu, ctx.has_res, ctx.R, ctx.C = relu, residual is not None, R, C
         ctx.params = (gamma, beta)
@@ -82,8 +91,8 @@ class _BNFn(torch.autograd.Function):
                         rstd.data_ptr(), dx.data_ptr(), 0 if dres is None else dres.data_ptr(), dgamma.data_ptr(),
                         dbeta.data_ptr(), coef.data_ptr(), part.data_ptr(), ctx.R, ctx.C, ctx.relu, direct, stream_ptr())
         if direct:
-            return dx, dres, None, None, None, None, None, None, None, None
-        return dx, dres, dgamma, dbeta, None, None, None, None, None, None
+            return dx, dres, None, None, None, None, None, None, None, None, None
+        return dx, dres, dgamma, dbeta, None, None, None, None, None, None, None
 
 
 class FusedBatchNormAct(nn.BatchNorm2d):
@@ -92,6 +101,22 @@ class FusedBatchNormAct(nn.BatchNorm2d):
     def __init__(self, num_features: int, relu: bool = True, **kw):
         super().__init__(num_features, **kw)
         self.relu = relu
+
+    def stats_buffers(self, device) -> dict:
+        """Arguments of the statistics epilogue of the producing convolution (ops/conv.py::conv_fprop ``bn=``): the
+        layer's affine parameters and running statistics plus fresh per-call outputs (mean, rstd, scale | bias)."""
+        C = self.num_features
+        return dict(gamma=self.weight, beta=self.bias, running_mean=self.running_mean, running_var=self.running_var,
+                    num_batches_tracked=self.num_batches_tracked, mean=torch.empty(C, device=device, dtype=torch.float32),
+                    rstd=torch.empty(C, device=device, dtype=torch.float32),
+                    scale_bias=torch.empty(2 * C, device=device, dtype=torch.float32), eps=self.eps,
+                    momentum=0.1 if self.momentum is None else self.momentum)
+
+    def apply_pre(self, x: torch.Tensor, stats: dict, residual: Optional[torch.Tensor] = None, relu: Optional[bool] = None):
+        """Training forward when the batch statistics of ``x`` were computed by the convolution that produced it."""
+        relu = self.relu if relu is None else relu
+        return _BNFn.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var, self.num_batches_tracked,
+                           self.eps, stats["momentum"], relu, (stats["mean"], stats["rstd"], stats["scale_bias"]))
 
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None, relu: Optional[bool] = None) -> torch.Tensor:
         relu = self.relu if relu is None else relu
@@ -106,7 +131,7 @@ class FusedBatchNormAct(nn.BatchNorm2d):
             y = torch.empty_like(x)
             N, C, H, W = x.shape
             native().bn_apply(x.data_ptr(), 0 if residual is None else residual.data_ptr(), scale.data_ptr(), bias.data_ptr(),
-                              y.data_ptr(), N * H * W, C, relu, stream_ptr())
+                              y.data_ptr(), 0, N * H * W, C, relu, stream_ptr())
             return y
         y = super().forward(x)
         if residual is not None:

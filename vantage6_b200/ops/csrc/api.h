@@ -81,6 +81,7 @@ struct OptimParams {
     float lr, momentum, dampening, weight_decay, beta1, beta2, eps, bias1, bias2;
     const float* bias_ptr;         // (optional) device [2]: Adam bias corrections computed on device (CUDA-graph safe)
     float contrib_scale;   // n_i
+    const float* contrib_scale_ptr;   // (optional) device scalar that overrides contrib_scale (a captured graph reads the current n_i)
     int nesterov;
     int save_ref;          // 1: w_ref <- w(before step)
     int publish;           // 0 none, 1 delta fp32, 2 delta bf16, 3 weights fp32 (n_i * w_new)
@@ -145,8 +146,8 @@ int v6_multi_accum_bf16(const MultiAccumParams* p, float* dst, cudaStream_t s);
 int v6_bn_fwd(const void* x, const void* res, const float* gamma, const float* beta, float* running_mean, float* running_var,
               long long* num_batches_tracked, void* y, void* relu_mask, float* mean, float* rstd, float* scale_bias,
               float* scratch, long long R, int C, float eps, float momentum, int relu, cudaStream_t s);
-int v6_bn_apply(const void* x, const void* res, const float* scale, const float* bias, void* y, long long R, int C, int relu,
-                cudaStream_t s);
+int v6_bn_apply(const void* x, const void* res, const float* scale, const float* bias, void* y, void* relu_mask, long long R, int C,
+                int relu, cudaStream_t s);
 int v6_bn_bwd(const void* dy, const void* relu_mask, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
               void* dres, float* dgamma, float* dbeta, float* coef, float* scratch, long long R, int C, int relu,
               int accumulate, cudaStream_t s);

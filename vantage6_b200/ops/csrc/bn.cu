@@ -320,17 +320,18 @@ extern "C" int v6_bn_fwd(const void* x, const void* res, const float* gamma, con
 }
 
 // inference / eval: y = relu(x*scale + bias + res) with caller-provided per-channel affine
-extern "C" int v6_bn_apply(const void* x, const void* res, const float* scale, const float* bias, void* y, long long R, int C,
-                           int relu, cudaStream_t s) {
+extern "C" int v6_bn_apply(const void* x, const void* res, const float* scale, const float* bias, void* y, void* relu_mask,
+                           long long R, int C, int relu, cudaStream_t s) {
     using namespace bn;
     if (!shape_ok(C)) return (int)cudaErrorInvalidValue;
     const int ag = apply_grid(R, C);
     const __nv_bfloat16* xx = (const __nv_bfloat16*)x;
     const __nv_bfloat16* rr = (const __nv_bfloat16*)res;
     __nv_bfloat16* yy = (__nv_bfloat16*)y;
+    unsigned char* mk = (unsigned char*)relu_mask;      // training with statistics from the convolution epilogue: 1 bit / element
     if (relu) {
-        if (res) bn_apply_kernel<true, true><<<ag, THREADS, 0, s>>>(xx, rr, scale, bias, yy, nullptr, R, C);
-        else bn_apply_kernel<true, false><<<ag, THREADS, 0, s>>>(xx, rr, scale, bias, yy, nullptr, R, C);
+        if (res) bn_apply_kernel<true, true><<<ag, THREADS, 0, s>>>(xx, rr, scale, bias, yy, mk, R, C);
+        else bn_apply_kernel<true, false><<<ag, THREADS, 0, s>>>(xx, rr, scale, bias, yy, mk, R, C);
     } else {
         if (res) bn_apply_kernel<false, true><<<ag, THREADS, 0, s>>>(xx, rr, scale, bias, yy, nullptr, R, C);
         else bn_apply_kernel<false, false><<<ag, THREADS, 0, s>>>(xx, rr, scale, bias, yy, nullptr, R, C);

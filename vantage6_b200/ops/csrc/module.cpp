@@ -115,8 +115,9 @@ PYBIND11_MODULE(_C, m) {
           [](int kind, u64 w, u64 g, u64 mm, u64 v, u64 w_ref, u64 upload, u64 shadow, u64 grad_scale_ptr, long long n,
              float lr, float momentum, float dampening, float weight_decay, float beta1, float beta2, float eps, float bias1,
              float bias2, float contrib_scale, bool nesterov, bool save_ref, int publish, bool first_momentum_step, u64 stream,
-             u64 bias_ptr) {
+             u64 bias_ptr, u64 contrib_scale_ptr) {
               OptimParams p;
+              p.contrib_scale_ptr = P<float>(contrib_scale_ptr);
               p.w = P<float>(w); p.g = P<float>(g); p.m = P<float>(mm); p.v = P<float>(v); p.w_ref = P<float>(w_ref);
               p.upload = P<void>(upload); p.shadow = P<void>(shadow); p.grad_scale_ptr = P<float>(grad_scale_ptr); p.n = n;
               p.lr = lr; p.momentum = momentum; p.dampening = dampening; p.weight_decay = weight_decay; p.beta1 = beta1;
@@ -209,8 +210,8 @@ PYBIND11_MODULE(_C, m) {
                         C, eps, momentum, relu, S(s)),
               "bn_fwd");
     });
-    m.def("bn_apply", [](u64 x, u64 res, u64 scale, u64 bias, u64 y, long long R, int C, bool relu, u64 s) {
-        check(v6_bn_apply(P<void>(x), P<void>(res), P<float>(scale), P<float>(bias), P<void>(y), R, C, relu, S(s)), "bn_apply");
+    m.def("bn_apply", [](u64 x, u64 res, u64 scale, u64 bias, u64 y, u64 mask, long long R, int C, bool relu, u64 s) {
+        check(v6_bn_apply(P<void>(x), P<void>(res), P<float>(scale), P<float>(bias), P<void>(y), P<void>(mask), R, C, relu, S(s)), "bn_apply");
     });
     m.def("bn_bwd", [](u64 dy, u64 y, u64 x, u64 gamma, u64 mean, u64 rstd, u64 dx, u64 dres, u64 dgamma, u64 dbeta, u64 coef,
                        u64 scratch, long long R, int C, bool relu, bool accumulate, u64 s) {

@@ -14,6 +14,7 @@
 
 template <int KIND /*0 sgd, 1 adamw*/>
 __global__ void __launch_bounds__(512, 2) flat_optim_kernel(const OptimParams P) {
+    const float cscale = P.contrib_scale_ptr ? __ldg(P.contrib_scale_ptr) : P.contrib_scale;   // n_i (device scalar: CUDA-graph safe)
     const float gs = P.grad_scale_ptr ? *P.grad_scale_ptr : 1.f;
     const float bias1 = P.bias_ptr ? P.bias_ptr[0] : P.bias1;
     const float bias2 = P.bias_ptr ? P.bias_ptr[1] : P.bias2;
@@ -63,15 +64,15 @@ __global__ void __launch_bounds__(512, 2) flat_optim_kernel(const OptimParams P)
         }
         if (P.publish == 1) {
             st_f4(reinterpret_cast<float4*>(P.upload) + i,
-                  make_float4(P.contrib_scale * (w[0] - ref[0]), P.contrib_scale * (w[1] - ref[1]),
-                              P.contrib_scale * (w[2] - ref[2]), P.contrib_scale * (w[3] - ref[3])));
+                  make_float4(cscale * (w[0] - ref[0]), cscale * (w[1] - ref[1]),
+                              cscale * (w[2] - ref[2]), cscale * (w[3] - ref[3])));
         } else if (P.publish == 2) {
-            uint2 d = make_uint2(pack_bf16x2(P.contrib_scale * (w[0] - ref[0]), P.contrib_scale * (w[1] - ref[1])),
-                                 pack_bf16x2(P.contrib_scale * (w[2] - ref[2]), P.contrib_scale * (w[3] - ref[3])));
+            uint2 d = make_uint2(pack_bf16x2(cscale * (w[0] - ref[0]), cscale * (w[1] - ref[1])),
+                                 pack_bf16x2(cscale * (w[2] - ref[2]), cscale * (w[3] - ref[3])));
             reinterpret_cast<uint2*>(P.upload)[i] = d;
         } else if (P.publish == 3) {
             st_f4(reinterpret_cast<float4*>(P.upload) + i,
-                  make_float4(P.contrib_scale * w[0], P.contrib_scale * w[1], P.contrib_scale * w[2], P.contrib_scale * w[3]));
+                  make_float4(cscale * w[0], cscale * w[1], cscale * w[2], cscale * w[3]));
         }
         if (P.shadow) {
             reinterpret_cast<uint2*>(P.shadow)[i] = make_uint2(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]));

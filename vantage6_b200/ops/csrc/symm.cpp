@@ -78,6 +78,11 @@ Driver& drv() {
 
 thread_local std::string g_last_error;
 
+// `swizzle128` arguments: 0 = none, 1 = SWIZZLE_128B, 2 = SWIZZLE_64B, 3 = SWIZZLE_32B
+CUtensorMapSwizzle swizzle_mode(int m) {
+    return m == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : m == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : m == 3 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+}
+
 bool cu_ok(CUresult r, const char* what) {
     if (r == CUDA_SUCCESS) return true;
     const char* s = nullptr;
@@ -406,7 +411,7 @@ int v6_make_tmap_2d_bf16(void* out, uint64_t gptr, uint64_t rows, uint64_t cols,
     cuuint32_t estr[2] = {1, 1};
     CUresult r = drv().p_cuTensorMapEncodeTiled(
         reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)gptr, dims, strides, box, estr,
-        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_mode(swizzle128),
         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return cu_ok(r, "cuTensorMapEncodeTiled") ? 0 : -1;
 }
@@ -421,7 +426,7 @@ int v6_make_tmap_tiled_bf16(void* out, uint64_t gptr, int rank, const uint64_t* 
     for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
     CUresult r = drv().p_cuTensorMapEncodeTiled(
         reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, (void*)gptr, d, st, b, es,
-        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_mode(swizzle128),
         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return cu_ok(r, "cuTensorMapEncodeTiled") ? 0 : -1;
 }

@@ -25,6 +25,16 @@ def _ptr(t: Optional[torch.Tensor]) -> int:
     return 0 if t is None else t.data_ptr()
 
 
+def _scale_val(cs) -> float:
+    """``contrib_scale`` (the node's n_i) is a float or a 1-element device tensor (read by the kernel at run time, so
+    a captured CUDA graph multiplies by the CURRENT sample count)."""
+    return 1.0 if torch.is_tensor(cs) else float(cs)
+
+
+def _scale_ptr(cs) -> int:
+    return cs.data_ptr() if torch.is_tensor(cs) else 0
+
+
 @dataclass
 class FlatSGD:
     """SGD with momentum / nesterov / weight decay over flat fp32 buffers (torch semantics)."""
@@ -53,8 +63,8 @@ class FlatSGD:
             count(1)
             native().flat_optim(0, self.params.data_ptr(), grads.data_ptr(), self.buf.data_ptr(), 0, _ptr(w_ref),
                                 _ptr(upload), _ptr(shadow), _ptr(grad_scale), n, self.lr, self.momentum,
-                                self.dampening, self.weight_decay, 0.0, 0.0, 0.0, 1.0, 1.0, contrib_scale,
-                                self.nesterov, save_ref, publish, first, stream_ptr(), 0)
+                                self.dampening, self.weight_decay, 0.0, 0.0, 0.0, 1.0, 1.0, _scale_val(contrib_scale),
+                                self.nesterov, save_ref, publish, first, stream_ptr(), 0, _scale_ptr(contrib_scale))
         else:
             reference_sgd_step(self.params, grads, self.buf, self.lr, self.momentum, self.dampening,
                                self.weight_decay, self.nesterov, first, w_ref=w_ref, save_ref=save_ref, upload=upload,
@@ -113,8 +123,8 @@ class FlatAdamW:
                 bias_ptr = self._dev_bias.data_ptr()
             native().flat_optim(1, self.params.data_ptr(), grads.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                 _ptr(w_ref), _ptr(upload), _ptr(shadow), _ptr(grad_scale), n, self.lr, 0.0, 0.0,
-                                self.weight_decay, self.beta1, self.beta2, self.eps, bias1, bias2, contrib_scale,
-                                False, save_ref, publish, False, stream_ptr(), bias_ptr)
+                                self.weight_decay, self.beta1, self.beta2, self.eps, bias1, bias2, _scale_val(contrib_scale),
+                                False, save_ref, publish, False, stream_ptr(), bias_ptr, _scale_ptr(contrib_scale))
         else:
             reference_adamw_step(self.params, grads, self.m, self.v, self.lr, self.beta1, self.beta2, self.eps,
                                  self.weight_decay, self.steps, w_ref=w_ref, save_ref=save_ref, upload=upload,

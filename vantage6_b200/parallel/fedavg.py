@@ -36,6 +36,22 @@ SERVER_OPTS = {"fedavg": 0, "fedavgm": 1, "fedadam": 2}
 UPLOAD_MODES = ("weights_f32", "delta_f32", "delta_bf16")
 
 
+def device_clock_khz(device) -> int:
+    """SM clock the in-kernel timeouts (clock64 cycles) are sized against: the device's maximum, queried -- not assumed."""
+    props = torch.cuda.get_device_properties(device)
+    khz = getattr(props, "clock_rate", 0)
+    if not khz:
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(torch.device(device).index or 0)
+            khz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM) * 1000
+        except Exception:  # noqa: BLE001
+            khz = 2_000_000
+    return int(khz)
+
+
 @dataclass
 class ServerOptConfig:
     name: str = "fedavg"
@@ -104,9 +120,7 @@ class FedAvgEngine:
             self.pad = self._pad_buf.view(torch.int32, PAD_WORDS)
             self.use_multicast = bool(self._w_buf.mc_ptr) and bool(self._up_buf.mc_ptr) and want_mc
             self._cta_counter = torch.zeros(4, dtype=torch.int32, device=self.device)
-            clock_khz = torch.cuda.get_device_properties(self.device).clock_rate if hasattr(
-                torch.cuda.get_device_properties(self.device), "clock_rate") else 1_965_000
-            self.timeout_cycles = int(timeout_ms * clock_khz)
+            self.timeout_cycles = int(timeout_ms * device_clock_khz(self.device))
         else:
             self.heap = None
             self.w = torch.zeros(self.n, dtype=torch.float32, device=self.device)
@@ -118,23 +132,42 @@ class FedAvgEngine:
             self.shadow = torch.zeros(self.n, dtype=torch.bfloat16, device=self.device) if shadow_bf16 else None
             self.use_multicast = False
         # server state (fp32 master + optimizer moments). Full-size for simplicity; only the
-        # owned slice is touched.
-        self.n_reducers = 1 if server_mode == "central" else world
-        chunk = (self.n + self.n_reducers - 1) // self.n_reducers
+        # owned slice is touched.  `reducers` = the ranks that own a slice of the global model: rank 0 alone in
+        # `central` mode (the vantage6 central server), every live rank in `sharded` mode.
+        self.reducers: List[int] = [0] if server_mode == "central" else list(range(world))
+        self.w_global = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self.opt_m = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self.opt_v = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self._reshard()
+        self.sm_count = (torch.cuda.get_device_properties(self.device).multi_processor_count
+                         if self.device.type == "cuda" else 1)
+
+    def _reshard(self) -> None:
+        """(Re)compute this rank's slice [lo, hi) from the reducer list and make sure the server state it needs exists."""
+        nr = len(self.reducers)
+        chunk = (self.n + nr - 1) // nr
         chunk = (chunk + 7) // 8 * 8
-        self.lo = min(self.n, rank * chunk) if rank < self.n_reducers else 0
-        self.hi = min(self.n, self.lo + chunk) if rank < self.n_reducers else 0
-        is_reducer = rank < self.n_reducers
-        self.w_global = torch.zeros(self.n if is_reducer else 8, dtype=torch.float32, device=self.device)
-        need_m = self.opt.name in ("fedavgm", "fedadam") and is_reducer
-        need_v = self.opt.name == "fedadam" and is_reducer
-        self.opt_m = torch.zeros(self.n if need_m else 8, dtype=torch.float32, device=self.device)
-        self.opt_v = torch.zeros(self.n if need_v else 8, dtype=torch.float32, device=self.device)
+        if self.rank in self.reducers:
+            pos = self.reducers.index(self.rank)
+            self.lo = min(self.n, pos * chunk)
+            self.hi = min(self.n, self.lo + chunk)
+        else:
+            self.lo = self.hi = 0
+        self.n_reducers = nr
+        self.reducer_mask = sum(1 << r for r in self.reducers)
+        if self.is_reducer:
+            def grow(t: torch.Tensor, need: bool) -> torch.Tensor:
+                if need and t.numel() < self.n:
+                    return torch.zeros(self.n, dtype=torch.float32, device=self.device)
+                return t
+            self.w_global = grow(self.w_global, True)
+            self.opt_m = grow(self.opt_m, self.opt.name in ("fedavgm", "fedadam"))
+            self.opt_v = grow(self.opt_v, self.opt.name == "fedadam")
 
     # ------------------------------------------------------------------ helpers
     @property
     def is_reducer(self) -> bool:
-        return self.rank < self.n_reducers
+        return self.rank in self.reducers
 
     def nvlink_bytes_per_round(self) -> int:
         """Bytes this rank must pull + push over NVLink in one native round (roofline numerator)."""
@@ -146,10 +179,8 @@ class FedAvgEngine:
         push = mine * 4 * (1 if self.use_multicast else self.world - 1)
         return pull + push
 
-    def _weights_vector(self, weight: float | Sequence[float]) -> List[float]:
-        """All ranks must pass the same vector; a scalar means 'everyone reports with this n_i'."""
-        if isinstance(weight, (int, float)):
-            return [float(weight)] * self.world
+    def _weights_vector(self, weight: Sequence[float]) -> List[float]:
+        """An explicit per-rank vector (every rank must pass the same one)."""
         w = [float(x) for x in weight]
         assert len(w) == self.world
         return w
@@ -174,20 +205,67 @@ class FedAvgEngine:
             self.shadow.copy_(self.w.to(torch.bfloat16))
 
     @torch.no_grad()
-    def aggregate(self, weight: float | Sequence[float] = 1.0) -> None:
-        """One federated aggregation: after it returns (stream order) ``w`` is the new global."""
-        self._aggregate(self._weights_vector(weight), count_step=True)
+    def aggregate(self, weight: float | Sequence[float] = 1.0, prescaled: bool = False) -> None:
+        """One federated aggregation: after it returns (stream order) ``w`` is the new global.
 
-    def mark_dead(self, rank: int) -> None:
+        ``weight`` is either THIS rank's sample count ``n_i`` (a scalar: the usual case -- a node only knows its own
+        data; the counts travel to the reducers next to the contributions, through the signal pads on the native
+        plane and a tiny all-gather on the collective plane) or the full per-rank vector (identical on every rank;
+        0 = that rank does not report this round).  ``prescaled``: the contribution buffer already holds
+        ``n_i * delta`` (delta upload modes with the fused publish) -- unequal ``n_i`` then still take the in-switch
+        ``multimem.ld_reduce`` path."""
+        if isinstance(weight, (int, float)):
+            self._aggregate(None, count_step=True, my_weight=float(weight), prescaled=prescaled)
+        else:
+            self._aggregate(self._weights_vector(weight), count_step=True, prescaled=prescaled)
+
+    def mark_dead(self, rank: int, master_hint: torch.Tensor | None = None) -> None:
         """Exclude a failed node from all future rounds (every surviving rank must call this with
         the same argument, e.g. after ``poll_status()`` reported a timeout): the FedAvg weights
-        renormalise over the reporters, as with any partial participation."""
+        renormalise over the reporters, as with any partial participation.  If the dead rank owned a slice of the
+        global model the slices are re-partitioned over the surviving reducers (``central`` mode: the lowest live rank
+        takes over as the server); the fp32 master of a newly owned range is seeded from ``master_hint`` (the global
+        model of the round start, when the caller has it) or from the current parameters, and its server-optimizer
+        moments restart from zero."""
+        if not (self.live_mask >> rank) & 1:
+            return
         self.live_mask &= ~(1 << rank)
+        if rank in self.reducers:
+            old_lo, old_hi = self.lo, self.hi
+            live = [r for r in range(self.world) if (self.live_mask >> r) & 1]
+            assert live, "no live rank left"
+            self.reducers = [live[0]] if self.server_mode == "central" else [r for r in self.reducers if r != rank]
+            self._reshard()
+            if self.is_reducer and self.hi > self.lo:
+                src = master_hint if master_hint is not None else self.w
+                for a, b in ((self.lo, min(self.hi, old_lo)), (max(self.lo, old_hi), self.hi)):
+                    if b > a:       # newly owned range
+                        self.w_global[a:b].copy_(src[a:b])
+                        if self.opt_m.numel() >= self.n:
+                            self.opt_m[a:b].zero_()
+                        if self.opt_v.numel() >= self.n:
+                            self.opt_v[a:b].zero_()
 
-    def _aggregate(self, weights: List[float], count_step: bool, force_p2p: bool = False) -> None:
-        weights = [w if (self.live_mask >> r) & 1 else 0.0 for r, w in enumerate(weights)]
-        total = sum(weights)
-        assert total > 0, "at least one node must report"
+    def _gather_weights(self, my_weight: float) -> List[float]:
+        """Collective plane: exchange the per-rank sample counts (one tiny all-gather)."""
+        if self.world == 1:
+            return [my_weight]
+        import torch.distributed as dist
+
+        mine = torch.tensor([my_weight], dtype=torch.float64, device=self.device if self.device.type == "cuda" else "cpu")
+        out = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(out, mine, group=self.pg)
+        return [float(t.item()) for t in out]
+
+    def _aggregate(self, weights: List[float] | None, count_step: bool, force_p2p: bool = False, my_weight: float = 0.0,
+                   prescaled: bool = False) -> None:
+        dynamic = weights is None
+        if dynamic and self.data_plane != "native":
+            weights, dynamic = self._gather_weights(my_weight), False
+        if not dynamic:
+            weights = [w if (self.live_mask >> r) & 1 else 0.0 for r, w in enumerate(weights)]
+            total = sum(weights)
+            assert total > 0, "at least one node must report"
         self.epoch += 1
         if count_step:
             self.server_step += 1
@@ -195,34 +273,34 @@ class FedAvgEngine:
         bias1 = 1.0 / (1.0 - self.opt.beta1 ** t)
         bias2 = 1.0 / (1.0 - self.opt.beta2 ** t)
         if self.data_plane == "native":
-            all_report = all(w > 0 for w in weights)
-            equal = all_report and len(set(weights)) == 1
             mode_idx = UPLOAD_MODES.index(self.upload_mode)
             is_delta = mode_idx != 0
-            # the in-switch reduction sums un-weighted, so it is used when all n_i are equal (the
-            # mean is then sum/world); unequal n_i take the P2P path where the reducer applies n_i.
-            use_mc_ld = self.use_multicast and equal and not force_p2p
-            prescaled = False
-            eff_weights = weights
-            inv_total = 1.0 / total
-            if use_mc_ld:
-                inv_total = 1.0 / self.world
+            # The kernel decides at run time (from the n_i it received) whether the in-switch reduction applies: every
+            # rank reports and (contributions pre-scaled by n_i, or all n_i equal -> mean = sum / world); otherwise the
+            # reducer applies n_i itself on the P2P path.  Multicast needs every bound GPU alive.
+            all_live = self.live_mask == (1 << self.world) - 1
+            mc_ok = self.use_multicast and not force_p2p and all_live
             from ..ops import stream_ptr
 
             up, wb = self._up_buf, self._w_buf
             null8 = [0] * 8
             self._C.fedavg_round(
                 up.peer(), wb.peer(), self._shadow_buf.peer() if self._shadow_buf else null8, self._pad_buf.peer(),
-                up.mc() if use_mc_ld else 0, wb.mc() if (self.use_multicast and not force_p2p) else 0,
-                self._shadow_buf.mc() if (self._shadow_buf and self.use_multicast and not force_p2p) else 0,
-                self.w_global.data_ptr(), self.opt_m.data_ptr(), self.opt_v.data_ptr(), eff_weights,
-                self.lo, self.hi, self.rank, self.world, self.n_reducers, self.live_mask, self.epoch, is_delta, prescaled,
+                up.mc() if mc_ok else 0, wb.mc() if mc_ok else 0,
+                self._shadow_buf.mc() if (self._shadow_buf and mc_ok) else 0,
+                self.w_global.data_ptr(), self.opt_m.data_ptr(), self.opt_v.data_ptr(), weights if not dynamic else [0.0] * self.world,
+                self.lo, self.hi, self.rank, self.world, self.n_reducers, self.live_mask, self.epoch, is_delta, bool(prescaled),
                 SERVER_OPTS[self.opt.name], self.opt.lr, self.opt.beta1, self.opt.beta2, self.opt.eps, bias1, bias2,
-                inv_total, self.timeout_cycles, self._cta_counter.data_ptr(),
+                0.0, self.timeout_cycles, self._cta_counter.data_ptr(),
                 1 if self.upload_mode == "delta_bf16" else 0,
-                148 if (self.is_reducer and self.hi > self.lo) else 1, stream_ptr())
+                self.sm_count if (self.is_reducer and self.hi > self.lo) else 1, stream_ptr(),
+                dynamic, float(my_weight), self.reducer_mask)
         else:
-            self._aggregate_collective(weights, total, bias1, bias2)
+            if prescaled:           # the collective arm applies the weights itself
+                weights_eff = [1.0 if w > 0 else 0.0 for w in weights]
+                self._aggregate_collective(weights_eff, total, bias1, bias2)
+            else:
+                self._aggregate_collective(weights, total, bias1, bias2)
 
     # -- baseline / CPU data plane -------------------------------------------------------------
     def _aggregate_collective(self, weights, total, bias1, bias2) -> None:
@@ -238,7 +316,7 @@ class FedAvgEngine:
             contrib = self.w * my_w
         if self.world > 1:
             if self.server_mode == "central":
-                dist.reduce(contrib, dst=0, group=self.pg)
+                dist.reduce(contrib, dst=self.reducers[0], group=self.pg)
             else:
                 dist.all_reduce(contrib, group=self.pg)
         if self.is_reducer:
@@ -259,10 +337,10 @@ class FedAvgEngine:
             else:
                 wg.add_(d, alpha=o.lr)
         if self.server_mode == "central":
-            if self.rank == 0:
+            if self.rank == self.reducers[0]:
                 self.w.copy_(self.w_global)
             if self.world > 1:
-                dist.broadcast(self.w, src=0, group=self.pg)
+                dist.broadcast(self.w, src=self.reducers[0], group=self.pg)
         else:
             if self.world > 1:
                 out = torch.zeros_like(self.w)
@@ -283,6 +361,23 @@ class FedAvgEngine:
 
         self.last_status = int(self.pad[native().PAD_STATUS].item())
         return self.last_status
+
+    def missing_mask(self) -> int:
+        """Bitmask of the ranks whose contribution (or slice push) never arrived in a failed round: this rank's own
+        waits OR'd with what the other reducers reported (csrc/fedavg.cu step 6)."""
+        if self.data_plane != "native":
+            return 0
+        from ..ops import native
+
+        return int(self.pad[native().PAD_MISSING].item()) & ((1 << self.world) - 1)
+
+    def clear_status(self) -> None:
+        if self.data_plane == "native":
+            from ..ops import native
+
+            self.pad[native().PAD_STATUS] = 0
+            self.pad[native().PAD_MISSING] = 0
+            self.last_status = 0
 
     def abort(self) -> None:
         """Raise the abort flag on this rank's pad: every kernel waiting on it returns promptly."""
@@ -333,7 +428,7 @@ class SmallAggregator:
             self._slots = self.heap.alloc(2 * self.n * 4, multicast=False)      # double-buffered by epoch parity
             self._pad_buf = self.heap.alloc(PAD_WORDS * 4, multicast=False)
             self.slots = self._slots.view(torch.float32, 2 * self.n).view(2, self.n)
-            self.timeout_cycles = int(timeout_ms * 1_965_000)
+            self.timeout_cycles = int(timeout_ms * device_clock_khz(self.device))
         else:
             self.heap = None
             self.slots = torch.zeros(2, self.n, dtype=torch.float32)

@@ -34,7 +34,9 @@ class FederatedTrainer:
                  upload: str = "weights_f32", data_plane: str = "auto", multicast="auto",
                  use_cuda_graph: Optional[bool] = None, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
                  max_grad_norm: Optional[float] = None, process_group=None, include_buffers: bool = True,
-                 shadow_bf16: bool = False, fused_local_optimizer: bool = True):
+                 shadow_bf16: bool = False, fused_local_optimizer: bool = True, fault_tolerant: bool = False,
+                 metrics=None, checkpoint_dir: Optional[str] = None, checkpoint_every: int = 0,
+                 timeout_ms: Optional[float] = None):
         self.rank, self.world = rank, world
         self.device = torch.device(device)
         self.model = model.to(self.device)
@@ -44,7 +46,8 @@ class FederatedTrainer:
         n = flat_size(self.model, include_buffers)
         self.engine = FedAvgEngine(n, rank, world, self.device, data_plane=data_plane, server_mode=server_mode,
                                    server_opt=server_opt, upload=upload, multicast=multicast,
-                                   process_group=process_group, shadow_bf16=shadow_bf16)
+                                   process_group=process_group, shadow_bf16=shadow_bf16,
+                                   **({"timeout_ms": timeout_ms} if timeout_ms is not None else {}))
         self.fm = FlatModel(self.model, storage=self.engine.w, shadow=self.engine.shadow,
                             include_buffers=include_buffers)
         from ..models.transformer import attach_shadow
@@ -77,6 +80,15 @@ class FederatedTrainer:
         self._static_y: Optional[torch.Tensor] = None
         self.loss_sum = torch.zeros((), dtype=torch.float32, device=self.device)
         self._clip_scratch = torch.zeros(2, dtype=torch.float32, device=self.device) if max_grad_norm else None
+        # delta uploads are published pre-multiplied by this node's sample count n_i (a device scalar, so the captured
+        # last-step graph picks up the current value): the reducers then only sum -- in the switch when NVLS is there --
+        # and divide by sum_i n_i, whatever the n_i are
+        self.n_i = torch.ones(1, dtype=torch.float32, device=self.device)
+        self._n_host = 1.0
+        self.fault_tolerant = fault_tolerant
+        self.metrics = metrics
+        self.checkpoint_dir, self.checkpoint_every = checkpoint_dir, int(checkpoint_every)
+        self.dead: List[int] = []
         self.copy_stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
         self._staging: List[Tuple[torch.Tensor, torch.Tensor]] = []
         self.native_launches = 0            # launches of OUR kernels so far (graph replays included)
@@ -103,7 +115,7 @@ class FederatedTrainer:
                 torch.nn.utils.clip_grad_norm_([p for p in self.model.parameters() if p.requires_grad], self.max_grad_norm)
             self.torch_opt.step()
             if delta_mode and variant in ("last", "only"):
-                fused_optim.delta_publish(self.fm.params, self.w_ref[:nt], self.engine.upload[:nt], 1.0)
+                fused_optim.delta_publish(self.fm.params, self.w_ref[:nt], self.engine.upload[:nt], self._n_host)
             return
         gs = None
         if self.max_grad_norm:
@@ -113,7 +125,7 @@ class FederatedTrainer:
             publish = fused_optim.PUBLISH_DELTA_F32 if self.upload_mode == "delta_f32" else fused_optim.PUBLISH_DELTA_BF16
             first, last = variant in ("first", "only"), variant in ("last", "only")
             kw = dict(w_ref=self.w_ref[: self.fm.n_trainable], save_ref=first, upload=self.engine.upload[: self.fm.n_trainable] if last else None,
-                      publish=publish if last else fused_optim.PUBLISH_NONE, contrib_scale=1.0)
+                      publish=publish if last else fused_optim.PUBLISH_NONE, contrib_scale=self.n_i)
         shadow = self.engine.shadow[: self.fm.n_trainable] if self.engine.shadow is not None else None
         if isinstance(self.opt, fused_optim.FlatSGD):
             self.opt.step(self.fm.grad, grad_scale=gs, shadow=shadow, first_momentum_step=False if self.use_graph else None, **kw)
@@ -135,6 +147,11 @@ class FederatedTrainer:
         # snapshot mutable state, warm up on a side stream, restore
         snap = (self.engine.w.clone(), self.opt.state_dict() if self.opt else None, self.loss_sum.clone())
         snap_opt = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in snap[1].items()} if snap[1] else None
+        # stock-optimizer arm (comparator "stock_graph"): its per-parameter state must be restored IN PLACE, the captured
+        # graph keeps pointing at these buffers
+        snap_torch = None
+        if self.torch_opt is not None:
+            snap_torch = {id(p): {k: v.clone() for k, v in st.items() if torch.is_tensor(v)} for p, st in self.torch_opt.state.items()}
         s = torch.cuda.Stream(self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
@@ -154,13 +171,22 @@ class FederatedTrainer:
             self.engine.shadow.copy_(self.engine.w.to(torch.bfloat16))
         if snap_opt is not None:
             self.opt.load_state_dict(snap_opt)
+        if self.torch_opt is not None:
+            for p, st in self.torch_opt.state.items():
+                saved = snap_torch.get(id(p), {})
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        if k in saved:
+                            v.copy_(saved[k])
+                        else:
+                            v.zero_()       # state created by the warm-up steps (e.g. momentum_buffer): momentum*0 + g == torch's first step
         self.loss_sum.copy_(snap[2])
         return g
 
     def local_step(self, x: torch.Tensor, y: torch.Tensor, i: int = 0, n: int = 1) -> None:
         """One local optimisation step on device-resident (x, y)."""
         variant = self._variant(i, n)
-        if self.use_graph and self.torch_opt is None:
+        if self.use_graph:
             if variant not in self._graphs:
                 self._graphs[variant] = self._capture(variant, x, y)
             self._static_x.copy_(x, non_blocking=True)
@@ -180,6 +206,47 @@ class FederatedTrainer:
     def initialize_global(self) -> None:
         self.engine.initialize_global()
 
+    def remember_init(self, seed: int = 0) -> None:
+        """Snapshot the freshly initialised model (a resident trainer restarts later tasks from it, see :meth:`reset`)."""
+        self._init_state = (int(seed), self.engine.w.detach().clone())
+
+    @torch.no_grad()
+    def reset(self, seed: int = 0) -> None:
+        """Start a NEW federated run on this resident trainer (node/gpu_worker.py keeps trainers across tasks): model
+        back to its initial weights, local and server optimizer state cleared, round counters zeroed.  The symmetric
+        heap, the flat views, the bf16 shadow and the captured CUDA graphs are reused as they are."""
+        init = getattr(self, "_init_state", None)
+        fresh_fn = getattr(self, "_fresh_model", None)
+        if init is not None and (init[0] == int(seed) or fresh_fn is None):
+            self.engine.w.copy_(init[1])                   # same seed (or no builder): the remembered initialisation
+        elif fresh_fn is not None:
+            torch.manual_seed(int(seed))                   # a different seed: draw a new initialisation on the host
+            fresh = fresh_fn()
+            src = dict(fresh.named_parameters())
+            src.update(dict(fresh.named_buffers()))
+            for name, view in self.fm.views().items():
+                if name in src:
+                    view.copy_(src[name].detach().to(device=view.device, dtype=torch.float32))
+            self._init_state = (int(seed), self.engine.w.detach().clone())
+        if self.engine.shadow is not None:
+            self.engine.shadow.copy_(self.engine.w.to(torch.bfloat16))
+        if self.opt is not None:
+            for v in self.opt.state_dict().values():
+                if torch.is_tensor(v):
+                    v.zero_()
+            self.opt.steps = 0
+            if getattr(self.opt, "_dev_step", None) is not None:
+                self.opt._dev_step.fill_(-1)
+        if self.torch_opt is not None:
+            self.torch_opt.state.clear()
+        eng = self.engine
+        eng.w_global.zero_(); eng.opt_m.zero_(); eng.opt_v.zero_()
+        eng.server_step = 0
+        if self.w_ref is not None:
+            self.w_ref.zero_()
+        self.loss_sum.zero_()
+        self.rounds = 0
+
     def _stage(self, k: int, x: torch.Tensor, y: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         while len(self._staging) <= k:
             self._staging.append((torch.empty_like(x, device=self.device), torch.empty_like(y, device=self.device)))
@@ -196,6 +263,11 @@ class FederatedTrainer:
         n = len(batches)
         if n_samples is None:
             n_samples = float(sum(b[0].shape[0] for b in batches))
+        if self.fault_tolerant and self.rounds > 0:
+            self.recover_if_failed()                    # the previous round's status word (GPU idle here: the caller read the loss)
+        if float(n_samples) != self._n_host:
+            self._n_host = float(n_samples)
+            self.n_i.fill_(self._n_host)                # read by the (captured) publish of the last local step
         self.loss_sum.zero_()
         nt, na = self.fm.n_trainable, self.fm.n_total
         has_tail = self.upload_mode != "weights_f32" and na > nt
@@ -235,13 +307,74 @@ class FederatedTrainer:
                 d.record(cur)
                 done[i & 1] = d
         if has_tail:        # publish the buffer deltas next to the parameter deltas of the last step
-            fused_optim.delta_publish(self.fm.flat[nt:na], self.w_ref[nt:na], self.engine.upload[nt:na], 1.0)
-        agg_w = weights if weights is not None else float(n_samples)
-        self.engine.aggregate(agg_w)
+            fused_optim.delta_publish(self.fm.flat[nt:na], self.w_ref[nt:na], self.engine.upload[nt:na], self._n_host)
+        # `n_samples` is THIS node's sample count: the engine moves it to the reducers with the contribution (a node
+        # never needs to know the other nodes' counts).  An explicit `weights` vector (identical on all ranks) overrides it.
+        self._last_agg = (weights, float(n_samples))
+        self._aggregate()
         if self.engine.data_plane == "native":
             self.native_launches += 1 + (1 if has_tail else 0)
         self.rounds += 1
-        return self.loss_sum / max(n, 1)
+        loss = self.loss_sum / max(n, 1)
+        if self.metrics is not None:
+            self.metrics.log_round(self.rounds, rank=self.rank, world=self.world, local_steps=n, n_samples=float(n_samples),
+                                   dead=list(self.dead), upload=self.upload_mode,
+                                   nvlink_bytes=self.engine.nvlink_bytes_per_round() if hasattr(self.engine, "nvlink_bytes_per_round") else 0)
+        if self.checkpoint_dir and self.checkpoint_every > 0 and self.rounds % self.checkpoint_every == 0:
+            self.save_checkpoint()
+        return loss
+
+    def _aggregate(self) -> None:
+        weights, n_samples = self._last_agg
+        delta = self.upload_mode != "weights_f32"
+        if weights is not None:
+            # explicit vector: in delta modes the contributions are already multiplied by this rank's n_i = n_samples
+            if delta:
+                self.engine.aggregate([w if w > 0 else 0.0 for w in weights], prescaled=True)
+            else:
+                self.engine.aggregate(weights)
+        else:
+            self.engine.aggregate(n_samples, prescaled=delta)
+
+    # ------------------------------------------------------------------ fault handling
+    def recover_if_failed(self) -> List[int]:
+        """Turn a timed-out aggregation into partial participation: read the status word of the last round; if a
+        contributor never arrived, every survivor marks the same ranks dead (the missing set travels between the
+        reducers inside the kernel), the slices are re-partitioned, and the aggregation of that round is re-run over
+        the survivors -- their contributions are still in place because a reducer that misses a contributor pushes
+        nothing.  Returns the ranks newly marked dead."""
+        if self.engine.poll_status() == 0:
+            return []
+        mask = self.engine.missing_mask()
+        newly = [r for r in range(self.world) if (mask >> r) & 1 and r != self.rank and r not in self.dead]
+        self.engine.clear_status()
+        for r in newly:
+            self.engine.mark_dead(r, master_hint=self.w_ref)
+            self.dead.append(r)
+        if newly and getattr(self, "_last_agg", None) is not None:
+            weights, n_samples = self._last_agg
+            if weights is not None:
+                self._last_agg = ([0.0 if i in self.dead else w for i, w in enumerate(weights)], n_samples)
+            self._aggregate()
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
+            if self.engine.poll_status() != 0:
+                raise RuntimeError(f"rank {self.rank}: aggregation still failing after excluding ranks {self.dead}")
+        if self.metrics is not None and newly:
+            self.metrics.log_round(self.rounds, rank=self.rank, event="recovered", dead=list(self.dead))
+        return newly
+
+    # ------------------------------------------------------------------ checkpoint / resume (SURVEY.md 5.4)
+    def save_checkpoint(self, directory: Optional[str] = None) -> str:
+        from ..utils.checkpoint import save_checkpoint
+
+        return save_checkpoint(directory or self.checkpoint_dir, self, self.rounds)
+
+    def load_checkpoint(self, directory: Optional[str] = None) -> int:
+        from ..utils.checkpoint import load_checkpoint
+
+        self.rounds = int(load_checkpoint(directory or self.checkpoint_dir, self)["round"])
+        return self.rounds
 
     def launches_per_round(self, n_steps: int) -> int:
         """Number of OUR kernels launched in one round (bench.py ``gpu_launches``): per local step the

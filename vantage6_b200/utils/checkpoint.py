@@ -26,10 +26,15 @@ def save_checkpoint(path, trainer, round_idx: int, extra: Dict[str, Any] | None 
     for k, v in local.items():
         if torch.is_tensor(v):
             tensors[f"local.{k}"] = v.detach().cpu().clone()
+    if getattr(trainer, "w_ref", None) is not None:
+        tensors["w_ref"] = trainer.w_ref.detach().cpu().clone()
     f = path / f"rank{eng.rank}.safetensors"
     save_file(tensors, str(f))
+    if getattr(trainer, "torch_opt", None) is not None:       # stock-optimizer arm: its state is not a flat tensor set
+        torch.save(trainer.torch_opt.state_dict(), str(path / f"rank{eng.rank}.torch_opt.pt"))
     meta = {"round": int(round_idx), "server_step": int(eng.server_step), "epoch": int(eng.epoch), "world": eng.world,
             "rank": eng.rank, "server_mode": eng.server_mode, "server_opt": eng.opt.name, "lo": eng.lo, "hi": eng.hi,
+            "reducers": list(getattr(eng, "reducers", [])), "live_mask": int(eng.live_mask),
             "local_steps": int(local.get("steps", 0)) if local else 0, "extra": extra or {}}
     (path / f"rank{eng.rank}.json").write_text(json.dumps(meta))
     return path
@@ -50,7 +55,12 @@ def load_checkpoint(path, trainer) -> Dict[str, Any]:
         eng.opt_v.copy_(t["opt_v"])
         if eng.shadow is not None:
             eng.shadow.copy_(eng.w.to(torch.bfloat16))
+        if "w_ref" in t and getattr(trainer, "w_ref", None) is not None:
+            trainer.w_ref.copy_(t["w_ref"])
     eng.server_step = int(meta["server_step"])
+    topt = path / f"rank{eng.rank}.torch_opt.pt"
+    if getattr(trainer, "torch_opt", None) is not None and topt.exists():
+        trainer.torch_opt.load_state_dict(torch.load(str(topt), map_location=eng.device))
     if trainer.opt is not None:
         sd = {k[len("local."):]: v for k, v in t.items() if k.startswith("local.")}
         sd["steps"] = meta["local_steps"]

@@ -30,3 +30,8 @@ class MetricsWriter:
         bus = (nvlink_bytes / (ms * 1e-3) / 1e9) if (ms and nvlink_bytes) else None
         return self.log(event="round", round=idx, ms=ms, rounds_per_sec=1e3 / ms if ms else None, loss=loss,
                         nvlink_bytes=nvlink_bytes, bus_GBps=bus, **extra)
+
+    def log_round(self, idx: int, **fields) -> Dict[str, Any]:
+        """Bookkeeping row written by ``FederatedTrainer.run_round`` (no device synchronisation: timings and the loss
+        are added by whoever reads them back, e.g. the ``fedavg`` algorithm through :meth:`round`)."""
+        return self.log(event=fields.pop("event", "round_done"), round=idx, **fields)
