@@ -12,7 +12,7 @@ import subprocess
 import sys
 import time
 
-GROUPS = ["fprop1x1", "fprop1x1_im2col", "fprop3x3", "fprop_strided", "fprop_stats", "dgrad1x1", "dgrad3x3", "wgrad1x1", "wgrad3x3",
+GROUPS = ["dgrad_strided", "stem", "fprop1x1", "fprop1x1_im2col", "fprop3x3", "fprop_strided", "fprop_stats", "dgrad1x1", "dgrad3x3", "wgrad1x1", "wgrad3x3",
           "wgrad_strided", "linear"]
 
 
@@ -102,19 +102,19 @@ def run_group(group: str, do_time: bool):
             rec["tflops"] = 2.0 * n * p * p * cout * cin * r * r / rec["us"] * 1e-6
         emit(**rec)
 
-    def dgrad_case(n, cin, cout, h, w, r, pad, force=False, seed=0):
-        p, q = h + 2 * pad - r + 1, w + 2 * pad - r + 1
+    def dgrad_case(n, cin, cout, h, w, r, pad, force=False, seed=0, stride=1):
+        p, q = (h + 2 * pad - r) // stride + 1, (w + 2 * pad - r) // stride + 1
         dy = _mk(n, cout, p, q, seed)
         wt = (_mk(cout, cin, r, r, seed + 1) * (1.0 / (cout * r * r) ** 0.5)).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        dx = C.conv_dgrad(dy, wt, (h, w), pad, force_im2col=force)
+        dx = C.conv_dgrad(dy, wt, (h, w), pad, force_im2col=force, stride=stride)
         torch.cuda.synchronize()
-        ref = torch.nn.grad.conv2d_input((n, cin, h, w), wt.float(), dy.float(), stride=1, padding=pad)
+        ref = torch.nn.grad.conv2d_input((n, cin, h, w), wt.float(), dy.float(), stride=stride, padding=pad)
         d, rel = _rel(dx, ref)
-        rec = dict(case=f"dgrad n{n} {cin}<-{cout} {h}x{w} k{r} p{pad} force={int(force)}", max_abs=d, rel=rel, ok=rel < 2e-2)
+        rec = dict(case=f"dgrad n{n} {cin}<-{cout} {h}x{w} k{r} s{stride} p{pad} force={int(force)}", max_abs=d, rel=rel, ok=rel < 2e-2)
         if do_time:
-            rec["us"] = _time(lambda: C.conv_dgrad(dy, wt, (h, w), pad, force_im2col=force))
+            rec["us"] = _time(lambda: C.conv_dgrad(dy, wt, (h, w), pad, force_im2col=force, stride=stride))
             x0 = _mk(n, cin, h, w, seed + 5)
-            rec["cudnn_us"] = _time(lambda: torch.ops.aten.convolution_backward(dy, x0, wt, None, (1, 1), (pad, pad), (1, 1), False, (0, 0), 1, (True, False, False)))
+            rec["cudnn_us"] = _time(lambda: torch.ops.aten.convolution_backward(dy, x0, wt, None, (stride, stride), (pad, pad), (1, 1), False, (0, 0), 1, (True, False, False)))
             rec["tflops"] = 2.0 * n * h * w * cout * cin * r * r / rec["us"] * 1e-6
         emit(**rec)
 
@@ -136,8 +136,42 @@ def run_group(group: str, do_time: bool):
             rec["tflops"] = 2.0 * n * p * q * cout * cin * r * r / rec["us"] * 1e-6
         emit(**rec)
 
+    def stem_case(n, hw, cout=64, seed=0):
+        from vantage6_b200.ops import pool as PL
+
+        hs = hw // 2 + 3
+        xs = _mk(n, 16, hs, hs, seed)
+        ws = (_mk(cout, 16, 4, 4, seed + 1) * (1.0 / 256 ** 0.5)).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        y = C.stem_fprop(xs, ws)
+        torch.cuda.synchronize()
+        ref = F.conv2d(xs.float(), ws.float())
+        d, rel = _rel(y, ref)
+        dy = (_mk(n, cout, hs - 3, hs - 3, seed + 2) * 0.1).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        dws = torch.zeros((cout, 4, 4, 16), device="cuda")
+        C.stem_wgrad(dy, xs, dws)
+        torch.cuda.synchronize()
+        refw = torch.nn.grad.conv2d_weight(xs.float(), (cout, 16, 4, 4), dy.float()).permute(0, 2, 3, 1)
+        d2, rel2 = _rel(dws, refw)
+        rec = dict(case=f"stem n{n} {hw}x{hw} -> {cout}", max_abs=d, rel=rel, wgrad_rel=rel2, ok=rel < 2e-2 and rel2 < 1e-2)
+        if do_time:
+            rec["us"] = _time(lambda: C.stem_fprop(xs, ws))
+            rec["cudnn_us"] = _time(lambda: torch.ops.aten.convolution(xs, ws, None, (1, 1), (0, 0), (1, 1), False, (0, 0), 1))
+            rec["wgrad_us"] = _time(lambda: C.stem_wgrad(dy, xs, dws))
+            rec["cudnn_wgrad_us"] = _time(lambda: torch.ops.aten.convolution_backward(dy, xs, ws, None, (1, 1), (0, 0), (1, 1), False, (0, 0), 1, (False, True, False)))
+        emit(**rec)
+
     B = 64 if do_time else 8
-    if group == "fprop1x1":
+    if group == "dgrad_strided":
+        dgrad_case(2, 64, 64, 16, 16, 3, 1, stride=2)
+        dgrad_case(2, 64, 128, 16, 16, 1, 0, stride=2)
+        dgrad_case(B, 128, 128, 56, 56, 3, 1, stride=2)
+        dgrad_case(B, 256, 512, 56, 56, 1, 0, stride=2)
+        dgrad_case(B, 512, 512, 14, 14, 3, 1, stride=2)
+        dgrad_case(B, 1024, 2048, 14, 14, 1, 0, stride=2)
+    elif group == "stem":
+        stem_case(2, 32)
+        stem_case(B, 224)
+    elif group == "fprop1x1":
         fprop_case(2, 64, 64, 8, 8, 1, 1, 0)            # one tile exactly (128 pixels)
         fprop_case(B, 64, 256, 56, 56, 1, 1, 0)
         fprop_case(B, 256, 64, 56, 56, 1, 1, 0)

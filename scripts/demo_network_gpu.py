@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--model", default="resnet50")
     ap.add_argument("--rounds", type=int, default=4)
     ap.add_argument("--glm", action="store_true", help="also run the fused GLM (K8 + K3) task")
+    ap.add_argument("--repeat", type=int, default=2, help="FedAvg tasks on the same network: the 2nd.. reuse the resident GPU workers")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     home = tempfile.mkdtemp(prefix="v6gpu")
@@ -27,7 +28,8 @@ def main():
         net.start(timeout=180)
         c = net.client()
         jobs = [("v6b200/fedavg", {"method": "master", "master": True,
-                                   "kwargs": {"model": args.model, "rounds": args.rounds, "return_weights": True}})]
+                                   "kwargs": {"model": args.model, "rounds": args.rounds, "return_weights": True, "seed": 0}})
+                for _ in range(max(1, args.repeat))]
         if args.glm:
             jobs.append(("v6b200/glm", {"method": "master_fused", "master": True,
                                         "kwargs": {"iterations": 200, "lr": 2.0, "rows_per_node": 125000, "features": 256,
@@ -47,7 +49,8 @@ def main():
                 raise SystemExit(1)
             out = {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in out.items() if k not in ("coef", "weights", "w")}
             out = {k: v for k, v in out.items() if not (isinstance(v, list) and len(v) > 64)}
-            out.update({"image": image, "nodes": args.nodes, "task_wall_s": round(time.time() - t0, 2)})
+            out.update({"image": image, "nodes": args.nodes, "task_wall_s": round(time.time() - t0, 2),
+                        "task_index": len(lines), "trainer_reused": [n.get("trainer_reused") for n in out.get("nodes", [])] if isinstance(out.get("nodes"), list) else None})
             lines.append(out)
             print(json.dumps(out), flush=True)
             if args.out:                                    # incremental: a later task may time out

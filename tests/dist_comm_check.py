@@ -118,8 +118,10 @@ def main():
                         e.initialize_global()
                     torch.cuda.synchronize()
                     torch.testing.assert_close(e1.w, w0)
+                    # explicit vector; equal scalar; a non-reporting node; every rank passing only ITS OWN n_i (unequal)
                     for rnd, weights in enumerate([[float(r + 1) for r in range(world)], 4.0,
-                                                   [0.0 if (r == world - 1 and world > 1) else 2.0 for r in range(world)]]):
+                                                   [0.0 if (r == world - 1 and world > 1) else 2.0 for r in range(world)],
+                                                   float(rank + 2)]):
                         gl = torch.Generator(device=dev).manual_seed(1000 * rnd + rank)
                         step = torch.randn(e1.n, device=dev, generator=gl) * 0.1
                         for e in (e1, e2):
@@ -195,6 +197,49 @@ def main():
         res["k1_shape"] = [M, Nw, K]
         dist.barrier()
         del w_srv
+        # ---- K1 v3: the owner multicasts the tiles (multimem.st), every rank consumes from its local copy behind tile flags
+        if heap.multicast:
+            k1p = {}
+            for (M2, N2, K2) in ((4096, 2304, 768), (4096, 4096, 4096)):
+                wsym = heap.alloc(N2 * K2 * 2, multicast=True)
+                n_fl = ((N2 + 255) // 256) * ((K2 + 63) // 64)
+                fsym = heap.alloc(n_fl * 4, multicast=False)
+                w_loc = wsym.view(torch.bfloat16, N2 * K2).view(N2, K2)
+                fl = fsym.view(torch.int32, n_fl)
+                fl.zero_()
+                gsrc = torch.Generator(device=dev).manual_seed(9)
+                w1 = (torch.randn(N2, K2, device=dev, generator=gsrc) * 0.05).to(torch.bfloat16)
+                w_loc.copy_(w1 if rank == 0 else torch.zeros_like(w1))
+                x2 = torch.randn(M2, K2, device=dev, dtype=torch.bfloat16)
+                y2 = torch.empty(M2, N2, device=dev, dtype=torch.bfloat16)
+                torch.cuda.synchronize()
+                dist.barrier()
+                epq = [0]
+
+                def k1push():
+                    epq[0] += 1
+                    G.bcast_push_gemm_bf16(x2, w_loc, wsym.mc_ptr, fl, fsym.peer_ptrs, world, rank == 0, epq[0], out=y2)
+                k1push()
+                torch.cuda.synchronize()
+                ref2 = x2.float() @ w1.float().t()
+                err2 = ((y2.float() - ref2).abs().max() / ref2.abs().max()).item()
+                assert err2 < 1e-2, f"K1 push output mismatch {err2}"
+                assert torch.equal(w_loc, w1), "K1 push: weights not bit-exact on this rank"
+                dist.barrier()
+                t_push = timed(k1push, iters=20, warm=5)
+                wb2 = w1.clone() if rank == 0 else torch.empty_like(w1)
+
+                def base2():
+                    dist.broadcast(wb2, src=0)
+                    torch.matmul(x2, wb2.t(), out=y2)
+                t_base = timed(base2, iters=20, warm=5)
+                t_gemm = timed(lambda: G.gemm_bf16(x2, w_loc, out=y2), iters=20, warm=5)
+                t_cublas = timed(lambda: torch.matmul(x2, wb2.t(), out=y2), iters=20, warm=5)
+                k1p[f"{M2}x{N2}x{K2}"] = {"k1_push_ms": t_push, "nccl_bcast_then_cublas_ms": t_base, "speedup": t_base / t_push,
+                                          "plain_tcgen05_gemm_ms": t_gemm, "cublas_gemm_ms": t_cublas,
+                                          "weight_MB": N2 * K2 * 2 / 1e6}
+                dist.barrier()
+            res["k1_push"] = k1p
         heap.close()
     except AssertionError:
         raise

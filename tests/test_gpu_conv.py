@@ -77,6 +77,34 @@ def test_conv_dgrad_matches_fp32(dev, n, cin, cout, h, w, k, stride, pad):
     torch.testing.assert_close(dx.float(), ref, rtol=2e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("n,cin,cout,h,w,k,pad", [(2, 64, 64, 16, 16, 3, 1), (2, 64, 128, 16, 16, 1, 0), (3, 128, 128, 28, 28, 3, 1),
+                                                  (3, 256, 512, 28, 28, 1, 0), (5, 512, 512, 14, 14, 3, 1)])
+def test_conv_dgrad_stride2_parity_classes(dev, n, cin, cout, h, w, k, pad):
+    from vantage6_b200.ops import conv as C
+
+    p, q = (h + 2 * pad - k) // 2 + 1, (w + 2 * pad - k) // 2 + 1
+    dy, wt = _t((n, cout, p, q), 15), _t((cout, cin, k, k), 16, (cout * k * k) ** -0.5)
+    dx = C.conv_dgrad(dy, wt, (h, w), pad, stride=2)
+    ref = torch.nn.grad.conv2d_input((n, cin, h, w), wt.float(), dy.float(), stride=2, padding=pad)
+    torch.testing.assert_close(dx.float(), ref, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("n,hw", [(2, 32), (4, 224)])
+def test_stem_space_to_depth_on_tensor_cores(dev, n, hw):
+    """4x4 convolution over the 16-channel space-to-depth image through the overlapping-window im2col map."""
+    from vantage6_b200.ops import conv as C
+
+    hs = hw // 2 + 3
+    xs, ws = _t((n, 16, hs, hs), 21), _t((64, 16, 4, 4), 22, 1.0 / 16)
+    y = C.stem_fprop(xs, ws)
+    torch.testing.assert_close(y.float(), F.conv2d(xs.float(), ws.float()), rtol=2e-2, atol=2e-2)
+    dy = _t((n, 64, hs - 3, hs - 3), 23, 0.1)
+    dws = torch.zeros((64, 4, 4, 16), device=dev)
+    C.stem_wgrad(dy, xs, dws)
+    ref = torch.nn.grad.conv2d_weight(xs.float(), (64, 16, 4, 4), dy.float()).permute(0, 2, 3, 1)
+    torch.testing.assert_close(dws, ref, rtol=1e-3, atol=2e-3 * float(ref.abs().max()))
+
+
 @pytest.mark.parametrize("n,cin,cout,h,w,k,stride,pad", CASES)
 def test_conv_wgrad_accumulates_into_fp32(dev, n, cin, cout, h, w, k, stride, pad):
     from vantage6_b200.ops import conv as C

@@ -79,9 +79,9 @@ class _TcConvFn(torch.autograd.Function):
         cout, cin, r, s = w_bf16.shape
         dx = None
         if ctx.needs_input_grad[0]:
-            if stride == 1:
-                dx = C.conv_dgrad(dy, w_bf16, (x.shape[2], x.shape[3]), pad)
-            else:       # stride-2 data gradient (6 layers of ResNet-50): library kernel for now
+            if C.dgrad_supported(cin, cout, r, s, stride, pad, x.shape[2], x.shape[3]):
+                dx = C.conv_dgrad(dy, w_bf16, (x.shape[2], x.shape[3]), pad, stride=stride)
+            else:       # odd spatial sizes under stride 2: library kernel
                 dx = torch.ops.aten.convolution_backward(dy, x, w_bf16, None, (stride, stride), (pad, pad), (1, 1), False, (0, 0), 1,
                                                          (True, False, False))[0]
         g = weight.grad

@@ -24,6 +24,17 @@ from ..ops import gemm as G
 from ..ops import norm as N
 
 
+def _tc_linear_bwd(dy2: torch.Tensor, w: torch.Tensor) -> bool:
+    """Backward GEMMs of the linear layers on the hand-written tcgen05 kernels (ops/conv.py::linear_dgrad /
+    linear_wgrad, the 1x1 case of the implicit-GEMM family): default on; ``V6B200_LINEAR_BWD=cublas`` selects the library."""
+    import os
+
+    from ..ops import conv as C
+
+    return (dy2.is_cuda and dy2.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.is_contiguous()
+            and os.environ.get("V6B200_LINEAR_BWD", "tc") == "tc" and C.linear_bwd_supported(w.shape[0], w.shape[1]))
+
+
 def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """bf16 x bf16 -> fp32 (cuBLAS, fp32 output when the build supports it)."""
     try:
@@ -53,6 +64,7 @@ class _ShadowLinearFn(torch.autograd.Function):
         ctx.save_for_backward(x2, wb, pre if act != G.ACT_NONE else None)
         ctx.act, ctx.xshape = act, x.shape
         ctx.need_w = weight.requires_grad
+        ctx.weight = weight
         ctx.bias = bias                           # the Parameter itself: its .grad may be a flat-buffer view
         ctx.sink, ctx.offset = sink, offset
         return y.view(*x.shape[:-1], wb.shape[0])
@@ -65,6 +77,20 @@ class _ShadowLinearFn(torch.autograd.Function):
             dy2 = dy2.contiguous()
         # one kernel: activation derivative, bf16 dpre, bias gradient (accumulated in place when possible)
         dy2, db = G.bias_act_backward(dy2, pre, ctx.act, ctx.bias)
+        tc = _tc_linear_bwd(dy2, wb)
+        if tc:
+            from ..ops import conv as C
+
+            dx = C.linear_dgrad(dy2, wb).view(ctx.xshape) if ctx.needs_input_grad[0] else None
+            g = ctx.weight.grad if ctx.need_w else None
+            if g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.shape == wb.shape:
+                C.linear_wgrad(dy2, x2, g)              # fp32, straight into the flat gradient buffer: no bf16 dW, no sink entry
+                return dx, None, db, None, None, None, None
+            if ctx.need_w:
+                dwf = torch.zeros(wb.shape, device=dy2.device, dtype=torch.float32)
+                C.linear_wgrad(dy2, x2, dwf)
+                return dx, dwf, db, None, None, None, None
+            return dx, None, db, None, None, None, None
         dx = torch.mm(dy2, wb).view(ctx.xshape) if ctx.needs_input_grad[0] else None
         dw = None
         if ctx.need_w:
@@ -129,6 +155,12 @@ class _FrozenLinearFn(torch.autograd.Function):
     def backward(ctx, dy):
         (w,) = ctx.saved_tensors
         dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        if _tc_linear_bwd(dy2, w):
+            from ..ops import conv as C
+
+            return C.linear_dgrad(dy2, w).view(ctx.xshape), None
         return torch.mm(dy2, w).view(ctx.xshape), None
 
 

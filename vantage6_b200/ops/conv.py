@@ -53,8 +53,10 @@ def supported(cin: int, cout: int, r: int, s: int, stride: int, pad: int) -> boo
     return cin % 64 == 0 and cout % 64 == 0 and r == s and stride in (1, 2) and 0 <= pad < r
 
 
-def dgrad_supported(cin: int, cout: int, r: int, s: int, stride: int, pad: int) -> bool:
-    return supported(cin, cout, r, s, stride, pad) and stride == 1
+def dgrad_supported(cin: int, cout: int, r: int, s: int, stride: int, pad: int, h: int = 0, w: int = 0) -> bool:
+    if not supported(cin, cout, r, s, stride, pad):
+        return False
+    return stride == 1 or ((r, pad) in ((3, 1), (1, 0)) and h % 2 == 0 and w % 2 == 0)
 
 
 def out_size(h: int, r: int, stride: int, pad: int) -> int:
@@ -83,20 +85,23 @@ def conv_fprop(x: torch.Tensor, w: torch.Tensor, stride: int = 1, pad: int = 0, 
                         ptr(g.get("gamma")), ptr(g.get("beta")), ptr(g.get("running_mean")), ptr(g.get("running_var")),
                         ptr(g.get("num_batches_tracked")), ptr(g.get("mean")), ptr(g.get("rstd")), ptr(g.get("scale_bias")),
                         igemm_scratch(x.device).data_ptr() if bn else 0, float(g.get("eps", 1e-5)), float(g.get("momentum", 0.1)),
-                        force_im2col, stream_ptr())
+                        force_im2col, stream_ptr(), 0, 0, 0)
     return y
 
 
-def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw: Tuple[int, int], pad: int = 0, force_im2col: bool = False) -> torch.Tensor:
-    """Data gradient of a stride-1 convolution: ``dy`` [N, Cout, P, Q] -> dx [N, Cin, H, W] (channels_last bf16)."""
+def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw: Tuple[int, int], pad: int = 0, force_im2col: bool = False,
+               stride: int = 1) -> torch.Tensor:
+    """Data gradient of a convolution: ``dy`` [N, Cout, P, Q] -> dx [N, Cin, H, W] (channels_last bf16).  stride 2 (3x3 /
+    pad 1 and 1x1 / pad 0, even H, W): one launch that walks the 4 output-pixel parity classes, each a stride-1 implicit
+    GEMM over dY with the sub-filter that reaches it."""
     assert dy.is_cuda and dy.dtype == torch.bfloat16 and _is_cl(dy) and _is_cl(w)
     n, p, q, cout = _nhwc(dy)
     cout2, cin, r, s = w.shape
     h, wd = in_hw
-    assert cout == cout2 and p == h + 2 * pad - r + 1 and q == wd + 2 * pad - s + 1
+    assert cout == cout2 and p == out_size(h, r, stride, pad) and q == out_size(wd, s, stride, pad)
     dx = torch.empty((n, cin, h, wd), device=dy.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
     count(1)
-    native().conv_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), n, h, wd, cin, cout, r, s, pad, force_im2col, stream_ptr())
+    native().conv_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), n, h, wd, cin, cout, r, s, stride, pad, force_im2col, stream_ptr())
     return dx
 
 
@@ -111,8 +116,67 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, rs: Tuple[in
     assert dw.numel() == cout * r * s * cin
     count(1)
     native().conv_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), n, h, wd, cin, cout, r, s, stride, pad, float(scale), int(splits),
-                        force_im2col, stream_ptr())
+                        force_im2col, stream_ptr(), 0, 0, 0)
     return dw
 
 
+# ------------------------------------------------------------------------------------------------- ResNet stem
+def stem_fprop(xs: torch.Tensor, ws: torch.Tensor) -> torch.Tensor:
+    """The 7x7 / stride-2 stem as a 4x4 / stride-1 convolution on the 16-channel space-to-depth image ``xs``
+    [N, 16, Hs, Ws] (ops/pool.py) -- on the tensor cores: the 4 horizontally adjacent 16-channel pixels of a filter row are
+    64 contiguous bf16 in NHWC memory, so the image is read through an im2col map whose "pixels" are those overlapping
+    64-element windows (pixel pitch 32 B): a 4x1 convolution with Cin = 64, K = 4 x 64 = 256."""
+    n, c16, hs, wsz = xs.shape
+    cout = ws.shape[0]
+    assert c16 == 16 and tuple(ws.shape[1:]) == (16, 4, 4) and _is_cl(xs) and _is_cl(ws)
+    p, q = hs - 3, wsz - 3
+    y = torch.empty((n, cout, p, q), device=xs.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+    count(1)
+    native().conv_fprop(xs.data_ptr(), ws.data_ptr(), y.data_ptr(), 0, 0, n, hs, q, 64, cout, 4, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1e-5,
+                        0.1, True, stream_ptr(), 32, wsz * 32, hs * wsz * 32)
+    return y
+
+
+def stem_wgrad(dy: torch.Tensor, xs: torch.Tensor, dws: torch.Tensor) -> torch.Tensor:
+    """``dws`` (fp32 [Cout, 4, 4, 16]) += dy^T . im2col(xs) through the same overlapping-window view."""
+    n, c16, hs, wsz = xs.shape
+    cout = dy.shape[1]
+    assert dws.dtype == torch.float32 and dws.numel() == cout * 256
+    count(1)
+    native().conv_wgrad(dy.data_ptr(), xs.data_ptr(), dws.data_ptr(), n, hs, wsz - 3, 64, cout, 4, 1, 1, 0, 1.0, 0, True, stream_ptr(),
+                        32, wsz * 32, hs * wsz * 32)
+    return dws
+
+
 FORCE_IM2COL = os.environ.get("V6B200_CONV_FORCE_IM2COL") == "1"
+
+
+# ------------------------------------------------------------------------------------------------- nn.Linear backward
+def linear_bwd_supported(n_out: int, k_in: int) -> bool:
+    """dX = dY . W (DGRAD form: K = n_out in 64-blocks) and dW += dY^T . X (WGRAD form: columns = k_in in 64-chunks)."""
+    return n_out % 64 == 0 and k_in % 64 == 0
+
+
+def linear_dgrad(dy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """``dx[M, K] = dy[M, N] . w[N, K]`` -- the weight is read in place as an MN-major UMMA operand (no transpose)."""
+    assert dy.is_cuda and dy.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and dy.is_contiguous() and w.is_contiguous()
+    m, n = dy.shape
+    n2, k = w.shape
+    assert n == n2
+    dx = torch.empty((m, k), device=dy.device, dtype=torch.bfloat16)
+    count(1)
+    native().conv_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), 1, 1, m, k, n, 1, 1, 1, 0, False, stream_ptr())
+    return dx
+
+
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """``dw[N, K] (fp32) += scale * dy[M, N]^T . x[M, K]`` -- both operands MN-major, split-K over the M rows, fp32
+    accumulation straight into ``dw`` (e.g. the ``.grad`` view of a flat model)."""
+    assert dy.is_cuda and dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and dy.is_contiguous() and x.is_contiguous()
+    assert dw.dtype == torch.float32 and dw.is_contiguous()
+    m, n = dy.shape
+    m2, k = x.shape
+    assert m == m2 and dw.numel() == n * k
+    count(1)
+    native().conv_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), 1, 1, m, k, n, 1, 1, 1, 0, float(scale), 0, False, stream_ptr(), 0, 0, 0)
+    return dw

@@ -154,6 +154,9 @@ int v6_bn_bwd(const void* dy, const void* relu_mask, const void* x, const float*
 int v6_gemm2_bf16(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, int lda, int ldb, int ldc,
                   int act, cudaStream_t stream);
 int v6_gemm_smem_bytes();
+int v6_bcast_push_gemm_bf16(const void* A, void* B_local, void* B_mc, void* C, const float* bias, int M, int N, int K, int lda, int ldb,
+                            int ldc, int act, uint32_t* ready_flags, const PeerTable* flag_peers, int world, int is_owner,
+                            uint32_t epoch, cudaStream_t stream);
 int v6_flash_attn_fwd2_vmn(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S, int Hq, int Hkv,
                            int D, long long ldq, long long ldk, long long ldv, float softmax_scale, int causal,
                            cudaStream_t stream);
@@ -175,17 +178,21 @@ int v6_make_tmap_2d_bf16(void* out, uint64_t gptr, uint64_t rows, uint64_t cols,
 int v6_make_tmap_tiled_bf16(void* out, uint64_t gptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                             const uint32_t* box, int swizzle128);
 int v6_make_tmap_im2col_bf16(void* out, uint64_t gptr, uint64_t C, uint64_t W, uint64_t H, uint64_t N, int lower_w, int lower_h,
-                             int upper_w, int upper_h, uint32_t channels, uint32_t pixels, uint32_t stride_w, uint32_t stride_h);
+                             int upper_w, int upper_h, uint32_t channels, uint32_t pixels, uint32_t stride_w, uint32_t stride_h,
+                             uint64_t pitch_w, uint64_t pitch_h, uint64_t pitch_n);
+int v6_stem_wgrad_d2s_f32(const float* dws, float* dw, int O, int accumulate, cudaStream_t s);
 // igemm.cu: implicit-GEMM convolution / linear-backward family
 long long v6_igemm_scratch_floats();
 int v6_conv_fprop(const void* x, const void* w, void* y, const float* bias, int act, int N, int H, int W, int Cin, int Cout, int R,
                   int S, int stride, int pad, const float* gamma, const float* beta, float* running_mean, float* running_var,
                   long long* num_batches_tracked, float* mean_out, float* rstd_out, float* scale_bias_out, float* scratch,
-                  float eps, float momentum, int force_im2col, cudaStream_t stream);
-int v6_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int R, int S, int pad,
+                  float eps, float momentum, int force_im2col, long long pitch_w, long long pitch_h, long long pitch_n,
+                  cudaStream_t stream);
+int v6_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad,
                   int force_im2col, cudaStream_t stream);
 int v6_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad,
-                  float scale, int splits, int force_im2col, cudaStream_t stream);
+                  float scale, int splits, int force_im2col, long long pitch_w, long long pitch_h, long long pitch_n,
+                  cudaStream_t stream);
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,13 @@ struct Params {
     int stages;                // smem ring depth (kStages or kStagesK1)
     uint32_t* ready_flags;     // [num_n_blk * num_k_blk] local, zero before round 1
     uint32_t epoch;            // flags are compared against this monotonically increasing value
+    // K1 v3 ("push", fused_bcast == 2): the OWNER of the weights multicasts every tile once through the switch
+    // (multimem.st: egress 1x instead of one pull per consumer) and raises the tile's flag on every rank; all ranks
+    // (the owner included) consume tiles from their local copy as the flags arrive.
+    int is_owner, world, ldb;
+    const __nv_bfloat16* b_src;      // owner's source (its own copy of the weights)
+    __nv_bfloat16* b_mc;             // multicast VA over every rank's weight buffer
+    PeerTable flag_peers;            // every rank's flag array (peer VAs)
 };
 
 V6_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
@@ -168,7 +175,38 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
         // first k-blocks of every column land first; all CTAs pull in parallel (NVLink saturated)
         // and never wait on anything but their own staging slots, so the GEMM tiles can start as
         // soon as their first weight tiles are local: transfer and MMA overlap tile by tile.
-        if (P.fused_bcast && lane == 0) {
+        if (P.fused_bcast == 2) {
+            // ---- push: owner only.  Tile order k-major like the consumers' first k-blocks; one tile = 256 rows x 128 B.
+            if (P.is_owner) {
+                const int n_tiles = num_k * num_n;
+                const int rsub = lane >> 3, ch = lane & 7;                      // 4 rows x 8 sixteen-byte chunks per warp instruction
+                for (int idx = blockIdx.x; idx < n_tiles; idx += gridDim.x) {
+                    const int kb = idx / num_n, nb = idx % num_n;
+                    const int rows = min(BLOCK_N, P.N - nb * BLOCK_N);
+                    const size_t base = (size_t)(nb * BLOCK_N) * P.ldb + (size_t)kb * BLOCK_K + ch * 8;
+                    const bool col_ok = kb * BLOCK_K + ch * 8 < P.K;
+#pragma unroll 1
+                    for (int r0 = 0; r0 < rows; r0 += 32) {
+                        uint4 v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int r = r0 + u * 4 + rsub;
+                            if (r < rows && col_ok) v[u] = *reinterpret_cast<const uint4*>(P.b_src + base + (size_t)r * P.ldb);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int r = r0 + u * 4 + rsub;
+                            if (r < rows && col_ok) multimem_st_u4(reinterpret_cast<uint4*>(P.b_mc + base + (size_t)r * P.ldb), v[u]);
+                        }
+                    }
+                    fence_acq_rel_sys();                       // every lane's multicast stores before the flag
+                    __syncwarp();
+                    if (lane < P.world)
+                        st_release_sys_u32(reinterpret_cast<uint32_t*>(P.flag_peers.p[lane]) + nb * num_k + kb, P.epoch);
+                    __syncwarp();
+                }
+            }
+        } else if (P.fused_bcast && lane == 0) {
             const int n_pull = num_k * num_n;
             uint8_t* stg = smem + PULL_OFF;
             int slot = 0; uint32_t ph[2] = {0, 0};
@@ -284,7 +322,7 @@ static int launch_gemm(const void* A, const void* B, const void* B_src, void* C,
     else tbs = tb;
     alignas(64) CUtensorMap tc;
     if (v6_make_tmap_2d_bf16(&tc, (uint64_t)C, M, N, (uint64_t)ldc * 2, 32, 64, 1)) return -2;
-    Params P;
+    Params P = {};
     P.M = M; P.N = N; P.K = K; P.C = (__nv_bfloat16*)C; P.ldc = ldc; P.bias = bias; P.act = act;
     P.fused_bcast = B_src ? 1 : 0; P.ready_flags = ready_flags; P.epoch = epoch;
     P.stages = B_src ? kStagesK1 : kStages;
@@ -310,5 +348,35 @@ extern "C" int v6_bcast_gemm_bf16(const void* A, void* B_local, const void* B_se
                                   int M, int N, int K, int lda, int ldb, int ldc, int act, uint32_t* ready_flags,
                                   uint32_t epoch, cudaStream_t stream) {
     return launch_gemm(A, B_local, B_server_peer, C, bias, M, N, K, lda, ldb, ldc, act, ready_flags, epoch, 0, stream);
+}
+// K1 v3: C = A . W^T where W (the global model's weight) is multicast by its owner from inside this kernel.
+//   B_local: this rank's copy (a buffer of the symmetric heap, bound to `B_mc`); flags: this rank's flag array;
+//   flag_peers: every rank's flag array.  The owner passes is_owner = 1 (its B_local holds the new weights).
+extern "C" int v6_bcast_push_gemm_bf16(const void* A, void* B_local, void* B_mc, void* C, const float* bias, int M, int N, int K,
+                                       int lda, int ldb, int ldc, int act, uint32_t* ready_flags, const PeerTable* flag_peers,
+                                       int world, int is_owner, uint32_t epoch, cudaStream_t stream) {
+    using namespace gemm;
+    if (K % 8 != 0 || lda % 8 != 0 || ldb % 8 != 0 || ldc % 8 != 0 || !B_mc) return (int)cudaErrorInvalidValue;
+    alignas(64) CUtensorMap ta, tb, tc;
+    if (v6_make_tmap_2d_bf16(&ta, (uint64_t)A, M, K, (uint64_t)lda * 2, BLOCK_M, BLOCK_K, 1)) return -2;
+    if (v6_make_tmap_2d_bf16(&tb, (uint64_t)B_local, N, K, (uint64_t)ldb * 2, BLOCK_N, BLOCK_K, 1)) return -2;
+    if (v6_make_tmap_2d_bf16(&tc, (uint64_t)C, M, N, (uint64_t)ldc * 2, 32, 64, 1)) return -2;
+    Params P = {};
+    P.M = M; P.N = N; P.K = K; P.C = (__nv_bfloat16*)C; P.ldc = ldc; P.bias = bias; P.act = act;
+    P.fused_bcast = 2; P.ready_flags = ready_flags; P.epoch = epoch; P.stages = kStages;
+    P.is_owner = is_owner; P.world = world; P.ldb = ldb; P.b_src = (const __nv_bfloat16*)B_local; P.b_mc = (__nv_bfloat16*)B_mc;
+    P.flag_peers = *flag_peers;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int num_tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
+    // the owner needs enough CTAs to push every weight tile promptly even when the GEMM itself has few output tiles
+    int grid = num_tiles < 148 ? (is_owner ? 148 : num_tiles) : 148;
+    gemm_bf16_kernel<<<grid, kThreads, SMEM_BYTES, stream>>>(ta, tb, tb, tc, P);
+    V6_CHECK_LAUNCH();
+    return 0;
 }
 extern "C" int v6_gemm_smem_bytes() { return gemm::SMEM_BYTES; }

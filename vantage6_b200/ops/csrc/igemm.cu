@@ -68,6 +68,15 @@ struct Params {
     int flip;                  // DGRAD: filter tap used = taps-1-tap
     int act;                   // bf16 epilogue: 0 none, 1 gelu(erf), 2 relu
     const float* bias;         // [N] or null
+    // DGRAD of a stride-2 convolution: one work item = (output parity class, tile); a class (a, b) holds the dX pixels
+    // (2i + a, 2j + b) and receives only the filter taps r = a + pad (mod 2), s = b + pad (mod 2): a stride-1 implicit
+    // GEMM over dY with that sub-filter, rows scattered to the class' pixels by direct 64-byte stores.
+    int dstride, ncls;
+    int cls_ntap[4], cls_a[4], cls_b[4];
+    unsigned char cls_off[4][4];     // dq | dp << 4 : im2col offset of the tap inside dY
+    unsigned char cls_wtap[4][4];    // filter tap r * S + s
+    int OH, OW, zero_fill;           // dX spatial size; zero_fill: also write zeros to the 3 pixels no tap reaches (1x1 / s2)
+    __nv_bfloat16* dx;
     // WGRAD
     float* dw; long long ldw; int splits, kb_per_split; float out_scale;
     // FPROP BatchNorm statistics (null gamma -> off)
@@ -126,7 +135,7 @@ V6_DEVINL void mbar_wait_u(uint32_t bar, uint32_t parity) {           // bounded
     }
 }
 
-struct Item { int m_blk, n_blk, kb0, kb1; };
+struct Item { int m_blk, n_blk, kb0, kb1, cls; };
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -145,20 +154,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     const int num_m = (P.M + BLOCK_M - 1) / BLOCK_M;
     const int num_n = (P.N + P.block_n - 1) / P.block_n;
     const int num_tiles = num_m * num_n;
-    const int num_items = MODE == WGRAD ? num_tiles * P.splits : num_tiles;
+    const bool strided = MODE == DGRAD && P.dstride == 2;
+    const int num_items = MODE == WGRAD ? num_tiles * P.splits : (strided ? num_tiles * P.ncls : num_tiles);
     // smem ring: a stage = A tile (16 KB) + B tile (block_n rows of 128 B); narrow tiles get a deeper ring
     const int stage_bytes = A_BYTES + P.block_n * 128;
     const int num_stages = min(kMaxStages, RING_BYTES / stage_bytes);
 
     auto decode = [&](int item) {
         Item it;
-        const int tile = MODE == WGRAD ? item % num_tiles : item;
+        it.cls = 0;
+        const int tile = (MODE == WGRAD || strided) ? item % num_tiles : item;
         it.m_blk = tile % num_m;                                  // m fastest: concurrent CTAs share the filter block
         it.n_blk = tile / num_m;
         if (MODE == WGRAD) {
             const int split = item / num_tiles;
             it.kb0 = split * P.kb_per_split;
             it.kb1 = min(P.num_kb, it.kb0 + P.kb_per_split);
+        } else if (strided) {
+            it.cls = item / num_tiles;                              // classes are ordered heaviest first by the host
+            it.kb0 = 0; it.kb1 = P.cls_ntap[it.cls] * P.cblocks;
         } else { it.kb0 = 0; it.kb1 = P.num_kb; }
         return it;
     };
@@ -198,7 +212,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     const int nch = P.block_n >> 6;
                     const uint32_t tx = MODE == FPROP ? A_BYTES + P.block_n * 128 : A_BYTES + nch * BOX_BYTES;
                     int tap = 0, tap_s = 0, tap_r = 0, cb = 0;   // k-block = (filter tap, 64-channel block), advanced incrementally
-                    for (int kb = 0; kb < P.num_kb; ++kb) {
+                    if (strided) { tap_s = P.cls_off[it.cls][0] & 15; tap_r = P.cls_off[it.cls][0] >> 4; }
+                    for (int kb = 0; kb < it.kb1; ++kb) {
                         const uint32_t fb = full0 + stage * 8;
                         mbar_wait_u(empty0 + stage * 8, phase ^ 1);
                         const uint32_t sa = smem0 + stage * stage_bytes, sb = sa + A_BYTES;
@@ -208,10 +223,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         if (MODE == FPROP) {
                             tma_load_2d_u(sb, &tmap_b, fb, kb * BLOCK_K, n0);
                         } else {
-                            const int wtap = P.flip ? P.taps - 1 - tap : tap;
+                            const int wtap = strided ? P.cls_wtap[it.cls][tap] : (P.flip ? P.taps - 1 - tap : tap);
                             for (int j = 0; j < nch; ++j) tma_load_3d_u(sb + j * BOX_BYTES, &tmap_b, fb, n0 + j * 64, wtap, cb * 64);
                         }
-                        if (++cb == P.cblocks) { cb = 0; ++tap; if (++tap_s == P.S) { tap_s = 0; ++tap_r; } }
+                        if (++cb == P.cblocks) {
+                            cb = 0; ++tap;
+                            if (strided) { const int o = P.cls_off[it.cls][tap & 3]; tap_s = o & 15; tap_r = o >> 4; }
+                            else if (++tap_s == P.S) { tap_s = 0; ++tap_r; }
+                        }
                         if (++stage == num_stages) { stage = 0; phase ^= 1; }
                     }
                 } else {
@@ -348,6 +367,27 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                                 }
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                            }
+                            if (strided) {
+                                // scatter: row (n, i, j) of the class grid -> dX pixel (2i + a, 2j + b); 32 channels = 64 B per thread
+                                const int m = row0 + lane;
+                                if (m < P.M) {
+                                    const int n_img = m / P.PQ, rem = m - n_img * P.PQ;
+                                    const int oi = 2 * (rem / P.Q), oj = 2 * (rem % P.Q);
+                                    __nv_bfloat16* base = P.dx + ((size_t)n_img * P.OH * P.OW) * P.N + col0;
+                                    uint4* dst = reinterpret_cast<uint4*>(base + ((size_t)(oi + P.cls_a[it.cls]) * P.OW + oj + P.cls_b[it.cls]) * P.N);
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                                    if (P.zero_fill) {
+#pragma unroll
+                                        for (int z = 1; z < 4; ++z) {
+                                            uint4* zd = reinterpret_cast<uint4*>(base + ((size_t)(oi + (z >> 1)) * P.OW + oj + (z & 1)) * P.N);
+#pragma unroll
+                                            for (int j = 0; j < 4; ++j) zd[j] = make_uint4(0u, 0u, 0u, 0u);
+                                        }
+                                    }
+                                }
+                                continue;
                             }
                             uint8_t* sbox = stg + box * STG_BOX_BYTES;
                             if (lane == 0) tma_store_wait_read_1();           // the store that last used THIS box has read it
@@ -489,6 +529,7 @@ struct ConvGeom {
     int N, H, W, C;          // the im2col-side activation tensor (NHWC)
     int R, S, stride, pad;   // filter window / traversal over that tensor
     int P, Q;                // traversal output size
+    long long pitch_w = 0, pitch_h = 0, pitch_n = 0;      // byte pitches (0 = dense)
 };
 
 int set_smem_attr() {
@@ -505,7 +546,7 @@ int set_smem_attr() {
 
 int im2col_map(void* out, const void* ptr, const ConvGeom& g, int pixels) {
     return v6_make_tmap_im2col_bf16(out, (uint64_t)ptr, g.C, g.W, g.H, g.N, -g.pad, -g.pad, g.pad - (g.S - 1), g.pad - (g.R - 1), 64, pixels,
-                                    g.stride, g.stride);
+                                    g.stride, g.stride, (uint64_t)g.pitch_w, (uint64_t)g.pitch_h, (uint64_t)g.pitch_n);
 }
 
 int pick_block_n(int M, int N) {
@@ -522,7 +563,7 @@ int launch(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     int rc = set_smem_attr();
     if (rc) return rc;
     const int num_m = (P.M + BLOCK_M - 1) / BLOCK_M, num_n = (P.N + P.block_n - 1) / P.block_n;
-    const int items = mode == WGRAD ? num_m * num_n * P.splits : num_m * num_n;
+    const int items = mode == WGRAD ? num_m * num_n * P.splits : (mode == DGRAD && P.dstride == 2 ? num_m * num_n * P.ncls : num_m * num_n);
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
     const int cap = sms < MAX_SLOTS ? sms : MAX_SLOTS;
@@ -540,14 +581,15 @@ int launch(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
 extern "C" int v6_conv_fprop(const void* x, const void* w, void* y, const float* bias, int act, int N, int H, int W, int Cin, int Cout,
                              int R, int S, int stride, int pad, const float* gamma, const float* beta, float* running_mean,
                              float* running_var, long long* num_batches_tracked, float* mean_out, float* rstd_out,
-                             float* scale_bias_out, float* scratch, float eps, float momentum, int force_im2col, cudaStream_t stream) {
+                             float* scale_bias_out, float* scratch, float eps, float momentum, int force_im2col, long long pitch_w,
+                             long long pitch_h, long long pitch_n, cudaStream_t stream) {
     using namespace igemm;
-    if (Cin % 64 != 0 || Cout % 8 != 0 || R != S) return (int)cudaErrorInvalidValue;
+    if (Cin % 64 != 0 || Cout % 8 != 0 || (R != S && pad != 0)) return (int)cudaErrorInvalidValue;
     const int Pp = (H + 2 * pad - R) / stride + 1, Qq = (W + 2 * pad - S) / stride + 1;
     const long long Mll = (long long)N * Pp * Qq;
     if (Mll >= (1LL << 31)) return (int)cudaErrorInvalidValue;
     const int M = (int)Mll, K = R * S * Cin;
-    const bool plain = R == 1 && stride == 1 && pad == 0 && !force_im2col;
+    const bool plain = R == 1 && S == 1 && stride == 1 && pad == 0 && !force_im2col && !pitch_w;
     Params P = {};
     P.M = M; P.N = Cout; P.num_kb = K / 64; P.block_n = pick_block_n(M, Cout);
     P.a_im2col = plain ? 0 : 1; P.PQ = Pp * Qq; P.Q = Qq; P.stride = stride; P.pad = pad; P.S = S; P.cblocks = Cin / 64; P.taps = R * S;
@@ -563,47 +605,86 @@ extern "C" int v6_conv_fprop(const void* x, const void* w, void* y, const float*
     }
     alignas(64) CUtensorMap ta, tb, tc;
     if (plain) { if (v6_make_tmap_2d_bf16(&ta, (uint64_t)x, M, Cin, (uint64_t)Cin * 2, BLOCK_M, BLOCK_K, 1)) return -2; }
-    else { ConvGeom g{N, H, W, Cin, R, S, stride, pad, Pp, Qq}; if (im2col_map(&ta, x, g, BLOCK_M)) return -2; }
+    else { ConvGeom g{N, H, W, Cin, R, S, stride, pad, Pp, Qq, pitch_w, pitch_h, pitch_n}; if (im2col_map(&ta, x, g, BLOCK_M)) return -2; }
     if (v6_make_tmap_2d_bf16(&tb, (uint64_t)w, Cout, K, (uint64_t)K * 2, P.block_n, BLOCK_K, 1)) return -2;
     if (v6_make_tmap_2d_bf16(&tc, (uint64_t)y, M, Cout, (uint64_t)Cout * 2, 32, 32, 2)) return -2;      // 32 x 32 boxes, SWIZZLE_64B
     return launch(FPROP, ta, tb, tc, P, stream);
 }
 
 // dx[N,H,W,Cin] = conv_transpose(dy[N,P,Q,Cout], w[Cout,R,S,Cin]) for stride 1 (P = H + 2*pad - R + 1)
-extern "C" int v6_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int R, int S, int pad,
-                             int force_im2col, cudaStream_t stream) {
+extern "C" int v6_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
+                             int pad, int force_im2col, cudaStream_t stream) {
     using namespace igemm;
     if (Cout % 64 != 0 || Cin % 8 != 0 || R != S) return (int)cudaErrorInvalidValue;
-    const int Pp = H + 2 * pad - R + 1, Qq = W + 2 * pad - S + 1;        // dY spatial size
-    const long long Mll = (long long)N * H * W;
-    if (Mll >= (1LL << 31)) return (int)cudaErrorInvalidValue;
-    const int M = (int)Mll;
-    const bool plain = R == 1 && pad == 0 && !force_im2col;
-    Params P = {};
-    P.M = M; P.N = Cin; P.num_kb = R * S * (Cout / 64); P.block_n = pick_block_n(M, Cin);
-    P.a_im2col = plain ? 0 : 1; P.PQ = H * W; P.Q = W; P.stride = 1; P.pad = R - 1 - pad; P.S = S; P.cblocks = Cout / 64; P.taps = R * S; P.flip = 1;
     alignas(64) CUtensorMap ta, tb, tc;
-    if (plain) { if (v6_make_tmap_2d_bf16(&ta, (uint64_t)dy, M, Cout, (uint64_t)Cout * 2, BLOCK_M, BLOCK_K, 1)) return -2; }
-    else { ConvGeom g{N, Pp, Qq, Cout, R, S, 1, R - 1 - pad, H, W}; if (im2col_map(&ta, dy, g, BLOCK_M)) return -2; }
     {
         const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)(R * S), (uint64_t)Cout};
         const uint64_t strides[2] = {(uint64_t)Cin * 2, (uint64_t)R * S * Cin * 2};
         const uint32_t box[3] = {64, 1, 64};
         if (v6_make_tmap_tiled_bf16(&tb, (uint64_t)w, 3, dims, strides, box, 1)) return -2;
     }
+    Params P = {};
+    if (stride == 2) {
+        // 3x3 / pad 1 (4 parity classes with 1, 2, 2, 4 taps) and 1x1 / pad 0 (one class, the other pixels are zeros)
+        if (!((R == 3 && pad == 1) || (R == 1 && pad == 0)) || (H & 1) || (W & 1)) return (int)cudaErrorInvalidValue;
+        const int Pp = H / 2, Qq = W / 2;
+        const long long Mll = (long long)N * Pp * Qq;
+        if (Mll >= (1LL << 31)) return (int)cudaErrorInvalidValue;
+        P.M = (int)Mll; P.N = Cin; P.block_n = pick_block_n(P.M, Cin);
+        P.a_im2col = 1; P.PQ = Pp * Qq; P.Q = Qq; P.stride = 1; P.pad = 0; P.S = S; P.cblocks = Cout / 64; P.taps = R * S;
+        P.dstride = 2; P.OH = H; P.OW = W; P.dx = (__nv_bfloat16*)dx;
+        int nc = 0;
+        // heaviest class first so that the long work items start early
+        for (int pass = 4; pass >= 1; --pass)
+            for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 2; ++b) {
+                    int rs[2], dps[2], nr = 0, ss[2], dqs[2], ns = 0;
+                    for (int r = 0; r < R; ++r) if (((a + pad - r) & 1) == 0 && a + pad - r >= 0) { rs[nr] = r; dps[nr++] = (a + pad - r) / 2; }
+                    for (int q = 0; q < S; ++q) if (((b + pad - q) & 1) == 0 && b + pad - q >= 0) { ss[ns] = q; dqs[ns++] = (b + pad - q) / 2; }
+                    if (nr * ns != pass) continue;
+                    P.cls_a[nc] = a; P.cls_b[nc] = b; P.cls_ntap[nc] = nr * ns;
+                    for (int i = 0; i < nr; ++i)
+                        for (int j = 0; j < ns; ++j) {
+                            P.cls_off[nc][i * ns + j] = (unsigned char)(dqs[j] | (dps[i] << 4));
+                            P.cls_wtap[nc][i * ns + j] = (unsigned char)(rs[i] * S + ss[j]);
+                        }
+                    ++nc;
+                }
+        P.ncls = nc;
+        P.zero_fill = (R == 1) ? 1 : 0;
+        P.num_kb = P.cls_ntap[0] * P.cblocks;
+        // dY traversed with stride 1: base pixel (i, j), tap offsets 0 / +1 (a 2-tap window with one row / column of back
+        // padding: lower corner 0, upper corner 0)
+        ConvGeom g{N, Pp, Qq, Cout, 1, 1, 1, 0, Pp, Qq};
+        if (im2col_map(&ta, dy, g, BLOCK_M)) return -2;
+        tc = ta;
+        return launch(DGRAD, ta, tb, tc, P, stream);
+    }
+    if (stride != 1) return (int)cudaErrorInvalidValue;
+    const int Pp = H + 2 * pad - R + 1, Qq = W + 2 * pad - S + 1;        // dY spatial size
+    const long long Mll = (long long)N * H * W;
+    if (Mll >= (1LL << 31)) return (int)cudaErrorInvalidValue;
+    const int M = (int)Mll;
+    const bool plain = R == 1 && pad == 0 && !force_im2col;
+    P.M = M; P.N = Cin; P.num_kb = R * S * (Cout / 64); P.block_n = pick_block_n(M, Cin);
+    P.a_im2col = plain ? 0 : 1; P.PQ = H * W; P.Q = W; P.stride = 1; P.pad = R - 1 - pad; P.S = S; P.cblocks = Cout / 64; P.taps = R * S; P.flip = 1;
+    P.dstride = 1;
+    if (plain) { if (v6_make_tmap_2d_bf16(&ta, (uint64_t)dy, M, Cout, (uint64_t)Cout * 2, BLOCK_M, BLOCK_K, 1)) return -2; }
+    else { ConvGeom g{N, Pp, Qq, Cout, R, S, 1, R - 1 - pad, H, W}; if (im2col_map(&ta, dy, g, BLOCK_M)) return -2; }
     if (v6_make_tmap_2d_bf16(&tc, (uint64_t)dx, M, Cin, (uint64_t)Cin * 2, 32, 32, 2)) return -2;
     return launch(DGRAD, ta, tb, tc, P, stream);
 }
 
 // dw[Cout,R,S,Cin] (fp32) += scale * dy[N,P,Q,Cout]^T . im2col(x[N,H,W,Cin])
 extern "C" int v6_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
-                             int pad, float scale, int splits, int force_im2col, cudaStream_t stream) {
+                             int pad, float scale, int splits, int force_im2col, long long pitch_w, long long pitch_h, long long pitch_n,
+                             cudaStream_t stream) {
     using namespace igemm;
-    if (Cin % 64 != 0 || Cout % 8 != 0 || R != S) return (int)cudaErrorInvalidValue;
+    if (Cin % 64 != 0 || Cout % 8 != 0 || (R != S && pad != 0)) return (int)cudaErrorInvalidValue;
     const int Pp = (H + 2 * pad - R) / stride + 1, Qq = (W + 2 * pad - S) / stride + 1;
     const long long pix = (long long)N * Pp * Qq;
     if (pix >= (1LL << 31)) return (int)cudaErrorInvalidValue;
-    const bool plain = R == 1 && stride == 1 && pad == 0 && !force_im2col;
+    const bool plain = R == 1 && S == 1 && stride == 1 && pad == 0 && !force_im2col && !pitch_w;
     Params P = {};
     P.M = Cout; P.N = R * S * Cin; P.num_kb = (int)((pix + 63) / 64); P.block_n = 256;
     P.b_im2col = plain ? 0 : 1; P.PQ = Pp * Qq; P.Q = Qq; P.stride = stride; P.pad = pad; P.S = S; P.cblocks = Cin / 64; P.taps = R * S;
@@ -620,7 +701,7 @@ extern "C" int v6_conv_wgrad(const void* dy, const void* x, float* dw, int N, in
     alignas(64) CUtensorMap ta, tb, tc;
     if (v6_make_tmap_2d_bf16(&ta, (uint64_t)dy, (uint64_t)pix, Cout, (uint64_t)Cout * 2, 64, 64, 1)) return -2;
     if (plain) { if (v6_make_tmap_2d_bf16(&tb, (uint64_t)x, (uint64_t)pix, Cin, (uint64_t)Cin * 2, 64, 64, 1)) return -2; }
-    else { ConvGeom g{N, H, W, Cin, R, S, stride, pad, Pp, Qq}; if (im2col_map(&tb, x, g, 64)) return -2; }
+    else { ConvGeom g{N, H, W, Cin, R, S, stride, pad, Pp, Qq, pitch_w, pitch_h, pitch_n}; if (im2col_map(&tb, x, g, 64)) return -2; }
     tc = ta;
     return launch(WGRAD, ta, tb, tc, P, stream);
 }

@@ -242,22 +242,27 @@ PYBIND11_MODULE(_C, m) {
 
     // ------------------------------------------------------------------ implicit-GEMM convolution family (igemm.cu)
     m.attr("IGEMM_SCRATCH_FLOATS") = v6_igemm_scratch_floats();
+    m.def("stem_wgrad_d2s_f32", [](u64 dws, u64 dw, int O, bool accumulate, u64 s) {
+        check(v6_stem_wgrad_d2s_f32(P<float>(dws), P<float>(dw), O, accumulate, S(s)), "stem_wgrad_d2s_f32");
+    });
     m.def("conv_fprop", [](u64 x, u64 w, u64 y, u64 bias, int act, int N, int H, int W, int Cin, int Cout, int R, int Sw, int stride,
                            int pad, u64 gamma, u64 beta, u64 rmean, u64 rvar, u64 nbt, u64 mean, u64 rstd, u64 scale_bias,
-                           u64 scratch, float eps, float momentum, bool force_im2col, u64 s) {
+                           u64 scratch, float eps, float momentum, bool force_im2col, u64 s, long long pitch_w, long long pitch_h,
+                           long long pitch_n) {
         check(v6_conv_fprop(P<void>(x), P<void>(w), P<void>(y), P<float>(bias), act, N, H, W, Cin, Cout, R, Sw, stride, pad,
                             P<float>(gamma), P<float>(beta), P<float>(rmean), P<float>(rvar), P<long long>(nbt), P<float>(mean),
-                            P<float>(rstd), P<float>(scale_bias), P<float>(scratch), eps, momentum, force_im2col, S(s)),
+                            P<float>(rstd), P<float>(scale_bias), P<float>(scratch), eps, momentum, force_im2col, pitch_w, pitch_h,
+                            pitch_n, S(s)),
               "conv_fprop");
     });
-    m.def("conv_dgrad", [](u64 dy, u64 w, u64 dx, int N, int H, int W, int Cin, int Cout, int R, int Sw, int pad, bool force_im2col,
-                           u64 s) {
-        check(v6_conv_dgrad(P<void>(dy), P<void>(w), P<void>(dx), N, H, W, Cin, Cout, R, Sw, pad, force_im2col, S(s)), "conv_dgrad");
+    m.def("conv_dgrad", [](u64 dy, u64 w, u64 dx, int N, int H, int W, int Cin, int Cout, int R, int Sw, int stride, int pad,
+                           bool force_im2col, u64 s) {
+        check(v6_conv_dgrad(P<void>(dy), P<void>(w), P<void>(dx), N, H, W, Cin, Cout, R, Sw, stride, pad, force_im2col, S(s)), "conv_dgrad");
     });
     m.def("conv_wgrad", [](u64 dy, u64 x, u64 dw, int N, int H, int W, int Cin, int Cout, int R, int Sw, int stride, int pad,
-                           float scale, int splits, bool force_im2col, u64 s) {
+                           float scale, int splits, bool force_im2col, u64 s, long long pitch_w, long long pitch_h, long long pitch_n) {
         check(v6_conv_wgrad(P<void>(dy), P<void>(x), P<float>(dw), N, H, W, Cin, Cout, R, Sw, stride, pad, scale, splits,
-                            force_im2col, S(s)), "conv_wgrad");
+                            force_im2col, pitch_w, pitch_h, pitch_n, S(s)), "conv_wgrad");
     });
     // ------------------------------------------------------------------ K1 / tcgen05 GEMM
     m.def("gemm_bf16", [](u64 A, u64 B, u64 C, u64 bias, int M, int N, int K, int lda, int ldb, int ldc, int act, u64 s) {
@@ -272,6 +277,13 @@ PYBIND11_MODULE(_C, m) {
                                  ldc, act, P<uint32_t>(flags), epoch, S(s)), "bcast_gemm_bf16");
     });
     m.def("gemm_smem_bytes", &v6_gemm_smem_bytes);
+    m.def("bcast_push_gemm_bf16", [](u64 A, u64 B_local, u64 B_mc, u64 C, u64 bias, int M, int N, int K, int lda, int ldb, int ldc,
+                                     int act, u64 flags, const std::vector<u64>& flag_peers, int world, bool is_owner, uint32_t epoch,
+                                     u64 s) {
+        PeerTable t = table(flag_peers);
+        check(v6_bcast_push_gemm_bf16(P<void>(A), P<void>(B_local), P<void>(B_mc), P<void>(C), P<float>(bias), M, N, K, lda, ldb,
+                                      ldc, act, P<uint32_t>(flags), &t, world, is_owner ? 1 : 0, epoch, S(s)), "bcast_push_gemm_bf16");
+    });
 
     m.def("flash_attn_bwd", [](u64 q, u64 k, u64 v, u64 dout, u64 kt, u64 qt, u64 dot, u64 lse2, u64 delta, u64 dq, u64 dk,
                                u64 dv, int B, int Sq, int Hq, int Hkv, int D, float scale, bool causal, u64 s) {

@@ -186,12 +186,13 @@ __global__ void stem_weight_s2d_kernel(const T* __restrict__ w, __nv_bfloat16* _
 }
 
 // dw[o][kh][kw][c] (fp32) (+)= dws[o][p][q][ch]
-__global__ void stem_wgrad_d2s_kernel(const __nv_bfloat16* __restrict__ dws, float* __restrict__ dw, int O, int accumulate) {
+template <typename T>
+__global__ void stem_wgrad_d2s_kernel(const T* __restrict__ dws, float* __restrict__ dw, int O, int accumulate) {
     const int total = O * 147;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
         const int c = t % 3, kw = (t / 3) % 7, kh = (t / 21) % 7, o = t / 147;
         const int p = (kh + 1) >> 1, r = (kh + 1) & 1, q = (kw + 1) >> 1, s2 = (kw + 1) & 1;
-        const float g = __bfloat162float(dws[((o * 4 + p) * 4 + q) * 16 + (r * 2 + s2) * 3 + c]);
+        const float g = (float)dws[((o * 4 + p) * 4 + q) * 16 + (r * 2 + s2) * 3 + c];
         dw[t] = accumulate ? dw[t] + g : g;
     }
 }
@@ -257,6 +258,13 @@ extern "C" int v6_stem_weight_s2d(const void* w, int w_is_bf16, void* ws, int O,
 extern "C" int v6_stem_wgrad_d2s(const void* dws, float* dw, int O, int accumulate, cudaStream_t s) {
     using namespace pool;
     stem_wgrad_d2s_kernel<<<grid_for((long long)O * 147), THREADS, 0, s>>>((const __nv_bfloat16*)dws, dw, O, accumulate);
+    V6_CHECK_LAUNCH();
+    return 0;
+}
+// same, from the fp32 filter gradient the tcgen05 WGRAD kernel accumulates (igemm.cu)
+extern "C" int v6_stem_wgrad_d2s_f32(const float* dws, float* dw, int O, int accumulate, cudaStream_t s) {
+    using namespace pool;
+    stem_wgrad_d2s_kernel<<<grid_for((long long)O * 147), THREADS, 0, s>>>(dws, dw, O, accumulate);
     V6_CHECK_LAUNCH();
     return 0;
 }

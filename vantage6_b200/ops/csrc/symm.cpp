@@ -435,10 +435,13 @@ int v6_make_tmap_tiled_bf16(void* out, uint64_t gptr, int rank, const uint64_t* 
 // output pixels x `channels` channels; base pixels range over [lower, dim + upper) with the traversal stride, the
 // filter-tap offset is given per load.  SWIZZLE_128B, out-of-bounds (padding) elements are zero-filled.
 int v6_make_tmap_im2col_bf16(void* out, uint64_t gptr, uint64_t C, uint64_t W, uint64_t H, uint64_t N, int lower_w, int lower_h,
-                             int upper_w, int upper_h, uint32_t channels, uint32_t pixels, uint32_t stride_w, uint32_t stride_h) {
+                             int upper_w, int upper_h, uint32_t channels, uint32_t pixels, uint32_t stride_w, uint32_t stride_h,
+                             uint64_t pitch_w, uint64_t pitch_h, uint64_t pitch_n) {
     if (!drv().ok) { g_last_error = "CUDA driver not available: " + drv().err; return -1; }
     cuuint64_t dims[4] = {C, W, H, N};
-    cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+    // byte pitches of the w / h / n dimensions; 0 = dense NHWC.  (Overlapping "virtual" pixels -- pitch_w < C*2 -- are
+    // legal for TMA: the space-to-depth stem reads 4 neighbouring 16-channel pixels as one 64-channel pixel.)
+    cuuint64_t strides[3] = {pitch_w ? pitch_w : C * 2, pitch_h ? pitch_h : W * C * 2, pitch_n ? pitch_n : H * W * C * 2};
     int lower[2] = {lower_w, lower_h};
     int upper[2] = {upper_w, upper_h};
     cuuint32_t estr[4] = {1, stride_w, stride_h, 1};

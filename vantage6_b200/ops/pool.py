@@ -69,6 +69,12 @@ def image_normalize(img: torch.Tensor, mean: Sequence[float], std: Sequence[floa
     return ((img.float() - m) / s).contiguous(memory_format=torch.channels_last)
 
 
+def _stem_tc() -> bool:
+    import os
+
+    return os.environ.get("V6B200_CONV", "tc") == "tc" and os.environ.get("V6B200_STEM", "tc") == "tc"
+
+
 class _StemS2DFn(torch.autograd.Function):
     """7x7/s2/p3 stem convolution on 3 channels as a 4x4/s1 convolution on the 16-channel space-to-depth image
     (csrc/pool.cu).  ``weight`` is the fp32 master filter ([O,3,7,7], channels-last memory), ``w_src`` the tensor the
@@ -81,7 +87,13 @@ class _StemS2DFn(torch.autograd.Function):
         src = weight.detach() if w_src is None else w_src
         count(1)
         native().stem_weight_s2d(src.data_ptr(), src.dtype == torch.bfloat16, ws.data_ptr(), O, stream_ptr())
-        y = torch.ops.aten.convolution(xs, ws, None, (1, 1), (0, 0), (1, 1), False, (0, 0), 1)
+        ctx.tc = _stem_tc() and O % 64 == 0
+        if ctx.tc:      # tcgen05 implicit GEMM through an overlapping-window im2col map (ops/conv.py::stem_fprop)
+            from . import conv as C
+
+            y = C.stem_fprop(xs, ws)
+        else:
+            y = torch.ops.aten.convolution(xs, ws, None, (1, 1), (0, 0), (1, 1), False, (0, 0), 1)
         ctx.save_for_backward(xs, ws)
         ctx.weight = weight
         return y
@@ -90,18 +102,26 @@ class _StemS2DFn(torch.autograd.Function):
     def backward(ctx, dy):
         xs, ws = ctx.saved_tensors
         w = ctx.weight
+        g = w.grad
+        direct = g is not None and g.dtype == torch.float32 and g.is_contiguous(memory_format=torch.channels_last)
+        dw = g if direct else torch.empty(w.shape, device=w.device, dtype=torch.float32, memory_format=torch.channels_last)
+        if ctx.tc:
+            from . import conv as C
+
+            if not dy.is_contiguous(memory_format=torch.channels_last):
+                dy = dy.contiguous(memory_format=torch.channels_last)
+            dws32 = torch.zeros((w.shape[0], 4, 4, 16), device=w.device, dtype=torch.float32)
+            C.stem_wgrad(dy, xs, dws32)
+            count(1)
+            native().stem_wgrad_d2s_f32(dws32.data_ptr(), dw.data_ptr(), w.shape[0], direct, stream_ptr())
+            return (None, None, None) if direct else (None, dw, None)
         _, dws, _ = torch.ops.aten.convolution_backward(dy, xs, ws, None, (1, 1), (0, 0), (1, 1), False, (0, 0), 1,
                                                         (False, True, False))
         if not dws.is_contiguous(memory_format=torch.channels_last):
             dws = dws.contiguous(memory_format=torch.channels_last)
         count(1)
-        g = w.grad
-        if g is not None and g.dtype == torch.float32 and g.is_contiguous(memory_format=torch.channels_last):
-            native().stem_wgrad_d2s(dws.data_ptr(), g.data_ptr(), w.shape[0], True, stream_ptr())     # straight into the flat grads
-            return None, None, None
-        dw = torch.empty(w.shape, device=w.device, dtype=torch.float32, memory_format=torch.channels_last)
-        native().stem_wgrad_d2s(dws.data_ptr(), dw.data_ptr(), w.shape[0], False, stream_ptr())
-        return None, dw, None
+        native().stem_wgrad_d2s(dws.data_ptr(), dw.data_ptr(), w.shape[0], direct, stream_ptr())     # direct: straight into the flat grads
+        return (None, None, None) if direct else (None, dw, None)
 
 
 def stem_s2d_supported(img: torch.Tensor, conv: nn.Conv2d) -> bool:
