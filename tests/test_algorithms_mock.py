@@ -158,3 +158,18 @@ def test_graft_entry_build_is_incremental():
     for fn in ("fedavg_round", "small_allreduce", "flat_optim", "layernorm_fwd", "rmsnorm_bwd", "rope", "glm_logistic_grad",
                "gemm_bf16", "bcast_gemm_bf16", "flash_attn_fwd", "symm_alloc"):
         assert hasattr(C, fn), fn
+
+
+def test_peer_channel_single_node_cpu():
+    """algorithm/peer.py (the in-box stand-in for vantage6's algorithm VPN): same API on a CPU node."""
+    from vantage6_b200.algorithm.peer import PeerChannel
+
+    ch = PeerChannel.open({"addr": "127.0.0.1", "port": 0, "world": 1, "ranks": {"7": 0}}, organization_id=7)
+    buf = ch.alloc(100)
+    assert buf.local.numel() >= 100 and buf.mc_ptr == 0
+    out = ch.allreduce([1.0, 2.0, 3.0], 5.0)
+    assert out.tolist() == [1.0, 2.0, 3.0]
+    out = ch.allreduce([1.0, 2.0, 3.0], 5.0, normalize=False)
+    assert out.tolist() == [5.0, 10.0, 15.0]
+    ch.barrier()
+    ch.close()

@@ -276,3 +276,39 @@ def test_item_endpoints_respect_collaboration_reach(server):
     mine = NodeClient("http://127.0.0.1", port, "/api")
     mine.authenticate("key-a")
     assert mine.request(f"task/{t['id']}")["name"] == "secret"
+
+
+def test_websocket_event_channel_pushes_and_authorises(server):
+    """The scalable event channel (server/ws_events.py, one asyncio thread for every listener): events are pushed to the
+    rooms an identity may see; a bad token is refused; a Viewer of another organization does not receive the task event."""
+    import json as _json
+
+    from websockets.sync.client import connect
+
+    app, port = server
+    alice, carol = user(port, "alice", "pw-a"), user(port, "carol", "pw-c")
+    ws_port = alice.request("health")["event_port"]
+    assert ws_port
+    since = alice.request("health")["events"]
+    node = NodeClient("http://127.0.0.1", port, "/api")
+    node.authenticate("key-a")
+    with connect(f"ws://127.0.0.1:{ws_port}/?token={node.token}&since={since}") as ws_node, \
+            connect(f"ws://127.0.0.1:{ws_port}/?token={carol.token}&since={since}") as ws_carol:
+        t = alice.task.create(collaboration=1, organizations=[1], name="pushed", image="img", input={"method": "m"})
+        ev = _json.loads(ws_node.recv(timeout=5))
+        while ev["name"] != "new_task":                     # the node's own status change arrives first
+            ev = _json.loads(ws_node.recv(timeout=5))
+        assert ev["data"]["task_id"] == t["id"]
+        with pytest.raises(TimeoutError):
+            ws_carol.recv(timeout=0.5)
+    # replay after `since`: a listener that connects later still gets the buffered event
+    with connect(f"ws://127.0.0.1:{ws_port}/?token={node.token}&since={since}") as ws2:
+        ev = _json.loads(ws2.recv(timeout=5))
+        while ev["name"] != "new_task":
+            ev = _json.loads(ws2.recv(timeout=5))
+        assert ev["data"]["task_id"] == t["id"]
+    from websockets.exceptions import ConnectionClosed
+
+    with connect(f"ws://127.0.0.1:{ws_port}/?token=garbage") as bad:
+        with pytest.raises(ConnectionClosed):
+            bad.recv(timeout=5)

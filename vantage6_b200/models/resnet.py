@@ -12,7 +12,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from .conv import ShadowConv2d, conv_bn
+from .conv import GradFork, ShadowConv2d, conv_bn
 
 
 class _StockBNAct(nn.BatchNorm2d):
@@ -61,10 +61,15 @@ class Bottleneck(nn.Module):
         self.downsample = downsample
 
     def forward(self, x):
-        out = conv_bn(self.conv1, self.bn1, x)             # conv (+ BN statistics in its epilogue) -> BN apply + ReLU
+        # the block input feeds conv1 AND the identity / downsample branch: the gradient of the second branch is handed to
+        # conv1's data-gradient kernel instead of being added by a separate pass (GradFork; only armed on the tcgen05 path)
+        fork = GradFork() if (self.training and torch.is_grad_enabled() and x.requires_grad) else None
+        out = conv_bn(self.conv1, self.bn1, x, fork_in=fork)       # conv (+ BN statistics in its epilogue) -> BN apply + ReLU
         out = conv_bn(self.conv2, self.bn2, out)
-        idt = x if self.downsample is None else conv_bn(self.downsample[0], self.downsample[1], x)
-        return conv_bn(self.conv3, self.bn3, out, residual=idt)     # BN + residual add + ReLU in one pass
+        if self.downsample is None:
+            return conv_bn(self.conv3, self.bn3, out, residual=x, res_fork=fork)     # BN + residual add + ReLU in one pass
+        idt = conv_bn(self.downsample[0], self.downsample[1], x, fork_out=fork)
+        return conv_bn(self.conv3, self.bn3, out, residual=idt)
 
 
 class ResNet(nn.Module):

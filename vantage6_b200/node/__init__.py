@@ -162,21 +162,59 @@ class Node:
         self._seen.add(result["id"])
         self.queue.put(result)
 
+    def _handle_event(self, ev: dict) -> None:
+        if ev["name"] == "new_task" and ev["data"].get("organization_id") == self.client.organization_id:
+            r = self.client.request(f"result/{ev['data']['result_id']}", params={"include": "task"})
+            if r.get("finished_at") is None:
+                self._enqueue(r)
+        elif ev["name"] == "kill_containers":
+            self.kill_task(ev["data"].get("task_id"))
+
+    def _listen_websocket(self, since) -> Optional[int]:
+        """Push channel (server/ws_events.py): returns the last event id seen when the connection ends, ``None`` when the
+        server offers no websocket channel (-> long-poll)."""
+        if os.environ.get("V6B200_EVENTS", "ws") != "ws":
+            return None
+        try:
+            from websockets.sync.client import connect
+        except Exception:  # noqa: BLE001
+            return None
+        port = self.client.request("health").get("event_port")
+        if not port:
+            return None
+        from urllib.parse import urlsplit
+
+        host = urlsplit(str(self.client.host)).hostname or "127.0.0.1"
+        if since is None:
+            since = self.client.request("health").get("events", 0)
+        url = f"ws://{host}:{port}/?token={self.client.token}&since={since}"
+        with connect(url, open_timeout=10, max_size=1 << 20) as ws:
+            log.info("event channel: websocket %s:%s", host, port)
+            self.sync_open_results()            # close the race between the first sync and the subscription
+            while not self._stop.is_set():
+                try:
+                    msg = ws.recv(timeout=1.0)
+                except TimeoutError:
+                    continue
+                ev = json.loads(msg)
+                since = max(since, ev["id"])
+                self._handle_event(ev)
+        return since
+
     def _listen(self) -> None:
         since = None
         while not self._stop.is_set():
             try:
+                got = self._listen_websocket(since)
+                if got is not None:
+                    since = got
+                    continue
                 params = {"timeout": 20}
                 if since is not None:
                     params["since"] = since
                 reply = self.client.request("event", params=params, timeout=40)
                 for ev in reply.get("events", []):
-                    if ev["name"] == "new_task" and ev["data"].get("organization_id") == self.client.organization_id:
-                        r = self.client.request(f"result/{ev['data']['result_id']}", params={"include": "task"})
-                        if r.get("finished_at") is None:
-                            self._enqueue(r)
-                    elif ev["name"] == "kill_containers":
-                        self.kill_task(ev["data"].get("task_id"))
+                    self._handle_event(ev)
                 if since is None:
                     self.sync_open_results()        # close the race between the first sync and the subscription
                 since = reply.get("last_id", since)

@@ -42,7 +42,8 @@ def _fast_path(x: torch.Tensor) -> bool:
 
 class _BNFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, num_batches_tracked, eps, momentum, relu, pre=None):
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, num_batches_tracked, eps, momentum, relu, pre=None,
+                res_fork=None):
         """``pre`` = (mean, rstd, scale_bias) already produced by the convolution that wrote ``x`` (the statistics
         epilogue of csrc/igemm.cu, which also updated the running statistics): only the apply pass runs here."""
         N, C, H, W = x.shape
@@ -70,6 +71,7 @@ class _BNFn(torch.autograd.Function):
         ctx.save_for_backward(x, mask, gamma, mean, rstd)        # the ReLU mask, not y: 16x fewer bytes re-read
         ctx.relu, ctx.has_res, ctx.R, ctx.C = relu, residual is not None, R, C
         ctx.params = (gamma, beta)
+        ctx.res_fork = res_fork             # models/conv.py::GradFork: park the residual gradient for the block's first conv
         return y
 
     @staticmethod
@@ -90,9 +92,11 @@ class _BNFn(torch.autograd.Function):
         native().bn_bwd(dy.data_ptr(), 0 if mask is None else mask.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
                         rstd.data_ptr(), dx.data_ptr(), 0 if dres is None else dres.data_ptr(), dgamma.data_ptr(),
                         dbeta.data_ptr(), coef.data_ptr(), part.data_ptr(), ctx.R, ctx.C, ctx.relu, direct, stream_ptr())
+        if dres is not None and ctx.res_fork is not None and ctx.res_fork.armed:
+            ctx.res_fork.grad, dres = dres, None
         if direct:
-            return dx, dres, None, None, None, None, None, None, None, None, None
-        return dx, dres, dgamma, dbeta, None, None, None, None, None, None, None
+            return dx, dres, None, None, None, None, None, None, None, None, None, None
+        return dx, dres, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
 class FusedBatchNormAct(nn.BatchNorm2d):
@@ -112,11 +116,12 @@ class FusedBatchNormAct(nn.BatchNorm2d):
                     scale_bias=torch.empty(2 * C, device=device, dtype=torch.float32), eps=self.eps,
                     momentum=0.1 if self.momentum is None else self.momentum)
 
-    def apply_pre(self, x: torch.Tensor, stats: dict, residual: Optional[torch.Tensor] = None, relu: Optional[bool] = None):
+    def apply_pre(self, x: torch.Tensor, stats: dict, residual: Optional[torch.Tensor] = None, relu: Optional[bool] = None,
+                  res_fork=None):
         """Training forward when the batch statistics of ``x`` were computed by the convolution that produced it."""
         relu = self.relu if relu is None else relu
         return _BNFn.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var, self.num_batches_tracked,
-                           self.eps, stats["momentum"], relu, (stats["mean"], stats["rstd"], stats["scale_bias"]))
+                           self.eps, stats["momentum"], relu, (stats["mean"], stats["rstd"], stats["scale_bias"]), res_fork)
 
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None, relu: Optional[bool] = None) -> torch.Tensor:
         relu = self.relu if relu is None else relu

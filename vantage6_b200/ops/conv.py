@@ -90,7 +90,7 @@ def conv_fprop(x: torch.Tensor, w: torch.Tensor, stride: int = 1, pad: int = 0, 
 
 
 def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw: Tuple[int, int], pad: int = 0, force_im2col: bool = False,
-               stride: int = 1) -> torch.Tensor:
+               stride: int = 1, add: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Data gradient of a convolution: ``dy`` [N, Cout, P, Q] -> dx [N, Cin, H, W] (channels_last bf16).  stride 2 (3x3 /
     pad 1 and 1x1 / pad 0, even H, W): one launch that walks the 4 output-pixel parity classes, each a stride-1 implicit
     GEMM over dY with the sub-filter that reaches it."""
@@ -100,8 +100,11 @@ def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw: Tuple[int, int], pad: i
     h, wd = in_hw
     assert cout == cout2 and p == out_size(h, r, stride, pad) and q == out_size(wd, s, stride, pad)
     dx = torch.empty((n, cin, h, wd), device=dy.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+    if add is not None:         # gradient arriving at the same tensor through another branch: folded into the epilogue (stride 1)
+        assert add.shape == dx.shape and add.dtype == torch.bfloat16 and _is_cl(add) and stride == 1
     count(1)
-    native().conv_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), n, h, wd, cin, cout, r, s, stride, pad, force_im2col, stream_ptr())
+    native().conv_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), n, h, wd, cin, cout, r, s, stride, pad, force_im2col, stream_ptr(),
+                        0 if add is None else add.data_ptr())
     return dx
 
 
@@ -165,7 +168,7 @@ def linear_dgrad(dy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     assert n == n2
     dx = torch.empty((m, k), device=dy.device, dtype=torch.bfloat16)
     count(1)
-    native().conv_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), 1, 1, m, k, n, 1, 1, 1, 0, False, stream_ptr())
+    native().conv_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), 1, 1, m, k, n, 1, 1, 1, 0, False, stream_ptr(), 0)
     return dx
 
 

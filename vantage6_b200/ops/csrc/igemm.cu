@@ -68,6 +68,8 @@ struct Params {
     int flip;                  // DGRAD: filter tap used = taps-1-tap
     int act;                   // bf16 epilogue: 0 none, 1 gelu(erf), 2 relu
     const float* bias;         // [N] or null
+    const __nv_bfloat16* add_src;   // [M, N] or null: added to the result before the bf16 rounding (DGRAD: the gradient
+                                    // that reaches the same tensor through the residual branch -> no separate add pass)
     // DGRAD of a stride-2 convolution: one work item = (output parity class, tile); a class (a, b) holds the dX pixels
     // (2i + a, 2j + b) and receives only the filter taps r = a + pad (mod 2), s = b + pad (mod 2): a stride-1 implicit
     // GEMM over dY with that sub-filter, rows scattered to the class' pixels by direct 64-byte stores.
@@ -358,6 +360,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #pragma unroll
                                     for (int j = 0; j < 32; ++j) if (col0 + j < P.N) f[j] += __ldg(P.bias + col0 + j);
                                 }
+                                if (P.add_src != nullptr && row0 + lane < P.M && col0 + 32 <= P.N) {
+                                    const uint4* ap = reinterpret_cast<const uint4*>(P.add_src + (size_t)(row0 + lane) * P.N + col0);
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        const uint4 t = __ldg(ap + j);
+                                        const float2 a0 = unpack_bf16x2(t.x), a1 = unpack_bf16x2(t.y), a2 = unpack_bf16x2(t.z), a3 = unpack_bf16x2(t.w);
+                                        f[8 * j + 0] += a0.x; f[8 * j + 1] += a0.y; f[8 * j + 2] += a1.x; f[8 * j + 3] += a1.y;
+                                        f[8 * j + 4] += a2.x; f[8 * j + 5] += a2.y; f[8 * j + 6] += a3.x; f[8 * j + 7] += a3.y;
+                                    }
+                                }
                                 if (P.act == 1) {
 #pragma unroll
                                     for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
@@ -613,9 +625,10 @@ extern "C" int v6_conv_fprop(const void* x, const void* w, void* y, const float*
 
 // dx[N,H,W,Cin] = conv_transpose(dy[N,P,Q,Cout], w[Cout,R,S,Cin]) for stride 1 (P = H + 2*pad - R + 1)
 extern "C" int v6_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
-                             int pad, int force_im2col, cudaStream_t stream) {
+                             int pad, int force_im2col, const void* add_src, cudaStream_t stream) {
     using namespace igemm;
     if (Cout % 64 != 0 || Cin % 8 != 0 || R != S) return (int)cudaErrorInvalidValue;
+    if (add_src && (stride != 1 || Cin % 32 != 0)) return (int)cudaErrorInvalidValue;
     alignas(64) CUtensorMap ta, tb, tc;
     {
         const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)(R * S), (uint64_t)Cout};
@@ -668,7 +681,7 @@ extern "C" int v6_conv_dgrad(const void* dy, const void* w, void* dx, int N, int
     const bool plain = R == 1 && pad == 0 && !force_im2col;
     P.M = M; P.N = Cin; P.num_kb = R * S * (Cout / 64); P.block_n = pick_block_n(M, Cin);
     P.a_im2col = plain ? 0 : 1; P.PQ = H * W; P.Q = W; P.stride = 1; P.pad = R - 1 - pad; P.S = S; P.cblocks = Cout / 64; P.taps = R * S; P.flip = 1;
-    P.dstride = 1;
+    P.dstride = 1; P.add_src = (const __nv_bfloat16*)add_src;
     if (plain) { if (v6_make_tmap_2d_bf16(&ta, (uint64_t)dy, M, Cout, (uint64_t)Cout * 2, BLOCK_M, BLOCK_K, 1)) return -2; }
     else { ConvGeom g{N, Pp, Qq, Cout, R, S, 1, R - 1 - pad, H, W}; if (im2col_map(&ta, dy, g, BLOCK_M)) return -2; }
     if (v6_make_tmap_2d_bf16(&tc, (uint64_t)dx, M, Cin, (uint64_t)Cin * 2, 32, 32, 2)) return -2;

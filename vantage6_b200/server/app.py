@@ -69,6 +69,7 @@ class EventBus:
         self._cond = threading.Condition()
         self._next_id = 1
         self.mirror: Optional[Callable[[dict], None]] = None
+        self.push: Optional[Callable[[dict], None]] = None     # websocket fan-out (server/ws_events.py)
 
     def emit(self, name: str, data: dict, rooms: List[str], mirrored: bool = False) -> int:
         with self._cond:
@@ -76,6 +77,11 @@ class EventBus:
             self._next_id += 1
             self._events.append(ev)
             self._cond.notify_all()
+        if self.push is not None:
+            try:
+                self.push(ev)
+            except Exception:  # noqa: BLE001
+                log.debug("event push failed", exc_info=True)
         if self.mirror is not None and not mirrored:
             try:
                 self.mirror({"name": name, "data": data, "rooms": rooms})
@@ -114,6 +120,7 @@ class ServerApp:
         self.token_expiry_s = int(config.get("token_expires_hours", 6) * 3600)
         self._routes: List[Tuple[str, re.Pattern, Callable]] = []
         self._httpd: Optional[ThreadingHTTPServer] = None
+        self.ws = None                                # websocket event channel (server/ws_events.py)
         self._thread: Optional[threading.Thread] = None
         self._register_routes()
         self.ensure_defaults()
@@ -205,6 +212,24 @@ class ServerApp:
         if sc == "global":
             return True
         return sc is not None and collaboration_id in set(self.db.organization_collaborations(ident["organization_id"]))
+
+    def event_rooms(self, ident: dict, task_id=None) -> List[str]:
+        """Event rooms an identity may listen to (shared by the long-poll endpoint and the websocket channel)."""
+        if ident["type"] == "user":
+            rooms = [f"collaboration_{c}" for c in self.db.organization_collaborations(ident["organization_id"])]
+            if self.scope_of(ident, "event", "view") == "global":
+                rooms = [f"collaboration_{c['id']}" for c in self.db.query("SELECT id FROM collaboration")]
+        else:
+            rooms = [f"collaboration_{ident['collaboration_id']}"]
+            if ident["type"] == "node":
+                rooms.append(f"node_{ident['id']}")
+        if task_id is not None:
+            t = self.db.get("task", int(task_id))
+            if t is None:
+                raise HTTPError(404, f"task id={task_id} is not found")
+            self.require_collaboration_view(ident, t["collaboration_id"], "task")
+            rooms.append(f"task_{t['id']}")
+        return rooms
 
     def require_collaboration_view(self, ident: dict, collaboration_id: int, resource: str = "task") -> None:
         if not self.can_view_collaboration(ident, collaboration_id, resource):
@@ -334,7 +359,9 @@ class ServerApp:
         @app.route("GET", "/health")
         def health(ident, body, q):
             db.one("SELECT 1 AS ok")
-            return {"database": True, "uptime_s": time.time() - app.started_at, "events": app.events.last_id()}
+            return {"database": True, "uptime_s": time.time() - app.started_at, "events": app.events.last_id(),
+                    "event_port": app.ws.port if app.ws is not None else None,
+                    "event_listeners": app.ws.connections if app.ws is not None else 0}
 
         # ---- tokens
         @app.route("POST", "/token/user")
@@ -875,20 +902,7 @@ class ServerApp:
             ident = app.require(ident)
             since = int(q.get("since", app.events.last_id()))
             timeout = min(float(q.get("timeout", 25)), 55.0)
-            if ident["type"] == "user":
-                rooms = [f"collaboration_{c}" for c in db.organization_collaborations(ident["organization_id"])]
-                if app.scope_of(ident, "event", "view") == "global":
-                    rooms = [f"collaboration_{c['id']}" for c in db.query("SELECT id FROM collaboration")]
-            else:
-                rooms = [f"collaboration_{ident['collaboration_id']}"]
-                if ident["type"] == "node":
-                    rooms.append(f"node_{ident['id']}")
-            if "task_id" in q:
-                t = db.get("task", int(q["task_id"]))
-                if t is None:
-                    raise HTTPError(404, f"task id={q['task_id']} is not found")
-                app.require_collaboration_view(ident, t["collaboration_id"], "task")
-                rooms.append(f"task_{t['id']}")
+            rooms = app.event_rooms(ident, q.get("task_id"))
             evs = app.events.wait(since, rooms, timeout)
             return {"events": evs, "last_id": evs[-1]["id"] if evs else since}
 
@@ -965,6 +979,17 @@ class ServerApp:
         threading.Thread(target=lambda: (time.sleep(1.0), self._reaper_loop()), daemon=True).start()
         self._httpd = _ApiHTTPServer((ip, port), self.make_handler())
         bound = self._httpd.server_address[1]
+        if self.config.get("event_websocket", True):
+            try:
+                from .ws_events import WebSocketEvents
+
+                ws_port = int(self.config.get("event_port") or 0)
+                self.ws = WebSocketEvents(self, ip, ws_port)
+                self.ws.start()
+                self.events.push = self.ws.publish
+            except Exception as e:  # noqa: BLE001 -- no `websockets` package: long-poll only
+                log.warning("websocket event channel unavailable (%s): long-poll only", e)
+                self.ws = None
         log.info("vantage6-b200 server %s listening on http://%s:%s%s", __version__, ip, bound, self.api_path)
         if block:
             try:
@@ -977,6 +1002,10 @@ class ServerApp:
         return bound
 
     def stop(self) -> None:
+        if getattr(self, "ws", None) is not None:
+            self.events.push = None
+            self.ws.stop()
+            self.ws = None
         if self._httpd is not None:
             self._httpd.shutdown()
             self._httpd.server_close()
