@@ -108,7 +108,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
     const uint32_t tmem_base = *tmem_slot;
 
     // tile order: m fastest, so CTAs running concurrently share the same weight column block (L2 reuse)
-    auto tile_coords = [&](int t, int& m_blk, int& n_blk) { m_blk = t % num_m; n_blk = t / num_m; };
+    // Tile order.  Few row tiles: m fastest (concurrent CTAs share one weight block).  Many row tiles (A does not stay in
+    // L2 between passes): grouped rasterisation -- a wave covers GROUP_N column blocks x ~148/GROUP_N row blocks, so every
+    // A tile is reused GROUP_N times and every B tile ~18 times out of L2 instead of A being re-streamed from HBM once
+    // per column block (8192^3: 32 passes over 134 MB).
+    constexpr int GROUP_N = 8;
+    const bool grouped = num_m >= 32 && num_n >= 2 * GROUP_N && !P.fused_bcast;
+    auto tile_coords = [&](int t, int& m_blk, int& n_blk) {
+        if (!grouped) { m_blk = t % num_m; n_blk = t / num_m; return; }
+        const int per_group = GROUP_N * num_m, g = t / per_group, first = g * GROUP_N, in_g = t - g * per_group;
+        const int gsz = min(GROUP_N, num_n - first);
+        n_blk = first + in_g % gsz;
+        m_blk = in_g / gsz;
+    };
 
     if (warp == 0) {
         // ============================ TMA producer ============================

@@ -139,7 +139,14 @@ V6_DEVINL void mbar_wait_u(uint32_t bar, uint32_t parity) {           // bounded
 
 struct Item { int m_blk, n_blk, kb0, kb1, cls; };
 
-template <int MODE>
+// EPI (FPROP / DGRAD epilogue flavour, so that each instantiation carries only the code it runs -- the v2 kernel spent a
+// fifth of its issue slots on instruction fetch and on branches around dead bias / GELU / scatter code):
+//   EPI_PLAIN  bf16 tile -> staging -> TMA store
+//   EPI_STATS  + BatchNorm statistics of the tile (FPROP)
+//   EPI_GEN    bias / activation / add_src / stride-2 scatter
+enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_GEN = 2 };
+
+template <int MODE, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ CUtensorMap tmap_c, const Params P) {
@@ -310,14 +317,93 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         const int quad = warp & 3;                    // TMEM lanes [32*quad, 32*quad+32)
         const int half = (warp - 4) >> 2;             // this warp takes the 32-column chunks with (chunk & 1) == half
         const int et = (warp - 4) * 32 + lane;        // epilogue thread id 0..255: owns column `et` of the statistics
-        const bool stats = MODE == FPROP && P.gamma != nullptr;
+        constexpr bool stats = MODE == FPROP && EPI == EPI_STATS;
         int acc = 0; uint32_t acc_phase = 0;
         float run1[4][2], run2[4][2];                 // running column sums of this warp's (<= 4) chunks: lanes 0..15 own a column pair
 #pragma unroll
         for (int k = 0; k < 4; ++k) run1[k][0] = run1[k][1] = run2[k][0] = run2[k][1] = 0.f;
         int run_first_m = -1;
         uint8_t* stg = smem + STG_OFF + (warp - 4) * STG_WARP_BYTES;
-        int box = 0;                                   // staging boxes alternate so that a TMA store overlaps the next chunk
+        const int nck = P.block_n >> 6;               // 32-column chunks of a tile this warp handles (chunk index 2k + half)
+
+        // fp32 accumulator row (32 columns) -> packed bf16 (EPI_GEN: + bias / residual-gradient add / activation)
+        auto finish = [&](const uint32_t (&v)[32], uint32_t (&packed)[16], int row, int col0) {
+            if (EPI != EPI_GEN) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                return;
+            }
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (P.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (col0 + j < P.N) f[j] += __ldg(P.bias + col0 + j);
+            }
+            if (P.add_src != nullptr && row < P.M && col0 + 32 <= P.N) {
+                const uint4* ap = reinterpret_cast<const uint4*>(P.add_src + (size_t)row * P.N + col0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint4 t = __ldg(ap + j);
+                    const float2 a0 = unpack_bf16x2(t.x), a1 = unpack_bf16x2(t.y), a2 = unpack_bf16x2(t.z), a3 = unpack_bf16x2(t.w);
+                    f[8 * j + 0] += a0.x; f[8 * j + 1] += a0.y; f[8 * j + 2] += a1.x; f[8 * j + 3] += a1.y;
+                    f[8 * j + 4] += a2.x; f[8 * j + 5] += a2.y; f[8 * j + 6] += a3.x; f[8 * j + 7] += a3.y;
+                }
+            }
+            if (P.act == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            } else if (P.act == 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+        };
+        // [32 rows][32 bf16 = 64 B] staging box, SWIZZLE_64B: 16-byte chunk j of row r sits at chunk j ^ ((r >> 1) & 3)
+        auto to_box = [&](uint8_t* sbox, const uint32_t (&packed)[16]) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(sbox + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                    make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        };
+        // column sums of the bf16-rounded box: lanes 0..15 take rows 0..15, lanes 16..31 rows 16..31 of column pair
+        // (lane & 15); the halves meet through one shuffle; added to the running sums of chunk slot k
+        auto box_stats = [&](const uint8_t* sbox, int k) {
+            const int cp = lane & 15, r0 = (lane >> 4) * 16;
+            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int rr = r0 + r;
+                const uint32_t wv = *reinterpret_cast<const uint32_t*>(sbox + rr * 64 + (((cp >> 2) ^ ((rr >> 1) & 3)) << 4) + (cp & 3) * 4);
+                const float x0 = __uint_as_float(wv << 16), x1 = __uint_as_float(wv & 0xffff0000u);
+                a0 += x0; a1 += x1; b0 = fmaf(x0, x0, b0); b1 = fmaf(x1, x1, b1);
+            }
+            a0 += __shfl_xor_sync(0xffffffffu, a0, 16); a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+            b0 += __shfl_xor_sync(0xffffffffu, b0, 16); b1 += __shfl_xor_sync(0xffffffffu, b1, 16);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                if (kk == k) { run1[kk][0] += a0; run1[kk][1] += a1; run2[kk][0] += b0; run2[kk][1] += b1; }
+        };
+        // stride-2 DGRAD: row (n, i, j) of the class grid -> dX pixel (2i + a, 2j + b); 32 channels = 64 B per thread
+        auto scatter = [&](const uint32_t (&packed)[16], int m, int col0, int cls) {
+            if (m >= P.M) return;
+            const int n_img = m / P.PQ, rem = m - n_img * P.PQ;
+            const int oi = 2 * (rem / P.Q), oj = 2 * (rem % P.Q);
+            __nv_bfloat16* base = P.dx + ((size_t)n_img * P.OH * P.OW) * P.N + col0;
+            uint4* dst = reinterpret_cast<uint4*>(base + ((size_t)(oi + P.cls_a[cls]) * P.OW + oj + P.cls_b[cls]) * P.N);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            if (P.zero_fill) {
+#pragma unroll
+                for (int z = 1; z < 4; ++z) {
+                    uint4* zd = reinterpret_cast<uint4*>(base + ((size_t)(oi + (z >> 1)) * P.OW + oj + (z & 1)) * P.N);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) zd[j] = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+        };
+
         for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
             const Item it = decode(item);
             mbar_wait(&tfull_bar[acc], acc_phase);
@@ -342,93 +428,58 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 }
             } else {
                 const int row0 = it.m_blk * BLOCK_M + quad * 32;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int c = (2 * k + half) * 32;                     // column offset of this warp's k-th chunk inside the tile
-                    if (c < P.block_n) {                                   // warp-uniform
-                        uint32_t v[32];
-                        tmem_ld_32x32b_x32(t_row + c, v);
-                        tmem_ld_wait();
-                        const int col0 = it.n_blk * P.block_n + c;
-                        if (row0 < P.M && col0 < P.N) {                    // warp-uniform
-                            uint32_t packed[16];
-                            {
-                                float f[32];
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                                if (P.bias) {
-#pragma unroll
-                                    for (int j = 0; j < 32; ++j) if (col0 + j < P.N) f[j] += __ldg(P.bias + col0 + j);
-                                }
-                                if (P.add_src != nullptr && row0 + lane < P.M && col0 + 32 <= P.N) {
-                                    const uint4* ap = reinterpret_cast<const uint4*>(P.add_src + (size_t)(row0 + lane) * P.N + col0);
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) {
-                                        const uint4 t = __ldg(ap + j);
-                                        const float2 a0 = unpack_bf16x2(t.x), a1 = unpack_bf16x2(t.y), a2 = unpack_bf16x2(t.z), a3 = unpack_bf16x2(t.w);
-                                        f[8 * j + 0] += a0.x; f[8 * j + 1] += a0.y; f[8 * j + 2] += a1.x; f[8 * j + 3] += a1.y;
-                                        f[8 * j + 4] += a2.x; f[8 * j + 5] += a2.y; f[8 * j + 6] += a3.x; f[8 * j + 7] += a3.y;
-                                    }
-                                }
-                                if (P.act == 1) {
-#pragma unroll
-                                    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-                                } else if (P.act == 2) {
-#pragma unroll
-                                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-                                }
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-                            }
-                            if (strided) {
-                                // scatter: row (n, i, j) of the class grid -> dX pixel (2i + a, 2j + b); 32 channels = 64 B per thread
-                                const int m = row0 + lane;
-                                if (m < P.M) {
-                                    const int n_img = m / P.PQ, rem = m - n_img * P.PQ;
-                                    const int oi = 2 * (rem / P.Q), oj = 2 * (rem % P.Q);
-                                    __nv_bfloat16* base = P.dx + ((size_t)n_img * P.OH * P.OW) * P.N + col0;
-                                    uint4* dst = reinterpret_cast<uint4*>(base + ((size_t)(oi + P.cls_a[it.cls]) * P.OW + oj + P.cls_b[it.cls]) * P.N);
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-                                    if (P.zero_fill) {
-#pragma unroll
-                                        for (int z = 1; z < 4; ++z) {
-                                            uint4* zd = reinterpret_cast<uint4*>(base + ((size_t)(oi + (z >> 1)) * P.OW + oj + (z & 1)) * P.N);
-#pragma unroll
-                                            for (int j = 0; j < 4; ++j) zd[j] = make_uint4(0u, 0u, 0u, 0u);
-                                        }
-                                    }
-                                }
-                                continue;
-                            }
-                            uint8_t* sbox = stg + box * STG_BOX_BYTES;
-                            if (lane == 0) tma_store_wait_read_1();           // the store that last used THIS box has read it
+                const int colb = it.n_blk * P.block_n + half * 32;          // first column of this warp's chunk 0
+                const bool rows_ok = row0 < P.M;
+                int k = 0;
+                // two chunks per iteration: both TMEM loads, conversions, box writes and TMA stores in flight together
+#pragma unroll 1
+                for (; k + 1 < nck; k += 2) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld_32x32b_x32(t_row + half * 32 + k * 64, v0);
+                    tmem_ld_32x32b_x32(t_row + half * 32 + k * 64 + 64, v1);
+                    tmem_ld_wait();
+                    const int c0 = colb + k * 64, c1 = c0 + 64;
+                    if (!rows_ok || c0 >= P.N) continue;                     // warp-uniform
+                    const bool second = c1 < P.N;
+                    uint32_t p0[16], p1[16];
+                    finish(v0, p0, row0 + lane, c0);
+                    finish(v1, p1, row0 + lane, c1);
+                    if (EPI == EPI_GEN && strided) {
+                        scatter(p0, row0 + lane, c0, it.cls);
+                        if (second) scatter(p1, row0 + lane, c1, it.cls);
+                        continue;
+                    }
+                    if (lane == 0) tma_store_wait_read();                    // both boxes: the previous pair's stores have read them
+                    __syncwarp();
+                    to_box(stg, p0);
+                    to_box(stg + STG_BOX_BYTES, p1);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmap_c, stg, c0, row0);
+                        if (second) tma_store_2d(&tmap_c, stg + STG_BOX_BYTES, c1, row0);
+                        tma_store_commit();
+                    }
+                    if (stats) { box_stats(stg, k); if (second) box_stats(stg + STG_BOX_BYTES, k + 1); }
+                }
+                if (k < nck) {                                               // odd chunk count (block_n = 64 / 192)
+                    uint32_t v0[32];
+                    tmem_ld_32x32b_x32(t_row + half * 32 + k * 64, v0);
+                    tmem_ld_wait();
+                    const int c0 = colb + k * 64;
+                    if (rows_ok && c0 < P.N) {
+                        uint32_t p0[16];
+                        finish(v0, p0, row0 + lane, c0);
+                        if (EPI == EPI_GEN && strided) {
+                            scatter(p0, row0 + lane, c0, it.cls);
+                        } else {
+                            if (lane == 0) tma_store_wait_read();
                             __syncwarp();
-                            // [32 rows][32 bf16 = 64 B] box, SWIZZLE_64B: 16-byte chunk j of row r sits at chunk j ^ ((r >> 1) & 3)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                *reinterpret_cast<uint4*>(sbox + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
-                                    make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                            to_box(stg, p0);
                             fence_proxy_async_smem();
                             __syncwarp();
-                            if (lane == 0) { tma_store_2d(&tmap_c, sbox, col0, row0); tma_store_commit(); }
-                            if (stats) {
-                                // column sums of the bf16-rounded box: lanes 0..15 take rows 0..15, lanes 16..31 rows 16..31 of
-                                // column pair (lane & 15); the halves meet through one shuffle
-                                const int cp = lane & 15, r0 = (lane >> 4) * 16;
-                                float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-#pragma unroll
-                                for (int r = 0; r < 16; ++r) {
-                                    const int rr = r0 + r;
-                                    const uint32_t wv = *reinterpret_cast<const uint32_t*>(sbox + rr * 64 + (((cp >> 2) ^ ((rr >> 1) & 3)) << 4) + (cp & 3) * 4);
-                                    const float x0 = __uint_as_float(wv << 16), x1 = __uint_as_float(wv & 0xffff0000u);
-                                    a0 += x0; a1 += x1; b0 = fmaf(x0, x0, b0); b1 = fmaf(x1, x1, b1);
-                                }
-                                a0 += __shfl_xor_sync(0xffffffffu, a0, 16); a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
-                                b0 += __shfl_xor_sync(0xffffffffu, b0, 16); b1 += __shfl_xor_sync(0xffffffffu, b1, 16);
-                                run1[k][0] += a0; run1[k][1] += a1; run2[k][0] += b0; run2[k][1] += b1;
-                            }
-                            box ^= 1;
+                            if (lane == 0) { tma_store_2d(&tmap_c, stg, c0, row0); tma_store_commit(); }
+                            if (stats) box_stats(stg, k);
                         }
                     }
                 }
@@ -544,13 +595,25 @@ struct ConvGeom {
     long long pitch_w = 0, pitch_h = 0, pitch_n = 0;      // byte pitches (0 = dense)
 };
 
+typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const igemm::Params);
+
+// one instantiation per (mode, epilogue flavour) that is actually used
+KernelFn pick_kernel(int mode, int epi) {
+    using namespace igemm;
+    if (mode == FPROP) return epi == EPI_STATS ? igemm_kernel<FPROP, EPI_STATS> : epi == EPI_GEN ? igemm_kernel<FPROP, EPI_GEN> : igemm_kernel<FPROP, EPI_PLAIN>;
+    if (mode == DGRAD) return epi == EPI_GEN ? igemm_kernel<DGRAD, EPI_GEN> : igemm_kernel<DGRAD, EPI_PLAIN>;
+    return igemm_kernel<WGRAD, EPI_PLAIN>;
+}
+
 int set_smem_attr() {
     static bool done = false;
     if (!done) {
-        cudaError_t e = cudaFuncSetAttribute(igemm::igemm_kernel<igemm::FPROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, igemm::SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(igemm::igemm_kernel<igemm::DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, igemm::SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(igemm::igemm_kernel<igemm::WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, igemm::SMEM_BYTES);
-        if (e != cudaSuccess) return (int)e;
+        using namespace igemm;
+        const int combos[6][2] = {{FPROP, EPI_PLAIN}, {FPROP, EPI_STATS}, {FPROP, EPI_GEN}, {DGRAD, EPI_PLAIN}, {DGRAD, EPI_GEN}, {WGRAD, EPI_PLAIN}};
+        for (auto& c : combos) {
+            cudaError_t e = cudaFuncSetAttribute(pick_kernel(c[0], c[1]), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+            if (e != cudaSuccess) return (int)e;
+        }
         done = true;
     }
     return 0;
@@ -561,13 +624,25 @@ int im2col_map(void* out, const void* ptr, const ConvGeom& g, int pixels) {
                                     g.stride, g.stride, (uint64_t)g.pitch_w, (uint64_t)g.pitch_h, (uint64_t)g.pitch_n);
 }
 
-int pick_block_n(int M, int N) {
-    const int num_m = (M + 127) / 128;
+// N-tile width from a small cost model (cycles, fitted to profiles/conv_probe_time_r2b.jsonl): a tile's main loop costs
+// num_kb x max(MMA issue time, operand fetch time) and its epilogue (BN / 64) store chains per warp; the two overlap
+// (2 TMEM accumulator stages), tiles run in waves of one per SM.
+int pick_block_n(int M, int N, int num_kb = 8, bool stats = false) {
+    const long long num_m = (M + 127) / 128;
     if (N <= 64) return 64;
-    if (N <= 128) return 128;
-    // keep >= ~1 wave of tiles: prefer the widest tile that still yields >= 120 tiles
-    for (int bn : {256, 128}) if (num_m * ((N + bn - 1) / bn) >= 120) return bn;
-    return 64;
+    int best = 64;
+    double best_t = 1e30;
+    for (int bn : {256, 128, 64}) {
+        if (bn > 64 && N < bn && N % bn != 0 && N <= bn / 2) continue;
+        const long long tiles = num_m * ((N + bn - 1) / bn);
+        const double waves = (double)((tiles + 147) / 148);
+        const double mma = 2.0 * bn, fetch = (16384.0 + bn * 128.0) / 60.0;
+        const double main_loop = num_kb * (mma > fetch ? mma : fetch) + 600.0;
+        const double epi = (bn / 64) * (stats ? 1500.0 : 900.0) * 0.5 + 300.0;      // pairs of chunks per chain
+        const double t = waves * (main_loop > epi ? main_loop : epi);
+        if (t < best_t * 0.97) { best_t = t; best = bn; }
+    }
+    return best;
 }
 
 int launch(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const igemm::Params& P, cudaStream_t s) {
@@ -580,9 +655,10 @@ int launch(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
     const int cap = sms < MAX_SLOTS ? sms : MAX_SLOTS;
     const int grid = items < cap ? items : cap;
-    if (mode == FPROP) igemm_kernel<FPROP><<<grid, kThreads, SMEM_BYTES, s>>>(ta, tb, tc, P);
-    else if (mode == DGRAD) igemm_kernel<DGRAD><<<grid, kThreads, SMEM_BYTES, s>>>(ta, tb, tc, P);
-    else igemm_kernel<WGRAD><<<grid, kThreads, SMEM_BYTES, s>>>(ta, tb, tc, P);
+    int epi = EPI_PLAIN;
+    if (mode == FPROP) epi = P.gamma ? EPI_STATS : ((P.bias || P.act) ? EPI_GEN : EPI_PLAIN);
+    else if (mode == DGRAD) epi = (P.dstride == 2 || P.add_src) ? EPI_GEN : EPI_PLAIN;
+    pick_kernel(mode, epi)<<<grid, kThreads, SMEM_BYTES, s>>>(ta, tb, tc, P);
     V6_CHECK_LAUNCH();
     return 0;
 }
@@ -603,7 +679,7 @@ extern "C" int v6_conv_fprop(const void* x, const void* w, void* y, const float*
     const int M = (int)Mll, K = R * S * Cin;
     const bool plain = R == 1 && S == 1 && stride == 1 && pad == 0 && !force_im2col && !pitch_w;
     Params P = {};
-    P.M = M; P.N = Cout; P.num_kb = K / 64; P.block_n = pick_block_n(M, Cout);
+    P.M = M; P.N = Cout; P.num_kb = K / 64; P.block_n = pick_block_n(M, Cout, K / 64, gamma != nullptr);
     P.a_im2col = plain ? 0 : 1; P.PQ = Pp * Qq; P.Q = Qq; P.stride = stride; P.pad = pad; P.S = S; P.cblocks = Cin / 64; P.taps = R * S;
     P.act = act; P.bias = bias;
     if (gamma) {
@@ -643,7 +719,7 @@ extern "C" int v6_conv_dgrad(const void* dy, const void* w, void* dx, int N, int
         const int Pp = H / 2, Qq = W / 2;
         const long long Mll = (long long)N * Pp * Qq;
         if (Mll >= (1LL << 31)) return (int)cudaErrorInvalidValue;
-        P.M = (int)Mll; P.N = Cin; P.block_n = pick_block_n(P.M, Cin);
+        P.M = (int)Mll; P.N = Cin; P.block_n = pick_block_n(P.M, Cin, 2 * (Cout / 64));
         P.a_im2col = 1; P.PQ = Pp * Qq; P.Q = Qq; P.stride = 1; P.pad = 0; P.S = S; P.cblocks = Cout / 64; P.taps = R * S;
         P.dstride = 2; P.OH = H; P.OW = W; P.dx = (__nv_bfloat16*)dx;
         int nc = 0;
@@ -679,7 +755,7 @@ extern "C" int v6_conv_dgrad(const void* dy, const void* w, void* dx, int N, int
     if (Mll >= (1LL << 31)) return (int)cudaErrorInvalidValue;
     const int M = (int)Mll;
     const bool plain = R == 1 && pad == 0 && !force_im2col;
-    P.M = M; P.N = Cin; P.num_kb = R * S * (Cout / 64); P.block_n = pick_block_n(M, Cin);
+    P.M = M; P.N = Cin; P.num_kb = R * S * (Cout / 64); P.block_n = pick_block_n(M, Cin, R * S * (Cout / 64));
     P.a_im2col = plain ? 0 : 1; P.PQ = H * W; P.Q = W; P.stride = 1; P.pad = R - 1 - pad; P.S = S; P.cblocks = Cout / 64; P.taps = R * S; P.flip = 1;
     P.dstride = 1; P.add_src = (const __nv_bfloat16*)add_src;
     if (plain) { if (v6_make_tmap_2d_bf16(&ta, (uint64_t)dy, M, Cout, (uint64_t)Cout * 2, BLOCK_M, BLOCK_K, 1)) return -2; }

@@ -188,19 +188,10 @@ class FedAvgEngine:
     # ------------------------------------------------------------------ rounds
     @torch.no_grad()
     def initialize_global(self) -> None:
-        """Round 0: the model in rank 0's ``w`` becomes the global model on every node."""
-        weights = [1.0] + [0.0] * (self.world - 1)
-        saved = (self.opt, self.upload_mode, self.upload, getattr(self, "_up_buf", None))
-        self.opt = ServerOptConfig("fedavg", 1.0)
-        self.upload_mode, self.upload = "weights_f32", self.w
-        if self.data_plane == "native":
-            self._up_buf = self._w_buf            # round 0 reads the weights themselves
-        try:
-            self._aggregate(weights, count_step=False, force_p2p=True)
-        finally:
-            self.opt, self.upload_mode, self.upload = saved[:3]
-            if self.data_plane == "native":
-                self._up_buf = saved[3]
+        """Round 0: the model in rank 0's ``w`` becomes the global model on every node (one aggregation in which only
+        rank 0 reports its *weights*, plain FedAvg with server lr 1, P2P path -- selected by the ``round0`` mode flag of
+        :meth:`_aggregate`, the engine's configuration is not touched)."""
+        self._aggregate([1.0] + [0.0] * (self.world - 1), count_step=False, force_p2p=True, round0=True)
         if self.shadow is not None:
             self.shadow.copy_(self.w.to(torch.bfloat16))
 
@@ -258,8 +249,10 @@ class FedAvgEngine:
         return [float(t.item()) for t in out]
 
     def _aggregate(self, weights: List[float] | None, count_step: bool, force_p2p: bool = False, my_weight: float = 0.0,
-                   prescaled: bool = False) -> None:
+                   prescaled: bool = False, round0: bool = False) -> None:
         dynamic = weights is None
+        opt = ServerOptConfig("fedavg", 1.0) if round0 else self.opt
+        upload_mode = "weights_f32" if round0 else self.upload_mode
         if dynamic and self.data_plane != "native":
             weights, dynamic = self._gather_weights(my_weight), False
         if not dynamic:
@@ -270,10 +263,10 @@ class FedAvgEngine:
         if count_step:
             self.server_step += 1
         t = max(self.server_step, 1)
-        bias1 = 1.0 / (1.0 - self.opt.beta1 ** t)
-        bias2 = 1.0 / (1.0 - self.opt.beta2 ** t)
+        bias1 = 1.0 / (1.0 - opt.beta1 ** t)
+        bias2 = 1.0 / (1.0 - opt.beta2 ** t)
         if self.data_plane == "native":
-            mode_idx = UPLOAD_MODES.index(self.upload_mode)
+            mode_idx = UPLOAD_MODES.index(upload_mode)
             is_delta = mode_idx != 0
             # The kernel decides at run time (from the n_i it received) whether the in-switch reduction applies: every
             # rank reports and (contributions pre-scaled by n_i, or all n_i equal -> mean = sum / world); otherwise the
@@ -282,7 +275,8 @@ class FedAvgEngine:
             mc_ok = self.use_multicast and not force_p2p and all_live
             from ..ops import stream_ptr
 
-            up, wb = self._up_buf, self._w_buf
+            wb = self._w_buf
+            up = wb if round0 else self._up_buf           # round 0 reads the weights themselves
             null8 = [0] * 8
             self._C.fedavg_round(
                 up.peer(), wb.peer(), self._shadow_buf.peer() if self._shadow_buf else null8, self._pad_buf.peer(),
@@ -290,23 +284,25 @@ class FedAvgEngine:
                 self._shadow_buf.mc() if (self._shadow_buf and mc_ok) else 0,
                 self.w_global.data_ptr(), self.opt_m.data_ptr(), self.opt_v.data_ptr(), weights if not dynamic else [0.0] * self.world,
                 self.lo, self.hi, self.rank, self.world, self.n_reducers, self.live_mask, self.epoch, is_delta, bool(prescaled),
-                SERVER_OPTS[self.opt.name], self.opt.lr, self.opt.beta1, self.opt.beta2, self.opt.eps, bias1, bias2,
+                SERVER_OPTS[opt.name], opt.lr, opt.beta1, opt.beta2, opt.eps, bias1, bias2,
                 0.0, self.timeout_cycles, self._cta_counter.data_ptr(),
-                1 if self.upload_mode == "delta_bf16" else 0,
+                1 if upload_mode == "delta_bf16" else 0,
                 self.sm_count if (self.is_reducer and self.hi > self.lo) else 1, stream_ptr(),
                 dynamic, float(my_weight), self.reducer_mask)
         else:
             if prescaled:           # the collective arm applies the weights itself
                 weights_eff = [1.0 if w > 0 else 0.0 for w in weights]
-                self._aggregate_collective(weights_eff, total, bias1, bias2)
+                self._aggregate_collective(weights_eff, total, bias1, bias2, opt, upload_mode)
             else:
-                self._aggregate_collective(weights, total, bias1, bias2)
+                self._aggregate_collective(weights, total, bias1, bias2, opt, upload_mode)
 
     # -- baseline / CPU data plane -------------------------------------------------------------
-    def _aggregate_collective(self, weights, total, bias1, bias2) -> None:
+    def _aggregate_collective(self, weights, total, bias1, bias2, opt=None, upload_mode=None) -> None:
         import torch.distributed as dist
 
-        is_delta = self.upload_mode != "weights_f32"
+        opt = opt or self.opt
+        upload_mode = upload_mode or self.upload_mode
+        is_delta = upload_mode != "weights_f32"
         my_w = weights[self.rank]
         if my_w == 0:
             contrib = torch.zeros(self.n, dtype=torch.float32, device=self.device)
@@ -324,7 +320,7 @@ class FedAvgEngine:
             mean = contrib[lo:hi] / total
             wg = self.w_global[lo:hi]
             d = mean if is_delta else mean - wg
-            o = self.opt
+            o = opt
             if o.name == "fedavgm":
                 m = self.opt_m[lo:hi]
                 m.mul_(o.beta1).add_(d)
