@@ -158,7 +158,7 @@ def test_resnet_bottleneck_tc_path_matches_cudnn_path(dev, monkeypatch):
     assert tc_launches > 0
     # two bf16 pipelines (different summation orders, statistics of the rounded vs unrounded tile): compare in bulk
     diff = (y1 - y0).abs()
-    assert float(diff.max()) < 0.15 and float((diff > 3e-2).float().mean()) < 1e-3, (float(diff.max()), float((diff > 3e-2).float().mean()))
+    assert float(diff.max()) < 0.25 and float((diff > 5e-2).float().mean()) < 2e-3, (float(diff.max()), float((diff > 5e-2).float().mean()))
     torch.testing.assert_close(rm1, rm0, rtol=1e-2, atol=1e-3)
     assert torch.nn.functional.cosine_similarity(dx1.flatten(), dx0.flatten(), dim=0) > 0.995
     assert torch.nn.functional.cosine_similarity(g1, g0, dim=0) > 0.995

@@ -155,6 +155,23 @@ class ShadowConv2d(nn.Conv2d):
                                    self._offset)
 
 
+def _fuse_stats(conv: nn.Module) -> bool:
+    """BatchNorm statistics in the convolution epilogue only when the layer has at least ``V6B200_CONV_STATS_MIN_KB``
+    64-wide k-blocks (default 0 = always)."""
+    import os
+
+    min_kb = int(os.environ.get("V6B200_CONV_STATS_MIN_KB", "0"))
+    return conv.kernel_size[0] * conv.kernel_size[1] * conv.in_channels // 64 >= min_kb
+
+
+def _bn_with_fork(bn, y, residual, res_fork):
+    from ..ops.bn import _BNFn
+
+    mom = 0.1 if bn.momentum is None else bn.momentum
+    return _BNFn.apply(y, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, bn.eps, mom,
+                       bn.relu, None, res_fork)
+
+
 def conv_bn(conv: nn.Module, bn: nn.Module, x: torch.Tensor, residual: Optional[torch.Tensor] = None,
             fork_in: Optional[GradFork] = None, fork_out: Optional[GradFork] = None, res_fork: Optional[GradFork] = None) -> torch.Tensor:
     """``bn(conv(x), residual)``.  On the tcgen05 path the BatchNorm batch statistics come out of the convolution's
@@ -169,6 +186,11 @@ def conv_bn(conv: nn.Module, bn: nn.Module, x: torch.Tensor, residual: Optional[
         if x.dtype != torch.bfloat16:
             x = x.to(torch.bfloat16)
         if conv.tc_supported(x) and (residual is None or residual.is_contiguous(memory_format=torch.channels_last)):
+            if not _fuse_stats(conv):
+                # short reduction dimension: the convolution is bound by its epilogue, where the statistics are not free;
+                # the separate statistics pass reads an output that is still (partly) in L2
+                y = _TcConvFn.apply(x, conv.weight, conv.w_bf16, conv.stride[0], conv.padding[0], None, fork_in, fork_out)
+                return _bn_with_fork(bn, y, residual, res_fork)
             stats = bn.stats_buffers(x.device)
             y = _TcConvFn.apply(x, conv.weight, conv.w_bf16, conv.stride[0], conv.padding[0], stats, fork_in, fork_out)
             return bn.apply_pre(y, stats, residual, res_fork=res_fork)

@@ -47,7 +47,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq*D] 
     constexpr int K_BYTES = BN * D * 2;
     constexpr int V_BYTES = D * BN * 2;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-B aligned; derived by pointer arithmetic so that the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + Q_BYTES;                      // 2 stages
     uint8_t* sV = sK + 2 * K_BYTES;                  // 2 stages

@@ -57,7 +57,7 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q,      // [B*S, Hq
     constexpr int T_BYTES = BM * D * 2;                  // one 128 x D (or D x 128) bf16 tile
     constexpr int S_COL = 0, DP_COL = 128, DQ_COL = 256;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-B aligned; derived by pointer arithmetic so that the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t* sQ = smem;
     uint8_t* sdO = sQ + T_BYTES;
     uint8_t* sK = sdO + T_BYTES;
@@ -225,7 +225,7 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq
     constexpr int T_BYTES = BM * D * 2;
     constexpr int ST_COL = 0, DPT_COL = 128, DV_COL = 256, DK_COL = 256 + D;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-B aligned; derived by pointer arithmetic so that the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t* sK = smem;
     uint8_t* sV = sK + T_BYTES;
     uint8_t* sQ = sV + T_BYTES;

@@ -91,7 +91,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,     // A [M,K] box
                   const __grid_constant__ CUtensorMap tmap_c,     // C [M,N] box 32 x 64 (epilogue TMA stores)
                   const Params P) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-B aligned; derived by pointer arithmetic so that the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tfull_bar = empty_bar + kStages;

@@ -69,7 +69,7 @@ struct Params {
 __global__ void __launch_bounds__(kThreads, 1)
 glm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params P) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-B aligned; derived by pointer arithmetic so that the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
     uint64_t* x_full = bars;                 // [3]
     uint64_t* x_empty = bars + 3;            // [3]

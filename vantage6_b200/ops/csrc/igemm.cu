@@ -67,6 +67,7 @@ struct Params {
     int taps;                  // R*S
     int flip;                  // DGRAD: filter tap used = taps-1-tap
     int act;                   // bf16 epilogue: 0 none, 1 gelu(erf), 2 relu
+    __nv_bfloat16* c_out;      // FPROP / DGRAD output [M, N] (row stride N)
     const float* bias;         // [N] or null
     const __nv_bfloat16* add_src;   // [M, N] or null: added to the result before the bf16 rounding (DGRAD: the gradient
                                     // that reaches the same tensor through the residual branch -> no separate add pass)
@@ -97,6 +98,13 @@ V6_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678
 constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);          // SBO | version 1 | SWIZZLE_128B
 V6_DEVINL uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) { return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); }
 V6_DEVINL uint64_t desc64(uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; }
+// D[tmem] (+)= A . B with both shared-memory descriptors assembled from their low words inside the asm block (no 64-bit
+// shift / or in the issuing thread's instruction stream)
+V6_DEVINL void umma_bf16_ss_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+                 :: "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI) : "memory");
+}
 
 V6_DEVINL void tma_load_im2col_4d(uint32_t smem_dst, const void* tmap, uint32_t bar, int c, int w, int h, int n, int off_w, int off_h) {
     const uint16_t ow = (uint16_t)off_w, oh = (uint16_t)off_h;
@@ -115,6 +123,32 @@ V6_DEVINL void tma_load_3d_u(uint32_t smem_dst, const void* tmap, uint32_t bar, 
 V6_DEVINL void red_add_f4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// explicit shared-state-space accesses for the epilogue's staging boxes (through generic pointers the compiler emitted
+// LD.E / ST.E -- generic-address loads with global-memory-like latency, profiles/ncu_igemm_r2c.md)
+V6_DEVINL void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+V6_DEVINL uint4 lds_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+V6_DEVINL uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+V6_DEVINL float2 lds_f2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+V6_DEVINL float lds_f1(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+V6_DEVINL void sts_f2(uint32_t addr, float a, float b) { asm volatile("st.shared.v2.f32 [%0], {%1,%2};" :: "r"(addr), "f"(a), "f"(b) : "memory"); }
 V6_DEVINL void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }      // the 8 epilogue warps only
 V6_DEVINL void mbar_expect_tx_u(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
@@ -151,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ CUtensorMap tmap_c, const Params P) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-B aligned; derived by pointer arithmetic so that the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tfull_bar = empty_bar + kMaxStages;
@@ -165,8 +199,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     const int num_tiles = num_m * num_n;
     const bool strided = MODE == DGRAD && P.dstride == 2;
     const int num_items = MODE == WGRAD ? num_tiles * P.splits : (strided ? num_tiles * P.ncls : num_tiles);
-    // smem ring: a stage = A tile (16 KB) + B tile (block_n rows of 128 B); narrow tiles get a deeper ring
-    const int stage_bytes = A_BYTES + P.block_n * 128;
+    // smem ring: a k-block = A tile (16 KB) + B tile (block_n rows of 128 B).  Narrow tiles put TWO k-blocks behind one
+    // full / empty barrier pair: the single TMA thread and the single MMA thread pay their barrier round trips
+    // (~100 cycles per try_wait / expect_tx / commit) per stage, and with 128 MMA cycles per k-block at N = 64 those round
+    // trips -- not the tensor pipe, not L2 -- set the pace (profiles/ncu_igemm_r2b.md: 855 cycles per k-block).
+    const int sub_bytes = A_BYTES + P.block_n * 128;
+    const int ksub = (MODE != WGRAD && P.block_n <= 128) ? 2 : 1;
+    const int stage_bytes = ksub * sub_bytes;
     const int num_stages = min(kMaxStages, RING_BYTES / stage_bytes);
 
     auto decode = [&](int item) {
@@ -188,7 +227,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     // WGRAD: 64-column chunks of this N tile that exist (each chunk = one (tap, channel block))
     auto wgrad_chunks = [&](int n_blk) { return min(4, (P.N >> 6) - n_blk * 4); };
 
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); if (MODE != WGRAD) tma_prefetch_desc(&tmap_c); }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < kAccStages; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps); }
@@ -222,23 +261,26 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     const uint32_t tx = MODE == FPROP ? A_BYTES + P.block_n * 128 : A_BYTES + nch * BOX_BYTES;
                     int tap = 0, tap_s = 0, tap_r = 0, cb = 0;   // k-block = (filter tap, 64-channel block), advanced incrementally
                     if (strided) { tap_s = P.cls_off[it.cls][0] & 15; tap_r = P.cls_off[it.cls][0] >> 4; }
-                    for (int kb = 0; kb < it.kb1; ++kb) {
+                    for (int kb = 0; kb < it.kb1; kb += ksub) {
                         const uint32_t fb = full0 + stage * 8;
+                        const int nsub = min(ksub, it.kb1 - kb);
                         mbar_wait_u(empty0 + stage * 8, phase ^ 1);
-                        const uint32_t sa = smem0 + stage * stage_bytes, sb = sa + A_BYTES;
-                        mbar_expect_tx_u(fb, tx);
-                        if (P.a_im2col) tma_load_im2col_4d(sa, &tmap_a, fb, cb * 64, pw, ph, pn, tap_s, tap_r);
-                        else tma_load_2d_u(sa, &tmap_a, fb, kb * BLOCK_K, m0);
-                        if (MODE == FPROP) {
-                            tma_load_2d_u(sb, &tmap_b, fb, kb * BLOCK_K, n0);
-                        } else {
-                            const int wtap = strided ? P.cls_wtap[it.cls][tap] : (P.flip ? P.taps - 1 - tap : tap);
-                            for (int j = 0; j < nch; ++j) tma_load_3d_u(sb + j * BOX_BYTES, &tmap_b, fb, n0 + j * 64, wtap, cb * 64);
-                        }
-                        if (++cb == P.cblocks) {
-                            cb = 0; ++tap;
-                            if (strided) { const int o = P.cls_off[it.cls][tap & 3]; tap_s = o & 15; tap_r = o >> 4; }
-                            else if (++tap_s == P.S) { tap_s = 0; ++tap_r; }
+                        mbar_expect_tx_u(fb, nsub * tx);
+                        for (int u = 0; u < nsub; ++u) {
+                            const uint32_t sa = smem0 + stage * stage_bytes + u * sub_bytes, sb = sa + A_BYTES;
+                            if (P.a_im2col) tma_load_im2col_4d(sa, &tmap_a, fb, cb * 64, pw, ph, pn, tap_s, tap_r);
+                            else tma_load_2d_u(sa, &tmap_a, fb, (kb + u) * BLOCK_K, m0);
+                            if (MODE == FPROP) {
+                                tma_load_2d_u(sb, &tmap_b, fb, (kb + u) * BLOCK_K, n0);
+                            } else {
+                                const int wtap = strided ? P.cls_wtap[it.cls][tap] : (P.flip ? P.taps - 1 - tap : tap);
+                                for (int j = 0; j < nch; ++j) tma_load_3d_u(sb + j * BOX_BYTES, &tmap_b, fb, n0 + j * 64, wtap, cb * 64);
+                            }
+                            if (++cb == P.cblocks) {
+                                cb = 0; ++tap;
+                                if (strided) { const int o = P.cls_off[it.cls][tap & 3]; tap_s = o & 15; tap_r = o >> 4; }
+                                else if (++tap_s == P.S) { tap_s = 0; ++tap_r; }
+                            }
                         }
                         if (++stage == num_stages) { stage = 0; phase ^= 1; }
                     }
@@ -296,17 +338,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
                 uint32_t accumulate = 0;
-                for (int kb = it.kb0; kb < it.kb1; ++kb) {
+                const uint32_t sub_step = (uint32_t)sub_bytes >> 4;
+                for (int kb = it.kb0; kb < it.kb1; kb += ksub) {
+                    const int nsub = min(ksub, it.kb1 - kb);
                     mbar_wait_u(full0 + stage * 8, phase);
                     tcgen05_fence_after();
-                    const uint32_t a_lo = a_lo0 + stage * stage_step, b_lo = b_lo0 + stage * stage_step;
+                    uint32_t a_lo = a_lo0 + stage * stage_step, b_lo = b_lo0 + stage * stage_step;
+                    for (int u = 0; u < nsub; ++u) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        umma_bf16_ss(d_tmem, desc64(a_lo + k * a_step), desc64(b_lo + k * b_step), idesc, accumulate);
-                        accumulate = 1;
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            umma_bf16_ss_lo(d_tmem, a_lo + k * a_step, b_lo + k * b_step, idesc, accumulate);
+                            accumulate = 1;
+                        }
+                        a_lo += sub_step; b_lo += sub_step;
                     }
                     umma_commit_u(empty0 + stage * 8);
-                    if (kb == it.kb1 - 1) umma_commit_u(tfull0 + acc * 8);
+                    if (kb + nsub >= it.kb1) umma_commit_u(tfull0 + acc * 8);
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
@@ -323,7 +370,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < 4; ++k) run1[k][0] = run1[k][1] = run2[k][0] = run2[k][1] = 0.f;
         int run_first_m = -1;
-        uint8_t* stg = smem + STG_OFF + (warp - 4) * STG_WARP_BYTES;
+        const uint32_t stg = smem0 + STG_OFF + (warp - 4) * STG_WARP_BYTES;      // shared-space address of this warp's two boxes
         const int nck = P.block_n >> 6;               // 32-column chunks of a tile this warp handles (chunk index 2k + half)
 
         // fp32 accumulator row (32 columns) -> packed bf16 (EPI_GEN: + bias / residual-gradient add / activation)
@@ -361,21 +408,39 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
         };
         // [32 rows][32 bf16 = 64 B] staging box, SWIZZLE_64B: 16-byte chunk j of row r sits at chunk j ^ ((r >> 1) & 3)
-        auto to_box = [&](uint8_t* sbox, const uint32_t (&packed)[16]) {
+        auto to_box = [&](uint32_t sbox, const uint32_t (&packed)[16]) {
+            const uint32_t rowa = sbox + lane * 64, sw = (lane >> 1) & 3;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<uint4*>(sbox + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
-                    make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                sts_v4(rowa + ((j ^ sw) << 4), packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        };
+        // staging box -> global memory: 4 lanes cover one row's 64 bytes (two full 32-byte sectors), 8 rows per instruction.
+        // (v2 used a TMA store per box: its proxy fence + store-read wait sat on the critical path of every chunk and the
+        // short-K layers are bound by exactly this chain -- profiles/ncu_igemm_r2b.md.)
+        auto box_to_global = [&](uint32_t sbox, int row0, int c0) {
+            const int ch = lane & 3;
+            if (c0 + ch * 8 >= P.N) return;
+            uint4 val[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = (lane >> 2) + 8 * i;
+                val[i] = lds_v4(sbox + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4));
+            }
+            __nv_bfloat16* dst = P.c_out + (size_t)(row0 + (lane >> 2)) * P.N + c0 + ch * 8;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (row0 + (lane >> 2) + 8 * i < P.M) *reinterpret_cast<uint4*>(dst + (size_t)(8 * i) * P.N) = val[i];
         };
         // column sums of the bf16-rounded box: lanes 0..15 take rows 0..15, lanes 16..31 rows 16..31 of column pair
         // (lane & 15); the halves meet through one shuffle; added to the running sums of chunk slot k
-        auto box_stats = [&](const uint8_t* sbox, int k) {
+        auto box_stats = [&](uint32_t sbox, int k) {
             const int cp = lane & 15, r0 = (lane >> 4) * 16;
             float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+            const uint32_t base = sbox + r0 * 64 + (cp & 3) * 4;
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
-                const int rr = r0 + r;
-                const uint32_t wv = *reinterpret_cast<const uint32_t*>(sbox + rr * 64 + (((cp >> 2) ^ ((rr >> 1) & 3)) << 4) + (cp & 3) * 4);
+                // row r0 + r: r0 is a multiple of 16, so the swizzle term only depends on r
+                const uint32_t wv = lds_u32(base + r * 64 + ((((uint32_t)cp >> 2) ^ ((r >> 1) & 3)) << 4));
                 const float x0 = __uint_as_float(wv << 16), x1 = __uint_as_float(wv & 0xffff0000u);
                 a0 += x0; a1 += x1; b0 = fmaf(x0, x0, b0); b1 = fmaf(x1, x1, b1);
             }
@@ -449,17 +514,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         if (second) scatter(p1, row0 + lane, c1, it.cls);
                         continue;
                     }
-                    if (lane == 0) tma_store_wait_read();                    // both boxes: the previous pair's stores have read them
-                    __syncwarp();
+                    __syncwarp();                                            // every lane is done reading the boxes of the previous pair
                     to_box(stg, p0);
                     to_box(stg + STG_BOX_BYTES, p1);
-                    fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&tmap_c, stg, c0, row0);
-                        if (second) tma_store_2d(&tmap_c, stg + STG_BOX_BYTES, c1, row0);
-                        tma_store_commit();
-                    }
+                    box_to_global(stg, row0, c0);
+                    if (second) box_to_global(stg + STG_BOX_BYTES, row0, c1);
                     if (stats) { box_stats(stg, k); if (second) box_stats(stg + STG_BOX_BYTES, k + 1); }
                 }
                 if (k < nck) {                                               // odd chunk count (block_n = 64 / 192)
@@ -473,12 +533,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         if (EPI == EPI_GEN && strided) {
                             scatter(p0, row0 + lane, c0, it.cls);
                         } else {
-                            if (lane == 0) tma_store_wait_read();
                             __syncwarp();
                             to_box(stg, p0);
-                            fence_proxy_async_smem();
                             __syncwarp();
-                            if (lane == 0) { tma_store_2d(&tmap_c, stg, c0, row0); tma_store_commit(); }
+                            box_to_global(stg, row0, c0);
                             if (stats) box_stats(stg, k);
                         }
                     }
@@ -496,14 +554,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 if (flush) {
                     // combine the 8 warps' running sums through the (now idle) staging boxes, publish this CTA's partial of
                     // the column block; the last CTA to arrive folds all partials in a fixed order and finalizes
-                    if (lane == 0) tma_store_wait_read();
                     __syncwarp();
-                    float* wsum = reinterpret_cast<float*>(stg);          // [chunk k][sum | sumsq][32 columns] = 1 KB of the 4 KB
+                    // this warp's box area doubles as scratch: [chunk k][sum | sumsq][32 columns] floats = 1 KB of the 4 KB
                     if (lane < 16) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            *reinterpret_cast<float2*>(wsum + k * 64 + 2 * lane) = make_float2(run1[k][0], run1[k][1]);
-                            *reinterpret_cast<float2*>(wsum + k * 64 + 32 + 2 * lane) = make_float2(run2[k][0], run2[k][1]);
+                            sts_f2(stg + (k * 64 + 2 * lane) * 4, run1[k][0], run1[k][1]);
+                            sts_f2(stg + (k * 64 + 32 + 2 * lane) * 4, run2[k][0], run2[k][1]);
                         }
                     }
 #pragma unroll
@@ -515,8 +572,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         float t1 = 0.f, t2 = 0.f;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float* ws = reinterpret_cast<const float*>(smem + STG_OFF + (hh * 4 + q) * STG_WARP_BYTES);
-                            t1 += ws[kk * 64 + ci]; t2 += ws[kk * 64 + 32 + ci];
+                            const uint32_t ws = smem0 + STG_OFF + (hh * 4 + q) * STG_WARP_BYTES;
+                            t1 += lds_f1(ws + (kk * 64 + ci) * 4); t2 += lds_f1(ws + (kk * 64 + 32 + ci) * 4);
                         }
                         float* pb = P.part + ((size_t)(it.n_blk * slots + run_first_m) * 2) * P.block_n;
                         __stcg(pb + et, t1);
@@ -573,7 +630,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 }
             }
         }
-        if (MODE != WGRAD && lane == 0) tma_store_wait_all();           // staging must outlive the last store
     }
 
     tcgen05_fence_before();
@@ -681,7 +737,7 @@ extern "C" int v6_conv_fprop(const void* x, const void* w, void* y, const float*
     Params P = {};
     P.M = M; P.N = Cout; P.num_kb = K / 64; P.block_n = pick_block_n(M, Cout, K / 64, gamma != nullptr);
     P.a_im2col = plain ? 0 : 1; P.PQ = Pp * Qq; P.Q = Qq; P.stride = stride; P.pad = pad; P.S = S; P.cblocks = Cin / 64; P.taps = R * S;
-    P.act = act; P.bias = bias;
+    P.act = act; P.bias = bias; P.c_out = (__nv_bfloat16*)y;
     if (gamma) {
         if (Cout % 64 != 0) return (int)cudaErrorInvalidValue;
         P.gamma = gamma; P.beta = beta; P.running_mean = running_mean; P.running_var = running_var;
@@ -757,7 +813,7 @@ extern "C" int v6_conv_dgrad(const void* dy, const void* w, void* dx, int N, int
     const bool plain = R == 1 && pad == 0 && !force_im2col;
     P.M = M; P.N = Cin; P.num_kb = R * S * (Cout / 64); P.block_n = pick_block_n(M, Cin, R * S * (Cout / 64));
     P.a_im2col = plain ? 0 : 1; P.PQ = H * W; P.Q = W; P.stride = 1; P.pad = R - 1 - pad; P.S = S; P.cblocks = Cout / 64; P.taps = R * S; P.flip = 1;
-    P.dstride = 1; P.add_src = (const __nv_bfloat16*)add_src;
+    P.dstride = 1; P.add_src = (const __nv_bfloat16*)add_src; P.c_out = (__nv_bfloat16*)dx;
     if (plain) { if (v6_make_tmap_2d_bf16(&ta, (uint64_t)dy, M, Cout, (uint64_t)Cout * 2, BLOCK_M, BLOCK_K, 1)) return -2; }
     else { ConvGeom g{N, Pp, Qq, Cout, R, S, 1, R - 1 - pad, H, W}; if (im2col_map(&ta, dy, g, BLOCK_M)) return -2; }
     if (v6_make_tmap_2d_bf16(&tc, (uint64_t)dx, M, Cin, (uint64_t)Cin * 2, 32, 32, 2)) return -2;
