@@ -62,8 +62,9 @@ def run_group(group: str, do_time: bool):
 
     def emit(**kw):
         kw["group"] = group
-        print(json.dumps(kw), flush=True)
         out.append(kw)
+        if group != "resnet50":
+            print(json.dumps(kw), flush=True)
 
     def fprop_case(n, cin, cout, h, w, r, stride, pad, force=False, stats=False, seed=0):
         x = _mk(n, cin, h, w, seed)
@@ -239,7 +240,33 @@ def run_group(group: str, do_time: bool):
         dgrad_case(1, 768, 3072, 1, 4096, 1, 0)
         wgrad_case(1, 768, 3072, 1, 4096, 1, 1, 0)
         fprop_case(1, 2048, 1000, 1, 64, 1, 1, 0)       # ResNet fc: N not a multiple of 64
+    elif group == "resnet50":
+        # every convolution of ResNet-50 (batch 64, 224x224; stem separately) with its multiplicity: the per-step accounting
+        # that scripts/conv_layer_table.py turns into "sum of our kernels vs sum of cuDNN's" (profiles/)
+        for (cin, cout, hw, r, stride, mult) in R50_LAYERS:
+            pad = 1 if r == 3 else 0
+            n0 = len(out)
+            fprop_case(64, cin, cout, hw, hw, r, stride, pad)
+            fprop_case(64, cin, cout, hw, hw, r, stride, pad, stats=True)
+            if C.dgrad_supported(cin, cout, r, r, stride, pad, hw, hw):
+                dgrad_case(64, cin, cout, hw, hw, r, pad, stride=stride)
+            wgrad_case(64, cin, cout, hw, hw, r, stride, pad)
+            for rec in out[n0:]:
+                rec["mult"] = mult
+        stem_case(64, 224)
+    if group == "resnet50":
+        for kw in out:
+            print(json.dumps(kw), flush=True)
     return out
+
+
+# (Cin, Cout, input H=W, filter, stride, how many times per forward pass)
+R50_LAYERS = [
+    (64, 64, 56, 1, 1, 1), (64, 64, 56, 3, 1, 3), (64, 256, 56, 1, 1, 4), (256, 64, 56, 1, 1, 2),
+    (256, 128, 56, 1, 1, 1), (128, 128, 56, 3, 2, 1), (128, 512, 28, 1, 1, 4), (256, 512, 56, 1, 2, 1), (512, 128, 28, 1, 1, 3), (128, 128, 28, 3, 1, 3),
+    (512, 256, 28, 1, 1, 1), (256, 256, 28, 3, 2, 1), (256, 1024, 14, 1, 1, 6), (512, 1024, 28, 1, 2, 1), (1024, 256, 14, 1, 1, 5), (256, 256, 14, 3, 1, 5),
+    (1024, 512, 14, 1, 1, 1), (512, 512, 14, 3, 2, 1), (512, 2048, 7, 1, 1, 3), (1024, 2048, 14, 1, 2, 1), (2048, 512, 7, 1, 1, 2), (512, 512, 7, 3, 1, 2),
+]
 
 
 def main():
@@ -257,7 +284,7 @@ def main():
         t0 = time.time()
         cmd = [sys.executable, __file__, "--child", g] + (["--time"] if a.time else [])
         try:
-            pr = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=240)
+            pr = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900 if g == "resnet50" else 240)
             rc, so, se = pr.returncode, pr.stdout, pr.stderr
         except subprocess.TimeoutExpired as e:
             rc, so, se = -9, (e.stdout or b"").decode() if isinstance(e.stdout, bytes) else (e.stdout or ""), "timeout"

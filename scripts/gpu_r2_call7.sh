@@ -14,3 +14,5 @@ timeout 300 python bench.py --model bert_base --steps 6 --warmup 3 --baselines '
 V6B200_LINEAR_BWD=cublas timeout 300 python bench.py --model bert_base --steps 6 --warmup 3 --baselines '' --no-e2e 2>/dev/null | cut -c1-330
 echo "== [6] kernel bench gemm"; timeout 300 python scripts/kernel_bench.py --only gemm 2>&1 | grep "^{" | cut -c1-330
 echo "== [7] ncu igemm"; timeout 400 ncu --set full --clock-control none --import-source on -k regex:igemm_kernel -c 8 -f -o gpurun_out/igemm_prof_r2e python scripts/conv_probe.py --child profile > gpurun_out/igemm_prof_r2e.log 2>&1; echo "rc=$?"
+echo "== [8] ResNet-50 layer table"; timeout 900 python scripts/conv_probe.py --time --groups resnet50 --out gpurun_out/conv_probe_r50_r2e.jsonl 2>&1 | grep -E "^# |crashed" | cut -c1-300; python scripts/conv_layer_table.py gpurun_out/conv_probe_r50_r2e.jsonl > gpurun_out/conv_layers_r50_r2e.md 2>&1; tail -8 gpurun_out/conv_layers_r50_r2e.md
+echo "== [9] attention bench (roles flipped)"; timeout 300 python scripts/kernel_bench.py --only attn,glm 2>&1 | grep "^{" | cut -c1-400

@@ -17,8 +17,24 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 KEY = re.compile(r"UTC\w*MMA\w*|LDTM|STTM|UTMALDG|UTMASTG|UBLKCP|UTCBAR|UTCATOMSWS|LDGMC|MULTIMEM|SYNCS|HMMA|REDG|ATOMG|LDG|STG|MEMBAR|CCTL|ERRBAR")
-FULL = ("gemm_bf16_kernel", "gemm2_bf16_kernel", "fedavg_round_kernel", "small_allreduce_kernel", "flash_fwd_kernel", "flash_fwd2_kernel",
+FULL = ("igemm_kernel", "gemm_bf16_kernel", "gemm2_bf16_kernel", "fedavg_round_kernel", "small_allreduce_kernel", "flash_fwd_kernel", "flash_fwd2_kernel",
         "flash_bwd_dq_kernel", "flash_bwd_dkv_kernel", "bn_stats_kernel", "bias_act_bwd_kernel", "glm_tc_kernel")
+
+
+def _short_name(dem: str) -> str:
+    """`void ns::kernel<(int)1, (int)2>(args...)` -> `ns::kernel<1, 2>` (template arguments kept, parameter list dropped)."""
+    d = dem[5:] if dem.startswith("void ") else dem
+    depth, out = 0, []
+    for ch in d:
+        if ch == "<":
+            depth += 1
+        elif ch == ">":
+            depth -= 1
+        elif ch == "(" and depth == 0:
+            break
+        out.append(ch)
+    name = "".join(out).strip()
+    return re.sub(r"\((int|bool|unsigned int)\)", "", name)
 
 
 def main():
@@ -32,8 +48,8 @@ def main():
     for f in funcs:
         name = f.split("\n", 1)[0].strip()
         dem = subprocess.run(["cu++filt", name], capture_output=True, text=True).stdout.strip() or name
-        short = dem.split("(")[0] if "<" not in dem.split("(")[0] else re.sub(r"\((CUtensorMap|FedAvgParams|SmallParams|OptimParams|const|__nv|float|int|PeerTable|long|unsigned).*", "", dem)
-        instrs = re.findall(r"/\*[0-9a-f]{4}\*/\s+([^;]+);", f)
+        short = _short_name(dem)
+        instrs = re.findall(r"/\*[0-9a-f]{4,6}\*/\s+([^;]+);", f)
         ops = collections.Counter()
         for ins in instrs:
             op = ins.strip().lstrip("@!P0123456789 ").split()[0] if ins.strip() else ""

@@ -6,12 +6,12 @@
 //   D in {64,128}; GQA (Hq multiple of Hkv); BERT: 12x64 non-causal, Llama: 32/8 x128 causal.
 //
 // One CTA per (128-query tile, head, batch), 256 threads:
-//   warp 0   TMA producer: Q once, then a 2-stage ring of K_j and Vt_j tiles (128 keys each)
-//   warp 1   MMA issuer (one lane):  S_j = Q K_j^T  (SS, 128x128xD)  into TMEM S[j%2]
+//   warp 4   TMA producer: Q once, then a 2-stage ring of K_j and Vt_j tiles (128 keys each)
+//   warp 5   MMA issuer (one lane):  S_j = Q K_j^T  (SS, 128x128xD)  into TMEM S[j%2]
 //                                    O  += P_j V_j  (TS: A = P_j from TMEM, 128xDx128) into TMEM O
 //            S_{j+1} is issued before softmax_j finishes, so the tensor pipe overlaps the softmax.
-//   warp 2   TMEM allocator (512 columns: S0 | S1 | O | P0 | P1)
-//   warps 4-7  softmax: thread == query row (tcgen05.ld 32x32b gives each thread its own row ->
+//   warp 6   TMEM allocator (512 columns: S0 | S1 | O | P0 | P1)
+//   warps 0-3  softmax: thread == query row (tcgen05.ld 32x32b gives each thread its own row ->
 //            row max / row sum need no shuffles); online softmax with LAZY rescaling: the running
 //            max is only raised when the tile max exceeds it by > 8 (log2 units); only then is O
 //            (in TMEM) rescaled, after waiting for the previous PV MMA.  P_j is written as packed
@@ -71,10 +71,10 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq*D] 
     const int n_kv_all = (P.S + BN - 1) / BN;
     const int nkv = CAUSAL ? min(n_kv_all, qt + 1) : n_kv_all;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_vt);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == 5 && lane == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
@@ -84,13 +84,13 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq*D] 
         mbar_init(pv_done, 1);
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+    if (warp == 6) tmem_alloc<kTmemCols>(tmem_slot);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 4) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             mbar_expect_tx(q_full, Q_BYTES);
@@ -112,7 +112,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq*D] 
                     tma_load_2d(sV + st * V_BYTES + kh * (D * 128), &tmap_vt, &v_full[st], j * BN + kh * 64, (b * P.Hkv + hk) * D);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 5) {
         // ================================ MMA issuer ==================================
         constexpr uint32_t idesc_s = make_idesc_bf16(BM, BN);
         constexpr uint32_t idesc_o = make_idesc_bf16(BM, D);
@@ -156,9 +156,9 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq*D] 
             __syncwarp();
             if (j + 2 < nkv) issue_s(j + 2);                 // executes after PV_j in the tensor pipe (in order)
         }
-    } else if (warp >= 4) {
+    } else if (warp < 4) {
         // ================================ softmax / epilogue ==========================
-        const int ew = warp - 4;
+        const int ew = warp;                                  // compute warps are 0-3: the role warps sit in the highest ids (issue priority)
         const int row = m0 + ew * 32 + lane;                 // query position of this thread
         const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
         float m_used = -INFINITY, l = 0.f;
@@ -270,7 +270,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq*D] 
 
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 2) { tcgen05_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
+    if (warp == 6) { tcgen05_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
 }
 
 template <int D>

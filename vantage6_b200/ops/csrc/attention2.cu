@@ -85,10 +85,10 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq*D]
     const int n_kv_all = (P.S + BN - 1) / BN;
     const int nkv = CAUSAL ? min(n_kv_all, qt + 1) : n_kv_all;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_vt);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == 5 && lane == 0) {
         mbar_init(q_full, 1);
         mbar_init(k_full, 1); mbar_init(k_empty, 1);
         mbar_init(v_full, 1); mbar_init(v_empty, 1);
@@ -96,13 +96,13 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq*D]
         mbar_init(pv_done, 1);
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+    if (warp == 6) tmem_alloc<kTmemCols>(tmem_slot);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 4) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             mbar_expect_tx(q_full, Q_BYTES);
@@ -129,7 +129,7 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq*D]
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 5) {
         // ================================ MMA issuer ==================================
         constexpr uint32_t idesc_s = make_idesc_bf16(BM, BN);
         constexpr uint32_t idesc_o = make_idesc_bf16(BM, D) | (VMN ? (1u << 16) : 0u);      // bit 16: B MN-major
@@ -169,9 +169,9 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq*D]
             }
             __syncwarp();
         }
-    } else if (warp >= 4) {
+    } else if (warp < 4) {
         // ================================ softmax / epilogue ==========================
-        const int ew = warp - 4;
+        const int ew = warp;                                  // compute warps are 0-3: the role warps sit in the highest ids (issue priority)
         const int row = m0 + ew * 32 + lane;                 // query position of this thread
         const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
         const uint32_t s_tmem = tmem_base + lane_addr + S_COL;
@@ -281,7 +281,7 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq*D]
 
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 2) { tcgen05_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
+    if (warp == 6) { tcgen05_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
 }
 
 template <int D>

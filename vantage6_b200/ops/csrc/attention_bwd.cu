@@ -81,22 +81,22 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q,      // [B*S, Hq
     const int n_kv_all = (P.S + BN - 1) / BN;
     const int nkv = CAUSAL ? min(n_kv_all, qt + 1) : n_kv_all;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_k);
         tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_kt);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == 5 && lane == 0) {
         mbar_init(qdo_full, 1); mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
         mbar_init(sdp_full, 1); mbar_init(ds_full, 4); mbar_init(dq_done, 1);
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+    if (warp == 6) tmem_alloc<kTmemCols>(tmem_slot);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 4) {
         if (lane == 0) {
             mbar_expect_tx(qdo_full, 2 * T_BYTES);
 #pragma unroll
@@ -117,7 +117,7 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q,      // [B*S, Hq
                     tma_load_2d(sKt + kh * (D * 128), &tmap_kt, kv_full, j * BN + kh * 64, (b * P.Hkv + hk) * D);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 5) {
         constexpr uint32_t idesc_s = make_idesc_bf16(BM, BN);
         constexpr uint32_t idesc_q = make_idesc_bf16(BM, D);
         mbar_wait(qdo_full, 0);
@@ -152,8 +152,8 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q,      // [B*S, Hq
             }
             __syncwarp();
         }
-    } else if (warp >= 4) {
-        const int ew = warp - 4;
+    } else if (warp < 4) {
+        const int ew = warp;                                  // compute warps are 0-3: the role warps sit in the highest ids (issue priority)
         const int row = m0 + ew * 32 + lane;
         const bool row_ok = row < P.S;
         const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
@@ -208,7 +208,7 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q,      // [B*S, Hq
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 2) { tcgen05_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
+    if (warp == 6) { tcgen05_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
 }
 
 // ============================================================================== dK / dV kernel
@@ -252,22 +252,22 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq
     const int n_iter = group * n_i;
     const int k0 = jt * BN;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_k);
         tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_qt); tma_prefetch_desc(&tmap_dot);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == 5 && lane == 0) {
         mbar_init(kv_full, 1); mbar_init(q_full, 1); mbar_init(q_empty, 1);
         mbar_init(st_full, 1); mbar_init(pt_full, 4); mbar_init(acc_done, 1);
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+    if (warp == 6) tmem_alloc<kTmemCols>(tmem_slot);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 4) {
         if (lane == 0) {
             mbar_expect_tx(kv_full, 2 * T_BYTES);
 #pragma unroll
@@ -291,7 +291,7 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 5) {
         constexpr uint32_t idesc_s = make_idesc_bf16(BN, BM);
         constexpr uint32_t idesc_d = make_idesc_bf16(BN, D);
         mbar_wait(kv_full, 0);
@@ -328,8 +328,8 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq
             }
             __syncwarp();
         }
-    } else if (warp >= 4) {
-        const int ew = warp - 4;
+    } else if (warp < 4) {
+        const int ew = warp;                                  // compute warps are 0-3: the role warps sit in the highest ids (issue priority)
         const int tid = ew * 32 + lane;                   // 0..127
         const int key = k0 + tid;
         const bool key_ok = key < P.S;
@@ -401,7 +401,7 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q,     // [B*S, Hq
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 2) { tcgen05_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
+    if (warp == 6) { tcgen05_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
 }
 
 template <int D> constexpr int dq_smem() { return 5 * BM * D * 2 + 1024 + 256; }

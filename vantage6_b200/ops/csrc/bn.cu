@@ -106,41 +106,55 @@ __global__ void __launch_bounds__(THREADS, 4) bn_stats_kernel(const __nv_bfloat1
     }
 }
 
-template <bool RELU, bool RES>
-__global__ void __launch_bounds__(THREADS) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
-                                                           const float* __restrict__ scale, const float* __restrict__ bias,
-                                                           __nv_bfloat16* __restrict__ y, unsigned char* __restrict__ mask,
-                                                           long long R, int C) {
+// Element-wise passes: U rows per thread are requested (raw 16 B vectors, kept packed until used) before the first one
+// is consumed, and the grid is exactly one wave of resident CTAs (apply_grid) -- HBM3e wants >= ~64 KB of loads in flight
+// per SM and a grid-stride loop has no tail.  SMEM_COEF keeps the per-channel coefficients in shared memory instead of
+// 16-24 registers so that 4 CTAs/SM stay resident with U = 4.
+template <bool RELU, bool RES, int U, int MINB, bool SMEM_COEF>
+__global__ void __launch_bounds__(THREADS, MINB) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                                                                 const float* __restrict__ scale, const float* __restrict__ bias,
+                                                                 __nv_bfloat16* __restrict__ y, unsigned char* __restrict__ mask,
+                                                                 long long R, int C) {
+    extern __shared__ float s_coef[];                           // SMEM_COEF: scale[C] | bias[C]
     const int CG = C >> 3, RL = THREADS / CG;
     const int cg = threadIdx.x % CG, rl = threadIdx.x / CG;
     pdl_wait();                                                 // scale / bias come from the stats kernel
     float sc[8], bi[8];
-    loadf8(scale + cg * 8, sc);
-    loadf8(bias + cg * 8, bi);
+    if (SMEM_COEF) {
+        for (int i = threadIdx.x; i < C; i += THREADS) { s_coef[i] = scale[i]; s_coef[C + i] = bias[i]; }
+        __syncthreads();
+    } else {
+        loadf8(scale + cg * 8, sc);
+        loadf8(bias + cg * 8, bi);
+    }
     const long long G = (long long)gridDim.x * RL;
-    for (long long r0 = (long long)blockIdx.x * RL + rl; r0 < R; r0 += 2 * G) {   // 2 rows x (x [+ res]) loads in flight
-        float v[2][8], q[2][8];
+    for (long long r0 = (long long)blockIdx.x * RL + rl; r0 < R; r0 += U * G) {
+        uint4 xr[U], qr[U];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
             const long long r = r0 + u * G;
             if (r < R) {
-                load8(x + r * C + cg * 8, v[u]);
-                if (RES) load8(res + r * C + cg * 8, q[u]);
+                xr[u] = ldg_nc_v4(x + r * C + cg * 8);
+                if (RES) qr[u] = ldg_nc_v4(res + r * C + cg * 8);
             }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
             const long long r = r0 + u * G;
             if (r < R) {
+                float v[8], q[8];
+                unpack8(xr[u], v);
+                if (RES) unpack8(qr[u], q);
+                if (SMEM_COEF) { loadf8(s_coef + cg * 8, sc); loadf8(s_coef + C + cg * 8, bi); }
                 unsigned bits = 0;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    float t = fmaf(v[u][k], sc[k], bi[k]);
-                    if (RES) t += q[u][k];
+                    float t = fmaf(v[k], sc[k], bi[k]);
+                    if (RES) t += q[k];
                     if (RELU) bits |= (t > 0.f ? 1u : 0u) << k;
-                    v[u][k] = RELU ? fmaxf(t, 0.f) : t;
+                    v[k] = RELU ? fmaxf(t, 0.f) : t;
                 }
-                store8(y + r * C + cg * 8, v[u]);
+                store8(y + r * C + cg * 8, v);
                 if (RELU && mask) mask[r * CG + cg] = (unsigned char)bits;      // 1 bit / element for the backward
             }
         }
@@ -165,6 +179,7 @@ V6_DEVINL void acc_bwd(const uint4& graw, const uint4& xraw, unsigned bits, cons
 // reduce + finalize: per channel dgamma, dbeta (optionally accumulated into the flat fp32 grad buffer) and
 // the coefficients of dx = c0 * g + c1 * x + c2 with
 //   c0 = gamma*rstd, c1 = -gamma*rstd^2*mean(g*xhat), c2 = -c0*mean(g) - c1*mean
+constexpr int RED_UNROLL = 4;
 template <bool RELU>
 __global__ void __launch_bounds__(THREADS, 3) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const unsigned char* __restrict__ mask,
                                        const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
@@ -183,18 +198,18 @@ __global__ void __launch_bounds__(THREADS, 3) bn_bwd_reduce_kernel(const __nv_bf
     for (int k = 0; k < 8; ++k) { sg[k] = 0.f; sgx[k] = 0.f; }
     const long long G = (long long)gridDim.x * RL;
     long long r = (long long)blockIdx.x * RL + rl;
-    for (; r + G < R; r += 2 * G) {                                            // 2 rows x 3 tensors in flight
-        uint4 g[2], xv[2];
-        unsigned mb[2] = {0xffu, 0xffu};
+    for (; r + (RED_UNROLL - 1) * G < R; r += RED_UNROLL * G) {                // RED_UNROLL rows x 3 tensors in flight
+        uint4 g[RED_UNROLL], xv[RED_UNROLL];
+        unsigned mb[RED_UNROLL];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < RED_UNROLL; ++u) {
             const long long o = (r + u * G) * C + c0;
             g[u] = ldg_nc_v4(dy + o);
             xv[u] = ldg_nc_v4(x + o);
-            if (RELU) mb[u] = __ldg(mask + (r + u * G) * CGT + cgt);
+            mb[u] = RELU ? (unsigned)__ldg(mask + (r + u * G) * CGT + cgt) : 0xffu;
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) acc_bwd<RELU>(g[u], xv[u], mb[u], mu, rs, sg, sgx);
+        for (int u = 0; u < RED_UNROLL; ++u) acc_bwd<RELU>(g[u], xv[u], mb[u], mu, rs, sg, sgx);
     }
     for (; r < R; r += G) {
         const long long o = r * C + c0;
@@ -218,42 +233,52 @@ __global__ void __launch_bounds__(THREADS, 3) bn_bwd_reduce_kernel(const __nv_bf
     }
 }
 
-template <bool RELU, bool RES>
-__global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const unsigned char* __restrict__ mask,
-                                                               const __nv_bfloat16* __restrict__ x, const float* __restrict__ coef,
-                                                               __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres,
-                                                               long long R, int C) {
+template <bool RELU, bool RES, int U, int MINB, bool SMEM_COEF>
+__global__ void __launch_bounds__(THREADS, MINB) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const unsigned char* __restrict__ mask,
+                                                                     const __nv_bfloat16* __restrict__ x, const float* __restrict__ coef,
+                                                                     __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres,
+                                                                     long long R, int C) {
+    extern __shared__ float s_coef[];                           // SMEM_COEF: c0[C] | c1[C] | c2[C]
     const int CG = C >> 3, RL = THREADS / CG;
     const int cg = threadIdx.x % CG, rl = threadIdx.x / CG;
     pdl_wait();                                                 // coefficients come from the reduce kernel
     float c0[8], c1[8], c2[8];
-    loadf8(coef + cg * 8, c0);
-    loadf8(coef + C + cg * 8, c1);
-    loadf8(coef + 2 * C + cg * 8, c2);
+    if (SMEM_COEF) {
+        for (int i = threadIdx.x; i < 3 * C; i += THREADS) s_coef[i] = coef[i];
+        __syncthreads();
+    } else {
+        loadf8(coef + cg * 8, c0);
+        loadf8(coef + C + cg * 8, c1);
+        loadf8(coef + 2 * C + cg * 8, c2);
+    }
     const long long G = (long long)gridDim.x * RL;
-    for (long long r0 = (long long)blockIdx.x * RL + rl; r0 < R; r0 += 2 * G) {
-        float g[2][8], xv[2][8];
-        unsigned mb[2] = {0xffu, 0xffu};
+    for (long long r0 = (long long)blockIdx.x * RL + rl; r0 < R; r0 += U * G) {
+        uint4 gr[U], xr[U];
+        unsigned mb[U];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
             const long long r = r0 + u * G;
+            mb[u] = 0xffu;
             if (r < R) {
-                load8(dy + r * C + cg * 8, g[u]);
-                load8(x + r * C + cg * 8, xv[u]);
+                gr[u] = ldg_nc_v4(dy + r * C + cg * 8);
+                xr[u] = ldg_nc_v4(x + r * C + cg * 8);
                 if (RELU) mb[u] = __ldg(mask + r * CG + cg);
             }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
             const long long r = r0 + u * G;
             if (r < R) {
-                float o[8];
+                float g[8], xv[8], o[8];
+                unpack8(gr[u], g);
+                unpack8(xr[u], xv);
+                if (SMEM_COEF) { loadf8(s_coef + cg * 8, c0); loadf8(s_coef + C + cg * 8, c1); loadf8(s_coef + 2 * C + cg * 8, c2); }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    if (RELU && !((mb[u] >> k) & 1u)) g[u][k] = 0.f;
-                    o[k] = fmaf(c0[k], g[u][k], fmaf(c1[k], xv[u][k], c2[k]));
+                    if (RELU && !((mb[u] >> k) & 1u)) g[k] = 0.f;
+                    o[k] = fmaf(c0[k], g[k], fmaf(c1[k], xv[k], c2[k]));
                 }
-                if (RES) store8(dres + r * C + cg * 8, g[u]);
+                if (RES) store8(dres + r * C + cg * 8, g);
                 store8(dx + r * C + cg * 8, o);
             }
         }
@@ -264,27 +289,77 @@ static inline bool shape_ok(int C) {
     const int cg = C >> 3;
     return C % 8 == 0 && cg >= 1 && cg <= THREADS && (cg & (cg - 1)) == 0;     // 8, 16, ..., 2048
 }
-// element-wise passes keep no partials: use every resident CTA slot (8 CTAs/SM x 148 SMs)
-static inline int apply_grid(long long R, int C) {
+// element-wise passes keep no partials: exactly one wave of resident CTAs (occupancy queried once per instantiation),
+// fewer when the tensor has fewer row groups than that
+template <typename K>
+static int apply_grid(K kernel, size_t smem, long long R, int C) {
+    int dev = 0, sms = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
     const int RL = THREADS / (C >> 3);
-    long long g = (R + RL - 1) / RL;
-    return (int)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
+    const long long g = (R + RL - 1) / RL, cap = (long long)occ * sms;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-// launch `kernel` as a programmatic dependent of the previous kernel in the stream (V6B200_PDL=0: plain launch)
+// launch `kernel` as a programmatic dependent of the previous kernel in the stream (V6B200_PDL=0 or pdl=false: plain launch)
 template <typename... KArgs, typename... Args>
-static void launch_dependent(void (*kernel)(KArgs...), int grid, cudaStream_t s, Args... args) {
+static void launch_dependent(void (*kernel)(KArgs...), int grid, size_t smem, bool dependent, cudaStream_t s, Args... args) {
     static const bool pdl = [] { const char* e = getenv("V6B200_PDL"); return !(e && e[0] == '0'); }();
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = (pdl && dependent) ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// tuning variant of the element-wise passes (V6B200_BN_CFG; scripts/bn_bench.py sweeps it):
+//   0  U = 4 rows in flight, coefficients in shared memory, 4 CTAs/SM            (default)
+//   1  U = 2, coefficients in registers, 3 CTAs/SM                                (the round-1 shape)
+//   2  U = 4, coefficients in registers, 2 CTAs/SM
+static int bn_cfg() {
+    static const int v = [] { const char* e = getenv("V6B200_BN_CFG"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
+template <bool RELU, bool RES>
+static void launch_apply(bool dependent, cudaStream_t s, const __nv_bfloat16* x, const __nv_bfloat16* res, const float* scale, const float* bias,
+                         __nv_bfloat16* y, unsigned char* mask, long long R, int C) {
+    const int cfg = bn_cfg();
+    if (cfg == 1) {
+        auto k = bn_apply_kernel<RELU, RES, 2, 3, false>;
+        launch_dependent(k, apply_grid(k, 0, R, C), 0, dependent, s, x, res, scale, bias, y, mask, R, C);
+    } else if (cfg == 2) {
+        auto k = bn_apply_kernel<RELU, RES, 4, 2, false>;
+        launch_dependent(k, apply_grid(k, 0, R, C), 0, dependent, s, x, res, scale, bias, y, mask, R, C);
+    } else {
+        auto k = bn_apply_kernel<RELU, RES, 4, 4, true>;
+        const size_t sm = (size_t)2 * C * sizeof(float);
+        launch_dependent(k, apply_grid(k, sm, R, C), sm, dependent, s, x, res, scale, bias, y, mask, R, C);
+    }
+}
+
+template <bool RELU, bool RES>
+static void launch_bwd_apply(cudaStream_t s, const __nv_bfloat16* dy, const unsigned char* mask, const __nv_bfloat16* x, const float* coef,
+                             __nv_bfloat16* dx, __nv_bfloat16* dres, long long R, int C) {
+    const int cfg = bn_cfg();
+    if (cfg == 1) {
+        auto k = bn_bwd_apply_kernel<RELU, RES, 2, 3, false>;
+        launch_dependent(k, apply_grid(k, 0, R, C), 0, true, s, dy, mask, x, coef, dx, dres, R, C);
+    } else if (cfg == 2) {
+        auto k = bn_bwd_apply_kernel<RELU, RES, 4, 2, false>;
+        launch_dependent(k, apply_grid(k, 0, R, C), 0, true, s, dy, mask, x, coef, dx, dres, R, C);
+    } else {
+        auto k = bn_bwd_apply_kernel<RELU, RES, 4, 4, true>;
+        const size_t sm = (size_t)3 * C * sizeof(float);
+        launch_dependent(k, apply_grid(k, sm, R, C), sm, true, s, dy, mask, x, coef, dx, dres, R, C);
+    }
 }
 
 }  // namespace bn
@@ -303,17 +378,16 @@ extern "C" int v6_bn_fwd(const void* x, const void* res, const float* gamma, con
     bn_stats_kernel<<<reduce_grid(R, C, wave_ctas(bn_stats_kernel, wave)), THREADS, 0, s>>>((const __nv_bfloat16*)x, make_red(scratch), gamma, beta,
                                                                   running_mean, running_var, num_batches_tracked, mean, rstd,
                                                                   scale_bias, scale_bias + C, R, C, eps, momentum);
-    const int ag = apply_grid(R, C);
     const __nv_bfloat16* xx = (const __nv_bfloat16*)x;
     const __nv_bfloat16* rr = (const __nv_bfloat16*)res;
     __nv_bfloat16* yy = (__nv_bfloat16*)y;
+    unsigned char* mk = (unsigned char*)relu_mask;
     if (relu) {
-        unsigned char* mk = (unsigned char*)relu_mask;
-        if (res) launch_dependent(bn_apply_kernel<true, true>, ag, s, xx, rr, scale_bias, scale_bias + C, yy, mk, R, C);
-        else launch_dependent(bn_apply_kernel<true, false>, ag, s, xx, rr, scale_bias, scale_bias + C, yy, mk, R, C);
+        if (res) launch_apply<true, true>(true, s, xx, rr, scale_bias, scale_bias + C, yy, mk, R, C);
+        else launch_apply<true, false>(true, s, xx, rr, scale_bias, scale_bias + C, yy, mk, R, C);
     } else {
-        if (res) launch_dependent(bn_apply_kernel<false, true>, ag, s, xx, rr, scale_bias, scale_bias + C, yy, nullptr, R, C);
-        else launch_dependent(bn_apply_kernel<false, false>, ag, s, xx, rr, scale_bias, scale_bias + C, yy, nullptr, R, C);
+        if (res) launch_apply<false, true>(true, s, xx, rr, scale_bias, scale_bias + C, yy, nullptr, R, C);
+        else launch_apply<false, false>(true, s, xx, rr, scale_bias, scale_bias + C, yy, nullptr, R, C);
     }
     V6_CHECK_LAUNCH();
     return 0;
@@ -324,17 +398,17 @@ extern "C" int v6_bn_apply(const void* x, const void* res, const float* scale, c
                            long long R, int C, int relu, cudaStream_t s) {
     using namespace bn;
     if (!shape_ok(C)) return (int)cudaErrorInvalidValue;
-    const int ag = apply_grid(R, C);
     const __nv_bfloat16* xx = (const __nv_bfloat16*)x;
     const __nv_bfloat16* rr = (const __nv_bfloat16*)res;
     __nv_bfloat16* yy = (__nv_bfloat16*)y;
     unsigned char* mk = (unsigned char*)relu_mask;      // training with statistics from the convolution epilogue: 1 bit / element
+    // (the statistics come from a kernel that is not written for programmatic dependent launch: plain stream order)
     if (relu) {
-        if (res) bn_apply_kernel<true, true><<<ag, THREADS, 0, s>>>(xx, rr, scale, bias, yy, mk, R, C);
-        else bn_apply_kernel<true, false><<<ag, THREADS, 0, s>>>(xx, rr, scale, bias, yy, mk, R, C);
+        if (res) launch_apply<true, true>(false, s, xx, rr, scale, bias, yy, mk, R, C);
+        else launch_apply<true, false>(false, s, xx, rr, scale, bias, yy, mk, R, C);
     } else {
-        if (res) bn_apply_kernel<false, true><<<ag, THREADS, 0, s>>>(xx, rr, scale, bias, yy, nullptr, R, C);
-        else bn_apply_kernel<false, false><<<ag, THREADS, 0, s>>>(xx, rr, scale, bias, yy, nullptr, R, C);
+        if (res) launch_apply<false, true>(false, s, xx, rr, scale, bias, yy, nullptr, R, C);
+        else launch_apply<false, false>(false, s, xx, rr, scale, bias, yy, nullptr, R, C);
     }
     V6_CHECK_LAUNCH();
     return 0;
@@ -354,15 +428,14 @@ extern "C" int v6_bn_bwd(const void* dy, const void* relu_mask, const void* x, c
     const dim3 rg = reduce_grid(R, C, relu ? wave_ctas(bn_bwd_reduce_kernel<true>, wave_relu) : wave_ctas(bn_bwd_reduce_kernel<false>, wave_lin));
     if (relu) bn_bwd_reduce_kernel<true><<<rg, THREADS, 0, s>>>(dyy, yy, xx, gamma, mean, rstd, make_red(scratch), dgamma, dbeta, coef, R, C, accumulate);
     else bn_bwd_reduce_kernel<false><<<rg, THREADS, 0, s>>>(dyy, yy, xx, gamma, mean, rstd, make_red(scratch), dgamma, dbeta, coef, R, C, accumulate);
-    const int ag = apply_grid(R, C);
     __nv_bfloat16* dxx = (__nv_bfloat16*)dx;
     __nv_bfloat16* drr = (__nv_bfloat16*)dres;
     if (relu) {
-        if (dres) launch_dependent(bn_bwd_apply_kernel<true, true>, ag, s, dyy, yy, xx, coef, dxx, drr, R, C);
-        else launch_dependent(bn_bwd_apply_kernel<true, false>, ag, s, dyy, yy, xx, coef, dxx, drr, R, C);
+        if (dres) launch_bwd_apply<true, true>(s, dyy, yy, xx, coef, dxx, drr, R, C);
+        else launch_bwd_apply<true, false>(s, dyy, yy, xx, coef, dxx, drr, R, C);
     } else {
-        if (dres) launch_dependent(bn_bwd_apply_kernel<false, true>, ag, s, dyy, yy, xx, coef, dxx, drr, R, C);
-        else launch_dependent(bn_bwd_apply_kernel<false, false>, ag, s, dyy, yy, xx, coef, dxx, drr, R, C);
+        if (dres) launch_bwd_apply<false, true>(s, dyy, yy, xx, coef, dxx, drr, R, C);
+        else launch_bwd_apply<false, false>(s, dyy, yy, xx, coef, dxx, drr, R, C);
     }
     V6_CHECK_LAUNCH();
     return 0;

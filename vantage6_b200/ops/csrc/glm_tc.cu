@@ -97,8 +97,8 @@ glm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params P) {
     }
     fence_proxy_async_smem();
 
-    if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_x);
-    if (warp == 1 && lane == 0) {
+    if (warp == 4 && lane == 0) tma_prefetch_desc(&tmap_x);
+    if (warp == 5 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&z_full[b], 1); mbar_init(&z_empty[b], 4);
@@ -107,13 +107,13 @@ glm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params P) {
         mbar_init(g_done, 1);
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+    if (warp == 6) tmem_alloc<kTmemCols>(tmem_slot);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 4) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             int it = 0;
@@ -126,7 +126,7 @@ glm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params P) {
                     tma_load_2d(smem + st * STAGE_BYTES + kb * BOX_BYTES, &tmap_x, &x_full[st], kb * 64, t * TILE_ROWS);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 5) {
         // ================================ MMA issuer ==================================
         constexpr uint32_t idesc_z = make_idesc_bf16(128, 16);
         constexpr uint32_t idesc_g = make_idesc_bf16_amn(128, 16);
@@ -173,9 +173,9 @@ glm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params P) {
             }
             __syncwarp();
         }
-    } else if (warp >= 4) {
+    } else if (warp < 4) {
         // ================================ sigmoid / epilogue ==========================
-        const int ew = warp - 4;
+        const int ew = warp;                                  // compute warps are 0-3: the role warps sit in the highest ids (issue priority)
         const int trow = ew * 32 + lane;                             // row of the tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
         const float bias = P.w[F];
@@ -236,7 +236,7 @@ glm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params P) {
 
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 2) { tcgen05_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
+    if (warp == 6) { tcgen05_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
 }
 
 }  // namespace glm_tc

@@ -20,13 +20,14 @@
 //   WGRAD : A MN-major (dY[pix][co]: co = M contiguous, pix = K rows),  B MN-major (X[pix][ci])
 // -> no transposed copy of the filter or of the activations exists anywhere.
 //
-// Structure (persistent, warp-specialised, 256 threads, one CTA per SM): warp 0 TMA producer, warp 1 MMA issuer,
-// warp 2 TMEM allocator, warps 4-7 epilogue; 4-stage smem ring (48 KB / stage), 2 TMEM accumulator stages.
-// FPROP epilogue = bf16 tile through a swizzled staging box + TMA store, and (optionally) the BatchNorm batch
-// statistics of the layer: per-column sum / sum-of-squares of the bf16-rounded outputs, accumulated per CTA over its
-// run of row-tiles, folded in a fixed order by the last CTA to finish a column block, which also does the per-channel
-// finalize (mean, rstd, scale/bias, running statistics).  The separate statistics pass over Y (bn.cu::bn_stats_kernel,
-// 9 % of a ResNet-50 round) disappears; the result is deterministic.
+// Structure (persistent, warp-specialised, 384 threads, one CTA per SM): warps 0-7 epilogue, warps 8 / 11 TMA producers
+// (A / B operand), warp 9 MMA issuer, warp 10 TMEM allocator -- the single-thread pacing roles sit in the highest warp
+// ids because the warp scheduler favours them there; smem ring of 192 KB, 2 TMEM accumulator stages.
+// FPROP epilogue = bf16 tile through swizzled staging boxes + coalesced stores, and (optionally) the BatchNorm batch
+// statistics of the layer: per-column sum / sum-of-squares of the bf16-rounded outputs, accumulated in registers over
+// ALL row tiles of the CTA (a CTA keeps one column block), published once with fp64 reductions into L2; the last CTA
+// of a column block to arrive does the per-channel finalize (mean, rstd, scale/bias, running statistics) from the
+// totals.  The separate statistics pass over Y (bn.cu::bn_stats_kernel) disappears.
 // WGRAD epilogue = red.global.add.v4.f32 of the fp32 accumulators into dW (split-K partial sums meet in L2).
 #include <cuda.h>
 #include <stdlib.h>
@@ -93,6 +94,7 @@ struct Params {
     const float* gamma; const float* beta; float* running_mean; float* running_var; long long* num_batches_tracked;
     float* mean_out; float* rstd_out; float* scale_out; float* bias_out;
     float* part; int* counters; float eps, momentum;
+    int stat_arrivals;       // CTAs that publish sums for one column block
 };
 
 V6_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
@@ -219,8 +221,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         Item it;
         it.cls = 0;
         const int tile = (MODE == WGRAD || strided) ? item % num_tiles : item;
-        it.m_blk = tile % num_m;                                  // m fastest: concurrent CTAs share the filter block
-        it.n_blk = tile / num_m;
+        if (EPI == EPI_STATS) {
+            // n fastest and gridDim.x a multiple of num_n (host): a CTA stays on ONE column block for all of its row tiles, so
+            // its per-channel running sums leave the registers once, at the end
+            it.n_blk = tile % num_n;
+            it.m_blk = tile / num_n;
+        } else {
+            it.m_blk = tile % num_m;                              // m fastest: concurrent CTAs share the filter block
+            it.n_blk = tile / num_m;
+        }
         if (MODE == WGRAD) {
             const int split = item / num_tiles;
             it.kb0 = split * P.kb_per_split;
@@ -387,7 +396,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         float run1[4][2], run2[4][2];                 // running column sums of this warp's (<= 4) chunks: lanes 0..15 own a column pair
 #pragma unroll
         for (int k = 0; k < 4; ++k) run1[k][0] = run1[k][1] = run2[k][0] = run2[k][1] = 0.f;
-        int run_first_m = -1;
         const uint32_t stg = smem0 + STG_OFF + warp * STG_WARP_BYTES;      // shared-space address of this warp's two boxes
         const int nck = P.block_n >> 6;               // 32-column chunks of a tile this warp handles (chunk index 2k + half)
 
@@ -576,12 +584,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
 
             if (stats) {
-                if (run_first_m < 0) run_first_m = it.m_blk;
                 const int nxt = item + gridDim.x;
                 const bool flush = nxt >= num_items || decode(nxt).n_blk != it.n_blk;
                 if (flush) {
-                    // combine the 8 warps' running sums through the (now idle) staging boxes, publish this CTA's partial of
-                    // the column block; the last CTA to arrive folds all partials in a fixed order and finalizes
+                    // combine the 8 warps' running sums through the (now idle) staging boxes and add this CTA's totals to the
+                    // column block's; the last CTA to arrive finalizes
                     __syncwarp();
                     // this warp's box area doubles as scratch: [chunk k][sum | sumsq][32 columns] floats = 1 KB of the 4 KB
                     if (lane < 16) {
@@ -594,7 +601,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < 4; ++k) run1[k][0] = run1[k][1] = run2[k][0] = run2[k][1] = 0.f;
                     epi_bar_sync();
-                    const int slots = min(num_m, (int)gridDim.x);
+                    double* sums = reinterpret_cast<double*>(P.part) + (size_t)it.n_blk * P.block_n * 2;
                     if (et < P.block_n) {
                         const int ch = et >> 5, hh = ch & 1, kk = ch >> 1, ci = et & 31;
                         float t1 = 0.f, t2 = 0.f;
@@ -603,17 +610,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                             const uint32_t ws = smem0 + STG_OFF + (hh * 4 + q) * STG_WARP_BYTES;
                             t1 += lds_f1(ws + (kk * 64 + ci) * 4); t2 += lds_f1(ws + (kk * 64 + 32 + ci) * 4);
                         }
-                        float* pb = P.part + ((size_t)(it.n_blk * slots + run_first_m) * 2) * P.block_n;
-                        __stcg(pb + et, t1);
-                        __stcg(pb + P.block_n + et, t2);
+                        // this CTA's sums of its whole run of row tiles meet the other CTAs' in L2 (fp64 reductions: the
+                        // arrival order only moves the 16th digit); nothing is folded serially by anybody
+                        asm volatile("red.global.add.f64 [%0], %1;" :: "l"(sums + et), "d"((double)t1) : "memory");
+                        asm volatile("red.global.add.f64 [%0], %1;" :: "l"(sums + P.block_n + et), "d"((double)t2) : "memory");
                     }
-                    run_first_m = -1;
                     __threadfence();
-                    epi_bar_sync();                                       // partial written; staging boxes free again
+                    epi_bar_sync();                                       // sums published; staging boxes free again
                     if (et == 0) {
                         int old;
                         asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(P.counters + it.n_blk) : "memory");
-                        const int last = old == slots - 1;
+                        const int last = old == P.stat_arrivals - 1;
                         if (last) P.counters[it.n_blk] = 0;              // every expected arrival has happened
                         *s_flag = last;
                     }
@@ -621,19 +628,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     const bool last = *s_flag != 0;
                     epi_bar_sync();                                      // s_flag may be rewritten by the next flush
                     if (last && et < P.block_n) {
-                        const float* fb = P.part + ((size_t)it.n_blk * slots * 2) * P.block_n;
-                        double t1 = 0.0, t2 = 0.0;
-                        for (int s0 = 0; s0 < slots; s0 += 8) {
-                            float u1[8], u2[8];
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                const int s = s0 + u;
-                                u1[u] = s < slots ? __ldcg(fb + (size_t)s * 2 * P.block_n + et) : 0.f;
-                                u2[u] = s < slots ? __ldcg(fb + (size_t)s * 2 * P.block_n + P.block_n + et) : 0.f;
-                            }
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) { t1 += u1[u]; t2 += u2[u]; }
-                        }
+                        const double t1 = __ldcg(sums + et), t2 = __ldcg(sums + P.block_n + et);
+                        __stcg(sums + et, 0.0);                          // self-resetting, like the counters
+                        __stcg(sums + P.block_n + et, 0.0);
                         const int c = it.n_blk * P.block_n + et;
                         if (c < P.N) {
                             const double invR = 1.0 / (double)P.M;
@@ -668,7 +665,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 }  // namespace igemm
 
 // ------------------------------------------------------------------------------------------------- host side
-extern "C" long long v6_igemm_scratch_floats() { return 64 + (long long)2048 * 2 * igemm::MAX_SLOTS; }   // counters | partials
+extern "C" long long v6_igemm_scratch_floats() { return 64 + (long long)2048 * 2 * 2; }   // counters | fp64 [sum | sumsq] per channel
 
 namespace {
 
@@ -738,9 +735,14 @@ int launch(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
     const int cap = sms < MAX_SLOTS ? sms : MAX_SLOTS;
-    const int grid = items < cap ? items : cap;
+    int grid = items < cap ? items : cap;
     int epi = EPI_PLAIN;
     if (mode == FPROP) epi = P.gamma ? EPI_STATS : ((P.bias || P.act) ? EPI_GEN : EPI_PLAIN);
+    igemm::Params Pl = P;
+    if (epi == EPI_STATS) {              // every CTA keeps one column block (see decode): grid = whole groups of num_n CTAs
+        grid = items < cap ? items : (cap / num_n) * num_n;
+        Pl.stat_arrivals = grid / num_n;
+    }
     else if (mode == DGRAD) epi = (P.dstride == 2 || P.add_src) ? EPI_GEN : EPI_PLAIN;
     static const bool pdl = [] { const char* e = getenv("V6B200_PDL"); return !(e && e[0] == '0'); }();
     cudaLaunchConfig_t cfg = {};
@@ -753,7 +755,7 @@ int launch(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, pick_kernel(mode, epi), ta, tb, tc, P);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, pick_kernel(mode, epi), ta, tb, tc, Pl);
     if (le != cudaSuccess) return (int)le;
     V6_CHECK_LAUNCH();
     return 0;

@@ -25,14 +25,15 @@ V6_DEVINL uint4 pack8(const float (&v)[8]) {
 }
 
 // one thread = 8 channels of one output pixel
+template <typename IdxT>       // int when the tensor has < 2^31 elements (32-bit div / mod instead of the 64-bit call sequence)
 __global__ void __launch_bounds__(THREADS) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                               unsigned char* __restrict__ idx, int N, int H, int W, int C, int Ho,
                                                               int Wo) {
     const int CG = C >> 3;
-    const long long total = (long long)N * Ho * Wo * CG;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const IdxT total = (IdxT)N * Ho * Wo * CG;
+    for (IdxT t = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (IdxT)gridDim.x * blockDim.x) {
         const int cg = (int)(t % CG);
-        long long p = t / CG;
+        IdxT p = t / CG;
         const int wo = (int)(p % Wo); p /= Wo;
         const int ho = (int)(p % Ho);
         const int n = (int)(p / Ho);
@@ -102,6 +103,60 @@ __global__ void __launch_bounds__(THREADS) maxpool_bwd_kernel(const __nv_bfloat1
             }
         }
         *reinterpret_cast<uint4*>(dx + (((long long)n * H + h) * W + w) * C + cg * 8) = pack8(acc);
+    }
+}
+
+// even H, W (the ResNet stem: 112 x 112): one thread = 8 channels of a 2x2 block of input pixels.  The block (2i..2i+1,
+// 2j..2j+1) is covered by exactly the 4 windows (i..i+1, j..j+1), so 4 (dy, arg-max) loads -- all issued before the
+// first use -- produce 4 outputs (the gather-per-pixel form above needs 2.25 loads per output), with 32-bit indexing.
+__global__ void __launch_bounds__(THREADS) maxpool_bwd2x2_kernel(const __nv_bfloat16* __restrict__ dy, const unsigned char* __restrict__ idx,
+                                                                 __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo) {
+    const int CG = C >> 3, H2 = H >> 1, W2 = W >> 1;
+    const int total = N * H2 * W2 * CG;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int cg = t % CG;
+        int p = t / CG;
+        const int j = p % W2; p /= W2;
+        const int i = p % H2;
+        const int n = p / H2;
+        uint4 g[4];
+        uint2 a[4];
+#pragma unroll
+        for (int wnd = 0; wnd < 4; ++wnd) {
+            const int ho = i + (wnd >> 1), wo = j + (wnd & 1);
+            g[wnd] = make_uint4(0, 0, 0, 0);
+            a[wnd] = make_uint2(0xffffffffu, 0xffffffffu);                   // arg 255: matches no position
+            if (ho < Ho && wo < Wo) {
+                const size_t o = ((size_t)(n * Ho + ho) * Wo + wo) * C + cg * 8;
+                a[wnd] = __ldg(reinterpret_cast<const uint2*>(idx + o));
+                g[wnd] = __ldg(reinterpret_cast<const uint4*>(dy + o));
+            }
+        }
+        float acc[4][8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[q][k] = 0.f;
+#pragma unroll
+        for (int wnd = 0; wnd < 4; ++wnd) {
+            float gv[8];
+            unpack8(g[wnd], gv);
+            const int dho = wnd >> 1, dwo = wnd & 1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {                                     // pixel (2i + qa, 2j + qb)
+                const int qa = q >> 1, qb = q & 1;
+                if ((dho && !qa) || (dwo && !qb)) continue;                   // the next window only reaches the odd row / column
+                const unsigned me = (unsigned)((dho ? 0 : 1 + qa) * 3 + (dwo ? 0 : 1 + qb));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const unsigned ak = ((k < 4 ? a[wnd].x : a[wnd].y) >> (8 * (k & 3))) & 0xffu;
+                    if (ak == me) acc[q][k] += gv[k];
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(dx + ((size_t)(n * H + 2 * i + (q >> 1)) * W + 2 * j + (q & 1)) * C + cg * 8) = pack8(acc[q]);
     }
 }
 
@@ -208,8 +263,12 @@ extern "C" int v6_maxpool3x3s2_fwd(const void* x, void* y, void* idx, int N, int
     using namespace pool;
     if (C % 8 != 0 || N < 1 || H < 1 || W < 1) return (int)cudaErrorInvalidValue;
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;           // floor((H + 2 - 3) / 2) + 1
-    maxpool_fwd_kernel<<<grid_for((long long)N * Ho * Wo * (C >> 3)), THREADS, 0, s>>>(
-        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (unsigned char*)idx, N, H, W, C, Ho, Wo);
+    if ((long long)N * H * W * C < (1LL << 31))
+        maxpool_fwd_kernel<int><<<grid_for((long long)N * Ho * Wo * (C >> 3)), THREADS, 0, s>>>(
+            (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (unsigned char*)idx, N, H, W, C, Ho, Wo);
+    else
+        maxpool_fwd_kernel<long long><<<grid_for((long long)N * Ho * Wo * (C >> 3)), THREADS, 0, s>>>(
+            (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (unsigned char*)idx, N, H, W, C, Ho, Wo);
     V6_CHECK_LAUNCH();
     return 0;
 }
@@ -218,8 +277,12 @@ extern "C" int v6_maxpool3x3s2_bwd(const void* dy, const void* idx, void* dx, in
     using namespace pool;
     if (C % 8 != 0 || N < 1 || H < 1 || W < 1) return (int)cudaErrorInvalidValue;
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-    maxpool_bwd_kernel<<<grid_for((long long)N * H * W * (C >> 3)), THREADS, 0, s>>>(
-        (const __nv_bfloat16*)dy, (const unsigned char*)idx, (__nv_bfloat16*)dx, N, H, W, C, Ho, Wo);
+    if (H % 2 == 0 && W % 2 == 0 && (long long)N * H * W * C < (1LL << 31))
+        maxpool_bwd2x2_kernel<<<grid_for((long long)N * (H / 2) * (W / 2) * (C >> 3)), THREADS, 0, s>>>(
+            (const __nv_bfloat16*)dy, (const unsigned char*)idx, (__nv_bfloat16*)dx, N, H, W, C, Ho, Wo);
+    else
+        maxpool_bwd_kernel<<<grid_for((long long)N * H * W * (C >> 3)), THREADS, 0, s>>>(
+            (const __nv_bfloat16*)dy, (const unsigned char*)idx, (__nv_bfloat16*)dx, N, H, W, C, Ho, Wo);
     V6_CHECK_LAUNCH();
     return 0;
 }
