@@ -163,3 +163,53 @@ def test_resnet_bottleneck_tc_path_matches_cudnn_path(dev, monkeypatch):
     assert torch.nn.functional.cosine_similarity(dx1.flatten(), dx0.flatten(), dim=0) > 0.995
     assert torch.nn.functional.cosine_similarity(g1, g0, dim=0) > 0.995
     torch.testing.assert_close(g1.norm(), g0.norm(), rtol=3e-2, atol=1e-4)
+
+
+def test_side_stream_filter_gradients_match_inline(dev, monkeypatch):
+    """Filter gradients issued on the second stream (models/conv.py::_SideWgrad, what the trainer switches on) give the
+    gradients of the in-line order; also under CUDA-graph capture, where the fork / join become graph edges."""
+    from vantage6_b200.models import conv as CV
+    from vantage6_b200.models.flat import FlatModel
+    from vantage6_b200.models.resnet import Bottleneck
+    from vantage6_b200.models.transformer import attach_shadow
+
+    monkeypatch.setenv("V6B200_CONV", "tc")
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(Bottleneck(256, 64), Bottleneck(256, 64)).to(dev).to(memory_format=torch.channels_last)
+    fm = FlatModel(m, shadow=None)
+    fm.shadow = fm.flat.to(torch.bfloat16)
+    attach_shadow(m, fm)
+    m.train()
+    x = _t((8, 256, 28, 28), 5)
+
+    def step(side):
+        fm.zero_grad()
+        CV.side_wgrad(side)
+        try:
+            (m(x).float() ** 2).mean().backward()
+        finally:
+            CV.join_side_wgrad()
+            CV.side_wgrad(False)
+        fm.flush_grad_sink()
+
+    step(False)
+    torch.cuda.synchronize()
+    g_inline = fm.grad.clone()
+    step(True)
+    torch.cuda.synchronize()
+    g_side = fm.grad.clone()
+    assert float(g_inline.abs().max()) > 0
+    torch.testing.assert_close(g_side, g_inline, rtol=1e-3, atol=1e-5 * float(g_inline.abs().max()) + 1e-7)
+    # captured: replay twice, the gradients of a replay equal the eager ones
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        step(True)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        step(True)
+    g.replay()
+    g.replay()
+    torch.cuda.synchronize()
+    torch.testing.assert_close(fm.grad, g_inline, rtol=1e-3, atol=1e-5 * float(g_inline.abs().max()) + 1e-7)

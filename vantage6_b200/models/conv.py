@@ -1,9 +1,14 @@
 """Convolution with an fp32 master filter and a bf16 compute copy (ResNet-50 local step).
 
-The convolution itself is library code (cuDNN's sm_100 implicit-GEMM kernels through
-``aten::convolution`` -- the same role cuBLAS plays for plain GEMMs); what this layer removes is
-everything *around* it that the autocast path launches per layer and per step
-(profiles/launches_resnet50_fusedbn_v2_r1.txt):
+Default path (``V6B200_CONV=tc``): the hand-written tcgen05 implicit-GEMM kernels of csrc/igemm.cu through ops/conv.py --
+forward (optionally with the BatchNorm batch statistics of the output in its epilogue), data gradient (filter read in
+place through an MN-major descriptor, residual-branch gradient folded into the epilogue: ``GradFork``) and filter gradient
+(split-K, fp32 accumulation straight into the flat gradient buffer, issued on a second stream so that it overlaps the
+BatchNorm backward passes of the next layer: ``side_wgrad``).
+
+Library arm (``V6B200_CONV=cudnn``, also the fallback for shapes the kernels do not take): ``aten::convolution`` on the
+bf16 shadow filter.  What this layer removes there is everything *around* the convolution that the autocast path
+launches per layer and per step (profiles/launches_resnet50_fusedbn_v2_r1.txt):
 
 * the fp32 -> bf16 filter cast: the forward reads the bf16 shadow copy that the fused optimizer (K7)
   and the aggregation kernel (K2) keep up to date,
@@ -49,6 +54,49 @@ def _tc_mode() -> str:
     import os
 
     return os.environ.get("V6B200_CONV", "tc")
+
+
+class _SideWgrad:
+    """Filter gradients on a second stream.  In the backward pass the data-gradient chain (dgrad -> BatchNorm backward ->
+    dgrad ...) is the critical path; the filter gradient of a layer only feeds the optimizer at the end of the step.  Both
+    convolution kernels own a whole SM (~200 KB of shared memory per CTA), but the memory-bound BatchNorm backward passes
+    of the next layer fit next to a filter-gradient CTA -- so the filter gradients are issued on a side stream (forked
+    after ``dy`` exists, joined once by :func:`join_side_wgrad` before the optimizer) and overlap them.  Under CUDA-graph
+    capture the fork / join events become graph edges.  Enabled by the trainer (``side_wgrad(True)``); tensors the side
+    stream reads are kept referenced until the join, so the caching allocator cannot hand their blocks out early."""
+
+    def __init__(self):
+        self.enabled = False
+        self.streams: dict = {}
+        self.pending: list = []
+        self.forked = False
+
+    def stream(self, device) -> "torch.cuda.Stream":
+        key = torch.device(device).index
+        st = self.streams.get(key)
+        if st is None:
+            st = self.streams[key] = torch.cuda.Stream(device=device)
+        return st
+
+
+_side = _SideWgrad()
+
+
+def side_wgrad(enable: bool) -> bool:
+    """Switch the side-stream filter gradients on / off (``V6B200_WGRAD_STREAM=0`` keeps them off); returns the state."""
+    import os
+
+    _side.enabled = bool(enable) and os.environ.get("V6B200_WGRAD_STREAM", "1") != "0"
+    return _side.enabled
+
+
+def join_side_wgrad() -> None:
+    """Make the current stream wait for the filter gradients issued since the last join (call before reading ``.grad``)."""
+    if _side.forked:
+        for st in _side.streams.values():
+            torch.cuda.current_stream(st.device).wait_stream(st)
+        _side.forked = False
+    _side.pending.clear()
 
 
 class GradFork:
@@ -112,7 +160,15 @@ class _TcConvFn(torch.autograd.Function):
         direct = (g is not None and g.dtype == torch.float32 and g.shape == weight.shape
                   and g.is_contiguous(memory_format=torch.channels_last))
         if direct:
-            C.conv_wgrad(dy, x, g, (r, s), stride, pad)
+            if _side.enabled:
+                st = _side.stream(x.device)
+                st.wait_stream(torch.cuda.current_stream(x.device))      # dy exists, the gradient buffer is zeroed
+                with torch.cuda.stream(st):
+                    C.conv_wgrad(dy, x, g, (r, s), stride, pad)
+                _side.pending.append((dy, x))
+                _side.forked = True
+            else:
+                C.conv_wgrad(dy, x, g, (r, s), stride, pad)
             return dx, None, None, None, None, None, None, None
         dw = torch.zeros((cout, r, s, cin), device=x.device, dtype=torch.float32)
         C.conv_wgrad(dy, x, dw, (r, s), stride, pad)

@@ -319,12 +319,12 @@ static void launch_dependent(void (*kernel)(KArgs...), int grid, size_t smem, bo
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-// tuning variant of the element-wise passes (V6B200_BN_CFG; scripts/bn_bench.py sweeps it):
-//   0  U = 4 rows in flight, coefficients in shared memory, 4 CTAs/SM            (default)
-//   1  U = 2, coefficients in registers, 3 CTAs/SM                                (the round-1 shape)
-//   2  U = 4, coefficients in registers, 2 CTAs/SM
+// tuning variant of the element-wise passes (V6B200_BN_CFG; scripts/bn_bench.py sweeps it, profiles/bn_bench_r2f.jsonl):
+//   0  U = 4 rows in flight, coefficients in shared memory, 4 CTAs/SM      2.93 ms of BN passes per ResNet-50 step
+//   1  U = 2, coefficients in registers, 3 CTAs/SM                          2.52 ms   (default; 5.5-6.0 TB/s on the
+//   2  U = 4, coefficients in registers, 2 CTAs/SM                          2.51 ms    100 MB layers = 0.84-0.91 of copy peak)
 static int bn_cfg() {
-    static const int v = [] { const char* e = getenv("V6B200_BN_CFG"); return e ? atoi(e) : 0; }();
+    static const int v = [] { const char* e = getenv("V6B200_BN_CFG"); return e ? atoi(e) : 1; }();
     return v;
 }
 

@@ -21,6 +21,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import torch
 from torch import nn
 
+from ..models import conv as conv_mod
 from ..models.flat import FlatModel, flat_size
 from ..ops import optim as fused_optim
 from .fedavg import FedAvgEngine, ServerOptConfig
@@ -36,9 +37,10 @@ class FederatedTrainer:
                  max_grad_norm: Optional[float] = None, process_group=None, include_buffers: bool = True,
                  shadow_bf16: bool = False, fused_local_optimizer: bool = True, fault_tolerant: bool = False,
                  metrics=None, checkpoint_dir: Optional[str] = None, checkpoint_every: int = 0,
-                 timeout_ms: Optional[float] = None):
+                 timeout_ms: Optional[float] = None, side_wgrad: bool = True):
         self.rank, self.world = rank, world
         self.device = torch.device(device)
+        self.side_wgrad = bool(side_wgrad) and self.device.type == "cuda"
         self.model = model.to(self.device)
         self.forward_loss = forward_loss
         self.amp_dtype = amp_dtype if self.device.type == "cuda" else None
@@ -101,7 +103,14 @@ class FederatedTrainer:
         ctx = torch.autocast("cuda", dtype=self.amp_dtype) if self.amp_dtype is not None else contextlib.nullcontext()
         with ctx:
             loss = self.forward_loss(self.model, x, y)
-        loss.backward()
+        if self.side_wgrad:
+            conv_mod.side_wgrad(True)      # filter gradients on a second stream (models/conv.py::_SideWgrad)
+        try:
+            loss.backward()
+        finally:
+            if self.side_wgrad:
+                conv_mod.join_side_wgrad()
+                conv_mod.side_wgrad(False)
         self.fm.flush_grad_sink()          # bf16 conv weight gradients -> flat fp32 grads, one multi-tensor kernel
         self.loss_sum += loss.detach().float()
         if self.torch_opt is not None:
