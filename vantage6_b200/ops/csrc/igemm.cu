@@ -486,21 +486,27 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             for (int kk = 0; kk < 4; ++kk)
                 if (kk == k) { run1[kk][0] += a0; run1[kk][1] += a1; run2[kk][0] += b0; run2[kk][1] += b1; }
         };
-        // stride-2 DGRAD: row (n, i, j) of the class grid -> dX pixel (2i + a, 2j + b); 32 channels = 64 B per thread
-        auto scatter = [&](const uint32_t (&packed)[16], int m, int col0, int cls) {
-            if (m >= P.M) return;
-            const int n_img = m / P.PQ, rem = m - n_img * P.PQ;
-            const int oi = 2 * (rem / P.Q), oj = 2 * (rem % P.Q);
-            __nv_bfloat16* base = P.dx + ((size_t)n_img * P.OH * P.OW) * P.N + col0;
-            uint4* dst = reinterpret_cast<uint4*>(base + ((size_t)(oi + P.cls_a[cls]) * P.OW + oj + P.cls_b[cls]) * P.N);
+        // stride-2 DGRAD: row (n, i, j) of the class grid -> dX pixel (2i + a, 2j + b).  Through the staging box like the
+        // dense path: 4 lanes cover the 64 bytes of one pixel's 32 channels (two full sectors), 8 pixels per instruction
+        // (one thread per pixel writing 4 x 16 B at a 2-pixel pitch was 4x the LSU transactions); the pixels of the
+        // classes no tap reaches (1x1 filters) are zero-filled with the same pattern.
+        auto box_scatter = [&](uint32_t sbox, int row0, int c0, int cls) {
+            const int ch = lane & 3;
+            if (c0 + ch * 8 >= P.N) return;
+            __nv_bfloat16* base = P.dx + c0 + ch * 8;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-            if (P.zero_fill) {
+            for (int i = 0; i < 4; ++i) {
+                const int r = (lane >> 2) + 8 * i, m = row0 + r;
+                if (m >= P.M) continue;
+                const uint4 val = lds_v4(sbox + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4));
+                const int n_img = m / P.PQ, rem = m - n_img * P.PQ;
+                const int qi = rem / P.Q, oi = 2 * qi, oj = 2 * (rem - qi * P.Q);
+                __nv_bfloat16* img = base + ((size_t)n_img * P.OH * P.OW) * P.N;
+                *reinterpret_cast<uint4*>(img + ((size_t)(oi + P.cls_a[cls]) * P.OW + oj + P.cls_b[cls]) * P.N) = val;
+                if (P.zero_fill) {
 #pragma unroll
-                for (int z = 1; z < 4; ++z) {
-                    uint4* zd = reinterpret_cast<uint4*>(base + ((size_t)(oi + (z >> 1)) * P.OW + oj + (z & 1)) * P.N);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) zd[j] = make_uint4(0u, 0u, 0u, 0u);
+                    for (int z = 1; z < 4; ++z)
+                        *reinterpret_cast<uint4*>(img + ((size_t)(oi + (z >> 1)) * P.OW + oj + (z & 1)) * P.N) = make_uint4(0u, 0u, 0u, 0u);
                 }
             }
         };
@@ -545,15 +551,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     uint32_t p0[16], p1[16];
                     finish(v0, p0, row0 + lane, c0);
                     finish(v1, p1, row0 + lane, c1);
-                    if (EPI == EPI_GEN && strided) {
-                        scatter(p0, row0 + lane, c0, it.cls);
-                        if (second) scatter(p1, row0 + lane, c1, it.cls);
-                        continue;
-                    }
                     __syncwarp();                                            // every lane is done reading the boxes of the previous pair
                     to_box(stg, p0);
                     to_box(stg + STG_BOX_BYTES, p1);
                     __syncwarp();
+                    if (EPI == EPI_GEN && strided) {
+                        box_scatter(stg, row0, c0, it.cls);
+                        if (second) box_scatter(stg + STG_BOX_BYTES, row0, c1, it.cls);
+                        continue;
+                    }
                     box_to_global(stg, row0, c0);
                     if (second) box_to_global(stg + STG_BOX_BYTES, row0, c1);
                     if (stats) { box_stats(stg, k); if (second) box_stats(stg + STG_BOX_BYTES, k + 1); }
@@ -566,12 +572,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     if (rows_ok && c0 < P.N) {
                         uint32_t p0[16];
                         finish(v0, p0, row0 + lane, c0);
+                        __syncwarp();
+                        to_box(stg, p0);
+                        __syncwarp();
                         if (EPI == EPI_GEN && strided) {
-                            scatter(p0, row0 + lane, c0, it.cls);
+                            box_scatter(stg, row0, c0, it.cls);
                         } else {
-                            __syncwarp();
-                            to_box(stg, p0);
-                            __syncwarp();
                             box_to_global(stg, row0, c0);
                             if (stats) box_stats(stg, k);
                         }
