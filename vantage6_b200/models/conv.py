@@ -106,10 +106,19 @@ class GradFork:
     kernel -- always the last consumer to run -- adds it in its epilogue.  One full-tensor add pass per residual block
     disappears (4 % of a ResNet-50 round, profiles/launches_resnet50_v4_r1.txt)."""
 
-    __slots__ = ("grad", "armed")
+    __slots__ = ("grad", "mask", "armed")
 
     def __init__(self):
-        self.grad, self.armed = None, False
+        # mask: the parked gradient counts only where this 1-bit-per-element ReLU mask is set (ops/bn.py parks the
+        # block-output gradient + the mask instead of writing a masked copy)
+        self.grad, self.mask, self.armed = None, None, False
+
+
+def expand_relu_mask(mask: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    """[pixels, C/8] mask bytes -> a 0/1 tensor shaped like the channels_last activation ``like`` (fallback paths only)."""
+    n, c, h, w = like.shape
+    bits = (mask.view(n, h, w, c // 8, 1) >> torch.arange(8, device=mask.device, dtype=torch.uint8)) & 1
+    return bits.view(n, h, w, c).permute(0, 3, 1, 2).to(like.dtype)
 
 
 class _TcConvFn(torch.autograd.Function):
@@ -143,19 +152,20 @@ class _TcConvFn(torch.autograd.Function):
         cout, cin, r, s = w_bf16.shape
         dx = None
         if ctx.needs_input_grad[0]:
-            add = None
+            add = add_mask = None
             if ctx.fork_in is not None and ctx.fork_in.armed:
-                add, ctx.fork_in.grad = ctx.fork_in.grad, None
+                add, add_mask = ctx.fork_in.grad, ctx.fork_in.mask
+                ctx.fork_in.grad = ctx.fork_in.mask = None
             if C.dgrad_supported(cin, cout, r, s, stride, pad, x.shape[2], x.shape[3]):
-                dx = C.conv_dgrad(dy, w_bf16, (x.shape[2], x.shape[3]), pad, stride=stride, add=add)
+                dx = C.conv_dgrad(dy, w_bf16, (x.shape[2], x.shape[3]), pad, stride=stride, add=add, add_mask=add_mask)
                 add = None
             else:       # odd spatial sizes under stride 2: library kernel
                 dx = torch.ops.aten.convolution_backward(dy, x, w_bf16, None, (stride, stride), (pad, pad), (1, 1), False, (0, 0), 1,
                                                          (True, False, False))[0]
             if add is not None:
-                dx = dx + add
+                dx = dx + (add if add_mask is None else add * expand_relu_mask(add_mask, add))
             if ctx.fork_out is not None and ctx.fork_out.armed:      # downsample branch: park, the block's conv1 adds it
-                ctx.fork_out.grad, dx = dx, None
+                ctx.fork_out.grad, ctx.fork_out.mask, dx = dx, None, None
         g = weight.grad
         direct = (g is not None and g.dtype == torch.float32 and g.shape == weight.shape
                   and g.is_contiguous(memory_format=torch.channels_last))

@@ -275,6 +275,13 @@ class Node:
                 env[f"{label.upper()}_DATABASE_URI"] = str(uri)
             if self.gpu is not None:
                 env["V6_GPU"] = str(self.gpu)
+            if self.gpu is not None and self.gpu_worker is not None and not self.gpu_worker_sock:
+                # the resident worker is still coming up (first CUDA / torch import on a fresh box): a task that arrives now
+                # waits for it instead of paying its own CUDA bring-up and leaving the worker cold for the next task
+                deadline = time.time() + 150
+                while (time.time() < deadline and not self.gpu_worker_sock and self.gpu_worker is not None
+                       and self.gpu_worker.poll() is None and not self._stop.is_set()):
+                    time.sleep(0.1)
             if self.gpu_worker_sock and self.gpu_worker is not None and self.gpu_worker.poll() is None:
                 env["V6_GPU_WORKER"] = self.gpu_worker_sock
             pkg_root = str(Path(__file__).resolve().parent.parent.parent)

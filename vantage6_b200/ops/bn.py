@@ -80,7 +80,10 @@ class _BNFn(torch.autograd.Function):
         if not dy.is_contiguous(memory_format=torch.channels_last):
             dy = dy.contiguous(memory_format=torch.channels_last)
         dx = torch.empty_like(x)
-        dres = torch.empty_like(x) if ctx.has_res else None
+        # residual branch gradient = dy . relu'(y).  With an armed GradFork (models/conv.py) the block's first convolution
+        # folds it into its data-gradient epilogue straight from (dy, mask): no masked copy is written at all
+        park = ctx.has_res and ctx.res_fork is not None and ctx.res_fork.armed and (mask is not None or not ctx.relu)
+        dres = torch.empty_like(x) if (ctx.has_res and not park) else None
         # Flat-buffer models pre-allocate .grad as views of one fp32 gradient buffer (models/flat.py): the
         # kernel then accumulates dgamma / dbeta straight into it (no AccumulateGrad add launches).
         pg, pb = ctx.params
@@ -92,8 +95,8 @@ class _BNFn(torch.autograd.Function):
         native().bn_bwd(dy.data_ptr(), 0 if mask is None else mask.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
                         rstd.data_ptr(), dx.data_ptr(), 0 if dres is None else dres.data_ptr(), dgamma.data_ptr(),
                         dbeta.data_ptr(), coef.data_ptr(), part.data_ptr(), ctx.R, ctx.C, ctx.relu, direct, stream_ptr())
-        if dres is not None and ctx.res_fork is not None and ctx.res_fork.armed:
-            ctx.res_fork.grad, dres = dres, None
+        if park:
+            ctx.res_fork.grad, ctx.res_fork.mask = dy, (mask if ctx.relu else None)
         if direct:
             return dx, dres, None, None, None, None, None, None, None, None, None, None
         return dx, dres, dgamma, dbeta, None, None, None, None, None, None, None, None

@@ -189,7 +189,7 @@ int v6_conv_fprop(const void* x, const void* w, void* y, const float* bias, int 
                   float eps, float momentum, int force_im2col, long long pitch_w, long long pitch_h, long long pitch_n,
                   cudaStream_t stream);
 int v6_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad,
-                  int force_im2col, const void* add_src, cudaStream_t stream);
+                  int force_im2col, const void* add_src, const void* add_mask, cudaStream_t stream);
 int v6_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad,
                   float scale, int splits, int force_im2col, long long pitch_w, long long pitch_h, long long pitch_n,
                   cudaStream_t stream);

@@ -77,6 +77,7 @@ struct Params {
     int act;                   // bf16 epilogue: 0 none, 1 gelu(erf), 2 relu
     __nv_bfloat16* c_out;      // FPROP / DGRAD output [M, N] (row stride N)
     const float* bias;         // [N] or null
+    const unsigned char* add_mask;  // [M, N/8] or null: 1 bit / element, add_src counts only where the bit is set (ReLU mask of the block output)
     const __nv_bfloat16* add_src;   // [M, N] or null: added to the result before the bf16 rounding (DGRAD: the gradient
                                     // that reaches the same tensor through the residual branch -> no separate add pass)
     // DGRAD of a stride-2 convolution: one work item = (output parity class, tile); a class (a, b) holds the dX pixels
@@ -439,11 +440,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             const size_t off = (size_t)(row0 + (lane >> 2)) * P.N + c0 + ch * 8;
             uint4 val[4], addv[4];
             const bool add = EPI == EPI_GEN && P.add_src != nullptr;
+            unsigned mbits[4] = {0xffu, 0xffu, 0xffu, 0xffu};
             if (add) {      // the gradient of the residual branch, read with the same fully coalesced pattern as the store
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    addv[i] = row0 + (lane >> 2) + 8 * i < P.M ? __ldg(reinterpret_cast<const uint4*>(P.add_src + off + (size_t)(8 * i) * P.N))
-                                                              : make_uint4(0u, 0u, 0u, 0u);
+                for (int i = 0; i < 4; ++i) {
+                    const bool in = row0 + (lane >> 2) + 8 * i < P.M;
+                    addv[i] = in ? __ldg(reinterpret_cast<const uint4*>(P.add_src + off + (size_t)(8 * i) * P.N)) : make_uint4(0u, 0u, 0u, 0u);
+                    // the branch gradient is dy . relu'(block output): the mask byte of these 8 channels instead of a masked copy
+                    if (P.add_mask && in) mbits[i] = __ldg(P.add_mask + (off + (size_t)(8 * i) * P.N) / 8);
+                }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -458,7 +463,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const float2 x = unpack_bf16x2(v[e]), y = unpack_bf16x2(q[e]);
-                        v[e] = pack_bf16x2(x.x + y.x, x.y + y.y);
+                        v[e] = pack_bf16x2(x.x + (((mbits[i] >> (2 * e)) & 1u) ? y.x : 0.f), x.y + (((mbits[i] >> (2 * e + 1)) & 1u) ? y.y : 0.f));
                     }
                 }
             }
@@ -805,7 +810,7 @@ extern "C" int v6_conv_fprop(const void* x, const void* w, void* y, const float*
 
 // dx[N,H,W,Cin] = conv_transpose(dy[N,P,Q,Cout], w[Cout,R,S,Cin]) for stride 1 (P = H + 2*pad - R + 1)
 extern "C" int v6_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
-                             int pad, int force_im2col, const void* add_src, cudaStream_t stream) {
+                             int pad, int force_im2col, const void* add_src, const void* add_mask, cudaStream_t stream) {
     using namespace igemm;
     if (Cout % 64 != 0 || Cin % 8 != 0 || R != S) return (int)cudaErrorInvalidValue;
     if (add_src && (stride != 1 || Cin % 32 != 0)) return (int)cudaErrorInvalidValue;
@@ -861,7 +866,7 @@ extern "C" int v6_conv_dgrad(const void* dy, const void* w, void* dx, int N, int
     const bool plain = R == 1 && pad == 0 && !force_im2col;
     P.M = M; P.N = Cin; P.num_kb = R * S * (Cout / 64); P.block_n = pick_block_n(M, Cin, R * S * (Cout / 64));
     P.a_im2col = plain ? 0 : 1; P.PQ = H * W; P.Q = W; P.stride = 1; P.pad = R - 1 - pad; P.S = S; P.cblocks = Cout / 64; P.taps = R * S; P.flip = 1;
-    P.dstride = 1; P.add_src = (const __nv_bfloat16*)add_src; P.c_out = (__nv_bfloat16*)dx;
+    P.dstride = 1; P.add_src = (const __nv_bfloat16*)add_src; P.add_mask = add_src ? (const unsigned char*)add_mask : nullptr; P.c_out = (__nv_bfloat16*)dx;
     if (plain) { if (v6_make_tmap_2d_bf16(&ta, (uint64_t)dy, M, Cout, (uint64_t)Cout * 2, BLOCK_M, BLOCK_K, 1)) return -2; }
     else { ConvGeom g{N, Pp, Qq, Cout, R, S, 1, R - 1 - pad, H, W}; if (im2col_map(&ta, dy, g, BLOCK_M)) return -2; }
     if (v6_make_tmap_2d_bf16(&tc, (uint64_t)dx, M, Cin, (uint64_t)Cin * 2, 32, 32, 2)) return -2;

@@ -256,8 +256,8 @@ PYBIND11_MODULE(_C, m) {
               "conv_fprop");
     });
     m.def("conv_dgrad", [](u64 dy, u64 w, u64 dx, int N, int H, int W, int Cin, int Cout, int R, int Sw, int stride, int pad,
-                           bool force_im2col, u64 s, u64 add_src) {
-        check(v6_conv_dgrad(P<void>(dy), P<void>(w), P<void>(dx), N, H, W, Cin, Cout, R, Sw, stride, pad, force_im2col, P<void>(add_src),
+                           bool force_im2col, u64 s, u64 add_src, u64 add_mask) {
+        check(v6_conv_dgrad(P<void>(dy), P<void>(w), P<void>(dx), N, H, W, Cin, Cout, R, Sw, stride, pad, force_im2col, P<void>(add_src), P<void>(add_mask),
                             S(s)), "conv_dgrad");
     });
     m.def("conv_wgrad", [](u64 dy, u64 x, u64 dw, int N, int H, int W, int Cin, int Cout, int R, int Sw, int stride, int pad,

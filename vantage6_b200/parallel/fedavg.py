@@ -104,7 +104,10 @@ class FedAvgEngine:
 
             self._C = native()
             self.heap = SymmetricHeap(rank, world, self.device)
-            want_mc = (multicast is True) or (multicast == "auto")
+            # "auto": the in-switch reduction / multicast store from 3 GPUs up.  Between two GPUs plain P2P loads and stores
+            # move the same bytes faster (measured, profiles/comm_2gpu_r1c.json: K2 0.186 ms P2P vs 0.313 ms multicast for
+            # 102 MB); at 8 it is the other way round (0.260 vs 0.316 ms, comm_8gpu_r1a.json).
+            want_mc = (multicast is True) or (multicast == "auto" and world >= 3)
             self._w_buf = self.heap.alloc(self.n * 4, multicast=want_mc)
             self.w = self._w_buf.view(torch.float32, self.n)
             if upload == "weights_f32":
