@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--server-opt", default="fedavg", choices=["fedavg", "fedavgm", "fedadam"])
     ap.add_argument("--baselines", default=None, help="comma list of comparator arms run after the product arm "
                                                       "(default: nccl,stock_graph for ResNet, nccl otherwise; '' = none)")
+    ap.add_argument("--bcast", default=os.environ.get("V6B200_BCAST", "push"), choices=["push", "fused"],
+                    help="fused: K1 -- the first-consumer weights arrive inside the first forward GEMM of the round (transformers, >= 2 GPUs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     return ap.parse_args()
@@ -99,7 +101,7 @@ def build_trainer(impl, args, rank, world, device):
 
     tr, spec = zoo.build_trainer(args.model, rank=rank, world=world, device=device, server_mode=args.server_mode,
                                  server_opt=sopt, data_plane="native" if b200 else "collective", fused_local_optimizer=b200,
-                                 use_cuda_graph=graph)
+                                 use_cuda_graph=graph, **({"bcast": "fused"} if (b200 and args.bcast == "fused") else {}))
     return tr, spec
 
 
@@ -201,6 +203,7 @@ def run_trainer_arm(impl, args, rank, world, local_rank, device):
            "config": {"model": args.model, "global_batch": B * world, "parallelism": f"fedavg{world} (1 node/GPU, server {args.server_mode})",
                       "local_steps_per_round": n_steps, "local_batch": B, "local_samples": int(n_samples), **shape,
                       "server_opt": args.server_opt, "param_dtype": "fp32 master", "upload": trainer.upload_mode,
+                      "bcast": ("fused (K1: %d layers)" % trainer.k1_layers) if getattr(trainer, "k1_layers", 0) else "push (K2)",
                       "n_federated_params": int(trainer.fm.n_total),
                       "l2": "inputs larger than L2 (per-round inputs + model + activations >> 126 MB), no flush",
                       "data_plane": trainer.engine.data_plane, "multicast": bool(trainer.engine.use_multicast),

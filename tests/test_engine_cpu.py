@@ -443,3 +443,31 @@ def test_packed_attention_falls_back_off_gpu():
     qkv = torch.randn(2, 8, 3, 2, 16)
     ref = attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], causal=False)
     torch.testing.assert_close(packed_attention(qkv, causal=False), ref)
+
+
+def test_flat_model_puts_first_consumer_weights_in_a_prefix():
+    """``_v6_first`` parameters (the weights K1 delivers: trainer bcast="fused") open the flat buffers as one contiguous range."""
+    from vantage6_b200.models.flat import FlatModel
+
+    m = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 24), torch.nn.Linear(24, 8))
+    m[1].weight._v6_first = True
+    m[2].weight._v6_first = True
+    ref = {n: p.detach().clone() for n, p in m.named_parameters()}
+    fm = FlatModel(m)
+    assert fm.segment("1.weight").offset == 0 and fm.segment("2.weight").offset == 16 * 24
+    assert fm.n_first == 16 * 24 + 24 * 8
+    assert fm.segment("0.weight").offset == fm.n_first
+    for n, p in m.named_parameters():                  # re-homing keeps the values, whatever the order
+        torch.testing.assert_close(p.detach(), ref[n])
+    assert fm.check_aliasing()
+
+
+def test_engine_shard_alignment():
+    from vantage6_b200.parallel.fedavg import FedAvgEngine
+
+    e = FedAvgEngine(10_000, 0, 1, "cpu", shard_align=256)
+    e.reducers = [0, 1, 2]
+    e.rank = 1
+    e._reshard()
+    assert e.lo % 256 == 0 and e.hi % 256 == 0 and e.hi > e.lo
+    assert e.k1_layer(0, 256, 8) is None               # no NVLink data plane on the CPU: K2 keeps pushing everything

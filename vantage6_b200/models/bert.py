@@ -35,7 +35,7 @@ class BertLayer(nn.Module):
     def __init__(self, c: BertConfig):
         super().__init__()
         self.heads, self.hd = c.heads, c.hidden // c.heads
-        self.qkv = ShadowLinear(c.hidden, 3 * c.hidden)
+        self.qkv = ShadowLinear(c.hidden, 3 * c.hidden, first_consumer=True)      # first GEMM of the layer: K1 candidate
         self.out = ShadowLinear(c.hidden, c.hidden)
         self.ln1 = FusedLayerNorm(c.hidden, c.eps)
         self.ffn1 = ShadowLinear(c.hidden, c.ffn, act=G.ACT_GELU)
@@ -87,6 +87,11 @@ def bert_base() -> BertForMaskedLM:
 
 def bert_tiny() -> BertForMaskedLM:
     return BertForMaskedLM(BertConfig(vocab_size=512, hidden=64, layers=2, heads=2, ffn=256, max_pos=64))
+
+
+def bert_small() -> BertForMaskedLM:
+    """4 layers of width 256 (QKV = 768 rows = three 256-row blocks): the smallest shape the K1 path takes; multi-GPU checks."""
+    return BertForMaskedLM(BertConfig(vocab_size=1024, hidden=256, layers=4, heads=4, ffn=1024, max_pos=128))
 
 
 def bert_forward_loss(model: nn.Module, input_ids: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:

@@ -40,11 +40,15 @@ class FlatModel:
         self.segments: List[Segment] = []
         off = 0
         params = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+        # parameters tagged ``_v6_first`` (the weights K1 delivers fused with their first GEMM: parallel/trainer.py
+        # ``bcast="fused"``) form one contiguous prefix [0, n_first) of the flat buffers
+        params.sort(key=lambda np_: 0 if getattr(np_[1], "_v6_first", False) else 1)
         frozen = [(n, p) for n, p in module.named_parameters() if not p.requires_grad]
         for n, p in params:
             self.segments.append(Segment(n, off, p.numel(), tuple(p.shape), True, _is_channels_last(p)))
             off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.n_trainable = off
+        self.n_first = sum((p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN for _, p in params if getattr(p, "_v6_first", False))
         bufs = []
         if include_buffers:
             bufs = [(n, b) for n, b in module.named_buffers() if b.dtype.is_floating_point]

@@ -45,14 +45,25 @@ def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         return torch.mm(a, b).float()
 
 
+# K1: in the FIRST local step of a round the layers tagged ``first_consumer`` do not find their new bf16
+# weights in the local shadow buffer -- the aggregation kernel left them on their owner (FedAvgEngine ``shadow_skip``) --
+# but receive them inside their forward GEMM: the owner's kernel multicasts the tiles through the NVSwitch, every rank's
+# main loop consumes them behind per-tile flags (ops/gemm.py::bcast_push_gemm_bf16).  The trainer switches this on for
+# that one step (``K1_STEP["on"]``); every other step is the plain GEMM on the (by then complete) local copy.
+K1_STEP = {"on": False}
+
+
 class _ShadowLinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, w_bf16, act, sink, offset):
+    def forward(ctx, x, weight, bias, w_bf16, act, sink, offset, k1=None):
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         wb = w_bf16 if w_bf16 is not None else weight.detach().to(torch.bfloat16)
-        if x2.is_cuda:
+        if x2.is_cuda and k1 is not None:
+            pre = G.bcast_push_gemm_bf16(x2, wb, k1["w_mc_ptr"], k1["flags"], k1["flag_peer_ptrs"], k1["world"], k1["is_owner"], 0,
+                                         bias=bias, own_blocks=k1["own_blocks"], epoch_ptr=k1["epoch_ptr"], status_ptr=k1["status_ptr"])
+        elif x2.is_cuda:
             pre = G.gemm_bf16(x2, wb, bias, G.ACT_NONE)
         else:
             pre = G.reference_linear(x2, wb, bias, G.ACT_NONE)
@@ -85,12 +96,12 @@ class _ShadowLinearFn(torch.autograd.Function):
             g = ctx.weight.grad if ctx.need_w else None
             if g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.shape == wb.shape:
                 C.linear_wgrad(dy2, x2, g)              # fp32, straight into the flat gradient buffer: no bf16 dW, no sink entry
-                return dx, None, db, None, None, None, None
+                return dx, None, db, None, None, None, None, None
             if ctx.need_w:
                 dwf = torch.zeros(wb.shape, device=dy2.device, dtype=torch.float32)
                 C.linear_wgrad(dy2, x2, dwf)
-                return dx, dwf, db, None, None, None, None
-            return dx, None, db, None, None, None, None
+                return dx, dwf, db, None, None, None, None, None
+            return dx, None, db, None, None, None, None, None
         dx = torch.mm(dy2, wb).view(ctx.xshape) if ctx.needs_input_grad[0] else None
         dw = None
         if ctx.need_w:
@@ -98,16 +109,18 @@ class _ShadowLinearFn(torch.autograd.Function):
                 ctx.sink.append((torch.mm(dy2.t(), x2), ctx.offset))      # bf16 dW -> flat fp32 grads, one kernel per step
             else:
                 dw = _mm_f32(dy2.t(), x2)
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
 class ShadowLinear(nn.Module):
     """nn.Linear with fp32 master weight, bf16 compute copy and optional fused activation."""
 
     def __init__(self, in_features: int, out_features: int, bias: bool = True, act: int = G.ACT_NONE,
-                 init_std: float = 0.02):
+                 init_std: float = 0.02, first_consumer: bool = False):
         super().__init__()
         self.in_features, self.out_features, self.act = in_features, out_features, act
+        self.first_consumer = bool(first_consumer)      # first GEMM of its block to read the new global weights (K1 candidate)
+        self.k1: Optional[dict] = None                  # set by the trainer (bcast="fused"): FedAvgEngine.k1_layer(...)
         self.weight = nn.Parameter(torch.empty(out_features, in_features).normal_(0.0, init_std))
         self.bias = nn.Parameter(torch.zeros(out_features)) if bias else None
         self.w_bf16: Optional[torch.Tensor] = None      # view into the shadow buffer (set by attach_shadow)
@@ -117,7 +130,8 @@ class ShadowLinear(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if x.dtype != torch.bfloat16:
             x = x.to(torch.bfloat16)
-        return _ShadowLinearFn.apply(x, self.weight, self.bias, self.w_bf16, self.act, self._sink, self._offset)
+        k1 = self.k1 if (K1_STEP["on"] and self.k1 is not None) else None
+        return _ShadowLinearFn.apply(x, self.weight, self.bias, self.w_bf16, self.act, self._sink, self._offset, k1)
 
 
 class FrozenLinear(nn.Module):

@@ -87,6 +87,8 @@ def _specs() -> Dict[str, ModelSpec]:
                                "adamw", 1e-4, "delta_bf16", True, False, 4, 32, dict(weight_decay=0.01, max_grad_norm=1.0)),
         "bert_tiny": ModelSpec("bert_tiny", lambda d: bert.bert_tiny(), bert.bert_forward_loss, _mlm_batches(512, 32),
                                "adamw", 1e-3, "delta_bf16", True, False, 2, 4, dict(weight_decay=0.01)),
+        "bert_small": ModelSpec("bert_small", lambda d: bert.bert_small(), bert.bert_forward_loss, _mlm_batches(1024, 64),
+                                "adamw", 1e-3, "delta_bf16", True, False, 2, 8, dict(weight_decay=0.01)),
         "llama3_8b_lora": ModelSpec("llama3_8b_lora", lambda d: llama.llama3_8b_lora(d), llama.llama_forward_loss,
                                     _lm_batches(128256, 1024), "adamw", 2e-4, "delta_bf16", True, False, 2, 1,
                                     dict(weight_decay=0.0, max_grad_norm=1.0, include_buffers=False)),

@@ -45,6 +45,8 @@ struct FedAvgParams {
     float inv_total;         // 1 / sum_i n_i over participants
     long long timeout_cycles;
     unsigned int* cta_counter;   // local scratch, zeroed by host once; self-resetting
+    long long shadow_skip_lo, shadow_skip_hi;   // bf16 shadow elements [lo, hi) are NOT pushed to the peers (only written locally):
+                                                // K1 delivers them, fused with the first GEMM that consumes them (gemm.cu)
 };
 
 struct SmallParams {
@@ -156,7 +158,8 @@ int v6_gemm2_bf16(const void* A, const void* B, void* C, const float* bias, int 
 int v6_gemm_smem_bytes();
 int v6_bcast_push_gemm_bf16(const void* A, void* B_local, void* B_mc, void* C, const float* bias, int M, int N, int K, int lda, int ldb,
                             int ldc, int act, uint32_t* ready_flags, const PeerTable* flag_peers, int world, int is_owner,
-                            uint32_t epoch, cudaStream_t stream);
+                            uint32_t epoch, int own_nb_lo, int own_nb_hi, const uint32_t* epoch_ptr, uint32_t* status_ptr,
+                            cudaStream_t stream);
 int v6_flash_attn_fwd2_vmn(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S, int Hq, int Hkv,
                            int D, long long ldq, long long ldk, long long ldv, float softmax_scale, int causal,
                            cudaStream_t stream);

@@ -197,11 +197,14 @@ fedavg_round_kernel(const FedAvgParams P) {
                     acc[4 * h + 0] = w[0]; acc[4 * h + 1] = w[1]; acc[4 * h + 2] = w[2]; acc[4 * h + 3] = w[3];
                 }
                 if (P.shadow_out.p[0] != nullptr || P.shadow_mc != nullptr) {
-                    // bf16 shadow copy of the new global for bf16 compute paths (VN elements)
+                    // bf16 shadow copy of the new global for bf16 compute paths (VN elements).  Elements in the K1 range stay
+                    // on the owner: the first GEMM that consumes them multicasts them tile by tile (gemm.cu, fused_bcast == 2)
+                    const bool local_only = e >= P.shadow_skip_lo && e < P.shadow_skip_hi;
                     if constexpr (VN == 8) {
                         uint4 s = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
                                              pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
-                        if (P.shadow_mc) multimem_st_u4(reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.shadow_mc) + e), s);
+                        if (local_only) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.shadow_out.p[P.rank]) + e) = s;
+                        else if (P.shadow_mc) multimem_st_u4(reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.shadow_mc) + e), s);
                         else {
 #pragma unroll
                             for (int p = 0; p < V6_MAX_PEERS; ++p)
@@ -212,7 +215,7 @@ fedavg_round_kernel(const FedAvgParams P) {
                         uint2 s = make_uint2(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]));
 #pragma unroll
                         for (int p = 0; p < V6_MAX_PEERS; ++p)
-                            if (p < P.world && ((P.live_mask >> p) & 1u))
+                            if (p < P.world && ((P.live_mask >> p) & 1u) && (!local_only || p == P.rank))
                                 *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.shadow_out.p[p]) + e) = s;
                     }
                 }

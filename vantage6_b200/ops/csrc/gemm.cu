@@ -61,6 +61,10 @@ struct Params {
     // (multimem.st: egress 1x instead of one pull per consumer) and raises the tile's flag on every rank; all ranks
     // (the owner included) consume tiles from their local copy as the flags arrive.
     int is_owner, world, ldb;
+    int push_kgroup;                   // push: k-blocks per push unit (1, 2 or 4)
+    int own_nb_lo, own_nb_hi;          // push: this rank owns (multicasts) the 256-row weight blocks [lo, hi)
+    const uint32_t* epoch_ptr;         // non-null: the epoch is read from device memory (a captured graph replays with the current round)
+    uint32_t* status_ptr;              // non-null: a flag wait that times out sets *status_ptr = 1 and goes on (instead of trapping)
     const __nv_bfloat16* b_src;      // owner's source (its own copy of the weights)
     __nv_bfloat16* b_mc;             // multicast VA over every rank's weight buffer
     PeerTable flag_peers;            // every rank's flag array (peer VAs)
@@ -126,6 +130,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
         // ============================ TMA producer ============================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            const uint32_t epoch = (P.fused_bcast && P.epoch_ptr) ? ld_acquire_sys_u32(P.epoch_ptr) : P.epoch;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 int m_blk, n_blk;
                 tile_coords(t, m_blk, n_blk);
@@ -139,9 +144,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
                         // K1: wait until some CTA's pull warp has landed this weight tile in the local copy
                         const uint32_t* f = P.ready_flags + n_blk * num_k + kb;
                         const long long t0 = clock64();
-                        while ((int32_t)(ld_acquire_sys_u32(f) - P.epoch) < 0) {
+                        while ((int32_t)(ld_acquire_sys_u32(f) - epoch) < 0) {
                             __nanosleep(32);
-                            if (clock64() - t0 > 4000000000LL) asm volatile("trap;");
+                            if (clock64() - t0 > 4000000000LL) {
+                                if (P.status_ptr) { *P.status_ptr = 1u; break; }      // dead owner: reported, the round is redone
+                                asm volatile("trap;");
+                            }
                         }
                         asm volatile("fence.proxy.async.global;" ::: "memory");
                     }
@@ -190,31 +198,43 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
         if (P.fused_bcast == 2) {
             // ---- push: owner only.  Tile order k-major like the consumers' first k-blocks; one tile = 256 rows x 128 B.
             if (P.is_owner) {
-                const int n_tiles = num_k * num_n;
-                const int rsub = lane >> 3, ch = lane & 7;                      // 4 rows x 8 sixteen-byte chunks per warp instruction
-                for (int idx = blockIdx.x; idx < n_tiles; idx += gridDim.x) {
-                    const int kb = idx / num_n, nb = idx % num_n;
+                const uint32_t epoch = P.epoch_ptr ? ld_acquire_sys_u32(P.epoch_ptr) : P.epoch;
+                // push unit = one 256-row weight block x `kg` consecutive k-blocks: a row of the unit is kg x 128 contiguous
+                // bytes (8 * kg lanes x 16 B, fully coalesced), 16 row-chunks in flight per lane, ONE fence + kg flags per
+                // unit.  (One 32 KB tile per fence with 4 rows per instruction reached 170 GB/s from inside the GEMM --
+                // profiles/comm_2gpu_r2b.json -- a third of what the link takes.)  Order: k-major, like the consumers.
+                const int kg = P.push_kgroup, num_kg = (num_k + kg - 1) / kg;
+                const int lpr = 8 * kg, rpi = 32 / lpr;                          // lanes per row, rows per instruction
+                const int rsub = lane / lpr, ch = lane % lpr;
+                const int n_units = num_kg * num_n;
+                for (int idx = blockIdx.x; idx < n_units; idx += gridDim.x) {
+                    const int kgi = idx / num_n, nb = idx % num_n;
+                    if (nb < P.own_nb_lo || nb >= P.own_nb_hi) continue;          // another rank's shard
                     const int rows = min(BLOCK_N, P.N - nb * BLOCK_N);
-                    const size_t base = (size_t)(nb * BLOCK_N) * P.ldb + (size_t)kb * BLOCK_K + ch * 8;
-                    const bool col_ok = kb * BLOCK_K + ch * 8 < P.K;
+                    const int col = kgi * kg * BLOCK_K + ch * 8;
+                    const size_t base = (size_t)(nb * BLOCK_N) * P.ldb + (size_t)col;
+                    const bool col_ok = col < P.K;
+                    constexpr int PU = 16;
 #pragma unroll 1
-                    for (int r0 = 0; r0 < rows; r0 += 32) {
-                        uint4 v[8];
+                    for (int r0 = 0; r0 < rows; r0 += PU * rpi) {
+                        uint4 v[PU];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int r = r0 + u * 4 + rsub;
+                        for (int u = 0; u < PU; ++u) {
+                            const int r = r0 + u * rpi + rsub;
                             if (r < rows && col_ok) v[u] = *reinterpret_cast<const uint4*>(P.b_src + base + (size_t)r * P.ldb);
                         }
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int r = r0 + u * 4 + rsub;
+                        for (int u = 0; u < PU; ++u) {
+                            const int r = r0 + u * rpi + rsub;
                             if (r < rows && col_ok) multimem_st_u4(reinterpret_cast<uint4*>(P.b_mc + base + (size_t)r * P.ldb), v[u]);
                         }
                     }
-                    fence_acq_rel_sys();                       // every lane's multicast stores before the flag
+                    fence_acq_rel_sys();                       // every lane's multicast stores before the flags
                     __syncwarp();
-                    if (lane < P.world)
-                        st_release_sys_u32(reinterpret_cast<uint32_t*>(P.flag_peers.p[lane]) + nb * num_k + kb, P.epoch);
+                    for (int j = lane; j < P.world * kg; j += 32) {
+                        const int peer = j / kg, kb = kgi * kg + j % kg;
+                        if (kb < num_k) st_release_sys_u32(reinterpret_cast<uint32_t*>(P.flag_peers.p[peer]) + nb * num_k + kb, epoch);
+                    }
                     __syncwarp();
                 }
             }
@@ -366,7 +386,8 @@ extern "C" int v6_bcast_gemm_bf16(const void* A, void* B_local, const void* B_se
 //   flag_peers: every rank's flag array.  The owner passes is_owner = 1 (its B_local holds the new weights).
 extern "C" int v6_bcast_push_gemm_bf16(const void* A, void* B_local, void* B_mc, void* C, const float* bias, int M, int N, int K,
                                        int lda, int ldb, int ldc, int act, uint32_t* ready_flags, const PeerTable* flag_peers,
-                                       int world, int is_owner, uint32_t epoch, cudaStream_t stream) {
+                                       int world, int is_owner, uint32_t epoch, int own_nb_lo, int own_nb_hi, const uint32_t* epoch_ptr,
+                                       uint32_t* status_ptr, cudaStream_t stream) {
     using namespace gemm;
     if (K % 8 != 0 || lda % 8 != 0 || ldb % 8 != 0 || ldc % 8 != 0 || !B_mc) return (int)cudaErrorInvalidValue;
     alignas(64) CUtensorMap ta, tb, tc;
@@ -376,7 +397,14 @@ extern "C" int v6_bcast_push_gemm_bf16(const void* A, void* B_local, void* B_mc,
     Params P = {};
     P.M = M; P.N = N; P.K = K; P.C = (__nv_bfloat16*)C; P.ldc = ldc; P.bias = bias; P.act = act;
     P.fused_bcast = 2; P.ready_flags = ready_flags; P.epoch = epoch; P.stages = kStages;
-    P.is_owner = is_owner; P.world = world; P.ldb = ldb; P.b_src = (const __nv_bfloat16*)B_local; P.b_mc = (__nv_bfloat16*)B_mc;
+    P.is_owner = is_owner; P.own_nb_lo = own_nb_lo; P.own_nb_hi = own_nb_hi < 0 ? (N + BLOCK_N - 1) / BLOCK_N : own_nb_hi;
+    P.epoch_ptr = epoch_ptr; P.status_ptr = status_ptr;
+    {   // widest push unit that still gives every CTA's pusher warp two units of the blocks this rank owns
+        const int nn = P.own_nb_hi - P.own_nb_lo, nk = (K + BLOCK_K - 1) / BLOCK_K;
+        P.push_kgroup = 1;
+        for (int kg : {4, 2}) if ((long long)nn * ((nk + kg - 1) / kg) >= 2 * 148) { P.push_kgroup = kg; break; }
+    }
+    P.world = world; P.ldb = ldb; P.b_src = (const __nv_bfloat16*)B_local; P.b_mc = (__nv_bfloat16*)B_mc;
     P.flag_peers = *flag_peers;
     static bool attr_set = false;
     if (!attr_set) {

@@ -67,8 +67,10 @@ PYBIND11_MODULE(_C, m) {
              const std::vector<float>& weight, long long lo, long long hi, int rank, int world, int n_reducers,
              uint32_t live_mask, uint32_t epoch, bool upload_is_delta, bool upload_prescaled, int server_opt, float server_lr, float beta1,
              float beta2, float eps, float bias1, float bias2, float inv_total, long long timeout_cycles, u64 cta_counter,
-             int upload_dtype, int grid, u64 stream, bool dynamic_weights, float my_weight, uint32_t reducer_mask) {
+             int upload_dtype, int grid, u64 stream, bool dynamic_weights, float my_weight, uint32_t reducer_mask, long long shadow_skip_lo,
+             long long shadow_skip_hi) {
               FedAvgParams p;
+              p.shadow_skip_lo = shadow_skip_lo; p.shadow_skip_hi = shadow_skip_hi;
               p.dynamic_weights = dynamic_weights ? 1 : 0; p.my_weight = my_weight;
               p.reducer_mask = reducer_mask ? reducer_mask : ((n_reducers >= 32) ? 0xffffffffu : ((1u << n_reducers) - 1u));
               p.upload = table(upload); p.param_out = table(param_out); p.shadow_out = table(shadow_out); p.pads = table(pads);
@@ -280,10 +282,11 @@ PYBIND11_MODULE(_C, m) {
     m.def("gemm_smem_bytes", &v6_gemm_smem_bytes);
     m.def("bcast_push_gemm_bf16", [](u64 A, u64 B_local, u64 B_mc, u64 C, u64 bias, int M, int N, int K, int lda, int ldb, int ldc,
                                      int act, u64 flags, const std::vector<u64>& flag_peers, int world, bool is_owner, uint32_t epoch,
-                                     u64 s) {
+                                     u64 s, int own_nb_lo, int own_nb_hi, u64 epoch_ptr, u64 status_ptr) {
         PeerTable t = table(flag_peers);
         check(v6_bcast_push_gemm_bf16(P<void>(A), P<void>(B_local), P<void>(B_mc), P<void>(C), P<float>(bias), M, N, K, lda, ldb,
-                                      ldc, act, P<uint32_t>(flags), &t, world, is_owner ? 1 : 0, epoch, S(s)), "bcast_push_gemm_bf16");
+                                      ldc, act, P<uint32_t>(flags), &t, world, is_owner ? 1 : 0, epoch, own_nb_lo, own_nb_hi,
+                                      P<uint32_t>(epoch_ptr), P<uint32_t>(status_ptr), S(s)), "bcast_push_gemm_bf16");
     });
 
     m.def("flash_attn_bwd", [](u64 q, u64 k, u64 v, u64 dout, u64 kt, u64 qt, u64 dot, u64 lse2, u64 delta, u64 dq, u64 dk,

@@ -111,12 +111,16 @@ def bcast_gemm_bf16(x2: torch.Tensor, W_local: torch.Tensor, W_server_ptr: int, 
 
 def bcast_push_gemm_bf16(x2: torch.Tensor, W_local: torch.Tensor, W_mc_ptr: int, ready_flags: torch.Tensor, flag_peer_ptrs,
                          world: int, is_owner: bool, epoch: int, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
-                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                         out: Optional[torch.Tensor] = None, own_blocks: Optional[tuple] = None, epoch_ptr: int = 0,
+                         status_ptr: int = 0) -> torch.Tensor:
     """K1 v3 (push): ``y = x2 @ W^T`` where the new weights are multicast by their owner from inside the GEMM kernel
     (``multimem.st`` through the NVSwitch: one egress copy for any number of nodes) with one ready flag per 256x64 weight
     tile; every rank's tcgen05 main loop consumes tiles from its local copy as their flags arrive -- broadcast and GEMM
     overlap tile by tile, no NCCL call, no separate copy kernel.  ``W_local`` must be this rank's buffer of a symmetric
-    allocation bound to the multicast address ``W_mc_ptr``; ``flag_peer_ptrs`` are the peer VAs of every rank's flags."""
+    allocation bound to the multicast address ``W_mc_ptr``; ``flag_peer_ptrs`` are the peer VAs of every rank's flags.
+    ``own_blocks = (lo, hi)``: this rank owns (multicasts) only the 256-row weight blocks [lo, hi) -- a sharded server
+    where several ranks hold parts of one layer; ``epoch_ptr``: device word holding the current round (CUDA-graph replays);
+    ``status_ptr``: device word set to 1 when a tile never arrives (dead owner) instead of trapping."""
     _check(x2, W_local)
     M, K = x2.shape
     N = W_local.shape[0]
@@ -127,7 +131,9 @@ def bcast_push_gemm_bf16(x2: torch.Tensor, W_local: torch.Tensor, W_mc_ptr: int,
     count(1)
     native().bcast_push_gemm_bf16(x2.data_ptr(), W_local.data_ptr(), W_mc_ptr, out.data_ptr(), 0 if bias is None else bias.data_ptr(),
                                   M, N, K, x2.stride(0), W_local.stride(0), out.stride(0), act, ready_flags.data_ptr(),
-                                  list(flag_peer_ptrs), world, bool(is_owner), epoch, stream_ptr())
+                                  list(flag_peer_ptrs), world, bool(is_owner), epoch, stream_ptr(),
+                                  0 if own_blocks is None else int(own_blocks[0]), -1 if own_blocks is None else int(own_blocks[1]),
+                                  int(epoch_ptr), int(status_ptr))
     return out
 
 

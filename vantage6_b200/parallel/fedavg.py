@@ -26,7 +26,7 @@ participation renormalises over the reporters (weight 0 == not reporting).
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Sequence
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 
@@ -76,8 +76,13 @@ class FedAvgEngine:
     def __init__(self, n_params: int, rank: int = 0, world: int = 1, device="cpu", *, data_plane: str = "auto",
                  server_mode: str = "sharded", server_opt: ServerOptConfig | None = None, upload: str = "weights_f32",
                  shadow_bf16: bool = False, multicast: bool | str = "auto", timeout_ms: float = 20000.0,
-                 process_group=None):
+                 process_group=None, shard_align: int = 8, shadow_skip: Tuple[int, int] = (0, 0), shadow_multicast: bool = False):
+        """``shard_align``: reducer slice boundaries are multiples of this many elements; ``shadow_skip`` = (lo, hi): the bf16
+        shadow elements K2 leaves on their owner (K1 -- :meth:`k1_layer` -- delivers them inside the first GEMM that reads
+        them); ``shadow_multicast``: bind the shadow buffer to a multicast address even when K2 itself runs on P2P."""
         assert upload in UPLOAD_MODES and server_mode in ("central", "sharded")
+        self.shard_align = max(8, int(shard_align))
+        self.shadow_skip = (int(shadow_skip[0]), int(shadow_skip[1]))
         self.rank, self.world = rank, world
         self.device = torch.device(device)
         self.server_mode = server_mode
@@ -117,13 +122,16 @@ class FedAvgEngine:
                 esz = 4 if upload == "delta_f32" else 2
                 self._up_buf = self.heap.alloc(self.n * esz, multicast=want_mc)
                 self.upload = self._up_buf.view(torch.float32 if esz == 4 else torch.bfloat16, self.n)
-            self._shadow_buf = self.heap.alloc(self.n * 2, multicast=want_mc) if shadow_bf16 else None
+            self._shadow_buf = self.heap.alloc(self.n * 2, multicast=want_mc or shadow_multicast) if shadow_bf16 else None
             self.shadow = self._shadow_buf.view(torch.bfloat16, self.n) if shadow_bf16 else None
             self._pad_buf = self.heap.alloc(PAD_WORDS * 4, multicast=False)
             self.pad = self._pad_buf.view(torch.int32, PAD_WORDS)
             self.use_multicast = bool(self._w_buf.mc_ptr) and bool(self._up_buf.mc_ptr) and want_mc
             self._cta_counter = torch.zeros(4, dtype=torch.int32, device=self.device)
             self.timeout_cycles = int(timeout_ms * device_clock_khz(self.device))
+            # K1: the current round as a device word (a captured first-step graph reads it) + a status word its waits report to
+            self.k1_words = torch.zeros(4, dtype=torch.int32, device=self.device)
+            self._k1_flag_bufs: list = []
         else:
             self.heap = None
             self.w = torch.zeros(self.n, dtype=torch.float32, device=self.device)
@@ -149,7 +157,8 @@ class FedAvgEngine:
         """(Re)compute this rank's slice [lo, hi) from the reducer list and make sure the server state it needs exists."""
         nr = len(self.reducers)
         chunk = (self.n + nr - 1) // nr
-        chunk = (chunk + 7) // 8 * 8
+        chunk = (chunk + self.shard_align - 1) // self.shard_align * self.shard_align
+        self._chunk = chunk
         if self.rank in self.reducers:
             pos = self.reducers.index(self.rank)
             self.lo = min(self.n, pos * chunk)
@@ -166,6 +175,42 @@ class FedAvgEngine:
             self.w_global = grow(self.w_global, True)
             self.opt_m = grow(self.opt_m, self.opt.name in ("fedavgm", "fedadam"))
             self.opt_v = grow(self.opt_v, self.opt.name == "fedadam")
+
+    # ------------------------------------------------------------------ K1: broadcast fused with the first consuming GEMM
+    def k1_layer(self, offset: int, n_out: int, k_in: int) -> Optional[dict]:
+        """Everything ``ops.gemm.bcast_push_gemm_bf16`` needs to deliver the [n_out, k_in] bf16 weight at flat ``offset`` (inside
+        ``shadow_skip``): the multicast address of the shadow slice, symmetric per-tile ready flags, and the 256-row blocks
+        of the layer that lie in THIS rank's reducer slice (their owner multicasts them).  ``None`` when the layout does not
+        allow it (no multicast binding, slice boundaries that cut a 256-row block)."""
+        if self.data_plane != "native" or self._shadow_buf is None or not self._shadow_buf.mc_ptr or self.world < 2:
+            return None
+        blk = 256 * k_in
+        if n_out % 256 or offset % 8 or not (self.shadow_skip[0] <= offset and offset + n_out * k_in <= self.shadow_skip[1]):
+            return None
+        # the same answer on every rank (the flag allocation below is collective): NO reducer boundary may cut a block
+        size = n_out * k_in
+        for pos in range(1, len(self.reducers)):
+            b = pos * self._chunk - offset
+            if 0 < b < size and b % blk:
+                return None
+        lo, hi = max(self.lo, offset) - offset, min(self.hi, offset + size) - offset
+        own = (lo // blk, hi // blk) if hi > lo else (0, 0)
+        n_flags = (n_out // 256) * ((k_in + 63) // 64)
+        fb = self.heap.alloc(n_flags * 4, multicast=False)
+        fb.view(torch.int32, n_flags).zero_()
+        self._k1_flag_bufs.append(fb)
+        return dict(w_mc_ptr=self._shadow_buf.mc_ptr + 2 * offset, flags=fb.view(torch.int32, n_flags), flag_peer_ptrs=list(fb.peer_ptrs),
+                    own_blocks=own, is_owner=own[1] > own[0], world=self.world, epoch_ptr=self.k1_words.data_ptr(),
+                    status_ptr=self.k1_words.data_ptr() + 4)
+
+    def k1_status(self) -> int:
+        """1 when a K1 tile never arrived (dead owner) since the last call; cleared."""
+        if self.data_plane != "native":
+            return 0
+        st = int(self.k1_words[1].item())
+        if st:
+            self.k1_words[1:2].zero_()
+        return st
 
     # ------------------------------------------------------------------ helpers
     @property
@@ -291,7 +336,9 @@ class FedAvgEngine:
                 0.0, self.timeout_cycles, self._cta_counter.data_ptr(),
                 1 if upload_mode == "delta_bf16" else 0,
                 self.sm_count if (self.is_reducer and self.hi > self.lo) else 1, stream_ptr(),
-                dynamic, float(my_weight), self.reducer_mask)
+                dynamic, float(my_weight), self.reducer_mask, self.shadow_skip[0], self.shadow_skip[1])
+            if self.shadow_skip[1] > self.shadow_skip[0]:
+                self.k1_words[0:1].fill_(self.epoch)          # stream-ordered after K2: the round K1's tile flags are compared with
         else:
             if prescaled:           # the collective arm applies the weights itself
                 weights_eff = [1.0 if w > 0 else 0.0 for w in weights]
@@ -359,6 +406,8 @@ class FedAvgEngine:
         from ..ops import native
 
         self.last_status = int(self.pad[native().PAD_STATUS].item())
+        if self.last_status == 0 and self.shadow_skip[1] > self.shadow_skip[0] and self.k1_status():
+            self.last_status = 3                     # a K1 weight tile never arrived (its owner died during the first local step)
         return self.last_status
 
     def missing_mask(self) -> int:

@@ -37,7 +37,7 @@ class FederatedTrainer:
                  max_grad_norm: Optional[float] = None, process_group=None, include_buffers: bool = True,
                  shadow_bf16: bool = False, fused_local_optimizer: bool = True, fault_tolerant: bool = False,
                  metrics=None, checkpoint_dir: Optional[str] = None, checkpoint_every: int = 0,
-                 timeout_ms: Optional[float] = None, side_wgrad: bool = True):
+                 timeout_ms: Optional[float] = None, side_wgrad: bool = True, bcast: str = "push"):
         self.rank, self.world = rank, world
         self.device = torch.device(device)
         self.side_wgrad = bool(side_wgrad) and self.device.type == "cuda"
@@ -46,15 +46,43 @@ class FederatedTrainer:
         self.amp_dtype = amp_dtype if self.device.type == "cuda" else None
         self.max_grad_norm = max_grad_norm
         n = flat_size(self.model, include_buffers)
+        # bcast="fused" (K1): the bf16 weights of the layers tagged ``first_consumer`` are not pushed by the aggregation
+        # kernel; they form a prefix of the flat buffers and reach the nodes inside the first forward GEMM that reads them
+        # (models/transformer.py::K1_STEP).  Needs the NVLink data plane with multicast, a bf16 shadow, a static set of
+        # reducers (not combined with fault_tolerant) and layers whose 256-row blocks line up with the reducer slices.
+        from ..models.transformer import ShadowLinear
+
+        self.bcast = bcast
+        k1_mods = []
+        if bcast == "fused" and world > 1 and shadow_bf16 and self.device.type == "cuda" and not fault_tolerant:
+            k1_mods = [m for m in self.model.modules() if isinstance(m, ShadowLinear) and m.first_consumer and m.weight.requires_grad
+                       and m.out_features % 256 == 0]
+            if len({m.in_features for m in k1_mods}) != 1:
+                k1_mods = []
+        extra = {}
+        if k1_mods:
+            for m in k1_mods:
+                m.weight._v6_first = True
+            n_first = sum((m.weight.numel() + 7) // 8 * 8 for m in k1_mods)
+            extra = dict(shard_align=256 * k1_mods[0].in_features, shadow_skip=(0, n_first), shadow_multicast=True)
         self.engine = FedAvgEngine(n, rank, world, self.device, data_plane=data_plane, server_mode=server_mode,
                                    server_opt=server_opt, upload=upload, multicast=multicast,
-                                   process_group=process_group, shadow_bf16=shadow_bf16,
+                                   process_group=process_group, shadow_bf16=shadow_bf16, **extra,
                                    **({"timeout_ms": timeout_ms} if timeout_ms is not None else {}))
         self.fm = FlatModel(self.model, storage=self.engine.w, shadow=self.engine.shadow,
                             include_buffers=include_buffers)
         from ..models.transformer import attach_shadow
 
         attach_shadow(self.model, self.fm)      # ShadowLinear / ShadowConv2d read the bf16 copy (no-op without a shadow)
+        self.k1_layers = 0
+        if k1_mods:
+            infos = [self.engine.k1_layer(m._offset, m.out_features, m.in_features) for m in k1_mods]
+            if all(i is not None for i in infos):
+                for m, i in zip(k1_mods, infos):
+                    m.k1 = i
+                self.k1_layers = len(infos)
+            else:       # layout does not allow it: K2 pushes everything, as without bcast="fused"
+                self.engine.shadow_skip = (0, 0)
         self.upload_mode = upload
         # delta modes: received global model (trainable prefix saved by the fused optimizer on the
         # first local step; the float-buffer tail, e.g. BatchNorm statistics, saved per round below)
@@ -101,8 +129,15 @@ class FederatedTrainer:
     def _step_body(self, x: torch.Tensor, y: torch.Tensor, variant: str) -> None:
         self.fm.zero_grad()
         ctx = torch.autocast("cuda", dtype=self.amp_dtype) if self.amp_dtype is not None else contextlib.nullcontext()
-        with ctx:
-            loss = self.forward_loss(self.model, x, y)
+        from ..models import transformer as tfm
+
+        tfm.K1_STEP["on"] = bool(self.k1_layers) and variant.endswith("+k1")
+        try:
+            with ctx:
+                loss = self.forward_loss(self.model, x, y)
+        finally:
+            tfm.K1_STEP["on"] = False
+        variant = variant.replace("+k1", "")
         if self.side_wgrad:
             conv_mod.side_wgrad(True)      # filter gradients on a second stream (models/conv.py::_SideWgrad)
         try:
@@ -144,11 +179,12 @@ class FederatedTrainer:
             self.opt.step(self.fm.grad, grad_scale=gs, shadow=shadow, device_step=bool(self.use_graph), **kw)
 
     def _variant(self, i: int, n: int) -> str:
+        k1 = "+k1" if (self.k1_layers and i == 0) else ""      # first step of the round: K1 delivers the tagged weights
         if self.upload_mode == "weights_f32":
-            return "mid"
+            return "mid" + k1
         if n == 1:
-            return "only"
-        return "first" if i == 0 else ("last" if i == n - 1 else "mid")
+            return "only" + k1
+        return ("first" if i == 0 else ("last" if i == n - 1 else "mid")) + k1
 
     def _capture(self, variant: str, x: torch.Tensor, y: torch.Tensor) -> torch.cuda.CUDAGraph:
         if self._static_x is None:
@@ -176,8 +212,16 @@ class FederatedTrainer:
             self._step_body(self._static_x, self._static_y, variant)
         self._graph_launches[variant] = LAUNCHES[0] - before      # our kernels inside one replay
         self.engine.w.copy_(snap[0])
+        if variant.endswith("+k1"):
+            # the warm-up runs multicast the owners' (locally advanced) shadow tiles into every rank: restore only after
+            # EVERY rank is through its capture, and let nobody start the round before everybody has restored
+            torch.cuda.synchronize(self.device)
+            self.engine.heap.host_barrier()
         if self.engine.shadow is not None:          # the warm-up / capture steps advanced the bf16 copy as well
             self.engine.shadow.copy_(self.engine.w.to(torch.bfloat16))
+        if variant.endswith("+k1"):
+            torch.cuda.synchronize(self.device)
+            self.engine.heap.host_barrier()
         if snap_opt is not None:
             self.opt.load_state_dict(snap_opt)
         if self.torch_opt is not None:
