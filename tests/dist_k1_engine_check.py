@@ -56,7 +56,7 @@ def main():
     assert trs["fused"].k1_layers > 0, "the K1 path did not engage"
     w0 = trs["push"].engine.w.clone()
     # same flat layout? no: the fused trainer orders the K1 weights first -- compare through the named views
-    batches = spec.make_batches(dev, spec.local_steps, spec.batch, 1000 + rank)
+    batches = [(x.to(dev), y.to(dev)) for x, y in spec.make_batches(spec.local_steps, spec.batch, 1000 + rank)]
     rows = []
     for r in range(a.rounds):
         losses = {m: float(trs[m].run_round(batches, float(spec.batch * spec.local_steps * (rank + 1))).item()) for m in ("fused", "push")}

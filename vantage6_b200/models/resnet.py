@@ -116,6 +116,11 @@ class ResNet(nn.Module):
             from ..ops import pool
 
             if pool.stem_s2d_supported(x, self.conv1):
+                from .conv import _fuse_stats
+
+                if (self.training and pool.stem_stats_fused(self.conv1) and hasattr(self.bn1, "stats_buffers") and _fuse_stats(self.layer1[0].conv3)):
+                    stats = self.bn1.stats_buffers(x.device)        # batch statistics out of the convolution's epilogue
+                    return self.bn1.apply_pre(pool.stem_s2d(x, self.conv1, _MEAN, _STD, bn=stats), stats)
                 return self.bn1(pool.stem_s2d(x, self.conv1, _MEAN, _STD))
             if x.is_contiguous() and (x.shape[2] * x.shape[3]) % 4 == 0:
                 return self.bn1(self.conv1(pool.image_normalize(x, _MEAN, _STD)))

@@ -126,19 +126,28 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, rs: Tuple[in
 
 
 # ------------------------------------------------------------------------------------------------- ResNet stem
-def stem_fprop(xs: torch.Tensor, ws: torch.Tensor) -> torch.Tensor:
+def stem_fprop(xs: torch.Tensor, ws: torch.Tensor, bn: Optional[dict] = None) -> torch.Tensor:
     """The 7x7 / stride-2 stem as a 4x4 / stride-1 convolution on the 16-channel space-to-depth image ``xs``
     [N, 16, Hs, Ws] (ops/pool.py) -- on the tensor cores: the 4 horizontally adjacent 16-channel pixels of a filter row are
     64 contiguous bf16 in NHWC memory, so the image is read through an im2col map whose "pixels" are those overlapping
-    64-element windows (pixel pitch 32 B): a 4x1 convolution with Cin = 64, K = 4 x 64 = 256."""
+    64-element windows (pixel pitch 32 B): a 4x1 convolution with Cin = 64, K = 4 x 64 = 256.  ``bn``: as in
+    :func:`conv_fprop` (the batch statistics of the output from the same launch)."""
     n, c16, hs, wsz = xs.shape
     cout = ws.shape[0]
     assert c16 == 16 and tuple(ws.shape[1:]) == (16, 4, 4) and _is_cl(xs) and _is_cl(ws)
     p, q = hs - 3, wsz - 3
     y = torch.empty((n, cout, p, q), device=xs.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+    g = bn or {}
+
+    def ptr(t):
+        return 0 if t is None else t.data_ptr()
+
     count(1)
-    native().conv_fprop(xs.data_ptr(), ws.data_ptr(), y.data_ptr(), 0, 0, n, hs, q, 64, cout, 4, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1e-5,
-                        0.1, True, stream_ptr(), 32, wsz * 32, hs * wsz * 32)
+    native().conv_fprop(xs.data_ptr(), ws.data_ptr(), y.data_ptr(), 0, 0, n, hs, q, 64, cout, 4, 1, 1, 0,
+                        ptr(g.get("gamma")), ptr(g.get("beta")), ptr(g.get("running_mean")), ptr(g.get("running_var")),
+                        ptr(g.get("num_batches_tracked")), ptr(g.get("mean")), ptr(g.get("rstd")), ptr(g.get("scale_bias")),
+                        igemm_scratch(xs.device).data_ptr() if bn else 0, float(g.get("eps", 1e-5)), float(g.get("momentum", 0.1)),
+                        True, stream_ptr(), 32, wsz * 32, hs * wsz * 32)
     return y
 
 

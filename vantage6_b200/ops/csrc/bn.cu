@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(THREADS, 3) bn_bwd_reduce_kernel(const __nv_bf
     const int SW = C < 64 ? C : 64, CGS = SW >> 3, RL = THREADS / CGS;
     const int cg = threadIdx.x % CGS, rl = threadIdx.x / CGS;
     const size_t c0 = (size_t)blockIdx.y * SW + cg * 8;
+    pdl_wait();                                                 // dy comes from the kernel before (programmatic dependent launch)
     const long long CGT = C >> 3, cgt = (long long)blockIdx.y * CGS + cg;       // mask: [R][C/8] bytes
     float mu[8], rs[8], sg[8], sgx[8];
     loadf8(mean + c0, mu);
@@ -319,6 +320,22 @@ static void launch_dependent(void (*kernel)(KArgs...), int grid, size_t smem, bo
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// same, 2-D grid, no dynamic shared memory (the reduce kernels)
+template <typename... KArgs, typename... Args>
+static void launch_dependent_grid(void (*kernel)(KArgs...), dim3 grid, cudaStream_t s, Args... args) {
+    static const bool pdl = [] { const char* e = getenv("V6B200_PDL"); return !(e && e[0] == '0'); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(THREADS);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // tuning variant of the element-wise passes (V6B200_BN_CFG; scripts/bn_bench.py sweeps it, profiles/bn_bench_r2f.jsonl):
 //   0  U = 4 rows in flight, coefficients in shared memory, 4 CTAs/SM      2.93 ms of BN passes per ResNet-50 step
 //   1  U = 2, coefficients in registers, 3 CTAs/SM                          2.52 ms   (default; 5.5-6.0 TB/s on the
@@ -402,13 +419,14 @@ extern "C" int v6_bn_apply(const void* x, const void* res, const float* scale, c
     const __nv_bfloat16* rr = (const __nv_bfloat16*)res;
     __nv_bfloat16* yy = (__nv_bfloat16*)y;
     unsigned char* mk = (unsigned char*)relu_mask;      // training with statistics from the convolution epilogue: 1 bit / element
-    // (the statistics come from a kernel that is not written for programmatic dependent launch: plain stream order)
+    // (x and the statistics come from the convolution kernel before it, which releases its dependents at its start: this
+    // kernel's CTAs are resident and past their prologue when that grid drains, and wait for it in griddepcontrol.wait)
     if (relu) {
-        if (res) launch_apply<true, true>(false, s, xx, rr, scale, bias, yy, mk, R, C);
-        else launch_apply<true, false>(false, s, xx, rr, scale, bias, yy, mk, R, C);
+        if (res) launch_apply<true, true>(true, s, xx, rr, scale, bias, yy, mk, R, C);
+        else launch_apply<true, false>(true, s, xx, rr, scale, bias, yy, mk, R, C);
     } else {
-        if (res) launch_apply<false, true>(false, s, xx, rr, scale, bias, yy, nullptr, R, C);
-        else launch_apply<false, false>(false, s, xx, rr, scale, bias, yy, nullptr, R, C);
+        if (res) launch_apply<false, true>(true, s, xx, rr, scale, bias, yy, nullptr, R, C);
+        else launch_apply<false, false>(true, s, xx, rr, scale, bias, yy, nullptr, R, C);
     }
     V6_CHECK_LAUNCH();
     return 0;
@@ -426,8 +444,8 @@ extern "C" int v6_bn_bwd(const void* dy, const void* relu_mask, const void* x, c
     if (relu && !relu_mask) return (int)cudaErrorInvalidValue;
     static int wave_relu = 0, wave_lin = 0;
     const dim3 rg = reduce_grid(R, C, relu ? wave_ctas(bn_bwd_reduce_kernel<true>, wave_relu) : wave_ctas(bn_bwd_reduce_kernel<false>, wave_lin));
-    if (relu) bn_bwd_reduce_kernel<true><<<rg, THREADS, 0, s>>>(dyy, yy, xx, gamma, mean, rstd, make_red(scratch), dgamma, dbeta, coef, R, C, accumulate);
-    else bn_bwd_reduce_kernel<false><<<rg, THREADS, 0, s>>>(dyy, yy, xx, gamma, mean, rstd, make_red(scratch), dgamma, dbeta, coef, R, C, accumulate);
+    if (relu) launch_dependent_grid(bn_bwd_reduce_kernel<true>, rg, s, dyy, yy, xx, gamma, mean, rstd, make_red(scratch), dgamma, dbeta, coef, R, C, accumulate);
+    else launch_dependent_grid(bn_bwd_reduce_kernel<false>, rg, s, dyy, yy, xx, gamma, mean, rstd, make_red(scratch), dgamma, dbeta, coef, R, C, accumulate);
     __nv_bfloat16* dxx = (__nv_bfloat16*)dx;
     __nv_bfloat16* drr = (__nv_bfloat16*)dres;
     if (relu) {

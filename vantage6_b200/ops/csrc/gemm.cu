@@ -126,6 +126,51 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
         m_blk = in_g / gsz;
     };
 
+    // K1 v3 push (owner side), run by the K1 warp of every CTA AND -- before their first accumulator exists -- by the four
+    // epilogue warps: 5 pusher warps per CTA keep ~6 MB of multicast stores in flight (one warp per CTA: 1.2 MB, a third of
+    // what the link takes -- profiles/comm_2gpu_r2c.json).
+    auto k1_push = [&](int pusher, int n_pushers) {
+        const uint32_t epoch = P.epoch_ptr ? ld_acquire_sys_u32(P.epoch_ptr) : P.epoch;
+        // push unit = one 256-row weight block x `kg` consecutive k-blocks: a row of the unit is kg x 128 contiguous
+        // bytes (8 * kg lanes x 16 B, fully coalesced), 16 row-chunks in flight per lane, ONE fence + kg flags per
+        // unit.  (One 32 KB tile per fence with 4 rows per instruction reached 170 GB/s from inside the GEMM --
+        // profiles/comm_2gpu_r2b.json -- a third of what the link takes.)  Order: k-major, like the consumers.
+        const int kg = P.push_kgroup, num_kg = (num_k + kg - 1) / kg;
+        const int lpr = 8 * kg, rpi = 32 / lpr;                          // lanes per row, rows per instruction
+        const int rsub = lane / lpr, ch = lane % lpr;
+        const int n_units = num_kg * num_n;
+        for (int idx = pusher; idx < n_units; idx += n_pushers) {
+            const int kgi = idx / num_n, nb = idx % num_n;
+            if (nb < P.own_nb_lo || nb >= P.own_nb_hi) continue;          // another rank's shard
+            const int rows = min(BLOCK_N, P.N - nb * BLOCK_N);
+            const int col = kgi * kg * BLOCK_K + ch * 8;
+            const size_t base = (size_t)(nb * BLOCK_N) * P.ldb + (size_t)col;
+            const bool col_ok = col < P.K;
+            constexpr int PU = 16;
+#pragma unroll 1
+            for (int r0 = 0; r0 < rows; r0 += PU * rpi) {
+                uint4 v[PU];
+#pragma unroll
+                for (int u = 0; u < PU; ++u) {
+                    const int r = r0 + u * rpi + rsub;
+                    if (r < rows && col_ok) v[u] = *reinterpret_cast<const uint4*>(P.b_src + base + (size_t)r * P.ldb);
+                }
+#pragma unroll
+                for (int u = 0; u < PU; ++u) {
+                    const int r = r0 + u * rpi + rsub;
+                    if (r < rows && col_ok) multimem_st_u4(reinterpret_cast<uint4*>(P.b_mc + base + (size_t)r * P.ldb), v[u]);
+                }
+            }
+            fence_acq_rel_sys();                       // every lane's multicast stores before the flags
+            __syncwarp();
+            for (int j = lane; j < P.world * kg; j += 32) {
+                const int peer = j / kg, kb = kgi * kg + j % kg;
+                if (kb < num_k) st_release_sys_u32(reinterpret_cast<uint32_t*>(P.flag_peers.p[peer]) + nb * num_k + kb, epoch);
+            }
+            __syncwarp();
+        }
+    };
+
     if (warp == 4) {
         // ============================ TMA producer ============================
         if (lane == 0) {
@@ -196,48 +241,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
         // and never wait on anything but their own staging slots, so the GEMM tiles can start as
         // soon as their first weight tiles are local: transfer and MMA overlap tile by tile.
         if (P.fused_bcast == 2) {
-            // ---- push: owner only.  Tile order k-major like the consumers' first k-blocks; one tile = 256 rows x 128 B.
-            if (P.is_owner) {
-                const uint32_t epoch = P.epoch_ptr ? ld_acquire_sys_u32(P.epoch_ptr) : P.epoch;
-                // push unit = one 256-row weight block x `kg` consecutive k-blocks: a row of the unit is kg x 128 contiguous
-                // bytes (8 * kg lanes x 16 B, fully coalesced), 16 row-chunks in flight per lane, ONE fence + kg flags per
-                // unit.  (One 32 KB tile per fence with 4 rows per instruction reached 170 GB/s from inside the GEMM --
-                // profiles/comm_2gpu_r2b.json -- a third of what the link takes.)  Order: k-major, like the consumers.
-                const int kg = P.push_kgroup, num_kg = (num_k + kg - 1) / kg;
-                const int lpr = 8 * kg, rpi = 32 / lpr;                          // lanes per row, rows per instruction
-                const int rsub = lane / lpr, ch = lane % lpr;
-                const int n_units = num_kg * num_n;
-                for (int idx = blockIdx.x; idx < n_units; idx += gridDim.x) {
-                    const int kgi = idx / num_n, nb = idx % num_n;
-                    if (nb < P.own_nb_lo || nb >= P.own_nb_hi) continue;          // another rank's shard
-                    const int rows = min(BLOCK_N, P.N - nb * BLOCK_N);
-                    const int col = kgi * kg * BLOCK_K + ch * 8;
-                    const size_t base = (size_t)(nb * BLOCK_N) * P.ldb + (size_t)col;
-                    const bool col_ok = col < P.K;
-                    constexpr int PU = 16;
-#pragma unroll 1
-                    for (int r0 = 0; r0 < rows; r0 += PU * rpi) {
-                        uint4 v[PU];
-#pragma unroll
-                        for (int u = 0; u < PU; ++u) {
-                            const int r = r0 + u * rpi + rsub;
-                            if (r < rows && col_ok) v[u] = *reinterpret_cast<const uint4*>(P.b_src + base + (size_t)r * P.ldb);
-                        }
-#pragma unroll
-                        for (int u = 0; u < PU; ++u) {
-                            const int r = r0 + u * rpi + rsub;
-                            if (r < rows && col_ok) multimem_st_u4(reinterpret_cast<uint4*>(P.b_mc + base + (size_t)r * P.ldb), v[u]);
-                        }
-                    }
-                    fence_acq_rel_sys();                       // every lane's multicast stores before the flags
-                    __syncwarp();
-                    for (int j = lane; j < P.world * kg; j += 32) {
-                        const int peer = j / kg, kb = kgi * kg + j % kg;
-                        if (kb < num_k) st_release_sys_u32(reinterpret_cast<uint32_t*>(P.flag_peers.p[peer]) + nb * num_k + kb, epoch);
-                    }
-                    __syncwarp();
-                }
-            }
+            if (P.is_owner) k1_push(blockIdx.x * 5 + 4, gridDim.x * 5);
         } else if (P.fused_bcast && lane == 0) {
             const int n_pull = num_k * num_n;
             uint8_t* stg = smem + PULL_OFF;
@@ -272,6 +276,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
             (void)issued;
         }
     } else if (warp < 4) {       // epilogue warps 0-3: the scheduler prefers the highest warp id, so the pacing single-thread roles sit in warps 4-7
+        if (P.fused_bcast == 2 && P.is_owner) k1_push(blockIdx.x * 5 + warp, gridDim.x * 5);     // idle until the first tile: help push
         // ============================ epilogue ================================
         const int ew = warp;                      // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
         int acc = 0; uint32_t acc_phase = 0;
@@ -402,7 +407,7 @@ extern "C" int v6_bcast_push_gemm_bf16(const void* A, void* B_local, void* B_mc,
     {   // widest push unit that still gives every CTA's pusher warp two units of the blocks this rank owns
         const int nn = P.own_nb_hi - P.own_nb_lo, nk = (K + BLOCK_K - 1) / BLOCK_K;
         P.push_kgroup = 1;
-        for (int kg : {4, 2}) if ((long long)nn * ((nk + kg - 1) / kg) >= 2 * 148) { P.push_kgroup = kg; break; }
+        for (int kg : {4, 2}) if ((long long)nn * ((nk + kg - 1) / kg) >= 148 * 5 / (kg == 2 ? 2 : 1)) { P.push_kgroup = kg; break; }
     }
     P.world = world; P.ldb = ldb; P.b_src = (const __nv_bfloat16*)B_local; P.b_mc = (__nv_bfloat16*)B_mc;
     P.flag_peers = *flag_peers;

@@ -4,7 +4,7 @@ uint8-NCHW -> normalised-bf16-NHWC image transform.  Anywhere the kernels do not
 dtypes / layouts / pooling shapes) the stock PyTorch ops run."""
 from __future__ import annotations
 
-from typing import Sequence
+from typing import Optional, Sequence
 
 import torch
 from torch import nn
@@ -81,7 +81,7 @@ class _StemS2DFn(torch.autograd.Function):
     filter values are read from (the bf16 shadow view when attached)."""
 
     @staticmethod
-    def forward(ctx, xs, weight, w_src):
+    def forward(ctx, xs, weight, w_src, bn=None):
         O = weight.shape[0]
         ws = torch.empty((O, 16, 4, 4), device=xs.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
         src = weight.detach() if w_src is None else w_src
@@ -91,7 +91,7 @@ class _StemS2DFn(torch.autograd.Function):
         if ctx.tc:      # tcgen05 implicit GEMM through an overlapping-window im2col map (ops/conv.py::stem_fprop)
             from . import conv as C
 
-            y = C.stem_fprop(xs, ws)
+            y = C.stem_fprop(xs, ws, bn=bn)       # bn: BatchNorm statistics of the output from the same launch
         else:
             y = torch.ops.aten.convolution(xs, ws, None, (1, 1), (0, 0), (1, 1), False, (0, 0), 1)
         ctx.save_for_backward(xs, ws)
@@ -114,14 +114,14 @@ class _StemS2DFn(torch.autograd.Function):
             C.stem_wgrad(dy, xs, dws32)
             count(1)
             native().stem_wgrad_d2s_f32(dws32.data_ptr(), dw.data_ptr(), w.shape[0], direct, stream_ptr())
-            return (None, None, None) if direct else (None, dw, None)
+            return (None, None, None, None) if direct else (None, dw, None, None)
         _, dws, _ = torch.ops.aten.convolution_backward(dy, xs, ws, None, (1, 1), (0, 0), (1, 1), False, (0, 0), 1,
                                                         (False, True, False))
         if not dws.is_contiguous(memory_format=torch.channels_last):
             dws = dws.contiguous(memory_format=torch.channels_last)
         count(1)
         native().stem_wgrad_d2s(dws.data_ptr(), dw.data_ptr(), w.shape[0], direct, stream_ptr())     # direct: straight into the flat grads
-        return (None, None, None) if direct else (None, dw, None)
+        return (None, None, None, None) if direct else (None, dw, None, None)
 
 
 def stem_s2d_supported(img: torch.Tensor, conv: nn.Conv2d) -> bool:
@@ -132,11 +132,18 @@ def stem_s2d_supported(img: torch.Tensor, conv: nn.Conv2d) -> bool:
             and conv.weight.is_contiguous(memory_format=torch.channels_last))
 
 
-def stem_s2d(img: torch.Tensor, conv: nn.Conv2d, mean: Sequence[float], std: Sequence[float]) -> torch.Tensor:
-    """uint8 NCHW images -> stem convolution output (bf16, channels-last), see :class:`_StemS2DFn`."""
+def stem_s2d(img: torch.Tensor, conv: nn.Conv2d, mean: Sequence[float], std: Sequence[float], bn: Optional[dict] = None) -> torch.Tensor:
+    """uint8 NCHW images -> stem convolution output (bf16, channels-last), see :class:`_StemS2DFn`.  ``bn``: statistics
+    buffers of the BatchNorm that follows (ops/bn.py ``stats_buffers``), filled by the convolution's epilogue on the
+    tensor-core path (check :func:`stem_stats_fused`)."""
     N, _, H, W = img.shape
     xs = torch.empty((N, 16, H // 2 + 3, W // 2 + 3), device=img.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
     count(1)
     native().image_normalize_s2d(img.data_ptr(), xs.data_ptr(), N, H, W, float(mean[0]), float(mean[1]), float(mean[2]),
                                  1.0 / float(std[0]), 1.0 / float(std[1]), 1.0 / float(std[2]), stream_ptr())
-    return _StemS2DFn.apply(xs, conv.weight, getattr(conv, "w_bf16", None))
+    return _StemS2DFn.apply(xs, conv.weight, getattr(conv, "w_bf16", None), bn if stem_stats_fused(conv) else None)
+
+
+def stem_stats_fused(conv: nn.Conv2d) -> bool:
+    """The stem runs on the tcgen05 kernel (which can produce the BatchNorm statistics in its epilogue)."""
+    return _stem_tc() and conv.weight.shape[0] % 64 == 0
