@@ -67,8 +67,12 @@ def main():
             d = (vf[k].float() - vp[k].float()).abs().max().item()
             worst = max(worst, d / (vp[k].float().abs().max().item() + 1e-6))
         sf, sp = trs["fused"].fm.shadow_views(), trs["push"].fm.shadow_views()
-        shadow_worst = max(((sf[k].float() - sp[k].float()).abs().max().item() for k in sp), default=0.0)
-        rows.append({"round": r, "loss_fused": losses["fused"], "loss_push": losses["push"], "worst_rel_diff": worst, "shadow_abs_diff": shadow_worst,
+        shadow_worst, shadow_key = 0.0, ""
+        for k in sp:
+            d = (sf[k].float() - sp[k].float()).abs().max().item()
+            if d > shadow_worst:
+                shadow_worst, shadow_key = d, k
+        rows.append({"round": r, "loss_fused": losses["fused"], "loss_push": losses["push"], "worst_rel_diff": worst, "shadow_abs_diff": shadow_worst, "shadow_key": shadow_key,
                      "status": trs["fused"].engine.poll_status()})
         assert trs["fused"].engine.poll_status() == 0
         assert abs(losses["fused"] - losses["push"]) < 2e-2 * max(1.0, abs(losses["push"])), rows[-1]

@@ -134,13 +134,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
         // push unit = one 256-row weight block x `kg` consecutive k-blocks: a row of the unit is kg x 128 contiguous
         // bytes (8 * kg lanes x 16 B, fully coalesced), 16 row-chunks in flight per lane, ONE fence + kg flags per
         // unit.  (One 32 KB tile per fence with 4 rows per instruction reached 170 GB/s from inside the GEMM --
-        // profiles/comm_2gpu_r2b.json -- a third of what the link takes.)  Order: k-major, like the consumers.
+        // profiles/comm_2gpu_r2b.json -- a third of what the link takes.)
         const int kg = P.push_kgroup, num_kg = (num_k + kg - 1) / kg;
         const int lpr = 8 * kg, rpi = 32 / lpr;                          // lanes per row, rows per instruction
         const int rsub = lane / lpr, ch = lane % lpr;
         const int n_units = num_kg * num_n;
         for (int idx = pusher; idx < n_units; idx += n_pushers) {
-            const int kgi = idx / num_n, nb = idx % num_n;
+            // n-slowest, like the consumers' tile order (m fastest, then n): the column blocks the first wave of output tiles
+            // needs are complete after 1/num_n of the transfer, and the GEMM follows the push block by block (k-major order
+            // let no tile finish before the LAST k-block of everything had arrived: push and GEMM ran back to back)
+            const int nb = idx / num_kg, kgi = idx % num_kg;
             if (nb < P.own_nb_lo || nb >= P.own_nb_hi) continue;          // another rank's shard
             const int rows = min(BLOCK_N, P.N - nb * BLOCK_N);
             const int col = kgi * kg * BLOCK_K + ch * 8;
