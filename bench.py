@@ -39,7 +39,7 @@ sys.path.insert(0, ROOT)
 MODELS = ["resnet50", "resnet_tiny", "resnet_mini", "bert_base", "bert_tiny", "llama3_8b_lora", "llama_tiny_lora", "glm"]
 
 
-def parse():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8, help="timed federated rounds")
@@ -57,7 +57,7 @@ def parse():
                     help="fused: K1 -- the first-consumer weights arrive inside the first forward GEMM of the round (transformers, >= 2 GPUs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    return ap.parse_args()
+    return ap.parse_args(argv)
 
 
 def reference_unavailable():
