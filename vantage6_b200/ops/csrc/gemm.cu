@@ -176,34 +176,67 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
 
     if (warp == 4) {
         // ============================ TMA producer ============================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            const uint32_t epoch = (P.fused_bcast && P.epoch_ptr) ? ld_acquire_sys_u32(P.epoch_ptr) : P.epoch;
+        int stage = 0; uint32_t phase = 0;                       // (advanced by lane 0 only)
+        auto issue = [&](int kb, int m_blk, int n_blk) {            // lane 0: one k-block of operands into the ring
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * STAGE_BYTES;
+            uint8_t* sb = sa + A_BYTES;
+            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+            if (++stage == P.stages) { stage = 0; phase ^= 1; }
+        };
+        if (!P.fused_bcast) {
+            if (lane == 0) {
+                for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                    int m_blk, n_blk;
+                    tile_coords(t, m_blk, n_blk);
+                    for (int kb = 0; kb < num_k; ++kb) issue(kb, m_blk, n_blk);
+                }
+            }
+        } else {
+            // K1: a weight tile may only be loaded once its ready flag carries this round's epoch.  The WHOLE warp polls: 32
+            // flags per L2 round trip (a system-scope load costs ~1 us; one dependent load per k-block in front of every TMA
+            // issue made the producer 3x slower than the MMA -- push and GEMM ran back to back, profiles/comm_8gpu_r2.json),
+            // lane 0 issues the k-blocks of the ready prefix; column blocks this CTA has seen complete are not polled again.
+            const uint32_t epoch = P.epoch_ptr ? ld_acquire_sys_u32(P.epoch_ptr) : P.epoch;
+            unsigned long long done_n = 0ull;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 int m_blk, n_blk;
                 tile_coords(t, m_blk, n_blk);
-                for (int kb = 0; kb < num_k; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * STAGE_BYTES;
-                    uint8_t* sb = sa + A_BYTES;
-                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-                    tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-                    if (P.fused_bcast) {
-                        // K1: wait until some CTA's pull warp has landed this weight tile in the local copy
-                        const uint32_t* f = P.ready_flags + n_blk * num_k + kb;
-                        const long long t0 = clock64();
-                        while ((int32_t)(ld_acquire_sys_u32(f) - epoch) < 0) {
-                            __nanosleep(32);
+                if (n_blk < 64 && ((done_n >> n_blk) & 1ull)) {
+                    if (lane == 0) for (int kb = 0; kb < num_k; ++kb) issue(kb, m_blk, n_blk);
+                    __syncwarp();
+                    continue;
+                }
+                for (int kb0 = 0; kb0 < num_k; kb0 += 32) {
+                    const int nb = min(32, num_k - kb0);
+                    const uint32_t* f = P.ready_flags + n_blk * num_k + kb0;
+                    int issued = 0;
+                    const long long t0 = clock64();
+                    while (issued < nb) {
+                        const uint32_t v = lane < nb ? ld_relaxed_sys_u32(f + lane) : epoch;
+                        const unsigned m = __ballot_sync(0xffffffffu, (int32_t)(v - epoch) >= 0);
+                        int cnt = m == 0xffffffffu ? 32 : __ffs(~m) - 1;          // length of the ready prefix
+                        cnt = min(cnt, nb);
+                        if (cnt == issued) {
+                            __nanosleep(64);
                             if (clock64() - t0 > 4000000000LL) {
-                                if (P.status_ptr) { *P.status_ptr = 1u; break; }      // dead owner: reported, the round is redone
-                                asm volatile("trap;");
+                                if (!P.status_ptr) asm volatile("trap;");
+                                if (lane == 0) *P.status_ptr = 1u;                  // dead owner: reported, the round is redone
+                                cnt = nb;
+                            } else {
+                                continue;
                             }
                         }
+                        fence_acq_rel_sys();                                       // the tiles behind the flags just observed
                         asm volatile("fence.proxy.async.global;" ::: "memory");
+                        if (lane == 0) for (int k = issued; k < cnt; ++k) issue(kb0 + k, m_blk, n_blk);
+                        issued = cnt;
+                        __syncwarp();
                     }
-                    tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
-                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
                 }
+                if (n_blk < 64) done_n |= 1ull << n_blk;
             }
         }
     } else if (warp == 5) {
