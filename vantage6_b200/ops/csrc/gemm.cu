@@ -215,7 +215,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
                     int issued = 0;
                     const long long t0 = clock64();
                     while (issued < nb) {
-                        const uint32_t v = lane < nb ? ld_relaxed_sys_u32(f + lane) : epoch;
+                        const uint32_t v = lane < nb ? ld_acquire_sys_u32(f + lane) : epoch;    // acquire: the tile behind a set flag is visible; the warp vote below carries that to lane 0
                         const unsigned m = __ballot_sync(0xffffffffu, (int32_t)(v - epoch) >= 0);
                         int cnt = m == 0xffffffffu ? 32 : __ffs(~m) - 1;          // length of the ready prefix
                         cnt = min(cnt, nb);
@@ -229,8 +229,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
                                 continue;
                             }
                         }
-                        fence_acq_rel_sys();                                       // the tiles behind the flags just observed
-                        asm volatile("fence.proxy.async.global;" ::: "memory");
+                        asm volatile("fence.proxy.async.global;" ::: "memory");          // generic-proxy stores -> the TMA (async proxy) reads
                         if (lane == 0) for (int k = issued; k < cnt; ++k) issue(kb0 + k, m_blk, n_blk);
                         issued = cnt;
                         __syncwarp();

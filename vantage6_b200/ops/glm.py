@@ -15,7 +15,7 @@ from typing import Optional
 
 import torch
 
-from . import native, stream_ptr
+from . import count, native, stream_ptr
 
 _MAX_PARTS = 148 * 4
 
@@ -33,6 +33,7 @@ def logistic_grad(X: torch.Tensor, y: torch.Tensor, w: torch.Tensor, out: Option
     if X.is_cuda:
         if scratch is None:
             scratch = torch.empty(_MAX_PARTS * (F + 2), device=X.device, dtype=torch.float32)
+        count(2)                     # gradient kernel + fold of the per-CTA partials
         if _tensor_core_path(X):     # UMMA formulation (csrc/glm_tc.cu): 99.6 us vs 124.2 us on 1M x 256 bf16
             native().glm_logistic_grad_tc(X.data_ptr(), y.data_ptr(), w.data_ptr(), scratch.data_ptr(), _MAX_PARTS,
                                           out.data_ptr(), rows, F, stream_ptr())

@@ -493,9 +493,10 @@ class SmallAggregator:
         self.epoch += 1
         par = self.epoch & 1
         if self.native:
-            from ..ops import stream_ptr
+            from ..ops import count, stream_ptr
 
             off = par * self.n * 4
+            count(1)
             self._C.small_allreduce(self._slots.peer(off), self._pad_buf.peer(), w, self.out.data_ptr(), self.n,
                                     self.rank, self.world, self.epoch, 1.0 / total, self.timeout_cycles, stream_ptr())
         else:
