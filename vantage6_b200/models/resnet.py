@@ -65,11 +65,13 @@ class Bottleneck(nn.Module):
         # conv1's data-gradient kernel instead of being added by a separate pass (GradFork; only armed on the tcgen05 path)
         fork = GradFork() if (self.training and torch.is_grad_enabled() and x.requires_grad) else None
         out = conv_bn(self.conv1, self.bn1, x, fork_in=fork)       # conv (+ BN statistics in its epilogue) -> BN apply + ReLU
-        out = conv_bn(self.conv2, self.bn2, out)
+        # absorb: conv2 / conv3 are the only consumers of bn1 / bn2's outputs -> their data-gradient kernels also do the
+        # reduction pass of those BatchNorms' backward (conv1 does it for the previous block's bn3 through the fork)
+        out = conv_bn(self.conv2, self.bn2, out, absorb=True)
         if self.downsample is None:
-            return conv_bn(self.conv3, self.bn3, out, residual=x, res_fork=fork)     # BN + residual add + ReLU in one pass
+            return conv_bn(self.conv3, self.bn3, out, residual=x, res_fork=fork, absorb=True)     # BN + residual add + ReLU in one pass
         idt = conv_bn(self.downsample[0], self.downsample[1], x, fork_out=fork)
-        return conv_bn(self.conv3, self.bn3, out, residual=idt)
+        return conv_bn(self.conv3, self.bn3, out, residual=idt, absorb=True)
 
 
 class ResNet(nn.Module):

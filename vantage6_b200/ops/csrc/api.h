@@ -150,6 +150,8 @@ int v6_bn_fwd(const void* x, const void* res, const float* gamma, const float* b
               float* scratch, long long R, int C, float eps, float momentum, int relu, cudaStream_t s);
 int v6_bn_apply(const void* x, const void* res, const float* scale, const float* bias, void* y, void* relu_mask, long long R, int C,
                 int relu, cudaStream_t s);
+int v6_bn_bwd_apply(const void* dy, const void* relu_mask, const void* x, const float* coef, void* dx, void* dres, long long R, int C,
+                    int relu, cudaStream_t s);
 int v6_bn_bwd(const void* dy, const void* relu_mask, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
               void* dres, float* dgamma, float* dbeta, float* coef, float* scratch, long long R, int C, int relu,
               int accumulate, cudaStream_t s);
@@ -192,7 +194,9 @@ int v6_conv_fprop(const void* x, const void* w, void* y, const float* bias, int 
                   float eps, float momentum, int force_im2col, long long pitch_w, long long pitch_h, long long pitch_n,
                   cudaStream_t stream);
 int v6_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad,
-                  int force_im2col, const void* add_src, const void* add_mask, cudaStream_t stream);
+                  int force_im2col, const void* add_src, const void* add_mask, const void* red_x, const void* red_mask,
+                  const float* red_mean, const float* red_rstd, const float* red_gamma, float* red_dgamma, float* red_dbeta, float* red_coef,
+                  int red_accumulate, float* scratch, cudaStream_t stream);
 int v6_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad,
                   float scale, int splits, int force_im2col, long long pitch_w, long long pitch_h, long long pitch_n,
                   cudaStream_t stream);

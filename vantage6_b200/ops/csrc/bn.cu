@@ -458,3 +458,25 @@ extern "C" int v6_bn_bwd(const void* dy, const void* relu_mask, const void* x, c
     V6_CHECK_LAUNCH();
     return 0;
 }
+
+// element-wise half of the backward alone: the reduction (dgamma, dbeta, coef) was done in the epilogue of the data-gradient
+// kernel that produced dy (igemm.cu EPI_RED).  coef: [3C] = c0 | c1 | c2.
+extern "C" int v6_bn_bwd_apply(const void* dy, const void* relu_mask, const void* x, const float* coef, void* dx, void* dres, long long R,
+                               int C, int relu, cudaStream_t s) {
+    using namespace bn;
+    if (!shape_ok(C) || (relu && !relu_mask)) return (int)cudaErrorInvalidValue;
+    const __nv_bfloat16* dyy = (const __nv_bfloat16*)dy;
+    const unsigned char* yy = (const unsigned char*)relu_mask;
+    const __nv_bfloat16* xx = (const __nv_bfloat16*)x;
+    __nv_bfloat16* dxx = (__nv_bfloat16*)dx;
+    __nv_bfloat16* drr = (__nv_bfloat16*)dres;
+    if (relu) {
+        if (dres) launch_bwd_apply<true, true>(s, dyy, yy, xx, coef, dxx, drr, R, C);
+        else launch_bwd_apply<true, false>(s, dyy, yy, xx, coef, dxx, drr, R, C);
+    } else {
+        if (dres) launch_bwd_apply<false, true>(s, dyy, yy, xx, coef, dxx, drr, R, C);
+        else launch_bwd_apply<false, false>(s, dyy, yy, xx, coef, dxx, drr, R, C);
+    }
+    V6_CHECK_LAUNCH();
+    return 0;
+}
