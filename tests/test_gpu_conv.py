@@ -215,6 +215,11 @@ def test_side_stream_filter_gradients_match_inline(dev, monkeypatch):
     torch.testing.assert_close(fm.grad, g_inline, rtol=1e-3, atol=1e-5 * float(g_inline.abs().max()) + 1e-7)
 
 
+_RED_OPT_IN = pytest.mark.skipif(os.environ.get("V6B200_TEST_BN_RED") != "1",
+                                 reason="EPI_RED (BatchNorm backward reduction in the dgrad epilogue) is an opt-in path: V6B200_TEST_BN_RED=1")
+
+
+@_RED_OPT_IN
 def test_bn_backward_reduction_in_dgrad_epilogue_matches_separate_pass(dev, monkeypatch):
     """EPI_RED (csrc/igemm.cu): the data-gradient kernel of the consuming convolution also produces the BatchNorm backward's
     per-channel sums / coefficients / dgamma / dbeta; against the same model with the reduction as its own pass."""
@@ -263,3 +268,34 @@ def test_bn_backward_reduction_in_dgrad_epilogue_matches_separate_pass(dev, monk
     assert torch.nn.functional.cosine_similarity(dx1.flatten(), dx0.flatten(), dim=0) > 0.9999
     torch.testing.assert_close(dx1, dx0, rtol=2e-2, atol=2e-2 * float(dx0.abs().max()))
     assert torch.nn.functional.cosine_similarity(g1, g0, dim=0) > 0.9999
+
+
+@_RED_OPT_IN
+@pytest.mark.parametrize("n,cin,cout,hw,r", [(4, 64, 64, 16, 1), (2, 128, 64, 16, 3), (4, 256, 64, 8, 1)])
+def test_dgrad_epilogue_bn_reduction_unit(dev, n, cin, cout, hw, r):
+    """EPI_RED in isolation: dx unchanged, dgamma / dbeta / coefficients equal to the formulas of the separate reduction pass."""
+    from vantage6_b200.ops import conv as C
+
+    pad = 1 if r == 3 else 0
+    dy = _t((n, cout, hw, hw), 1)
+    w = (_t((cout, cin, r, r), 2) * (1.0 / (cout * r * r) ** 0.5)).contiguous(memory_format=torch.channels_last)
+    xbn = _t((n, cin, hw, hw), 3)
+    R = n * hw * hw
+    mask_bits = torch.rand(R, cin, device=dev) > 0.4
+    mask = (mask_bits.view(R, cin // 8, 8).to(torch.uint8) << torch.arange(8, device=dev, dtype=torch.uint8)).sum(-1).to(torch.uint8)
+    mean, rstd, gamma = torch.randn(cin, device=dev) * 0.1, torch.rand(cin, device=dev) + 0.5, torch.rand(cin, device=dev) + 0.5
+    dgamma, dbeta, coef = torch.zeros(cin, device=dev), torch.zeros(cin, device=dev), torch.zeros(3 * cin, device=dev)
+    ref_dx = C.conv_dgrad(dy, w, (hw, hw), pad)
+    dx = C.conv_dgrad(dy, w, (hw, hw), pad, bn_red=dict(x=xbn, mask=mask, mean=mean, rstd=rstd, gamma=gamma, dgamma=dgamma, dbeta=dbeta,
+                                                         coef=coef, accumulate=False))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dx.float(), ref_dx.float(), rtol=0, atol=0)
+    g = dx.float().permute(0, 2, 3, 1).reshape(R, cin) * mask_bits
+    xh = (xbn.float().permute(0, 2, 3, 1).reshape(R, cin) - mean) * rstd
+    tg, tgx = g.sum(0), (g * xh).sum(0)
+    torch.testing.assert_close(dbeta, tg, rtol=2e-3, atol=2e-3 * float(tg.abs().max()))
+    torch.testing.assert_close(dgamma, tgx, rtol=2e-3, atol=2e-3 * float(tgx.abs().max()))
+    k0 = gamma * rstd
+    k1 = -k0 * rstd * tgx / R
+    k2 = -k0 * tg / R - k1 * mean
+    torch.testing.assert_close(coef, torch.cat([k0, k1, k2]), rtol=2e-3, atol=2e-3 * float(k0.abs().max()))
