@@ -125,3 +125,20 @@ def test_llama_tiny_fused_arm_matches_stock_arm(dev):
     a, b = run(True), run(False)
     assert abs(a[0] - b[0]) < 0.05, (a, b)
     assert a[-1] < a[0] and abs(a[-1] - b[-1]) < 0.3, (a, b)
+
+
+def test_frozen_linear_dx_through_transposed_copy(dev, monkeypatch):
+    """FrozenLinear: dX = dY . W on the K-major tcgen05 GEMM with a transposed copy of the frozen weight made once
+    (models/transformer.py::frozen_transposed) vs the fp32 product."""
+    from vantage6_b200.models import transformer as T
+
+    monkeypatch.setenv("V6B200_FROZEN_DX", "gemm")
+    torch.manual_seed(5)
+    lin = T.FrozenLinear(256, 384, device=dev, init_std=0.05)
+    x = (torch.randn(3, 50, 256, device=dev) * 0.5).to(torch.bfloat16).requires_grad_()
+    y = lin(x)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    assert T.frozen_transposed(lin.weight_bf16) is not None and T.frozen_transposed(lin.weight_bf16).shape == (256, 384)
+    ref = dy.float().reshape(-1, 384) @ lin.weight_bf16.float()
+    torch.testing.assert_close(x.grad.float().reshape(-1, 256), ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))

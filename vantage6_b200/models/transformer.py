@@ -135,8 +135,8 @@ class ShadowLinear(nn.Module):
 
 
 class FrozenLinear(nn.Module):
-    """Frozen bf16 base weight (Llama LoRA): forward on the tcgen05 GEMM, dX on cuBLAS; the
-    weight is a buffer-less plain tensor so it is neither federated nor optimised."""
+    """Frozen bf16 base weight (Llama LoRA): forward and dX on the tcgen05 GEMM (dX through a transposed copy made once,
+    :func:`frozen_transposed`); the weight is a buffer-less plain tensor so it is neither federated nor optimised."""
 
     def __init__(self, in_features: int, out_features: int, device=None, init_std: float = 0.02):
         super().__init__()
@@ -152,6 +152,27 @@ class FrozenLinear(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return _FrozenLinearFn.apply(x, self.weight_bf16)
+
+
+_WT_CACHE: dict = {}
+
+
+def frozen_transposed(w: torch.Tensor) -> Optional[torch.Tensor]:
+    """[K_in, N_out] copy of a FROZEN bf16 weight, made once: dX = dY . W then runs on the K-major tcgen05 GEMM of
+    ops/gemm.py (0.88-0.99x cuBLAS on the Llama shapes) instead of the MN-major implicit-GEMM form (0.6-0.7x) or cuBLAS.
+    Costs one extra copy of the frozen weights (Llama-3 8B: 15 GB of 180); ``V6B200_FROZEN_DX=igemm|cublas`` selects the
+    other paths."""
+    import os
+
+    if os.environ.get("V6B200_FROZEN_DX", "gemm") != "gemm" or not w.is_cuda or w.dtype != torch.bfloat16 or w.dim() != 2:
+        return None
+    if w.shape[0] % 8 or w.shape[1] % 8:
+        return None
+    key = (w.data_ptr(), tuple(w.shape))
+    wt = _WT_CACHE.get(key)
+    if wt is None:
+        wt = _WT_CACHE[key] = w.t().contiguous()
+    return wt
 
 
 class _FrozenLinearFn(torch.autograd.Function):
@@ -171,6 +192,9 @@ class _FrozenLinearFn(torch.autograd.Function):
         dy2 = dy.reshape(-1, dy.shape[-1])
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
+        wt = frozen_transposed(w) if dy2.dtype == torch.bfloat16 else None
+        if wt is not None:
+            return G.gemm_bf16(dy2, wt).view(ctx.xshape), None
         if _tc_linear_bwd(dy2, w):
             from ..ops import conv as C
 
@@ -213,7 +237,8 @@ class _LoRALinearFn(torch.autograd.Function):
         da_s = torch.mm(dy2, b_w) * ctx.scaling                              # [M, r]
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = torch.mm(dy2, w_base.to(cdt))
+            wt = frozen_transposed(w_base) if cdt == torch.bfloat16 else None
+            dx = G.gemm_bf16(dy2, wt) if wt is not None else torch.mm(dy2, w_base.to(cdt))     # frozen base: own GEMM on the transposed copy
             dx.addmm_(da_s, a_w)
             dx = dx.view(ctx.xshape)
         d_a = d_b = None
