@@ -833,12 +833,12 @@ int launch(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     int grid = items < cap ? items : cap;
     int epi = EPI_PLAIN;
     if (mode == FPROP) epi = P.gamma ? EPI_STATS : ((P.bias || P.act) ? EPI_GEN : EPI_PLAIN);
+    else if (mode == DGRAD) epi = P.red_x ? EPI_RED : ((P.dstride == 2 || P.add_src) ? EPI_GEN : EPI_PLAIN);
     igemm::Params Pl = P;
     if (epi == EPI_STATS || epi == EPI_RED) {      // every CTA keeps one column block (see decode): grid = whole groups of num_n CTAs
         grid = items < cap ? items : (cap / num_n) * num_n;
         Pl.stat_arrivals = grid / num_n;
     }
-    else if (mode == DGRAD) epi = P.red_x ? EPI_RED : ((P.dstride == 2 || P.add_src) ? EPI_GEN : EPI_PLAIN);
     static const bool pdl = [] { const char* e = getenv("V6B200_PDL"); return !(e && e[0] == '0'); }();
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
