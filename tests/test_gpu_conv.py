@@ -215,11 +215,6 @@ def test_side_stream_filter_gradients_match_inline(dev, monkeypatch):
     torch.testing.assert_close(fm.grad, g_inline, rtol=1e-3, atol=1e-5 * float(g_inline.abs().max()) + 1e-7)
 
 
-_RED_OPT_IN = pytest.mark.skipif(os.environ.get("V6B200_TEST_BN_RED") != "1",
-                                 reason="EPI_RED (BatchNorm backward reduction in the dgrad epilogue) is an opt-in path: V6B200_TEST_BN_RED=1")
-
-
-@_RED_OPT_IN
 def test_bn_backward_reduction_in_dgrad_epilogue_matches_separate_pass(dev, monkeypatch):
     """EPI_RED (csrc/igemm.cu): the data-gradient kernel of the consuming convolution also produces the BatchNorm backward's
     per-channel sums / coefficients / dgamma / dbeta; against the same model with the reduction as its own pass."""
@@ -270,7 +265,6 @@ def test_bn_backward_reduction_in_dgrad_epilogue_matches_separate_pass(dev, monk
     assert torch.nn.functional.cosine_similarity(g1, g0, dim=0) > 0.9999
 
 
-@_RED_OPT_IN
 @pytest.mark.parametrize("n,cin,cout,hw,r", [(4, 64, 64, 16, 1), (2, 128, 64, 16, 3), (4, 256, 64, 8, 1)])
 def test_dgrad_epilogue_bn_reduction_unit(dev, n, cin, cout, hw, r):
     """EPI_RED in isolation: dx unchanged, dgamma / dbeta / coefficients equal to the formulas of the separate reduction pass."""

@@ -51,7 +51,7 @@ class _ShadowConvFn(torch.autograd.Function):
 
 def _bn_red_on() -> bool:
     """V6B200_BN_RED=1: BatchNorm backward reduction in the data-gradient epilogue (csrc/igemm.cu EPI_RED).  Off by default:
-    measured 50.1 vs 50.3 ms per ResNet-50 round -- the x read and the arithmetic move into an epilogue that is already the
+    measured 51.5 vs 50.5 ms per ResNet-50 round -- the x read and the arithmetic move into an epilogue that is already the
     bottleneck of the memory-bound layers, and the dy re-read it saves was an L2 hit."""
     import os
 
