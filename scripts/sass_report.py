@@ -58,7 +58,8 @@ def main():
                 base = op.split(".")[0]
                 if base in ("LDG", "STG") and ".MMR" not in op and "MC" not in op:
                     continue
-                ops[op if base in ("LDGMC",) or ".MMR" in op else base] += 1
+                keep_full = base in ("LDGMC",) or ".MMR" in op or (base == "UTMALDG" and "IM2COL" in op)       # the im2col form of TMA is evidence by itself
+                ops[op if keep_full else base] += 1
         rows.append((short, len(instrs), ops))
         for k in FULL:
             if k in short:
