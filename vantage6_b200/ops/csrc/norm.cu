@@ -7,6 +7,7 @@
 // without re-reading HBM.  gamma/beta stay fp32 (they live in the flat fp32 master buffer).
 // Backward: persistent CTAs walk rows; dgamma/dbeta are accumulated in registers across rows,
 // written as per-CTA partials and folded by a second tiny kernel (no atomics).
+#include <stdlib.h>
 #include "common.cuh"
 #include "api.h"
 
@@ -242,6 +243,123 @@ __global__ void __launch_bounds__(256) norm_param_grad_fold(const float* __restr
     }
 }
 
+// ---------------------------------------------------------------------------------- backward, second generation
+// The one-kernel backward above keeps 4 x 8 x 4 floats of row data AND 64 partial dgamma / dbeta accumulators per thread:
+// 157 registers, one CTA per SM, 1.3-3.1 TB/s (profiles/ncu_misc_r1a.md).  Split by access pattern instead:
+//   norm_bwd_dx_kernel     row-wise: dx (+ residual gradient); the row stays packed (bf16 vectors) in registers, no
+//                          parameter-gradient state -> 4 CTAs/SM
+//   norm_bwd_param_kernel  column-wise: a thread owns 8 columns and walks rows (dgamma += dy.xhat, dbeta += dy), 8 warps x
+//                          2 rows in flight, per-CTA partial [slice][cols] -> norm_param_grad_fold
+template <typename T, int TPR, bool RMS, int VPT>
+__global__ void __launch_bounds__(NORM_THREADS, (VPT <= 2 ? 4 : (VPT == 3 ? 3 : 2))) norm_bwd_dx_kernel(
+    const T* __restrict__ dy, const T* __restrict__ x_in, const T* __restrict__ dres, const float* __restrict__ gamma,
+    const float* __restrict__ mean_in, const float* __restrict__ rstd_in, T* __restrict__ dx, int rows, int cols) {
+    constexpr int RPC = NORM_THREADS / TPR;
+    __shared__ float red[NORM_THREADS / 32 * 2];
+    const int t = threadIdx.x % TPR, rin = threadIdx.x / TPR;
+    const int nvec = cols / 8;
+    for (int row0 = blockIdx.x * RPC; row0 < rows; row0 += gridDim.x * RPC) {
+        const int row = row0 + rin;
+        const bool active = row < rows;
+        const float mean = (active && !RMS) ? mean_in[row] : 0.f;
+        const float rstd = active ? rstd_in[row] : 0.f;
+        float d[VPT][8], xv[VPT][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            const int vi = t + j * TPR;
+            if (active && vi < nvec) {
+                IO<T>::load(dy + (size_t)row * cols + vi * 8, d[j]);
+                IO<T>::load(x_in + (size_t)row * cols + vi * 8, xv[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            const int vi = t + j * TPR;
+            if (active && vi < nvec) {
+                float g[8];
+                IO<float>::load(gamma + vi * 8, g);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    xv[j][k] = (xv[j][k] - mean) * rstd;
+                    d[j][k] *= g[k];
+                    s1 += d[j][k];
+                    s2 = fmaf(d[j][k], xv[j][k], s2);
+                }
+            }
+        }
+        float m1 = 0.f;
+        if constexpr (!RMS) m1 = group_sum<TPR>(s1, red, rin, t) / cols;
+        const float m2 = group_sum<TPR>(s2, red + NORM_THREADS / 32, rin, t) / cols;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            const int vi = t + j * TPR;
+            if (active && vi < nvec) {
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = rstd * (d[j][k] - m1 - xv[j][k] * m2);
+                if (dres) {
+                    float r[8];
+                    IO<T>::load(dres + (size_t)row * cols + vi * 8, r);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o[k] += r[k];
+                }
+                IO<T>::store(dx + (size_t)row * cols + vi * 8, o);
+            }
+        }
+    }
+}
+
+// grid (ceil(cols / 256), slices); block 256 = 8 warps; lane owns 8 columns, warps stride the slice's rows
+template <typename T, bool RMS>
+__global__ void __launch_bounds__(256) norm_bwd_param_kernel(
+    const T* __restrict__ dy, const T* __restrict__ x_in, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+    float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int rows, int cols, int rows_per_slice) {
+    __shared__ float sm[2][8][256 + 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 256 + lane * 8;
+    const bool col_ok = c0 < cols;
+    const int r_begin = blockIdx.y * rows_per_slice, r_end = min(rows, r_begin + rows_per_slice);
+    float dg[8], db[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { dg[k] = 0.f; db[k] = 0.f; }
+    for (int r = r_begin + warp; r < r_end; r += 16) {
+        float d[2][8], xv[2][8], mu[2], rs[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int rr = r + 8 * u;
+            mu[u] = 0.f; rs[u] = 0.f;
+            if (rr < r_end && col_ok) {
+                IO<T>::load(dy + (size_t)rr * cols + c0, d[u]);
+                IO<T>::load(x_in + (size_t)rr * cols + c0, xv[u]);
+                mu[u] = RMS ? 0.f : mean_in[rr];
+                rs[u] = rstd_in[rr];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { d[u][k] = 0.f; xv[u][k] = 0.f; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                dg[k] = fmaf(d[u][k], (xv[u][k] - mu[u]) * rs[u], dg[k]);
+                db[k] += d[u][k];
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sm[0][warp][lane * 8 + k] = dg[k]; sm[1][warp][lane * 8 + k] = db[k]; }
+    __syncthreads();
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < cols) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { a += sm[0][w][threadIdx.x]; b += sm[1][w][threadIdx.x]; }
+        dgamma_part[(size_t)blockIdx.y * cols + c] = a;
+        if (!RMS) dbeta_part[(size_t)blockIdx.y * cols + c] = b;
+    }
+}
+
 static inline int pick_tpr(int cols) {
     const int nvec = cols / 8;
     int tpr = 8;
@@ -278,22 +396,50 @@ static int launch_bwd(const void* dy, const void* x_in, const void* dres, const 
                       const float* rstd, void* dx, float* dgamma, float* dbeta, float* scratch, int scratch_parts,
                       int rows, int cols, int accumulate, cudaStream_t s) {
     if (cols % 8 != 0 || cols > 8 * MAXV * 256) return (int)cudaErrorInvalidValue;
+    static const bool v1 = [] { const char* e = getenv("V6B200_NORM_BWD"); return e && e[0] == '1'; }();      // the one-kernel form (A/B)
     const int tpr = pick_tpr(cols);
     const int rpc = NORM_THREADS / tpr;
-    int grid = (rows + rpc - 1) / rpc;
-    if (grid > scratch_parts) grid = scratch_parts;
-    const size_t smem = (size_t)rpc * cols * sizeof(float) * (RMS ? 1 : 2);
     float* pg = scratch;
     float* pb = scratch + (size_t)scratch_parts * cols;
+    if (v1) {
+        int grid = (rows + rpc - 1) / rpc;
+        if (grid > scratch_parts) grid = scratch_parts;
+        const size_t smem = (size_t)rpc * cols * sizeof(float) * (RMS ? 1 : 2);
+        DISPATCH_TPR(tpr, {
+            auto kern = norm_bwd_kernel<T, TPR, RMS>;
+            if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kern<<<grid, NORM_THREADS, smem, s>>>((const T*)dy, (const T*)x_in, (const T*)dres, gamma, mean, rstd,
+                                                    (T*)dx, pg, pb, rows, cols);
+        });
+        V6_CHECK_LAUNCH();
+        if (dgamma)      // frozen norm weights (LoRA fine-tuning): nothing to fold
+            norm_param_grad_fold<<<dim3((cols + 31) / 32, RMS ? 1 : 2), 256, 0, s>>>(pg, pb, dgamma, dbeta, grid, cols, accumulate);
+        V6_CHECK_LAUNCH();
+        return 0;
+    }
+    // parameter gradients first (they only read dy / x), then dx
+    if (dgamma) {
+        int slices = (rows + 31) / 32;
+        if (slices > scratch_parts) slices = scratch_parts;
+        const int rps = (rows + slices - 1) / slices;
+        slices = (rows + rps - 1) / rps;
+        norm_bwd_param_kernel<T, RMS><<<dim3((cols + 255) / 256, slices), 256, 0, s>>>((const T*)dy, (const T*)x_in, mean, rstd, pg, pb, rows,
+                                                                                        cols, rps);
+        V6_CHECK_LAUNCH();
+        norm_param_grad_fold<<<dim3((cols + 31) / 32, RMS ? 1 : 2), 256, 0, s>>>(pg, pb, dgamma, dbeta, slices, cols, accumulate);
+        V6_CHECK_LAUNCH();
+    }
+    const int nvec = cols / 8, vpt = (nvec + tpr - 1) / tpr;
+    int grid = (rows + rpc - 1) / rpc;
+    if (grid > 148 * 4) grid = 148 * 4;
+#define V6_NORM_DX(VPTV) norm_bwd_dx_kernel<T, TPR, RMS, VPTV><<<grid, NORM_THREADS, 0, s>>>((const T*)dy, (const T*)x_in, (const T*)dres, gamma, mean, rstd, (T*)dx, rows, cols)
     DISPATCH_TPR(tpr, {
-        auto kern = norm_bwd_kernel<T, TPR, RMS>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<grid, NORM_THREADS, smem, s>>>((const T*)dy, (const T*)x_in, (const T*)dres, gamma, mean, rstd,
-                                                (T*)dx, pg, pb, rows, cols);
+        if (vpt <= 1) V6_NORM_DX(1);
+        else if (vpt == 2) V6_NORM_DX(2);
+        else if (vpt == 3) V6_NORM_DX(3);
+        else V6_NORM_DX(4);
     });
-    V6_CHECK_LAUNCH();
-    if (dgamma)      // frozen norm weights (LoRA fine-tuning): nothing to fold
-        norm_param_grad_fold<<<dim3((cols + 31) / 32, RMS ? 1 : 2), 256, 0, s>>>(pg, pb, dgamma, dbeta, grid, cols, accumulate);
+#undef V6_NORM_DX
     V6_CHECK_LAUNCH();
     return 0;
 }
