@@ -153,3 +153,42 @@ def test_stem_space_to_depth_matches_direct_conv(dev, N, H, W, O):
     y2 = pool.stem_s2d(img, conv, _MEAN, _STD)
     y2.backward(dy)
     assert ((conv.weight.grad - 1.0) - wr.grad).abs().max().item() < 2e-2 * scale
+
+
+@pytest.mark.parametrize("N,C,H,W", [(4, 64, 112, 112), (2, 64, 10, 14), (3, 128, 16, 16)])
+def test_fused_bn_relu_maxpool_matches_separate_passes(dev, N, C, H, W):
+    """Stem: maxpool(relu(bn(x))) as one pass per direction (csrc/bn.cu) against the separate fused-BN + max-pool kernels."""
+    from vantage6_b200.ops import bn as BN
+    from vantage6_b200.ops.pool import MaxPool3x3s2
+
+    torch.manual_seed(0)
+    x0 = torch.randn(N, C, H, W, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    bnm = BN.FusedBatchNormAct(C, relu=True).to(dev)
+    with torch.no_grad():
+        bnm.weight.uniform_(0.5, 1.5)
+        bnm.bias.normal_(0, 0.3)
+    bnm.train()
+    xf = x0.float()
+    mean = xf.mean((0, 2, 3))
+    var = xf.var((0, 2, 3), unbiased=False)
+    rstd = torch.rsqrt(var + bnm.eps)
+    sb = torch.cat([bnm.weight.detach() * rstd, bnm.bias.detach() - mean * bnm.weight.detach() * rstd]).contiguous()
+    stats = dict(mean=mean.contiguous(), rstd=rstd.contiguous(), scale_bias=sb, momentum=0.1)
+    pool = MaxPool3x3s2()
+
+    xa = x0.clone().requires_grad_()
+    ya = pool(bnm.apply_pre(xa, stats))
+    dy = torch.randn_like(ya)
+    ya.backward(dy)
+    ga, ba = bnm.weight.grad.clone(), bnm.bias.grad.clone()
+    bnm.weight.grad = bnm.bias.grad = None
+
+    xb = x0.clone().requires_grad_()
+    yb = BN.bn_relu_maxpool(bnm, xb, stats)
+    yb.backward(dy)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(yb.float(), ya.float(), rtol=0, atol=0)
+    torch.testing.assert_close(bnm.weight.grad, ga, rtol=2e-3, atol=2e-3 * float(ga.abs().max()))
+    torch.testing.assert_close(bnm.bias.grad, ba, rtol=2e-3, atol=2e-3 * float(ba.abs().max()))
+    d = (xb.grad.float() - xa.grad.float()).abs()
+    assert float(d.max()) <= 2e-2 * float(xa.grad.float().abs().max()) + 1e-6, float(d.max())

@@ -108,9 +108,10 @@ class ResNet(nn.Module):
         layers += [Bottleneck(self.inplanes, planes, fused_bn=self.fused_bn) for _ in range(1, blocks)]
         return nn.Sequential(*layers)
 
-    def _stem(self, x: torch.Tensor) -> torch.Tensor:
+    def _stem(self, x: torch.Tensor, with_pool: bool = False):
         """conv1 + bn1(+ReLU).  uint8 NCHW images are normalised on the GPU (the host only ships raw bytes);
-        on the fused path the stem runs as a space-to-depth 4x4 convolution (ops/pool.py::stem_s2d)."""
+        on the fused path the stem runs as a space-to-depth 4x4 convolution (ops/pool.py::stem_s2d).  ``with_pool``: the
+        caller applies ``self.maxpool`` next -- when the fused pass exists the result is ``(pooled tensor, True)``."""
         if x.dtype != torch.uint8:
             return self.bn1(self.conv1(x.contiguous(memory_format=torch.channels_last)))
         bf16_stem = torch.is_autocast_enabled() or getattr(self.conv1, "w_bf16", None) is not None
@@ -122,7 +123,13 @@ class ResNet(nn.Module):
 
                 if (self.training and pool.stem_stats_fused(self.conv1) and hasattr(self.bn1, "stats_buffers") and _fuse_stats(self.layer1[0].conv3)):
                     stats = self.bn1.stats_buffers(x.device)        # batch statistics out of the convolution's epilogue
-                    return self.bn1.apply_pre(pool.stem_s2d(x, self.conv1, _MEAN, _STD, bn=stats), stats)
+                    y = pool.stem_s2d(x, self.conv1, _MEAN, _STD, bn=stats)
+                    if with_pool:
+                        from ..ops.bn import bn_pool_fusable, bn_relu_maxpool
+
+                        if bn_pool_fusable(self.bn1, self.maxpool, y):
+                            return bn_relu_maxpool(self.bn1, y, stats), True      # BN apply + ReLU + max-pool as one pass
+                    return self.bn1.apply_pre(y, stats)
                 return self.bn1(pool.stem_s2d(x, self.conv1, _MEAN, _STD))
             if x.is_contiguous() and (x.shape[2] * x.shape[3]) % 4 == 0:
                 return self.bn1(self.conv1(pool.image_normalize(x, _MEAN, _STD)))
@@ -135,7 +142,8 @@ class ResNet(nn.Module):
         return self.bn1(self.conv1(x))
 
     def forward(self, x):
-        x = self.maxpool(self._stem(x))
+        x = self._stem(x, with_pool=True)
+        x = x[0] if isinstance(x, tuple) else self.maxpool(x)        # (pooled, True): the stem did BN + ReLU + max-pool in one pass
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.fc(torch.flatten(self.avgpool(x), 1))
 

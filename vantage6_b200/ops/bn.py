@@ -146,6 +146,61 @@ class _BNFn(torch.autograd.Function):
         return dx, dres, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
+class _BNPoolFn(torch.autograd.Function):
+    """``maxpool3x3s2p1(relu(bn(x)))`` of the ResNet stem as one pass in each direction (csrc/bn.cu: bn_relu_maxpool_fwd_kernel,
+    bn_pool_bwd_*): the 112 x 112 BatchNorm output, its ReLU mask and the 112 x 112 gradient the max-pool backward would
+    write never exist.  The batch statistics come from the stem convolution's epilogue (``pre``)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, pre):
+        mean, rstd, scale_bias = pre
+        n, c, h, w = x.shape
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        p = torch.empty((n, c, ho, wo), device=x.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+        idx = torch.empty((n, ho, wo, c), device=x.device, dtype=torch.uint8)
+        count(1)
+        native().bn_pool_fwd(x.data_ptr(), scale_bias.data_ptr(), scale_bias.data_ptr() + 4 * c, p.data_ptr(), idx.data_ptr(), n, h, w, c,
+                             stream_ptr())
+        ctx.save_for_backward(x, idx, gamma, mean, rstd, scale_bias)
+        ctx.params = (gamma, beta)
+        return p
+
+    @staticmethod
+    def backward(ctx, dp):
+        x, idx, gamma, mean, rstd, scale_bias = ctx.saved_tensors
+        if not dp.is_contiguous(memory_format=torch.channels_last):
+            dp = dp.contiguous(memory_format=torch.channels_last)
+        n, c, h, w = x.shape
+        dx = torch.empty_like(x)
+        pg, pb = ctx.params
+        direct = all(p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous() for p in (pg, pb))
+        dgamma = pg.grad if direct else torch.empty_like(gamma)
+        dbeta = pb.grad if direct else torch.empty_like(gamma)
+        part, _ = _get_scratch(x.device, c)
+        coef = torch.empty(3 * c, device=x.device, dtype=torch.float32)
+        count(2)
+        native().bn_pool_bwd(dp.data_ptr(), idx.data_ptr(), x.data_ptr(), scale_bias.data_ptr(), scale_bias.data_ptr() + 4 * c,
+                             gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                             coef.data_ptr(), part.data_ptr(), n, h, w, c, direct, stream_ptr())
+        if direct:
+            return dx, None, None, None
+        return dx, dgamma, dbeta, None
+
+
+def bn_relu_maxpool(bn: "FusedBatchNormAct", x: torch.Tensor, stats: dict) -> torch.Tensor:
+    """Training-time ``maxpool(relu(bn(x)))`` with the batch statistics in ``stats`` (filled by the producing convolution)."""
+    return _BNPoolFn.apply(x, bn.weight, bn.bias, (stats["mean"], stats["rstd"], stats["scale_bias"]))
+
+
+def bn_pool_fusable(bn, pool, x: torch.Tensor) -> bool:
+    import os
+
+    from .pool import MaxPool3x3s2
+
+    return (os.environ.get("V6B200_STEM_POOL", "fused") == "fused" and isinstance(bn, FusedBatchNormAct) and bn.relu and bn.training
+            and isinstance(pool, MaxPool3x3s2) and x.is_cuda and torch.is_grad_enabled() and bn.num_features % 64 == 0)
+
+
 class FusedBatchNormAct(nn.BatchNorm2d):
     """BatchNorm2d with fused residual add and ReLU (``relu`` is the module default, overridable per call)."""
 

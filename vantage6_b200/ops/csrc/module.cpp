@@ -221,6 +221,15 @@ PYBIND11_MODULE(_C, m) {
                         P<void>(dres), P<float>(dgamma), P<float>(dbeta), P<float>(coef), P<float>(scratch), R, C, relu,
                         accumulate, S(s)), "bn_bwd");
     });
+    m.def("bn_pool_fwd", [](u64 x, u64 scale, u64 bias, u64 p, u64 idx, int N, int H, int W, int C, u64 s) {
+        check(v6_bn_pool_fwd(P<void>(x), P<float>(scale), P<float>(bias), P<void>(p), P<void>(idx), N, H, W, C, S(s)), "bn_pool_fwd");
+    });
+    m.def("bn_pool_bwd", [](u64 dp, u64 idx, u64 x, u64 scale, u64 bias, u64 gamma, u64 mean, u64 rstd, u64 dx, u64 dgamma, u64 dbeta, u64 coef,
+                            u64 scratch, int N, int H, int W, int C, bool accumulate, u64 s) {
+        check(v6_bn_pool_bwd(P<void>(dp), P<void>(idx), P<void>(x), P<float>(scale), P<float>(bias), P<float>(gamma), P<float>(mean), P<float>(rstd),
+                             P<void>(dx), P<float>(dgamma), P<float>(dbeta), P<float>(coef), P<float>(scratch), N, H, W, C, accumulate ? 1 : 0, S(s)),
+              "bn_pool_bwd");
+    });
     m.def("bn_bwd_apply", [](u64 dy, u64 mask, u64 x, u64 coef, u64 dx, u64 dres, long long R, int C, bool relu, u64 s) {
         check(v6_bn_bwd_apply(P<void>(dy), P<void>(mask), P<void>(x), P<float>(coef), P<void>(dx), P<void>(dres), R, C, relu, S(s)), "bn_bwd_apply");
     });
