@@ -396,8 +396,12 @@ static int launch_bwd(const void* dy, const void* x_in, const void* dres, const 
                       const float* rstd, void* dx, float* dgamma, float* dbeta, float* scratch, int scratch_parts,
                       int rows, int cols, int accumulate, cudaStream_t s) {
     if (cols % 8 != 0 || cols > 8 * MAXV * 256) return (int)cudaErrorInvalidValue;
-    static const bool v1 = [] { const char* e = getenv("V6B200_NORM_BWD"); return e && e[0] == '1'; }();      // the one-kernel form (A/B)
+    static const bool force_v1 = [] { const char* e = getenv("V6B200_NORM_BWD"); return e && e[0] == '1'; }();      // the one-kernel form (A/B)
     const int tpr = pick_tpr(cols);
+    // split form where a row fits one warp (cols <= 1024: shuffle-only row sums): 0.091 vs 0.105 ms at 32768 x 768, BERT-base round
+    // 30.4 vs 31.6 ms; wide rows (Llama, 4096) need the shared-memory row sums twice per row and are faster in the one-kernel
+    // form (0.137 vs 0.198 ms) -- profiles/kernel_bench_norm_r2.txt
+    const bool v1 = force_v1 || tpr > 32;
     const int rpc = NORM_THREADS / tpr;
     float* pg = scratch;
     float* pb = scratch + (size_t)scratch_parts * cols;
