@@ -197,7 +197,10 @@ def bn_pool_fusable(bn, pool, x: torch.Tensor) -> bool:
 
     from .pool import MaxPool3x3s2
 
-    return (os.environ.get("V6B200_STEM_POOL", "fused") == "fused" and isinstance(bn, FusedBatchNormAct) and bn.relu and bn.training
+    # opt-in (V6B200_STEM_POOL=fused): correct (tests/test_gpu_resnet_ops.py) but measured 51.1 vs 50.4 ms per ResNet-50 round --
+    # the per-pixel gather of the pooled gradient in BOTH backward passes and the 9-tap affine + ReLU in the forward cost more
+    # than the 2 x 103 MB per step they avoid
+    return (os.environ.get("V6B200_STEM_POOL", "separate") == "fused" and isinstance(bn, FusedBatchNormAct) and bn.relu and bn.training
             and isinstance(pool, MaxPool3x3s2) and x.is_cuda and torch.is_grad_enabled() and bn.num_features % 64 == 0)
 
 
