@@ -27,6 +27,25 @@ def _check(x: torch.Tensor, W: torch.Tensor):
     assert W.shape[1] == K and K % 8 == 0, "K must be a multiple of 8 (16-byte TMA rows)"
 
 
+_SPLITK_TILES = 74           # a final wave with more tiles than half the SMs is not split
+_splitk_ws: dict = {}
+
+
+def _splitk_workspace(device):
+    """fp32 [74][128][256] partial-tile workspace + arrival counters of the split-K tail (csrc/gemm.cu Params::split_s); zeroed once,
+    the kernel leaves it zero.  One per device: launches on one stream are ordered."""
+    import os
+
+    if os.environ.get("V6B200_GEMM_SPLITK", "1") == "0":
+        return None
+    key = str(device)
+    ws = _splitk_ws.get(key)
+    if ws is None:
+        ws = _splitk_ws[key] = (torch.zeros(_SPLITK_TILES * 128 * 256, device=device, dtype=torch.float32),
+                                torch.zeros(_SPLITK_TILES, device=device, dtype=torch.int32))
+    return ws
+
+
 def gemm_bf16(x2: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
               out: Optional[torch.Tensor] = None, variant: Optional[str] = None) -> torch.Tensor:
     """x2:[M,K], W:[N,K] -> [M,N] bf16 (raw op, no autograd)."""
@@ -45,8 +64,14 @@ def gemm_bf16(x2: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = 
         C.gemm2_bf16(x2.data_ptr(), W.data_ptr(), out.data_ptr(), 0 if bias is None else bias.data_ptr(),
                      M, N, K, x2.stride(0), W.stride(0), out.stride(0), act, stream_ptr())
     else:
-        C.gemm_bf16(x2.data_ptr(), W.data_ptr(), out.data_ptr(), 0 if bias is None else bias.data_ptr(),
-                    M, N, K, x2.stride(0), W.stride(0), out.stride(0), act, stream_ptr())
+        ws = _splitk_workspace(x2.device)
+        if ws is not None:      # same kernel; the tiles of a mostly empty final wave are cut along K over all SMs
+            C.gemm_bf16_ws(x2.data_ptr(), W.data_ptr(), out.data_ptr(), 0 if bias is None else bias.data_ptr(),
+                           M, N, K, x2.stride(0), W.stride(0), out.stride(0), act, ws[0].data_ptr(), ws[1].data_ptr(), _SPLITK_TILES,
+                           stream_ptr())
+        else:
+            C.gemm_bf16(x2.data_ptr(), W.data_ptr(), out.data_ptr(), 0 if bias is None else bias.data_ptr(),
+                        M, N, K, x2.stride(0), W.stride(0), out.stride(0), act, stream_ptr())
     return out
 
 
