@@ -182,11 +182,12 @@ def test_tcgen05_gemm(dev, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", [(1024, 14336, 4096), (1024, 1024, 4096), (256, 512, 1024), (1024, 4096, 14336), (640, 768, 512)])
-def test_tcgen05_gemm_split_k_tail(dev, M, N, K):
+def test_tcgen05_gemm_split_k_tail(dev, M, N, K, monkeypatch):
     """Shapes whose final wave of 128x256 tiles is mostly empty: those tiles are cut along K over all SMs (fp32 reductions
     into a workspace, last arriver runs the epilogue); run twice -- the workspace must come back zeroed."""
     from vantage6_b200.ops import gemm as G
 
+    monkeypatch.setenv("V6B200_GEMM_SPLITK", "1")
     torch.manual_seed(8)
     a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
     w = torch.randn(N, K, device=dev, dtype=torch.bfloat16)

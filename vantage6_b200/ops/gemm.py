@@ -33,10 +33,14 @@ _splitk_ws: dict = {}
 
 def _splitk_workspace(device):
     """fp32 [74][128][256] partial-tile workspace + arrival counters of the split-K tail (csrc/gemm.cu Params::split_s); zeroed once,
-    the kernel leaves it zero.  One per device: launches on one stream are ordered."""
+    the kernel leaves it zero.  One per device: launches on one stream are ordered.
+
+    Opt-in (``V6B200_GEMM_SPLITK=1``): correct (tests/test_gpu_kernels.py) but not faster -- 1024 x 14336 x 4096: 0.107 ms split vs
+    0.101 ms plain (cuBLAS 0.090); 148 CTAs pushing 128 KB each through ``red.global.add.v4.f32`` take longer than the mostly
+    empty wave they replace (profiles/kernel_bench_gemm_splitk_r2.txt)."""
     import os
 
-    if os.environ.get("V6B200_GEMM_SPLITK", "1") == "0":
+    if os.environ.get("V6B200_GEMM_SPLITK", "0") != "1":
         return None
     key = str(device)
     ws = _splitk_ws.get(key)
