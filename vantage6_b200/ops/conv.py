@@ -182,6 +182,21 @@ def linear_bwd_supported(n_out: int, k_in: int) -> bool:
     return n_out % 64 == 0 and k_in % 64 == 0
 
 
+def linear_fprop(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = 0) -> torch.Tensor:
+    """``y[M, N] = act(x[M, K] . w[N, K]^T + bias)`` on the implicit-GEMM kernel (a 1x1 convolution over a 1 x M image): its N tile
+    is chosen per problem (64 / 128 / 256 columns), which fills the SMs on shapes where the fixed 128x256 tile of ops/gemm.py
+    leaves most of them idle."""
+    assert x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.is_contiguous() and w.is_contiguous()
+    m, k = x.shape
+    n, k2 = w.shape
+    assert k == k2 and k % 64 == 0 and n % 8 == 0
+    y = torch.empty((m, n), device=x.device, dtype=torch.bfloat16)
+    count(1)
+    native().conv_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(), 0 if bias is None else bias.data_ptr(), int(act), 1, 1, m, k, n, 1, 1, 1, 0,
+                        0, 0, 0, 0, 0, 0, 0, 0, 0, 1e-5, 0.1, False, stream_ptr(), 0, 0, 0)
+    return y
+
+
 def linear_dgrad(dy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """``dx[M, K] = dy[M, N] . w[N, K]`` -- the weight is read in place as an MN-major UMMA operand (no transpose)."""
     assert dy.is_cuda and dy.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and dy.is_contiguous() and w.is_contiguous()
