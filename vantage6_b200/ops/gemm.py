@@ -59,6 +59,13 @@ def gemm_bf16(x2: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = 
     assert N % 8 == 0
     if out is None:
         out = torch.empty(M, N, device=x2.device, dtype=torch.bfloat16)
+    if variant is None and out is None and _igemm_better(M, N, K) and x2.is_contiguous() and W.is_contiguous():
+        # few-tile problems: the implicit-GEMM kernel picks its N tile per problem (64 / 128 / 256 columns) and fills the SMs where
+        # the fixed 128x256 tile leaves most idle -- 1024x1024x4096: 18.5 vs 27.1 us, 4096x2304x768: 14.7 vs 16.9 us (cuBLAS 14.9),
+        # profiles/kernel_bench_linear_fwd_r2.txt
+        from . import conv as _conv
+
+        return _conv.linear_fprop(x2, W, bias, act)
     count(1)
     C = native()
     # 2-CTA (cta_group::2, 256x256 tiles) when there is enough work to fill 74 SM pairs; the 1-CTA
@@ -77,6 +84,17 @@ def gemm_bf16(x2: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = 
             C.gemm_bf16(x2.data_ptr(), W.data_ptr(), out.data_ptr(), 0 if bias is None else bias.data_ptr(),
                         M, N, K, x2.stride(0), W.stride(0), out.stride(0), act, stream_ptr())
     return out
+
+
+def _igemm_better(M: int, N: int, K: int) -> bool:
+    """Measured crossover (scripts/gpu_r2_call16.sh): up to ~400 tiles of 128x256 and K <= 8192 the implicit-GEMM forward kernel is
+    the faster of the two tcgen05 GEMMs; large problems stay on the 128x256 / 256x256 kernels of csrc/gemm.cu / gemm2.cu."""
+    import os
+
+    if os.environ.get("V6B200_LINEAR_FWD", "auto") == "gemm" or K % 64 != 0 or N % 8 != 0:
+        return False
+    tiles = ((M + 127) // 128) * ((N + 255) // 256)
+    return tiles <= 400 and K <= 8192
 
 
 def _two_cta_default(M: int, N: int, K: int) -> bool:
