@@ -126,8 +126,6 @@ int v6_glm_logistic_grad(const void* X, const float* y, const float* w, float* p
                          int F, int bf16, cudaStream_t s);
 int v6_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, int lda, int ldb, int ldc,
                  int act, cudaStream_t stream);
-int v6_gemm_bf16_ws(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, int lda, int ldb, int ldc, int act,
-                    float* ws, int* ws_cnt, int ws_tiles, cudaStream_t stream);
 int v6_bcast_gemm_bf16(const void* A, void* B_local, const void* B_server_peer, void* C, const float* bias, int M, int N,
                        int K, int lda, int ldb, int ldc, int act, uint32_t* ready_flags, uint32_t epoch, cudaStream_t stream);
 int v6_flash_attn_bwd(const void* q, const void* k, const void* v, const void* dout, const void* kt, const void* qt,

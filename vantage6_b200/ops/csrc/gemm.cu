@@ -68,11 +68,6 @@ struct Params {
     const __nv_bfloat16* b_src;      // owner's source (its own copy of the weights)
     __nv_bfloat16* b_mc;             // multicast VA over every rank's weight buffer
     PeerTable flag_peers;            // every rank's flag array (peer VAs)
-    // split-K of the final partial wave (plain GEMM): the tiles beyond the last FULL wave of the persistent grid are cut into
-    // `split_s` k-ranges of `kb_per` k-blocks, one work item each; partial accumulators meet by fp32 reductions in `ws`
-    // ([tile][128][256] floats, zero between launches), the last item of a tile to arrive runs the normal epilogue from it.
-    int full_tiles, split_s, kb_per;
-    float* ws; int* ws_cnt;
 };
 
 V6_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
@@ -129,19 +124,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
         const int gsz = min(GROUP_N, num_n - first);
         n_blk = first + in_g % gsz;
         m_blk = in_g / gsz;
-    };
-
-    struct Work { int tile, kb0, kb1, split; };
-    const int num_items = P.split_s > 1 ? P.full_tiles + (num_tiles - P.full_tiles) * P.split_s : num_tiles;
-    auto work_of = [&](int it) {
-        Work w;
-        if (P.split_s <= 1 || it < P.full_tiles) { w.tile = it; w.kb0 = 0; w.kb1 = num_k; w.split = 0; return w; }
-        const int j = it - P.full_tiles;
-        w.tile = P.full_tiles + j / P.split_s;
-        w.kb0 = (j % P.split_s) * P.kb_per;
-        w.kb1 = min(num_k, w.kb0 + P.kb_per);
-        w.split = 1;
-        return w;
     };
 
     // K1 v3 push (owner side), run by the K1 warp of every CTA AND -- before their first accumulator exists -- by the four
@@ -206,11 +188,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
         };
         if (!P.fused_bcast) {
             if (lane == 0) {
-                for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
-                    const Work w = work_of(it);
+                for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                     int m_blk, n_blk;
-                    tile_coords(w.tile, m_blk, n_blk);
-                    for (int kb = w.kb0; kb < w.kb1; ++kb) issue(kb, m_blk, n_blk);
+                    tile_coords(t, m_blk, n_blk);
+                    for (int kb = 0; kb < num_k; ++kb) issue(kb, m_blk, n_blk);
                 }
             }
         } else {
@@ -262,13 +243,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
         constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
-            const Work w = work_of(it);
-            const int kb_first = w.kb0, kb_last = w.kb1 - 1;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-            for (int kb = w.kb0; kb < w.kb1; ++kb) {
+            for (int kb = 0; kb < num_k; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tcgen05_fence_after();
                 if (lane == 0) {
@@ -278,10 +257,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         const uint64_t da = make_smem_desc_sw128(sa + k * UMMA_K * 2);
                         const uint64_t db = make_smem_desc_sw128(sb + k * UMMA_K * 2);
-                        umma_bf16_ss(d_tmem, da, db, idesc, (kb > kb_first || k > 0) ? 1u : 0u);
+                        umma_bf16_ss(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);               // frees the smem stage when the MMAs retire
-                    if (kb == kb_last) umma_commit(&tfull_bar[acc]);
+                    if (kb == num_k - 1) umma_commit(&tfull_bar[acc]);
                 }
                 __syncwarp();
                 if (++stage == P.stages) { stage = 0; phase ^= 1; }
@@ -336,49 +315,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
         // ============================ epilogue ================================
         const int ew = warp;                      // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
         int acc = 0; uint32_t acc_phase = 0;
-        __shared__ int s_split_last;
-        for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
-            const Work w = work_of(it);
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             int m_blk, n_blk;
-            tile_coords(w.tile, m_blk, n_blk);
+            tile_coords(t, m_blk, n_blk);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tcgen05_fence_after();
-            bool from_ws = false;
-            float* wrow = nullptr;
-            if (w.split) {
-                // split item: add this k-range's partial accumulators into the tile's fp32 workspace; whoever arrives last owns
-                // the epilogue and reads the totals back (zeroing them for the next launch)
-                wrow = P.ws + (size_t)(w.tile - P.full_tiles) * (BLOCK_M * BLOCK_N) + (size_t)(ew * 32 + lane) * BLOCK_N;
-                const uint32_t t_row_s = tmem_base + acc * BLOCK_N + ((uint32_t)(ew * 32) << 16);
-#pragma unroll 1
-                for (int c = 0; c < BLOCK_N; c += 32) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(t_row_s + c, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(wrow + c + j), "f"(__uint_as_float(v[j])),
-                                     "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3])) : "memory");
-                }
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);             // TMEM drained
-                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
-                __threadfence();
-                asm volatile("bar.sync 1, 128;" ::: "memory");            // the 4 epilogue warps
-                if (threadIdx.x == 0) {
-                    int old;
-                    asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(P.ws_cnt + (w.tile - P.full_tiles)) : "memory");
-                    const int last = old == P.split_s - 1;
-                    if (last) P.ws_cnt[w.tile - P.full_tiles] = 0;
-                    s_split_last = last;
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const bool last = s_split_last != 0;
-                asm volatile("bar.sync 1, 128;" ::: "memory");            // s_split_last may be rewritten by the next item
-                if (!last) continue;
-                from_ws = true;
-            }
             // v2 epilogue: 64-column chunks go TMEM -> registers (bias / activation / bf16) -> a swizzled 4 KB
             // staging box in shared memory -> ONE coalesced TMA store per chunk (v1 wrote 16 B per lane at a
             // row stride: partial-sector writes, 77 us for a 200704x256x64 problem cuBLAS does in 26 us --
@@ -389,21 +330,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N; c += 64) {
                 uint32_t v[2][32];
-                if (!from_ws) {
-                    tmem_ld_32x32b_x32(t_row + c, v[0]);
-                    tmem_ld_32x32b_x32(t_row + c + 32, v[1]);
-                    tmem_ld_wait();
-                } else {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h)
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 q = __ldcg(reinterpret_cast<const float4*>(wrow + c + h * 32 + j));
-                            __stcg(reinterpret_cast<float4*>(wrow + c + h * 32 + j), make_float4(0.f, 0.f, 0.f, 0.f));
-                            v[h][j] = __float_as_uint(q.x); v[h][j + 1] = __float_as_uint(q.y);
-                            v[h][j + 2] = __float_as_uint(q.z); v[h][j + 3] = __float_as_uint(q.w);
-                        }
-                }
+                tmem_ld_32x32b_x32(t_row + c, v[0]);
+                tmem_ld_32x32b_x32(t_row + c + 32, v[1]);
+                tmem_ld_wait();
                 const int col0 = n_blk * BLOCK_N + c;
                 if (row0 < P.M && col0 < P.N) {                       // warp-uniform
                     uint32_t packed[32];
@@ -437,12 +366,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
                     if (lane == 0) { tma_store_2d(&tmap_c, stg, col0, row0); tma_store_commit(); }
                 }
             }
-            if (!from_ws) {
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
-            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
         if (lane == 0) tma_store_wait_all();                          // staging must outlive the last store
     }
@@ -457,7 +384,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,        // A  [M,K] 
 
 static int launch_gemm(const void* A, const void* B, const void* B_src, void* C, const float* bias, int M, int N, int K,
                        int lda, int ldb, int ldc, int act, uint32_t* ready_flags, uint32_t epoch, int max_ctas,
-                       cudaStream_t stream, float* ws = nullptr, int* ws_cnt = nullptr, int ws_tiles = 0) {
+                       cudaStream_t stream) {
     using namespace gemm;
     if (K % 8 != 0 || lda % 8 != 0 || ldb % 8 != 0 || ldc % 8 != 0) return (int)cudaErrorInvalidValue;
     alignas(64) CUtensorMap ta, tb, tbs;
@@ -479,25 +406,7 @@ static int launch_gemm(const void* A, const void* B, const void* B_src, void* C,
     }
     const int num_tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
     int sms = max_ctas > 0 ? max_ctas : 148;
-    int grid = num_tiles < sms ? num_tiles : sms;
-    // wave quantisation: a persistent grid of `sms` CTAs runs ceil(tiles / sms) waves; when the last one is mostly empty (448
-    // tiles = 3 full waves + 4 tiles: a quarter of the time for 1 % of the work) its tiles are cut along K so that every SM
-    // gets a slice (see Params::split_s)
-    if (ws && !B_src && ws_tiles > 0) {
-        const int num_k = (K + BLOCK_K - 1) / BLOCK_K;
-        const int full = (num_tiles / sms) * sms, r = num_tiles - full;
-        if (r > 0 && r <= ws_tiles && sms / r >= 2 && num_k >= 4) {
-            int s = sms / r;
-            if (s > num_k / 2) s = num_k / 2;                       // at least 2 k-blocks per slice
-            const int kb_per = (num_k + s - 1) / s;
-            s = (num_k + kb_per - 1) / kb_per;
-            if (s >= 2) {
-                P.full_tiles = full; P.split_s = s; P.kb_per = kb_per; P.ws = ws; P.ws_cnt = ws_cnt;
-                const int items = full + r * s;
-                grid = items < sms ? items : sms;
-            }
-        }
-    }
+    const int grid = num_tiles < sms ? num_tiles : sms;
     gemm_bf16_kernel<<<grid, kThreads, SMEM_BYTES, stream>>>(ta, tb, tbs, tc, P);
     V6_CHECK_LAUNCH();
     return 0;
@@ -506,11 +415,6 @@ static int launch_gemm(const void* A, const void* B, const void* B_src, void* C,
 extern "C" int v6_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, int lda,
                             int ldb, int ldc, int act, cudaStream_t stream) {
     return launch_gemm(A, B, nullptr, C, bias, M, N, K, lda, ldb, ldc, act, nullptr, 0, 0, stream);
-}
-// same, with the split-K workspace for the final partial wave: ws = ws_tiles x 128 x 256 floats, ws_cnt = ws_tiles ints, both zero
-extern "C" int v6_gemm_bf16_ws(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, int lda,
-                               int ldb, int ldc, int act, float* ws, int* ws_cnt, int ws_tiles, cudaStream_t stream) {
-    return launch_gemm(A, B, nullptr, C, bias, M, N, K, lda, ldb, ldc, act, nullptr, 0, 0, stream, ws, ws_cnt, ws_tiles);
 }
 extern "C" int v6_bcast_gemm_bf16(const void* A, void* B_local, const void* B_server_peer, void* C, const float* bias,
                                   int M, int N, int K, int lda, int ldb, int ldc, int act, uint32_t* ready_flags,

@@ -285,11 +285,6 @@ PYBIND11_MODULE(_C, m) {
     m.def("gemm_bf16", [](u64 A, u64 B, u64 C, u64 bias, int M, int N, int K, int lda, int ldb, int ldc, int act, u64 s) {
         check(v6_gemm_bf16(P<void>(A), P<void>(B), P<void>(C), P<float>(bias), M, N, K, lda, ldb, ldc, act, S(s)), "gemm_bf16");
     });
-    m.def("gemm_bf16_ws", [](u64 A, u64 B, u64 C, u64 bias, int M, int N, int K, int lda, int ldb, int ldc, int act, u64 ws, u64 ws_cnt,
-                             int ws_tiles, u64 s) {
-        check(v6_gemm_bf16_ws(P<void>(A), P<void>(B), P<void>(C), P<float>(bias), M, N, K, lda, ldb, ldc, act, P<float>(ws), P<int>(ws_cnt),
-                              ws_tiles, S(s)), "gemm_bf16_ws");
-    });
     m.def("gemm2_bf16", [](u64 A, u64 B, u64 C, u64 bias, int M, int N, int K, int lda, int ldb, int ldc, int act, u64 s) {
         check(v6_gemm2_bf16(P<void>(A), P<void>(B), P<void>(C), P<float>(bias), M, N, K, lda, ldb, ldc, act, S(s)), "gemm2_bf16");
     });

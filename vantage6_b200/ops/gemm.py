@@ -27,29 +27,6 @@ def _check(x: torch.Tensor, W: torch.Tensor):
     assert W.shape[1] == K and K % 8 == 0, "K must be a multiple of 8 (16-byte TMA rows)"
 
 
-_SPLITK_TILES = 74           # a final wave with more tiles than half the SMs is not split
-_splitk_ws: dict = {}
-
-
-def _splitk_workspace(device):
-    """fp32 [74][128][256] partial-tile workspace + arrival counters of the split-K tail (csrc/gemm.cu Params::split_s); zeroed once,
-    the kernel leaves it zero.  One per device: launches on one stream are ordered.
-
-    Opt-in (``V6B200_GEMM_SPLITK=1``): correct (tests/test_gpu_kernels.py) but not faster -- 1024 x 14336 x 4096: 0.107 ms split vs
-    0.101 ms plain (cuBLAS 0.090); 148 CTAs pushing 128 KB each through ``red.global.add.v4.f32`` take longer than the mostly
-    empty wave they replace (profiles/kernel_bench_gemm_splitk_r2.txt)."""
-    import os
-
-    if os.environ.get("V6B200_GEMM_SPLITK", "0") != "1":
-        return None
-    key = str(device)
-    ws = _splitk_ws.get(key)
-    if ws is None:
-        ws = _splitk_ws[key] = (torch.zeros(_SPLITK_TILES * 128 * 256, device=device, dtype=torch.float32),
-                                torch.zeros(_SPLITK_TILES, device=device, dtype=torch.int32))
-    return ws
-
-
 def gemm_bf16(x2: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
               out: Optional[torch.Tensor] = None, variant: Optional[str] = None) -> torch.Tensor:
     """x2:[M,K], W:[N,K] -> [M,N] bf16 (raw op, no autograd)."""
@@ -75,14 +52,11 @@ def gemm_bf16(x2: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = 
         C.gemm2_bf16(x2.data_ptr(), W.data_ptr(), out.data_ptr(), 0 if bias is None else bias.data_ptr(),
                      M, N, K, x2.stride(0), W.stride(0), out.stride(0), act, stream_ptr())
     else:
-        ws = _splitk_workspace(x2.device)
-        if ws is not None:      # same kernel; the tiles of a mostly empty final wave are cut along K over all SMs
-            C.gemm_bf16_ws(x2.data_ptr(), W.data_ptr(), out.data_ptr(), 0 if bias is None else bias.data_ptr(),
-                           M, N, K, x2.stride(0), W.stride(0), out.stride(0), act, ws[0].data_ptr(), ws[1].data_ptr(), _SPLITK_TILES,
-                           stream_ptr())
-        else:
-            C.gemm_bf16(x2.data_ptr(), W.data_ptr(), out.data_ptr(), 0 if bias is None else bias.data_ptr(),
-                        M, N, K, x2.stride(0), W.stride(0), out.stride(0), act, stream_ptr())
+        # (a split-K of the final partial wave -- fp32 reductions into a workspace, last arriver runs the epilogue -- was written and
+        # measured: 0.107 vs 0.101 ms on 1024 x 14336 x 4096, and the extra control flow cost the plain path 4 % on the Llama round;
+        # removed again, timings in profiles/kernel_bench_gemm_splitk_r2.txt)
+        C.gemm_bf16(x2.data_ptr(), W.data_ptr(), out.data_ptr(), 0 if bias is None else bias.data_ptr(),
+                    M, N, K, x2.stride(0), W.stride(0), out.stride(0), act, stream_ptr())
     return out
 
 
