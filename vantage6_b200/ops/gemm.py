@@ -34,8 +34,6 @@ def gemm_bf16(x2: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = 
     M, K = x2.shape
     N = W.shape[0]
     assert N % 8 == 0
-    if out is None:
-        out = torch.empty(M, N, device=x2.device, dtype=torch.bfloat16)
     if variant is None and out is None and _igemm_better(M, N, K) and x2.is_contiguous() and W.is_contiguous():
         # few-tile problems: the implicit-GEMM kernel picks its N tile per problem (64 / 128 / 256 columns) and fills the SMs where
         # the fixed 128x256 tile leaves most idle -- 1024x1024x4096: 18.5 vs 27.1 us, 4096x2304x768: 14.7 vs 16.9 us (cuBLAS 14.9),
@@ -43,6 +41,8 @@ def gemm_bf16(x2: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = 
         from . import conv as _conv
 
         return _conv.linear_fprop(x2, W, bias, act)
+    if out is None:
+        out = torch.empty(M, N, device=x2.device, dtype=torch.bfloat16)
     count(1)
     C = native()
     # 2-CTA (cta_group::2, 256x256 tiles) when there is enough work to fill 74 SM pairs; the 1-CTA
