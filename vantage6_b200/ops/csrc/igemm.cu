@@ -30,6 +30,7 @@
 // totals.  The separate statistics pass over Y (bn.cu::bn_stats_kernel) disappears.
 // WGRAD epilogue = red.global.add.v4.f32 of the fp32 accumulators into dW (split-K partial sums meet in L2).
 #include <cuda.h>
+#include <math.h>
 #include <stdlib.h>
 #include "common.cuh"
 #include "api.h"
@@ -251,7 +252,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         return it;
     };
     // WGRAD: 64-column chunks of this N tile that exist (each chunk = one (tap, channel block))
-    auto wgrad_chunks = [&](int n_blk) { return min(4, (P.N >> 6) - n_blk * 4); };
+    const int wch = P.block_n >> 6;                 // WGRAD: 64-column chunks per N tile (4, or 2 for block_n = 128)
+    auto wgrad_chunks = [&](int n_blk) { return min(wch, (P.N >> 6) - n_blk * wch); };
 
     if (warp == W_TMA_A && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
     if (warp == W_MMA && lane == 0) {
@@ -326,7 +328,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     int cs[4], cr[4], cc[4];                     // (tap_s, tap_r, channel block) of the tile's column chunks
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const int chunk = it.n_blk * 4 + j, tap = chunk / P.cblocks;
+                        const int chunk = it.n_blk * wch + j, tap = chunk / P.cblocks;
                         cc[j] = (chunk - tap * P.cblocks) * 64; cs[j] = tap % P.S; cr[j] = tap / P.S;
                     }
                     const uint32_t tx = (is_a ? na : nch) * BOX_BYTES;
@@ -347,7 +349,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         } else {
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
-                                if (j < nch) tma_load_2d_u(sb + j * BOX_BYTES, &tmap_b, fb, (it.n_blk * 4 + j) * 64, pix0);
+                                if (j < nch) tma_load_2d_u(sb + j * BOX_BYTES, &tmap_b, fb, (it.n_blk * wch + j) * 64, pix0);
                         }
                         if (++stage == num_stages) { stage = 0; phase ^= 1; }
                     }
@@ -569,20 +571,36 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             tcgen05_fence_after();
             const uint32_t t_row = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
             if (MODE == WGRAD) {
-                // fp32 accumulators -> red.add into dW[row][n_blk*256 + col]; row = output channel
+                // fp32 accumulators -> dW[row][n_blk*block_n + col] (+=); row = output channel.  split-K partial sums meet by
+                // red.add in L2; with ONE k-range per tile the tile owns its output and a plain load-add-store does it -- L2 fp32
+                // reductions run at ~0.7 TB/s, an order of magnitude below plain stores, and were the whole gap to cuDNN on the
+                // layers with large filters (512x512x3x3: 19 MB of reductions per launch; profiles/kernel_bench_linear_bwd_r2.txt)
                 const int row = it.m_blk * BLOCK_M + quad * 32 + lane;
                 const int ncols = wgrad_chunks(it.n_blk) * 64;
-                float* drow = P.dw + (long long)row * P.ldw + it.n_blk * 256;
+                float* drow = P.dw + (long long)row * P.ldw + it.n_blk * P.block_n;
+                const bool owned = P.splits == 1;
 #pragma unroll 1
                 for (int c = half * 32; c < ncols; c += 64) {
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(t_row + c, v);
                     tmem_ld_wait();
                     if (row < P.M) {
+                        if (owned) {
+                            float4 o[8];
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            red_add_f4(drow + c + j, __uint_as_float(v[j]) * P.out_scale, __uint_as_float(v[j + 1]) * P.out_scale,
-                                       __uint_as_float(v[j + 2]) * P.out_scale, __uint_as_float(v[j + 3]) * P.out_scale);
+                            for (int j = 0; j < 8; ++j) o[j] = *reinterpret_cast<const float4*>(drow + c + 4 * j);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                o[j].x = fmaf(__uint_as_float(v[4 * j]), P.out_scale, o[j].x); o[j].y = fmaf(__uint_as_float(v[4 * j + 1]), P.out_scale, o[j].y);
+                                o[j].z = fmaf(__uint_as_float(v[4 * j + 2]), P.out_scale, o[j].z); o[j].w = fmaf(__uint_as_float(v[4 * j + 3]), P.out_scale, o[j].w);
+                                *reinterpret_cast<float4*>(drow + c + 4 * j) = o[j];
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                red_add_f4(drow + c + j, __uint_as_float(v[j]) * P.out_scale, __uint_as_float(v[j + 1]) * P.out_scale,
+                                           __uint_as_float(v[j + 2]) * P.out_scale, __uint_as_float(v[j + 3]) * P.out_scale);
+                        }
                     }
                 }
             } else {
@@ -980,11 +998,36 @@ extern "C" int v6_conv_wgrad(const void* dy, const void* x, float* dw, int N, in
     P.M = Cout; P.N = R * S * Cin; P.num_kb = (int)((pix + 63) / 64); P.block_n = 256;
     P.b_im2col = plain ? 0 : 1; P.PQ = Pp * Qq; P.Q = Qq; P.stride = stride; P.pad = pad; P.S = S; P.cblocks = Cin / 64; P.taps = R * S;
     P.dw = dw; P.ldw = (long long)R * S * Cin; P.out_scale = scale;
-    const int tiles = ((Cout + 127) / 128) * ((P.N / 64 + 3) / 4);
     if (splits <= 0) {
-        splits = (148 + tiles - 1) / tiles;                              // about one wave of work items
-        const int max_splits = P.num_kb / 4 > 0 ? P.num_kb / 4 : 1;      // >= 4 k-blocks per item
-        if (splits > max_splits) splits = max_splits;
+        // (N tile, k-ranges per tile) by a small cost model in cycles: waves x k-blocks x max(MMA, operand fetch through L2) for the
+        // main loop; the epilogue moves Cout x R*S*Cin x 4 B per k-range -- through L2 reductions (~370 B/cycle chip-wide, measured)
+        // when a tile has several k-ranges, by plain load-add-store (~3000 B/cycle) when it has one.  Few tiles + long K (the
+        // 56x56 layers) -> many k-ranges of a tiny output; big filters + short K (7x7 / 14x14 layers, nn.Linear) -> one k-range.
+        static const bool legacy = [] { const char* e = getenv("V6B200_WGRAD_PLAN"); return e && e[0] == '0'; }();
+        double best = 1e30;
+        int best_bn = 256, best_s = 1;
+        const double out_bytes = (double)Cout * P.N * 4.0;
+        for (int bn : {256, 128}) {
+            const long long tiles = (long long)((Cout + 127) / 128) * ((P.N + bn - 1) / bn);
+            const double per_kb = fmax(2.0 * bn, (16384.0 + bn * 128.0) / 60.0);
+            for (int s = 1; s <= 64; s = s < 4 ? s + 1 : s * 2) {
+                if (s > 1 && P.num_kb / s < 4) break;                    // >= 4 k-blocks per item
+                const long long items = tiles * s;
+                const double waves = (double)((items + 147) / 148);
+                const double kb = (double)((P.num_kb + s - 1) / s);
+                const double t = waves * (kb * per_kb + 1500.0) + (s == 1 ? out_bytes / 3000.0 : out_bytes * s / 370.0);
+                if (t < best) { best = t; best_bn = bn; best_s = s; }
+            }
+        }
+        if (legacy) {
+            const int tiles = ((Cout + 127) / 128) * ((P.N / 64 + 3) / 4);
+            best_bn = 256;
+            best_s = (148 + tiles - 1) / tiles;
+            const int max_splits = P.num_kb / 4 > 0 ? P.num_kb / 4 : 1;
+            if (best_s > max_splits) best_s = max_splits;
+        }
+        P.block_n = best_bn;
+        splits = best_s;
     }
     if (splits > P.num_kb) splits = P.num_kb;
     P.kb_per_split = (P.num_kb + splits - 1) / splits;
