@@ -151,39 +151,37 @@ class FrozenLinear(nn.Module):
         return self
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return _FrozenLinearFn.apply(x, self.weight_bf16)
+        return _FrozenLinearFn.apply(x, self.weight_bf16, self)
 
 
-_WT_CACHE: dict = {}
-
-
-def frozen_transposed(w: torch.Tensor) -> Optional[torch.Tensor]:
-    """[K_in, N_out] copy of a FROZEN bf16 weight, made once: dX = dY . W then runs on the K-major tcgen05 GEMM of
-    ops/gemm.py (0.88-0.99x cuBLAS on the Llama shapes) instead of the MN-major implicit-GEMM form (0.6-0.7x) or cuBLAS.
-    Costs one extra copy of the frozen weights (Llama-3 8B: 15 GB of 180); ``V6B200_FROZEN_DX=igemm|cublas`` selects the
-    other paths."""
+def frozen_transposed(holder) -> Optional[torch.Tensor]:
+    """[K_in, N_out] copy of the FROZEN bf16 weight of ``holder`` (a :class:`FrozenLinear`), made once and owned by the module:
+    dX = dY . W then runs on the K-major tcgen05 GEMM of ops/gemm.py (0.88-0.99x cuBLAS on the Llama shapes) instead of the
+    MN-major implicit-GEMM form or cuBLAS.  Costs one extra copy of the frozen weights (Llama-3 8B: 15 GB of 180);
+    ``V6B200_FROZEN_DX=igemm|cublas`` selects the other paths.  Re-made when the weight was moved or overwritten in place."""
     import os
 
-    if os.environ.get("V6B200_FROZEN_DX", "gemm") != "gemm" or not w.is_cuda or w.dtype != torch.bfloat16 or w.dim() != 2:
+    w = getattr(holder, "weight_bf16", None)
+    if (w is None or os.environ.get("V6B200_FROZEN_DX", "gemm") != "gemm" or not w.is_cuda or w.dtype != torch.bfloat16 or w.dim() != 2
+            or w.shape[0] % 8 or w.shape[1] % 8):
         return None
-    if w.shape[0] % 8 or w.shape[1] % 8:
-        return None
-    key = (w.data_ptr(), tuple(w.shape))
-    wt = _WT_CACHE.get(key)
-    if wt is None:
-        wt = _WT_CACHE[key] = w.t().contiguous()
-    return wt
+    tag = (w.data_ptr(), w._version, tuple(w.shape))
+    if getattr(holder, "_wt_tag", None) != tag:
+        holder._wt = w.t().contiguous()
+        holder._wt_tag = tag
+    return holder._wt
 
 
 class _FrozenLinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w):
+    def forward(ctx, x, w, holder=None):
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         y = G.gemm_bf16(x2, w) if x2.is_cuda else G.reference_linear(x2, w)
         ctx.save_for_backward(w)
         ctx.xshape = x.shape
+        ctx.holder = holder
         return y.view(*x.shape[:-1], w.shape[0])
 
     @staticmethod
@@ -192,14 +190,14 @@ class _FrozenLinearFn(torch.autograd.Function):
         dy2 = dy.reshape(-1, dy.shape[-1])
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
-        wt = frozen_transposed(w) if dy2.dtype == torch.bfloat16 else None
+        wt = frozen_transposed(ctx.holder) if (dy2.dtype == torch.bfloat16 and ctx.holder is not None) else None
         if wt is not None:
-            return G.gemm_bf16(dy2, wt).view(ctx.xshape), None
+            return G.gemm_bf16(dy2, wt).view(ctx.xshape), None, None
         if _tc_linear_bwd(dy2, w):
             from ..ops import conv as C
 
-            return C.linear_dgrad(dy2, w).view(ctx.xshape), None
-        return torch.mm(dy2, w).view(ctx.xshape), None
+            return C.linear_dgrad(dy2, w).view(ctx.xshape), None, None
+        return torch.mm(dy2, w).view(ctx.xshape), None, None
 
 
 class _LoRALinearFn(torch.autograd.Function):
@@ -209,7 +207,7 @@ class _LoRALinearFn(torch.autograd.Function):
     and step -- 128 adapters in Llama-3-8B.)"""
 
     @staticmethod
-    def forward(ctx, x, lora_a, lora_b, w_base, a16, b16, scaling, sink, off_a, off_b):
+    def forward(ctx, x, lora_a, lora_b, w_base, a16, b16, scaling, sink, off_a, off_b, holder=None):
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
@@ -223,6 +221,7 @@ class _LoRALinearFn(torch.autograd.Function):
         ctx.scaling, ctx.xshape = scaling, x.shape
         ctx.sink, ctx.off_a, ctx.off_b = sink, off_a, off_b
         ctx.need_ab = lora_a.requires_grad
+        ctx.holder = holder
         return y.view(*x.shape[:-1], w_base.shape[0])
 
     @staticmethod
@@ -237,7 +236,7 @@ class _LoRALinearFn(torch.autograd.Function):
         da_s = torch.mm(dy2, b_w) * ctx.scaling                              # [M, r]
         dx = None
         if ctx.needs_input_grad[0]:
-            wt = frozen_transposed(w_base) if cdt == torch.bfloat16 else None
+            wt = frozen_transposed(ctx.holder) if (cdt == torch.bfloat16 and ctx.holder is not None) else None
             dx = G.gemm_bf16(dy2, wt) if wt is not None else torch.mm(dy2, w_base.to(cdt))     # frozen base: own GEMM on the transposed copy
             dx.addmm_(da_s, a_w)
             dx = dx.view(ctx.xshape)
@@ -250,7 +249,7 @@ class _LoRALinearFn(torch.autograd.Function):
                 ctx.sink.append((g_b, ctx.off_b))
             else:
                 d_a, d_b = g_a.float(), g_b.float()
-        return dx, d_a, d_b, None, None, None, None, None, None, None
+        return dx, d_a, d_b, None, None, None, None, None, None, None, None
 
 
 class LoRALinear(nn.Module):
@@ -269,7 +268,7 @@ class LoRALinear(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return _LoRALinearFn.apply(x, self.lora_A, self.lora_B, self.base.weight_bf16, self.a_bf16, self.b_bf16,
-                                   self.scaling, self._sink, self._off_a, self._off_b)
+                                   self.scaling, self._sink, self._off_a, self._off_b, self.base)
 
 
 class FusedLayerNorm(nn.Module):
