@@ -263,3 +263,26 @@ def test_trainer_graph_matches_eager(dev):
     torch.testing.assert_close(a.engine.w, b.engine.w, rtol=1e-2, atol=1e-3)
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("T,V", [(64, 1000), (33, 128256), (128, 512), (7, 30522)])
+def test_fused_cross_entropy(dev, T, V):
+    """csrc/ce.cu: mean cross-entropy over bf16 logits (online log-sum-exp, ignore_index) and its in-place gradient vs PyTorch fp32."""
+    from vantage6_b200.ops.ce import fused_cross_entropy
+
+    torch.manual_seed(12)
+    Vp = (V + 7) // 8 * 8
+    buf = (torch.randn(T, Vp, device=dev) * 3).to(torch.bfloat16)
+    logits = buf[:, :V].requires_grad_() if Vp == V else buf[:, :V].detach().requires_grad_()
+    labels = torch.randint(0, V, (T,), device=dev)
+    labels[::5] = -100
+    ref_in = logits.detach().float().requires_grad_()
+    ref = torch.nn.functional.cross_entropy(ref_in, labels, ignore_index=-100)
+    ref.backward()
+    x = logits.detach().clone().requires_grad_() if Vp == V else logits
+    loss = fused_cross_entropy(x, labels)
+    (loss * 1.0).backward()
+    torch.cuda.synchronize()
+    torch.testing.assert_close(loss.float(), ref, rtol=2e-3, atol=2e-3)
+    g = x.grad.float()
+    torch.testing.assert_close(g, ref_in.grad, rtol=5e-2, atol=2e-2 * float(ref_in.grad.abs().max()))

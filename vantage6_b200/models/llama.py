@@ -99,7 +99,15 @@ class LlamaLoRA(nn.Module):
         for layer in self.layers:
             h, stream = layer(h, stream, cos, sin)
         x, _ = self.norm(h, residual=stream)
-        logits = self.lm_head(x).float()
+        logits = self.lm_head(x)
+        if logits.is_cuda and logits.dtype == torch.bfloat16:
+            # next-token targets for every position, the last one ignored: the fused cross-entropy reads the bf16 logits once per
+            # direction and writes dlogits in place (ops/ce.py) instead of slicing + an fp32 copy + log_softmax
+            from ..ops.ce import fused_cross_entropy
+
+            tgt = torch.cat([labels[:, 1:], torch.full_like(labels[:, :1], -100)], dim=1)
+            return fused_cross_entropy(logits.reshape(-1, logits.shape[-1]), tgt.reshape(-1))
+        logits = logits.float()
         return torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]), labels[:, 1:].reshape(-1))
 
 

@@ -150,6 +150,10 @@ int v6_bn_fwd(const void* x, const void* res, const float* gamma, const float* b
               float* scratch, long long R, int C, float eps, float momentum, int relu, cudaStream_t s);
 int v6_bn_apply(const void* x, const void* res, const float* scale, const float* bias, void* y, void* relu_mask, long long R, int C,
                 int relu, cudaStream_t s);
+int v6_ce_fwd(const void* logits, const long long* labels, float* lse, float* loss, int T, int V, long long ld, long long ignore_index,
+              cudaStream_t s);
+int v6_ce_bwd(void* logits, const long long* labels, const float* lse, const float* scale_ptr, int T, int V, long long ld,
+              long long ignore_index, cudaStream_t s);
 int v6_bn_pool_fwd(const void* x, const float* scale, const float* bias, void* p, void* idx, int N, int H, int W, int C, cudaStream_t s);
 int v6_bn_pool_bwd(const void* dp, const void* idx, const void* x, const float* scale, const float* bias, const float* gamma, const float* mean,
                    const float* rstd, void* dx, float* dgamma, float* dbeta, float* coef, float* scratch, int N, int H, int W, int C,
