@@ -140,8 +140,8 @@ def test_frozen_linear_dx_through_transposed_copy(dev, monkeypatch):
     dy = torch.randn_like(y)
     y.backward(dy)
     assert T.frozen_transposed(lin) is not None and T.frozen_transposed(lin).shape == (256, 384)
+    ref = dy.float().reshape(-1, 384) @ lin.weight_bf16.float()
+    torch.testing.assert_close(x.grad.float().reshape(-1, 256), ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))
     with torch.no_grad():
         lin.weight_bf16.mul_(2.0)                      # overwritten in place (checkpoint load): the copy follows
     torch.testing.assert_close(T.frozen_transposed(lin).float(), lin.weight_bf16.float().t())
-    ref = dy.float().reshape(-1, 384) @ lin.weight_bf16.float()
-    torch.testing.assert_close(x.grad.float().reshape(-1, 256), ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))

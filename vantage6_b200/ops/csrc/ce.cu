@@ -22,7 +22,8 @@ V6_DEVINL void unpack8(const uint4& t, float (&v)[8]) {
 // combine two (max, sum-of-exp relative to max) pairs
 V6_DEVINL void merge(float& m, float& s, float m2, float s2) {
     const float mm = fmaxf(m, m2);
-    s = s * __expf(m - mm) + s2 * __expf(m2 - mm);
+    // a thread / warp that saw no element carries (-inf, 0): exp(-inf - -inf) would be NaN
+    s = (m == -INFINITY ? 0.f : s * __expf(m - mm)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mm));
     m = mm;
 }
 
