@@ -55,7 +55,13 @@ class BertForMaskedLM(nn.Module):
     def __init__(self, c: BertConfig = BertConfig()):
         super().__init__()
         self.cfg = c
-        self.word = nn.Embedding(c.vocab_size, c.hidden)
+        # the vocabulary is padded to a multiple of 64 rows (30522 -> 30528; the extra rows are never looked up and never enter the
+        # softmax): the tied output projection then runs on the tcgen05 kernels (forward, dX, dW) instead of the unaligned-N library
+        # fallback (an sm_80 mma.sync kernel at ~180 TFLOP/s, profiles/launches_bert_base_r2_final.txt)
+        self.vocab_padded = (c.vocab_size + 63) // 64 * 64
+        self.word = nn.Embedding(self.vocab_padded, c.hidden)
+        self.word_bf16 = None                    # bf16 shadow of the embedding table (set by attach_shadow)
+        self._sink, self._word_offset = None, 0
         self.pos = nn.Embedding(c.max_pos, c.hidden)
         self.tok_type = nn.Embedding(c.type_vocab, c.hidden)
         for e in (self.word, self.pos, self.tok_type):
@@ -64,7 +70,7 @@ class BertForMaskedLM(nn.Module):
         self.layers = nn.ModuleList(BertLayer(c) for _ in range(c.layers))
         self.head_dense = ShadowLinear(c.hidden, c.hidden, act=G.ACT_GELU)
         self.head_ln = FusedLayerNorm(c.hidden, c.eps)
-        self.head_bias = nn.Parameter(torch.zeros(c.vocab_size))
+        self.head_bias = nn.Parameter(torch.zeros(self.vocab_padded))
 
     def forward(self, input_ids: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         B, S = input_ids.shape
@@ -77,7 +83,15 @@ class BertForMaskedLM(nn.Module):
         # so every shape is static (CUDA-graph friendly, no nonzero() sync).
         xs = x.reshape(B * S, -1).index_select(0, labels[:, 0])
         t = self.head_ln(self.head_dense(xs))
-        logits = torch.nn.functional.linear(t, self.word.weight.to(t.dtype)).float() + self.head_bias
+        V = self.cfg.vocab_size
+        if t.is_cuda and t.dtype == torch.bfloat16:
+            # tied output projection on the tcgen05 GEMMs (bias in the epilogue), cross-entropy on csrc/ce.cu over the bf16 logits
+            from ..ops.ce import fused_cross_entropy
+            from .transformer import _ShadowLinearFn
+
+            logits = _ShadowLinearFn.apply(t, self.word.weight, self.head_bias, self.word_bf16, G.ACT_NONE, self._sink, self._word_offset)
+            return fused_cross_entropy(logits, labels[:, 1].contiguous(), n_classes=V)
+        logits = torch.nn.functional.linear(t, self.word.weight[:V].to(t.dtype)).float() + self.head_bias[:V]
         return torch.nn.functional.cross_entropy(logits, labels[:, 1])
 
 

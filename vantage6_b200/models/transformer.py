@@ -304,6 +304,10 @@ def attach_shadow(module: nn.Module, flat_model) -> int:
 
     views = flat_model.shadow_views()
     n = 0
+    if hasattr(module, "word_bf16") and "word.weight" in views:      # tied embedding / output projection (models/bert.py)
+        module.word_bf16 = views["word.weight"]
+        module._sink, module._word_offset = flat_model.grad_sink, flat_model.segment("word.weight").offset
+        n += 1
     for name, m in module.named_modules():
         if isinstance(m, LoRALinear):
             ka, kb = (f"{name}.lora_A", f"{name}.lora_B") if name else ("lora_A", "lora_B")

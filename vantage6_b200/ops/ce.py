@@ -16,8 +16,9 @@ from . import count, native, stream_ptr
 
 class _CEFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits: torch.Tensor, labels: torch.Tensor, ignore_index: int):
-        T, V = logits.shape
+    def forward(ctx, logits: torch.Tensor, labels: torch.Tensor, ignore_index: int, n_classes: int):
+        T, v_alloc = logits.shape
+        V = int(n_classes)
         lse = torch.empty(T, device=logits.device, dtype=torch.float32)
         rows = torch.empty(T, device=logits.device, dtype=torch.float32)
         count(1)
@@ -25,23 +26,26 @@ class _CEFn(torch.autograd.Function):
                         stream_ptr())
         n = (labels != ignore_index).sum().clamp_(min=1).to(torch.float32)
         ctx.save_for_backward(logits, labels, lse, n)
-        ctx.ignore_index = int(ignore_index)
+        ctx.ignore_index, ctx.n_classes = int(ignore_index), V
         return rows.sum() / n
 
     @staticmethod
     def backward(ctx, g):
         logits, labels, lse, n = ctx.saved_tensors
-        T, V = logits.shape
+        T, v_alloc = logits.shape
         scale = (g.to(torch.float32) / n).reshape(1).contiguous()
         count(1)
-        native().ce_bwd(logits.data_ptr(), labels.data_ptr(), lse.data_ptr(), scale.data_ptr(), T, V, logits.stride(0), ctx.ignore_index,
-                        stream_ptr())
-        return logits, None, None          # the logits buffer now holds dlogits
+        native().ce_bwd(logits.data_ptr(), labels.data_ptr(), lse.data_ptr(), scale.data_ptr(), T, ctx.n_classes, v_alloc, logits.stride(0),
+                        ctx.ignore_index, stream_ptr())
+        return logits, None, None, None    # the logits buffer now holds dlogits (zero in the padding columns)
 
 
-def fused_cross_entropy(logits: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
-    """Mean cross-entropy of ``logits`` [T, V] against ``labels`` [T]; rows labelled ``ignore_index`` do not count."""
+def fused_cross_entropy(logits: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100, n_classes: int | None = None) -> torch.Tensor:
+    """Mean cross-entropy of ``logits`` [T, V] against ``labels`` [T]; rows labelled ``ignore_index`` do not count.
+    ``n_classes`` < V: the trailing columns are padding of the head GEMM (vocabulary padded to a tile multiple) -- they take no part
+    in the softmax and get a zero gradient."""
+    V = logits.shape[1] if n_classes is None else int(n_classes)
     if (logits.is_cuda and logits.dtype == torch.bfloat16 and logits.dim() == 2 and logits.stride(1) == 1 and logits.stride(0) % 8 == 0
             and labels.dtype == torch.int64 and labels.is_contiguous()):
-        return _CEFn.apply(logits, labels, ignore_index)
-    return torch.nn.functional.cross_entropy(logits.float(), labels, ignore_index=ignore_index)
+        return _CEFn.apply(logits, labels, ignore_index, V)
+    return torch.nn.functional.cross_entropy(logits[:, :V].float(), labels, ignore_index=ignore_index)

@@ -152,7 +152,7 @@ int v6_bn_apply(const void* x, const void* res, const float* scale, const float*
                 int relu, cudaStream_t s);
 int v6_ce_fwd(const void* logits, const long long* labels, float* lse, float* loss, int T, int V, long long ld, long long ignore_index,
               cudaStream_t s);
-int v6_ce_bwd(void* logits, const long long* labels, const float* lse, const float* scale_ptr, int T, int V, long long ld,
+int v6_ce_bwd(void* logits, const long long* labels, const float* lse, const float* scale_ptr, int T, int V, int V_alloc, long long ld,
               long long ignore_index, cudaStream_t s);
 int v6_bn_pool_fwd(const void* x, const float* scale, const float* bias, void* p, void* idx, int N, int H, int W, int C, cudaStream_t s);
 int v6_bn_pool_bwd(const void* dp, const void* idx, const void* x, const float* scale, const float* bias, const float* gamma, const float* mean,

@@ -71,9 +71,10 @@ __global__ void __launch_bounds__(THREADS) ce_fwd_kernel(const __nv_bfloat16* __
 }
 
 // scale_ptr: device scalar = upstream gradient / number of counted rows
+// V_alloc >= V: columns [V, V_alloc) are padding of the head GEMM (vocabulary padded to a tile multiple); their gradient is zero
 __global__ void __launch_bounds__(THREADS) ce_bwd_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restrict__ labels,
                                                          const float* __restrict__ lse, const float* __restrict__ scale_ptr, int V,
-                                                         long long ld, long long ignore_index) {
+                                                         int V_alloc, long long ld, long long ignore_index) {
     const int row = blockIdx.x;
     __nv_bfloat16* x = logits + (size_t)row * ld;
     const long long lab = labels[row];
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(THREADS) ce_bwd_kernel(__nv_bfloat16* __restri
         const float p = __expf(__bfloat162float(x[i]) - l);
         x[i] = __float2bfloat16_rn(g * (p - ((long long)i == lab ? 1.f : 0.f)));
     }
+    for (int i = V + threadIdx.x; i < V_alloc; i += THREADS) x[i] = __float2bfloat16_rn(0.f);
 }
 
 }  // namespace ce
@@ -106,10 +108,10 @@ extern "C" int v6_ce_fwd(const void* logits, const long long* labels, float* lse
     return 0;
 }
 
-extern "C" int v6_ce_bwd(void* logits, const long long* labels, const float* lse, const float* scale_ptr, int T, int V, long long ld,
-                         long long ignore_index, cudaStream_t s) {
-    if (T < 1 || V < 1 || ld % 8 != 0) return (int)cudaErrorInvalidValue;
-    ce::ce_bwd_kernel<<<T, ce::THREADS, 0, s>>>((__nv_bfloat16*)logits, labels, lse, scale_ptr, V, ld, ignore_index);
+extern "C" int v6_ce_bwd(void* logits, const long long* labels, const float* lse, const float* scale_ptr, int T, int V, int V_alloc,
+                         long long ld, long long ignore_index, cudaStream_t s) {
+    if (T < 1 || V < 1 || ld % 8 != 0 || V_alloc < V || V_alloc > ld) return (int)cudaErrorInvalidValue;
+    ce::ce_bwd_kernel<<<T, ce::THREADS, 0, s>>>((__nv_bfloat16*)logits, labels, lse, scale_ptr, V, V_alloc, ld, ignore_index);
     V6_CHECK_LAUNCH();
     return 0;
 }

@@ -224,8 +224,8 @@ PYBIND11_MODULE(_C, m) {
     m.def("ce_fwd", [](u64 logits, u64 labels, u64 lse, u64 loss, int T, int V, long long ld, long long ignore_index, u64 s) {
         check(v6_ce_fwd(P<void>(logits), P<long long>(labels), P<float>(lse), P<float>(loss), T, V, ld, ignore_index, S(s)), "ce_fwd");
     });
-    m.def("ce_bwd", [](u64 logits, u64 labels, u64 lse, u64 scale, int T, int V, long long ld, long long ignore_index, u64 s) {
-        check(v6_ce_bwd(P<void>(logits), P<long long>(labels), P<float>(lse), P<float>(scale), T, V, ld, ignore_index, S(s)), "ce_bwd");
+    m.def("ce_bwd", [](u64 logits, u64 labels, u64 lse, u64 scale, int T, int V, int V_alloc, long long ld, long long ignore_index, u64 s) {
+        check(v6_ce_bwd(P<void>(logits), P<long long>(labels), P<float>(lse), P<float>(scale), T, V, V_alloc, ld, ignore_index, S(s)), "ce_bwd");
     });
     m.def("bn_pool_fwd", [](u64 x, u64 scale, u64 bias, u64 p, u64 idx, int N, int H, int W, int C, u64 s) {
         check(v6_bn_pool_fwd(P<void>(x), P<float>(scale), P<float>(bias), P<void>(p), P<void>(idx), N, H, W, C, S(s)), "bn_pool_fwd");
