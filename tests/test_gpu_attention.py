@@ -121,13 +121,13 @@ def test_packed_qkv_attention_forward_backward(dev, variant, monkeypatch):
     assert (qkv.grad.float() - ref.grad).abs().max().item() < 6e-2
 
 
-@pytest.mark.skipif(__import__("os").environ.get("V6B200_EXPERIMENTAL") != "1", reason="set V6B200_EXPERIMENTAL=1")
+@pytest.mark.parametrize("mode", ["mn", "t"])
 @pytest.mark.parametrize("B,S,Hq,Hkv,D,causal", [(2, 256, 12, 12, 64, False), (1, 1024, 8, 2, 128, True), (1, 200, 2, 2, 64, True)])
-def test_experimental_attention_v_in_place(dev, B, S, Hq, Hkv, D, causal, monkeypatch):
-    """Opt-in (not validated on hardware yet): V consumed in its natural layout as an MN-major UMMA operand."""
+def test_attention_v_in_place_and_transposed(dev, B, S, Hq, Hkv, D, causal, mode, monkeypatch):
+    """V consumed in its natural layout as an MN-major UMMA operand (default) and through the transposed copy (V6B200_ATTN_V=t)."""
     from vantage6_b200.ops import attention as A
 
-    monkeypatch.setenv("V6B200_ATTN_V", "mn")
+    monkeypatch.setenv("V6B200_ATTN_V", mode)
     torch.manual_seed(7)
     q = torch.randn(B, S, Hq, D, device=dev, dtype=torch.bfloat16)
     k = torch.randn(B, S, Hkv, D, device=dev, dtype=torch.bfloat16)

@@ -49,8 +49,9 @@ def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
     o = torch.empty((B, S, Hq, D), device=q.device, dtype=q.dtype)
     lse = torch.empty(B, Hq, S, device=q.device, dtype=torch.float32)
     count(1)
-    if os.environ.get("V6B200_ATTN_V") == "mn" and _fwd_variant(variant) == "2cta" and hasattr(native(), "flash_attn_fwd2_vmn"):
-        # opt-in, unvalidated: V consumed in place as an MN-major UMMA operand (no Vt copy)
+    if os.environ.get("V6B200_ATTN_V", "mn") == "mn" and _fwd_variant(variant) == "2cta" and hasattr(native(), "flash_attn_fwd2_vmn"):
+        # default: V consumed in place as an MN-major UMMA operand -- no Vt copy (validated on hardware in round 2: S = 128:
+        # 28.7 vs 45.3 us, causal 2048 x 128: 0.350 vs 0.386 ms, BERT-base round 27.6 vs 28.3 ms; V6B200_ATTN_V=t: transposed copy)
         v, ldv = _token_strided(v)
         native().flash_attn_fwd2_vmn(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(), B, S, Hq, Hkv, D,
                                      ldq, ldk, ldv, float(scale), bool(causal), stream_ptr())
