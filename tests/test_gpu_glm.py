@@ -60,19 +60,15 @@ def test_glm_kernel_timing(monkeypatch, capsys):
               f"({512e6 / tc / 1e6:.0f} GB/s of X)")
 
 
-@opt_in
-def test_experimental_fused_glm_iteration(monkeypatch):
-    """Opt-in (not validated on hardware yet): gradient kernel + one fold / all-reduce / update kernel == the default path."""
+def test_fused_glm_iteration_matches_composed_path(monkeypatch):
+    """Gradient kernel + one fold / all-reduce / update kernel (default) == the composed path (V6B200_GLM_FUSED=0)."""
     from vantage6_b200.models.glm import FederatedGLM, synthetic_glm_shard
 
     dev = torch.device("cuda", 0)
     X, y, _ = synthetic_glm_shard(20_000, 256, seed=3, device=dev, dtype=torch.bfloat16)
 
     def run(fused):
-        if fused:
-            monkeypatch.setenv("V6B200_GLM_FUSED", "1")
-        else:
-            monkeypatch.delenv("V6B200_GLM_FUSED", raising=False)
+        monkeypatch.setenv("V6B200_GLM_FUSED", "1" if fused else "0")
         glm = FederatedGLM(X, y, 0, 1, lr=1.0)
         losses = [float(glm.step().item()) for _ in range(5)]
         w = glm.w.clone()
