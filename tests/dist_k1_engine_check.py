@@ -11,6 +11,7 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("V6B200_LINEAR_BWD", "cublas")       # deterministic filter gradients: the two runs are compared closely
+os.environ.setdefault("V6B200_LINEAR_FWD", "gemm")         # both runs on csrc/gemm.cu (the K1 kernel is that kernel): bit-comparable
 
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
