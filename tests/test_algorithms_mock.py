@@ -173,3 +173,28 @@ def test_peer_channel_single_node_cpu():
     assert out.tolist() == [5.0, 10.0, 15.0]
     ch.barrier()
     ch.close()
+
+
+def test_fedavg_confines_researcher_paths(tmp_path, monkeypatch):
+    """checkpoint_dir / resume_from / metrics_file arrive in the task input: they may only point into the directories the node
+    set aside for algorithms (per-run temporary folder, log directory, V6_ALGORITHM_DATA_DIR)."""
+    import pytest
+
+    from vantage6_b200.algorithm.builtin import fedavg
+
+    run_dir, log_dir = tmp_path / "run", tmp_path / "log"
+    run_dir.mkdir()
+    log_dir.mkdir()
+    monkeypatch.setenv("TEMPORARY_FOLDER", str(run_dir))
+    monkeypatch.setenv("V6_LOG_DIR", str(log_dir))
+    assert fedavg._confined("ckpt", "checkpoint_dir") == str(run_dir / "ckpt")                 # relative: inside the run folder
+    assert fedavg._confined(str(log_dir / "m.jsonl"), "metrics_file") == str(log_dir / "m.jsonl")
+    with pytest.raises(PermissionError):
+        fedavg._confined("/etc/cron.d/x", "metrics_file")
+    with pytest.raises(PermissionError):
+        fedavg._confined(str(run_dir / ".." / "escape"), "checkpoint_dir")
+    with pytest.raises(PermissionError):
+        fedavg.train_partial(None, model="resnet_tiny", rounds=1, checkpoint_dir="/root/elsewhere")
+    out = fedavg.train_partial(None, model="resnet_tiny", rounds=2, local_steps=1, batch=4, checkpoint_every=1, checkpoint_dir="ckpt",
+                               metrics_file=str(log_dir / "m.jsonl"))
+    assert len(out["losses"]) == 2 and (run_dir / "ckpt").is_dir() and (log_dir / "m.jsonl").exists()

@@ -61,6 +61,24 @@ def master(client, data, model: str = "resnet_tiny", rounds: int = 2, local_step
     return out
 
 
+def _confined(path: Optional[str], what: str) -> Optional[str]:
+    """Task inputs come from researchers: a path they name (checkpoints, metrics) may only point into directories the node
+    set aside for algorithms -- its per-run temporary folder, its log directory, or ``V6_ALGORITHM_DATA_DIR`` (a colon-separated
+    list the node operator adds).  Relative paths are taken inside the first of them.  Anything else is refused (the reference
+    confines algorithms to container mounts: reference vantage6/cli/node.py:360-378)."""
+    if not path:
+        return None
+    roots = [os.path.realpath(r) for r in (os.environ.get("TEMPORARY_FOLDER"), os.environ.get("V6_LOG_DIR"),
+                                           *(os.environ.get("V6_ALGORITHM_DATA_DIR", "").split(os.pathsep))) if r]
+    if not roots:
+        raise PermissionError(f"{what}: the node exported no directory an algorithm may write to")
+    p = path if os.path.isabs(path) else os.path.join(roots[0], path)
+    real = os.path.realpath(p)
+    if not any(real == r or real.startswith(r + os.sep) for r in roots):
+        raise PermissionError(f"{what}={path!r} is outside the directories this node allows algorithms to use")
+    return real
+
+
 def RPC_train(data, **kwargs) -> Dict[str, Any]:
     """Node-side partial.  On a node with a resident GPU worker (``vnode start --gpu K``, node/gpu_worker.py) the
     request is forwarded to it -- CUDA context, symmetric heap, model and CUDA graphs live there across tasks --
@@ -89,6 +107,9 @@ def train_partial(data, model: str = "resnet_tiny", rounds: int = 2, local_steps
     import torch
     import torch.distributed as dist
 
+    checkpoint_dir = _confined(checkpoint_dir, "checkpoint_dir")
+    resume_from = _confined(resume_from, "resume_from")
+    metrics_file = _confined(metrics_file, "metrics_file")
     from ...models import zoo
     from ...parallel.fedavg import ServerOptConfig
     from ...utils.metrics import MetricsWriter
