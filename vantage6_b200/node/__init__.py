@@ -331,6 +331,11 @@ class Node:
         env = {k: v for k, v in os.environ.items()
                if (k in self.ENV_PASSTHROUGH or k.startswith(self.ENV_PREFIXES)) and k not in self.ENV_BLOCKED}
         env["V6B200_ALLOW_PICKLE"] = "1" if self.config.get("allow_pickle") else "0"
+        # directories (besides the per-run temporary folder and the log directory) that task inputs may name for checkpoints /
+        # metrics: node config ``algorithm_data_dirs`` or the operator's V6_ALGORITHM_DATA_DIR (algorithm/builtin/fedavg.py::_confined)
+        extra = list(self.config.get("algorithm_data_dirs") or []) + [d for d in os.environ.get("V6_ALGORITHM_DATA_DIR", "").split(os.pathsep) if d]
+        if extra:
+            env["V6_ALGORITHM_DATA_DIR"] = os.pathsep.join(str(d) for d in extra)
         log_dir = getattr(self.ctx, "log_dir", None)
         if log_dir:
             env["V6_LOG_DIR"] = str(log_dir)
