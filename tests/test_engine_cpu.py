@@ -471,3 +471,18 @@ def test_engine_shard_alignment():
     e._reshard()
     assert e.lo % 256 == 0 and e.hi % 256 == 0 and e.hi > e.lo
     assert e.k1_layer(0, 256, 8) is None               # no NVLink data plane on the CPU: K2 keeps pushing everything
+
+
+def test_trainer_bcast_fused_is_a_noop_without_the_nvlink_plane():
+    """bcast="fused" (K1 on the engine path) needs the NVLink data plane + multicast: on the CPU / collective plane the trainer
+    runs the plain path (no K1 layers, no skipped shadow range) and trains as usual."""
+    from vantage6_b200.models import zoo
+
+    tr, spec = zoo.build_trainer("bert_tiny", rank=0, world=1, device="cpu", bcast="fused")
+    assert tr.k1_layers == 0 and tr.engine.shadow_skip == (0, 0)
+    tr.initialize_global()
+    batches = spec.make_batches(2, 4, 3)
+    l0 = float(tr.run_round(batches).item())
+    l1 = float(tr.run_round(batches).item())
+    assert l1 < l0
+    tr.close()
