@@ -434,3 +434,7 @@ def remove_file(file: str, file_type: str):
     except Exception as e:  # noqa: BLE001
         error(f"Could not delete file: {file}")
         error(e)
+
+
+if __name__ == "__main__":
+    cli_node()
