@@ -312,3 +312,163 @@ def test_websocket_event_channel_pushes_and_authorises(server):
     with connect(f"ws://127.0.0.1:{ws_port}/?token=garbage") as bad:
         with pytest.raises(ConnectionClosed):
             bad.recv(timeout=5)
+
+
+def test_role_management_and_its_grant_check(server):
+    """Custom roles: an Organization Admin builds roles for its own organization out of rules it holds itself; default
+    roles are read-only for it; another organization's roles are invisible; nothing it lacks can be put into a role."""
+    app, port = server
+    alice = user(port, "alice", "pw-a")
+    roles = {r["name"]: r["id"] for r in alice.role.list()}
+    alice.user.create("dan", "pw-d", organization=2, roles=[roles["Organization Admin"]])
+    dan = user(port, "dan", "pw-d")
+    rules = alice.rule.list()
+    pick = lambda name, op, scope: next(r["id"] for r in rules if (r["name"], r["operation"], r["scope"]) == (name, op, scope))  # noqa: E731
+    assert alice.rule.get(pick("task", "view", "organization"))["name"] == "task"
+    role = dan.role.create("Task watcher", "sees the tasks", rules=[pick("task", "view", "organization")])
+    assert role["organization_id"] == 2 and len(role["rules"]) == 1
+    with pytest.raises(ServerError) as e:            # a rule dan does not hold
+        dan.role.create("Sneaky", rules=[pick("collaboration", "delete", "global")])
+    assert e.value.status == 401
+    with pytest.raises(ServerError) as e:
+        dan.role.add_rule(role["id"], pick("task", "view", "global"))
+    assert e.value.status == 401
+    with pytest.raises(ServerError) as e:            # another organization
+        dan.role.create("Elsewhere", organization=1)
+    assert e.value.status == 401
+    with pytest.raises(ServerError) as e:            # default roles stay as they are
+        dan.role.update(roles["Viewer"], name="Hacked")
+    assert e.value.status == 401
+    dan.role.add_rule(role["id"], pick("result", "view", "organization"))
+    assert {r["name"] for r in dan.role.rules(role["id"])} == {"task", "result"}
+    dan.role.remove_rule(role["id"], pick("result", "view", "organization"))
+    upd = dan.role.update(role["id"], description="only tasks", rules=[pick("task", "view", "organization"), pick("node", "view", "organization")])
+    assert upd["description"] == "only tasks" and len(upd["rules"]) == 2
+    # the role works: erin holds nothing but it
+    dan.user.create("erin", "pw-e", organization=2, roles=[role["id"]])
+    erin = user(port, "erin", "pw-e")
+    assert erin.task.list() == [] and {n["organization"]["id"] for n in erin.node.list()} == {2}
+    with pytest.raises(ServerError):
+        erin.user.create("x", "y")
+    # bob (organization 2) sees it, carol (organization 3) does not, alice (global) does
+    assert role["id"] in {r["id"] for r in user(port, "bob", "pw-b").role.list()}
+    carol = user(port, "carol", "pw-c")
+    assert role["id"] not in {r["id"] for r in carol.role.list()}
+    with pytest.raises(ServerError):
+        carol.role.get(role["id"])
+    assert alice.role.get(role["id"])["users"][0]["id"] == erin.whoami.id_
+    # deletion: refused while assigned, unless the dependents are dropped too; default roles never
+    with pytest.raises(ServerError) as e:
+        dan.role.delete(role["id"])
+    assert e.value.status == 400
+    with pytest.raises(ServerError) as e:
+        alice.role.delete(roles["Viewer"])
+    assert e.value.status == 400
+    dan.role.delete(role["id"], delete_dependents=True)
+    assert erin.user.get()["roles"] == []
+    with pytest.raises(ServerError) as e:
+        alice.role.get(role["id"])
+    assert e.value.status == 404
+
+
+def test_password_change_recovery_and_lockout():
+    app = ServerApp({"uri": "sqlite://", "api_path": "/api", "jwt_secret_key": "s" * 40,
+                     "password_policy": {"max_failed_attempts": 3, "inactivation_minutes": 10, "min_length": 6}})
+    port = app.start("127.0.0.1", 0)
+    try:
+        root = user(port, "root", "root")
+        root.user.update(email="root@a.test")
+        with pytest.raises(ServerError) as e:
+            root.util.change_my_password("wrong", "new-password")
+        assert e.value.status == 401
+        with pytest.raises(ServerError) as e:
+            root.util.change_my_password("root", "short")
+        assert e.value.status == 400
+        root.util.change_my_password("root", "new-password")
+        with pytest.raises(ServerError):
+            user(port, "root", "root")
+        user(port, "root", "new-password")
+        # recovery: same reply whether or not the account exists; the token works once
+        anon = UserClient("http://127.0.0.1", port, "/api")
+        assert anon.util.reset_my_password(username="nobody") == anon.util.reset_my_password(email="root@a.test")
+        assert len(app.outbox) == 1 and app.outbox[0]["username"] == "root"
+        token = app.outbox[0]["reset_token"]
+        with pytest.raises(ServerError) as e:
+            anon.util.set_my_password(token + "x", "another-password")
+        assert e.value.status == 401
+        access = user(port, "root", "new-password").token
+        with pytest.raises(ServerError):                       # an access token is not a reset token
+            anon.util.set_my_password(access, "another-password")
+        anon.util.set_my_password(token, "another-password")
+        user(port, "root", "another-password")
+        with pytest.raises(ServerError) as e:                  # bound to the password it was issued for
+            anon.util.set_my_password(token, "third-password")
+        assert e.value.status == 401
+        # lockout after three failures, even with the right password; the recovery path reopens the account
+        for _ in range(3):
+            with pytest.raises(ServerError):
+                user(port, "root", "guess")
+        with pytest.raises(ServerError) as e:
+            user(port, "root", "another-password")
+        assert "blocked" in e.value.msg
+        anon.util.reset_my_password(username="root")
+        anon.util.set_my_password(app.outbox[-1]["reset_token"], "fourth-password")
+        user(port, "root", "fourth-password")
+    finally:
+        app.stop()
+
+
+def test_membership_sub_resources(server):
+    app, port = server
+    alice, bob, carol = user(port, "alice", "pw-a"), user(port, "bob", "pw-b"), user(port, "carol", "pw-c")
+    assert [o["id"] for o in alice.collaboration.add_organization(1, 3)] == [1, 2, 3]
+    with pytest.raises(ServerError) as e:
+        bob.collaboration.add_organization(1, 3)
+    assert e.value.status == 401
+    assert [c["name"] for c in carol.organization.collaborations()] == ["AB"]
+    node = alice.node.create(1, 3)
+    assert [n["id"] for n in alice.organization.nodes(3)] == [node["id"]]
+    with pytest.raises(ServerError) as e:            # a member with a node cannot be dropped
+        alice.collaboration.remove_organization(1, 3)
+    assert e.value.status == 400
+    # detach: the node keeps its key but cannot log in; attach it again and it can
+    assert node["id"] not in [n["id"] for n in alice.collaboration.remove_node(1, node["id"])]
+    nc = NodeClient("http://127.0.0.1", port, "/api")
+    with pytest.raises(ServerError) as e:
+        nc.authenticate(node["api_key"])
+    assert e.value.status == 401
+    assert alice.node.get(node["id"])["collaboration"] is None
+    assert node["id"] in [n["id"] for n in alice.collaboration.add_node(1, node["id"])]
+    nc.authenticate(node["api_key"])
+    # tasks of a node
+    t = alice.task.create(collaboration=1, organizations=[1, 3], name="t", image="img", input={"method": "m"})
+    assert [x["id"] for x in alice.node.tasks(node["id"])] == [t["id"]]
+    assert [x["id"] for x in alice.node.tasks(node["id"], open_only=True)] == [t["id"]]
+    assert [x["id"] for x in nc.request(f"node/{node['id']}/task")] == [t["id"]]
+    b_node = next(n for n in alice.node.list() if n["organization"]["id"] == 2)
+    assert alice.node.tasks(b_node["id"]) == []
+    with pytest.raises(ServerError):                 # a node asks about itself only, unless it shares the collaboration view
+        UserClient("http://127.0.0.1", port, "/api").request(f"node/{node['id']}/task")
+    alice.node.delete(node["id"])
+    assert [o["id"] for o in alice.collaboration.remove_organization(1, 3)] == [1, 2]
+    assert carol.organization.collaborations() == []
+
+
+def test_signing_key_is_kept_with_the_database(tmp_path):
+    """Without ``jwt_secret_key`` two processes on one database (a restarted server, ``vserver shell``) share the key:
+    an operator-minted reset token is accepted by the running server."""
+    from vantage6_b200.server.admin_routes import issue_reset_token
+
+    cfg = {"uri": f"sqlite:///{tmp_path}/s.sqlite", "api_path": "/api"}
+    app = ServerApp(cfg)
+    port = app.start("127.0.0.1", 0)
+    try:
+        shell = ServerApp(cfg)                                    # what `vserver shell` builds
+        assert shell.secret == app.secret and len(app.secret) == 64
+        token = issue_reset_token(shell, "root")
+        UserClient("http://127.0.0.1", port, "/api").util.set_my_password(token, "better-password")
+        user(port, "root", "better-password")
+        with pytest.raises(KeyError):
+            issue_reset_token(shell, "nobody")
+    finally:
+        app.stop()

@@ -91,8 +91,10 @@ def shell(config, environment):
     """Interactive python shell with ``app`` and ``db`` bound (IPython is not required)."""
     ctx = _ctx(config, environment)
     app = _make_app(ctx)
-    banner = f"vantage6-b200 server shell ({ctx.name}); objects: app, db, ctx"
-    code.interact(banner=banner, local={"app": app, "db": app.db, "ctx": ctx})
+    from ..server.admin_routes import issue_reset_token
+
+    banner = f"vantage6-b200 server shell ({ctx.name}); objects: app, db, ctx; reset_token(username) mints a password reset token"
+    code.interact(banner=banner, local={"app": app, "db": app.db, "ctx": ctx, "reset_token": lambda username: issue_reset_token(app, username)})
 
 
 @cli_server_local.command(name="version")

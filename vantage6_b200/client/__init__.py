@@ -198,6 +198,18 @@ class UserClient(ClientBase):
         def get_server_health(self) -> dict:
             return self.parent.request("health")
 
+        def change_my_password(self, current_password: str, new_password: str) -> dict:
+            return self.parent.request("password/change", method="patch",
+                                       json={"current_password": current_password, "new_password": new_password})
+
+        def reset_my_password(self, email: Optional[str] = None, username: Optional[str] = None) -> dict:
+            """Ask for a reset token (mailed, or handed out by the server's operator); no authentication needed."""
+            assert email or username, "You need to provide username or email!"
+            return self.parent.request("recover/lost", method="post", json={"username": username, "email": email})
+
+        def set_my_password(self, token: str, password: str) -> dict:
+            return self.parent.request("recover/reset", method="post", json={"reset_token": token, "password": password})
+
     class Collaboration(SubClient):
         def list(self) -> List[dict]:
             return self.parent.request("collaboration")
@@ -215,6 +227,27 @@ class UserClient(ClientBase):
         def delete(self, id_: int) -> dict:
             return self.parent.request(f"collaboration/{id_}", method="delete")
 
+        def organizations(self, id_: int) -> List[dict]:
+            return self.parent.request(f"collaboration/{id_}/organization")
+
+        def nodes(self, id_: int) -> List[dict]:
+            return self.parent.request(f"collaboration/{id_}/node")
+
+        def tasks(self, id_: int) -> List[dict]:
+            return self.parent.request(f"collaboration/{id_}/task")
+
+        def add_organization(self, id_: int, organization: int) -> List[dict]:
+            return self.parent.request(f"collaboration/{id_}/organization", method="post", json={"id": organization})
+
+        def remove_organization(self, id_: int, organization: int) -> List[dict]:
+            return self.parent.request(f"collaboration/{id_}/organization", method="delete", json={"id": organization})
+
+        def add_node(self, id_: int, node: int) -> List[dict]:
+            return self.parent.request(f"collaboration/{id_}/node", method="post", json={"id": node})
+
+        def remove_node(self, id_: int, node: int) -> List[dict]:
+            return self.parent.request(f"collaboration/{id_}/node", method="delete", json={"id": node})
+
     class Organization(SubClient):
         def list(self) -> List[dict]:
             return self.parent.request("organization")
@@ -229,6 +262,14 @@ class UserClient(ClientBase):
         def update(self, id_: Optional[int] = None, **fields) -> dict:
             id_ = id_ if id_ is not None else self.parent.whoami.organization_id
             return self.parent.request(f"organization/{id_}", method="patch", json=fields)
+
+        def collaborations(self, id_: Optional[int] = None) -> List[dict]:
+            id_ = id_ if id_ is not None else self.parent.whoami.organization_id
+            return self.parent.request(f"organization/{id_}/collaboration")
+
+        def nodes(self, id_: Optional[int] = None) -> List[dict]:
+            id_ = id_ if id_ is not None else self.parent.whoami.organization_id
+            return self.parent.request(f"organization/{id_}/node")
 
     class User(SubClient):
         def list(self) -> List[dict]:
@@ -255,9 +296,39 @@ class UserClient(ClientBase):
         def list(self) -> List[dict]:
             return self.parent.request("role")
 
+        def get(self, id_: int) -> dict:
+            return self.parent.request(f"role/{id_}")
+
+        def create(self, name: str, description: str = "", rules: List[int] = (), organization: Optional[int] = None) -> dict:
+            """A role in ``organization`` (default: your own) holding ``rules`` -- only rules you hold yourself."""
+            body = {"name": name, "description": description, "rules": list(rules)}
+            if organization is not None:
+                body["organization_id"] = organization
+            return self.parent.request("role", method="post", json=body)
+
+        def update(self, id_: int, **fields) -> dict:
+            """``name``, ``description`` and / or ``rules`` (the full new list of rule ids)."""
+            return self.parent.request(f"role/{id_}", method="patch", json=fields)
+
+        def delete(self, id_: int, delete_dependents: bool = False) -> dict:
+            return self.parent.request(f"role/{id_}", method="delete",
+                                       params={"delete_dependents": "true"} if delete_dependents else None)
+
+        def rules(self, id_: int) -> List[dict]:
+            return self.parent.request(f"role/{id_}/rule")
+
+        def add_rule(self, id_: int, rule: int) -> dict:
+            return self.parent.request(f"role/{id_}/rule/{rule}", method="post")
+
+        def remove_rule(self, id_: int, rule: int) -> dict:
+            return self.parent.request(f"role/{id_}/rule/{rule}", method="delete")
+
     class Rule(SubClient):
         def list(self) -> List[dict]:
             return self.parent.request("rule")
+
+        def get(self, id_: int) -> dict:
+            return self.parent.request(f"rule/{id_}")
 
     class Node(SubClient):
         def list(self) -> List[dict]:
@@ -276,6 +347,9 @@ class UserClient(ClientBase):
 
         def delete(self, id_: int) -> dict:
             return self.parent.request(f"node/{id_}", method="delete")
+
+        def tasks(self, id_: int, open_only: bool = False) -> List[dict]:
+            return self.parent.request(f"node/{id_}/task", params={"state": "open"} if open_only else None)
 
     class Task(SubClient):
         def list(self, **filters) -> List[dict]:

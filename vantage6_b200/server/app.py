@@ -4,7 +4,8 @@ reference vantage6/cli/server.py:223-228; resources per SURVEY.md Appendix C).
 
 * JSON REST resources under ``api_path``: ``/token/{user,node,container,refresh}``,
   ``/organization``, ``/collaboration``, ``/node``, ``/user``, ``/role``, ``/rule``, ``/task``,
-  ``/result``, ``/health``, ``/version``, ``/event``.
+  ``/result``, ``/health``, ``/version``, ``/event``; role management, ``/recover/{lost,reset}``,
+  ``/password/change`` and the membership sub-resources live in ``admin_routes.py``.
 * JWT identities of three kinds (user, node, container) signed with ``jwt_secret_key``.
 * Rule-based permissions: rule = (resource, scope in {own, organization, collaboration, global},
   operation in {view, create, edit, delete}); default roles are created on first start.
@@ -33,6 +34,7 @@ from urllib.parse import parse_qs, urlsplit
 import jwt
 
 from .._version import __version__
+from . import admin_routes
 from .db import Database, check_password, hash_password, now
 
 log = logging.getLogger("server")
@@ -280,7 +282,7 @@ class ServerApp:
     def node_json(self, n: dict, with_key: bool = False) -> dict:
         out = {"id": n["id"], "name": n["name"], "ip": n["ip"], "status": n["status"], "last_seen": n["last_seen"],
                "gpu": n.get("gpu"), "type": "node",
-               "collaboration": self.link("collaboration", n["collaboration_id"]),
+               "collaboration": self.link("collaboration", n["collaboration_id"]) if n["collaboration_id"] is not None else None,
                "organization": self.link("organization", n["organization_id"])}
         if with_key:
             out["api_key"] = n["api_key"]
@@ -370,9 +372,18 @@ class ServerApp:
             if not username or not password:
                 raise HTTPError(400, "Username and/or password missing in JSON body")
             u = db.one("SELECT * FROM user WHERE username=?", (username,))
+            policy = app.config.get("password_policy") or {}
+            max_failed, lock_min = int(policy.get("max_failed_attempts", 5)), float(policy.get("inactivation_minutes", 15))
+            if u is not None and (u["failed_login_attempts"] or 0) >= max_failed and u.get("last_login_attempt"):
+                since = (_dt.datetime.now(_dt.timezone.utc) - _dt.datetime.fromisoformat(u["last_login_attempt"])).total_seconds()
+                if since < lock_min * 60:
+                    raise HTTPError(401, f"Your account is blocked for the next {max(1, int(lock_min - since / 60))} minutes due to failed "
+                                         "login attempts. Please wait or reactivate your account via the password recovery.")
+                db.update("user", u["id"], failed_login_attempts=0)
+                u["failed_login_attempts"] = 0
             if u is None or not check_password(password, u["password"]):
                 if u is not None:
-                    db.update("user", u["id"], failed_login_attempts=(u["failed_login_attempts"] or 0) + 1)
+                    db.update("user", u["id"], failed_login_attempts=(u["failed_login_attempts"] or 0) + 1, last_login_attempt=now())
                 raise HTTPError(401, "Invalid username or password!")
             db.update("user", u["id"], last_seen=now(), failed_login_attempts=0)
             ident_ = {"id": u["id"], "organization_id": u["organization_id"]}
@@ -387,6 +398,8 @@ class ServerApp:
             n = db.one("SELECT * FROM node WHERE api_key=?", (key,))
             if n is None:
                 raise HTTPError(401, "Api key is not recognized!")
+            if n["collaboration_id"] is None:
+                raise HTTPError(401, "This node is not attached to a collaboration")
             db.update("node", n["id"], last_seen=now(), status="online", ip=body.get("ip"), gpu=body.get("gpu"))
             ident_ = {"id": n["id"], "organization_id": n["organization_id"], "collaboration_id": n["collaboration_id"]}
             app.events.emit("node-status-changed", {"id": n["id"], "name": n["name"], "online": True},
@@ -722,12 +735,11 @@ class ServerApp:
 
         @app.route("GET", "/role")
         def role_list(ident, body, q):
-            app.require(ident, "user")
-            out = []
-            for r in db.query("SELECT * FROM role ORDER BY id"):
-                rules = db.query("SELECT rule_id FROM role_rule WHERE role_id=?", (r["id"],))
-                out.append({**r, "rules": [app.link("rule", x["rule_id"]) for x in rules]})
-            return out
+            """Default roles plus the roles of the caller's organization (every role with global ``role view`` scope)."""
+            ident = app.require(ident, "user")
+            everything = app.scope_of(ident, "role", "view") == "global"
+            return [admin_routes.role_json(app, r) for r in db.query("SELECT * FROM role ORDER BY id")
+                    if everything or r["organization_id"] in (None, ident["organization_id"])]
 
         @app.route("GET", "/rule")
         def rule_list(ident, body, q):
@@ -905,6 +917,8 @@ class ServerApp:
             rooms = app.event_rooms(ident, q.get("task_id"))
             evs = app.events.wait(since, rooms, timeout)
             return {"events": evs, "last_id": evs[-1]["id"] if evs else since}
+
+        admin_routes.register(app)          # roles / rules, account recovery, membership sub-resources
 
     # ------------------------------------------------------------------ http plumbing
     def make_handler(self):

@@ -54,6 +54,7 @@ CREATE TABLE IF NOT EXISTS task (
 CREATE TABLE IF NOT EXISTS result (
   id INTEGER PRIMARY KEY AUTOINCREMENT, task_id INTEGER, organization_id INTEGER, input TEXT, result TEXT,
   log TEXT, assigned_at TEXT, started_at TEXT, finished_at TEXT, status TEXT DEFAULT 'pending');
+CREATE TABLE IF NOT EXISTS setting (key TEXT PRIMARY KEY, value TEXT);
 CREATE INDEX IF NOT EXISTS idx_result_task ON result(task_id);
 CREATE INDEX IF NOT EXISTS idx_result_org ON result(organization_id);
 """
@@ -110,6 +111,17 @@ class Database:
         self._conn.execute("PRAGMA synchronous=NORMAL")
         with self._lock:
             self._conn.executescript(SCHEMA)
+            self._migrate()
+
+    # columns added after the first release: an existing database file gains them on open
+    MIGRATIONS = {"user": {"last_login_attempt": "TEXT"}}
+
+    def _migrate(self) -> None:
+        for table, columns in self.MIGRATIONS.items():
+            have = {r["name"] for r in self._conn.execute(f"PRAGMA table_info({table})").fetchall()}
+            for col, decl in columns.items():
+                if col not in have:
+                    self._conn.execute(f"ALTER TABLE {table} ADD COLUMN {col} {decl}")
 
     # -- primitives --------------------------------------------------------------------------
     def execute(self, sql: str, args: Iterable = ()) -> sqlite3.Cursor:
@@ -160,6 +172,7 @@ class Database:
             for t in TABLES:
                 self._conn.execute(f"DROP TABLE IF EXISTS {t}")
             self._conn.executescript(SCHEMA)
+            self._migrate()
 
     def close(self) -> None:
         with self._lock:
@@ -194,5 +207,11 @@ class Database:
             (user_id, user_id))
 
     def token_secret(self, configured: Optional[str]) -> str:
-        """JWT secret: the configured constant (``jwt_secret_key``) or a per-database random one."""
-        return configured or secrets.token_hex(32)
+        """JWT secret: the configured constant (``jwt_secret_key``) or a random one kept with the database, so that
+        tokens outlive a server restart and a second process on the same database (``vserver shell``, a second server
+        behind the message queue) signs and verifies with the same key.  ``drop_all`` does not touch it."""
+        if configured:
+            return configured
+        with self._lock:
+            self._conn.execute("INSERT OR IGNORE INTO setting VALUES ('jwt_secret_key', ?)", (secrets.token_hex(32),))
+            return self._conn.execute("SELECT value FROM setting WHERE key='jwt_secret_key'").fetchone()[0]
