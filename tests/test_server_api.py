@@ -114,6 +114,22 @@ def test_task_lifecycle_with_node_and_container_identities(server):
     assert [o["name"] for o in cc.get_organizations_in_my_collaboration()] == ["A", "B"]
     assert [a["rank"] for a in cc.get_algorithm_addresses(sub["id"])] == [0, 1]
 
+    # address book: the node registers where the algorithm of its sub-task result listens; siblings of the run see it
+    sub_rid = [r["id"] for r in node.request("result", params={"task_id": sub["id"]}) if r["organization"]["id"] == 1][0]
+    reg = node.request("port", method="post", json={"result_id": sub_rid, "port": 29617, "label": "rendezvous"})
+    assert reg["node_id"] == node.node_id and reg["gpu"] == 3
+    with pytest.raises(ServerError):                 # another organization's result
+        other_rid = [r["id"] for r in node.request("result", params={"task_id": sub["id"]}) if r["organization"]["id"] == 2][0]
+        node.request("port", method="post", json={"result_id": other_rid, "port": 1})
+    book = cc.get_algorithm_addresses(sub["id"])
+    assert book[0]["ports"] == [{"port": 29617, "label": "rendezvous"}] and book[1]["ports"] == []
+    assert [p["port"] for p in bob.request("port", params={"run_id": task["run_id"]})] == [29617]
+    assert user(port, "carol", "pw-c").request("port", params={"run_id": task["run_id"]}) == []      # not in the collaboration
+    node.request("port", method="delete", params={"result_id": sub_rid})
+    assert bob.request("port") == []
+    spec = {(r["method"], r["path"]) for r in cc.request("spec")}
+    assert {("POST", "/api/port"), ("GET", "/api/role/<id>/rule"), ("PATCH", "/api/result/<id>"), ("POST", "/api/recover/lost")} <= spec
+
     # node reports; a finished result cannot be patched again; other orgs' results are off limits
     node.request(f"result/{rid}", method="patch", json={"started_at": "now"})
     out = DummyCryptor().bytes_to_str(serialize({"answer": 42}))

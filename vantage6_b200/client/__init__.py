@@ -469,10 +469,19 @@ class ContainerClient(ClientBase):
 
     def get_algorithm_addresses(self, task_id: int) -> List[dict]:
         """vantage6's VPN address book; on one NVSwitch box node-to-node traffic is symmetric
-        memory, so the 'address' of a peer algorithm is its rank in the rendezvous."""
+        memory, so the 'address' of a peer algorithm is its rank in the rendezvous.  Ports that the nodes registered
+        for the algorithms of ``task_id`` (``/port``) are listed with the node they belong to."""
         nodes = self.request(f"collaboration/{self.collaboration_id}/node")
-        return [{"rank": i, "node_id": n["id"], "organization_id": n["organization"]["id"], "gpu": n.get("gpu")}
-                for i, n in enumerate(sorted(nodes, key=lambda n: n["id"]))]
+        try:
+            ports = self.request("port", params={"task_id": task_id})
+        except ServerError:
+            ports = []
+        out = []
+        for i, n in enumerate(sorted(nodes, key=lambda n: n["id"])):
+            mine = [p for p in ports if p.get("node_id") == n["id"]]
+            out.append({"rank": i, "node_id": n["id"], "organization_id": n["organization"]["id"], "gpu": n.get("gpu"),
+                        "ip": n.get("ip"), "ports": [{"port": p["port"], "label": p["label"]} for p in mine]})
+        return out
 
 
 __all__ = ["ClientBase", "UserClient", "Client", "ContainerClient", "ServerError", "RSACryptor", "DummyCryptor"]

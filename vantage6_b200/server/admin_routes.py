@@ -11,6 +11,10 @@ SURVEY.md Appendix C).  ``register(app)`` is called from ``ServerApp._register_r
   mint one from ``vserver shell`` with ``reset_token(username)``).
 * ``/collaboration/<id>/organization`` and ``/collaboration/<id>/node`` (``POST`` / ``DELETE``), ``/organization/<id>/
   collaboration``, ``/organization/<id>/node``, ``/node/<id>/task``.
+* ``/port`` -- the address book of running algorithms (vantage6: the VPN ports of algorithm containers): a node registers
+  under which address / port / label the algorithm it runs for a result can be reached by its siblings of the same run.
+  On one NVSwitch box the "address" is the node's GPU and its rank in the run's rendezvous (algorithm/peer.py).
+* ``/spec`` -- the route table itself.
 """
 from __future__ import annotations
 
@@ -361,3 +365,64 @@ def register(app) -> None:  # noqa: C901 -- a flat route table reads best in one
         if q.get("state") == "open":
             sql += " AND result.finished_at IS NULL"
         return [app.task_json(t) for t in db.query(sql + " ORDER BY task.id", (n["collaboration_id"], n["organization_id"]))]
+
+    # ------------------------------------------------------------------ algorithm address book
+    def port_json(p: dict) -> dict:
+        r = db.get("result", p["result_id"])
+        n = None
+        if r is not None:
+            t = db.get("task", r["task_id"])
+            n = db.one("SELECT id, gpu, ip FROM node WHERE organization_id=? AND collaboration_id=?", (r["organization_id"], t["collaboration_id"])) if t else None
+        return {"id": p["id"], "port": p["port"], "label": p["label"], "address": p["address"] or (n or {}).get("ip"),
+                "result": app.link("result", p["result_id"]), "organization_id": r["organization_id"] if r else None,
+                "node_id": n["id"] if n else None, "gpu": n["gpu"] if n else None}
+
+    @app.route("POST", "/port")
+    def port_create(ident, body, q):
+        ident = app.require(ident, "node")
+        for k in ("port", "result_id"):
+            if body.get(k) is None:
+                raise HTTPError(400, f"{k} is required")
+        r = db.get("result", int(body["result_id"]))
+        t = db.get("task", r["task_id"]) if r else None
+        if r is None or t is None:
+            raise HTTPError(404, f"result id={body['result_id']} not found")
+        if r["organization_id"] != ident["organization_id"] or t["collaboration_id"] != ident["collaboration_id"]:
+            raise HTTPError(401, "You lack the permissions to do that")
+        pid = db.insert("port", result_id=r["id"], port=int(body["port"]), label=body.get("label"), address=body.get("address"))
+        return port_json(db.get("port", pid)), 201
+
+    @app.route("GET", "/port")
+    def port_list(ident, body, q):
+        """``?result_id=`` one algorithm, ``?task_id=`` every algorithm of a task, ``?run_id=`` of a whole run."""
+        ident = app.require(ident)
+        sql = ("SELECT port.*, task.collaboration_id AS cid FROM port JOIN result ON result.id = port.result_id "
+               "JOIN task ON task.id = result.task_id WHERE 1=1")
+        args = []
+        for key, col in (("result_id", "port.result_id"), ("task_id", "result.task_id"), ("run_id", "task.run_id")):
+            if key in q:
+                sql += f" AND {col}=?"
+                args.append(int(q[key]))
+        rows = db.query(sql + " ORDER BY port.id", args)
+        return [port_json(p) for p in rows if app.can_view_collaboration(ident, p["cid"], "port")]
+
+    @app.route("DELETE", "/port")
+    def port_delete(ident, body, q):
+        ident = app.require(ident, "node")
+        rid = q.get("result_id", body.get("result_id"))
+        if rid is None:
+            raise HTTPError(400, "result_id is required")
+        r = db.get("result", int(rid))
+        if r is None or r["organization_id"] != ident["organization_id"]:
+            raise HTTPError(401, "You lack the permissions to do that")
+        db.execute("DELETE FROM port WHERE result_id=?", (r["id"],))
+        return {"msg": f"ports of result id={rid} removed"}
+
+    # ------------------------------------------------------------------ the API describes itself
+    @app.route("GET", "/spec")
+    def spec(ident, body, q):
+        out = []
+        for method, rx, fn in app._routes:
+            path = rx.pattern[1:-3].replace("(\\d+)", "<id>")
+            out.append({"method": method, "path": app.api_path + path, "doc": " ".join((fn.__doc__ or "").split()) or None})
+        return sorted(out, key=lambda r: (r["path"], r["method"]))

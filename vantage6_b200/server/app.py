@@ -50,9 +50,9 @@ RESOURCES = ["user", "organization", "collaboration", "role", "node", "task", "r
 
 DEFAULT_ROLES = {
     "Root": ("Super role", [(r, "global", o) for r in RESOURCES for o in OPERATIONS]),
-    "Collaboration Admin": ("Can manage a collaboration", [(r, "collaboration", o) for r in ("organization", "collaboration", "node", "task", "result", "user") for o in OPERATIONS]),
-    "Organization Admin": ("Can manage an organization", [(r, "organization", o) for r in ("user", "organization", "node", "task", "result", "role") for o in OPERATIONS] + [("collaboration", "organization", "view")]),
-    "Researcher": ("Can create tasks and view results", [("task", "organization", "view"), ("task", "organization", "create"), ("result", "organization", "view"), ("organization", "collaboration", "view"), ("collaboration", "organization", "view"), ("node", "organization", "view"), ("user", "organization", "view")]),
+    "Collaboration Admin": ("Can manage a collaboration", [(r, "collaboration", o) for r in ("organization", "collaboration", "node", "task", "result", "user", "port") for o in OPERATIONS]),
+    "Organization Admin": ("Can manage an organization", [(r, "organization", o) for r in ("user", "organization", "node", "task", "result", "role", "port") for o in OPERATIONS] + [("collaboration", "organization", "view")]),
+    "Researcher": ("Can create tasks and view results", [("task", "organization", "view"), ("task", "organization", "create"), ("result", "organization", "view"), ("organization", "collaboration", "view"), ("collaboration", "organization", "view"), ("node", "organization", "view"), ("user", "organization", "view"), ("port", "organization", "view")]),
     "Viewer": ("Can view tasks and results", [("task", "organization", "view"), ("result", "organization", "view"), ("organization", "organization", "view"), ("collaboration", "organization", "view"), ("node", "organization", "view")]),
 }
 

@@ -55,12 +55,14 @@ CREATE TABLE IF NOT EXISTS result (
   id INTEGER PRIMARY KEY AUTOINCREMENT, task_id INTEGER, organization_id INTEGER, input TEXT, result TEXT,
   log TEXT, assigned_at TEXT, started_at TEXT, finished_at TEXT, status TEXT DEFAULT 'pending');
 CREATE TABLE IF NOT EXISTS setting (key TEXT PRIMARY KEY, value TEXT);
+CREATE TABLE IF NOT EXISTS port (
+  id INTEGER PRIMARY KEY AUTOINCREMENT, result_id INTEGER, port INTEGER, label TEXT, address TEXT);
 CREATE INDEX IF NOT EXISTS idx_result_task ON result(task_id);
 CREATE INDEX IF NOT EXISTS idx_result_org ON result(organization_id);
 """
 
 TABLES = ["organization", "collaboration", "member", "node", "user", "role", "rule", "role_rule", "user_role",
-          "user_rule", "task", "result"]
+          "user_rule", "task", "result", "port"]
 
 
 def now() -> str:
