@@ -141,3 +141,21 @@ def test_kill_request_targets_only_the_named_task():
     assert procs[1].kill.called and procs[3].kill.called and not procs[2].kill.called
     node.kill_task()
     assert procs[2].kill.called
+
+
+def test_allowed_images_is_the_nodes_own_veto():
+    """``allowed_images`` in the node configuration: regular expressions matched against the full image name."""
+    from types import SimpleNamespace
+
+    from vantage6_b200.node import Node
+
+    base = {"server_url": "http://127.0.0.1", "port": 1, "api_path": "/api", "api_key": "k"}
+    Node(SimpleNamespace(config=dict(base))).check_image_allowed("anything/at:all")          # no policy: no veto
+    node = Node(SimpleNamespace(config=dict(base, allowed_images=[r"v6b200/(average|glm)(:.*)?", r"harbor2\.vantage6\.ai/demo/.*"])))
+    node.check_image_allowed("v6b200/average")
+    node.check_image_allowed("v6b200/glm:1.2")
+    node.check_image_allowed("harbor2.vantage6.ai/demo/average")
+    for image in ("v6b200/fedavg", "evil/v6b200/average", "v6b200/average; rm -rf", "harbor2xvantage6.ai/demo/x"):
+        with pytest.raises(PermissionError):
+            node.check_image_allowed(image)
+    Node(SimpleNamespace(config=dict(base, allowed_images="v6b200/.*"))).check_image_allowed("v6b200/fedavg")

@@ -20,6 +20,7 @@ import json
 import logging
 import os
 import queue
+import re
 import signal
 import subprocess
 import sys
@@ -236,6 +237,18 @@ class Node:
                 log.debug("heartbeat failed: %s", e)
 
     # ------------------------------------------------------------------ execution
+    def check_image_allowed(self, image: str) -> None:
+        """Node-side policy (vantage6 node configuration ``allowed_images``): a list of regular expressions; when present,
+        an algorithm image runs only if one of them matches its full name.  This is the data station's own veto -- it holds
+        whatever the server or the researcher says."""
+        allowed = self.config.get("allowed_images")
+        if not allowed:
+            return
+        if isinstance(allowed, str):
+            allowed = [allowed]
+        if not any(re.fullmatch(str(rx), image) for rx in allowed):
+            raise PermissionError(f"image {image!r} is not allowed on this node (allowed_images: {list(allowed)})")
+
     def _worker(self) -> None:
         while not self._stop.is_set():
             try:
@@ -251,6 +264,7 @@ class Node:
         self.client.request(f"result/{rid}", method="patch", json={"started_at": _now(), "status": "active"})
         logtxt, out_b64, status = "", None, "failed"
         try:
+            self.check_image_allowed(task["image"])
             module = resolve_image(task["image"], self.config.get("algorithms"), bool(self.config.get("allow_module_images")))
             plain = self.cryptor.decrypt_str_to_bytes(result["input"]) if result.get("input") else b"{}"
             token = self.client.request("token/container", method="post",
