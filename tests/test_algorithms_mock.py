@@ -198,3 +198,83 @@ def test_fedavg_confines_researcher_paths(tmp_path, monkeypatch):
     out = fedavg.train_partial(None, model="resnet_tiny", rounds=2, local_steps=1, batch=4, checkpoint_every=1, checkpoint_dir="ckpt",
                                metrics_file=str(log_dir / "m.jsonl"))
     assert len(out["losses"]) == 2 and (run_dir / "ckpt").is_dir() and (log_dir / "m.jsonl").exists()
+
+
+def _patients(rng, n, shift=0.0):
+    import pandas as pd
+
+    return pd.DataFrame({
+        "age": rng.normal(60 + shift, 10, n).round(1), "bmi": np.where(rng.random(n) < 0.1, np.nan, rng.normal(26, 4, n)),
+        "sex": rng.choice(["f", "m"], n), "stage": rng.choice(["I", "II", "III"], n, p=[0.5, 0.3, 0.2]),
+        "time": rng.exponential(24 + shift, n).round(0) + 1, "event": (rng.random(n) < 0.7).astype(int)})
+
+
+def test_summary_matches_pooled_statistics():
+    import pandas as pd
+
+    from vantage6_b200.algorithm.builtin import summary
+
+    rng = np.random.default_rng(3)
+    frames = [_patients(rng, 80), _patients(rng, 120, 5.0), _patients(rng, 50, -3.0)]
+    pooled = pd.concat(frames)
+    out = summary.master(ClientMockProtocol(frames, summary), frames[0], columns=["age", "bmi", "sex", "stage"])
+    assert out["n_rows"] == 250 and out["n_nodes"] == 3
+    for c in ("age", "bmi"):
+        np.testing.assert_allclose(out["columns"][c]["mean"], pooled[c].mean(), rtol=1e-12)
+        np.testing.assert_allclose(out["columns"][c]["std"], pooled[c].std(), rtol=1e-10)          # exact pooled variance
+        assert out["columns"][c]["min"] == pooled[c].min() and out["columns"][c]["max"] == pooled[c].max()
+    assert out["columns"]["bmi"]["missing"] == int(pooled["bmi"].isna().sum()) > 0
+    assert out["columns"]["sex"]["counts"] == pooled["sex"].value_counts().to_dict()
+    # privacy guards: a tiny node refuses, rare levels are suppressed
+    with pytest.raises(PermissionError):
+        summary.RPC_summary_partial(frames[0].head(5))
+    rare = frames[0].copy()
+    rare.loc[rare.index[:2], "stage"] = "IV"
+    part = summary.RPC_summary_partial(rare, columns=["stage"])
+    assert part["categorical"]["stage"]["counts"]["IV"] == 0 and part["categorical"]["stage"]["suppressed"]
+    with pytest.raises(KeyError):
+        summary.RPC_summary_partial(frames[0], columns=["nope"])
+
+
+def test_crosstab_and_chi_square_match_scipy():
+    import pandas as pd
+    from scipy.stats import chi2_contingency
+
+    from vantage6_b200.algorithm.builtin import crosstab
+
+    rng = np.random.default_rng(4)
+    frames = [_patients(rng, 200), _patients(rng, 300)]
+    out = crosstab.master(ClientMockProtocol(frames, crosstab), frames[0], row="sex", column="stage")
+    both = pd.concat(frames, ignore_index=True)
+    pooled = pd.crosstab(both["sex"], both["stage"])
+    assert out["rows"] == list(pooled.index) and out["columns"] == list(pooled.columns)
+    assert out["table"] == pooled.to_numpy().tolist() and out["n"] == 500 and not out["suppressed"]
+    ref = chi2_contingency(pooled.to_numpy(), correction=False)
+    np.testing.assert_allclose(out["chi2"], ref[0], rtol=1e-10)
+    assert out["dof"] == ref[2]
+    small = crosstab.RPC_crosstab_partial(frames[0].head(12), "sex", "stage")
+    assert small["suppressed"] and 0 in {n for cells in small["table"].values() for n in cells.values()}
+
+
+def test_kaplan_meier_matches_pooled_estimator():
+    import pandas as pd
+
+    from vantage6_b200.algorithm.builtin import kaplan_meier
+
+    rng = np.random.default_rng(5)
+    frames = [_patients(rng, 150), _patients(rng, 90, 6.0)]
+    out = kaplan_meier.master(ClientMockProtocol(frames, kaplan_meier), frames[0], time_column="time", censor_column="event")
+    pooled = pd.concat(frames)
+    t, e = pooled["time"].to_numpy(), pooled["event"].to_numpy().astype(bool)
+    s, ref = 1.0, []
+    for ti in sorted(set(t[e])):
+        s *= 1.0 - ((t == ti) & e).sum() / (t >= ti).sum()
+        ref.append(s)
+    np.testing.assert_allclose([c["survival"] for c in out["curve"]], ref, rtol=1e-12)
+    assert out["n"] == 240 and out["curve"][0]["at_risk"] <= 240
+    assert out["median_survival"] == next(c["time"] for c in out["curve"] if c["survival"] <= 0.5)
+    assert all(b["std_err"] >= 0 for b in out["curve"])
+    binned = kaplan_meier.master(ClientMockProtocol(frames, kaplan_meier), frames[0], "time", "event", bin_width=6.0)
+    assert len(binned["curve"]) < len(out["curve"]) and all(c["time"] % 6.0 == 0 for c in binned["curve"])
+    with pytest.raises(PermissionError):
+        kaplan_meier.RPC_event_times(frames[0].head(3), "time", "event")

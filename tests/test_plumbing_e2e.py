@@ -23,11 +23,15 @@ def network(tmp_path_factory):
     home = tmp_path_factory.mktemp("v6net")
     rng = np.random.default_rng(0)
     mats = [rng.normal(size=(30, 1000)), rng.normal(loc=1.0, size=(70, 1000))]
+    import pandas as pd
+
     dbs = []
     for i, m in enumerate(mats):
         p = home / f"vec{i}.npy"
         np.save(p, m)
-        dbs.append(str(p))
+        n = 40 + 20 * i
+        pd.DataFrame({"age": rng.normal(55 + 10 * i, 8, n).round(1), "sex": rng.choice(["f", "m"], n)}).to_csv(home / f"patients{i}.csv", index=False)
+        dbs.append({"default": str(p), "patients": str(home / f"patients{i}.csv")})
     old = os.environ.get("V6B200_HOME")
     net = DemoNetwork(2, home=str(home), databases=dbs)
     try:
@@ -42,10 +46,10 @@ def network(tmp_path_factory):
             os.environ["V6B200_HOME"] = old
 
 
-def run_task(net, image, input_, orgs=None, timeout=240):
+def run_task(net, image, input_, orgs=None, timeout=240, database="default"):
     c = net.client()
     task = c.task.create(collaboration=net.collaboration_id, organizations=orgs or [net.org_ids[0]], name="t",
-                         image=image, input=input_)
+                         image=image, input=input_, database=database)
     try:
         return c.wait_for_results(task["id"], timeout=timeout), c, task
     except TimeoutError:
@@ -81,6 +85,21 @@ def test_column_average_on_csv(network, tmp_path):
     dfs = [pd.DataFrame({"age": [10.0, 20.0]}), pd.DataFrame({"age": [30.0, 40.0, 50.0]})]
     out = average.master(ClientMockProtocol(dfs, average), dfs[0], "age")
     assert out == {"average": 30.0, "count": 5}
+
+
+def test_summary_on_a_labelled_csv_database(network):
+    """Second database label per node (``patients``: CSV) + a two-round master through the real control plane."""
+    import pandas as pd
+
+    res, _, _ = run_task(network, "v6b200/summary", {"method": "master", "master": True, "kwargs": {"columns": ["age", "sex"]}},
+                         database="patients")
+    out = res[0]["result"]
+    assert out is not None, res[0]["log"]
+    pooled = pd.concat([pd.read_csv(network.home / f"patients{i}.csv") for i in range(2)], ignore_index=True)
+    assert out["n_rows"] == 100 and out["n_nodes"] == 2, (out, res[0]["log"][-1500:])
+    np.testing.assert_allclose(out["columns"]["age"]["mean"], pooled["age"].mean(), rtol=1e-9)
+    np.testing.assert_allclose(out["columns"]["age"]["std"], pooled["age"].std(), rtol=1e-9)
+    assert out["columns"]["sex"]["counts"] == pooled["sex"].value_counts().to_dict()
 
 
 def test_fedavg_tiny_resnet_through_control_plane(network):

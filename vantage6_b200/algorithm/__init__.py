@@ -8,6 +8,13 @@ IMAGES = {
     "harbor2.vantage6.ai/demo/average": "vantage6_b200.algorithm.builtin.average",
     "v6-average-py": "vantage6_b200.algorithm.builtin.average",
     "v6b200/average": "vantage6_b200.algorithm.builtin.average",
+    # descriptive statistics on tabular node data (control plane only: a few numbers per column)
+    "v6b200/summary": "vantage6_b200.algorithm.builtin.summary",
+    "v6-summary-py": "vantage6_b200.algorithm.builtin.summary",
+    "v6b200/crosstab": "vantage6_b200.algorithm.builtin.crosstab",
+    "v6-crosstab-py": "vantage6_b200.algorithm.builtin.crosstab",
+    "v6b200/kaplan-meier": "vantage6_b200.algorithm.builtin.kaplan_meier",
+    "v6-kaplan-meier-py": "vantage6_b200.algorithm.builtin.kaplan_meier",
     # BASELINE config 1: weighted mean of a parameter vector
     "v6b200/weighted-mean": "vantage6_b200.algorithm.builtin.weighted_mean",
     # BASELINE configs 2-4: FedAvg over NVLink symmetric memory

@@ -71,7 +71,8 @@ class DemoNetwork:
         for i in range(self.n_nodes):
             node_cfg = {"api_key": self.api_keys[i], "server_url": "http://127.0.0.1", "port": self.port, "api_path": "/api",
                         "task_dir": str(self.home / "tasks" / f"node-{i}"),
-                        "databases": {"default": self.databases[i] or f"synthetic://node-{i}"},
+                        "databases": (dict(self.databases[i]) if isinstance(self.databases[i], dict)      # {label: uri}
+                                      else {"default": self.databases[i] or f"synthetic://node-{i}"}),
                         "logging": dict(LOGGING, file=f"node-{i}.log"),
                         "encryption": {"enabled": self.encrypted, "private_key": ""}}
             if self.gpus is not None:

@@ -782,7 +782,7 @@ class ServerApp:
             image = body.get("image")
             if not image:
                 raise HTTPError(400, "image is required")
-            parent_id, run_id, initiator, init_user = None, None, None, None
+            parent_id, run_id, initiator, init_user, parent_db = None, None, None, None, None
             if ident["type"] == "user":
                 sc = app.scope_of(ident, "task", "create")
                 if not (sc == "global" or (sc and ident["organization_id"] in members)):
@@ -798,9 +798,10 @@ class ServerApp:
                 if parent is None or db.task_complete(parent["id"]):
                     raise HTTPError(401, "Parent task is finished: no new sub-tasks allowed")
                 parent_id, run_id, initiator, init_user = parent["id"], parent["run_id"], ident["organization_id"], parent["init_user_id"]
+                parent_db = parent["database"]             # a sub-task reads the database label its parent was pointed at
             tid = db.insert("task", name=body.get("name", ""), description=body.get("description", ""), image=image,
                             collaboration_id=c["id"], run_id=run_id, parent_id=parent_id,
-                            database=body.get("database", "default"), initiator_id=initiator, init_user_id=init_user,
+                            database=body.get("database") or parent_db or "default", initiator_id=initiator, init_user_id=init_user,
                             created_at=now())
             for o in orgs:
                 inp = o.get("input")
