@@ -488,3 +488,71 @@ def test_signing_key_is_kept_with_the_database(tmp_path):
             issue_reset_token(shell, "nobody")
     finally:
         app.stop()
+
+
+def test_json_http_transport_reconnects_and_drops_none_params(server):
+    from vantage6_b200.common.jsonhttp import JsonHttp
+
+    app, port = server
+    h = JsonHttp()
+    base = f"http://127.0.0.1:{port}/api"
+    assert h.request("GET", base + "/version").json()["version"] == "3.1.0"
+    conn = next(iter(h._pool().values()))
+    assert h.request("GET", base + "/version", params={"x": None, "y": 1}).status_code == 200
+    assert next(iter(h._pool().values())) is conn                      # kept alive and reused
+    conn.sock.close()                                                   # the peer (or a firewall) dropped the idle connection
+    assert h.request("GET", base + "/version").status_code == 200       # noticed before sending: fresh connection
+    assert next(iter(h._pool().values())) is not conn
+    r = h.request("POST", base + "/token/user", json={"username": "alice", "password": "nope"})
+    assert r.status_code == 401 and "Invalid" in r.json()["msg"]
+    assert h.request("GET", base + "/nothing-here").status_code == 404
+    results = []
+    threads = [threading.Thread(target=lambda: results.append(h.request("GET", base + "/health").status_code)) for _ in range(8)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert results == [200] * 8                                         # one connection per thread, none shared
+    h.close()
+
+
+def test_fewer_round_trips_per_work_item(server):
+    """The node's own room gets the whole work item, the token request reports the start, status events say whether they
+    completed the task -- and a client that waits is not woken into useless GETs."""
+    app, port = server
+    alice = user(port, "alice", "pw-a")
+    node = NodeClient("http://127.0.0.1", port, "/api")
+    node.authenticate("key-a")
+    since = app.events.last_id()
+    task = alice.task.create(collaboration=1, organizations=[1, 2], name="t", image="img", input={"method": "m"})
+    evs = node.request("event", params={"since": since, "timeout": 1})["events"]
+    mine = [e for e in evs if e["name"] == "new_task" and "result" in e["data"]]
+    assert len(mine) == 1 and mine[0]["data"]["result"]["task"]["image"] == "img"          # only its own work item, with the task block
+    assert mine[0]["data"]["result"]["task"]["initiator"] == 1
+    assert sum(e["name"] == "new_task" for e in evs) == 3                                  # + the two collaboration-wide notices
+    bob_events = user(port, "bob", "pw-b").request("event", params={"since": since, "timeout": 1})["events"]
+    assert all("result" not in e["data"] for e in bob_events)                              # nobody else sees work items
+    rid = mine[0]["data"]["result"]["id"]
+    reply = node.request("token/container", method="post", json={"task_id": task["id"], "image": "img", "result_id": rid})
+    assert reply["started"] is True
+    r = alice.result.get(rid)
+    assert r["started_at"] is not None and r["status"] == "active"
+    other = [x["id"] for x in alice.result.list(task_id=task["id"]) if x["id"] != rid][0]
+    assert "started" not in node.request("token/container", method="post", json={"task_id": task["id"], "image": "img", "result_id": other})
+    assert alice.result.get(other)["started_at"] is None                                   # not this node's result: untouched
+    # a waiting client: woken by the first completion (not complete), returns on the second without extra polling
+    calls = []
+    real = alice.request
+    alice.request = lambda endpoint, *a, **k: (calls.append(endpoint), real(endpoint, *a, **k))[1]
+    got = {}
+    waiter = threading.Thread(target=lambda: got.update(rows=alice.wait_for_results(task["id"], timeout=20)))
+    waiter.start()
+    time.sleep(0.3)
+    node.request(f"result/{rid}", method="patch", json={"finished_at": "now", "result": DummyCryptor().bytes_to_str(serialize({"v": 1}))})
+    time.sleep(0.3)
+    node_b = NodeClient("http://127.0.0.1", port, "/api")
+    node_b.authenticate("key-b")
+    node_b.request(f"result/{other}", method="patch", json={"finished_at": "now", "result": DummyCryptor().bytes_to_str(serialize({"v": 2}))})
+    waiter.join(timeout=20)
+    assert sorted(r["result"]["v"] for r in got["rows"]) == [1, 2]
+    assert calls.count(f"task/{task['id']}") == 2 and f"task/{task['id']}/result" not in calls   # first check + the completing event
+    done = [e for e in node.request("event", params={"since": since, "timeout": 1})["events"] if e["name"] == "status_update"]
+    assert [e["data"]["task_complete"] for e in done] == [False, False, True]              # started, first result, last result

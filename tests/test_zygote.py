@@ -76,3 +76,12 @@ def test_children_run_concurrently(zygote):
     t0 = time.time()
     assert [p.wait(timeout=30) for p in procs] == [0, 0, 0, 0]
     assert time.time() - t0 < 1.8          # four 0.5 s sleeps side by side, not back to back
+
+
+def test_preload_follows_the_nodes_databases():
+    from vantage6_b200.node.zygote import PRELOAD, preload_for
+
+    assert "pandas" not in preload_for(["/data/vec.npy", "synthetic://imagenet", "/data/shard.pt"])
+    assert "pandas" in preload_for(["/data/vec.npy", "/data/patients.CSV"])
+    assert "pandas" in preload_for(["/data/x.parquet"])
+    assert preload_for([]) == PRELOAD and preload_for(None) == PRELOAD

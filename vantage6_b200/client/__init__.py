@@ -18,10 +18,9 @@ import time
 from types import SimpleNamespace
 from typing import Any, Dict, List, Optional, Union
 
-import requests
-
 from ..common import STRING_ENCODING, bytes_to_base64s  # noqa: F401
 from ..common.encryption import CryptorBase, DummyCryptor, RSACryptor
+from ..common.jsonhttp import JsonHttp
 from ..common.serialization import deserialize, serialize
 
 module_name = __name__.split(".")[-1]
@@ -33,6 +32,38 @@ class ServerError(Exception):
         self.status, self.msg = status, msg
 
 
+def _wait_for_task(client: "ClientBase", task_id: int, sleep: float, timeout: float, include_results: bool = False) -> dict:
+    """Shared by the researcher's and the algorithm's client: returns the task once it is complete (with its results when
+    asked, so that no second request is needed).  The event cursor is taken BEFORE the first completeness check, so no
+    wake-up can be missed; ``status_update`` events say whether they completed the task, so the task is only fetched
+    again when one of them does (or when a poll times out, as a safety net)."""
+    t0 = time.time()
+    params = {"include": "results"} if include_results else None
+    try:
+        cursor = client.request("event", params={"timeout": 0}, timeout=15).get("last_id")
+    except Exception:  # noqa: BLE001 -- no event channel: plain polling
+        cursor = None
+    while True:
+        task = client.request(f"task/{task_id}", params=params)
+        if task.get("complete"):
+            return task
+        while True:
+            if time.time() - t0 > timeout:
+                raise TimeoutError(f"task {task_id} did not complete in {timeout}s")
+            if cursor is None:
+                time.sleep(sleep)
+                break
+            try:
+                reply = client.request("event", params={"since": cursor, "timeout": 5, "task_id": task_id}, timeout=15)
+                cursor = reply.get("last_id", cursor)
+                evs = [e for e in reply.get("events", []) if e.get("name") == "status_update" and e.get("data", {}).get("task_id") == task_id]
+                if not reply.get("events") or any(e["data"].get("task_complete", True) for e in evs):
+                    break                       # timed out (safety re-check) or an event that may have completed the task
+            except Exception:  # noqa: BLE001
+                cursor = None
+                break
+
+
 class ClientBase:
     def __init__(self, host: str, port: Optional[int] = 5000, path: str = "/api"):
         self.log = logging.getLogger(module_name)
@@ -42,8 +73,7 @@ class ClientBase:
         self.__refresh_url: Optional[str] = None
         self.cryptor: Optional[CryptorBase] = None
         self.whoami: Optional[SimpleNamespace] = None
-        self._session = requests.Session()
-        self._session.trust_env = False          # never route loopback traffic through a proxy
+        self._http = JsonHttp()                  # keep-alive connection per thread; never routed through a proxy
 
     # -- addresses ---------------------------------------------------------------------------
     @property
@@ -81,9 +111,8 @@ class ClientBase:
     def request(self, endpoint: str, json: dict = None, method: str = "get", params: dict = None,
                 first_try: bool = True, timeout: float = 70.0):
         url = self.generate_path_to(endpoint)
-        rest = {"get": self._session.get, "post": self._session.post, "put": self._session.put,
-                "patch": self._session.patch, "delete": self._session.delete}.get(method.lower(), self._session.get)
-        response = rest(url, json=json, headers=self.headers, params=params, timeout=timeout)
+        verb = method.upper() if method.lower() in ("get", "post", "put", "patch", "delete") else "GET"
+        response = self._http.request(verb, url, json=json, headers=self.headers, params=params, timeout=timeout)
         if response.status_code > 210:
             try:
                 msg = response.json().get("msg", response.text)
@@ -106,7 +135,7 @@ class ClientBase:
     def refresh_token(self) -> None:
         assert self.__refresh_token, "Refresh token not found, did you authenticate?"
         url = f"{self.host}:{self.port}{self.__refresh_url}" if self.port else f"{self.host}{self.__refresh_url}"
-        r = self._session.post(url, headers={"Authorization": "Bearer " + self.__refresh_token}, timeout=30)
+        r = self._http.request("POST", url, headers={"Authorization": "Bearer " + self.__refresh_token}, timeout=30)
         if r.status_code != 200:
             raise ServerError(r.status_code, "Authentication Error!")
         self._access_token = r.json()["access_token"]
@@ -166,25 +195,11 @@ class UserClient(ClientBase):
     def wait_for_results(self, task_id: int, sleep: float = 0.05, timeout: float = 600.0) -> List[Any]:
         """Block until the task is complete, then return the decrypted results.  Woken by the server's
         ``status_update`` events (long poll); plain polling every ``sleep`` seconds is the fallback."""
-        t0 = time.time()
-        try:        # event cursor taken BEFORE the first completeness check: no wake-up can be missed
-            cursor = self.request("event", params={"timeout": 0}, timeout=15).get("last_id")
-        except Exception:  # noqa: BLE001
-            cursor = None
-        while True:
-            if self.request(f"task/{task_id}").get("complete"):
-                break
-            if time.time() - t0 > timeout:
-                raise TimeoutError(f"task {task_id} did not complete in {timeout}s")
-            if cursor is None:
-                time.sleep(sleep)
-                continue
-            try:
-                reply = self.request("event", params={"since": cursor, "timeout": 5, "task_id": task_id}, timeout=15)
-                cursor = reply.get("last_id", cursor)
-            except Exception:  # noqa: BLE001
-                cursor = None
-        return self.result.from_task(task_id)
+        task = _wait_for_task(self, task_id, sleep, timeout, include_results=True)
+        rows = task["results"]
+        for r in rows:
+            r["result"] = self._decrypt_result(r.get("result"))
+        return rows
 
     # ---------------------------------------------------------------- sub clients
     class SubClient:
@@ -440,25 +455,7 @@ class ContainerClient(ClientBase):
     def wait_for_task(self, task_id: int, sleep: float = 0.05, timeout: float = 3600.0) -> dict:
         """Block until ``task_id`` is complete; woken by the server's ``status_update`` events (long poll through the
         node's proxy) instead of sleeping between polls, with plain polling as the fallback."""
-        t0 = time.time()
-        try:        # event cursor taken BEFORE the first completeness check: no wake-up can be missed
-            cursor = self.request("event", params={"timeout": 0}, timeout=15).get("last_id")
-        except Exception:  # noqa: BLE001
-            cursor = None
-        while True:
-            task = self.get_task(task_id)
-            if task.get("complete"):
-                return task
-            if time.time() - t0 > timeout:
-                raise TimeoutError(f"subtask {task_id} did not complete in {timeout}s")
-            if cursor is None:
-                time.sleep(sleep)
-                continue
-            try:
-                reply = self.request("event", params={"since": cursor, "timeout": 5, "task_id": task_id}, timeout=15)
-                cursor = reply.get("last_id", cursor)
-            except Exception:  # noqa: BLE001
-                cursor = None
+        return _wait_for_task(self, task_id, sleep, timeout)
 
     def wait_for_results(self, task_id: int, sleep: float = 0.05, timeout: float = 3600.0) -> List[Any]:
         self.wait_for_task(task_id, sleep=sleep, timeout=timeout)

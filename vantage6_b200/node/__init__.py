@@ -36,7 +36,7 @@ from ..common import base64s_to_bytes, bytes_to_base64s
 from ..common.encryption import DummyCryptor, RSACryptor
 from ..runtime import runtime_dir
 from .proxy import ProxyServer
-from .zygote import Zygote, ZygoteProcess
+from .zygote import Zygote, ZygoteProcess, preload_for
 
 log = logging.getLogger("node")
 
@@ -165,7 +165,10 @@ class Node:
 
     def _handle_event(self, ev: dict) -> None:
         if ev["name"] == "new_task" and ev["data"].get("organization_id") == self.client.organization_id:
-            r = self.client.request(f"result/{ev['data']['result_id']}", params={"include": "task"})
+            if ev["data"].get("result_id") in self._seen:
+                return
+            # the event addressed to this node's own room carries the work item; the collaboration-wide one only names it
+            r = ev["data"].get("result") or self.client.request(f"result/{ev['data']['result_id']}", params={"include": "task"})
             if r.get("finished_at") is None:
                 self._enqueue(r)
         elif ev["name"] == "kill_containers":
@@ -257,24 +260,40 @@ class Node:
                 continue
             threading.Thread(target=self._run_result, args=(result,), daemon=True).start()
 
+    def _report_started(self, rid: int) -> None:
+        try:
+            self.client.request(f"result/{rid}", method="patch", json={"started_at": _now(), "status": "active"})
+        except Exception as e:  # noqa: BLE001
+            log.warning("could not report the start of result %s: %s", rid, e)
+
     def _run_result(self, result: dict) -> None:
         rid = result["id"]
         task = result["task"]
         log.info("starting task %s (result %s, image %s)", task["id"], rid, task.get("image"))
-        self.client.request(f"result/{rid}", method="patch", json={"started_at": _now(), "status": "active"})
+        marks = [("picked", time.perf_counter())]          # phase trace of the run (V6B200_TRACE_TASKS=1 logs it)
+
+        def mark(name: str) -> None:
+            marks.append((name, time.perf_counter()))
+        started, start_reported = None, False
         logtxt, out_b64, status = "", None, "failed"
         try:
             self.check_image_allowed(task["image"])
             module = resolve_image(task["image"], self.config.get("algorithms"), bool(self.config.get("allow_module_images")))
             plain = self.cryptor.decrypt_str_to_bytes(result["input"]) if result.get("input") else b"{}"
-            token = self.client.request("token/container", method="post",
-                                        json={"task_id": task["id"], "image": task["image"]})["container_token"]
+            reply = self.client.request("token/container", method="post",
+                                        json={"task_id": task["id"], "image": task["image"], "result_id": rid})
+            token = reply["container_token"]
+            start_reported = True
+            if not reply.get("started"):             # a server that does not take the start report with the token request
+                started = threading.Thread(target=self._report_started, args=(rid,), daemon=True)
+                started.start()
             run_dir = runtime_dir() / "volumes" / self.ctx.docker_temporary_volume_name(task["run_id"])
             work = run_dir / f"result-{rid}"
             work.mkdir(parents=True, exist_ok=True)
             (work / "input").write_bytes(plain)
             (work / "token").write_text(token)
             (work / "output").write_bytes(b"")
+            mark("token+files")
             env = self._algorithm_env()
             label = (task.get("database") or "default")
             uri = self.ctx.databases.get(label) if hasattr(self.ctx, "databases") else None
@@ -301,6 +320,7 @@ class Node:
             pkg_root = str(Path(__file__).resolve().parent.parent.parent)
             env["PYTHONPATH"] = pkg_root + os.pathsep + env.get("PYTHONPATH", "")
             proc = self._launch_algorithm(module, env, work / "log")
+            mark("spawned")
             self.running[rid] = proc
             self._task_of[rid] = task["id"]
             budget = float(self.config.get("task_timeout_s", 3600))
@@ -310,6 +330,7 @@ class Node:
             else:
                 out, _ = proc.communicate(timeout=budget)
                 logtxt = out.decode("utf-8", errors="replace")
+            mark("algorithm done")
             if proc.returncode == 0:
                 data = (work / "output").read_bytes()
                 dest_org = task.get("initiator") or self.client.request(f"task/{task['id']}").get("initiator")
@@ -326,12 +347,19 @@ class Node:
         finally:
             self.running.pop(rid, None)
             self._task_of.pop(rid, None)
+        if started is not None:
+            started.join(timeout=30)
         try:
-            self.client.request(f"result/{rid}", method="patch",
-                                json={"finished_at": _now(), "result": out_b64, "log": logtxt[-20000:], "status": status})
+            final = {"finished_at": _now(), "result": out_b64, "log": logtxt[-20000:], "status": status}
+            if not start_reported:                   # refused before it began (image policy, unknown image, bad input)
+                final["started_at"] = final["finished_at"]
+            self.client.request(f"result/{rid}", method="patch", json=final)
         except Exception as e:  # noqa: BLE001
             log.error("could not report result %s: %s", rid, e)
+        mark("reported")
         log.info("task %s result %s: %s", task.get("id"), rid, status)
+        if os.environ.get("V6B200_TRACE_TASKS") == "1":
+            log.info("result %s phases (ms): %s", rid, ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f}" for a, b in zip(marks, marks[1:])))
 
     # environment variables an algorithm process inherits from the node (everything else is dropped: the reference
     # isolates algorithms in containers -- reference vantage6/cli/node.py:320 hands the node the docker socket for that --
@@ -398,7 +426,8 @@ class Node:
         default = "1" if (self.gpu is None or os.environ.get("V6B200_GPU_WORKER", "1") != "0") else "0"
         if os.environ.get("V6B200_ZYGOTE", default) == "0":
             return
-        zygote = Zygote(runtime_dir())
+        databases = getattr(self.ctx, "databases", None) or self.config.get("databases") or {}
+        zygote = Zygote(runtime_dir(), preload=preload_for(list(databases.values()) if isinstance(databases, dict) else []))
         try:
             if zygote.start() and not self._stop.is_set():
                 self.zygote = zygote

@@ -15,9 +15,8 @@ import threading
 from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
 from urllib.parse import urlsplit
 
-import requests
-
 from ..common import base64s_to_bytes
+from ..common.jsonhttp import JsonHttp
 
 log = logging.getLogger("proxy")
 
@@ -31,8 +30,7 @@ class ProxyServer:
         self.node = node
         self._httpd = None
         self.port = None
-        self._session = requests.Session()
-        self._session.trust_env = False
+        self._http = JsonHttp()
 
     def start(self) -> int:
         proxy = self
@@ -94,7 +92,7 @@ class ProxyServer:
                 for org in body.get("organizations", []):
                     plain = base64s_to_bytes(org["input"]) if isinstance(org.get("input"), str) else b""
                     org["input"] = node.encrypt_for_organization(plain, int(org["id"]))
-            r = self._session.request(method, url, json=body, headers=headers, timeout=70)
+            r = self._http.request(method, url, json=body, headers=headers, timeout=70)
             try:
                 payload = r.json()
             except Exception:  # noqa: BLE001

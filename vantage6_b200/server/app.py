@@ -304,7 +304,8 @@ class ServerApp:
         if with_task:
             t = self.db.get("task", r["task_id"])
             out["task"] = {**self.link("task", t["id"]), "name": t["name"], "image": t["image"], "database": t["database"],
-                           "run_id": t["run_id"], "collaboration_id": t["collaboration_id"], "parent_id": t["parent_id"]}
+                           "run_id": t["run_id"], "collaboration_id": t["collaboration_id"], "parent_id": t["parent_id"],
+                           "initiator": t["initiator_id"]}
         return out
 
     def task_json(self, t: dict, include_results: bool = False) -> dict:
@@ -422,7 +423,20 @@ class ServerApp:
                 raise HTTPError(400, "Task is already finished")
             ident_ = {"node_id": ident["id"], "organization_id": ident["organization_id"],
                       "collaboration_id": ident["collaboration_id"], "task_id": t["id"], "image": image}
-            return {"container_token": app.make_token("container", ident_)}
+            reply = {"container_token": app.make_token("container", ident_)}
+            if body.get("result_id") is not None:
+                # asking for the algorithm's token is the first thing a node does for a work item: with ``result_id`` the
+                # same request reports the start (one round trip less than a separate PATCH /result/<id>)
+                r = db.get("result", int(body["result_id"]))
+                if r is not None and r["task_id"] == t["id"] and r["organization_id"] == ident["organization_id"] and r["finished_at"] is None:
+                    if r["started_at"] is None:
+                        db.update("result", r["id"], started_at=now(), status="active")
+                        app.events.emit("status_update", {"result_id": r["id"], "task_id": t["id"], "status": "active",
+                                                          "organization_id": r["organization_id"], "parent_id": t["parent_id"],
+                                                          "task_complete": False},
+                                        [f"collaboration_{t['collaboration_id']}", f"task_{t['id']}"])
+                    reply["started"] = True
+            return reply
 
         @app.route("POST", "/token/refresh")
         def token_refresh(ident, body, q):
@@ -810,6 +824,12 @@ class ServerApp:
                 node = db.one("SELECT id FROM node WHERE organization_id=? AND collaboration_id=?", (int(o["id"]), c["id"]))
                 if node is None:
                     log.warning("organization %s has no node in collaboration %s", o["id"], c["id"])
+                if node is not None and len(inp if isinstance(inp, str) else "") <= 65536:
+                    # the node that has to run it gets the whole work item in its own room (nobody else listens there):
+                    # no GET /result round trip before it can start
+                    app.events.emit("new_task", {"task_id": tid, "result_id": rid, "organization_id": int(o["id"]),
+                                                 "result": app.result_json(db.get("result", rid), with_task=True)},
+                                    [f"node_{node['id']}"])
                 app.events.emit("new_task", {"task_id": tid, "result_id": rid, "organization_id": int(o["id"])},
                                 [f"collaboration_{c['id']}"])
             return app.task_json(db.get("task", tid)), 201
@@ -905,7 +925,8 @@ class ServerApp:
             db.update("result", r["id"], **fields)
             if "finished_at" in fields or "status" in fields:
                 app.events.emit("status_update", {"result_id": r["id"], "task_id": t["id"], "status": fields.get("status", "completed"),
-                                                  "organization_id": r["organization_id"], "parent_id": t["parent_id"]},
+                                                  "organization_id": r["organization_id"], "parent_id": t["parent_id"],
+                                                  "task_complete": "finished_at" in fields and db.task_complete(t["id"])},
                                 [f"collaboration_{t['collaboration_id']}", f"task_{t['id']}"])
             return app.result_json(db.get("result", r["id"]))
 
