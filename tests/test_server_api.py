@@ -497,12 +497,12 @@ def test_json_http_transport_reconnects_and_drops_none_params(server):
     h = JsonHttp()
     base = f"http://127.0.0.1:{port}/api"
     assert h.request("GET", base + "/version").json()["version"] == "3.1.0"
-    conn = next(iter(h._pool().values()))
+    conn = h._idle[("http", "127.0.0.1", port)][0]
     assert h.request("GET", base + "/version", params={"x": None, "y": 1}).status_code == 200
-    assert next(iter(h._pool().values())) is conn                      # kept alive and reused
+    assert h._idle[("http", "127.0.0.1", port)] == [conn]                 # kept alive and reused
     conn.sock.close()                                                   # the peer (or a firewall) dropped the idle connection
     assert h.request("GET", base + "/version").status_code == 200       # noticed before sending: fresh connection
-    assert next(iter(h._pool().values())) is not conn
+    assert h._idle[("http", "127.0.0.1", port)][0] is not conn
     r = h.request("POST", base + "/token/user", json={"username": "alice", "password": "nope"})
     assert r.status_code == 401 and "Invalid" in r.json()["msg"]
     assert h.request("GET", base + "/nothing-here").status_code == 404
@@ -510,8 +510,16 @@ def test_json_http_transport_reconnects_and_drops_none_params(server):
     threads = [threading.Thread(target=lambda: results.append(h.request("GET", base + "/health").status_code)) for _ in range(8)]
     [t.start() for t in threads]
     [t.join() for t in threads]
-    assert results == [200] * 8                                         # one connection per thread, none shared
+    assert results == [200] * 8                                         # a connection serves one request at a time
+    assert 1 <= h.idle_connections() <= 8
+    done = []
+    t = threading.Thread(target=lambda: done.append(h.request("GET", base + "/version").status_code))   # a new thread reuses a warm one
+    before = h.idle_connections()
+    t.start()
+    t.join()
+    assert done == [200] and h.idle_connections() == before
     h.close()
+    assert h.idle_connections() == 0
 
 
 def test_fewer_round_trips_per_work_item(server):

@@ -280,9 +280,11 @@ class Node:
             self.check_image_allowed(task["image"])
             module = resolve_image(task["image"], self.config.get("algorithms"), bool(self.config.get("allow_module_images")))
             plain = self.cryptor.decrypt_str_to_bytes(result["input"]) if result.get("input") else b"{}"
+            mark("resolve+decrypt")
             reply = self.client.request("token/container", method="post",
                                         json={"task_id": task["id"], "image": task["image"], "result_id": rid})
             token = reply["container_token"]
+            mark("token")
             start_reported = True
             if not reply.get("started"):             # a server that does not take the start report with the token request
                 started = threading.Thread(target=self._report_started, args=(rid,), daemon=True)

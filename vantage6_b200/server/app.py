@@ -23,6 +23,7 @@ import collections
 import datetime as _dt
 import json
 import logging
+import os
 import re
 import threading
 import time
@@ -38,6 +39,7 @@ from . import admin_routes
 from .db import Database, check_password, hash_password, now
 
 log = logging.getLogger("server")
+TRACE_HTTP = os.environ.get("V6B200_TRACE_HTTP") == "1"        # log every request with its handling time
 
 
 class _ApiHTTPServer(ThreadingHTTPServer):
@@ -963,8 +965,11 @@ class ServerApp:
                     body = json.loads(raw.decode("utf-8")) if raw else {}
                 except Exception:  # noqa: BLE001
                     body = {}
+                t0 = time.perf_counter()
                 status, payload = app.dispatch(method, parts.path, parse_qs(parts.query), body, self.headers)
                 data = json.dumps(payload).encode("utf-8")
+                if TRACE_HTTP:
+                    log.info("http %s %s -> %s in %.2f ms", method, self.path[:80], status, 1e3 * (time.perf_counter() - t0))
                 self.send_response(status)
                 self.send_header("Content-Type", "application/json")
                 self.send_header("Content-Length", str(len(data)))
