@@ -564,3 +564,29 @@ def test_fewer_round_trips_per_work_item(server):
     assert calls.count(f"task/{task['id']}") == 2 and f"task/{task['id']}/result" not in calls   # first check + the completing event
     done = [e for e in node.request("event", params={"since": since, "timeout": 1})["events"] if e["name"] == "status_update"]
     assert [e["data"]["task_complete"] for e in done] == [False, False, True]              # started, first result, last result
+
+
+def test_metrics_endpoint_prometheus_text(server):
+    import requests
+
+    app, port = server
+    alice = user(port, "alice", "pw-a")
+    alice.task.create(collaboration=1, organizations=[1, 2], name="t", image="img", input={})
+    with pytest.raises(ServerError):
+        alice.request("task/999")
+    url = f"http://127.0.0.1:{port}/api/metrics"
+    s = requests.Session()
+    s.trust_env = False
+    assert s.get(url).status_code == 401                                   # a token is needed unless metrics_public is set
+    r = s.get(url, headers=alice.headers)
+    assert r.status_code == 200 and r.headers["Content-Type"].startswith("text/plain")
+    lines = r.text.splitlines()
+    assert 'v6_http_requests_total{method="POST",route="/task",status="201"} 1' in lines
+    assert 'v6_http_requests_total{method="GET",route="/task/<id>",status="404"} 1' in lines
+    assert 'v6_nodes{status="offline"} 2' in lines and 'v6_results{status="pending"} 2' in lines
+    assert "v6_tasks_open 1" in lines and "v6_tasks_total 1" in lines
+    assert any(l.startswith('v6_http_request_seconds_total{method="POST",route="/token/user"}') for l in lines)
+    for l in lines:                                                        # well-formed exposition
+        assert l.startswith("# ") or (" " in l and float(l.rsplit(" ", 1)[1]) >= 0)
+    app.config["metrics_public"] = True
+    assert s.get(url).status_code == 200

@@ -4,7 +4,7 @@ The control plane of a federated round is a dozen tiny JSON requests between pro
 server, node -> server, algorithm -> node proxy -> server); with ``requests`` each of them costs ~0.6-1.0 ms of client-side
 machinery (session / adapter / urllib3 pool / cookie jar), three to five times the server's own work.  This keeps a small
 pool of keep-alive connections per host and does nothing else: measured 0.14 ms for ``GET /version`` and 0.41 ms for an
-authenticated item against 0.63 / 0.99 ms (profiles/control_plane_cpu_r2.jsonl).
+authenticated item against 0.63 / 0.99 ms (profiles/README.md, control plane section).
 
 Environment proxies are never used (the peers are loopback or a configured server address).
 """

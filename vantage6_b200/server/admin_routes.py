@@ -14,7 +14,7 @@ SURVEY.md Appendix C).  ``register(app)`` is called from ``ServerApp._register_r
 * ``/port`` -- the address book of running algorithms (vantage6: the VPN ports of algorithm containers): a node registers
   under which address / port / label the algorithm it runs for a result can be reached by its siblings of the same run.
   On one NVSwitch box the "address" is the node's GPU and its rank in the run's rendezvous (algorithm/peer.py).
-* ``/spec`` -- the route table itself.
+* ``/spec`` -- the route table itself.  ``/metrics`` -- counters and gauges in the Prometheus text format.
 """
 from __future__ import annotations
 
@@ -426,3 +426,45 @@ def register(app) -> None:  # noqa: C901 -- a flat route table reads best in one
             path = rx.pattern[1:-3].replace("(\\d+)", "<id>")
             out.append({"method": method, "path": app.api_path + path, "doc": " ".join((fn.__doc__ or "").split()) or None})
         return sorted(out, key=lambda r: (r["path"], r["method"]))
+
+    # ------------------------------------------------------------------ observability
+    @app.route("GET", "/metrics")
+    def metrics(ident, body, q):
+        """Prometheus text exposition: requests by route and status, handling time, events, listeners, nodes, tasks, results."""
+        if not app.config.get("metrics_public", False):
+            app.require(ident)
+        from .app import PlainText
+
+        def esc(v) -> str:
+            return str(v).replace("\\", "\\\\").replace('"', '\\"')
+
+        out = ["# HELP v6_http_requests_total Requests handled, by method, route and status.", "# TYPE v6_http_requests_total counter"]
+        with app._stats_lock:
+            stats = {k: list(v) for k, v in app._stats.items()}
+        for (method, route, status), (n, _) in sorted(stats.items()):
+            out.append(f'v6_http_requests_total{{method="{method}",route="{esc(route)}",status="{status}"}} {int(n)}')
+        out += ["# HELP v6_http_request_seconds_total Time spent handling requests (long polls excluded).", "# TYPE v6_http_request_seconds_total counter"]
+        per_route: dict = {}
+        for (method, route, _), (n, sec) in stats.items():
+            acc = per_route.setdefault((method, route), 0.0)
+            per_route[(method, route)] = acc + sec
+        for (method, route), sec in sorted(per_route.items()):
+            out.append(f'v6_http_request_seconds_total{{method="{method}",route="{esc(route)}"}} {sec:.6f}')
+        import time as _time
+
+        gauges = [("v6_uptime_seconds", "Seconds since the server started.", _time.time() - app.started_at),
+                  ("v6_events_emitted_total", "Events emitted on the event bus.", app.events.last_id()),
+                  ("v6_event_listeners", "Open websocket event subscriptions.", app.ws.connections if app.ws is not None else 0),
+                  ("v6_tasks_total", "Tasks in the database.", db.one("SELECT COUNT(*) AS n FROM task")["n"]),
+                  ("v6_tasks_open", "Tasks with at least one unfinished result.",
+                   db.one("SELECT COUNT(DISTINCT task_id) AS n FROM result WHERE finished_at IS NULL")["n"])]
+        for name, help_, value in gauges:
+            kind = "counter" if name.endswith("_total") and name != "v6_tasks_total" else "gauge"
+            out += [f"# HELP {name} {help_}", f"# TYPE {name} {kind}", f"{name} {value}"]
+        out += ["# HELP v6_nodes Nodes by status.", "# TYPE v6_nodes gauge"]
+        for r in db.query("SELECT status, COUNT(*) AS n FROM node GROUP BY status ORDER BY status"):
+            out.append(f'v6_nodes{{status="{esc(r["status"])}"}} {r["n"]}')
+        out += ["# HELP v6_results Results by status.", "# TYPE v6_results gauge"]
+        for r in db.query("SELECT status, COUNT(*) AS n FROM result GROUP BY status ORDER BY status"):
+            out.append(f'v6_results{{status="{esc(r["status"])}"}} {r["n"]}')
+        return PlainText("\n".join(out) + "\n")

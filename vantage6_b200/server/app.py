@@ -59,6 +59,10 @@ DEFAULT_ROLES = {
 }
 
 
+class PlainText(str):
+    """A handler's reply that goes out as ``text/plain`` instead of JSON (``GET /metrics``)."""
+
+
 class HTTPError(Exception):
     def __init__(self, status: int, msg: str):
         super().__init__(msg)
@@ -123,6 +127,8 @@ class ServerApp:
         self.started_at = time.time()
         self.token_expiry_s = int(config.get("token_expires_hours", 6) * 3600)
         self._routes: List[Tuple[str, re.Pattern, Callable]] = []
+        self._stats: Dict[Tuple[str, str, int], List[float]] = {}      # (method, route, status) -> [count, seconds]
+        self._stats_lock = threading.Lock()
         self._httpd: Optional[ThreadingHTTPServer] = None
         self.ws = None                                # websocket event channel (server/ws_events.py)
         self._thread: Optional[threading.Thread] = None
@@ -333,6 +339,8 @@ class ServerApp:
         if not path.startswith(self.api_path):
             return 404, {"msg": f"unknown path {path}"}
         sub = path[len(self.api_path):] or "/"
+        t0, route = time.perf_counter(), "(unmatched)"
+        status, payload = 404, {"msg": f"no route for {method} {sub}"}
         try:
             ident = self.identity(headers)
             for m, rx, fn in self._routes:
@@ -340,17 +348,22 @@ class ServerApp:
                     continue
                 mt = rx.match(sub)
                 if mt:
+                    route = rx.pattern[1:-3].replace("(\\d+)", "<id>")
                     q = {k: v[0] for k, v in query.items()}
                     res = fn(ident, body if isinstance(body, dict) else {}, q, *mt.groups())
-                    if isinstance(res, tuple):
-                        return res[1], res[0]
-                    return 200, res
-            return 404, {"msg": f"no route for {method} {sub}"}
+                    status, payload = (res[1], res[0]) if isinstance(res, tuple) else (200, res)
+                    break
         except HTTPError as e:
-            return e.status, {"msg": e.msg}
+            status, payload = e.status, {"msg": e.msg}
         except Exception as e:  # noqa: BLE001
             log.error("unhandled error in %s %s: %s", method, path, traceback.format_exc())
-            return 500, {"msg": f"internal server error: {e}"}
+            status, payload = 500, {"msg": f"internal server error: {e}"}
+        if route != "/event":                   # long polls would only measure their own timeout
+            with self._stats_lock:
+                st = self._stats.setdefault((method, route, status), [0, 0.0])
+                st[0] += 1
+                st[1] += time.perf_counter() - t0
+        return status, payload
 
     # ------------------------------------------------------------------ resources
     def _register_routes(self) -> None:  # noqa: C901 -- a flat route table reads best in one place
@@ -967,11 +980,11 @@ class ServerApp:
                     body = {}
                 t0 = time.perf_counter()
                 status, payload = app.dispatch(method, parts.path, parse_qs(parts.query), body, self.headers)
-                data = json.dumps(payload).encode("utf-8")
+                data = payload.encode("utf-8") if isinstance(payload, PlainText) else json.dumps(payload).encode("utf-8")
                 if TRACE_HTTP:
                     log.info("http %s %s -> %s in %.2f ms", method, self.path[:80], status, 1e3 * (time.perf_counter() - t0))
                 self.send_response(status)
-                self.send_header("Content-Type", "application/json")
+                self.send_header("Content-Type", "text/plain; version=0.0.4; charset=utf-8" if isinstance(payload, PlainText) else "application/json")
                 self.send_header("Content-Length", str(len(data)))
                 self.end_headers()
                 self.wfile.write(data)
