@@ -278,3 +278,11 @@ def test_kaplan_meier_matches_pooled_estimator():
     assert len(binned["curve"]) < len(out["curve"]) and all(c["time"] % 6.0 == 0 for c in binned["curve"])
     with pytest.raises(PermissionError):
         kaplan_meier.RPC_event_times(frames[0].head(3), "time", "event")
+
+
+def test_component_inventory_is_current():
+    """docs/INVENTORY.md maps every SURVEY.md section-2 item to file:line; the generator fails when a symbol moved."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "inventory.py")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert out.returncode == 0, out.stderr[-500:]
+    with open(os.path.join(ROOT, "docs", "INVENTORY.md")) as f:
+        assert f.read() == out.stdout, "docs/INVENTORY.md is stale: python scripts/inventory.py > docs/INVENTORY.md"
