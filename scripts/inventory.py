@@ -1,12 +1,23 @@
-"""Regenerates docs/INVENTORY.md: where each item of SURVEY.md section 2 / 5 lives, with the file:line of the defining symbol looked up\nin the tree (fails loudly when a symbol has moved).\n\n    python scripts/inventory.py > docs/INVENTORY.md\n"""
-import re, subprocess, sys
+"""Regenerates docs/INVENTORY.md: where each item of SURVEY.md sections 2 and 5 lives, with the file:line of the defining
+symbol looked up in the tree (fails loudly when a symbol has moved).
+
+    python scripts/inventory.py > docs/INVENTORY.md
+"""
+import re
+import sys
 from pathlib import Path
+
 ROOT = Path(__file__).resolve().parent.parent
+
+
 def loc(path, pattern):
-    p=ROOT/path
-    for i,l in enumerate(p.read_text().splitlines(),1):
-        if re.search(pattern,l): return f"`{path}:{i}`"
+    """`path:line` of the first line of ``path`` that matches ``pattern``."""
+    for i, line in enumerate((ROOT / path).read_text().splitlines(), 1):
+        if re.search(pattern, line):
+            return f"`{path}:{i}`"
     raise SystemExit(f"NOT FOUND {path} {pattern}")
+
+
 rows=[
 ("C1","Packaging, console scripts",[("setup.py",r"entry_points")],"`vnode`, `vserver`, `vnode-local`, `vserver-local`; `requirements.txt`"),
 ("C2","Version / `__build__`",[("vantage6_b200/_version.py",r"^version_info =")],"`__version__` (PEP 440 from `version_info` + `__build__`)"),
