@@ -178,3 +178,48 @@ def test_allowed_images_is_the_nodes_own_veto():
         with pytest.raises(PermissionError):
             node.check_image_allowed(image)
     Node(SimpleNamespace(config=dict(base, allowed_images="v6b200/.*"))).check_image_allowed("v6b200/fedavg")
+
+
+def test_encrypted_collaboration_end_to_end(tmp_path):
+    """Encrypted collaboration through the real stack: the researcher seals the input per organization, the nodes unseal it,
+    the master's sub-task inputs are sealed by the node's proxy for each destination, partial results come back sealed for the
+    organization that started the task -- the server only ever stores ciphertext."""
+    rng = np.random.default_rng(7)
+    mats = [rng.normal(size=(20, 50)), rng.normal(loc=2.0, size=(60, 50))]
+    dbs = []
+    for i, m in enumerate(mats):
+        np.save(tmp_path / f"vec{i}.npy", m)
+        dbs.append(str(tmp_path / f"vec{i}.npy"))
+    old = os.environ.get("V6B200_HOME")
+    net = DemoNetwork(2, home=str(tmp_path / "home"), name="sealed", databases=dbs, encrypted=True)
+    try:
+        net.start()
+        c = net.client()
+        assert c.collaboration.get(net.collaboration_id)["encrypted"] is True
+        assert all(o["public_key"] for o in c.organization.list() if o["name"] in net.org_names)      # uploaded by the nodes
+        task = c.task.create(collaboration=net.collaboration_id, organizations=[net.org_ids[0]], name="t",
+                             image="v6b200/weighted-mean", input={"method": "master", "master": True})
+        res = c.wait_for_results(task["id"], timeout=120)
+        out = res[0]["result"]
+        assert out is not None, res[0]["log"]
+        np.testing.assert_allclose(out["mean"], np.concatenate(mats).mean(0), rtol=1e-12)
+        assert out["count"] == 80 and out["n_nodes"] == 2
+        # what the server stores: sealed envelopes, for the input, the sub-task inputs and every result
+        import sqlite3
+
+        db = next((tmp_path / "home").rglob("demo.sqlite"))
+        rows = sqlite3.connect(db).execute("SELECT input, result FROM result").fetchall()
+        assert len(rows) == 3
+        for inp, result in rows:
+            for blob in (inp, result):
+                assert blob and "method" not in blob and "mean" not in blob and "sum" not in blob and "$" in blob
+        # a researcher of the other organization cannot read what was sealed for organization 0
+        other = net.client(user=1)
+        sealed = other.result.get(res[0]["id"])["result"]
+        assert not isinstance(sealed, dict)
+    finally:
+        net.stop()
+        if old is None:
+            os.environ.pop("V6B200_HOME", None)
+        else:
+            os.environ["V6B200_HOME"] = old

@@ -52,6 +52,7 @@ class DemoNetwork:
         self.org_ids: List[int] = []
         self.collaboration_id: Optional[int] = None
         self.password = "demo-password"
+        self.key_bits = 2048                     # demo keys; `vnode create-private-key` makes 4096-bit ones
         self.log: List[str] = []
 
     # ------------------------------------------------------------------ config files
@@ -59,6 +60,15 @@ class DemoNetwork:
         d = self.home / "user" / "config" / kind
         d.mkdir(parents=True, exist_ok=True)
         return d
+
+    def key_file(self, org: int) -> str:
+        """RSA key of organization ``org`` (shared by its node and its researchers, as in vantage6); created on first use."""
+        path = self.home / "keys" / f"privkey_{self.org_names[org]}.pem"
+        if not path.exists():
+            from .common.encryption import RSACryptor
+
+            RSACryptor.create_new_rsa_key(path, bits=self.key_bits)
+        return str(path)
 
     def write_configs(self) -> None:
         server_cfg = {"description": "demo network", "ip": "127.0.0.1", "port": self.port, "api_path": "/api",
@@ -74,7 +84,7 @@ class DemoNetwork:
                         "databases": (dict(self.databases[i]) if isinstance(self.databases[i], dict)      # {label: uri}
                                       else {"default": self.databases[i] or f"synthetic://node-{i}"}),
                         "logging": dict(LOGGING, file=f"node-{i}.log"),
-                        "encryption": {"enabled": self.encrypted, "private_key": ""}}
+                        "encryption": {"enabled": self.encrypted, "private_key": self.key_file(i) if self.encrypted else ""}}
             if self.gpus is not None:
                 node_cfg["gpu"] = self.gpus[i]
             with open(self._cfg_dir("node") / f"{self.name}-node-{i}.yaml", "w") as f:
@@ -147,7 +157,7 @@ class DemoNetwork:
                 if time.time() - t0 > timeout:
                     raise
                 time.sleep(0.2)
-        c.setup_encryption(None)
+        c.setup_encryption(self.key_file(user) if self.encrypted else None)
         return c
 
     def tail_logs(self, n: int = 30) -> str:
