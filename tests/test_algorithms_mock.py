@@ -286,3 +286,39 @@ def test_component_inventory_is_current():
     assert out.returncode == 0, out.stderr[-500:]
     with open(os.path.join(ROOT, "docs", "INVENTORY.md")) as f:
         assert f.read() == out.stdout, "docs/INVENTORY.md is stale: python scripts/inventory.py > docs/INVENTORY.md"
+
+
+def test_serialization_roundtrip_property():
+    """Any nesting of JSON scalars, bytes and numpy arrays survives ``serialize`` -> ``deserialize`` (hypothesis)."""
+    import math
+
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+    from hypothesis.extra import numpy as hnp
+
+    arrays = st.one_of(*[hnp.arrays(dt, hnp.array_shapes(min_dims=0, max_dims=3, max_side=4))
+                         for dt in (np.float32, np.float64, np.int32, np.int64, np.uint8, np.bool_)])
+    leaves = st.one_of(st.none(), st.booleans(), st.integers(-2**53, 2**53), st.floats(allow_nan=True, allow_infinity=True),
+                       st.text(max_size=20), st.binary(max_size=32), arrays)
+    trees = st.recursive(leaves, lambda kids: st.one_of(st.lists(kids, max_size=4), st.dictionaries(st.text(max_size=8), kids, max_size=4)),
+                         max_leaves=12)
+
+    def same(a, b) -> bool:
+        if isinstance(a, np.ndarray):
+            return isinstance(b, np.ndarray) and a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b, equal_nan=a.dtype.kind == "f")
+        if isinstance(a, float):
+            return isinstance(b, float) and (a == b or (math.isnan(a) and math.isnan(b)))
+        if isinstance(a, dict):
+            return isinstance(b, dict) and a.keys() == b.keys() and all(same(a[k], b[k]) for k in a)
+        if isinstance(a, list):
+            return isinstance(b, list) and len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+        return type(a) is type(b) and a == b
+
+    @settings(max_examples=150, deadline=None)
+    @given(trees)
+    def check(tree):
+        assert same(tree, deserialize(serialize(tree)))
+
+    check()
+    for special in (float("nan"), float("inf"), float("-inf")):           # bare non-finite tokens are still JSON, not "pickle"
+        assert same(special, deserialize(serialize(special)))

@@ -24,7 +24,7 @@ def _default(o: Any):
             t = t.float()
         o = t.numpy()
     if isinstance(o, np.ndarray):
-        a = np.ascontiguousarray(o)
+        a = np.asarray(o, order="C")               # (ascontiguousarray would turn a 0-d array into shape (1,))
         return {"__ndarray__": base64.b64encode(a.tobytes()).decode("ascii"), "dtype": str(a.dtype), "shape": list(a.shape)}
     if isinstance(o, (np.integer,)):
         return int(o)
@@ -75,7 +75,8 @@ def deserialize(blob: bytes | str, data_format: str | None = None, allow_pickle:
     if isinstance(blob, str):
         blob = blob.encode("utf-8")
     head = blob.lstrip()[:5]
-    looks_json = head[:1] in (b"{", b"[", b'"', b"-") or head[:1].isdigit() or head[:4] in (b"null", b"true") or head == b"false"
+    looks_json = (head[:1] in (b"{", b"[", b'"', b"-") or head[:1].isdigit() or head[:4] in (b"null", b"true") or head == b"false"
+                  or head[:3] == b"NaN" or head == b"Infin")            # python's json writes non-finite floats as bare tokens
     if data_format is None:
         data_format = "json" if looks_json else "pickle"
     if data_format == "json":
