@@ -68,7 +68,7 @@ ext=[
 ("`NetworkManager`",[("vantage6_b200/runtime/addons.py",r"class NetworkManager")],""),
 ("`utest.{find_tests, run_tests}`",[("vantage6_b200/common/utest.py",r"def run_tests")],""),
 ("`vantage6.client.Client`",[("vantage6_b200/client/__init__.py",r"^class UserClient"),("vantage6_b200/client/__init__.py",r"^class ContainerClient"),("vantage6_b200/client/mock.py",r"^class ClientMockProtocol")],"endpoint / call table: `docs/SERVER_API.md`"),
-("`RSACryptor`",[("vantage6_b200/common/encryption.py",r"^class RSACryptor")],"RSA-OAEP sealed AES-GCM envelope per organization"),
+("`RSACryptor`",[("vantage6_b200/common/encryption.py",r"^class RSACryptor")],"vantage6 wire format `key$iv$ciphertext`: AES-256-CTR payload, its key sealed with the receiving organization's RSA key (PKCS#1 v1.5)"),
 ("server runtime (`vserver-local`, WSGI `app`)",[("vantage6_b200/cli/server_local.py",r"def cli_server_local"),("vantage6_b200/server/app.py",r"^class ServerApp"),("vantage6_b200/server/admin_routes.py",r"^def register"),("vantage6_b200/server/ws_events.py",r"^class WebSocketEvents"),("vantage6_b200/server/db.py",r"^class Database")],"REST + JWT + rules, websocket events, sqlite"),
 ("node runtime (`vnode-local`)",[("vantage6_b200/cli/node_local.py",r"def cli_node_local"),("vantage6_b200/node/__init__.py",r"^class Node\b"),("vantage6_b200/node/proxy.py",r"^class ProxyServer"),("vantage6_b200/node/zygote.py",r"^class Zygote:"),("vantage6_b200/node/gpu_worker.py",r"^class GpuWorker")],"runs algorithms as child processes with the container env / file contract; resident GPU worker"),
 ("algorithm interface",[("vantage6_b200/algorithm/wrapper.py",r"^def dispatch"),("vantage6_b200/algorithm/__init__.py",r"^IMAGES"),("vantage6_b200/algorithm/data.py",r"^def make_local_batches"),("vantage6_b200/algorithm/peer.py",r"^class PeerChannel")],"`master` / `RPC_`, data loaders, node-to-node channel; built-ins in `algorithm/builtin/`"),

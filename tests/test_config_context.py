@@ -147,3 +147,50 @@ def test_check_config_name_allowed(capsys):
         check_config_name_allowed("bad name")
     assert e.value.code == 1
     assert "[error]" in capsys.readouterr().out
+
+
+def test_small_pure_functions_properties(tmp_path):
+    """hypothesis over the pure helpers: PEP 440 strings, queue URIs, the hybrid encryption envelope."""
+    import re
+
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from vantage6_b200._version import pep440
+    from vantage6_b200.cli.rabbitmq.queue_manager import split_rabbitmq_uri
+    from vantage6_b200.common.encryption import DummyCryptor, RSACryptor
+
+    @given(st.integers(0, 99), st.integers(0, 99), st.integers(0, 99), st.sampled_from(["alpha", "beta", "candidate", "final"]),
+           st.integers(0, 999), st.integers(0, 99))
+    def versions(major, minor, patch, stage, build, post):
+        v = pep440((major, minor, patch, stage, build, post))
+        assert re.fullmatch(r"\d+\.\d+\.\d+(\.(a|b|rc)\d+)?(\.post\d+)?", v)
+        assert (stage == "final") == (re.search(r"\.(a|b|rc)\d+", v) is None) and (post > 0) == (".post" in v)
+
+    ident = st.text(alphabet="abcdefghijklmnopqrstuvwxyz0123456789-_.", min_size=1, max_size=12)
+
+    @given(ident, st.text(alphabet="abcXYZ019:!#%^&*()-_+=", min_size=1, max_size=16), ident, st.integers(1, 65535), ident)
+    def uris(user, password, host, port, vhost):
+        parts = split_rabbitmq_uri(f"amqp://{user}:{password}@{host}:{port}/{vhost}")
+        assert parts == {"user": user, "password": password, "host": host, "port": str(port), "vhost": vhost}
+
+    key_a, key_b = tmp_path / "a.pem", tmp_path / "b.pem"
+    RSACryptor.create_new_rsa_key(key_a, bits=2048)
+    RSACryptor.create_new_rsa_key(key_b, bits=2048)
+    a, b = RSACryptor(key_a), RSACryptor(key_b)
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.binary(max_size=5000))
+    def envelopes(blob):
+        sealed = a.encrypt_bytes_to_str(blob, b.public_key_str)
+        assert sealed.count("$") == 2 and b.decrypt_str_to_bytes(sealed) == blob
+        if blob:
+            assert a.encrypt_bytes_to_str(blob, b.public_key_str) != sealed             # fresh key and iv every time
+        assert DummyCryptor().decrypt_str_to_bytes(DummyCryptor().encrypt_bytes_to_str(blob, "")) == blob
+
+    versions()
+    uris()
+    envelopes()
+    with pytest.raises(Exception):                                                      # sealed for b: a cannot open it
+        a.decrypt_str_to_bytes(a.encrypt_bytes_to_str(b"secret", b.public_key_str))
+    assert b.verify_public_key(b.public_key_str) and not b.verify_public_key(a.public_key_str)
