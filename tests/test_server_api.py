@@ -590,3 +590,45 @@ def test_metrics_endpoint_prometheus_text(server):
         assert l.startswith("# ") or (" " in l and float(l.rsplit(" ", 1)[1]) >= 0)
     app.config["metrics_public"] = True
     assert s.get(url).status_code == 200
+
+
+def test_grant_cap_holds_for_random_rule_sets():
+    """Property (hypothesis): whatever rules a user holds, it can put a rule into a role exactly when it holds that
+    (resource, operation) itself at an equal or wider scope -- checked against an independent oracle, in-process."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from vantage6_b200.server.app import SCOPES
+
+    app = ServerApp({"uri": "sqlite://", "api_path": "/api", "jwt_secret_key": "s" * 40})
+    rules = app.db.query("SELECT * FROM rule ORDER BY id")
+    by_id = {r["id"]: r for r in rules}
+    org = app.db.one("SELECT id FROM organization WHERE name='root'")["id"]
+    counter = [0]
+
+    def call(method, path, body, uid):
+        tok = app.make_token("user", {"id": uid, "organization_id": org})
+        return app.dispatch(method, "/api" + path, {}, body, {"Authorization": "Bearer " + tok})
+
+    ids = st.lists(st.sampled_from([r["id"] for r in rules]), min_size=0, max_size=12, unique=True)
+
+    @settings(max_examples=80, deadline=None)
+    @given(ids, ids)
+    def check(held, wanted):
+        counter[0] += 1
+        uid = app.db.insert("user", username=f"u{counter[0]}", password="x", organization_id=org)
+        for rid in held:
+            app.db.execute("INSERT INTO user_rule VALUES (?,?)", (uid, rid))
+        status, payload = call("POST", "/role", {"name": f"r{counter[0]}", "rules": wanted}, uid)
+        best = {}
+        for rid in held:
+            r = by_id[rid]
+            key = (r["name"], r["operation"])
+            best[key] = max(best.get(key, -1), SCOPES.index(r["scope"]))
+        may_create = ("role", "create") in best
+        covered = all(best.get((by_id[w]["name"], by_id[w]["operation"]), -1) >= SCOPES.index(by_id[w]["scope"]) for w in wanted)
+        assert (status == 201) == (may_create and covered), (status, payload, held, wanted)
+        if status == 201:
+            assert sorted(x["id"] for x in payload["rules"]) == sorted(wanted)
+
+    check()
