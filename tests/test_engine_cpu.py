@@ -486,3 +486,51 @@ def test_trainer_bcast_fused_is_a_noop_without_the_nvlink_plane():
     l1 = float(tr.run_round(batches).item())
     assert l1 < l0
     tr.close()
+
+
+def test_slice_and_k1_block_ownership_properties():
+    """Pure layout math of the engine (hypothesis): reducer slices tile the flat buffer exactly on aligned boundaries, and
+    the 256-row blocks of a K1 layer are owned by exactly one reducer each -- or the layer is refused on every rank alike."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from vantage6_b200.parallel.fedavg import k1_own_blocks, slice_bounds
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(1, 5_000_000), st.integers(1, 8), st.sampled_from([8, 64, 256, 256 * 64, 256 * 768]))
+    def slices(n, nr, align):
+        bounds = [slice_bounds(n, nr, pos, align) for pos in range(nr)]
+        chunk = bounds[0][2]
+        assert all(b[2] == chunk for b in bounds) and chunk % align == 0 and chunk * nr >= n
+        assert bounds[0][0] == 0 and bounds[-1][1] == n
+        for (lo, hi, _), (lo2, _, _) in zip(bounds, bounds[1:]):
+            assert lo <= hi == lo2 and (lo % align == 0 or lo == n)         # empty tail slices sit at n
+        assert slice_bounds(n, nr, None, align)[:2] == (0, 0)
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(1, 8), st.integers(1, 12), st.sampled_from([64, 768, 1024]), st.integers(0, 40), st.integers(0, 5_000_000),
+           st.booleans())
+    def blocks(nr, n_blocks, k_in, prefix_blocks, tail, aligned):
+        n_out, blk = 256 * n_blocks, 256 * k_in
+        offset = prefix_blocks * blk if aligned else prefix_blocks * blk + 8 * 3            # a layer that starts off the block grid
+        n = offset + n_out * k_in + tail
+        align = blk if aligned else 8
+        bounds = [slice_bounds(n, nr, pos, align) for pos in range(nr)]
+        owns = [k1_own_blocks(lo, hi, chunk, nr, offset, n_out, k_in) for lo, hi, chunk in bounds]
+        assert all(o is None for o in owns) or all(o is not None for o in owns)            # collective decision
+        if owns[0] is None:
+            return
+        covered = []
+        for a, z in owns:
+            assert 0 <= a <= z <= n_blocks
+            covered += list(range(a, z))
+        assert covered == list(range(n_blocks))                                            # every block exactly once, in order
+        for (lo, hi, _), (a, z) in zip(bounds, owns):                                      # and an owner really holds its blocks
+            assert z == a or (lo <= offset + a * blk and offset + z * blk <= hi)
+
+    slices()
+    blocks()
+    # block-aligned shards (what the trainer asks for with bcast="fused") are never refused
+    for nr in range(1, 9):
+        bounds = [slice_bounds(10_000_000, nr, pos, 256 * 768) for pos in range(nr)]
+        assert all(k1_own_blocks(lo, hi, c, nr, 3 * 256 * 768, 2304, 768) is not None for lo, hi, c in bounds)

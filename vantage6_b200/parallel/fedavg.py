@@ -61,6 +61,31 @@ class ServerOptConfig:
     eps: float = 1e-3
 
 
+def slice_bounds(n: int, n_reducers: int, pos: Optional[int], align: int) -> Tuple[int, int, int]:
+    """Slice [lo, hi) of the ``pos``-th of ``n_reducers`` reducers over ``n`` elements (``pos=None``: not a reducer, empty
+    slice) and the chunk length: equal chunks rounded up to ``align`` elements, the last ones possibly short or empty.  Over
+    all positions the slices tile [0, n) exactly."""
+    chunk = (n + n_reducers - 1) // n_reducers
+    chunk = (chunk + align - 1) // align * align
+    if pos is None:
+        return 0, 0, chunk
+    lo = min(n, pos * chunk)
+    return lo, min(n, lo + chunk), chunk
+
+
+def k1_own_blocks(lo: int, hi: int, chunk: int, n_reducers: int, offset: int, n_out: int, k_in: int) -> Optional[Tuple[int, int]]:
+    """Which 256-row blocks of the [n_out, k_in] weight at flat ``offset`` lie in the reducer slice [lo, hi): a half-open
+    block range, (0, 0) when none.  ``None`` -- on every rank alike, it only depends on the shared layout -- when some
+    reducer boundary cuts a block (then no single owner could multicast it)."""
+    blk, size = 256 * k_in, n_out * k_in
+    for pos in range(1, n_reducers):
+        b = pos * chunk - offset
+        if 0 < b < size and b % blk:
+            return None
+    a, z = max(lo, offset) - offset, min(hi, offset + size) - offset
+    return (a // blk, z // blk) if z > a else (0, 0)
+
+
 class FedAvgEngine:
     """Owns the symmetric buffers of one rank and runs aggregation rounds.
 
@@ -156,15 +181,8 @@ class FedAvgEngine:
     def _reshard(self) -> None:
         """(Re)compute this rank's slice [lo, hi) from the reducer list and make sure the server state it needs exists."""
         nr = len(self.reducers)
-        chunk = (self.n + nr - 1) // nr
-        chunk = (chunk + self.shard_align - 1) // self.shard_align * self.shard_align
-        self._chunk = chunk
-        if self.rank in self.reducers:
-            pos = self.reducers.index(self.rank)
-            self.lo = min(self.n, pos * chunk)
-            self.hi = min(self.n, self.lo + chunk)
-        else:
-            self.lo = self.hi = 0
+        pos = self.reducers.index(self.rank) if self.rank in self.reducers else None
+        self.lo, self.hi, self._chunk = slice_bounds(self.n, nr, pos, self.shard_align)
         self.n_reducers = nr
         self.reducer_mask = sum(1 << r for r in self.reducers)
         if self.is_reducer:
@@ -184,17 +202,12 @@ class FedAvgEngine:
         allow it (no multicast binding, slice boundaries that cut a 256-row block)."""
         if self.data_plane != "native" or self._shadow_buf is None or not self._shadow_buf.mc_ptr or self.world < 2:
             return None
-        blk = 256 * k_in
         if n_out % 256 or offset % 8 or not (self.shadow_skip[0] <= offset and offset + n_out * k_in <= self.shadow_skip[1]):
             return None
         # the same answer on every rank (the flag allocation below is collective): NO reducer boundary may cut a block
-        size = n_out * k_in
-        for pos in range(1, len(self.reducers)):
-            b = pos * self._chunk - offset
-            if 0 < b < size and b % blk:
-                return None
-        lo, hi = max(self.lo, offset) - offset, min(self.hi, offset + size) - offset
-        own = (lo // blk, hi // blk) if hi > lo else (0, 0)
+        own = k1_own_blocks(self.lo, self.hi, self._chunk, len(self.reducers), offset, n_out, k_in)
+        if own is None:
+            return None
         n_flags = (n_out // 256) * ((k_in + 63) // 64)
         fb = self.heap.alloc(n_flags * 4, multicast=False)
         fb.view(torch.int32, n_flags).zero_()
