@@ -322,3 +322,43 @@ def test_serialization_roundtrip_property():
     check()
     for special in (float("nan"), float("inf"), float("-inf")):           # bare non-finite tokens are still JSON, not "pickle"
         assert same(special, deserialize(serialize(special)))
+
+
+@pytest.mark.parametrize("family", ["gaussian", "binomial", "poisson"])
+def test_glm_irls_matches_pooled_fit(family):
+    """Fisher scoring over three mock nodes against scikit-learn fitted on the pooled rows (no penalty)."""
+    from sklearn.linear_model import LinearRegression, LogisticRegression, PoissonRegressor
+
+    rng = np.random.default_rng({"gaussian": 1, "binomial": 2, "poisson": 3}[family])
+    w_true, b_true = np.array([0.8, -0.5, 0.3, 0.0]), 0.4
+    frames = []
+    for n in (150, 400, 250):
+        X = rng.normal(size=(n, 4))
+        eta = X @ w_true + b_true
+        y = {"gaussian": eta + rng.normal(scale=0.7, size=n), "binomial": (rng.random(n) < 1 / (1 + np.exp(-eta))).astype(float),
+             "poisson": rng.poisson(np.exp(eta)).astype(float)}[family]
+        frames.append(np.column_stack([X, y]))
+    out = glm.master_irls(ClientMockProtocol(frames, glm), frames[0], family=family)
+    pooled = np.concatenate(frames)
+    ref = {"gaussian": LinearRegression(), "binomial": LogisticRegression(C=np.inf, tol=1e-10, max_iter=500),
+           "poisson": PoissonRegressor(alpha=0.0, tol=1e-10, max_iter=500)}[family].fit(pooled[:, :-1], pooled[:, -1])
+    np.testing.assert_allclose(out["coefficients"], np.ravel(ref.coef_), rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(out["intercept"], float(np.ravel(ref.intercept_)[0]), rtol=2e-4, atol=2e-5)
+    assert out["n"] == 800 and out["n_nodes"] == 3 and out["iterations"] <= 12
+    assert out["deviance_history"][-1] <= out["deviance_history"][0] + 1e-9
+    assert np.all(out["std_errors"] > 0) and np.all(np.abs(out["coefficients"] - w_true) < 5 * out["std_errors"][:-1])
+    with pytest.raises(ValueError):
+        glm.master_irls(ClientMockProtocol(frames, glm), frames[0], family="gamma")
+
+
+def test_glm_irls_named_columns_on_frames():
+    import pandas as pd
+
+    rng = np.random.default_rng(9)
+    frames = []
+    for n in (120, 200):
+        df = pd.DataFrame({"age": rng.normal(60, 10, n), "dose": rng.normal(2, 1, n), "noise": rng.normal(size=n)})
+        df["event"] = (rng.random(n) < 1 / (1 + np.exp(-(0.05 * (df["age"] - 60) + 0.8 * df["dose"] - 1.5)))).astype(float)
+        frames.append(df[["event", "age", "dose", "noise"]])            # outcome is NOT the last column
+    out = glm.master_irls(ClientMockProtocol(frames, glm), frames[0], family="binomial", columns=["age", "dose"], outcome="event")
+    assert len(out["coefficients"]) == 2 and out["coefficients"][1] > 0.3

@@ -1,6 +1,10 @@
-"""Federated logistic-regression GLM as a vantage6 algorithm (BASELINE config 5).
+"""Federated GLM as a vantage6 algorithm (BASELINE config 5: logistic regression).
 
-Two flavours:
+Three flavours:
+* ``master_irls`` / ``RPC_irls_partial`` -- Fisher scoring on the control plane for the gaussian, binomial (logit) and
+  poisson (log) families, the ``v6-glm-py`` formulation: each iteration every node returns its (p+1)x(p+1) ``X'WX`` and
+  ``X'Wz``, the master solves the pooled normal equations -- the coefficients, standard errors and deviance a pooled fit
+  would give, in a handful of round trips;
 * ``master`` / ``RPC_gradient``   -- classic vantage6 iteration on the CONTROL plane: every
   iteration is a sub-task round trip through the server (works on CPU nodes, any transport);
 * ``master_fused`` / ``RPC_fit``  -- the B200 path: ONE sub-task; the partials rendezvous and
@@ -54,6 +58,88 @@ def RPC_gradient(data, w=None) -> Dict[str, Any]:
     r = p - y
     loss = float(np.sum(np.maximum(z, 0) - z * y + np.log1p(np.exp(-np.abs(z)))))
     return {"grad": np.concatenate([X.T @ r, [r.sum()]]), "loss": loss, "n": int(X.shape[0])}
+
+
+# ------------------------------------------------------------------ Fisher scoring (IRLS) for three families
+FAMILIES = ("gaussian", "binomial", "poisson")
+
+
+def _design(data, columns=None, outcome=None):
+    """(X with a trailing intercept column, y).  Data frames may name the ``outcome`` column and the feature ``columns``;
+    otherwise the last column is the outcome."""
+    if outcome is not None and hasattr(data, "columns"):
+        feats = list(columns) if columns else [c for c in data.columns if c != outcome]
+        X, y = data[feats].to_numpy(dtype=np.float64), data[outcome].to_numpy(dtype=np.float64)
+    else:
+        X, y = _xy(data)
+    return np.hstack([X, np.ones((X.shape[0], 1))]), y
+
+
+def _mean_and_weights(family: str, eta, y):
+    """Mean, IRLS weights, working response and the unit deviance for the canonical link of ``family``."""
+    if family == "gaussian":
+        mu = eta
+        return mu, np.ones_like(eta), y, (y - mu) ** 2
+    if family == "binomial":
+        mu = np.clip(1.0 / (1.0 + np.exp(-eta)), 1e-10, 1 - 1e-10)
+        var = mu * (1 - mu)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dev = 2 * (np.where(y > 0, y * np.log(y / mu), 0.0) + np.where(y < 1, (1 - y) * np.log((1 - y) / (1 - mu)), 0.0))
+        return mu, var, eta + (y - mu) / var, dev
+    if family == "poisson":
+        mu = np.exp(np.clip(eta, -30, 30))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dev = 2 * (np.where(y > 0, y * np.log(y / mu), 0.0) - (y - mu))
+        return mu, mu, eta + (y - mu) / mu, dev
+    raise ValueError(f"unknown family {family!r} (known: {FAMILIES})")
+
+
+def master_irls(client, data, family: str = "binomial", columns=None, outcome=None, max_iterations: int = 25, tol: float = 1e-8,
+                organization_ids=None) -> Dict[str, Any]:
+    if family not in FAMILIES:
+        raise ValueError(f"unknown family {family!r} (known: {FAMILIES})")
+    ids = organization_ids or [o["id"] for o in client.get_organizations_in_my_collaboration()]
+    beta, deviance, history = None, None, []
+    for it in range(1, max_iterations + 1):
+        kw = {"family": family, "columns": columns, "outcome": outcome, "beta": None if beta is None else beta.tolist()}
+        task = client.create_new_task(input_={"method": "irls_partial", "kwargs": kw}, organization_ids=ids)
+        client.wait_for_task(task["id"])
+        parts = client.get_results(task_id=task["id"])
+        if len(parts) != len(ids):
+            raise RuntimeError(f"{len(ids) - len(parts)} of {len(ids)} nodes returned no result")
+        xtwx = sum(np.asarray(p["xtwx"], dtype=np.float64) for p in parts)
+        xtwz = sum(np.asarray(p["xtwz"], dtype=np.float64) for p in parts)
+        n = sum(int(p["n"]) for p in parts)
+        new_dev = float(sum(p["deviance"] for p in parts))            # deviance AT the beta that was sent out
+        if beta is not None:                                            # (the first pass starts from the data, not from a model)
+            history.append(new_dev)
+        new_beta = np.linalg.solve(xtwx, xtwz)
+        converged = beta is not None and (abs(new_dev - deviance) <= tol * (abs(new_dev) + 0.1) or family == "gaussian")
+        beta, deviance = new_beta, new_dev
+        if converged:
+            break
+    p_ = beta.shape[0]
+    dispersion = deviance / max(1, n - p_) if family == "gaussian" else 1.0
+    cov = np.linalg.inv(xtwx) * dispersion
+    return {"family": family, "coefficients": beta[:-1], "intercept": float(beta[-1]), "std_errors": np.sqrt(np.diag(cov)),
+            "deviance": deviance, "deviance_history": history, "dispersion": dispersion, "iterations": it, "n": n, "n_nodes": len(parts)}
+
+
+def RPC_irls_partial(data, family: str = "binomial", columns=None, outcome=None, beta=None) -> Dict[str, Any]:
+    X, y = _design(data, columns, outcome)
+    if beta is None:                                   # start from the family's usual initial mean
+        if family == "gaussian":
+            eta = y
+        elif family == "binomial":
+            mu0 = (y + 0.5) / 2
+            eta = np.log(mu0 / (1 - mu0))
+        else:
+            eta = np.log(np.maximum(y, 0) + 0.1)
+    else:
+        eta = X @ np.asarray(beta, dtype=np.float64)
+    _, w, z, dev = _mean_and_weights(family, eta, y)
+    xw = X * w[:, None]
+    return {"xtwx": xw.T @ X, "xtwz": xw.T @ z, "deviance": float(dev.sum()), "n": int(X.shape[0])}
 
 
 # ------------------------------------------------------------------ data-plane flavour
