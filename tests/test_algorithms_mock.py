@@ -365,3 +365,40 @@ def test_glm_irls_named_columns_on_frames():
         frames.append(df[["event", "age", "dose", "noise"]])            # outcome is NOT the last column
     out = glm.master_irls(ClientMockProtocol(frames, glm), frames[0], family="binomial", columns=["age", "dose"], outcome="event")
     assert len(out["coefficients"]) == 2 and out["coefficients"][1] > 0.3
+
+
+def test_coxph_matches_pooled_partial_likelihood():
+    """Federated Newton iterations against a direct maximisation of the pooled Breslow partial likelihood (scipy)."""
+    import pandas as pd
+    from scipy.optimize import minimize
+
+    from vantage6_b200.algorithm.builtin import coxph
+
+    rng = np.random.default_rng(11)
+    b_true = np.array([0.7, -0.4, 0.0])
+    frames = []
+    for n in (180, 260, 140):
+        X = rng.normal(size=(n, 3))
+        t_event = rng.exponential(1.0 / np.exp(X @ b_true))
+        t_cens = rng.exponential(2.0, n)
+        frames.append(pd.DataFrame({"x1": X[:, 0], "x2": X[:, 1], "x3": X[:, 2], "time": np.round(np.minimum(t_event, t_cens), 2) + 0.01,
+                                    "event": (t_event <= t_cens).astype(int)}))
+    out = coxph.master(ClientMockProtocol(frames, coxph), frames[0], time_column="time", censor_column="event")
+    pooled = pd.concat(frames, ignore_index=True)
+    X, t, e = pooled[["x1", "x2", "x3"]].to_numpy(), pooled["time"].to_numpy(), pooled["event"].to_numpy().astype(bool)
+
+    def negll(b):
+        r = np.exp(X @ b)
+        return -sum((X[(t == u) & e] @ b).sum() - ((t == u) & e).sum() * np.log(r[t >= u].sum()) for u in np.unique(t[e]))
+
+    ref = minimize(negll, np.zeros(3), method="BFGS", options={"gtol": 1e-8})
+    np.testing.assert_allclose(out["coefficients"], ref.x, atol=2e-5)
+    np.testing.assert_allclose(out["log_likelihood"][-1], -ref.fun, rtol=1e-8)
+    assert out["columns"] == ["x1", "x2", "x3"] and out["n"] == 580 and out["n_events"] == int(e.sum()) and out["iterations"] <= 8
+    assert all(b > a - 1e-9 for a, b in zip(out["log_likelihood"], out["log_likelihood"][1:]))        # Newton climbs
+    assert np.all(np.abs(out["coefficients"] - b_true) < 4 * out["std_errors"])
+    np.testing.assert_allclose(out["hazard_ratios"], np.exp(out["coefficients"]))
+    with pytest.raises(PermissionError):
+        coxph.RPC_event_sums(frames[0].head(4), "time", "event")
+    sub = coxph.master(ClientMockProtocol(frames, coxph), frames[0], "time", "event", columns=["x1"], bin_width=0.25)
+    assert sub["columns"] == ["x1"] and sub["coefficients"][0] > 0.3
