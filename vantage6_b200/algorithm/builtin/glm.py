@@ -18,6 +18,7 @@ from typing import Any, Dict, Optional
 
 import numpy as np
 
+from ._common import collect
 from .fedavg import _free_port
 
 
@@ -39,8 +40,7 @@ def master(client, data, iterations: int = 10, lr: float = 1.0, organization_ids
     for _ in range(iterations):
         task = client.create_new_task(input_={"method": "gradient", "kwargs": {"w": None if w is None else w.tolist()}},
                                       organization_ids=ids)
-        client.wait_for_task(task["id"])
-        res = client.get_results(task_id=task["id"])
+        res = collect(client, task, ids)
         g = sum(np.asarray(r["grad"], dtype=np.float64) for r in res)
         n = sum(r["n"] for r in res)
         if w is None:
@@ -103,10 +103,7 @@ def master_irls(client, data, family: str = "binomial", columns=None, outcome=No
     for it in range(1, max_iterations + 1):
         kw = {"family": family, "columns": columns, "outcome": outcome, "beta": None if beta is None else beta.tolist()}
         task = client.create_new_task(input_={"method": "irls_partial", "kwargs": kw}, organization_ids=ids)
-        client.wait_for_task(task["id"])
-        parts = client.get_results(task_id=task["id"])
-        if len(parts) != len(ids):
-            raise RuntimeError(f"{len(ids) - len(parts)} of {len(ids)} nodes returned no result")
+        parts = collect(client, task, ids)
         xtwx = sum(np.asarray(p["xtwx"], dtype=np.float64) for p in parts)
         xtwz = sum(np.asarray(p["xtwz"], dtype=np.float64) for p in parts)
         n = sum(int(p["n"]) for p in parts)

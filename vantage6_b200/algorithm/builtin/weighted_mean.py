@@ -8,6 +8,8 @@ the partial returns ``(sum over rows, n_i)`` and the master forms ``sum_i sum_i 
 
 import numpy as np
 
+from ._common import collect
+
 
 def _as_matrix(data):
     if isinstance(data, dict):
@@ -23,8 +25,7 @@ def _as_matrix(data):
 def master(client, data, organization_ids=None):
     ids = organization_ids or [o.get("id") for o in client.get_organizations_in_my_collaboration()]
     task = client.create_new_task(input_={"method": "partial_sum"}, organization_ids=ids)
-    client.wait_for_task(task.get("id"))
-    results = client.get_results(task_id=task.get("id"))
+    results = collect(client, task, ids)
     total = sum(int(r["count"]) for r in results)
     acc = sum(np.asarray(r["sum"], dtype=np.float64) for r in results)
     return {"mean": acc / total, "count": total, "n_nodes": len(results)}
