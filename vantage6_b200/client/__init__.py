@@ -458,8 +458,11 @@ class ContainerClient(ClientBase):
         return _wait_for_task(self, task_id, sleep, timeout)
 
     def wait_for_results(self, task_id: int, sleep: float = 0.05, timeout: float = 3600.0) -> List[Any]:
-        self.wait_for_task(task_id, sleep=sleep, timeout=timeout)
-        return self.get_results(task_id)
+        """Wait for ``task_id`` and return the decoded outputs of its (non-empty) results -- the completeness check that
+        ends the wait already carries them, so there is no second request."""
+        task = _wait_for_task(self, task_id, sleep, timeout, include_results=True)
+        return [deserialize(self.cryptor.str_to_bytes(r["result"])) for r in task.get("results", [])
+                if isinstance(r, dict) and r.get("result")]
 
     def get_organizations_in_my_collaboration(self) -> List[dict]:
         return self.request(f"collaboration/{self.collaboration_id}/organization")

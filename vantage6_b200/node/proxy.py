@@ -103,6 +103,10 @@ class ProxyServer:
                         res["result"] = node.decrypt_to_plain_b64(res.get("result"))
                 elif re.fullmatch(r"/?result/\d+/?", sub) and isinstance(payload, dict):
                     payload["result"] = node.decrypt_to_plain_b64(payload.get("result"))
+                elif re.fullmatch(r"/?task/\d+/?", sub) and isinstance(payload, dict):
+                    for res in payload.get("results") or []:               # ?include=results: a task with its results inline
+                        if isinstance(res, dict) and "result" in res:
+                            res["result"] = node.decrypt_to_plain_b64(res.get("result"))
             return r.status_code, payload
         except Exception as e:  # noqa: BLE001
             log.exception("proxy failure")
