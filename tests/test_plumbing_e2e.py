@@ -223,3 +223,36 @@ def test_encrypted_collaboration_end_to_end(tmp_path):
             os.environ.pop("V6B200_HOME", None)
         else:
             os.environ["V6B200_HOME"] = old
+
+
+def test_finished_result_survives_a_server_outage():
+    """The final report is retried with backoff over connection errors and 5xx, not over a definite refusal."""
+    from types import SimpleNamespace
+
+    from vantage6_b200.client import ServerError
+    from vantage6_b200.node import Node
+
+    node = Node(SimpleNamespace(config={"server_url": "http://127.0.0.1", "port": 1, "api_path": "/api", "api_key": "k"}))
+    node.REPORT_BACKOFF_S = (0.01, 0.01, 0.01, 0.01)
+    calls = []
+
+    def flaky(endpoint, method="get", json=None, **_):
+        calls.append((endpoint, method, json["status"]))
+        if len(calls) == 1:
+            raise ConnectionRefusedError("server restarting")
+        if len(calls) == 2:
+            raise ServerError(502, "bad gateway")
+        return {}
+
+    node.client.request = flaky
+    assert node._report_final(7, {"finished_at": "now", "result": "r", "log": "", "status": "completed"}) is True
+    assert calls == [("result/7", "patch", "completed")] * 3
+    calls.clear()
+    node.client.request = lambda *a, **k: (calls.append(1), (_ for _ in ()).throw(ServerError(400, "Cannot update an already finished result!")))[1]
+    assert node._report_final(7, {"status": "completed"}) is False and len(calls) == 1          # refused for good: no retry
+    calls.clear()
+    node.client.request = lambda *a, **k: (calls.append(1), (_ for _ in ()).throw(ConnectionRefusedError()))[1]
+    assert node._report_final(7, {"status": "completed"}) is False and len(calls) == 5          # first try + the whole backoff
+    node._stop.set()
+    calls.clear()
+    assert node._report_final(7, {"status": "completed"}) is False and len(calls) == 1          # a stopping node does not linger

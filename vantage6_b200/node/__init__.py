@@ -260,6 +260,30 @@ class Node:
                 continue
             threading.Thread(target=self._run_result, args=(result,), daemon=True).start()
 
+    REPORT_BACKOFF_S = (0.5, 1, 2, 4, 8, 15, 30, 30, 30)      # a result outlives a server restart of about two minutes
+
+    def _report_final(self, rid: int, final: dict) -> bool:
+        """Hand a finished result to the server; a computed result is not thrown away because the server was unreachable
+        for a moment (restart, network blip): retried with backoff.  What the server refuses for good (4xx: the result was
+        deleted with its task, or is already finished) is not retried."""
+        for attempt, pause in enumerate((0,) + self.REPORT_BACKOFF_S):
+            if pause and self._stop.wait(pause):
+                break
+            try:
+                self.client.request(f"result/{rid}", method="patch", json=final)
+                if attempt:
+                    log.info("result %s reported after %d retries", rid, attempt)
+                return True
+            except ServerError as e:
+                if 400 <= e.status < 500 and e.status != 401:
+                    log.error("the server refused result %s: %s", rid, e)
+                    return False
+                log.warning("could not report result %s (%s); retrying", rid, e)
+            except Exception as e:  # noqa: BLE001 -- connection refused / reset / timeout
+                log.warning("could not report result %s (%s: %s); retrying", rid, type(e).__name__, e)
+        log.error("giving up on reporting result %s", rid)
+        return False
+
     def _report_started(self, rid: int) -> None:
         try:
             self.client.request(f"result/{rid}", method="patch", json={"started_at": _now(), "status": "active"})
@@ -351,13 +375,10 @@ class Node:
             self._task_of.pop(rid, None)
         if started is not None:
             started.join(timeout=30)
-        try:
-            final = {"finished_at": _now(), "result": out_b64, "log": logtxt[-20000:], "status": status}
-            if not start_reported:                   # refused before it began (image policy, unknown image, bad input)
-                final["started_at"] = final["finished_at"]
-            self.client.request(f"result/{rid}", method="patch", json=final)
-        except Exception as e:  # noqa: BLE001
-            log.error("could not report result %s: %s", rid, e)
+        final = {"finished_at": _now(), "result": out_b64, "log": logtxt[-20000:], "status": status}
+        if not start_reported:                       # refused before it began (image policy, unknown image, bad input)
+            final["started_at"] = final["finished_at"]
+        self._report_final(rid, final)
         mark("reported")
         log.info("task %s result %s: %s", task.get("id"), rid, status)
         if os.environ.get("V6B200_TRACE_TASKS") == "1":
