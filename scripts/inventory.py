@@ -4,7 +4,6 @@ symbol looked up in the tree (fails loudly when a symbol has moved).
     python scripts/inventory.py > docs/INVENTORY.md
 """
 import re
-import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent

@@ -1,14 +1,12 @@
 """Configuration manager, schema, contexts, utils, version (components the reference leaves
 untested: context.py, configuration_manager.py -- SURVEY.md section 4)."""
-import os
 from pathlib import Path
 
 import pytest
 import yaml
 
 from vantage6_b200 import __version__
-from vantage6_b200.cli.configuration_manager import (NodeConfiguration, NodeConfigurationManager, ServerConfiguration,
-                                                     ServerConfigurationManager)
+from vantage6_b200.cli.configuration_manager import NodeConfiguration, NodeConfigurationManager, ServerConfiguration
 from vantage6_b200.cli.context import NodeContext, ServerContext
 from vantage6_b200.cli.utils import check_config_name_allowed
 from vantage6_b200.common.schema import And, Optional, Or, Schema, SchemaError, Use

@@ -24,7 +24,6 @@ import click
 from .. import runtime as docker
 from ..common import check_config_write_permissions, error, info, warning  # noqa: F401
 from ..common import debug as debug_msg
-from ..common import prompts as q
 from ..common.globals import APPNAME, DEFAULT_DOCKER_REGISTRY, DEFAULT_SERVER_IMAGE
 from ..runtime import LocalRuntime as DockerClient
 from ..runtime.addons import (NetworkManager, check_docker_running, get_server_config_name, pull_if_newer,  # noqa: F401
