@@ -22,5 +22,6 @@ setup(
         "vserver=vantage6_b200.cli.server:cli_server",
         "vnode-local=vantage6_b200.cli.node_local:main",
         "vserver-local=vantage6_b200.cli.server_local:main",
+        "vdev=vantage6_b200.cli.dev:cli_dev",
     ]},
 )

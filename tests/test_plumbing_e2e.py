@@ -256,3 +256,51 @@ def test_finished_result_survives_a_server_outage():
     node._stop.set()
     calls.clear()
     assert node._report_final(7, {"status": "completed"}) is False and len(calls) == 1          # a stopping node does not linger
+
+
+def test_vdev_create_start_use_stop_remove(tmp_path):
+    """The developer CLI end to end: separate invocations share the saved network description."""
+    from click.testing import CliRunner
+
+    from vantage6_b200.cli.dev import cli_dev
+    from vantage6_b200.client import UserClient
+
+    home = str(tmp_path / "devhome")
+    old = os.environ.get("V6B200_HOME")
+    run = lambda *args: CliRunner().invoke(cli_dev, list(args), catch_exceptions=False)      # noqa: E731
+    try:
+        r = run("start-demo-network", "-n", "nope", "--home", home)
+        assert r.exit_code == 1 and "No demo network" in r.output
+        r = run("create-demo-network", "-n", "devnet", "--home", home, "--nodes", "3", "--gpus", "0,1")
+        assert r.exit_code == 1 and "--gpus names 2 devices for 3 nodes" in r.output
+        for i, n in enumerate((5, 9)):
+            np.save(tmp_path / f"v{i}.npy", np.full((n, 4), float(i + 1)))
+        r = run("create-demo-network", "-n", "devnet", "--home", home, "--nodes", "2", "--database", str(tmp_path / "v0.npy"),
+                "--database", str(tmp_path / "v1.npy"))
+        assert r.exit_code == 0 and "Created demo network 'devnet'" in r.output, r.output
+        r = run("start-demo-network", "-n", "devnet", "--home", home)
+        assert r.exit_code == 0 and "is up" in r.output, r.output
+        net = DemoNetwork.load("devnet", home)
+        c = UserClient("http://127.0.0.1", net.port, "/api")
+        c.authenticate("user-0", net.password)
+        c.setup_encryption(None)
+        assert sorted(n["status"] for n in c.node.list()) == ["online", "online"]
+        collab = c.collaboration.list()[0]
+        task = c.task.create(collaboration=collab["id"], organizations=[o["id"] for o in collab["organizations"]], name="t",
+                             image="v6b200/weighted-mean", input={"method": "partial_sum"}, database="default")
+        res = c.wait_for_results(task["id"], timeout=60)
+        assert sorted(r_["result"]["count"] for r_ in res) == [5, 9], [r_["log"] for r_ in res]
+        r = run("stop-demo-network", "-n", "devnet", "--home", home)
+        assert r.exit_code == 0 and "stopped" in r.output
+        with pytest.raises(Exception):
+            c.node.list()                                                     # the server is gone
+        r = run("remove-demo-network", "-n", "devnet", "--home", home)
+        assert r.exit_code == 0
+        assert not (tmp_path / "devhome" / "devnet-network.json").exists()
+        assert not list((tmp_path / "devhome").rglob("devnet*.yaml"))
+    finally:
+        CliRunner().invoke(cli_dev, ["stop-demo-network", "-n", "devnet", "--home", home])
+        if old is None:
+            os.environ.pop("V6B200_HOME", None)
+        else:
+            os.environ["V6B200_HOME"] = old

@@ -109,14 +109,39 @@ class DemoNetwork:
             raise RuntimeError(f"{cmd.name} {' '.join(args)} failed ({r.exit_code}):\n{r.output}")
         return r
 
-    def start(self, timeout: float = 60.0) -> "DemoNetwork":
-        from .cli.node import cli_node_start
-        from .cli.server import cli_server_import, cli_server_start
+    # -- persistence: `vdev create-demo-network` and `vdev start-demo-network` are separate invocations --------------
+    def description_file(self) -> Path:
+        return self.home / f"{self.name}-network.json"
+
+    def save(self) -> Path:
+        import json
+
+        doc = {k: getattr(self, k) for k in ("n_nodes", "name", "gpus", "databases", "encrypted", "rabbitmq", "port", "api_keys",
+                                             "org_names", "password", "key_bits")}
+        self.description_file().write_text(json.dumps(doc, indent=1))
+        return self.description_file()
+
+    @classmethod
+    def load(cls, name: str = "demo", home: Optional[str] = None) -> "DemoNetwork":
+        import json
+
+        root = Path(home or os.environ.get(HOME_ENV) or Path.cwd() / ".v6b200")
+        doc = json.loads((root / f"{name}-network.json").read_text())
+        net = cls(doc["n_nodes"], home=str(root), name=doc["name"], gpus=doc["gpus"], databases=doc["databases"],
+                  encrypted=doc["encrypted"], rabbitmq=doc["rabbitmq"])
+        for k in ("port", "api_keys", "org_names", "password", "key_bits"):
+            setattr(net, k, doc[k])
+        net.fixtures_file = net.home / f"{net.name}-entities.yaml"
+        return net
+
+    def create(self, timeout: float = 60.0) -> "DemoNetwork":
+        """Configuration files, keys, the entities file and the imported database -- everything but running processes."""
+        from .cli.server import cli_server_import
         from .runtime import from_env
 
         self.write_configs()
+        self.save()
         self._invoke(cli_server_import, ["--user", "-n", self.name, "--drop-all", str(self.fixtures_file)])
-        # the import runs as its own process: wait for it to finish before the server opens the DB
         rt = from_env()
         t0 = time.time()
         while any(c.labels.get("name") == self.name and "import" in " ".join(c.meta["command"])
@@ -124,6 +149,16 @@ class DemoNetwork:
             if time.time() - t0 > timeout:
                 raise TimeoutError("vserver import did not finish")
             time.sleep(0.1)
+        return self
+
+    def start(self, timeout: float = 60.0) -> "DemoNetwork":
+        return self.create(timeout).up(timeout)
+
+    def up(self, timeout: float = 60.0) -> "DemoNetwork":
+        """Start the server and the nodes of a created network."""
+        from .cli.node import cli_node_start
+        from .cli.server import cli_server_start
+
         self._invoke(cli_server_start, ["--user", "-n", self.name])
         client = self.client(timeout=timeout)
         orgs = {o["name"]: o["id"] for o in client.organization.list()}
@@ -173,3 +208,23 @@ class DemoNetwork:
 
         CliRunner().invoke(cli_node_stop, ["--all"])
         CliRunner().invoke(cli_server_stop, ["--user", "--all"])
+
+    def remove(self) -> None:
+        """Stop everything and delete what ``create`` wrote (configurations, keys, entities, database, logs, runtime files)."""
+        import shutil
+
+        self.stop()
+        for path in (self._cfg_dir("server") / f"{self.name}.yaml", self.fixtures_file if hasattr(self, "fixtures_file") else None,
+                     self.description_file(), *[self._cfg_dir("node") / f"{self.name}-node-{i}.yaml" for i in range(self.n_nodes)]):
+            if path is not None and Path(path).exists():
+                Path(path).unlink()
+        for sub in ("keys", "tasks"):
+            shutil.rmtree(self.home / sub, ignore_errors=True)
+        for kind in ("server", "node"):
+            for scope in ("user", "system"):
+                for base in ("data", "log"):
+                    root = self.home / scope / base / kind
+                    if root.is_dir():
+                        for d in root.iterdir():
+                            if d.name == self.name or d.name.startswith(f"{self.name}-node-"):
+                                shutil.rmtree(d, ignore_errors=True)
