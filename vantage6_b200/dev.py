@@ -172,7 +172,10 @@ class DemoNetwork:
         t0 = time.time()
         while True:
             online = [n for n in client.node.list() if n["status"] == "online"]
-            if len(online) >= self.n_nodes:
+            # a node is online as soon as it has a token; in an encrypted collaboration it is usable once it has also
+            # published its organization's public key (the next thing it does)
+            keyed = not self.encrypted or all(o.get("public_key") for o in client.organization.list() if o["name"] in self.org_names)
+            if len(online) >= self.n_nodes and keyed:
                 break
             if time.time() - t0 > timeout:
                 raise TimeoutError(f"only {len(online)}/{self.n_nodes} nodes came online:\n{self.tail_logs()}")
