@@ -561,7 +561,7 @@ def test_fewer_round_trips_per_work_item(server):
     node_b.request(f"result/{other}", method="patch", json={"finished_at": "now", "result": DummyCryptor().bytes_to_str(serialize({"v": 2}))})
     waiter.join(timeout=20)
     assert sorted(r["result"]["v"] for r in got["rows"]) == [1, 2]
-    assert calls.count(f"task/{task['id']}") == 2 and f"task/{task['id']}/result" not in calls   # first check + the completing event
+    assert calls.count(f"task/{task['id']}") <= 2 and f"task/{task['id']}/result" not in calls   # first check + the completing event
     done = [e for e in node.request("event", params={"since": since, "timeout": 1})["events"] if e["name"] == "status_update"]
     assert [e["data"]["task_complete"] for e in done] == [False, False, True]              # started, first result, last result
 
