@@ -632,3 +632,16 @@ def test_grant_cap_holds_for_random_rule_sets():
             assert sorted(x["id"] for x in payload["rules"]) == sorted(wanted)
 
     check()
+
+
+def test_event_log_keeps_only_recent_work_item_payloads():
+    from vantage6_b200.server.app import EventBus
+
+    bus = EventBus()
+    bus.HEAVY_KEPT = 3
+    for i in range(5):
+        bus.emit("new_task", {"result_id": i, "result": {"input": "x" * 100}}, ["node_1"])
+        bus.emit("new_task", {"result_id": i}, ["collaboration_1"])
+    evs = bus.wait(0, ["node_1"], 0.0)
+    assert [("result" in e["data"]) for e in evs] == [False, False, True, True, True]       # old payloads dropped, ids kept
+    assert [e["data"]["result_id"] for e in evs] == [0, 1, 2, 3, 4]

@@ -72,8 +72,11 @@ class HTTPError(Exception):
 class EventBus:
     """In-memory event log with blocking reads (long-poll)."""
 
+    HEAVY_KEPT = 256
+
     def __init__(self, maxlen: int = 10000):
         self._events: collections.deque = collections.deque(maxlen=maxlen)
+        self._heavy: collections.deque = collections.deque()       # recent events that carry a work item (see emit)
         self._cond = threading.Condition()
         self._next_id = 1
         self.mirror: Optional[Callable[[dict], None]] = None
@@ -84,6 +87,13 @@ class EventBus:
             ev = {"id": self._next_id, "name": name, "data": data, "rooms": rooms, "ts": time.time()}
             self._next_id += 1
             self._events.append(ev)
+            if "result" in data:
+                # a work item rides on its event so that the node can start at once; the log keeps thousands of events, the
+                # payloads only of the most recent ones (a listener that far behind fetches the item by id instead)
+                self._heavy.append(ev)
+                if len(self._heavy) > self.HEAVY_KEPT:
+                    old = self._heavy.popleft()
+                    old["data"] = {k: v for k, v in old["data"].items() if k != "result"}
             self._cond.notify_all()
         if self.push is not None:
             try:
