@@ -225,6 +225,15 @@ def test_summary_matches_pooled_statistics():
         assert out["columns"][c]["min"] == pooled[c].min() and out["columns"][c]["max"] == pooled[c].max()
     assert out["columns"]["bmi"]["missing"] == int(pooled["bmi"].isna().sum()) > 0
     assert out["columns"]["sex"]["counts"] == pooled["sex"].value_counts().to_dict()
+    q = summary.master(ClientMockProtocol(frames, summary), frames[0], columns=["age", "bmi"], quantiles=[0.0, 0.25, 0.5, 0.9, 1.0])
+    for c in ("age", "bmi"):
+        cell = (pooled[c].max() - pooled[c].min()) / 512
+        vals = pooled[c].dropna().to_numpy()
+        for k, v in q["columns"][c]["quantiles"].items():          # within a cell of a value whose empirical rank is q
+            assert (vals <= v + cell).mean() >= float(k) - 1e-12 and (vals < v - cell).mean() <= float(k) + 1e-12, (c, k, v)
+        assert q["columns"][c]["quantiles"]["0.0"] <= vals.min() + cell and q["columns"][c]["quantiles"]["1.0"] >= vals.max() - cell
+    with pytest.raises(ValueError):
+        summary.master(ClientMockProtocol(frames, summary), frames[0], columns=["age"], quantiles=[1.5])
     # privacy guards: a tiny node refuses, rare levels are suppressed
     with pytest.raises(PermissionError):
         summary.RPC_summary_partial(frames[0].head(5))

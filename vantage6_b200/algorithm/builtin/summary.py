@@ -10,6 +10,8 @@ Privacy guard (the node's side of the bargain): a node refuses to answer when it
 """
 import math
 
+import numpy as np
+
 from ._common import collect
 
 MIN_ROWS, MIN_COUNT = 10, 5
@@ -27,7 +29,11 @@ def _numeric(series) -> bool:
     return series.dtype.kind in "biuf"
 
 
-def master(client, data, columns=None, organization_ids=None, min_rows: int = MIN_ROWS, min_count: int = MIN_COUNT):
+def master(client, data, columns=None, organization_ids=None, min_rows: int = MIN_ROWS, min_count: int = MIN_COUNT,
+           quantiles=None, bins: int = 512):
+    """``quantiles`` (e.g. ``[0.25, 0.5, 0.75]``) adds a third round: every node histograms its numeric columns on a common
+    grid of ``bins`` cells between the pooled minimum and maximum, the master reads the quantiles off the pooled histogram
+    (linear within a cell: the answer is within one cell width, (max - min) / bins, of a value whose pooled rank is q)."""
     ids = organization_ids or [o.get("id") for o in client.get_organizations_in_my_collaboration()]
     kw = {"columns": columns, "min_rows": min_rows, "min_count": min_count}
     t = client.create_new_task(input_={"method": "summary_partial", "kwargs": kw}, organization_ids=ids)
@@ -48,6 +54,17 @@ def master(client, data, columns=None, organization_ids=None, min_rows: int = MI
         ss = sum(p.get(c, 0.0) for p in devs)
         n = out[c]["count"]
         out[c]["std"] = math.sqrt(ss / (n - 1)) if n > 1 else float("nan")
+    if quantiles:
+        qs = [float(q) for q in quantiles]
+        if any(not 0.0 <= q <= 1.0 for q in qs):
+            raise ValueError("quantiles must lie in [0, 1]")
+        ranges = {c: (out[c]["min"], out[c]["max"]) for c in numeric if out[c]["count"]}
+        t3 = client.create_new_task(input_={"method": "histogram_partial", "kwargs": {"ranges": ranges, "bins": bins, "min_rows": min_rows}},
+                                    organization_ids=ids)
+        hists = collect(client, t3, ids)
+        for c, (lo, hi) in ranges.items():
+            counts = [sum(h[c][i] for h in hists) for i in range(bins)]
+            out[c]["quantiles"] = {str(q): _quantile(counts, lo, hi, q) for q in qs}
     for c in sorted(set().union(*[set(p["categorical"]) for p in parts])):
         levels, suppressed = {}, False
         for p in parts:
@@ -59,6 +76,32 @@ def master(client, data, columns=None, organization_ids=None, min_rows: int = MI
                 levels[k] = levels.get(k, 0) + int(v)
         out[c] = {"counts": levels, "suppressed": suppressed}
     return {"n_rows": sum(p["n_rows"] for p in parts), "n_nodes": len(parts), "columns": out}
+
+
+def _quantile(counts, lo: float, hi: float, q: float) -> float:
+    total = sum(counts)
+    if total == 0 or hi <= lo:
+        return lo
+    target, width, acc = q * total, (hi - lo) / len(counts), 0.0
+    for i, n in enumerate(counts):
+        if n and acc + n >= target:
+            return lo + (i + (target - acc) / n) * width
+        acc += n
+    return hi
+
+
+def RPC_histogram_partial(data, ranges: dict, bins: int = 512, min_rows: int = MIN_ROWS):
+    if len(data) < min_rows:
+        raise PermissionError(f"this node holds fewer than {min_rows} rows: refusing to report statistics")
+    out = {}
+    for c, (lo, hi) in ranges.items():
+        v = data[c].dropna().to_numpy(dtype=float)
+        if hi <= lo:
+            out[c] = [int(len(v))] + [0] * (bins - 1)
+            continue
+        idx = ((v - lo) / (hi - lo) * bins).astype(int).clip(0, bins - 1)
+        out[c] = [int(n) for n in np.bincount(idx, minlength=bins)]
+    return out
 
 
 def RPC_summary_partial(data, columns=None, min_rows: int = MIN_ROWS, min_count: int = MIN_COUNT):
