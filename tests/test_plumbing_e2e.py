@@ -210,9 +210,14 @@ def test_encrypted_collaboration_end_to_end(tmp_path):
         db = next((tmp_path / "home").rglob("demo.sqlite"))
         rows = sqlite3.connect(db).execute("SELECT input, result FROM result").fetchall()
         assert len(rows) == 3
+        import base64
+
         for inp, result in rows:
             for blob in (inp, result):
-                assert blob and "method" not in blob and "mean" not in blob and "sum" not in blob and "$" in blob
+                key, iv, body = blob.split("$")                                 # sealed key, iv, ciphertext -- base64 each
+                assert len(base64.b64decode(key)) == 256 and len(base64.b64decode(iv)) == 16
+                raw = base64.b64decode(body)
+                assert raw and not any(marker in raw for marker in (b'"method"', b'"mean"', b'"sum"', b'"count"', b"__ndarray__"))
         # a researcher of the other organization cannot read what was sealed for organization 0
         other = net.client(user=1)
         sealed = other.result.get(res[0]["id"])["result"]
