@@ -10,6 +10,14 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    try:        # property tests: the same examples on every run (a suite that is green stays green); HYPOTHESIS_PROFILE=explore
+        from hypothesis import settings          # draws fresh ones to go hunting
+
+        settings.register_profile("repeatable", derandomize=True, database=None, deadline=None)
+        settings.register_profile("explore", deadline=None)
+        settings.load_profile(os.environ.get("HYPOTHESIS_PROFILE", "repeatable"))
+    except ImportError:
+        pass
 
 
 def pytest_collection_modifyitems(config, items):
