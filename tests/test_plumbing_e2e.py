@@ -309,3 +309,33 @@ def test_vdev_create_start_use_stop_remove(tmp_path):
             os.environ.pop("V6B200_HOME", None)
         else:
             os.environ["V6B200_HOME"] = old
+
+
+def test_tls_network_end_to_end(tmp_path):
+    """The whole stack over TLS (``vdev ... --tls`` / ``DemoNetwork(tls=True)``): researcher -> server https, node -> server
+    https + wss events, algorithm -> node proxy -> server https, all verified against the server's certificate."""
+    for i, n in enumerate((4, 6)):
+        np.save(tmp_path / f"v{i}.npy", np.full((n, 3), float(i + 1)))
+    old = os.environ.get("V6B200_HOME")
+    net = DemoNetwork(2, home=str(tmp_path / "home"), name="tlsnet", databases=[str(tmp_path / "v0.npy"), str(tmp_path / "v1.npy")], tls=True)
+    try:
+        net.start()
+        c = net.client()
+        assert c.host.startswith("https://")
+        task = c.task.create(collaboration=net.collaboration_id, organizations=[net.org_ids[0]], name="t",
+                             image="v6b200/weighted-mean", input={"method": "master", "master": True})
+        res = c.wait_for_results(task["id"], timeout=120)
+        assert res[0]["result"] is not None, res[0]["log"]
+        np.testing.assert_allclose(res[0]["result"]["mean"], np.full(3, (4 * 1.0 + 6 * 2.0) / 10))
+        logs = net.tail_logs(200)
+        assert "event channel: websocket" in logs and "listening on https://" in logs
+        from vantage6_b200.client import UserClient
+
+        with pytest.raises(Exception):                      # no CA file: the self-signed certificate is not trusted
+            UserClient("https://127.0.0.1", net.port, "/api").util.get_server_version()
+    finally:
+        net.stop()
+        if old is None:
+            os.environ.pop("V6B200_HOME", None)
+        else:
+            os.environ["V6B200_HOME"] = old

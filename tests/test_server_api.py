@@ -645,3 +645,69 @@ def test_event_log_keeps_only_recent_work_item_payloads():
     evs = bus.wait(0, ["node_1"], 0.0)
     assert [("result" in e["data"]) for e in evs] == [False, False, True, True, True]       # old payloads dropped, ids kept
     assert [e["data"]["result_id"] for e in evs] == [0, 1, 2, 3, 4]
+
+
+def _self_signed(tmp_path):
+    import datetime
+    import ipaddress
+
+    from cryptography import x509
+    from cryptography.hazmat.primitives import hashes, serialization
+    from cryptography.hazmat.primitives.asymmetric import rsa
+    from cryptography.x509.oid import NameOID
+
+    key = rsa.generate_private_key(public_exponent=65537, key_size=2048)
+    name = x509.Name([x509.NameAttribute(NameOID.COMMON_NAME, "vantage6-b200 test server")])
+    now = datetime.datetime.now(datetime.timezone.utc)
+    cert = (x509.CertificateBuilder().subject_name(name).issuer_name(name).public_key(key.public_key())
+            .serial_number(x509.random_serial_number()).not_valid_before(now - datetime.timedelta(minutes=5))
+            .not_valid_after(now + datetime.timedelta(days=2))
+            .add_extension(x509.SubjectAlternativeName([x509.IPAddress(ipaddress.ip_address("127.0.0.1")), x509.DNSName("localhost")]), False)
+            .add_extension(x509.BasicConstraints(ca=True, path_length=None), True)
+            .sign(key, hashes.SHA256()))
+    certfile, keyfile = tmp_path / "server.crt", tmp_path / "server.key"
+    certfile.write_bytes(cert.public_bytes(serialization.Encoding.PEM))
+    keyfile.write_bytes(key.private_bytes(serialization.Encoding.PEM, serialization.PrivateFormat.TraditionalOpenSSL, serialization.NoEncryption()))
+    return str(certfile), str(keyfile)
+
+
+def test_tls_for_rest_and_event_channel(tmp_path):
+    """``ssl: {certfile, keyfile}`` in the server configuration: REST over https and events over wss, verified against the
+    certificate the client was given -- and refused without it."""
+    import json as _json
+    import ssl
+
+    from websockets.sync.client import connect
+
+    certfile, keyfile = _self_signed(tmp_path)
+    app = ServerApp({"uri": "sqlite://", "api_path": "/api", "jwt_secret_key": "s" * 40, "ssl": {"certfile": certfile, "keyfile": keyfile}})
+    port = app.start("127.0.0.1", 0)
+    try:
+        c = UserClient("https://127.0.0.1", port, "/api", ca_file=certfile)
+        c.authenticate("root", "root")
+        c.setup_encryption(None)
+        assert c.util.get_server_health()["database"] is True
+        for _ in range(3):                                             # kept-alive TLS connection is reused
+            assert c.util.get_server_version()["version"] == "3.1.0"
+        assert c._http.idle_connections() == 1
+        with pytest.raises(ssl.SSLCertVerificationError):              # unknown issuer without the CA file
+            UserClient("https://127.0.0.1", port, "/api").util.get_server_version()
+        with pytest.raises(Exception):                                 # plain http against the TLS port
+            UserClient("http://127.0.0.1", port, "/api").util.get_server_version()
+        org = c.organization.create("O")
+        collab = c.collaboration.create("C", [org["id"]])
+        node = c.node.create(collab["id"], org["id"])
+        nc = NodeClient("https://127.0.0.1", port, "/api", ca_file=certfile)
+        nc.authenticate(node["api_key"])
+        ev_port = c.util.get_server_health()["event_port"]
+        with connect(f"wss://127.0.0.1:{ev_port}/?token={nc.token}&since={app.events.last_id()}", ssl=nc._http.ssl_context(), open_timeout=10) as ws:
+            # the root user is in organization "root": create the task as a member of the collaboration instead
+            c.user.create("res", "pw-res", organization=org["id"], roles=[r["id"] for r in c.role.list() if r["name"] == "Researcher"])
+            res = UserClient("https://127.0.0.1", port, "/api", ca_file=certfile)
+            res.authenticate("res", "pw-res")
+            res.setup_encryption(None)
+            task = res.task.create(collaboration=collab["id"], organizations=[org["id"]], name="t", image="img", input={"m": 1})
+            ev = _json.loads(ws.recv(timeout=10))
+            assert ev["name"] == "new_task" and ev["data"]["task_id"] == task["id"] and "result" in ev["data"]
+    finally:
+        app.stop()

@@ -33,7 +33,8 @@ def _common(fn):
 @click.option("--gpus", default=None, help="comma-separated GPU indices, one per node (default: CPU nodes)")
 @click.option("--database", "databases", multiple=True, help="database of node i (repeat per node; default: synthetic://node-i)")
 @click.option("--encrypted/--not-encrypted", default=False, show_default=True, help="encrypted collaboration (RSA keys per organization)")
-def create(name, home, n_nodes, gpus, databases, encrypted):
+@click.option("--tls/--no-tls", default=False, show_default=True, help="https / wss with a self-signed certificate")
+def create(name, home, n_nodes, gpus, databases, encrypted, tls):
     """Write the configurations, keys and entities of a network and import them into a fresh server database."""
     gpu_list = [int(g) for g in gpus.split(",")] if gpus else None
     if gpu_list is not None and len(gpu_list) != n_nodes:
@@ -42,7 +43,7 @@ def create(name, home, n_nodes, gpus, databases, encrypted):
     if databases and len(databases) != n_nodes:
         error(f"--database given {len(databases)} times for {n_nodes} nodes")
         raise SystemExit(1)
-    net = DemoNetwork(n_nodes, home=home, name=name, gpus=gpu_list, databases=list(databases) or None, encrypted=encrypted)
+    net = DemoNetwork(n_nodes, home=home, name=name, gpus=gpu_list, databases=list(databases) or None, encrypted=encrypted, tls=tls)
     net.create()
     info(f"Created demo network {name!r}: {n_nodes} node(s), server port {net.port}, description {net.description_file()}")
     info(f"Start it with `vdev start-demo-network -n {name}`; researcher login user-0 / {net.password}")
@@ -61,7 +62,7 @@ def _load(name, home) -> DemoNetwork:
 def start(name, home):
     """Start the server and every node of a created network and wait until all nodes are online."""
     net = _load(name, home).up()
-    info(f"Demo network {name!r} is up: http://127.0.0.1:{net.port}/api, collaboration id {net.collaboration_id}, "
+    info(f"Demo network {name!r} is up: {net.server_url}:{net.port}/api, collaboration id {net.collaboration_id}, "
          f"organizations {net.org_ids}")
 
 

@@ -58,7 +58,8 @@ def start(config, environment, ip, port, system_folders):
 
         attach_app(app, ctx.config["rabbitmq_uri"])
     signal.signal(signal.SIGTERM, lambda *_: sys.exit(0))
-    print(f"vantage6-b200 server '{ctx.name}' v{__version__} listening on http://{ip}:{port}{app.api_path}", flush=True)
+    scheme = "https" if (ctx.config.get("ssl") or {}).get("certfile") else "http"
+    print(f"vantage6-b200 server '{ctx.name}' v{__version__} listening on {scheme}://{ip}:{port}{app.api_path}", flush=True)
     app.start(ip, port, block=True)
 
 

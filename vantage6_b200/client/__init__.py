@@ -65,7 +65,7 @@ def _wait_for_task(client: "ClientBase", task_id: int, sleep: float, timeout: fl
 
 
 class ClientBase:
-    def __init__(self, host: str, port: Optional[int] = 5000, path: str = "/api"):
+    def __init__(self, host: str, port: Optional[int] = 5000, path: str = "/api", ca_file: Optional[str] = None):
         self.log = logging.getLogger(module_name)
         self.__host, self.__port, self.__api_path = host.rstrip("/"), port, path
         self._access_token: Optional[str] = None
@@ -73,7 +73,7 @@ class ClientBase:
         self.__refresh_url: Optional[str] = None
         self.cryptor: Optional[CryptorBase] = None
         self.whoami: Optional[SimpleNamespace] = None
-        self._http = JsonHttp()                  # keep-alive connection per thread; never routed through a proxy
+        self._http = JsonHttp(ca_file)           # keep-alive connections; never routed through a proxy; https verified against ca_file
 
     # -- addresses ---------------------------------------------------------------------------
     @property
@@ -172,8 +172,8 @@ class UserClient(ClientBase):
     """Researcher client."""
 
     def __init__(self, host: str = "http://localhost", port: Optional[int] = 5000, path: str = "/api",
-                 verbose: bool = False):
-        super().__init__(host, port, path)
+                 verbose: bool = False, ca_file: Optional[str] = None):
+        super().__init__(host, port, path, ca_file=ca_file)
         self.util = self.Util(self)
         self.collaboration = self.Collaboration(self)
         self.organization = self.Organization(self)

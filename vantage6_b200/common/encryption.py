@@ -119,4 +119,39 @@ class RSACryptor(CryptorBase):
         return dec.update(self.str_to_bytes(ciphertext)) + dec.finalize()
 
 
-__all__ = ["CryptorBase", "DummyCryptor", "RSACryptor", "STRING_ENCODING"]
+def create_self_signed_certificate(certfile, keyfile, hosts=("127.0.0.1", "localhost"), days: int = 365, bits: int = 2048) -> None:
+    """A self-signed server certificate (subject alternative names ``hosts``) for demo networks and tests; production
+    servers get theirs from a CA.  The certificate doubles as the ``ca_file`` the clients verify against."""
+    import datetime
+    import ipaddress
+
+    from cryptography import x509
+    from cryptography.hazmat.primitives import hashes
+    from cryptography.x509.oid import NameOID
+
+    key = rsa.generate_private_key(public_exponent=65537, key_size=bits, backend=default_backend())
+    name = x509.Name([x509.NameAttribute(NameOID.COMMON_NAME, "vantage6-b200 server")])
+    now = datetime.datetime.now(datetime.timezone.utc)
+    sans = []
+    for h in hosts:
+        try:
+            sans.append(x509.IPAddress(ipaddress.ip_address(h)))
+        except ValueError:
+            sans.append(x509.DNSName(h))
+    cert = (x509.CertificateBuilder().subject_name(name).issuer_name(name).public_key(key.public_key())
+            .serial_number(x509.random_serial_number()).not_valid_before(now - datetime.timedelta(minutes=5))
+            .not_valid_after(now + datetime.timedelta(days=days))
+            .add_extension(x509.SubjectAlternativeName(sans), critical=False)
+            .add_extension(x509.BasicConstraints(ca=True, path_length=None), critical=True)
+            .sign(key, hashes.SHA256()))
+    Path(certfile).parent.mkdir(parents=True, exist_ok=True)
+    Path(certfile).write_bytes(cert.public_bytes(serialization.Encoding.PEM))
+    Path(keyfile).write_bytes(key.private_bytes(encoding=serialization.Encoding.PEM, format=serialization.PrivateFormat.TraditionalOpenSSL,
+                                                encryption_algorithm=serialization.NoEncryption()))
+    try:
+        os.chmod(keyfile, 0o600)
+    except OSError:
+        pass
+
+
+__all__ = ["CryptorBase", "DummyCryptor", "RSACryptor", "STRING_ENCODING", "create_self_signed_certificate"]

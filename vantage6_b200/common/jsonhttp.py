@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import http.client
 import json as _json
+import os
 import select
 import socket
 import threading
@@ -44,9 +45,20 @@ class JsonHttp:
 
     MAX_IDLE = 8           # per (scheme, host, port)
 
-    def __init__(self):
+    def __init__(self, ca_file: Optional[str] = None):
+        """``ca_file``: PEM bundle to verify an ``https`` server against (a private CA or the server's self-signed
+        certificate); default: the system trust store.  ``$V6B200_CA_FILE`` supplies it where no argument can."""
         self._idle: Dict[Tuple[str, str, int], list] = {}
         self._lock = threading.Lock()
+        self.ca_file = ca_file or os.environ.get("V6B200_CA_FILE") or None
+        self._ssl_context = None
+
+    def ssl_context(self):
+        if self._ssl_context is None:
+            import ssl
+
+            self._ssl_context = ssl.create_default_context(cafile=self.ca_file)
+        return self._ssl_context
 
     # ------------------------------------------------------------------ connections
     @staticmethod
@@ -55,6 +67,8 @@ class JsonHttp:
         sock = conn.sock
         if sock is None:
             return True
+        if hasattr(sock, "pending"):        # TLS: post-handshake records (session tickets) make a healthy socket readable;
+            return False                    # a dead one is caught by the retry in request()
         try:
             ready, _, _ = select.select([sock], [], [], 0)
             return bool(ready)
@@ -73,8 +87,10 @@ class JsonHttp:
                 return conn, True
             conn.close()
         scheme, host, port = key
-        cls = http.client.HTTPSConnection if scheme == "https" else http.client.HTTPConnection
-        conn = cls(host, port, timeout=timeout)
+        if scheme == "https":
+            conn = http.client.HTTPSConnection(host, port, timeout=timeout, context=self.ssl_context())
+        else:
+            conn = http.client.HTTPConnection(host, port, timeout=timeout)
         conn.connect()
         try:
             conn.sock.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)

@@ -38,7 +38,7 @@ def free_port() -> int:
 
 class DemoNetwork:
     def __init__(self, n_nodes: int = 2, home: Optional[str] = None, name: str = "demo", gpus: Optional[List[int]] = None,
-                 databases: Optional[List[str]] = None, encrypted: bool = False, rabbitmq: bool = False):
+                 databases: Optional[List[str]] = None, encrypted: bool = False, rabbitmq: bool = False, tls: bool = False):
         self.n_nodes, self.name = n_nodes, name
         self.home = Path(home or os.environ.get(HOME_ENV) or Path.cwd() / ".v6b200")
         os.environ[HOME_ENV] = str(self.home)
@@ -46,6 +46,7 @@ class DemoNetwork:
         self.databases = databases or [""] * n_nodes
         self.encrypted = encrypted
         self.rabbitmq = rabbitmq
+        self.tls = tls                           # https / wss with a self-signed certificate the nodes and clients verify against
         self.port = free_port()
         self.api_keys = [str(uuid.uuid4()) for _ in range(n_nodes)]
         self.org_names = [f"org-{i}" for i in range(n_nodes)]
@@ -61,6 +62,14 @@ class DemoNetwork:
         d.mkdir(parents=True, exist_ok=True)
         return d
 
+    @property
+    def server_url(self) -> str:
+        return ("https" if self.tls else "http") + "://127.0.0.1"
+
+    @property
+    def cert_file(self) -> str:
+        return str(self.home / "keys" / "server.crt")
+
     def key_file(self, org: int) -> str:
         """RSA key of organization ``org`` (shared by its node and its researchers, as in vantage6); created on first use."""
         path = self.home / "keys" / f"privkey_{self.org_names[org]}.pem"
@@ -74,12 +83,19 @@ class DemoNetwork:
         server_cfg = {"description": "demo network", "ip": "127.0.0.1", "port": self.port, "api_path": "/api",
                       "uri": "sqlite:///demo.sqlite", "allow_drop_all": True, "jwt_secret_key": str(uuid.uuid4()),
                       "logging": dict(LOGGING, file=f"{self.name}.log")}
+        if self.tls:
+            from .common.encryption import create_self_signed_certificate
+
+            if not Path(self.cert_file).exists():
+                create_self_signed_certificate(self.cert_file, str(self.home / "keys" / "server.key"))
+            server_cfg["ssl"] = {"certfile": self.cert_file, "keyfile": str(self.home / "keys" / "server.key")}
         if self.rabbitmq:
             server_cfg["rabbitmq_uri"] = f"amqp://demo:demo@127.0.0.1:{free_port()}/demo"
         with open(self._cfg_dir("server") / f"{self.name}.yaml", "w") as f:
             yaml.safe_dump({"application": {}, "environments": {"prod": server_cfg, "acc": {}, "test": {}, "dev": {}}}, f)
         for i in range(self.n_nodes):
-            node_cfg = {"api_key": self.api_keys[i], "server_url": "http://127.0.0.1", "port": self.port, "api_path": "/api",
+            node_cfg = {"api_key": self.api_keys[i], "server_url": self.server_url, "port": self.port, "api_path": "/api",
+                        **({"server_ca_file": self.cert_file} if self.tls else {}),
                         "task_dir": str(self.home / "tasks" / f"node-{i}"),
                         "databases": (dict(self.databases[i]) if isinstance(self.databases[i], dict)      # {label: uri}
                                       else {"default": self.databases[i] or f"synthetic://node-{i}"}),
@@ -116,7 +132,7 @@ class DemoNetwork:
     def save(self) -> Path:
         import json
 
-        doc = {k: getattr(self, k) for k in ("n_nodes", "name", "gpus", "databases", "encrypted", "rabbitmq", "port", "api_keys",
+        doc = {k: getattr(self, k) for k in ("n_nodes", "name", "gpus", "databases", "encrypted", "rabbitmq", "tls", "port", "api_keys",
                                              "org_names", "password", "key_bits")}
         self.description_file().write_text(json.dumps(doc, indent=1))
         return self.description_file()
@@ -128,7 +144,7 @@ class DemoNetwork:
         root = Path(home or os.environ.get(HOME_ENV) or Path.cwd() / ".v6b200")
         doc = json.loads((root / f"{name}-network.json").read_text())
         net = cls(doc["n_nodes"], home=str(root), name=doc["name"], gpus=doc["gpus"], databases=doc["databases"],
-                  encrypted=doc["encrypted"], rabbitmq=doc["rabbitmq"])
+                  encrypted=doc["encrypted"], rabbitmq=doc["rabbitmq"], tls=doc.get("tls", False))
         for k in ("port", "api_keys", "org_names", "password", "key_bits"):
             setattr(net, k, doc[k])
         net.fixtures_file = net.home / f"{net.name}-entities.yaml"
@@ -185,7 +201,7 @@ class DemoNetwork:
     def client(self, user: int = 0, timeout: float = 30.0):
         from .client import UserClient
 
-        c = UserClient("http://127.0.0.1", self.port, "/api")
+        c = UserClient(self.server_url, self.port, "/api", ca_file=self.cert_file if self.tls else None)
         t0 = time.time()
         while True:
             try:

@@ -66,7 +66,8 @@ class Node:
         self.ctx = ctx
         self.config = ctx.config
         self.heartbeat_s = heartbeat_s
-        self.client = NodeClient(self.config["server_url"], self.config.get("port"), self.config.get("api_path", "/api"))
+        self.client = NodeClient(self.config["server_url"], self.config.get("port"), self.config.get("api_path", "/api"),
+                                 ca_file=self.config.get("server_ca_file"))
         self.proxy = ProxyServer(self)
         self.queue: "queue.Queue[dict]" = queue.Queue()
         self.running: Dict[int, subprocess.Popen] = {}           # result id -> algorithm process
@@ -191,8 +192,9 @@ class Node:
         host = urlsplit(str(self.client.host)).hostname or "127.0.0.1"
         if since is None:
             since = self.client.request("health").get("events", 0)
-        url = f"ws://{host}:{port}/?token={self.client.token}&since={since}"
-        with connect(url, open_timeout=10, max_size=1 << 20) as ws:
+        secure = urlsplit(str(self.client.host)).scheme == "https"
+        url = f"{'wss' if secure else 'ws'}://{host}:{port}/?token={self.client.token}&since={since}"
+        with connect(url, open_timeout=10, max_size=1 << 20, ssl=self.client._http.ssl_context() if secure else None) as ws:
             log.info("event channel: websocket %s:%s", host, port)
             self.sync_open_results()            # close the race between the first sync and the subscription
             while not self._stop.is_set():

@@ -30,7 +30,8 @@ class ProxyServer:
         self.node = node
         self._httpd = None
         self.port = None
-        self._http = JsonHttp()
+        client_http = getattr(getattr(node, "client", None), "_http", None)
+        self._http = client_http if isinstance(client_http, JsonHttp) else JsonHttp()      # same connections, same CA file
 
     def start(self) -> int:
         proxy = self

@@ -1038,23 +1038,39 @@ class ServerApp:
             except Exception:  # noqa: BLE001
                 log.debug("reaper error", exc_info=True)
 
+    def tls_context(self):
+        """Server-side TLS from the ``ssl: {certfile, keyfile}`` block of the configuration (REST and the websocket event
+        channel alike); ``None`` = plain HTTP, e.g. behind a reverse proxy that terminates TLS, as vantage6 deployments do."""
+        cfg = self.config.get("ssl") or {}
+        if not cfg.get("certfile"):
+            return None
+        import ssl
+
+        ctx = ssl.SSLContext(ssl.PROTOCOL_TLS_SERVER)
+        ctx.minimum_version = ssl.TLSVersion.TLSv1_2
+        ctx.load_cert_chain(cfg["certfile"], cfg.get("keyfile"))
+        return ctx
+
     def start(self, ip: str = "127.0.0.1", port: int = 5000, block: bool = False) -> int:
         """Serve; returns the bound port (``port=0`` picks a free one)."""
         threading.Thread(target=lambda: (time.sleep(1.0), self._reaper_loop()), daemon=True).start()
         self._httpd = _ApiHTTPServer((ip, port), self.make_handler())
         bound = self._httpd.server_address[1]
+        tls = self.tls_context()
+        if tls is not None:     # handshake in the connection's own thread (first read), not in the accept loop
+            self._httpd.socket = tls.wrap_socket(self._httpd.socket, server_side=True, do_handshake_on_connect=False)
         if self.config.get("event_websocket", True):
             try:
                 from .ws_events import WebSocketEvents
 
                 ws_port = int(self.config.get("event_port") or 0)
-                self.ws = WebSocketEvents(self, ip, ws_port)
+                self.ws = WebSocketEvents(self, ip, ws_port, ssl_context=tls)
                 self.ws.start()
                 self.events.push = self.ws.publish
             except Exception as e:  # noqa: BLE001 -- no `websockets` package: long-poll only
                 log.warning("websocket event channel unavailable (%s): long-poll only", e)
                 self.ws = None
-        log.info("vantage6-b200 server %s listening on http://%s:%s%s", __version__, ip, bound, self.api_path)
+        log.info("vantage6-b200 server %s listening on %s://%s:%s%s", __version__, "https" if tls else "http", ip, bound, self.api_path)
         if block:
             try:
                 self._httpd.serve_forever(poll_interval=0.2)

@@ -23,8 +23,8 @@ log = logging.getLogger("server.ws")
 
 
 class WebSocketEvents:
-    def __init__(self, app, ip: str = "127.0.0.1", port: int = 0):
-        self.app, self.ip, self.port = app, ip, port
+    def __init__(self, app, ip: str = "127.0.0.1", port: int = 0, ssl_context=None):
+        self.app, self.ip, self.port, self.ssl_context = app, ip, port, ssl_context
         self.loop: Optional[asyncio.AbstractEventLoop] = None
         self._thread: Optional[threading.Thread] = None
         self._server = None
@@ -88,7 +88,8 @@ class WebSocketEvents:
             asyncio.set_event_loop(self.loop)
 
             async def boot():
-                self._server = await websockets.serve(self._handler, self.ip, self.port, ping_interval=20, max_size=1 << 20)
+                self._server = await websockets.serve(self._handler, self.ip, self.port, ping_interval=20, max_size=1 << 20,
+                                                      ssl=self.ssl_context)
                 self.port = self._server.sockets[0].getsockname()[1]
                 self._ready.set()
             self.loop.run_until_complete(boot())
