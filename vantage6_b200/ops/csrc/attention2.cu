@@ -47,7 +47,7 @@ V6_DEVINL uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_byte
     return d;
 }
 
-// VMN (opt-in, V6B200_ATTN_V=mn, not yet validated on hardware): V is read in its natural [B,S,Hkv,D] layout -- tiles
+// VMN (default; V6B200_ATTN_V=t = transposed copy; validated, BERT round 27.6 vs 28.3 ms): V is read in its natural [B,S,Hkv,D] layout -- tiles
 // of [128 keys x 64 d] loaded like K tiles and consumed by the PV MMA as an MN-major B operand -- instead of from a
 // pre-transposed Vt copy; `tmap_vt` is then a map over V ([B*S, Hkv*D], box 128 x 64).
 template <int D, bool CAUSAL, bool VMN>
