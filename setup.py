@@ -15,7 +15,8 @@ setup(
     description="Blackwell-native federated-learning engine with vantage6's capabilities",
     packages=find_packages(include=["vantage6_b200", "vantage6_b200.*"]),
     python_requires=">=3.10",
-    install_requires=["click", "pyyaml", "requests", "pyjwt", "cryptography", "numpy", "torch", "pyzmq"],
+    install_requires=["click", "pyyaml", "pyjwt", "cryptography", "numpy", "torch", "pyzmq"],
+    extras_require={"events": ["websockets"], "tabular": ["pandas"], "test": ["pytest", "requests", "hypothesis", "scipy", "scikit-learn"]},
     package_data={"vantage6_b200": ["__build__", "cli/rabbitmq/rabbitmq.config", "ops/csrc/*", "ops/*.so"]},
     entry_points={"console_scripts": [
         "vnode=vantage6_b200.cli.node:cli_node",
