@@ -711,3 +711,22 @@ def test_tls_for_rest_and_event_channel(tmp_path):
             assert ev["name"] == "new_task" and ev["data"]["task_id"] == task["id"] and "result" in ev["data"]
     finally:
         app.stop()
+
+
+def test_tls_client_survives_a_server_restart(tmp_path):
+    """A kept-alive TLS connection whose server went away is replaced on the next request (also for a POST)."""
+    certfile, keyfile = _self_signed(tmp_path)
+    cfg = {"uri": f"sqlite:///{tmp_path}/s.sqlite", "api_path": "/api", "jwt_secret_key": "s" * 40, "ssl": {"certfile": certfile, "keyfile": keyfile}}
+    app = ServerApp(cfg)
+    port = app.start("127.0.0.1", 0)
+    c = UserClient("https://127.0.0.1", port, "/api", ca_file=certfile)
+    c.authenticate("root", "root")
+    assert c._http.idle_connections() == 1
+    app.stop()
+    app2 = ServerApp(cfg)
+    app2.start("127.0.0.1", port)
+    try:
+        made = c.request("organization", method="post", json={"name": "after-restart"})          # POST on the stale connection
+        assert made["name"] == "after-restart" and c.util.get_server_health()["database"] is True
+    finally:
+        app2.stop()

@@ -15,13 +15,15 @@ import json as _json
 import os
 import select
 import socket
+import ssl
 import threading
 from typing import Any, Dict, Optional, Tuple
 from urllib.parse import urlencode, urlsplit
 
 _IDEMPOTENT = ("GET", "HEAD", "DELETE", "PUT")
 _STALE = (ConnectionResetError, BrokenPipeError, ConnectionAbortedError, http.client.RemoteDisconnected,
-          http.client.BadStatusLine, http.client.CannotSendRequest, http.client.ResponseNotReady)
+          http.client.BadStatusLine, http.client.CannotSendRequest, http.client.ResponseNotReady,
+          ssl.SSLEOFError, ssl.SSLZeroReturnError)          # a TLS peer that went away while the connection sat idle
 
 
 class Response:
@@ -55,8 +57,6 @@ class JsonHttp:
 
     def ssl_context(self):
         if self._ssl_context is None:
-            import ssl
-
             self._ssl_context = ssl.create_default_context(cafile=self.ca_file)
         return self._ssl_context
 

@@ -25,6 +25,7 @@ import json
 import logging
 import os
 import re
+import socket
 import threading
 import time
 import traceback
@@ -137,6 +138,8 @@ class ServerApp:
         self.started_at = time.time()
         self.token_expiry_s = int(config.get("token_expires_hours", 6) * 3600)
         self._routes: List[Tuple[str, re.Pattern, Callable]] = []
+        self._conns: set = set()                                       # open keep-alive connections (closed by stop())
+        self._conns_lock = threading.Lock()
         self._stats: Dict[Tuple[str, str, int], List[float]] = {}      # (method, route, status) -> [count, seconds]
         self._stats_lock = threading.Lock()
         self._httpd: Optional[ThreadingHTTPServer] = None
@@ -980,6 +983,16 @@ class ServerApp:
             def log_message(self, fmt, *args):
                 log.debug("%s - %s", self.address_string(), fmt % args)
 
+            def setup(self):
+                super().setup()
+                with app._conns_lock:
+                    app._conns.add(self.connection)
+
+            def finish(self):
+                with app._conns_lock:
+                    app._conns.discard(self.connection)
+                super().finish()
+
             def _serve(self, method):
                 parts = urlsplit(self.path)
                 length = int(self.headers.get("Content-Length") or 0)
@@ -1090,3 +1103,10 @@ class ServerApp:
             self._httpd.shutdown()
             self._httpd.server_close()
             self._httpd = None
+            with self._conns_lock:                 # kept-alive connections would otherwise be served on by their threads
+                conns = list(self._conns)
+            for conn in conns:
+                try:
+                    conn.shutdown(socket.SHUT_RDWR)
+                except OSError:
+                    pass
