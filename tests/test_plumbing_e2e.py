@@ -87,6 +87,18 @@ def test_column_average_on_csv(network, tmp_path):
     assert out == {"average": 30.0, "count": 5}
 
 
+def test_client_run_is_create_wait_decode(network):
+    c = network.client()
+    out = c.run("v6b200/weighted-mean", {"method": "master", "master": True})                 # defaults: my collaboration, my organization
+    assert out[0]["count"] == 100 and out[0]["n_nodes"] == 2
+    parts = c.run("v6b200/weighted-mean", {"method": "partial_sum"}, organizations=network.org_ids)
+    assert sorted(p["count"] for p in parts) == [30, 70]
+    with pytest.raises(RuntimeError) as e:                                                     # the node's log travels with the error
+        c.run("v6b200/weighted-mean", {"method": "no_such_method"})
+    assert "RPC_no_such_method" in str(e.value)
+    assert c.run("v6b200/weighted-mean", {"method": "no_such_method"}, raise_on_failure=False) == [None]
+
+
 def test_summary_on_a_labelled_csv_database(network):
     """Second database label per node (``patients``: CSV) + a two-round master through the real control plane."""
     import pandas as pd

@@ -201,6 +201,26 @@ class UserClient(ClientBase):
             r["result"] = self._decrypt_result(r.get("result"))
         return rows
 
+    def run(self, image: str, input: dict, collaboration: Optional[int] = None, organizations: Optional[List[int]] = None,  # noqa: A002
+            name: str = "task", database: str = "default", timeout: float = 600.0, raise_on_failure: bool = True) -> List[Any]:
+        """Create a task, wait for it and return the decoded results -- the three calls every script makes.  Defaults: the
+        only collaboration you are in, your own organization (where a ``master`` usually runs).  A result that came back
+        empty (failed algorithm, refused image) raises with the node's log unless ``raise_on_failure=False``."""
+        if collaboration is None:
+            mine = self.collaboration.list()
+            if len(mine) != 1:
+                raise ValueError(f"name the collaboration: you are in {len(mine)} of them")
+            collaboration = mine[0]["id"]
+        orgs = list(organizations) if organizations else [self.whoami.organization_id]
+        task = self.task.create(collaboration=collaboration, organizations=orgs, name=name, image=image, input=input, database=database)
+        rows = self.wait_for_results(task["id"], timeout=timeout)
+        failed = [r for r in rows if r.get("result") is None]
+        if failed and raise_on_failure:
+            r = failed[0]
+            raise RuntimeError(f"task {task['id']}: {len(failed)} of {len(rows)} results are empty (status {r.get('status')!r}, organization "
+                               f"{r['organization']['id']}); log of the first:\n{(r.get('log') or '')[-2000:]}")
+        return [r["result"] for r in rows]
+
     # ---------------------------------------------------------------- sub clients
     class SubClient:
         def __init__(self, parent: "UserClient"):
