@@ -730,3 +730,64 @@ def test_tls_client_survives_a_server_restart(tmp_path):
         assert made["name"] == "after-restart" and c.util.get_server_health()["database"] is True
     finally:
         app2.stop()
+
+
+def test_concurrent_researchers_and_nodes_keep_the_books_straight(tmp_path):
+    """Four researchers create tasks while four nodes start and finish the work items, all at once, against a file
+    database: no request fails, every result is started and finished exactly once, event ids are unique and ordered."""
+    app = ServerApp({"uri": f"sqlite:///{tmp_path}/s.sqlite", "api_path": "/api", "jwt_secret_key": "s" * 40})
+    entities = {"organizations": [{"name": f"O{i}", "users": [{"username": f"u{i}", "password": "pw", "roles": ["Researcher"]}]} for i in range(4)],
+                "collaborations": [{"name": "C", "participants": [{"name": f"O{i}", "api-key": f"k{i}"} for i in range(4)]}]}
+    fixtures.load(app.db, entities)
+    port = app.start("127.0.0.1", 0)
+    orgs = [o["id"] for o in app.db.query("SELECT id FROM organization WHERE name LIKE 'O%' ORDER BY id")]
+    cid = app.db.one("SELECT id FROM collaboration")["id"]
+    errors, created, done = [], [], []
+    per_researcher = 10
+
+    def researcher(i):
+        try:
+            c = user(port, f"u{i}", "pw")
+            for k in range(per_researcher):
+                t = c.task.create(collaboration=cid, organizations=orgs, name=f"t{i}-{k}", image="img", input={"k": k})
+                created.append(t["id"])
+                c.task.list()
+                c.result.list(task_id=t["id"])
+        except Exception as e:  # noqa: BLE001
+            errors.append(("researcher", i, repr(e)))
+
+    def node(i):
+        try:
+            n = NodeClient("http://127.0.0.1", port, "/api")
+            n.authenticate(f"k{i}")
+            seen, deadline = set(), time.time() + 60
+            while time.time() < deadline and len(seen) < 4 * per_researcher:
+                for r in n.request("result", params={"state": "open", "node_id": n.node_id}):
+                    if r["id"] in seen:
+                        continue
+                    seen.add(r["id"])
+                    assert n.request("token/container", method="post", json={"task_id": r["task"]["id"], "image": "img", "result_id": r["id"]})["started"]
+                    n.request(f"result/{r['id']}", method="patch", json={"finished_at": "now", "result": "x", "status": "completed"})
+                    done.append(r["id"])
+                time.sleep(0.01)
+        except Exception as e:  # noqa: BLE001
+            errors.append(("node", i, repr(e)))
+
+    threads = [threading.Thread(target=researcher, args=(i,)) for i in range(4)] + [threading.Thread(target=node, args=(i,)) for i in range(4)]
+    try:
+        [t.start() for t in threads]
+        [t.join(timeout=90) for t in threads]
+        assert not errors, errors[:3]
+        n_results = 4 * 4 * per_researcher
+        assert len(created) == 4 * per_researcher and sorted(done) == sorted(set(done)) and len(done) == n_results
+        books = app.db.one("SELECT COUNT(*) AS n, SUM(finished_at IS NOT NULL) AS f, SUM(started_at IS NOT NULL) AS s FROM result")
+        assert (books["n"], books["f"], books["s"]) == (n_results, n_results, n_results)
+        evs = app.events.wait(0, [f"collaboration_{cid}"], 0.0)
+        ids = [e["id"] for e in evs]
+        assert ids == sorted(set(ids))
+        names = [e["name"] for e in evs]
+        assert names.count("new_task") == n_results and names.count("status_update") == 2 * n_results          # started + finished
+        completing = {e["data"]["task_id"] for e in evs if e["name"] == "status_update" and e["data"].get("task_complete")}
+        assert completing == set(created)                  # every task announced complete (two racing finishers may both say so)
+    finally:
+        app.stop()
