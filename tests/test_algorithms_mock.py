@@ -411,3 +411,22 @@ def test_coxph_matches_pooled_partial_likelihood():
         coxph.RPC_event_sums(frames[0].head(4), "time", "event")
     sub = coxph.master(ClientMockProtocol(frames, coxph), frames[0], "time", "event", columns=["x1"], bin_width=0.25)
     assert sub["columns"] == ["x1"] and sub["coefficients"][0] > 0.3
+
+
+def test_correlation_matches_pooled_complete_cases():
+    import pandas as pd
+
+    from vantage6_b200.algorithm.builtin import correlation
+
+    rng = np.random.default_rng(21)
+    frames = [_patients(rng, 90), _patients(rng, 140, 4.0), _patients(rng, 60, -2.0)]
+    cols = ["age", "bmi", "time"]
+    out = correlation.master(ClientMockProtocol(frames, correlation), frames[0], columns=cols)
+    pooled = pd.concat(frames, ignore_index=True)[cols].dropna()
+    assert out["n"] == len(pooled) < 290                                   # bmi has missing values: complete cases only
+    np.testing.assert_allclose(out["mean"], pooled.mean().to_numpy(), rtol=1e-12)
+    np.testing.assert_allclose(out["covariance"], pooled.cov().to_numpy(), rtol=1e-9)
+    np.testing.assert_allclose(out["correlation"], pooled.corr().to_numpy(), rtol=1e-9)
+    assert np.allclose(np.diag(out["correlation"]), 1.0)
+    with pytest.raises(PermissionError):
+        correlation.RPC_moments(frames[0].head(6), cols)

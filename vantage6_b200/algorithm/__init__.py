@@ -15,6 +15,7 @@ IMAGES = {
     "v6-crosstab-py": "vantage6_b200.algorithm.builtin.crosstab",
     "v6b200/kaplan-meier": "vantage6_b200.algorithm.builtin.kaplan_meier",
     "v6-kaplan-meier-py": "vantage6_b200.algorithm.builtin.kaplan_meier",
+    "v6b200/correlation": "vantage6_b200.algorithm.builtin.correlation",
     "v6b200/coxph": "vantage6_b200.algorithm.builtin.coxph",
     "v6-coxph-py": "vantage6_b200.algorithm.builtin.coxph",
     # BASELINE config 1: weighted mean of a parameter vector
