@@ -791,3 +791,20 @@ def test_concurrent_researchers_and_nodes_keep_the_books_straight(tmp_path):
         assert completing == set(created)                  # every task announced complete (two racing finishers may both say so)
     finally:
         app.stop()
+
+
+def test_a_node_cannot_be_taken_from_another_collaboration(server):
+    """Attaching an attached node moves it: allowed only to someone who may edit BOTH collaborations."""
+    app, port = server
+    alice = user(port, "alice", "pw-a")
+    roles = {r["name"]: r["id"] for r in alice.role.list()}
+    other = alice.collaboration.create("BC", [2, 3])                                  # bob's organization is in AB and in BC
+    alice.user.create("cadmin", "pw", organization=3, roles=[roles["Collaboration Admin"]])      # organization 3: only in BC
+    cadmin = user(port, "cadmin", "pw")
+    b_node = next(n for n in alice.node.list() if n["organization"]["id"] == 2)       # B's node, attached to AB
+    with pytest.raises(ServerError) as e:
+        cadmin.collaboration.add_node(other["id"], b_node["id"])                       # may edit BC, not AB
+    assert e.value.status == 401
+    assert alice.node.get(b_node["id"])["collaboration"]["id"] == 1
+    moved = alice.collaboration.add_node(other["id"], b_node["id"])                    # global scope: fine
+    assert b_node["id"] in [n["id"] for n in moved]

@@ -304,6 +304,8 @@ def register(app) -> None:  # noqa: C901 -- a flat route table reads best in one
             raise HTTPError(404, f"node id={body.get('id')} not found")
         if n["collaboration_id"] == c["id"]:
             raise HTTPError(400, f"node id={n['id']} is already in collaboration id={cid}")
+        if n["collaboration_id"] is not None:          # moving a node takes it away from where it is: needs the say there too
+            require_collab_edit(ident, get_collab(n["collaboration_id"]))
         if n["organization_id"] not in db.collaboration_organizations(c["id"]):
             raise HTTPError(400, f"the node's organization id={n['organization_id']} is not part of collaboration id={cid}")
         if db.one("SELECT id FROM node WHERE organization_id=? AND collaboration_id=?", (n["organization_id"], c["id"])):
