@@ -808,3 +808,16 @@ def test_a_node_cannot_be_taken_from_another_collaboration(server):
     assert alice.node.get(b_node["id"])["collaboration"]["id"] == 1
     moved = alice.collaboration.add_node(other["id"], b_node["id"])                    # global scope: fine
     assert b_node["id"] in [n["id"] for n in moved]
+
+
+def test_a_node_may_only_publish_its_organizations_key(server):
+    app, port = server
+    node = NodeClient("http://127.0.0.1", port, "/api")
+    node.authenticate("key-a")
+    node.request("organization/1", method="patch", json={"public_key": "abc"})
+    assert app.db.get("organization", 1)["public_key"] == "abc"
+    with pytest.raises(ServerError) as e:
+        node.request("organization/1", method="patch", json={"name": "renamed", "public_key": "x"})
+    assert e.value.status == 401 and app.db.get("organization", 1)["name"] == "A" and app.db.get("organization", 1)["public_key"] == "abc"
+    with pytest.raises(ServerError):
+        node.request("organization/2", method="patch", json={"public_key": "x"})           # not its organization

@@ -525,7 +525,10 @@ class ServerApp:
                     raise HTTPError(401, "You do not have permission to edit this organization")
             elif ident["organization_id"] != o["id"]:
                 raise HTTPError(401, "A node can only edit its own organization")
-            fields = {k: body[k] for k in ("name", "domain", "address1", "address2", "zipcode", "country", "public_key") if k in body}
+            editable = ("public_key",) if ident["type"] == "node" else ("name", "domain", "address1", "address2", "zipcode", "country", "public_key")
+            fields = {k: body[k] for k in editable if k in body}       # a node publishes its organization's key, nothing else
+            if ident["type"] == "node" and set(body) - set(editable):
+                raise HTTPError(401, "A node may only update its organization's public key")
             db.update("organization", o["id"], **fields)
             return app.org_json(db.get("organization", o["id"]))
 
