@@ -821,3 +821,22 @@ def test_a_node_may_only_publish_its_organizations_key(server):
     assert e.value.status == 401 and app.db.get("organization", 1)["name"] == "A" and app.db.get("organization", 1)["public_key"] == "abc"
     with pytest.raises(ServerError):
         node.request("organization/2", method="patch", json={"public_key": "x"})           # not its organization
+
+
+def test_tokens_die_with_their_account(server):
+    app, port = server
+    alice = user(port, "alice", "pw-a")
+    eve = alice.user.create("eve", "pw-e", organization=2, roles=[r["id"] for r in alice.role.list() if r["name"] == "Researcher"])
+    eve_client = user(port, "eve", "pw-e")
+    assert eve_client.task.list() == []
+    alice.user.delete(eve["id"])
+    with pytest.raises(ServerError) as e:
+        eve_client.task.list()
+    assert e.value.status == 401 and "deleted" in e.value.msg
+    node = NodeClient("http://127.0.0.1", port, "/api")
+    node.authenticate("key-b")
+    node.request("result", params={"state": "open", "node_id": node.node_id})
+    alice.node.delete(node.node_id)
+    with pytest.raises(ServerError) as e:
+        node.request("result", params={"state": "open"})
+    assert e.value.status == 401

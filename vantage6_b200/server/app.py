@@ -223,6 +223,10 @@ class ServerApp:
             raise HTTPError(401, "Only access tokens are allowed")
         if kinds and ident["type"] not in kinds:
             raise HTTPError(403, f"Not allowed for identity type {ident['type']!r}")
+        # a token outlives nothing: the account (or the node / the task of a container token) must still be there
+        table, key = {"user": ("user", "id"), "node": ("node", "id"), "container": ("task", "task_id")}[ident["type"]]
+        if self.db.one(f"SELECT id FROM {table} WHERE id=?", (ident.get(key),)) is None:
+            raise HTTPError(401, f"This {ident['type']} token belongs to a deleted {table}")
         return ident
 
     def can_view_collaboration(self, ident: dict, collaboration_id: int, resource: str = "task") -> bool:
