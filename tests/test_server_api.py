@@ -840,3 +840,16 @@ def test_tokens_die_with_their_account(server):
     with pytest.raises(ServerError) as e:
         node.request("result", params={"state": "open"})
     assert e.value.status == 401
+
+
+def test_oversized_or_malformed_content_length_is_refused_unread(server):
+    import socket as _socket
+
+    app, port = server
+    for header, status in ((b"Content-Length: 999999999999", b"413"), (b"Content-Length: banana", b"400"), (b"Content-Length: -5", b"400")):
+        with _socket.create_connection(("127.0.0.1", port), timeout=5) as s:
+            s.sendall(b"POST /api/token/user HTTP/1.1\r\nHost: x\r\nContent-Type: application/json\r\n" + header + b"\r\n\r\n{}")
+            reply = s.recv(4096)
+            assert reply.startswith(b"HTTP/1.1 " + status) or reply.startswith(b"HTTP/1.0 " + status), reply[:80]
+            assert b"Connection: close" in reply
+    assert UserClient("http://127.0.0.1", port, "/api").util.get_server_version()["version"] == "3.1.0"      # the server is fine

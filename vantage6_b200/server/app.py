@@ -60,6 +60,9 @@ DEFAULT_ROLES = {
 }
 
 
+MAX_BODY_BYTES = 256 << 20          # task inputs / results are small; model tensors never travel on this API
+
+
 class PlainText(str):
     """A handler's reply that goes out as ``text/plain`` instead of JSON (``GET /metrics``)."""
 
@@ -1002,7 +1005,20 @@ class ServerApp:
 
             def _serve(self, method):
                 parts = urlsplit(self.path)
-                length = int(self.headers.get("Content-Length") or 0)
+                try:
+                    length = int(self.headers.get("Content-Length") or 0)
+                except ValueError:
+                    length = -1
+                if length < 0 or length > MAX_BODY_BYTES:      # refuse before reading: the framing of this connection is void
+                    self.close_connection = True
+                    data = json.dumps({"msg": f"request body must be 0..{MAX_BODY_BYTES} bytes with a valid Content-Length"}).encode("utf-8")
+                    self.send_response(413 if length > 0 else 400)
+                    self.send_header("Content-Type", "application/json")
+                    self.send_header("Content-Length", str(len(data)))
+                    self.send_header("Connection", "close")
+                    self.end_headers()
+                    self.wfile.write(data)
+                    return
                 raw = self.rfile.read(length) if length else b""
                 try:
                     body = json.loads(raw.decode("utf-8")) if raw else {}
