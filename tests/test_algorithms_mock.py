@@ -430,3 +430,27 @@ def test_correlation_matches_pooled_complete_cases():
     assert np.allclose(np.diag(out["correlation"]), 1.0)
     with pytest.raises(PermissionError):
         correlation.RPC_moments(frames[0].head(6), cols)
+
+
+def test_privacy_floors_belong_to_the_node(monkeypatch):
+    """``min_rows`` / ``min_count`` in a task input can tighten the node's floors, never loosen them."""
+    from vantage6_b200.algorithm.builtin import crosstab, summary
+    from vantage6_b200.algorithm.builtin._common import effective_min_count, effective_min_rows
+
+    rng = np.random.default_rng(5)
+    small = _patients(rng, 8)
+    with pytest.raises(PermissionError):
+        summary.RPC_summary_partial(small, columns=["age"], min_rows=1)          # the researcher asks for less: ignored
+    assert effective_min_rows(1) == 10 and effective_min_rows(50) == 50 and effective_min_count(0) == 5
+    monkeypatch.setenv("V6B200_MIN_ROWS", "5")                                     # the node's operator lowers the floor
+    monkeypatch.setenv("V6B200_MIN_COUNT", "2")
+    assert summary.RPC_summary_partial(small, columns=["age"], min_rows=1)["n_rows"] == 8
+    with pytest.raises(PermissionError):
+        summary.RPC_summary_partial(small, columns=["age"], min_rows=9)           # stricter than the floor: honoured
+    frame = _patients(rng, 30)
+    lax = crosstab.RPC_crosstab_partial(frame, "sex", "stage", min_count=0)
+    strict = crosstab.RPC_crosstab_partial(frame, "sex", "stage", min_count=8)
+    cells = lambda part: [n for row in part["table"].values() for n in row.values()]      # noqa: E731
+    assert all(n == 0 or n >= 2 for n in cells(lax)) and all(n == 0 or n >= 8 for n in cells(strict))
+    monkeypatch.setenv("V6B200_MIN_ROWS", "not-a-number")
+    assert effective_min_rows() == 10

@@ -4,7 +4,7 @@ covariance and correlation -- one round, (p + 1)(p + 2) / 2 numbers per node.  A
 cases refuses (the sums of a handful of rows say too much about them)."""
 import numpy as np
 
-from ._common import collect
+from ._common import collect, guard_rows
 
 MIN_ROWS = 10
 
@@ -26,6 +26,5 @@ def master(client, data, columns, organization_ids=None, min_rows: int = MIN_ROW
 
 def RPC_moments(data, columns, min_rows: int = MIN_ROWS):
     x = data[list(columns)].dropna().to_numpy(dtype=np.float64)
-    if x.shape[0] < min_rows:
-        raise PermissionError(f"this node holds fewer than {min_rows} complete rows: refusing to report moments")
+    guard_rows(x.shape[0], min_rows, "report moments (complete cases)")
     return {"n": int(x.shape[0]), "sum": x.sum(axis=0), "cross": x.T @ x}

@@ -11,7 +11,7 @@ pooled analysis would, and takes the Newton step.  What leaves a node are sums o
 """
 import numpy as np
 
-from ._common import collect
+from ._common import collect, guard_rows
 
 MIN_ROWS = 10
 
@@ -68,8 +68,7 @@ def master(client, data, time_column: str, censor_column: str, columns=None, org
 
 
 def RPC_event_sums(data, time_column: str, censor_column: str, columns=None, bin_width: float = 0.0, min_rows: int = MIN_ROWS):
-    if len(data) < min_rows:
-        raise PermissionError(f"this node holds fewer than {min_rows} rows: refusing to take part")
+    guard_rows(len(data), min_rows, "take part")
     X, t, ev, cols = _frame(data, time_column, censor_column, columns)
     t = _binned(t, bin_width)
     times = sorted(set(t[ev].tolist()))
@@ -78,8 +77,7 @@ def RPC_event_sums(data, time_column: str, censor_column: str, columns=None, bin
 
 
 def RPC_risk_sums(data, time_column: str, censor_column: str, grid, beta, columns=None, bin_width: float = 0.0, min_rows: int = MIN_ROWS):
-    if len(data) < min_rows:
-        raise PermissionError(f"this node holds fewer than {min_rows} rows: refusing to take part")
+    guard_rows(len(data), min_rows, "take part")
     X, t, _, _ = _frame(data, time_column, censor_column, columns)
     t = _binned(t, bin_width)
     r = np.exp(X @ np.asarray(beta, dtype=np.float64))

@@ -4,7 +4,7 @@ every node's data, with the chi-square statistic of independence computed by the
 One round; a node reports its local table with cells below ``min_count`` (default 5) zeroed and flagged, and nothing at
 all when it holds fewer than ``min_rows`` rows.
 """
-from ._common import collect
+from ._common import collect, effective_min_count, guard_rows
 
 MIN_ROWS, MIN_COUNT = 10, 5
 
@@ -33,8 +33,8 @@ def master(client, data, row: str, column: str, organization_ids=None, min_rows:
 
 
 def RPC_crosstab_partial(data, row: str, column: str, min_rows: int = MIN_ROWS, min_count: int = MIN_COUNT):
-    if len(data) < min_rows:
-        raise PermissionError(f"this node holds fewer than {min_rows} rows: refusing to report counts")
+    guard_rows(len(data), min_rows, "report counts")
+    min_count = effective_min_count(min_count)
     sub = data[[row, column]].dropna().astype(str)
     counts = sub.groupby([row, column]).size()
     table, suppressed = {}, False

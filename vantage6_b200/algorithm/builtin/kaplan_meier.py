@@ -9,7 +9,7 @@ import math
 
 import numpy as np
 
-from ._common import collect
+from ._common import collect, guard_rows
 
 MIN_ROWS = 10
 
@@ -44,16 +44,14 @@ def master(client, data, time_column: str, censor_column: str, organization_ids=
 
 
 def RPC_event_times(data, time_column: str, censor_column: str, bin_width: float = 0.0, min_rows: int = MIN_ROWS):
-    if len(data) < min_rows:
-        raise PermissionError(f"this node holds fewer than {min_rows} rows: refusing to report event times")
+    guard_rows(len(data), min_rows, "report event times")
     t = _times(data, time_column, bin_width)
     ev = np.asarray(data[censor_column]).astype(bool)
     return {"times": sorted(set(t[ev].tolist()))}
 
 
 def RPC_risk_table(data, time_column: str, censor_column: str, grid, bin_width: float = 0.0, min_rows: int = MIN_ROWS):
-    if len(data) < min_rows:
-        raise PermissionError(f"this node holds fewer than {min_rows} rows: refusing to report a risk table")
+    guard_rows(len(data), min_rows, "report a risk table")
     t = _times(data, time_column, bin_width)
     ev = np.asarray(data[censor_column]).astype(bool)
     g = np.asarray(grid, dtype=np.float64)

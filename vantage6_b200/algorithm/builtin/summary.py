@@ -12,7 +12,7 @@ import math
 
 import numpy as np
 
-from ._common import collect
+from ._common import collect, effective_min_count, guard_rows
 
 MIN_ROWS, MIN_COUNT = 10, 5
 
@@ -91,8 +91,7 @@ def _quantile(counts, lo: float, hi: float, q: float) -> float:
 
 
 def RPC_histogram_partial(data, ranges: dict, bins: int = 512, min_rows: int = MIN_ROWS):
-    if len(data) < min_rows:
-        raise PermissionError(f"this node holds fewer than {min_rows} rows: refusing to report statistics")
+    guard_rows(len(data), min_rows, "report statistics")
     out = {}
     for c, (lo, hi) in ranges.items():
         v = data[c].dropna().to_numpy(dtype=float)
@@ -105,8 +104,8 @@ def RPC_histogram_partial(data, ranges: dict, bins: int = 512, min_rows: int = M
 
 
 def RPC_summary_partial(data, columns=None, min_rows: int = MIN_ROWS, min_count: int = MIN_COUNT):
-    if len(data) < min_rows:
-        raise PermissionError(f"this node holds fewer than {min_rows} rows: refusing to report statistics")
+    guard_rows(len(data), min_rows, "report statistics")
+    min_count = effective_min_count(min_count)
     numeric, categorical = {}, {}
     for c in _columns(data, columns):
         s = data[c]
@@ -122,6 +121,5 @@ def RPC_summary_partial(data, columns=None, min_rows: int = MIN_ROWS, min_count:
 
 
 def RPC_deviation_partial(data, means: dict, min_rows: int = MIN_ROWS):
-    if len(data) < min_rows:
-        raise PermissionError(f"this node holds fewer than {min_rows} rows: refusing to report statistics")
+    guard_rows(len(data), min_rows, "report statistics")
     return {c: float(((data[c].dropna() - m) ** 2).sum()) for c, m in means.items() if c in data.columns}

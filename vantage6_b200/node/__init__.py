@@ -331,6 +331,10 @@ class Node:
                 "DATABASE_LABEL": label, "V6_ORGANIZATION_ID": str(self.client.organization_id),
                 "V6_NODE_ID": str(self.client.node_id), "V6_COLLABORATION_ID": str(self.client.collaboration_id),
             })
+            privacy = self.config.get("privacy") or {}             # the data station's floors for the tabular algorithms
+            for key, var in (("min_rows", "V6B200_MIN_ROWS"), ("min_count", "V6B200_MIN_COUNT")):
+                if privacy.get(key) is not None:
+                    env[var] = str(int(privacy[key]))
             if uri is not None:
                 env["DATABASE_URI"] = str(uri)
                 env[f"{label.upper()}_DATABASE_URI"] = str(uri)
