@@ -18,7 +18,7 @@ from typing import Any, Dict, Optional
 
 import numpy as np
 
-from ._common import collect
+from ._common import collect, guard_rows
 from .fedavg import _free_port
 
 
@@ -52,6 +52,7 @@ def master(client, data, iterations: int = 10, lr: float = 1.0, organization_ids
 
 def RPC_gradient(data, w=None) -> Dict[str, Any]:
     X, y = _xy(data)
+    guard_rows(X.shape[0], None, "report a gradient")          # the gradient of a handful of rows gives them away
     wv = np.zeros(X.shape[1] + 1) if w is None else np.asarray(w, dtype=np.float64)
     z = X @ wv[:-1] + wv[-1]
     p = 1.0 / (1.0 + np.exp(-z))
@@ -124,6 +125,7 @@ def master_irls(client, data, family: str = "binomial", columns=None, outcome=No
 
 def RPC_irls_partial(data, family: str = "binomial", columns=None, outcome=None, beta=None) -> Dict[str, Any]:
     X, y = _design(data, columns, outcome)
+    guard_rows(X.shape[0], None, "report normal equations")
     if beta is None:                                   # start from the family's usual initial mean
         if family == "gaussian":
             eta = y
